@@ -1,0 +1,67 @@
+// capi.cu -- the C ABI declared in include/arriba_b200.h: thin exception-to-status shims over arb::engine.
+#include "engine.h"
+#include <new>
+
+using namespace arb;
+
+struct arb_ctx { engine e; };
+static std::string g_create_error;
+
+#define ARB_API_BEGIN(ctx) if (!(ctx)) return 2; try {
+#define ARB_API_END(ctx) } catch (const std::exception& x) { (ctx)->e.last_error = x.what(); return 1; } catch (...) { (ctx)->e.last_error = "unknown error"; return 1; } return 0;
+
+extern "C" {
+
+const char* arb_backend(void) {
+#ifdef ARB_DEVICE_BUILD
+	return "cuda-sm_100a";
+#else
+	return "hostsim-TEST-ONLY";
+#endif
+}
+
+uint64_t arb_kernel_launches(void) { return stats().kernels; }
+
+int arb_ctx_create(arb_ctx** out, int device) {
+	if (!out) return 2;
+	*out = NULL;
+	try {
+#ifdef ARB_DEVICE_BUILD
+		int count = 0;
+		cudaError_t e = cudaGetDeviceCount(&count);
+		if (e != cudaSuccess || count == 0) throw arb_error(std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); arriba-b200 has no CPU fallback");
+		if (device < 0 || device >= count) throw arb_error("device index out of range");
+		ARB_CUDA_CHECK(cudaSetDevice(device));
+		cudaDeviceProp prop;
+		ARB_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+		if (prop.major < 10) throw arb_error(std::string("device '") + prop.name + "' is not sm_100-class; this build targets sm_100a only");
+#else
+		(void) device;
+#endif
+		*out = new arb_ctx();
+	} catch (const std::exception& x) { g_create_error = x.what(); return 1; }
+	return 0;
+}
+
+void arb_ctx_destroy(arb_ctx* ctx) { delete ctx; }
+const char* arb_last_error(arb_ctx* ctx) { return ctx ? ctx->e.last_error.c_str() : g_create_error.c_str(); }
+
+void arb_default_params(arb_params* p) { if (p) default_params(*p); }
+int arb_set_params(arb_ctx* ctx, const arb_params* p) { ARB_API_BEGIN(ctx) ctx->e.set_params(*p); ARB_API_END(ctx) }
+int arb_set_contigs(arb_ctx* ctx, const arb_contigs* c) { ARB_API_BEGIN(ctx) ctx->e.set_contigs(*c); ARB_API_END(ctx) }
+int arb_set_annotation(arb_ctx* ctx, const arb_annotation* a) { ARB_API_BEGIN(ctx) ctx->e.set_annotation(*a); ARB_API_END(ctx) }
+int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk(*c); ARB_API_END(ctx) }
+int arb_run_read_filters(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.run_read_filters(); ARB_API_END(ctx) }
+int arb_get_fragment_filters(arb_ctx* ctx, uint8_t* f, uint8_t* early) { ARB_API_BEGIN(ctx) ctx->e.get_fragment_filters(f, early); ARB_API_END(ctx) }
+int arb_set_fragment_filters(arb_ctx* ctx, const uint8_t* f) { ARB_API_BEGIN(ctx) ctx->e.set_fragment_filters(f); ARB_API_END(ctx) }
+int arb_get_filter_counts(arb_ctx* ctx, uint32_t counts[ARB_N_FILTERS]) { ARB_API_BEGIN(ctx) ctx->e.get_filter_counts(counts); ARB_API_END(ctx) }
+int arb_find_fusions(arb_ctx* ctx, int32_t max_mate_gap) { ARB_API_BEGIN(ctx) ctx->e.find_fusions(max_mate_gap); ARB_API_END(ctx) }
+int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n1, uint64_t* n2, uint64_t* nd) {
+	ARB_API_BEGIN(ctx)
+	if (n) *n = ctx->e.cands.n; if (n1) *n1 = ctx->e.cands.n_list1; if (n2) *n2 = ctx->e.cands.n_list2; if (nd) *nd = ctx->e.cands.n_listd;
+	ARB_API_END(ctx)
+}
+int arb_get_candidates(arb_ctx* ctx, arb_candidates* out) { ARB_API_BEGIN(ctx) ctx->e.get_candidates(*out); ARB_API_END(ctx) }
+int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.get_slot_swaps(out); ARB_API_END(ctx) }
+
+} // extern "C"

@@ -1,0 +1,93 @@
+// engine.h -- device-resident state of one arriba-b200 context and the stage drivers.
+#pragma once
+#include "model.h"
+#include "prims.h"
+#include "read_filters.h"
+#include "../../include/arriba_b200.h"
+#include <vector>
+#include <string>
+
+namespace arb {
+
+struct frag_store {
+	u32 n; u32 max_seq_len;
+	dbuf<u8> n_aln, fflags, filter, early, aflags, seq, swapped;
+	dbuf<u16> contig, cigar_cnt, seq_len, genes_cnt;
+	dbuf<i32> start, end;
+	dbuf<u32> cigar_off, seq_off, genes_off, cigar, genes;
+	frag_store(): n(0), max_seq_len(0) {}
+	frag_view view() const {
+		frag_view v;
+		v.n = n; v.n_aln = n_aln.ptr(); v.fflags = fflags.ptr(); v.filter = filter.ptr();
+		v.contig = contig.ptr(); v.start = start.ptr(); v.end = end.ptr(); v.aflags = aflags.ptr();
+		v.cigar_off = cigar_off.ptr(); v.cigar_cnt = cigar_cnt.ptr(); v.seq_off = seq_off.ptr(); v.seq_len = seq_len.ptr();
+		v.genes_off = genes_off.ptr(); v.genes_cnt = genes_cnt.ptr(); v.cigar = cigar.ptr(); v.seq = seq.ptr(); v.genes = genes.ptr();
+		return v;
+	}
+};
+
+struct annot_store {
+	u32 n_genes, n_exons, n_contigs;
+	dbuf<u16> gene_contig; dbuf<i32> gene_start, gene_end, gene_exonic_length; dbuf<u8> gene_strand, gene_flags;
+	dbuf<u32> exon_gene; dbuf<i32> exon_start, exon_end, exon_cds_start, exon_cds_end, exon_next_start; dbuf<u8> exon_flags;
+	dbuf<u32> exon_region_begin, exon_region_off, exon_region_items, gene_region_begin, gene_region_off, gene_region_items;
+	dbuf<i32> exon_region_end, gene_region_end;
+	dbuf<u8> contig_flags; dbuf<u64> contig_seq_off; dbuf<u32> contig_len; dbuf<char> assembly;
+	std::vector<u8> h_contig_flags; std::vector<u32> h_contig_len;
+	// host mirrors needed by host-side steps
+	std::vector<u16> h_gene_contig; std::vector<i32> h_gene_start, h_gene_end; std::vector<u8> h_gene_strand, h_gene_flags;
+	annot_store(): n_genes(0), n_exons(0), n_contigs(0) {}
+	annot_view view() const {
+		annot_view v;
+		v.n_genes = n_genes; v.gene_contig = gene_contig.ptr(); v.gene_start = gene_start.ptr(); v.gene_end = gene_end.ptr();
+		v.gene_strand = gene_strand.ptr(); v.gene_exonic_length = gene_exonic_length.ptr(); v.gene_flags = gene_flags.ptr();
+		v.n_exons = n_exons; v.exon_gene = exon_gene.ptr(); v.exon_start = exon_start.ptr(); v.exon_end = exon_end.ptr();
+		v.exon_cds_start = exon_cds_start.ptr(); v.exon_cds_end = exon_cds_end.ptr(); v.exon_next_start = exon_next_start.ptr(); v.exon_flags = exon_flags.ptr();
+		v.n_contigs = n_contigs;
+		v.exon_region_begin = exon_region_begin.ptr(); v.exon_region_end = exon_region_end.ptr(); v.exon_region_off = exon_region_off.ptr(); v.exon_region_items = exon_region_items.ptr();
+		v.gene_region_begin = gene_region_begin.ptr(); v.gene_region_end = gene_region_end.ptr(); v.gene_region_off = gene_region_off.ptr(); v.gene_region_items = gene_region_items.ptr();
+		v.contig_flags = contig_flags.ptr(); v.contig_seq_off = contig_seq_off.ptr(); v.contig_len = contig_len.ptr(); v.assembly = assembly.ptr();
+		return v;
+	}
+};
+
+struct cand_store {
+	u32 n; u64 n_list1, n_list2, n_listd;
+	dbuf<u32> gene1, gene2, split_reads1, split_reads2, discordant_mates, list1_off, list2_off, listd_off, list1, list2, listd;
+	dbuf<u16> contig1, contig2; dbuf<i32> bp1, bp2, anchor1, anchor2; dbuf<u8> dir1, dir2, filter, bits, bits2; dbuf<float> evalue;
+	cand_store(): n(0), n_list1(0), n_list2(0), n_listd(0) {}
+};
+
+class engine {
+public:
+	exec_ctx ex;
+	std::string last_error;
+	arb_params params;
+	frag_store frags;
+	annot_store annot;
+	cand_store cands;
+	dbuf<u8> mismatch_table; u32 table_n, table_k;
+	hash_index table;
+	dbuf<u32> label_counts;
+	bool has_contigs, has_annotation, filters_done;
+
+	engine();
+	void set_contigs(const arb_contigs& c);
+	void set_annotation(const arb_annotation& a);
+	void set_params(const arb_params& p) { params = p; }
+	void push_chunk(const arb_soa_chunk& c);
+	void run_read_filters();
+	void get_fragment_filters(u8* filter_out, u8* early_out);
+	void set_fragment_filters(const u8* filter);
+	void get_filter_counts(u32* counts);
+	void find_fusions(i32 max_mate_gap);
+	void get_candidates(arb_candidates& out);
+	void get_slot_swaps(u8* out);
+private:
+	read_filter_params make_filter_params();
+	unsigned long genome_size() const;
+};
+
+void default_params(arb_params& p);
+
+} // namespace arb

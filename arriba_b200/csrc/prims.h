@@ -1,0 +1,217 @@
+// prims.h -- data-parallel primitives used by every stage: device buffers, for_each, exclusive scan,
+// stable LSD radix sort of (key,value) pairs, and an exact "group by key, smallest index wins" hash index.
+//
+// Two builds of the SAME interface:
+//   * product (nvcc, sm_100a): hand-written CUDA kernels below (#ifdef ARB_DEVICE_BUILD). No CUB/Thrust.
+//   * tests/hostsim (g++ -DARB_HOSTSIM): sequential stand-ins, used only by the CPU test-suite to check the
+//     per-element rules against the oracle. The product library is never built this way.
+#pragma once
+#include "hd.h"
+#include <stdlib.h>
+#include <string.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#ifdef ARB_DEVICE_BUILD
+#include <cuda_runtime.h>
+#endif
+
+namespace arb {
+
+struct arb_error: public std::runtime_error { explicit arb_error(const std::string& m): std::runtime_error(m) {} };
+
+#ifdef ARB_DEVICE_BUILD
+#define ARB_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) throw arb::arb_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); } while (0)
+#endif
+
+// launch statistics (bench.py reports gpu_launches from here)
+struct launch_stats { u64 kernels; };
+inline launch_stats& stats() { static launch_stats s = {0}; return s; }
+
+struct exec_ctx {
+#ifdef ARB_DEVICE_BUILD
+	cudaStream_t stream;
+	exec_ctx(): stream(0) {}
+	void sync() const { ARB_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+#else
+	void sync() const {}
+#endif
+};
+
+// ------------------------------------------------------------------------------------------- device buffer
+template <class T> class dbuf {
+	T* p_; size_t n_;
+	dbuf(const dbuf&); dbuf& operator=(const dbuf&);
+public:
+	dbuf(): p_(NULL), n_(0) {}
+	explicit dbuf(size_t n): p_(NULL), n_(0) { alloc(n); }
+	~dbuf() { release(); }
+	void release() {
+		if (!p_) return;
+#ifdef ARB_DEVICE_BUILD
+		cudaFree(p_);
+#else
+		free(p_);
+#endif
+		p_ = NULL; n_ = 0;
+	}
+	void alloc(size_t n) {
+		release();
+		n_ = n;
+		size_t bytes = (n ? n : 1) * sizeof(T) + 64; // slack for vectorised tail reads
+#ifdef ARB_DEVICE_BUILD
+		ARB_CUDA_CHECK(cudaMalloc((void**) &p_, bytes));
+#else
+		p_ = (T*) malloc(bytes);
+		if (!p_) throw arb_error("out of memory");
+#endif
+	}
+	void ensure(size_t n) { if (n > n_) alloc(n + n / 4); }
+	T* ptr() const { return p_; }
+	size_t size() const { return n_; }
+	void zero(const exec_ctx& ex, size_t n) { fill_bytes(ex, 0, n); }
+	void fill_bytes(const exec_ctx& ex, int byte, size_t n) {
+		(void) ex;
+#ifdef ARB_DEVICE_BUILD
+		ARB_CUDA_CHECK(cudaMemsetAsync(p_, byte, n * sizeof(T), ex.stream));
+#else
+		memset(p_, byte, n * sizeof(T));
+#endif
+	}
+	void upload(const exec_ctx& ex, const T* host, size_t n) {
+		(void) ex;
+		ensure(n);
+		if (!n) return;
+#ifdef ARB_DEVICE_BUILD
+		ARB_CUDA_CHECK(cudaMemcpyAsync(p_, host, n * sizeof(T), cudaMemcpyHostToDevice, ex.stream));
+#else
+		memcpy(p_, host, n * sizeof(T));
+#endif
+	}
+	void download(const exec_ctx& ex, T* host, size_t n, size_t offset = 0) const {
+		(void) ex;
+		if (!n) return;
+#ifdef ARB_DEVICE_BUILD
+		ARB_CUDA_CHECK(cudaMemcpyAsync(host, p_ + offset, n * sizeof(T), cudaMemcpyDeviceToHost, ex.stream));
+		ARB_CUDA_CHECK(cudaStreamSynchronize(ex.stream));
+#else
+		memcpy(host, p_ + offset, n * sizeof(T));
+#endif
+	}
+	std::vector<T> to_host(const exec_ctx& ex, size_t n) const { std::vector<T> v(n); download(ex, v.data(), n); return v; }
+};
+
+// ------------------------------------------------------------------------------------------- for_each
+#ifdef ARB_DEVICE_BUILD
+template <class F> __global__ void __launch_bounds__(256) k_for_each(u32 n, F f) {
+	u32 i = blockIdx.x * 256u + threadIdx.x;
+	if (i < n) f(i);
+}
+template <class F> void for_each(const exec_ctx& ex, u32 n, const F& f) {
+	if (n == 0) return;
+	k_for_each<F><<<(n + 255) / 256, 256, 0, ex.stream>>>(n, f);
+	ARB_CUDA_CHECK(cudaGetLastError());
+	++stats().kernels;
+}
+#else
+template <class F> void for_each(const exec_ctx&, u32 n, const F& f) { for (u32 i = 0; i < n; ++i) f(i); ++stats().kernels; }
+#endif
+
+// ------------------------------------------------------------------------------------------- atomics usable from HD functors
+ARB_HD u32 atomic_cas_u32(u32* p, u32 expected, u32 desired) {
+#ifdef __CUDA_ARCH__
+	return atomicCAS(p, expected, desired);
+#else
+	u32 old = *p; if (old == expected) *p = desired; return old;
+#endif
+}
+ARB_HD u32 atomic_min_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+	return atomicMin(p, v);
+#else
+	u32 old = *p; if (v < old) *p = v; return old;
+#endif
+}
+ARB_HD u32 atomic_add_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+	return atomicAdd(p, v);
+#else
+	u32 old = *p; *p = old + v; return old;
+#endif
+}
+ARB_HD u32 atomic_or_u32(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+	return atomicOr(p, v);
+#else
+	u32 old = *p; *p = old | v; return old;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------- exclusive scan (u32)
+// out[i] = sum(in[0..i)), returns nothing; total is written to out[n] (out must hold n+1 elements). in may alias out.
+void exclusive_scan_u32(const exec_ctx& ex, const u32* in, u32* out, u32 n);
+
+// ------------------------------------------------------------------------------------------- stable radix sort of pairs
+// Sorts (keys, vals) ascending by the low `bits` bits of the 32-bit key; stable. Uses (keys_tmp, vals_tmp) as ping-pong
+// space; on return the sorted data is in keys/vals.
+void radix_sort_pairs_u32(const exec_ctx& ex, u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, u32 n, u32 bits);
+
+// ------------------------------------------------------------------------------------------- exact group-by with smallest-index representative
+// hash_index: open-addressing table over item indices. Each slot holds a representative item (`rep`, claimed by CAS)
+// and the smallest item index with an equal key (`mn`). Keys are compared in full through KeyOps, so grouping is exact.
+//   KeyOps requirements:  u64 hash(u32 item) const;  bool equal(u32 item_a, u32 item_b) const;
+struct hash_index_view {
+	u32* rep; u32* mn; u32 mask;
+	static const u32 EMPTY = 0xFFFFFFFFu;
+	template <class K> ARB_HD u32 insert(const K& k, u32 item) const { // returns slot
+		u32 h = (u32) k.hash(item) & mask;
+		for (;;) {
+			u32 r = atomic_cas_u32(&rep[h], EMPTY, item);
+			if (r == EMPTY || r == item || k.equal(r, item)) { atomic_min_u32(&mn[h], item); return h; }
+			h = (h + 1) & mask;
+		}
+	}
+	// lookup by an external probe object: P must provide  u64 hash() const;  bool equal_item(u32 item) const;
+	template <class P> ARB_HD u32 find(const P& probe) const { // returns slot or EMPTY
+		u32 h = (u32) probe.hash() & mask;
+		for (;;) {
+			u32 r = rep[h];
+			if (r == EMPTY) return EMPTY;
+			if (probe.equal_item(r)) return h;
+			h = (h + 1) & mask;
+		}
+	}
+};
+
+struct hash_index {
+	dbuf<u32> rep, mn; u32 cap;
+	hash_index(): cap(0) {}
+	hash_index_view view() const { hash_index_view v = {rep.ptr(), mn.ptr(), cap - 1}; return v; }
+	void reset(const exec_ctx& ex, u32 n_items) {
+		u32 c = 1024; while (c < 2 * (u64) n_items + 16) c <<= 1;
+		cap = c;
+		rep.ensure(c); mn.ensure(c);
+		rep.fill_bytes(ex, 0xFF, c); mn.fill_bytes(ex, 0xFF, c);
+	}
+};
+
+template <class K> struct group_insert_fn {
+	hash_index_view t; K k; u32* slot_of; const u8* participate;
+	ARB_HD void operator()(u32 i) const { slot_of[i] = (participate == NULL || participate[i]) ? t.insert(k, i) : hash_index_view::EMPTY; }
+};
+struct group_first_fn {
+	hash_index_view t; const u32* slot_of; u32* first;
+	ARB_HD void operator()(u32 i) const { first[i] = slot_of[i] == hash_index_view::EMPTY ? i : t.mn[slot_of[i]]; }
+};
+// first[i] = smallest j with key(j) == key(i) among participating items (first[i] = i for non-participants)
+template <class K> void group_min_index(const exec_ctx& ex, hash_index& table, u32 n, const K& k, const u8* participate, u32* slot_scratch, u32* first) {
+	table.reset(ex, n);
+	group_insert_fn<K> ins = {table.view(), k, slot_scratch, participate};
+	for_each(ex, n, ins);
+	group_first_fn fin = {table.view(), slot_scratch, first};
+	for_each(ex, n, fin);
+}
+
+} // namespace arb

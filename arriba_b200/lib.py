@@ -1,0 +1,225 @@
+"""ctypes binding of the C ABI in include/arriba_b200.h.
+
+`load()` opens the CUDA product library (arriba_b200/libarriba_b200.so) and nothing else; it raises if the
+library is missing. The CPU test-suite passes the path of tests/hostsim explicitly (`load(path)`)."""
+import ctypes as C
+import os
+import numpy as np
+
+from . import _build
+
+N_FILTERS = 38
+FILTER_NAMES = ["", "duplicates", "inconsistently_clipped", "homopolymer", "read_through", "same_gene", "small_insert_size", "long_gap",
+                "hairpin", "multimappers", "mismatches", "mismappers", "relative_support", "intronic", "non_coding_neighbors",
+                "intragenic_exonic", "internal_tandem_duplication", "min_support", "known_fusions", "spliced", "blacklist", "end_to_end",
+                "in_vitro", "merge_adjacent", "select_best", "marginal_read_through", "short_anchor", "no_coverage", "many_spliced",
+                "no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs",
+                "genomic_support", "isoforms", "low_entropy", "homologs"]
+
+_p = C.POINTER
+
+
+class Contigs(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("flags", _p(C.c_uint8)), ("length", _p(C.c_uint32)), ("sequence", _p(C.c_char_p))]
+
+
+class Annotation(C.Structure):
+    _fields_ = [("n_genes", C.c_uint32), ("gene_contig", _p(C.c_uint16)), ("gene_start", _p(C.c_int32)), ("gene_end", _p(C.c_int32)),
+                ("gene_strand", _p(C.c_uint8)), ("gene_exonic_length", _p(C.c_int32)), ("gene_flags", _p(C.c_uint8)),
+                ("n_exons", C.c_uint32), ("exon_gene", _p(C.c_uint32)), ("exon_start", _p(C.c_int32)), ("exon_end", _p(C.c_int32)),
+                ("exon_cds_start", _p(C.c_int32)), ("exon_cds_end", _p(C.c_int32)), ("exon_next_start", _p(C.c_int32)), ("exon_flags", _p(C.c_uint8)),
+                ("n_contigs", C.c_uint32),
+                ("exon_region_begin", _p(C.c_uint32)), ("exon_region_end", _p(C.c_int32)), ("exon_region_off", _p(C.c_uint32)), ("exon_region_items", _p(C.c_uint32)),
+                ("gene_region_begin", _p(C.c_uint32)), ("gene_region_end", _p(C.c_int32)), ("gene_region_off", _p(C.c_uint32)), ("gene_region_items", _p(C.c_uint32))]
+
+
+class Params(C.Structure):
+    _fields_ = [("filter_mask", C.c_uint64), ("homopolymer_length", C.c_uint32), ("min_read_through_distance", C.c_int32),
+                ("max_kmer_content", C.c_float), ("max_itd_length", C.c_uint32), ("external_duplicate_marking", C.c_uint32),
+                ("mismatch_pvalue_cutoff", C.c_float), ("subsampling_threshold", C.c_uint32), ("evalue_cutoff", C.c_float),
+                ("max_mismapper_fraction", C.c_float), ("max_homolog_identity", C.c_float)]
+
+
+class SoaChunk(C.Structure):
+    _fields_ = [("n_fragments", C.c_uint32), ("n_aln", _p(C.c_uint8)), ("fflags", _p(C.c_uint8)), ("filter", _p(C.c_uint8)),
+                ("contig", _p(C.c_uint16)), ("start", _p(C.c_int32)), ("end", _p(C.c_int32)), ("aflags", _p(C.c_uint8)),
+                ("cigar_off", _p(C.c_uint32)), ("cigar_cnt", _p(C.c_uint16)), ("seq_off", _p(C.c_uint32)), ("seq_len", _p(C.c_uint16)),
+                ("genes_off", _p(C.c_uint32)), ("genes_cnt", _p(C.c_uint16)),
+                ("cigar", _p(C.c_uint32)), ("n_cigar", C.c_uint64), ("seq", _p(C.c_uint8)), ("n_seq_bytes", C.c_uint64),
+                ("genes", _p(C.c_uint32)), ("n_genes", C.c_uint64)]
+
+
+class Candidates(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("gene1", _p(C.c_uint32)), ("gene2", _p(C.c_uint32)), ("contig1", _p(C.c_uint16)), ("contig2", _p(C.c_uint16)),
+                ("breakpoint1", _p(C.c_int32)), ("breakpoint2", _p(C.c_int32)), ("direction1", _p(C.c_uint8)), ("direction2", _p(C.c_uint8)),
+                ("split_reads1", _p(C.c_uint32)), ("split_reads2", _p(C.c_uint32)), ("discordant_mates", _p(C.c_uint32)),
+                ("filter", _p(C.c_uint8)), ("bits", _p(C.c_uint8)), ("bits2", _p(C.c_uint8)),
+                ("anchor_start1", _p(C.c_int32)), ("anchor_start2", _p(C.c_int32)), ("evalue", _p(C.c_float)),
+                ("list1_off", _p(C.c_uint32)), ("list2_off", _p(C.c_uint32)), ("listd_off", _p(C.c_uint32)),
+                ("list1", _p(C.c_uint32)), ("list2", _p(C.c_uint32)), ("listd", _p(C.c_uint32))]
+
+
+_CTYPE = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.uint16): C.c_uint16, np.dtype(np.uint32): C.c_uint32, np.dtype(np.int32): C.c_int32,
+          np.dtype(np.float32): C.c_float, np.dtype(np.uint64): C.c_uint64}
+
+
+def ptr(a):
+    """numpy array -> typed ctypes pointer (array must be C-contiguous and stay alive)."""
+    assert a.flags["C_CONTIGUOUS"], "array must be contiguous"
+    return a.ctypes.data_as(_p(_CTYPE[a.dtype]))
+
+
+class ArbError(RuntimeError):
+    pass
+
+
+_LIBS = {}
+
+
+def load(path=None):
+    """Opens the C-ABI library. Default: the CUDA product library; fails loudly if it has not been built."""
+    path = path or _build.PRODUCT_LIB
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise ArbError("%s not found: run `python -c 'import __graft_entry__ as g; g.build()'` first (there is no CPU fallback)" % path)
+    lib = C.CDLL(path)
+    lib.arb_backend.restype = C.c_char_p
+    lib.arb_last_error.restype = C.c_char_p
+    lib.arb_last_error.argtypes = [C.c_void_p]
+    lib.arb_kernel_launches.restype = C.c_uint64
+    lib.arb_ctx_create.argtypes = [_p(C.c_void_p), C.c_int]
+    lib.arb_ctx_destroy.argtypes = [C.c_void_p]
+    lib.arb_default_params.argtypes = [_p(Params)]
+    for name, args in [("arb_set_params", [_p(Params)]), ("arb_set_contigs", [_p(Contigs)]), ("arb_set_annotation", [_p(Annotation)]),
+                       ("arb_push_chunk", [_p(SoaChunk)]), ("arb_run_read_filters", []),
+                       ("arb_get_fragment_filters", [_p(C.c_uint8), _p(C.c_uint8)]), ("arb_set_fragment_filters", [_p(C.c_uint8)]),
+                       ("arb_get_filter_counts", [_p(C.c_uint32)]), ("arb_find_fusions", [C.c_int32]),
+                       ("arb_candidates_size", [_p(C.c_uint32), _p(C.c_uint64), _p(C.c_uint64), _p(C.c_uint64)]),
+                       ("arb_get_candidates", [_p(Candidates)]), ("arb_get_slot_swaps", [_p(C.c_uint8)])]:
+        fn = getattr(lib, name)
+        fn.argtypes = [C.c_void_p] + args
+        fn.restype = C.c_int
+    _LIBS[path] = lib
+    return lib
+
+
+class Context:
+    """One device context (one CUDA device, one stream)."""
+
+    def __init__(self, device=0, lib_path=None):
+        self.lib = load(lib_path)
+        h = C.c_void_p()
+        if self.lib.arb_ctx_create(C.byref(h), device) != 0:
+            raise ArbError(self.lib.arb_last_error(None).decode())
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.arb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ArbError(self.lib.arb_last_error(self.h).decode())
+
+    @property
+    def backend(self):
+        return self.lib.arb_backend().decode()
+
+    def default_params(self):
+        p = Params()
+        self.lib.arb_default_params(C.byref(p))
+        return p
+
+    def set_params(self, p):
+        self._check(self.lib.arb_set_params(self.h, C.byref(p)))
+
+    def set_contigs(self, flags, sequences):
+        """flags: uint8 per contig; sequences: list of bytes (or None)."""
+        n = len(flags)
+        flags = np.ascontiguousarray(flags, np.uint8)
+        length = np.array([len(s) if s is not None else 0 for s in sequences], np.uint32)
+        arr = (C.c_char_p * n)(*[s if s is not None else None for s in sequences])
+        c = Contigs(n, ptr(flags), ptr(length), C.cast(arr, _p(C.c_char_p)))
+        self._check(self.lib.arb_set_contigs(self.h, C.byref(c)))
+
+    def set_annotation(self, a):
+        """a: dict of numpy arrays named like the struct fields."""
+        s = Annotation()
+        keep = []
+        for name, ctype in Annotation._fields_:
+            if name in ("n_genes", "n_exons", "n_contigs"):
+                setattr(s, name, int(a[name]))
+            else:
+                arr = np.ascontiguousarray(a[name]); keep.append(arr)
+                setattr(s, name, ptr(arr))
+        self._check(self.lib.arb_set_annotation(self.h, C.byref(s)))
+
+    def push_chunk(self, ch):
+        """ch: dict of numpy arrays named like arb_soa_chunk fields."""
+        s = SoaChunk()
+        keep = []
+        s.n_fragments = int(ch["n_fragments"])
+        for name, ctype in SoaChunk._fields_:
+            if name in ("n_fragments", "n_cigar", "n_seq_bytes", "n_genes"):
+                continue
+            arr = np.ascontiguousarray(ch[name]); keep.append(arr)
+            setattr(s, name, ptr(arr))
+        s.n_cigar = len(ch["cigar"]); s.n_seq_bytes = len(ch["seq"]); s.n_genes = len(ch["genes"])
+        self.n_fragments = s.n_fragments
+        self._check(self.lib.arb_push_chunk(self.h, C.byref(s)))
+
+    def run_read_filters(self):
+        self._check(self.lib.arb_run_read_filters(self.h))
+
+    def fragment_filters(self):
+        f = np.zeros(self.n_fragments, np.uint8); e = np.zeros(self.n_fragments, np.uint8)
+        self._check(self.lib.arb_get_fragment_filters(self.h, ptr(f), ptr(e)))
+        return f, e
+
+    def set_fragment_filters(self, f):
+        f = np.ascontiguousarray(f, np.uint8)
+        self._check(self.lib.arb_set_fragment_filters(self.h, ptr(f)))
+
+    def filter_counts(self):
+        c = np.zeros(N_FILTERS, np.uint32)
+        self._check(self.lib.arb_get_filter_counts(self.h, ptr(c)))
+        return c
+
+    def find_fusions(self, max_mate_gap):
+        self._check(self.lib.arb_find_fusions(self.h, int(max_mate_gap)))
+
+    def candidates(self):
+        n = C.c_uint32(); n1 = C.c_uint64(); n2 = C.c_uint64(); nd = C.c_uint64()
+        self._check(self.lib.arb_candidates_size(self.h, C.byref(n), C.byref(n1), C.byref(n2), C.byref(nd)))
+        n = n.value
+        out = {}
+        c = Candidates()
+        spec = {"gene1": np.uint32, "gene2": np.uint32, "contig1": np.uint16, "contig2": np.uint16, "breakpoint1": np.int32, "breakpoint2": np.int32,
+                "direction1": np.uint8, "direction2": np.uint8, "split_reads1": np.uint32, "split_reads2": np.uint32, "discordant_mates": np.uint32,
+                "filter": np.uint8, "bits": np.uint8, "bits2": np.uint8, "anchor_start1": np.int32, "anchor_start2": np.int32, "evalue": np.float32}
+        for k, dt in spec.items():
+            out[k] = np.zeros(max(n, 1), dt); setattr(c, k, ptr(out[k]))
+        for k in ("list1_off", "list2_off", "listd_off"):
+            out[k] = np.zeros(n + 1, np.uint32); setattr(c, k, ptr(out[k]))
+        for k, m in (("list1", n1.value), ("list2", n2.value), ("listd", nd.value)):
+            out[k] = np.zeros(max(m, 1), np.uint32); setattr(c, k, ptr(out[k]))
+        self._check(self.lib.arb_get_candidates(self.h, C.byref(c)))
+        for k in spec:
+            out[k] = out[k][:n]
+        out["list1"] = out["list1"][:n1.value]; out["list2"] = out["list2"][:n2.value]; out["listd"] = out["listd"][:nd.value]
+        out["n"] = n
+        return out
+
+    def slot_swaps(self):
+        s = np.zeros(self.n_fragments, np.uint8)
+        self._check(self.lib.arb_get_slot_swaps(self.h, ptr(s)))
+        return s

@@ -1,0 +1,134 @@
+/* arriba_b200.h -- C ABI of the B200-native implementation of Arriba's post-alignment hot path.
+ *
+ * The reference (suhrig/arriba v2.5.1) has no FFI: its seam is the set of C++ free functions that
+ * `main` (source/arriba.cpp:79) calls on two in-memory containers. Each entry point below names the
+ * reference function(s) it replaces. Plain pointers and sizes only; all arrays are caller-owned host
+ * memory (pinned memory makes the copies asynchronous), device memory is library-owned.
+ * Every function returns 0 on success, non-zero on error (message via arb_last_error). No exceptions
+ * cross the boundary. One context per thread; a context is bound to one CUDA device.
+ * There is no CPU fallback: arb_ctx_create fails when no CUDA device is usable.
+ */
+#ifndef ARRIBA_B200_H
+#define ARRIBA_B200_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ARB_N_FILTERS 38 /* filter ids follow the reference registry, source/common.hpp:30-67 */
+
+typedef struct arb_ctx arb_ctx;
+
+int arb_ctx_create(arb_ctx** out, int device);
+void arb_ctx_destroy(arb_ctx* ctx);
+const char* arb_last_error(arb_ctx* ctx);         /* ctx may be NULL: last error of arb_ctx_create */
+const char* arb_backend(void);                    /* "cuda-sm_100a" for the product library */
+uint64_t arb_kernel_launches(void);               /* kernels launched by this library since load */
+
+/* ---- reference genome and annotation --------------------------------------------------------------------
+ * Replaces the in-memory products of load_assembly (source/assembly.cpp:28), read_annotation_gtf
+ * (source/annotation.cpp:161) and make_annotation_index (source/annotation.t.hpp:25) as inputs of the kernels. */
+typedef struct arb_contigs {
+	uint32_t n_contigs;
+	const uint8_t* flags;          /* bit0 interesting (-i), bit1 viral (-v) */
+	const uint32_t* length;        /* 0 if the sequence is not loaded */
+	const char* const* sequence;   /* upper-case bases per contig, NULL if not loaded */
+} arb_contigs;
+int arb_set_contigs(arb_ctx* ctx, const arb_contigs* contigs);
+
+typedef struct arb_annotation {
+	uint32_t n_genes;              /* gene id == index; ids ascend in creation order (GTF order, then dummy genes) */
+	const uint16_t* gene_contig; const int32_t* gene_start; const int32_t* gene_end;
+	const uint8_t* gene_strand;    /* 1 = forward */
+	const int32_t* gene_exonic_length;
+	const uint8_t* gene_flags;     /* bit0 dummy, bit1 protein coding */
+	uint32_t n_exons;              /* exon id == index, creation (GTF) order */
+	const uint32_t* exon_gene; const int32_t* exon_start; const int32_t* exon_end;
+	const int32_t* exon_cds_start; const int32_t* exon_cds_end; /* -1 = none */
+	const int32_t* exon_next_start;                             /* start of the next exon of the transcript, -1 = none */
+	const uint8_t* exon_flags;     /* bit0 has previous exon, bit1 has next exon */
+	uint32_t n_contigs;
+	/* disjoint-region indices: region r of contig c (exon_region_begin[c] <= r < exon_region_begin[c+1]) covers
+	   (end[r-1], end[r]] and lists the ids overlapping it (ascending) */
+	const uint32_t* exon_region_begin; const int32_t* exon_region_end; const uint32_t* exon_region_off; const uint32_t* exon_region_items;
+	const uint32_t* gene_region_begin; const int32_t* gene_region_end; const uint32_t* gene_region_off; const uint32_t* gene_region_items;
+} arb_annotation;
+int arb_set_annotation(arb_ctx* ctx, const arb_annotation* annotation);
+
+/* ---- options that the kernels need (subset of options_t, source/options.hpp:25-69; defaults options.cpp:71-107) */
+typedef struct arb_params {
+	uint64_t filter_mask;              /* bit f set = filter id f enabled (-f clears bits) */
+	uint32_t homopolymer_length;       /* -H 6 */
+	int32_t min_read_through_distance; /* -R 10000 */
+	float max_kmer_content;            /* -K 0.6 */
+	uint32_t max_itd_length;           /* -l 100 */
+	uint32_t external_duplicate_marking; /* -u */
+	float mismatch_pvalue_cutoff;      /* -V 0.01 */
+	uint32_t subsampling_threshold;    /* -U 300 */
+	float evalue_cutoff;               /* -E 0.3 */
+	float max_mismapper_fraction;      /* -m 0.8 */
+	float max_homolog_identity;        /* -L 0.3 */
+} arb_params;
+void arb_default_params(arb_params* p);
+int arb_set_params(arb_ctx* ctx, const arb_params* p);
+
+/* ---- fragments -----------------------------------------------------------------------------------------
+ * Structure-of-arrays image of chimeric_alignments_t (source/common.hpp:191-220) as produced by
+ * read_chimeric_alignments (source/read_chimeric_alignments.cpp:560) + annotation (arriba.cpp:165-325).
+ * Fragments are in NAME ORDER of "<qname>,<HI>" (the std::map order every reference loop relies on);
+ * the index of a fragment is its name rank. Per-alignment arrays hold 3*n entries: index = slot*n + fragment,
+ * slot 0 = MATE1, 1 = MATE2 / SPLIT_READ, 2 = SUPPLEMENTARY (unused for discordant mates). */
+typedef struct arb_soa_chunk {
+	uint32_t n_fragments;
+	const uint8_t* n_aln;          /* 2 or 3 */
+	const uint8_t* fflags;         /* bit0 single_end, bit1 multimapper, bit2 duplicate (BAM 0x400) */
+	const uint8_t* filter;         /* initial labels (normally all 0) */
+	const uint16_t* contig; const int32_t* start; const int32_t* end;
+	const uint8_t* aflags;         /* bit0 supplementary, 1 first_in_pair, 2 exonic, 3 forward strand, 4 predicted strand forward, 5 predicted strand ambiguous */
+	const uint32_t* cigar_off; const uint16_t* cigar_cnt;
+	const uint32_t* seq_off;       /* slots 0 and 1 (2*n entries used), units of 16 bytes */
+	const uint16_t* seq_len;
+	const uint32_t* genes_off; const uint16_t* genes_cnt;
+	const uint32_t* cigar; uint64_t n_cigar;     /* BAM-encoded CIGAR operations */
+	const uint8_t* seq; uint64_t n_seq_bytes;    /* nt16 4-bit bases, BAM nibble order */
+	const uint32_t* genes; uint64_t n_genes;     /* gene ids, each set ascending */
+} arb_soa_chunk;
+int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* chunk); /* H2D copy; replaces the resident fragment table */
+
+/* ---- read-level filter cascade ---------------------------------------------------------------------------
+ * Replaces filter_duplicates, filter_uninteresting_contigs, filter_viral_contigs, filter_proximal_read_through,
+ * filter_inconsistently_clipped_mates, filter_homopolymer, filter_small_insert_size, filter_long_gap, filter_same_gene,
+ * filter_hairpin, filter_mismatches, filter_low_entropy (source/filter_*.cpp; call order arriba.cpp:327-409).
+ * genome_size: sum of the lengths of interesting contigs (filter_mismatches.cpp:105-108). */
+int arb_run_read_filters(arb_ctx* ctx);
+int arb_get_fragment_filters(arb_ctx* ctx, uint8_t* filter_out /* n */, uint8_t* early_out /* n or NULL: labels after the contig filters */);
+int arb_set_fragment_filters(arb_ctx* ctx, const uint8_t* filter /* n */); /* host-side filters (viral, multimappers, ITD recovery) write back */
+int arb_get_filter_counts(arb_ctx* ctx, uint32_t counts[ARB_N_FILTERS]); /* fragments per label; `(remaining=..)` lines derive from it */
+
+/* ---- candidate generation --------------------------------------------------------------------------------
+ * Replaces find_fusions (source/fusions.cpp:203). Candidates are numbered in the order the reference would first
+ * insert them into fusions_t (fragment name order, then gene1 x gene2 loop order). */
+typedef struct arb_candidates {
+	uint32_t n;
+	uint32_t *gene1, *gene2; uint16_t *contig1, *contig2; int32_t *breakpoint1, *breakpoint2; uint8_t *direction1, *direction2; /* 1 = upstream */
+	uint32_t *split_reads1, *split_reads2, *discordant_mates;
+	uint8_t* filter;
+	uint8_t* bits;   /* 1 exonic1, 2 exonic2, 4 spliced1, 8 spliced2, 16 predicted_strand1 fwd, 32 predicted_strand2 fwd, 64 predicted strands ambiguous,
+	                    128 transcript start = gene1 */
+	uint8_t* bits2;  /* 1 transcript start ambiguous */
+	int32_t *anchor_start1, *anchor_start2;
+	float* evalue;
+	uint32_t *list1_off, *list2_off, *listd_off; /* n+1 each */
+	uint32_t *list1, *list2, *listd;             /* fragment indices (name ranks), name order */
+} arb_candidates;
+int arb_find_fusions(arb_ctx* ctx, int32_t max_mate_gap);
+int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n_list1, uint64_t* n_list2, uint64_t* n_listd);
+int arb_get_candidates(arb_ctx* ctx, arb_candidates* out /* caller-allocated to arb_candidates_size */);
+int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if MATE1/MATE2 were canonicalised (fusions.cpp:416-421) */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
