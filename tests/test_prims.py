@@ -1,0 +1,50 @@
+"""Device primitives (scan, stable radix sort, exact hash group-by) against numpy."""
+import ctypes as C
+import numpy as np
+import pytest
+from arriba_b200 import lib as L
+
+
+def _fns(path):
+    lib = L.load(path)
+    p32 = C.POINTER(C.c_uint32)
+    lib.arb_selftest_scan.argtypes = [p32, p32, C.c_uint32]
+    lib.arb_selftest_sort.argtypes = [p32, p32, C.c_uint32, C.c_uint32]
+    lib.arb_selftest_group.argtypes = [p32, p32, C.c_uint32]
+    return lib
+
+
+def check_prims(path, sizes):
+    lib = _fns(path)
+    rng = np.random.default_rng(5)
+    for n in sizes:
+        a = rng.integers(0, 1000, n, dtype=np.uint32)
+        out = np.zeros(n + 1, np.uint32)
+        assert lib.arb_selftest_scan(L.ptr(a), L.ptr(out), n) == 0
+        want = np.concatenate([[0], np.cumsum(a, dtype=np.uint64)]).astype(np.uint32)
+        assert np.array_equal(out, want), "scan n=%d" % n
+        for bits in (1, 8, 13, 24, 32):
+            hi = (1 << bits) - 1
+            k = rng.integers(0, hi + 1, n, dtype=np.uint64).astype(np.uint32)
+            if n > 10:
+                k[: n // 3] = k[0]  # long runs of equal keys: stability matters
+            v = np.arange(n, dtype=np.uint32)
+            k2, v2 = k.copy(), v.copy()
+            assert lib.arb_selftest_sort(L.ptr(k2), L.ptr(v2), n, bits) == 0
+            order = np.argsort(k, kind="stable")
+            assert np.array_equal(k2, k[order]) and np.array_equal(v2, v[order]), "sort n=%d bits=%d" % (n, bits)
+        g = rng.integers(0, max(1, n // 7), n, dtype=np.uint32)
+        first = np.zeros(max(n, 1), np.uint32)
+        assert lib.arb_selftest_group(L.ptr(g), L.ptr(first), n) == 0
+        if n:
+            _, idx, inv = np.unique(g, return_index=True, return_inverse=True)
+            assert np.array_equal(first[:n], idx[inv].astype(np.uint32)), "group n=%d" % n
+
+
+def test_prims_hostsim(hostsim_lib):
+    check_prims(hostsim_lib, [0, 1, 2, 33, 2047, 2048, 2049, 10000])
+
+
+@pytest.mark.gpu
+def test_prims_cuda(cuda_lib):
+    check_prims(cuda_lib, [0, 1, 2, 33, 255, 256, 2047, 2048, 2049, 8192, 8193, 100000, 3000001])
