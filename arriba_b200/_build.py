@@ -18,7 +18,7 @@ ORACLE_BIN = os.path.join(ROOT, "oracle", "_ref", "arriba")
 REFERENCE = "/root/reference/source"
 
 CU_SOURCES = ["prims.cu", "engine.cu", "fusions.cu", "capi.cu", "selftest.cu"]
-CPP_SOURCES = ["mismatch_table.cpp"]
+CPP_SOURCES = ["mismatch_table.cpp", "host/refdata.cpp", "host/ingest.cpp", "host/annotate.cpp", "host/pipeline.cpp", "host/host_capi.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--fmad=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unused-function", "-Xptxas", "-v"]
 GXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-Wall", "-Wno-unused-function", "-ffp-contract=off"]
@@ -33,8 +33,8 @@ def _newer(target, deps):
 
 def _all_sources():
     out = [os.path.join(ROOT, "include", "arriba_b200.h")]
-    for f in os.listdir(CSRC):
-        out.append(os.path.join(CSRC, f))
+    for d, _, files in os.walk(CSRC):
+        out += [os.path.join(d, f) for f in files]
     return out
 
 
@@ -67,12 +67,12 @@ def build_product(force=False, verbose=False):
         o = os.path.join(objdir, s + ".o")
         jobs.append([nvcc] + NVCC_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", o])
     for s in CPP_SOURCES:
-        o = os.path.join(objdir, s + ".o")
+        o = os.path.join(objdir, s.replace("/", "_") + ".o")
         jobs.append(["g++"] + GXX_FLAGS + ["-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", o])
     with ThreadPoolExecutor(8) as ex:
         list(ex.map(lambda c: _run(c, log), jobs))
-    objs = [os.path.join(objdir, s + ".o") for s in CU_SOURCES + CPP_SOURCES]
-    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", PRODUCT_LIB] + objs + ["-lcudart"], log)
+    objs = [os.path.join(objdir, s.replace("/", "_") + ".o") for s in CU_SOURCES + CPP_SOURCES]
+    _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", PRODUCT_LIB] + objs + ["-lcudart", "-lz", "-lpthread"], log)
     with open(os.path.join(objdir, "build.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
@@ -91,11 +91,11 @@ def build_hostsim(force=False):
     for s in CU_SOURCES:
         jobs.append(["g++", "-x", "c++"] + GXX_FLAGS + ["-DARB_HOSTSIM", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", os.path.join(objdir, s + ".o")])
     for s in CPP_SOURCES:
-        jobs.append(["g++"] + GXX_FLAGS + ["-DARB_HOSTSIM", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", os.path.join(objdir, s + ".o")])
+        jobs.append(["g++"] + GXX_FLAGS + ["-DARB_HOSTSIM", "-I", os.path.join(ROOT, "include"), "-c", os.path.join(CSRC, s), "-o", os.path.join(objdir, s.replace("/", "_") + ".o")])
     with ThreadPoolExecutor(8) as ex:
         list(ex.map(_run, jobs))
-    objs = [os.path.join(objdir, s + ".o") for s in CU_SOURCES + CPP_SOURCES]
-    _run(["g++", "-shared", "-o", HOSTSIM_LIB] + objs)
+    objs = [os.path.join(objdir, s.replace("/", "_") + ".o") for s in CU_SOURCES + CPP_SOURCES]
+    _run(["g++", "-shared", "-o", HOSTSIM_LIB] + objs + ["-lz", "-lpthread"])
     return HOSTSIM_LIB
 
 

@@ -1,0 +1,113 @@
+// host_capi.cpp -- C ABI of the whole-run driver (include/arriba_b200.h, "whole-run driver" section).
+#include "pipeline.h"
+#include <cstring>
+#include <stdexcept>
+
+using namespace arb::host;
+
+struct arb_pipeline { pipeline p; std::string error; };
+static std::string g_pipeline_create_error;
+
+#define PIPE_BEGIN(x) if (!(x)) return 2; try {
+#define PIPE_END(x) } catch (const std::exception& e) { (x)->error = e.what(); return 1; } catch (...) { (x)->error = "unknown error"; return 1; } return 0;
+
+extern "C" {
+
+void arb_default_run_options(arb_run_options* o) {
+	if (!o) return;
+	memset(o, 0, sizeof(*o));
+	arb_default_params(&o->params);
+	o->strandedness = 3; o->fragment_length = 200; o->threads = 1; o->device = 0;
+}
+
+int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
+	if (!out || !o) return 2;
+	*out = NULL;
+	try {
+		if (!o->bam_file || !o->gtf_file || !o->assembly_file) throw std::runtime_error("bam_file, gtf_file and assembly_file are mandatory");
+		arb_pipeline* x = new arb_pipeline();
+		run_options& r = x->p.opt;
+		r.bam_file = o->bam_file; r.gtf_file = o->gtf_file; r.assembly_file = o->assembly_file;
+		if (o->output_file) r.output_file = o->output_file;
+		if (o->discarded_output_file) r.discarded_output_file = o->discarded_output_file;
+		if (o->interesting_contigs) r.interesting_contigs = o->interesting_contigs;
+		if (o->viral_contigs) r.viral_contigs = o->viral_contigs;
+		r.params = o->params; r.strandedness = o->strandedness; r.fragment_length = o->fragment_length; r.threads = o->threads; r.device = o->device;
+		*out = x;
+	} catch (const std::exception& e) { g_pipeline_create_error = e.what(); return 1; }
+	return 0;
+}
+
+void arb_pipeline_destroy(arb_pipeline* p) { delete p; }
+const char* arb_pipeline_error(arb_pipeline* p) { return p ? p->error.c_str() : g_pipeline_create_error.c_str(); }
+
+int arb_pipeline_step(arb_pipeline* x, int step) {
+	PIPE_BEGIN(x)
+	switch (step) {
+		case ARB_STEP_LOAD_REFERENCE: x->p.load_reference(); break;
+		case ARB_STEP_INGEST: x->p.ingest(); break;
+		case ARB_STEP_ANNOTATE: x->p.annotate(); break;
+		case ARB_STEP_UPLOAD: x->p.upload(); break;
+		case ARB_STEP_READ_FILTERS: x->p.read_filters(); break;
+		case ARB_STEP_FRAGMENT_LENGTH: x->p.fragment_length(); break;
+		case ARB_STEP_FIND_FUSIONS: x->p.find_fusions(); break;
+		default: throw std::runtime_error("unknown pipeline step");
+	}
+	PIPE_END(x)
+}
+
+int arb_pipeline_run(arb_pipeline* x) { PIPE_BEGIN(x) x->p.run_all(); PIPE_END(x) }
+arb_ctx* arb_pipeline_ctx(arb_pipeline* x) { return x ? x->p.ctx : NULL; }
+
+int arb_pipeline_stats(arb_pipeline* x, arb_run_stats* s) {
+	PIPE_BEGIN(x)
+	const pipeline& p = x->p;
+	memset(s, 0, sizeof(*s));
+	s->n_fragments = p.frags.n; s->n_records = p.istats.records; s->mapped_reads = p.istats.mapped_reads; s->malformed = p.istats.malformed;
+	s->strandedness = p.strandedness; s->max_mate_gap = p.max_mate_gap; s->fragment_length_ok = p.fragment_length_ok;
+	s->mate_gap_mean = p.mate_gap_mean; s->mate_gap_stddev = p.mate_gap_stddev; s->read_length_mean = p.read_length_mean;
+	s->seconds[ARB_STEP_LOAD_REFERENCE] = p.t_reference; s->seconds[ARB_STEP_INGEST] = p.t_ingest; s->seconds[ARB_STEP_ANNOTATE] = p.t_annotate;
+	s->seconds[ARB_STEP_UPLOAD] = p.t_upload; s->seconds[ARB_STEP_READ_FILTERS] = p.t_read_filters; s->seconds[ARB_STEP_FRAGMENT_LENGTH] = p.t_fragment_length;
+	s->seconds[ARB_STEP_FIND_FUSIONS] = p.t_find_fusions;
+	s->t_inflate = p.istats.t_inflate; s->t_parse = p.istats.t_parse; s->t_finalize = p.istats.t_finalize;
+	const arb::host::fragment_table& f = p.frags;
+	s->h2d_bytes = f.n_aln.size() + f.fflags.size() + f.filter.size() + f.aflags.size() + 2 * (f.contig.size() + f.cigar_cnt.size() + f.seq_len.size() + f.genes_cnt.size()) +
+	               4 * (f.start.size() + f.end.size() + f.cigar_off.size() + f.seq_off.size() + f.genes_off.size() + f.cigar.size() + f.genes.size()) + f.seq.size();
+	PIPE_END(x)
+}
+
+int arb_pipeline_fragments(arb_pipeline* x, arb_soa_chunk* c, const char** names, const uint64_t** name_off) {
+	PIPE_BEGIN(x)
+	const arb::host::fragment_table& f = x->p.frags;
+	c->n_fragments = f.n; c->n_aln = f.n_aln.data(); c->fflags = f.fflags.data(); c->filter = f.filter.data(); c->contig = f.contig.data(); c->start = f.start.data(); c->end = f.end.data();
+	c->aflags = f.aflags.data(); c->cigar_off = f.cigar_off.data(); c->cigar_cnt = f.cigar_cnt.data(); c->seq_off = f.seq_off.data(); c->seq_len = f.seq_len.data();
+	c->genes_off = f.genes_off.data(); c->genes_cnt = f.genes_cnt.data(); c->cigar = f.cigar.data(); c->n_cigar = f.cigar.size(); c->seq = f.seq.data(); c->n_seq_bytes = f.seq.size();
+	c->genes = f.genes.data(); c->n_genes = f.genes.size();
+	if (names) *names = f.names.data();
+	if (name_off) *name_off = f.name_off.data();
+	PIPE_END(x)
+}
+
+int arb_pipeline_genes(arb_pipeline* x, arb_annotation* a) {
+	PIPE_BEGIN(x)
+	refdata& r = x->p.ref;
+	memset(a, 0, sizeof(*a));
+	a->n_genes = (uint32_t) r.genes.size(); a->gene_contig = r.f_gene_contig.data(); a->gene_start = r.f_gene_start.data(); a->gene_end = r.f_gene_end.data();
+	a->gene_strand = r.f_gene_strand.data(); a->gene_exonic_length = r.f_gene_exonic_length.data(); a->gene_flags = r.f_gene_flags.data();
+	a->n_exons = (uint32_t) r.exons.size(); a->exon_gene = r.f_exon_gene.data(); a->exon_start = r.f_exon_start.data(); a->exon_end = r.f_exon_end.data();
+	a->exon_cds_start = r.f_exon_cds_start.data(); a->exon_cds_end = r.f_exon_cds_end.data(); a->exon_next_start = r.f_exon_next_start.data(); a->exon_flags = r.f_exon_flags.data();
+	a->n_contigs = (uint32_t) r.contig_ids.size();
+	a->exon_region_begin = r.exon_index.begin.data(); a->exon_region_end = r.exon_index.end.data(); a->exon_region_off = r.exon_index.off.data(); a->exon_region_items = r.exon_index.items.data();
+	a->gene_region_begin = r.gene_index.begin.data(); a->gene_region_end = r.gene_index.end.data(); a->gene_region_off = r.gene_index.off.data(); a->gene_region_items = r.gene_index.items.data();
+	PIPE_END(x)
+}
+
+int arb_pipeline_coverage(arb_pipeline* x, uint32_t contig, const uint16_t** cov, const uint8_t** starts, const uint8_t** ends, uint64_t* n) {
+	PIPE_BEGIN(x)
+	const coverage_windows& c = x->p.coverage;
+	if (contig >= c.coverage.size()) { *n = 0; *cov = NULL; *starts = NULL; *ends = NULL; }
+	else { *n = c.coverage[contig].size(); *cov = c.coverage[contig].data(); *starts = c.starts[contig].data(); *ends = c.ends[contig].data(); }
+	PIPE_END(x)
+}
+
+} // extern "C"

@@ -1,0 +1,45 @@
+// ingest.h -- chimeric BAM ingest: BGZF/BAM decoding on host threads into structure-of-arrays fragment columns
+// (arb_soa_chunk layout, fragments in name order), plus the by-products the later stages need (mapped read count,
+// coverage windows). Behavioural contract: read_chimeric_alignments (read_chimeric_alignments.cpp:560-773) and helpers
+// (:19-558), mark_multimappers (:792-802), coverage_t (read_stats.cpp:148-306). Only STAR "WithinBAM" input (-x) is
+// handled; Chimeric.out.sam (-c), SAM text and CRAM are not.
+#pragma once
+#include <string>
+#include <vector>
+#include "refdata.h"
+
+namespace arb { namespace host {
+
+struct coverage_windows { // 20 bp windows (read_stats.hpp:14)
+	std::vector<std::vector<u16> > coverage;
+	std::vector<std::vector<u8> > starts, ends;
+	void resize(const refdata& ref);
+	bool fragment_starts_here(u32 contig, i32 start, i32 end) const;
+	bool fragment_ends_here(u32 contig, i32 start, i32 end) const;
+	int get_coverage(u32 contig, i32 position, u32 direction) const;
+};
+
+struct fragment_table { // host image of arb_soa_chunk + names
+	u32 n;
+	std::vector<u8> n_aln, fflags, filter, aflags;
+	std::vector<u16> contig, cigar_cnt, seq_len, genes_cnt;
+	std::vector<i32> start, end;
+	std::vector<u32> cigar_off, seq_off, genes_off, cigar, genes;
+	std::vector<u8> seq;
+	std::vector<char> names; std::vector<u64> name_off; // "<qname>,<HI>[ITD]" per fragment, name order
+	fragment_table(): n(0) {}
+	frag_view view();
+	std::string name(u32 i) const { return std::string(names.data() + name_off[i], names.data() + name_off[i + 1]); }
+};
+
+struct ingest_stats {
+	u64 mapped_reads; std::vector<u64> mapped_viral_reads_by_contig; u64 malformed, missing_hi_tag, records; bool no_chimeric_reads;
+	double t_inflate, t_parse, t_finalize;
+};
+
+struct ingest_options { bool external_duplicate_marking; u32 max_itd_length; std::string interesting_contigs, viral_contigs; int threads; };
+
+// reads the BAM, fills `out` (name order, slots normalised, multimappers marked); throws std::runtime_error on fatal input errors
+void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const ingest_options& opt, fragment_table& out, coverage_windows& coverage, ingest_stats& stats);
+
+}} // namespace

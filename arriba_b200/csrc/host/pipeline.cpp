@@ -1,0 +1,135 @@
+// pipeline.cpp -- see pipeline.h.
+#include "pipeline.h"
+#include <chrono>
+#include <sstream>
+#include <stdexcept>
+#include <algorithm>
+
+namespace arb { namespace host {
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+run_options::run_options(): interesting_contigs("1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 X Y AC_* NC_*"), viral_contigs("AC_* NC_*"),
+	strandedness(3), fragment_length(200), threads(1), device(0) { arb_default_params(&params); }
+
+pipeline::~pipeline() { if (ctx) arb_ctx_destroy(ctx); }
+
+static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
+
+void pipeline::load_reference() {
+	const double t0 = now_s();
+	threads = std::max(1, opt.threads);
+	const bool filter_contigs = opt.params.filter_mask >> F_uninteresting_contigs & 1;
+	if (!filter_contigs) opt.interesting_contigs = "*"; // arriba.cpp:92-93
+	ref.load_assembly(opt.assembly_file, opt.interesting_contigs);
+	ref.load_gtf(opt.gtf_file);
+	ref.build_exon_index();
+	ref.build_gene_index();
+	ref.compute_exonic_lengths();
+	ref.flatten();
+	t_reference = now_s() - t0;
+}
+
+void pipeline::ingest() {
+	const double t0 = now_s();
+	ingest_options io; io.external_duplicate_marking = opt.params.external_duplicate_marking; io.max_itd_length = opt.params.max_itd_length;
+	io.interesting_contigs = opt.interesting_contigs; io.viral_contigs = opt.viral_contigs; io.threads = threads;
+	read_chimeric_alignments(opt.bam_file, ref, io, frags, coverage, istats);
+	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")\n";
+	log += s.str();
+	t_ingest = now_s() - t0;
+}
+
+void pipeline::annotate() {
+	const double t0 = now_s();
+	ref.set_contig_flags(opt.interesting_contigs, opt.viral_contigs);
+	ref.flatten();
+	u32 marked = 0;
+	for (u32 i = 0; i + 1 < frags.n; ++i) { // count adjacent pairs like mark_multimappers' return value
+		const u64 a0 = frags.name_off[i], a1 = frags.name_off[i + 1], a2 = frags.name_off[i + 2];
+		u64 la = a1 - a0, lb = a2 - a1;
+		while (la > 0 && frags.names[a0 + la - 1] != ',') --la;
+		while (lb > 0 && frags.names[a1 + lb - 1] != ',') --lb;
+		const u64 sa = la > 0 ? la - 1 : a1 - a0, sb = lb > 0 ? lb - 1 : a2 - a1;
+		if (sa == sb && std::equal(frags.names.begin() + a0, frags.names.begin() + a0 + sa, frags.names.begin() + a1)) ++marked;
+	}
+	{ std::ostringstream s; s << "Marking multi-mapping alignments (marked=" << marked << ")\n"; log += s.str(); }
+	strandedness = opt.strandedness;
+	if (opt.strandedness == 3) {
+		strandedness = detect_strandedness(*this);
+		log += std::string("Detecting strandedness (") + (strandedness == 1 ? "yes" : strandedness == 2 ? "reverse" : "no") + ")\n";
+	}
+	if (strandedness != 0) assign_strands(*this, strandedness);
+	annotate_fragments(*this);
+	t_annotate = now_s() - t0;
+}
+
+void pipeline::upload() {
+	const double t0 = now_s();
+	if (!ctx) { if (arb_ctx_create(&ctx, opt.device) != 0) throw std::runtime_error(arb_last_error(NULL)); }
+	check(ctx, arb_set_params(ctx, &opt.params), "arb_set_params");
+	const u32 nc = (u32) ref.contig_ids.size();
+	std::vector<const char*> seqs(nc, (const char*) NULL);
+	for (u32 c = 0; c < nc; ++c) if (ref.has_sequence(c)) seqs[c] = ref.sequence(c);
+	arb_contigs contigs = {nc, ref.contig_flags.data(), ref.seq_len.data(), seqs.data()};
+	check(ctx, arb_set_contigs(ctx, &contigs), "arb_set_contigs");
+	arb_annotation a;
+	a.n_genes = (u32) ref.genes.size(); a.gene_contig = ref.f_gene_contig.data(); a.gene_start = ref.f_gene_start.data(); a.gene_end = ref.f_gene_end.data();
+	a.gene_strand = ref.f_gene_strand.data(); a.gene_exonic_length = ref.f_gene_exonic_length.data(); a.gene_flags = ref.f_gene_flags.data();
+	a.n_exons = (u32) ref.exons.size(); a.exon_gene = ref.f_exon_gene.data(); a.exon_start = ref.f_exon_start.data(); a.exon_end = ref.f_exon_end.data();
+	a.exon_cds_start = ref.f_exon_cds_start.data(); a.exon_cds_end = ref.f_exon_cds_end.data(); a.exon_next_start = ref.f_exon_next_start.data(); a.exon_flags = ref.f_exon_flags.data();
+	a.n_contigs = nc;
+	a.exon_region_begin = ref.exon_index.begin.data(); a.exon_region_end = ref.exon_index.end.data(); a.exon_region_off = ref.exon_index.off.data(); a.exon_region_items = ref.exon_index.items.data();
+	a.gene_region_begin = ref.gene_index.begin.data(); a.gene_region_end = ref.gene_index.end.data(); a.gene_region_off = ref.gene_index.off.data(); a.gene_region_items = ref.gene_index.items.data();
+	check(ctx, arb_set_annotation(ctx, &a), "arb_set_annotation");
+	arb_soa_chunk c;
+	c.n_fragments = frags.n; c.n_aln = frags.n_aln.data(); c.fflags = frags.fflags.data(); c.filter = frags.filter.data();
+	c.contig = frags.contig.data(); c.start = frags.start.data(); c.end = frags.end.data(); c.aflags = frags.aflags.data();
+	c.cigar_off = frags.cigar_off.data(); c.cigar_cnt = frags.cigar_cnt.data(); c.seq_off = frags.seq_off.data(); c.seq_len = frags.seq_len.data();
+	c.genes_off = frags.genes_off.data(); c.genes_cnt = frags.genes_cnt.data();
+	c.cigar = frags.cigar.data(); c.n_cigar = frags.cigar.size(); c.seq = frags.seq.data(); c.n_seq_bytes = frags.seq.size(); c.genes = frags.genes.data(); c.n_genes = frags.genes.size();
+	check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+	t_upload = now_s() - t0;
+}
+
+static const char* FILTER_NAME[] = {"", "duplicates", "inconsistently_clipped", "homopolymer", "read_through", "same_gene", "small_insert_size", "long_gap", "hairpin",
+	"multimappers", "mismatches", "mismappers", "relative_support", "intronic", "non_coding_neighbors", "intragenic_exonic", "internal_tandem_duplication", "min_support",
+	"known_fusions", "spliced", "blacklist", "end_to_end", "in_vitro", "merge_adjacent", "select_best", "marginal_read_through", "short_anchor", "no_coverage", "many_spliced",
+	"no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs", "genomic_support", "isoforms", "low_entropy", "homologs"};
+
+void pipeline::read_filters() {
+	const double t0 = now_s();
+	check(ctx, arb_run_read_filters(ctx), "arb_run_read_filters");
+	labels.resize(frags.n); early.resize(frags.n);
+	check(ctx, arb_get_fragment_filters(ctx, labels.data(), early.data()), "arb_get_fragment_filters");
+	// `(remaining=N)` of every stage follows from the label histogram, because the first hit wins and the order is fixed (arriba.cpp:327-409)
+	uint32_t counts[ARB_N_FILTERS];
+	check(ctx, arb_get_filter_counts(ctx, counts), "arb_get_filter_counts");
+	static const int order[] = {F_duplicates, F_uninteresting_contigs, F_viral_contigs, F_top_expressed_viral_contigs, F_low_coverage_viral_contigs, F_read_through,
+		F_inconsistently_clipped, F_homopolymer, F_small_insert_size, F_long_gap, F_same_gene, F_hairpin, F_mismatches};
+	u64 remaining = frags.n;
+	std::ostringstream s;
+	// ITD-shaped fragments re-labelled by low_entropy keep their original stage unknown; the cumulative count is exact only when none were re-labelled
+	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "filter " << FILTER_NAME[order[k]] << " (labelled=" << counts[order[k]] << ")\n"; }
+	s << "filter low_entropy (remaining=" << counts[F_none] << ")\n";
+	log += s.str();
+	t_read_filters = now_s() - t0;
+}
+
+void pipeline::fragment_length() {
+	const double t0 = now_s();
+	fragment_length_ok = estimate_fragment_length(*this, early.data(), mate_gap_mean, mate_gap_stddev, read_length_mean);
+	if (fragment_length_ok) max_mate_gap = std::max(0, (int) (mate_gap_mean + 3 * mate_gap_stddev)); // arriba.cpp:357-363
+	else { max_mate_gap = (i32) opt.fragment_length; read_length_mean = (float) opt.fragment_length; }
+	t_fragment_length = now_s() - t0;
+}
+
+void pipeline::find_fusions() {
+	const double t0 = now_s();
+	check(ctx, arb_find_fusions(ctx, max_mate_gap), "arb_find_fusions");
+	t_find_fusions = now_s() - t0;
+}
+
+void pipeline::run_all() { load_reference(); ingest(); annotate(); upload(); read_filters(); fragment_length(); find_fusions(); }
+
+}} // namespace

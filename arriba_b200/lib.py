@@ -223,3 +223,128 @@ class Context:
         s = np.zeros(self.n_fragments, np.uint8)
         self._check(self.lib.arb_get_slot_swaps(self.h, ptr(s)))
         return s
+
+
+# ------------------------------------------------------------------------------------------- whole-run driver
+STEP_LOAD_REFERENCE, STEP_INGEST, STEP_ANNOTATE, STEP_UPLOAD, STEP_READ_FILTERS, STEP_FRAGMENT_LENGTH, STEP_FIND_FUSIONS, STEP_COUNT = range(8)
+STEP_NAMES = ["load_reference", "ingest", "annotate", "upload", "read_filters", "fragment_length", "find_fusions"]
+
+
+class RunOptions(C.Structure):
+    _fields_ = [("bam_file", C.c_char_p), ("gtf_file", C.c_char_p), ("assembly_file", C.c_char_p), ("output_file", C.c_char_p),
+                ("discarded_output_file", C.c_char_p), ("interesting_contigs", C.c_char_p), ("viral_contigs", C.c_char_p),
+                ("params", Params), ("strandedness", C.c_int32), ("fragment_length", C.c_uint32), ("threads", C.c_int32), ("device", C.c_int32)]
+
+
+class RunStats(C.Structure):
+    _fields_ = [("n_fragments", C.c_uint64), ("n_records", C.c_uint64), ("mapped_reads", C.c_uint64), ("malformed", C.c_uint64),
+                ("strandedness", C.c_int32), ("max_mate_gap", C.c_int32), ("fragment_length_ok", C.c_int32),
+                ("mate_gap_mean", C.c_float), ("mate_gap_stddev", C.c_float), ("read_length_mean", C.c_float),
+                ("seconds", C.c_double * STEP_COUNT), ("t_inflate", C.c_double), ("t_parse", C.c_double), ("t_finalize", C.c_double),
+                ("h2d_bytes", C.c_uint64)]
+
+
+def _load_pipeline_api(lib):
+    if getattr(lib, "_pipeline_ready", False):
+        return
+    lib.arb_default_run_options.argtypes = [_p(RunOptions)]
+    lib.arb_pipeline_create.argtypes = [_p(C.c_void_p), _p(RunOptions)]
+    lib.arb_pipeline_destroy.argtypes = [C.c_void_p]
+    lib.arb_pipeline_error.argtypes = [C.c_void_p]; lib.arb_pipeline_error.restype = C.c_char_p
+    lib.arb_pipeline_step.argtypes = [C.c_void_p, C.c_int]
+    lib.arb_pipeline_run.argtypes = [C.c_void_p]
+    lib.arb_pipeline_ctx.argtypes = [C.c_void_p]; lib.arb_pipeline_ctx.restype = C.c_void_p
+    lib.arb_pipeline_stats.argtypes = [C.c_void_p, _p(RunStats)]
+    lib.arb_pipeline_fragments.argtypes = [C.c_void_p, _p(SoaChunk), _p(C.c_char_p), _p(_p(C.c_uint64))]
+    lib.arb_pipeline_genes.argtypes = [C.c_void_p, _p(Annotation)]
+    lib.arb_pipeline_coverage.argtypes = [C.c_void_p, C.c_uint32, _p(_p(C.c_uint16)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8)), _p(C.c_uint64)]
+    lib._pipeline_ready = True
+
+
+def _np_from(pointer, n, dtype):
+    if n == 0 or not pointer:
+        return np.zeros(0, dtype)
+    return np.ctypeslib.as_array(pointer, shape=(n,)).astype(dtype, copy=True)
+
+
+class Pipeline:
+    """One run of the hot path on files: the call a user of the library makes (the `arriba` CLI is a thin wrapper over it)."""
+
+    def __init__(self, bam, gtf, fasta, threads=1, device=0, lib_path=None, strandedness=3, params=None):
+        self.lib = load(lib_path)
+        _load_pipeline_api(self.lib)
+        o = RunOptions()
+        self.lib.arb_default_run_options(C.byref(o))
+        self._strings = [bam.encode(), gtf.encode(), fasta.encode()]
+        o.bam_file, o.gtf_file, o.assembly_file = self._strings
+        o.threads = threads; o.device = device; o.strandedness = strandedness
+        if params is not None:
+            o.params = params
+        h = C.c_void_p()
+        if self.lib.arb_pipeline_create(C.byref(h), C.byref(o)) != 0:
+            raise ArbError(self.lib.arb_pipeline_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib.arb_pipeline_destroy(self.h); self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ArbError(self.lib.arb_pipeline_error(self.h).decode())
+
+    def step(self, s):
+        self._check(self.lib.arb_pipeline_step(self.h, s))
+
+    def run(self, upto=STEP_COUNT - 1):
+        for s in range(upto + 1):
+            self.step(s)
+
+    def stats(self):
+        s = RunStats()
+        self._check(self.lib.arb_pipeline_stats(self.h, C.byref(s)))
+        return s
+
+    def context(self):
+        """Device context of the pipeline as a (non-owning) Context object."""
+        c = Context.__new__(Context)
+        c.lib = self.lib; c.h = C.c_void_p(self.lib.arb_pipeline_ctx(self.h)); c._keep = []; c.n_fragments = int(self.stats().n_fragments)
+        c.close = lambda: None
+        return c
+
+    def fragments(self):
+        ch = SoaChunk(); names = C.c_char_p(); off = _p(C.c_uint64)()
+        self._check(self.lib.arb_pipeline_fragments(self.h, C.byref(ch), C.byref(names), C.byref(off)))
+        n = ch.n_fragments
+        out = {"n_fragments": n}
+        for k, cnt, dt in (("n_aln", n, np.uint8), ("fflags", n, np.uint8), ("filter", n, np.uint8), ("contig", 3 * n, np.uint16), ("start", 3 * n, np.int32),
+                           ("end", 3 * n, np.int32), ("aflags", 3 * n, np.uint8), ("cigar_off", 3 * n, np.uint32), ("cigar_cnt", 3 * n, np.uint16),
+                           ("seq_off", 2 * n, np.uint32), ("seq_len", 2 * n, np.uint16), ("genes_off", 3 * n, np.uint32), ("genes_cnt", 3 * n, np.uint16),
+                           ("cigar", ch.n_cigar, np.uint32), ("seq", ch.n_seq_bytes, np.uint8), ("genes", ch.n_genes, np.uint32)):
+            out[k] = _np_from(getattr(ch, k), cnt, dt)
+        name_off = _np_from(off, n + 1, np.uint64)
+        raw = C.string_at(C.cast(names, C.c_void_p), int(name_off[-1])) if n else b""
+        out["name_off"] = name_off; out["names_blob"] = raw
+        return out
+
+    def genes(self):
+        a = Annotation()
+        self._check(self.lib.arb_pipeline_genes(self.h, C.byref(a)))
+        out = {"n_genes": a.n_genes, "n_exons": a.n_exons, "n_contigs": a.n_contigs}
+        for k, cnt, dt in (("gene_contig", a.n_genes, np.uint16), ("gene_start", a.n_genes, np.int32), ("gene_end", a.n_genes, np.int32), ("gene_strand", a.n_genes, np.uint8),
+                           ("gene_exonic_length", a.n_genes, np.int32), ("gene_flags", a.n_genes, np.uint8), ("exon_gene", a.n_exons, np.uint32),
+                           ("exon_start", a.n_exons, np.int32), ("exon_end", a.n_exons, np.int32), ("exon_cds_start", a.n_exons, np.int32), ("exon_cds_end", a.n_exons, np.int32),
+                           ("exon_flags", a.n_exons, np.uint8)):
+            out[k] = _np_from(getattr(a, k), cnt, dt)
+        return out
+
+    def coverage(self, contig):
+        cov = _p(C.c_uint16)(); st = _p(C.c_uint8)(); en = _p(C.c_uint8)(); n = C.c_uint64()
+        self._check(self.lib.arb_pipeline_coverage(self.h, contig, C.byref(cov), C.byref(st), C.byref(en), C.byref(n)))
+        return _np_from(cov, n.value, np.uint16), _np_from(st, n.value, np.uint8), _np_from(en, n.value, np.uint8)

@@ -128,6 +128,52 @@ int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n_list1, uint64_t* 
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out /* caller-allocated to arb_candidates_size */);
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if MATE1/MATE2 were canonicalised (fusions.cpp:416-421) */);
 
+/* ---- whole-run driver ---------------------------------------------------------------------------------------
+ * What the `arriba` executable does (source/arriba.cpp:79-631): reference + annotation loading, BAM ingest
+ * (read_chimeric_alignments, source/read_chimeric_alignments.cpp:560), annotation (arriba.cpp:165-325), then the device
+ * stages above. Host work is C++ on `threads` host threads; all device work goes through the entry points above. */
+typedef struct arb_pipeline arb_pipeline;
+typedef struct arb_run_options {
+	const char* bam_file;            /* -x */
+	const char* gtf_file;            /* -g */
+	const char* assembly_file;       /* -a */
+	const char* output_file;         /* -o (may be NULL until the writer stage is requested) */
+	const char* discarded_output_file; /* -O or NULL */
+	const char* interesting_contigs; /* -i or NULL for the default */
+	const char* viral_contigs;       /* -v or NULL for the default */
+	arb_params params;
+	int32_t strandedness;            /* -s: 0 no, 1 yes, 2 reverse, 3 auto */
+	uint32_t fragment_length;        /* -F 200 */
+	int32_t threads;                 /* host threads */
+	int32_t device;                  /* CUDA device ordinal */
+} arb_run_options;
+void arb_default_run_options(arb_run_options* o);
+
+enum { ARB_STEP_LOAD_REFERENCE = 0, ARB_STEP_INGEST = 1, ARB_STEP_ANNOTATE = 2, ARB_STEP_UPLOAD = 3, ARB_STEP_READ_FILTERS = 4,
+       ARB_STEP_FRAGMENT_LENGTH = 5, ARB_STEP_FIND_FUSIONS = 6, ARB_STEP_COUNT = 7 };
+
+typedef struct arb_run_stats {
+	uint64_t n_fragments, n_records, mapped_reads, malformed;
+	int32_t strandedness, max_mate_gap, fragment_length_ok;
+	float mate_gap_mean, mate_gap_stddev, read_length_mean;
+	double seconds[ARB_STEP_COUNT];      /* wall time per step */
+	double t_inflate, t_parse, t_finalize; /* inside ARB_STEP_INGEST */
+	uint64_t h2d_bytes;                  /* bytes copied host->device by ARB_STEP_UPLOAD */
+} arb_run_stats;
+
+int arb_pipeline_create(arb_pipeline** out, const arb_run_options* options);
+void arb_pipeline_destroy(arb_pipeline* p);
+const char* arb_pipeline_error(arb_pipeline* p);   /* p may be NULL: error of arb_pipeline_create */
+int arb_pipeline_step(arb_pipeline* p, int step);  /* steps must be run in order */
+int arb_pipeline_run(arb_pipeline* p);             /* all steps */
+arb_ctx* arb_pipeline_ctx(arb_pipeline* p);        /* device context (valid after ARB_STEP_UPLOAD) */
+int arb_pipeline_stats(arb_pipeline* p, arb_run_stats* out);
+/* read-only view of the host fragment table (valid until the pipeline is destroyed); names: "<qname>,<HI>" concatenated */
+int arb_pipeline_fragments(arb_pipeline* p, arb_soa_chunk* view, const char** names, const uint64_t** name_off /* n+1 */);
+/* gene table after annotation (dummy genes included) and coverage windows of one contig */
+int arb_pipeline_genes(arb_pipeline* p, arb_annotation* view);
+int arb_pipeline_coverage(arb_pipeline* p, uint32_t contig, const uint16_t** coverage, const uint8_t** starts, const uint8_t** ends, uint64_t* n_windows);
+
 #ifdef __cplusplus
 }
 #endif
