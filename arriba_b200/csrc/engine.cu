@@ -14,6 +14,7 @@ void default_params(arb_params& p) { // options.cpp:71-107
 
 engine::engine(): table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false) {
 	default_params(params);
+	memset(&timings, 0, sizeof(timings));
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
 #endif
@@ -72,6 +73,7 @@ void engine::set_annotation(const arb_annotation& a) {
 void engine::push_chunk(const arb_soa_chunk& c) {
 	const u32 n = c.n_fragments;
 	frags.n = n;
+	stage_timer t_h2d(ex);
 	frags.n_aln.upload(ex, c.n_aln, n); frags.fflags.upload(ex, c.fflags, n); frags.filter.upload(ex, c.filter, n);
 	frags.early.ensure(n); frags.swapped.ensure(n); frags.swapped.zero(ex, n);
 	frags.contig.upload(ex, c.contig, 3 * (size_t) n); frags.start.upload(ex, c.start, 3 * (size_t) n); frags.end.upload(ex, c.end, 3 * (size_t) n);
@@ -82,6 +84,12 @@ void engine::push_chunk(const arb_soa_chunk& c) {
 	u32 max_len = 0;
 	for (size_t k = 0; k < 2 * (size_t) n; ++k) if (c.seq_len[k] > max_len) max_len = c.seq_len[k];
 	frags.max_seq_len = max_len;
+	timings.h2d_ms = t_h2d.stop();
+	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 1 + 4 + 2 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes + c.n_genes * 4;
+	// bytes the fused cascade has to touch once: all per-fragment/per-alignment columns, the three pools, the reference bases under the
+	// two alignments the mismatch rule walks (~ one read length each), and the two label bytes it writes
+	timings.classify_algorithmic_bytes = timings.h2d_bytes + (u64) n * 2;
+	for (size_t k = 0; k < 2 * (size_t) n; ++k) timings.classify_algorithmic_bytes += c.seq_len[k];
 	ex.sync();
 	filters_done = false;
 	cands.n = 0;
@@ -154,6 +162,9 @@ void engine::run_read_filters() {
 	const u32 n = frags.n;
 	const read_filter_params p = make_filter_params();
 	frag_view f = frags.view();
+	stage_timer t_all(ex);
+	{
+	stage_timer t_dup(ex);
 	if (p.enabled(F_duplicates)) {
 		if (p.external_duplicate_marking) {
 			dup_external_fn fn = {f};
@@ -169,8 +180,15 @@ void engine::run_read_filters() {
 			ex.sync();
 		}
 	}
+	timings.duplicates_ms = t_dup.stop();
+	}
 	classify_fn cf = {p, f, annot.view(), frags.early.ptr()};
-	for_each(ex, n, cf);
+	{
+		stage_timer t_cls(ex);
+		for_each(ex, n, cf);
+		timings.classify_ms = t_cls.stop();
+	}
+	timings.read_filters_ms = t_all.stop();
 	ex.sync();
 	filters_done = true;
 }

@@ -4,10 +4,27 @@
 #include "prims.h"
 #include "read_filters.h"
 #include "../../include/arriba_b200.h"
+#include <time.h>
 #include <vector>
 #include <string>
 
 namespace arb {
+
+// CUDA-event stopwatch on the context's stream (wall clock in the hostsim build)
+struct stage_timer {
+#ifdef ARB_DEVICE_BUILD
+	cudaEvent_t a, b; cudaStream_t s;
+	explicit stage_timer(const exec_ctx& ex): s(ex.stream) { ARB_CUDA_CHECK(cudaEventCreate(&a)); ARB_CUDA_CHECK(cudaEventCreate(&b)); ARB_CUDA_CHECK(cudaEventRecord(a, s)); }
+	float stop() { float ms = 0; ARB_CUDA_CHECK(cudaEventRecord(b, s)); ARB_CUDA_CHECK(cudaEventSynchronize(b)); ARB_CUDA_CHECK(cudaEventElapsedTime(&ms, a, b)); return ms; }
+	~stage_timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+#else
+	double t0;
+	static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+	explicit stage_timer(const exec_ctx&): t0(now()) {}
+	float stop() { return (float) (now() - t0); }
+#endif
+};
+
 
 struct frag_store {
 	u32 n; u32 max_seq_len;
@@ -70,6 +87,7 @@ public:
 	hash_index table;
 	dbuf<u32> label_counts;
 	bool has_contigs, has_annotation, filters_done;
+	arb_timings timings;
 
 	engine();
 	void set_contigs(const arb_contigs& c);

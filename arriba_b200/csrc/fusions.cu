@@ -14,6 +14,7 @@ void engine::find_fusions(i32 max_mate_gap) {
 	const u32 T = params.subsampling_threshold;
 	frag_view f = frags.view();
 	annot_view an = annot.view();
+	stage_timer t_all(ex);
 
 	// 1. records
 	dbuf<u32> rec_off((size_t) n + 1);
@@ -110,6 +111,7 @@ void engine::find_fusions(i32 max_mate_gap) {
 	// 7. pass C
 	walk_c_fn wc = {f, an, cob, cands.list1_off.ptr(), cands.list2_off.ptr(), cands.listd_off.ptr(), cands.list1.ptr(), cands.list2.ptr(), cands.listd.ptr()};
 	for_each(ex, C, wc);
+	timings.find_fusions_ms = t_all.stop();
 	ex.sync();
 }
 

@@ -59,6 +59,11 @@ class Candidates(C.Structure):
                 ("list1", _p(C.c_uint32)), ("list2", _p(C.c_uint32)), ("listd", _p(C.c_uint32))]
 
 
+class Timings(C.Structure):
+    _fields_ = [("duplicates_ms", C.c_float), ("classify_ms", C.c_float), ("read_filters_ms", C.c_float), ("find_fusions_ms", C.c_float),
+                ("classify_algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("h2d_ms", C.c_float)]
+
+
 _CTYPE = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.uint16): C.c_uint16, np.dtype(np.uint32): C.c_uint32, np.dtype(np.int32): C.c_int32,
           np.dtype(np.float32): C.c_float, np.dtype(np.uint64): C.c_uint64}
 
@@ -96,7 +101,7 @@ def load(path=None):
                        ("arb_get_fragment_filters", [_p(C.c_uint8), _p(C.c_uint8)]), ("arb_set_fragment_filters", [_p(C.c_uint8)]),
                        ("arb_get_filter_counts", [_p(C.c_uint32)]), ("arb_find_fusions", [C.c_int32]),
                        ("arb_candidates_size", [_p(C.c_uint32), _p(C.c_uint64), _p(C.c_uint64), _p(C.c_uint64)]),
-                       ("arb_get_candidates", [_p(Candidates)]), ("arb_get_slot_swaps", [_p(C.c_uint8)])]:
+                       ("arb_get_candidates", [_p(Candidates)]), ("arb_get_slot_swaps", [_p(C.c_uint8)]), ("arb_get_timings", [_p(Timings)])]:
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p] + args
         fn.restype = C.c_int
@@ -218,6 +223,11 @@ class Context:
         out["list1"] = out["list1"][:n1.value]; out["list2"] = out["list2"][:n2.value]; out["listd"] = out["listd"][:nd.value]
         out["n"] = n
         return out
+
+    def timings(self):
+        t = Timings()
+        self._check(self.lib.arb_get_timings(self.h, C.byref(t)))
+        return t
 
     def slot_swaps(self):
         s = np.zeros(self.n_fragments, np.uint8)

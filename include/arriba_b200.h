@@ -128,6 +128,18 @@ int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n_list1, uint64_t* 
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out /* caller-allocated to arb_candidates_size */);
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if MATE1/MATE2 were canonicalised (fusions.cpp:416-421) */);
 
+/* ---- device timing (CUDA events recorded on the context's stream around each stage) ---------------------------------- */
+typedef struct arb_timings {
+	float duplicates_ms;        /* duplicate marking (key build + hash group-by + mark) */
+	float classify_ms;          /* the fused read-level cascade kernel, one launch */
+	float read_filters_ms;      /* whole arb_run_read_filters */
+	float find_fusions_ms;      /* whole arb_find_fusions */
+	uint64_t classify_algorithmic_bytes; /* bytes the cascade kernel must read/write once: every input column and pool + gathered reference bases + 2 label bytes per fragment */
+	uint64_t h2d_bytes;         /* bytes copied by the last arb_push_chunk */
+	float h2d_ms;               /* duration of those copies */
+} arb_timings;
+int arb_get_timings(arb_ctx* ctx, arb_timings* out);
+
 /* ---- whole-run driver ---------------------------------------------------------------------------------------
  * What the `arriba` executable does (source/arriba.cpp:79-631): reference + annotation loading, BAM ingest
  * (read_chimeric_alignments, source/read_chimeric_alignments.cpp:560), annotation (arriba.cpp:165-325), then the device

@@ -106,6 +106,7 @@ struct params_t {
 	int compress = 0;
 	bool chr_prefix = false;
 	bool write_world = true, write_reads = true;
+	int emit_breakpoints = -1; // emit reads of the first K breakpoints only (bounded samples of the same world)
 };
 
 static void make_genome(world_t& w, const params_t& P, rng_t& rng) {
@@ -799,6 +800,7 @@ struct generator_t {
 		long normal_every = P.normal_frac > 0 ? max(1L, (long) (1.0 / P.normal_frac)) : 0;
 		long since_normal = 0;
 		for (size_t b = 0; b < w.bps.size(); ++b) {
+			if (P.emit_breakpoints >= 0 && (int) b >= P.emit_breakpoints) break;
 			const breakpoint_t& B = w.bps[b];
 			walk_segment(w, B.contig1, B.pos1, B.down1, B.gene1, B.tr1, need, g1);
 			walk_segment(w, B.contig2, B.pos2, B.down2, B.gene2, B.tr2, need, g2);
@@ -883,6 +885,7 @@ int main(int argc, char** argv) {
 		else if (a == "--compress") P.compress = atoi(NEXT);
 		else if (a == "--chr") P.chr_prefix = true;
 		else if (a == "--reads-only") P.write_world = false;
+		else if (a == "--emit-breakpoints") P.emit_breakpoints = atoi(NEXT);
 		else usage();
 	}
 	rng_t rng(P.seed);
