@@ -43,7 +43,7 @@ int arb_ctx_create(arb_ctx** out, int device) {
 	return 0;
 }
 
-void arb_ctx_destroy(arb_ctx* ctx) { delete ctx; }
+void arb_ctx_destroy(arb_ctx* ctx) { delete ctx; pool_trim(); }
 const char* arb_last_error(arb_ctx* ctx) { return ctx ? ctx->e.last_error.c_str() : g_create_error.c_str(); }
 
 void arb_default_params(arb_params* p) { if (p) default_params(*p); }
@@ -62,6 +62,13 @@ int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n1, uint64_t* n2, u
 	ARB_API_END(ctx)
 }
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out) { ARB_API_BEGIN(ctx) ctx->e.get_candidates(*out); ARB_API_END(ctx) }
+int arb_set_candidate_state(arb_ctx* ctx, const uint8_t* f, const uint32_t* s1, const uint32_t* s2, const uint32_t* dm, const float* ev) { ARB_API_BEGIN(ctx) ctx->e.set_candidate_state(f, s1, s2, dm, ev); ARB_API_END(ctx) }
+int arb_get_candidate_state(arb_ctx* ctx, uint8_t* f, uint32_t* s1, uint32_t* s2, uint32_t* dm, float* ev) { ARB_API_BEGIN(ctx) ctx->e.get_candidate_state(f, s1, s2, dm, ev); ARB_API_END(ctx) }
+int arb_set_candidate_lists(arb_ctx* ctx, const uint32_t* l1o, const uint32_t* l1, const uint32_t* l2o, const uint32_t* l2) { ARB_API_BEGIN(ctx) ctx->e.set_candidate_lists(l1o, l1, l2o, l2); ARB_API_END(ctx) }
+int arb_merge_adjacent(arb_ctx* ctx, int32_t max_distance, uint32_t* n) { ARB_API_BEGIN(ctx) uint32_t k = ctx->e.merge_adjacent(max_distance); if (n) *n = k; ARB_API_END(ctx) }
+int arb_get_merge_log(arb_ctx* ctx, uint32_t* triples, uint32_t n) { ARB_API_BEGIN(ctx) ctx->e.get_merge_log(triples, n); ARB_API_END(ctx) }
+int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in) { ARB_API_BEGIN(ctx) ctx->e.estimate_evalues(*in); ARB_API_END(ctx) }
+int arb_filter_relative_support(arb_ctx* ctx, float cutoff) { ARB_API_BEGIN(ctx) ctx->e.filter_relative_support(cutoff); ARB_API_END(ctx) }
 int arb_get_timings(arb_ctx* ctx, arb_timings* out) { ARB_API_BEGIN(ctx) *out = ctx->e.timings; ARB_API_END(ctx) }
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.get_slot_swaps(out); ARB_API_END(ctx) }
 

@@ -101,6 +101,14 @@ public:
 	void find_fusions(i32 max_mate_gap);
 	void get_candidates(arb_candidates& out);
 	void get_slot_swaps(u8* out);
+	void set_candidate_state(const u8* filter, const u32* s1, const u32* s2, const u32* dm, const float* ev);
+	void get_candidate_state(u8* filter, u32* s1, u32* s2, u32* dm, float* ev);
+	void set_candidate_lists(const u32* l1o, const u32* l1, const u32* l2o, const u32* l2);
+	u32 merge_adjacent(i32 max_distance);
+	void get_merge_log(u32* triples, u32 n);
+	void estimate_evalues(const arb_evalue_inputs& in);
+	void filter_relative_support(float cutoff);
+	dbuf<u32> merge_log; u32 merge_log_n;
 private:
 	read_filter_params make_filter_params();
 	unsigned long genome_size() const;

@@ -1,0 +1,110 @@
+// events.cu -- drivers of the candidate-level device stages (see events_hd.h).
+#include "engine.h"
+#include "events_hd.h"
+
+namespace arb {
+
+static cand_state make_state(cand_store& c, u32* n1, u32* n2) {
+	cand_state s;
+	s.n = c.n; s.gene1 = c.gene1.ptr(); s.gene2 = c.gene2.ptr(); s.contig1 = c.contig1.ptr(); s.contig2 = c.contig2.ptr(); s.bp1 = c.bp1.ptr(); s.bp2 = c.bp2.ptr();
+	s.dir1 = c.dir1.ptr(); s.dir2 = c.dir2.ptr(); s.bits = c.bits.ptr();
+	s.split_reads1 = c.split_reads1.ptr(); s.split_reads2 = c.split_reads2.ptr(); s.discordant_mates = c.discordant_mates.ptr(); s.filter = c.filter.ptr(); s.evalue = c.evalue.ptr();
+	s.n_list1 = n1; s.n_list2 = n2;
+	return s;
+}
+
+void engine::set_candidate_state(const u8* f, const u32* s1, const u32* s2, const u32* dm, const float* ev) {
+	const u32 C = cands.n;
+	cands.filter.upload(ex, f, C); cands.split_reads1.upload(ex, s1, C); cands.split_reads2.upload(ex, s2, C); cands.discordant_mates.upload(ex, dm, C); cands.evalue.upload(ex, ev, C);
+	ex.sync();
+}
+void engine::get_candidate_state(u8* f, u32* s1, u32* s2, u32* dm, float* ev) {
+	const u32 C = cands.n;
+	cands.filter.download(ex, f, C); cands.split_reads1.download(ex, s1, C); cands.split_reads2.download(ex, s2, C); cands.discordant_mates.download(ex, dm, C); cands.evalue.download(ex, ev, C);
+}
+void engine::set_candidate_lists(const u32* l1o, const u32* l1, const u32* l2o, const u32* l2) {
+	const u32 C = cands.n;
+	cands.n_list1 = l1o[C]; cands.n_list2 = l2o[C];
+	cands.list1_off.upload(ex, l1o, (size_t) C + 1); cands.list2_off.upload(ex, l2o, (size_t) C + 1);
+	cands.list1.upload(ex, l1, cands.n_list1); cands.list2.upload(ex, l2, cands.n_list2);
+	ex.sync();
+}
+
+struct list_size_fn { const u32* off; u32* n; ARB_HD void operator()(u32 k) const { n[k] = off[k + 1] - off[k]; } };
+struct identity_fn { u32* p; ARB_HD void operator()(u32 k) const { p[k] = k; } };
+struct gather_u32_fn { const u32* src; const u32* perm; u32* dst; ARB_HD void operator()(u32 k) const { dst[k] = src[perm[k]]; } };
+
+u32 engine::merge_adjacent(i32 max_distance) {
+	const u32 C = cands.n;
+	merge_log_n = 0;
+	if (C == 0) return 0;
+	dbuf<u32> n1(C), n2(C), flag((size_t) C + 1);
+	list_size_fn ls1 = {cands.list1_off.ptr(), n1.ptr()}, ls2 = {cands.list2_off.ptr(), n2.ptr()};
+	for_each(ex, C, ls1); for_each(ex, C, ls2);
+	cand_state s = make_state(cands, n1.ptr(), n2.ptr());
+	merge_eligible_fn el = {s, params.max_itd_length, flag.ptr()};
+	for_each(ex, C, el);
+	exclusive_scan_u32(ex, flag.ptr(), flag.ptr(), C);
+	u32 M = 0; flag.download(ex, &M, 1, C);
+	if (M == 0) return 0;
+	dbuf<u32> ids(M), key(M), perm(M), tk(M), tv(M), ids_sorted(M);
+	merge_gather_fn mg = {flag.ptr(), ids.ptr()};
+	for_each(ex, C, mg);
+	// LSD over the four key fields; every pass sorts the current permutation of candidate ids (stable)
+	for (int which = 0; which < 4; ++which) {
+		merge_key_fn kf = {s, ids.ptr(), key.ptr(), which};
+		for_each(ex, M, kf);
+		const u32 bits = (which == 1 || which == 3) ? 16 : 32;
+		radix_sort_pairs_u32(ex, key.ptr(), ids.ptr(), tk.ptr(), tv.ptr(), M, bits);
+	}
+	dbuf<u32> head((size_t) M + 1);
+	merge_cluster_head_fn hf = {s, ids.ptr(), head.ptr(), max_distance};
+	for_each(ex, M, hf);
+	exclusive_scan_u32(ex, head.ptr(), head.ptr(), M);
+	u32 K = 0; head.download(ex, &K, 1, M);
+	dbuf<u32> cluster_start((size_t) K + 1), log_count(1);
+	merge_cluster_start_fn cs = {head.ptr(), cluster_start.ptr(), M, K};
+	for_each(ex, M, cs);
+	const u32 capacity = 1u << 20;
+	merge_log.ensure(3 * (size_t) capacity);
+	log_count.zero(ex, 1);
+	merge_cluster_fn mc = {s, ids.ptr(), cluster_start.ptr(), max_distance, params.max_itd_length, merge_log.ptr(), log_count.ptr(), capacity};
+	for_each(ex, K, mc);
+	u32 n_log = 0; log_count.download(ex, &n_log, 1);
+	if (n_log > capacity) throw arb_error("merge_adjacent: more internal tandem duplication merges than the log can hold");
+	merge_log_n = n_log;
+	return n_log;
+}
+
+void engine::get_merge_log(u32* triples, u32 n) { merge_log.download(ex, triples, 3 * (size_t) std::min(n, merge_log_n)); }
+
+void engine::estimate_evalues(const arb_evalue_inputs& a) {
+	const u32 C = cands.n;
+	if (C == 0) return;
+	if (a.n_genes != annot.n_genes) throw arb_error("arb_estimate_evalues: partner_count must have one entry per gene");
+	dbuf<i32> pc; pc.upload(ex, a.partner_count, a.n_genes);
+	dbuf<double> t_reads, t_intra, t_inter, t1000, t400, trt, tprox;
+	t_reads.upload(ex, a.pow_reads, a.n_read_table); t_intra.upload(ex, a.pow_intragenic, a.n_read_table); t_inter.upload(ex, a.pow_intergenic, a.n_read_table);
+	t1000.upload(ex, a.pow_spliced1000, 1000); t400.upload(ex, a.pow_spliced400, 400); trt.upload(ex, a.pow_read_through, 400000); tprox.upload(ex, a.pow_proximal, 400000);
+	evalue_inputs in;
+	in.partner_count = pc.ptr();
+	in.spliced_breakpoints = a.spliced_breakpoints; in.exonic_breakpoints = a.exonic_breakpoints; in.intronic_breakpoints = a.intronic_breakpoints; in.exonic_intronic_breakpoints = a.exonic_intronic_breakpoints;
+	in.intragenic_duplications = a.intragenic_duplications; in.intragenic_inversions = a.intragenic_inversions; in.spliced_same_gene = a.spliced_same_gene; in.spliced_different_genes = a.spliced_different_genes;
+	in.read_through_fraction = a.read_through_fraction; in.mapped_reads = a.mapped_reads;
+	in.pow_reads = t_reads.ptr(); in.pow_intragenic = t_intra.ptr(); in.pow_intergenic = t_inter.ptr(); in.n_read_table = a.n_read_table;
+	in.pow_spliced1000 = t1000.ptr(); in.pow_spliced400 = t400.ptr(); in.pow_read_through = trt.ptr(); in.pow_proximal = tprox.ptr();
+	in.read_through_penalty = a.read_through_penalty; in.cutoff = 0; in.apply_filter = 0;
+	cand_state s = make_state(cands, NULL, NULL);
+	evalue_fn fn = {s, annot.view(), in};
+	for_each(ex, C, fn);
+	ex.sync();
+}
+
+void engine::filter_relative_support(float cutoff) {
+	cand_state s = make_state(cands, NULL, NULL);
+	relative_support_fn fn = {s, annot.view(), cutoff};
+	for_each(ex, cands.n, fn);
+	ex.sync();
+}
+
+} // namespace arb

@@ -1,0 +1,735 @@
+// events.cpp -- event-level stages (everything after find_fusions, arriba.cpp:415-589). Stages named in the hot path
+// (merge_adjacent, e-value / relative_support, k-mer index, homologs, mismappers) run on the device through the C ABI; the
+// cheap O(#candidates) predicates and recoveries run here, visiting candidates in the reference's iteration order.
+// Each function cites the reference file it reproduces.
+#include "pipeline.h"
+#include "../annot_hd.h"
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <tuple>
+#include <unordered_map>
+
+namespace arb { namespace host {
+
+static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
+
+// ------------------------------------------------------------------------------------------- iteration order
+namespace {
+typedef std::tuple<unsigned int, unsigned int, unsigned short, unsigned short, int, int, bool, bool> cand_key;
+struct cand_key_hash { // value-identical to the reference's recursive tuple hash: h(e0) ^ (H(rest) << 4), H() = 0   (common.hpp:295-314)
+	size_t operator()(const cand_key& k) const {
+		size_t h = 0;
+		h = std::hash<bool>()(std::get<7>(k)) ^ (h << 4);
+		h = std::hash<bool>()(std::get<6>(k)) ^ (h << 4);
+		h = std::hash<int>()(std::get<5>(k)) ^ (h << 4);
+		h = std::hash<int>()(std::get<4>(k)) ^ (h << 4);
+		h = std::hash<unsigned short>()(std::get<3>(k)) ^ (h << 4);
+		h = std::hash<unsigned short>()(std::get<2>(k)) ^ (h << 4);
+		h = std::hash<unsigned int>()(std::get<1>(k)) ^ (h << 4);
+		h = std::hash<unsigned int>()(std::get<0>(k)) ^ (h << 4);
+		return h;
+	}
+};
+}
+
+void event_table::replay_iteration_order() {
+	std::unordered_map<cand_key, u32, cand_key_hash> m;
+	for (u32 k = 0; k < n; ++k) m.insert(std::make_pair(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k]), k));
+	if (m.size() != n) throw std::runtime_error("candidate keys are not unique");
+	order.clear(); order.reserve(n);
+	for (std::unordered_map<cand_key, u32, cand_key_hash>::const_iterator it = m.begin(); it != m.end(); ++it) order.push_back(it->second);
+}
+
+// ------------------------------------------------------------------------------------------- helpers on (table, reference)
+static inline bool overlaps_both(const event_table& e, const refdata& r, u32 k, int which = 0) { // common.hpp:260-264
+	if (which == 1) return e.bp1[k] >= r.genes[e.gene2[k]].start && e.bp1[k] <= r.genes[e.gene2[k]].end;
+	if (which == 2) return e.bp2[k] >= r.genes[e.gene1[k]].start && e.bp2[k] <= r.genes[e.gene1[k]].end;
+	return overlaps_both(e, r, k, 1) || overlaps_both(e, r, k, 2);
+}
+static inline bool both_spliced(const event_table& e, const refdata& r, u32 k) { // common.hpp:280-284
+	return e.spliced1(k) && e.spliced2(k) && ((r.genes[e.gene1[k]].forward == r.genes[e.gene2[k]].forward && e.dir1[k] != e.dir2[k]) || (r.genes[e.gene1[k]].forward != r.genes[e.gene2[k]].forward && e.dir1[k] == e.dir2[k]));
+}
+static inline bool is_intragenic(const event_table& e, const refdata& r, u32 k) { // common.hpp:275-279
+	const gene_rec& g1 = r.genes[e.gene1[k]]; const gene_rec& g2 = r.genes[e.gene2[k]];
+	return e.gene1[k] == e.gene2[k] || (e.bp1[k] >= g2.start - 10000 && e.bp1[k] <= g2.end + 10000 && e.bp2[k] >= g1.start - 10000 && e.bp2[k] <= g1.end + 10000);
+}
+static u32 count_unfiltered(const event_table& e) { u32 c = 0; for (u32 k = 0; k < e.n; ++k) if (e.filter[k] == F_none) ++c; return c; }
+
+void pipeline::log_remaining(const char* what) { std::ostringstream s; s << what << " (remaining=" << count_unfiltered(ev) << ")\n"; log += s.str(); }
+
+// ------------------------------------------------------------------------------------------- device <-> host state
+void pipeline::fetch_candidates() {
+	uint32_t n; uint64_t n1, n2, nd;
+	check(ctx, arb_candidates_size(ctx, &n, &n1, &n2, &nd), "arb_candidates_size");
+	event_table& e = ev;
+	e.n = n;
+	e.gene1.resize(n); e.gene2.resize(n); e.contig1.resize(n); e.contig2.resize(n); e.bp1.resize(n); e.bp2.resize(n); e.dir1.resize(n); e.dir2.resize(n);
+	e.split_reads1.resize(n); e.split_reads2.resize(n); e.discordant_mates.resize(n); e.filter.resize(n); e.bits.resize(n); e.bits2.resize(n);
+	e.anchor1.resize(n); e.anchor2.resize(n); e.evalue.resize(n); e.confidence.assign(n, 0);
+	e.list1_off.resize((size_t) n + 1); e.list2_off.resize((size_t) n + 1); e.listd_off.resize((size_t) n + 1);
+	e.list1.resize(n1 + 1); e.list2.resize(n2 + 1); e.listd.resize(nd + 1);
+	arb_candidates c;
+	c.n = n; c.gene1 = e.gene1.data(); c.gene2 = e.gene2.data(); c.contig1 = e.contig1.data(); c.contig2 = e.contig2.data(); c.breakpoint1 = e.bp1.data(); c.breakpoint2 = e.bp2.data();
+	c.direction1 = e.dir1.data(); c.direction2 = e.dir2.data(); c.split_reads1 = e.split_reads1.data(); c.split_reads2 = e.split_reads2.data(); c.discordant_mates = e.discordant_mates.data();
+	c.filter = e.filter.data(); c.bits = e.bits.data(); c.bits2 = e.bits2.data(); c.anchor_start1 = e.anchor1.data(); c.anchor_start2 = e.anchor2.data(); c.evalue = e.evalue.data();
+	c.list1_off = e.list1_off.data(); c.list2_off = e.list2_off.data(); c.listd_off = e.listd_off.data(); c.list1 = e.list1.data(); c.list2 = e.list2.data(); c.listd = e.listd.data();
+	check(ctx, arb_get_candidates(ctx, &c), "arb_get_candidates");
+	e.list1.resize(n1); e.list2.resize(n2); e.listd.resize(nd);
+	e.replay_iteration_order();
+	// mirror the canonical mate order the device established for listed discordant mates (fusions.cpp:414-421)
+	std::vector<u8> swapped(frags.n);
+	check(ctx, arb_get_slot_swaps(ctx, swapped.data()), "arb_get_slot_swaps");
+	const size_t N = frags.n;
+	for (size_t i = 0; i < N; ++i) if (swapped[i]) {
+		const size_t a = i, b = N + i;
+		std::swap(frags.contig[a], frags.contig[b]); std::swap(frags.start[a], frags.start[b]); std::swap(frags.end[a], frags.end[b]); std::swap(frags.aflags[a], frags.aflags[b]);
+		std::swap(frags.cigar_off[a], frags.cigar_off[b]); std::swap(frags.cigar_cnt[a], frags.cigar_cnt[b]); std::swap(frags.seq_off[a], frags.seq_off[b]); std::swap(frags.seq_len[a], frags.seq_len[b]);
+		std::swap(frags.genes_off[a], frags.genes_off[b]); std::swap(frags.genes_cnt[a], frags.genes_cnt[b]);
+	}
+	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
+	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")\n"; log += s.str();
+}
+
+void pipeline::push_candidate_state() {
+	check(ctx, arb_set_candidate_state(ctx, ev.filter.data(), ev.split_reads1.data(), ev.split_reads2.data(), ev.discordant_mates.data(), ev.evalue.data()), "arb_set_candidate_state");
+}
+void pipeline::pull_candidate_state() {
+	check(ctx, arb_get_candidate_state(ctx, ev.filter.data(), ev.split_reads1.data(), ev.split_reads2.data(), ev.discordant_mates.data(), ev.evalue.data()), "arb_get_candidate_state");
+}
+
+// ------------------------------------------------------------------------------------------- merge_adjacent (device) + ITD list concatenation
+void pipeline::merge_adjacent() {
+	push_candidate_state();
+	uint32_t n_log = 0;
+	check(ctx, arb_merge_adjacent(ctx, 5, &n_log), "arb_merge_adjacent"); // max_distance 5 (arriba.cpp:422)
+	pull_candidate_state();
+	if (n_log > 0) { // internal tandem duplications: the absorbed candidates' read lists are appended, in the order the reference merges
+		std::vector<u32> triples(3 * (size_t) n_log);
+		check(ctx, arb_get_merge_log(ctx, triples.data(), n_log), "arb_get_merge_log");
+		struct entry { u32 winner, loser, pos, seq; };
+		std::vector<entry> es(n_log);
+		for (u32 k = 0; k < n_log; ++k) { es[k].winner = triples[3 * k]; es[k].loser = triples[3 * k + 1]; es[k].pos = triples[3 * k + 2]; es[k].seq = k; }
+		// a winner's entries were logged by one thread in order; winners are replayed by sorted position
+		std::stable_sort(es.begin(), es.end(), [](const entry& a, const entry& b) { return a.pos != b.pos ? a.pos < b.pos : a.seq < b.seq; });
+		std::vector<std::vector<u32> > l1(ev.n), l2(ev.n); std::vector<u8> touched(ev.n, 0);
+		auto materialise = [&](u32 k) { if (!touched[k]) { touched[k] = 1; l1[k].assign(ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); l2[k].assign(ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]); } };
+		for (size_t k = 0; k < es.size(); ++k) {
+			materialise(es[k].winner); materialise(es[k].loser);
+			l1[es[k].winner].insert(l1[es[k].winner].end(), l1[es[k].loser].begin(), l1[es[k].loser].end());
+			l2[es[k].winner].insert(l2[es[k].winner].end(), l2[es[k].loser].begin(), l2[es[k].loser].end());
+		}
+		std::vector<u32> o1((size_t) ev.n + 1, 0), o2((size_t) ev.n + 1, 0), n1, n2;
+		for (u32 k = 0; k < ev.n; ++k) {
+			if (touched[k]) { n1.insert(n1.end(), l1[k].begin(), l1[k].end()); n2.insert(n2.end(), l2[k].begin(), l2[k].end()); }
+			else { n1.insert(n1.end(), ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); n2.insert(n2.end(), ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]); }
+			o1[k + 1] = (u32) n1.size(); o2[k + 1] = (u32) n2.size();
+		}
+		ev.list1.swap(n1); ev.list2.swap(n2); ev.list1_off.swap(o1); ev.list2_off.swap(o2);
+		check(ctx, arb_set_candidate_lists(ctx, ev.list1_off.data(), ev.list1.data(), ev.list2_off.data(), ev.list2.data()), "arb_set_candidate_lists");
+	}
+	log_remaining("Merging adjacent fusion breakpoints");
+}
+
+// ------------------------------------------------------------------------------------------- multimappers (filter_multimappers.cpp)
+static int segment_score(const frag_view& f, const annot_view& an, u32 a, const u8* seq, u32 seq_len, bool revcomp) {
+	const u32 contig = f.contig[a];
+	if (an.contig_len[contig] == 0) return 0;
+	int score = 0; i32 ref = f.start[a]; u32 rp = 0;
+	const u32* c = f.cig(a);
+	const u64 base = an.contig_seq_off[contig];
+	auto gap_at_splice_site = [&](i32 pos, u32 direction) { for (u32 k = 0; k < f.genes_cnt[a]; ++k) if (is_breakpoint_spliced(an, f.genes[f.genes_off[a] + k], direction, pos)) return true; return false; };
+	for (u32 k = 0; k < f.cigar_cnt[a]; ++k) {
+		const u32 op = cig_op(c[k]), len = cig_len(c[k]);
+		switch (op) {
+			case C_S: case C_H: rp += len; break;
+			case C_D: --score; ref += (i32) len; break;
+			case C_N: if (!gap_at_splice_site(ref, DOWNSTREAM) || !gap_at_splice_site(ref + (i32) len, UPSTREAM)) --score; ref += (i32) len; break;
+			case C_I: --score; rp += len; break;
+			case C_EQ: score += (int) len; ref += (i32) len; rp += len; break;
+			case C_X: ref += (i32) len; rp += len; break;
+			case C_M:
+				for (u32 j = 0; j < len; ++j, ++ref, ++rp) {
+					if (rp >= seq_len) continue;
+					const u32 code = revcomp ? nt16_complement(nt16_at(seq, seq_len - 1 - rp)) : nt16_at(seq, rp);
+					if ((u32) ref < an.contig_len[contig] && nt16_char(code) == an.assembly[base + (u32) ref]) ++score;
+				}
+				break;
+			default: break;
+		}
+	}
+	return score;
+}
+static int alignment_score(const frag_view& f, const annot_view& an, u32 i) {
+	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
+	int score = segment_score(f, an, a0, f.sq(a0), f.seq_len[a0], false) + segment_score(f, an, a1, f.sq(a1), f.seq_len[a1], false);
+	if (f.n_aln[i] == 3) {
+		score += segment_score(f, an, a2, f.sq(a1), f.seq_len[a1], f.fwd(a2) != f.fwd(a1));
+		auto any_spliced = [&](u32 a, i32 pos, u32 direction) { for (u32 k = 0; k < f.genes_cnt[a]; ++k) if (is_breakpoint_spliced(an, f.genes[f.genes_off[a] + k], direction, pos)) return true; return false; };
+		if (!any_spliced(a2, f.fwd(a2) ? f.end[a2] : f.start[a2], f.fwd(a2) ? DOWNSTREAM : UPSTREAM) || !any_spliced(a1, f.fwd(a1) ? f.start[a1] : f.end[a1], f.fwd(a1) ? UPSTREAM : DOWNSTREAM)) --score;
+	}
+	return score;
+}
+
+void pipeline::filter_multimappers() {
+	event_table& e = ev;
+	const frag_view f = frags.view(); const annot_view an = ref.host_view();
+	const u32 N = frags.n;
+	// total order "has more support" (filter_multimappers.cpp:79-113); smaller rank = better
+	auto better = [&](u32 x, u32 y) { // is candidate x better than y?
+		if (e.supporting_reads(y) != e.supporting_reads(x)) return e.supporting_reads(y) < e.supporting_reads(x);
+		const bool c1x = ref.genes[e.gene1[x]].is_protein_coding, c1y = ref.genes[e.gene1[y]].is_protein_coding;
+		if (c1x != c1y) return c1x;
+		const bool c2x = ref.genes[e.gene2[x]].is_protein_coding, c2y = ref.genes[e.gene2[y]].is_protein_coding;
+		if (c2x != c2y) return c2x;
+		if (e.contig1[x] != e.contig1[y]) return e.contig1[x] < e.contig1[y];
+		if (e.contig2[x] != e.contig2[y]) return e.contig2[x] < e.contig2[y];
+		if (e.bp1[x] != e.bp1[y]) return e.bp1[x] < e.bp1[y];
+		if (e.bp2[x] != e.bp2[y]) return e.bp2[x] < e.bp2[y];
+		if (e.dir1[x] != e.dir1[y]) return e.dir1[x] < e.dir1[y];
+		if (e.dir2[x] != e.dir2[y]) return e.dir2[x] < e.dir2[y];
+		if (e.gene1[x] != e.gene1[y]) return e.gene1[x] < e.gene1[y];
+		return e.gene2[x] < e.gene2[y];
+	};
+	const u32 NONE = 0xFFFFFFFFu;
+	std::vector<u32> best(N, NONE); // most supported candidate per multimapping fragment
+	auto consider = [&](u32 cand, u32 frag) { if (!(frags.fflags[frag] & FF_MULTIMAPPER)) return; if (best[frag] == NONE || better(cand, best[frag])) best[frag] = cand; };
+	for (u32 k = 0; k < e.n; ++k) {
+		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) consider(k, e.list1[p]);
+		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) consider(k, e.list2[p]);
+		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) consider(k, e.listd[p]);
+	}
+	auto more_support = [&](u32 fa, u32 fb) { // fusion_has_more_support(most_supported[fa], most_supported[fb]) with NULL handling
+		const u32 x = best[fa], y = best[fb];
+		if (x == NONE) return false;
+		if (y == NONE) return true;
+		return better(x, y);
+	};
+	// clusters = maximal runs of fragments sharing the name up to the last comma
+	auto stem = [&](u32 i, u64& len) { const char* s = frags.names.data() + frags.name_off[i]; u64 l = frags.name_off[i + 1] - frags.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; len = k > 0 ? k - 1 : l; return s; };
+	u32 i = 0;
+	while (i < N) {
+		u64 li; const char* si = stem(i, li);
+		u32 j = i + 1;
+		for (; j < N; ++j) { u64 lj; const char* sj = stem(j, lj); if (lj != li || memcmp(si, sj, li) != 0) break; }
+		if (j - i > 1) {
+			u32 best_frag = NONE; int best_score = INT_MIN;
+			for (u32 x = i; x < j; ++x) {
+				const int s = alignment_score(f, an, x);
+				if (best_score < s) { best_frag = x; best_score = s; }
+				else if (best_score == s && more_support(x, best_frag)) best_frag = x;
+			}
+			for (u32 x = i; x < j; ++x) if (x != best_frag && labels[x] == F_none) labels[x] = F_multimappers;
+		}
+		i = j;
+	}
+	for (u32 k = 0; k < e.n; ++k) {
+		if (e.filter[k] != F_none || e.supporting_reads(k) == 0) continue;
+		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) if (labels[e.list1[p]] == F_multimappers && e.split_reads1[k] > 0) --e.split_reads1[k];
+		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) if (labels[e.list2[p]] == F_multimappers && e.split_reads2[k] > 0) --e.split_reads2[k];
+		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) if (labels[e.listd[p]] == F_multimappers && e.discordant_mates[k] > 0) --e.discordant_mates[k];
+		if (e.supporting_reads(k) == 0) e.filter[k] = F_multimappers;
+	}
+	log_remaining("Filtering multi-mapping fusions by alignment score and read support");
+}
+
+// ------------------------------------------------------------------------------------------- e-value (filter_relative_support.cpp)
+void pipeline::estimate_evalues() {
+	event_table& e = ev;
+	// order-dependent global statistics, visited in the reference's iteration order (filter_relative_support.cpp:19-127)
+	std::unordered_map<u32, std::vector<u32> > partners; // sorted unique gene ids
+	{
+		struct key3 { u32 g; i32 a, b; bool operator==(const key3& o) const { return g == o.g && a == o.a && b == o.b; } };
+		struct key3_hash { size_t operator()(const key3& k) const { return ((size_t) k.g * 0x9E3779B97F4A7C15ULL) ^ ((size_t) (u32) k.a << 21) ^ (size_t) (u32) k.b; } };
+		std::unordered_map<key3, char, key3_hash> seen;
+		auto add = [](std::vector<u32>& v, u32 g) { std::vector<u32>::iterator it = std::lower_bound(v.begin(), v.end(), g); if (it == v.end() || *it != g) v.insert(it, g); };
+		for (size_t q = 0; q < e.order.size(); ++q) {
+			const u32 k = e.order[q];
+			if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
+			key3 a = {e.gene2[k], e.bp1[k], e.bp2[k]}; if (!seen[a]++) add(partners[e.gene2[k]], e.gene1[k]);
+			key3 b = {e.gene1[k], e.bp1[k], e.bp2[k]}; if (!seen[b]++) add(partners[e.gene1[k]], e.gene2[k]);
+		}
+	}
+	std::vector<i32> partner_count(ref.genes.size(), 0);
+	for (std::unordered_map<u32, std::vector<u32> >::iterator p1 = partners.begin(); p1 != partners.end(); ++p1)
+		for (size_t j = 0; j < p1->second.size(); ++j)
+			if (p1->second.size() >= partners[p1->second[j]].size()) ++partner_count[p1->first];
+	arb_evalue_inputs in; memset(&in, 0, sizeof(in));
+	u32 spliced = 0, exonic = 0, intronic = 0, mixed = 0, dups = 0, invs = 0, same = 0, diff = 0;
+	std::set<u32> genes_with_fusions, genes_with_read_through;
+	for (u32 k = 0; k < e.n; ++k) {
+		const bool dummy = ref.genes[e.gene1[k]].is_dummy || ref.genes[e.gene2[k]].is_dummy;
+		const u32 split = e.split_reads1[k] + e.split_reads2[k];
+		if (e.filter[k] == F_none && (e.contig1[k] != e.contig2[k] || e.bp2[k] - e.bp1[k] > 500000) && e.supporting_reads(k) >= 2 && split > 0 && !dummy) {
+			if (e.spliced1(k) || e.spliced2(k)) ++spliced; else if (e.exonic1(k) && e.exonic2(k)) ++exonic; else if (!e.exonic1(k) && !e.exonic2(k)) ++intronic; else ++mixed;
+		}
+		if (e.filter[k] == F_none && e.gene1[k] == e.gene2[k] && split >= 2) { if (e.dir1[k] == UPSTREAM && e.dir2[k] == DOWNSTREAM) ++dups; else if (e.dir1[k] == e.dir2[k]) ++invs; }
+		if (e.spliced1(k) && e.spliced2(k)) { if (e.gene1[k] == e.gene2[k]) ++same; else ++diff; }
+		if (!dummy && split > 0) {
+			genes_with_fusions.insert(e.gene1[k]); genes_with_fusions.insert(e.gene2[k]);
+			if (e.is_read_through(k)) { genes_with_read_through.insert(e.gene1[k]); genes_with_read_through.insert(e.gene2[k]); }
+		}
+	}
+	if (spliced + exonic + intronic + mixed < 100 || spliced == 0 || exonic == 0 || intronic == 0 || mixed == 0) { spliced = 10; exonic = 65; intronic = 10; mixed = 15; }
+	if (invs + dups < 100) { invs = 1; dups = 1; }
+	if (same + diff < 100) { same = 0; diff = 100; }
+	const float rt_fraction = genes_with_fusions.empty() ? 0 : 1.0 * genes_with_read_through.size() / genes_with_fusions.size();
+	// pow() tables over the integer domains of the reference's expressions (filter_relative_support.cpp:143-205), same libm
+	u32 max_reads = 0; for (u32 k = 0; k < e.n; ++k) max_reads = std::max(max_reads, e.supporting_reads(k));
+	std::vector<double> t_reads(max_reads + 2), t_intra(max_reads + 2), t_inter(max_reads + 2), t_s1000(1000), t_s400(400), t_rt(400000), t_prox(400000);
+	for (unsigned int nr = 0; nr < t_reads.size(); ++nr) { t_reads[nr] = pow(0.02, nr - 2); t_intra[nr] = pow(nr - 0.42, -2.11) * pow(10, -1.11); t_inter[nr] = pow(nr - 0.73, -2.28) * pow(10, -1.75); }
+	for (int d = 0; d < 1000; ++d) t_s1000[d] = pow(std::max(400, d) / 1000.0, -2);
+	for (int d = 0; d < 400; ++d) t_s400[d] = pow(std::max(1, d) / 400.0, -4.58);
+	for (int d = 0; d < 400000; ++d) { t_rt[d] = pow(std::max(1, d) / 400000.0, -0.63); t_prox[d] = pow(std::max(1, d) / 400000.0, -1.53); }
+	in.partner_count = partner_count.data(); in.n_genes = (uint32_t) partner_count.size();
+	in.spliced_breakpoints = spliced; in.exonic_breakpoints = exonic; in.intronic_breakpoints = intronic; in.exonic_intronic_breakpoints = mixed;
+	in.intragenic_duplications = dups; in.intragenic_inversions = invs; in.spliced_same_gene = same; in.spliced_different_genes = diff;
+	in.read_through_fraction = rt_fraction; in.mapped_reads = istats.mapped_reads;
+	in.pow_reads = t_reads.data(); in.pow_intragenic = t_intra.data(); in.pow_intergenic = t_inter.data(); in.n_read_table = (uint32_t) t_reads.size();
+	in.pow_spliced1000 = t_s1000.data(); in.pow_spliced400 = t_s400.data(); in.pow_read_through = t_rt.data(); in.pow_proximal = t_prox.data();
+	in.read_through_penalty = 1 + pow((rt_fraction - 0.25) * 20, 2);
+	push_candidate_state();
+	check(ctx, arb_estimate_evalues(ctx, &in), "arb_estimate_evalues");
+	pull_candidate_state();
+	log += "Estimating expected number of fusions by random chance (e-value)\n";
+}
+
+void pipeline::filter_relative_support() {
+	push_candidate_state();
+	check(ctx, arb_filter_relative_support(ctx, opt.params.evalue_cutoff), "arb_filter_relative_support");
+	pull_candidate_state();
+	log_remaining("Filtering fusions with an e-value >=cutoff");
+}
+
+// ------------------------------------------------------------------------------------------- cheap predicates
+void pipeline::filter_non_coding_neighbors() { // filter_non_coding_neighbors.cpp
+	for (u32 k = 0; k < ev.n; ++k) if (ev.filter[k] == F_none && !ref.genes[ev.gene1[k]].is_protein_coding && !ref.genes[ev.gene2[k]].is_protein_coding && ev.is_read_through(k)) ev.filter[k] = F_non_coding_neighbors;
+	log_remaining("Filtering fusions with both breakpoints in adjacent non-coding/intergenic regions");
+}
+
+void pipeline::filter_intragenic_both_exonic() { // filter_intragenic_both_exonic.cpp
+	const annot_view an = ref.host_view();
+	const float exonic_fraction = 0.33f; // options.cpp:99
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if ((overlaps_both(ev, ref, k) || ev.gene1[k] == ev.gene2[k]) && ev.exonic1(k) && ev.exonic2(k) && !(ev.spliced1(k) && ev.spliced2(k))) {
+			const int sd = spliced_distance(an, ev.contig1[k], ev.bp1[k], ev.bp2[k], ev.gene1[k]);
+			const int distance = ev.bp2[k] - ev.bp1[k];
+			if (sd == distance || 1.0 * sd / distance < exonic_fraction) ev.filter[k] = F_intragenic_exonic;
+		}
+	}
+	log_remaining("Filtering intragenic fusions with both breakpoints in exonic regions");
+}
+
+void pipeline::filter_min_support() { // filter_min_support.cpp
+	const int min_support = 2; // options.cpp:84
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if ((int) ev.supporting_reads(k) < min_support || (overlaps_both(ev, ref, k) && (int) (ev.split_reads1[k] + ev.split_reads2[k]) < min_support)) ev.filter[k] = F_min_support;
+	}
+	log_remaining("Filtering fusions with <2 supporting reads");
+}
+
+void pipeline::recover_internal_tandem_duplication() { // recover_internal_tandem_duplication.cpp
+	const annot_view an = ref.host_view();
+	const unsigned int max_itd_length = opt.params.max_itd_length, min_supporting_reads = 10, subsampling_threshold = opt.params.subsampling_threshold;
+	const float min_fraction_of_coverage = 0.07f; // options.cpp:105-106
+	unsigned int duplicates = 0;
+	for (u32 i = 0; i < frags.n; ++i) if (labels[i] == F_duplicates) ++duplicates;
+	const float duplication_rate = 1.0 * duplicates / frags.n;
+	auto recoverable = [](u8 f) { return f == F_hairpin || f == F_inconsistently_clipped || f == F_mismatches; };
+	for (size_t q = 0; q < ev.order.size(); ++q) {
+		const u32 k = ev.order[q];
+		const u8 fl = ev.filter[k];
+		if (fl != F_relative_support && fl != F_intragenic_exonic && fl != F_hairpin && fl != F_inconsistently_clipped && fl != F_mismatches) continue;
+		if (!(ev.gene1[k] == ev.gene2[k] && ev.exonic1(k) && ev.exonic2(k) && ev.dir1[k] == UPSTREAM && ev.dir2[k] == DOWNSTREAM && ref.genes[ev.gene1[k]].is_protein_coding &&
+		      ((unsigned int) ev.bp2[k] - (unsigned int) ev.bp1[k]) < max_itd_length)) continue;
+		idset<64> exons;
+		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp2[k], exons);
+		bool coding = false;
+		for (u32 x = 0; x < exons.n; ++x) {
+			const exon_rec& ex = ref.exons[exons.v[x]];
+			if (ex.gene == ev.gene1[k] && ex.cds_start <= ev.bp1[k] + 7 && ex.cds_end + 7 >= ev.bp1[k] && ex.cds_start <= ev.bp2[k] + 7 && ex.cds_end + 7 >= ev.bp2[k]) coding = true;
+		}
+		if (!coding) continue;
+		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		unsigned int split_reads = 0;
+		for (u32 p = ev.list1_off[k]; p < ev.list1_off[k + 1]; ++p) if (labels[ev.list1[p]] == F_none || recoverable(labels[ev.list1[p]])) ++split_reads;
+		for (u32 p = ev.list2_off[k]; p < ev.list2_off[k + 1]; ++p) if (labels[ev.list2[p]] == F_none || recoverable(labels[ev.list2[p]])) ++split_reads;
+		if (split_reads >= min_supporting_reads && (1.0 * split_reads / std::max(cov1, cov2) / (1 - duplication_rate) > min_fraction_of_coverage || split_reads >= subsampling_threshold)) {
+			ev.filter[k] = F_none;
+			for (u32 p = ev.list1_off[k]; p < ev.list1_off[k + 1]; ++p) if (recoverable(labels[ev.list1[p]])) { labels[ev.list1[p]] = F_none; ++ev.split_reads1[k]; }
+			for (u32 p = ev.list2_off[k]; p < ev.list2_off[k + 1]; ++p) if (recoverable(labels[ev.list2[p]])) { labels[ev.list2[p]] = F_none; ++ev.split_reads2[k]; }
+		}
+	}
+	log_remaining("Searching for internal tandem duplications");
+}
+
+void pipeline::filter_both_intronic() { // filter_both_intronic.cpp
+	const u32 N = frags.n;
+	auto has_exonic = [&](const std::vector<u32>& list, u32 lo, u32 hi) {
+		for (u32 p = lo; p < hi; ++p) { const u32 i = list[p]; if (labels[i] != F_none) continue; for (u32 s = 0; s < frags.n_aln[i]; ++s) if (frags.aflags[(size_t) s * N + i] & AF_EXONIC) return true; }
+		return false;
+	};
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if ((ref.contig_flags[ev.contig1[k]] & CF_VIRAL) || (ref.contig_flags[ev.contig2[k]] & CF_VIRAL)) continue;
+		if (!has_exonic(ev.list1, ev.list1_off[k], ev.list1_off[k + 1]) && !has_exonic(ev.list2, ev.list2_off[k], ev.list2_off[k + 1]) && !has_exonic(ev.listd, ev.listd_off[k], ev.listd_off[k + 1])) ev.filter[k] = F_intronic;
+	}
+	log_remaining("Filtering fusions with both breakpoints in intronic/intergenic regions");
+}
+
+// chimeric read count per gene and the expression quantile (filter_in_vitro.cpp:48-83)
+void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold) {
+	const u32 N = frags.n;
+	reads_by_gene.assign(ref.genes.size(), 0); present.assign(ref.genes.size(), 0);
+	for (u32 i = 0; i < N; ++i) {
+		const size_t a = i, b = (size_t) (frags.n_aln[i] == 2 ? 1 : 2) * N + i;
+		for (u32 g = 0; g < frags.genes_cnt[a]; ++g) { ++reads_by_gene[frags.genes[frags.genes_off[a] + g]]; present[frags.genes[frags.genes_off[a] + g]] = 1; }
+		for (u32 g = 0; g < frags.genes_cnt[b]; ++g) { ++reads_by_gene[frags.genes[frags.genes_off[b] + g]]; present[frags.genes[frags.genes_off[b] + g]] = 1; }
+	}
+	std::vector<u32> genes;
+	for (u32 g = 0; g < present.size(); ++g) if (present[g]) genes.push_back(g);
+	threshold = 0;
+	if (genes.empty()) return;
+	const float quantile_f = 0.998f; // options.cpp:98
+	unsigned int q = static_cast<int>(floor(quantile_f * genes.size()));
+	if (q >= genes.size()) q = genes.size() - 1;
+	// the q-th element under (reads, id) ordering is unique, whatever nth_element's internal order
+	std::nth_element(genes.begin(), genes.begin() + q, genes.end(), [&](u32 x, u32 y) { return reads_by_gene[x] != reads_by_gene[y] ? reads_by_gene[x] < reads_by_gene[y] : x < y; });
+	threshold = reads_by_gene[genes[q]];
+}
+
+void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
+	const annot_view an = ref.host_view();
+	const u32 N = frags.n;
+	const frag_view f = frags.view();
+	std::map<std::pair<u32, u32>, unsigned int> exonic_breakpoints;
+	for (u32 k = 0; k < ev.n; ++k)
+		if (ev.gene1[k] != ev.gene2[k] && !ev.spliced1(k) && !ev.spliced2(k) && ev.exonic1(k) && ev.exonic2(k) && ev.n_list1(k) + ev.n_list2(k) > 0 && ev.filter[k] != F_merge_adjacent && ev.filter[k] != F_uninteresting_contigs) {
+			++exonic_breakpoints[std::make_pair(ev.gene1[k], ev.gene2[k])]; ++exonic_breakpoints[std::make_pair(ev.gene2[k], ev.gene1[k])];
+		}
+	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
+	find_top_expressed_genes(reads_by_gene, present, threshold);
+	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
+		unsigned int highest = reads_by_gene[gene];
+		idset<64> genes; query_index(gene_index(an), contig, bp, bp, genes);
+		for (u32 x = 0; x < genes.n; ++x) if (reads_by_gene[genes.v[x]] > highest) { highest = reads_by_gene[genes.v[x]]; gene = genes.v[x]; }
+		return gene;
+	};
+	auto pair_count = [&](u32 a, u32 b) { std::map<std::pair<u32, u32>, unsigned int>::iterator it = exonic_breakpoints.find(std::make_pair(a, b)); return it == exonic_breakpoints.end() ? 0u : it->second; };
+	for (u32 k = 0; k < ev.n; ++k) {
+		const u8 fl = ev.filter[k];
+		if (fl != F_none && !((ev.spliced1(k) || ev.spliced2(k)) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) continue;
+		float rt = 0;
+		if (!ev.exonic1(k)) rt += 0.5; else if (!ev.spliced1(k)) rt += 1;
+		if (!ev.exonic2(k)) rt += 0.5; else if (!ev.spliced2(k)) rt += 1;
+		unsigned int clipped1 = 0, clipped2 = 0;
+		for (u32 p = ev.listd_off[k]; p < ev.listd_off[k + 1]; ++p) {
+			const u32 i = ev.listd[p];
+			if (labels[i] != F_none) continue;
+			for (u32 s = 0; s < frags.n_aln[i]; ++s) {
+				const u32 a = (u32) ((size_t) s * N + i);
+				if (f.fwd(a) && f.postclip(a) >= 3) { if (f.contig[a] == ev.contig1[k] && f.end[a] == ev.bp1[k]) ++clipped1; else if (f.contig[a] == ev.contig2[k] && f.end[a] == ev.bp2[k]) ++clipped2; }
+				else if (!f.fwd(a) && f.preclip(a) >= 3) { if (f.contig[a] == ev.contig1[k] && f.start[a] == ev.bp1[k]) ++clipped1; else if (f.contig[a] == ev.contig2[k] && f.start[a] == ev.bp2[k]) ++clipped2; }
+			}
+		}
+		const unsigned int total_split = std::min(clipped1, clipped2) + ev.split_reads1[k] + ev.split_reads2[k];
+		const u32 g1 = higher_expressed(ev.contig1[k], ev.bp1[k], ev.gene1[k]), g2 = higher_expressed(ev.contig2[k], ev.bp2[k], ev.gene2[k]);
+		const unsigned int x1 = reads_by_gene[g1], x2 = reads_by_gene[g2];
+		const unsigned int exonic_bp = std::max(pair_count(g1, g2), pair_count(ev.gene1[k], ev.gene2[k]));
+		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const unsigned int sup = ev.supporting_reads(k);
+		if (total_split <= 2 + 0.0001 * (x1 + x2) &&
+		    (total_split * 2 <= ev.discordant_mates[k] || total_split <= 2) &&
+		    x1 + x2 > threshold &&
+		    !(sup >= 10 && ((int) sup * 4) >= std::max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup && (ev.spliced1(k) || ev.spliced2(k)) && ((ev.spliced1(k) || !ev.exonic1(k)) && (ev.spliced2(k) || !ev.exonic2(k)))) &&
+		    (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || exonic_bp > 8 || sup <= 1))
+			ev.filter[k] = F_in_vitro;
+	}
+	log_remaining("Filtering in vitro-generated fusions");
+}
+
+// recover_both_spliced.cpp:15-62
+unsigned int pipeline::spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold) {
+	const annot_view an = ref.host_view();
+	const int max_exon_size = 1000; const unsigned int max_coverage = 1000; // arriba.cpp:492
+	if (reads_by_gene[ev.gene1[k]] > threshold || reads_by_gene[ev.gene2[k]] > threshold)
+		return (both_spliced(ev, ref, k) && ev.discordant_mates[k] <= ev.split_reads1[k] + ev.split_reads2[k]) ? 1 : 0;
+	if (!both_spliced(ev, ref, k)) {
+		const unsigned int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const unsigned int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		if (cov1 + cov2 > ev.supporting_reads(k) * max_coverage) return 0;
+		idset<64> exons;
+		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp1[k], exons);
+		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
+		query_index(exon_index(an), ev.contig2[k], ev.bp2[k], ev.bp2[k], exons);
+		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
+	}
+	unsigned int multi = 0, unique = 0;
+	auto scan = [&](const std::vector<u32>& list, u32 lo, u32 hi) { for (u32 p = lo; p < hi; ++p) { if (frags.fflags[list[p]] & FF_MULTIMAPPER) ++multi; else if (labels[list[p]] == F_none) ++unique; } };
+	scan(ev.list1, ev.list1_off[k], ev.list1_off[k + 1]); scan(ev.list2, ev.list2_off[k], ev.list2_off[k + 1]); scan(ev.listd, ev.listd_off[k], ev.listd_off[k + 1]);
+	if (multi >= 0.5 * (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) return 0;
+	if (unique == 0) return 1;
+	return unique;
+}
+
+void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
+	const unsigned int max_fusions_to_recover = 200;
+	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
+	find_top_expressed_genes(reads_by_gene, present, threshold);
+	typedef std::tuple<u32, u32, bool, bool> pair_key;
+	std::map<pair_key, std::vector<u32> > by_pair;
+	for (size_t q = 0; q < ev.order.size(); ++q) {
+		const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
+		if (fl == F_merge_adjacent) continue;
+		if (fl == F_none || fl == F_in_vitro || fl == F_intronic || fl == F_relative_support || fl == F_min_support || (fl == F_inconsistently_clipped && both_spliced(ev, ref, k)))
+			if (spliced_support(k, reads_by_gene, threshold) > 0) by_pair[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])].push_back(k);
+	}
+	std::map<unsigned int, unsigned int> recovered_by_reads;
+	unsigned int min_supporting_reads = 1;
+	for (int mode = 0; mode <= 1; ++mode) {
+		for (size_t q = 0; q < ev.order.size(); ++q) {
+			const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
+			if (fl == F_none) continue;
+			if (!both_spliced(ev, ref, k)) continue;
+			if (ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) continue;
+			if (ev.is_read_through(k)) continue;
+			if (fl != F_relative_support && fl != F_min_support && fl != F_in_vitro) continue;
+			unsigned int sum = 0;
+			std::map<pair_key, std::vector<u32> >::iterator same = by_pair.find(pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]));
+			if (same != by_pair.end()) for (size_t x = 0; x < same->second.size(); ++x) sum += spliced_support(same->second[x], reads_by_gene, threshold);
+			std::map<pair_key, std::vector<u32> >::iterator rec = by_pair.find(pair_key(ev.gene1[k], ev.gene2[k], !(bool) ev.dir1[k], !(bool) ev.dir2[k]));
+			if (rec != by_pair.end()) for (size_t x = 0; x < rec->second.size(); ++x) {
+				const u32 o = rec->second[x];
+				if (ev.is_read_through(o)) continue;
+				if (both_spliced(ev, ref, o) || (((ev.dir1[k] == DOWNSTREAM) != (ev.bp1[k] > ev.bp1[o])) && ((ev.dir2[k] == DOWNSTREAM) != (ev.bp2[k] > ev.bp2[o])))) sum += spliced_support(o, reads_by_gene, threshold);
+			}
+			if (sum >= 2) {
+				if (mode == 1) {
+					const unsigned int proximal = (ev.contig1[k] == ev.contig2[k] && std::abs(ev.bp1[k] - ev.bp2[k]) < 1000000) ? 1 : 0;
+					if (ev.supporting_reads(k) >= min_supporting_reads + proximal) ev.filter[k] = F_none;
+				} else ++recovered_by_reads[ev.supporting_reads(k)];
+			}
+		}
+		if (mode == 0) {
+			unsigned int would = 0;
+			for (std::map<unsigned int, unsigned int>::reverse_iterator it = recovered_by_reads.rbegin(); it != recovered_by_reads.rend(); ++it) { would += it->second; if (would >= max_fusions_to_recover) { min_supporting_reads = it->first + 1; break; } }
+		}
+	}
+	log_remaining("Searching for fusions with spliced split reads");
+}
+
+void pipeline::select_best() { // select_best.cpp
+	auto rank = [&](u32 k) { const bool s1 = ev.split_reads1[k] != 0, s2 = ev.split_reads2[k] != 0, d = ev.discordant_mates[k] != 0; return (s1 && s2) ? 3u : ((s1 || s2) && d) ? 2u : (s1 || s2) ? 1u : 0u; };
+	typedef std::tuple<u32, u32, bool, bool> pair_key;
+	std::map<pair_key, u32> best;
+	for (size_t q = 0; q < ev.order.size(); ++q) {
+		const u32 k = ev.order[q];
+		if (ev.filter[k] != F_none) continue;
+		const pair_key key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]);
+		std::map<pair_key, u32>::iterator it = best.find(key);
+		if (it == best.end()) { best[key] = k; continue; }
+		const u32 b = it->second;
+		bool take = false;
+		if (rank(k) > rank(b)) take = true;
+		else if (rank(k) == rank(b)) {
+			if (ev.supporting_reads(k) > ev.supporting_reads(b)) take = true;
+			else if (ev.supporting_reads(k) == ev.supporting_reads(b)) {
+				if ((ev.exonic1(k) && !ev.exonic1(b)) || (ev.exonic2(k) && !ev.exonic2(b))) take = true;
+				else if ((!ev.exonic1(b) || ev.exonic1(k) == ev.exonic1(b)) && (!ev.exonic2(b) || ev.exonic2(k) == ev.exonic2(b))) {
+					if ((ev.dir1[k] == DOWNSTREAM && ev.bp1[k] > ev.bp1[b]) || (ev.dir1[k] == UPSTREAM && ev.bp1[k] < ev.bp1[b])) take = true;
+					else if (ev.bp1[k] == ev.bp1[b]) { if ((ev.dir2[k] == DOWNSTREAM && ev.bp2[k] > ev.bp2[b]) || (ev.dir2[k] == UPSTREAM && ev.bp2[k] < ev.bp2[b])) take = true; }
+				}
+			}
+		}
+		if (take) it->second = k;
+	}
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if (best[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])] != k) ev.filter[k] = F_select_best;
+	}
+	log_remaining("Selecting best breakpoints from genes with multiple breakpoints");
+}
+
+void pipeline::filter_marginal_read_through() { // filter_marginal_read_through.cpp
+	const float margin = 0.01f, min_vaf = 0.07f;
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (!(ev.filter[k] == F_none && ev.is_read_through(k))) continue;
+		const gene_rec& g1 = ref.genes[ev.gene1[k]]; const gene_rec& g2 = ref.genes[ev.gene2[k]];
+		double donor = 1, acceptor = 1;
+		if (!g1.is_dummy && g1.forward && ev.dir1[k] == DOWNSTREAM) donor = 1.0 * (ev.bp1[k] - g1.start) / (g1.end - g1.start);
+		else if (!g2.is_dummy && !g2.forward && ev.dir2[k] == UPSTREAM) donor = 1.0 * (g2.end - ev.bp2[k]) / (g2.end - g2.start);
+		else if (!g1.is_dummy && !g1.forward && ev.dir1[k] == DOWNSTREAM) acceptor = 1.0 * (ev.bp1[k] - g1.start) / (g1.end - g1.start);
+		else if (!g2.is_dummy && g2.forward && ev.dir2[k] == UPSTREAM) acceptor = 1.0 * (g2.end - ev.bp2[k]) / (g2.end - g2.start);
+		else continue;
+		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		if (donor > 1 - margin && acceptor > 1 - margin && ev.supporting_reads(k) < min_vaf * std::max(cov1, cov2)) ev.filter[k] = F_marginal_read_through;
+	}
+	log_remaining("Filtering read-through fusions with breakpoints near the gene boundary");
+}
+
+void pipeline::recover_many_spliced() { // recover_many_spliced.cpp
+	const unsigned int min_spliced_events = 4; // options.cpp:94
+	auto eligible_filter = [](u8 f) { return f == F_inconsistently_clipped || f == F_relative_support || f == F_min_support || f == F_select_best; };
+	std::map<std::pair<u32, u32>, std::set<std::pair<i32, i32> > > spliced;
+	for (u32 k = 0; k < ev.n; ++k)
+		if (!ev.is_read_through(k) && (ev.spliced1(k) || ev.spliced2(k)) && ev.gene1[k] != ev.gene2[k] && !overlaps_both(ev, ref, k) && (ev.filter[k] == F_none || eligible_filter(ev.filter[k])))
+			spliced[std::make_pair(ev.gene1[k], ev.gene2[k])].insert(std::make_pair(ev.bp1[k] / 10, ev.bp2[k] / 10));
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] == F_none) continue;
+		if (ev.is_read_through(k) || ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) continue;
+		if (eligible_filter(ev.filter[k]) && (ev.spliced1(k) || ev.spliced2(k)) && spliced[std::make_pair(ev.gene1[k], ev.gene2[k])].size() >= min_spliced_events) ev.filter[k] = F_none;
+	}
+	log_remaining("Searching for fusions with >=4 spliced events");
+}
+
+void pipeline::filter_short_anchor() { // filter_short_anchor.cpp
+	const unsigned int min_length = 23; // options.cpp:87
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if (!(ev.spliced1(k) && ev.spliced2(k)) && ((unsigned int) std::abs(ev.anchor1[k] - ev.bp1[k]) < min_length || (unsigned int) std::abs(ev.anchor2[k] - ev.bp2[k]) < min_length)) ev.filter[k] = F_short_anchor;
+	}
+	log_remaining("Filtering fusions with anchors <=23nt");
+}
+
+float pipeline::intronic_fraction(u32 gene) { // filter_end_to_end.cpp:9-25
+	const gene_rec& g = ref.genes[gene];
+	const region_index& ix = ref.exon_index;
+	unsigned int intronic = 0; i32 previous = g.start;
+	const u32 lo = ix.begin[g.contig], hi = ix.begin[g.contig + 1];
+	for (u32 r = (u32) (std::lower_bound(ix.end.begin() + lo, ix.end.begin() + hi, g.start) - ix.end.begin()); r < hi && ix.end[r] <= g.end; ++r)
+		for (u32 x = ix.off[r]; x < ix.off[r + 1]; ++x) {
+			const exon_rec& ex = ref.exons[ix.items[x]];
+			if (ex.gene != gene) continue;
+			if (previous < ex.start) intronic += ex.start - previous;
+			if (previous < ex.end) previous = ex.end + 1;
+			break;
+		}
+	return ((float) intronic) / (g.end - g.start + 1);
+}
+
+void pipeline::filter_end_to_end() { // filter_end_to_end.cpp:27-78
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		if ((ref.contig_flags[ev.contig1[k]] & CF_VIRAL) || (ref.contig_flags[ev.contig2[k]] & CF_VIRAL)) continue;
+		if (!ev.is_read_through(k) && ev.gene1[k] != ev.gene2[k] && (ev.spliced1(k) || ev.spliced2(k))) continue;
+		const u32 s1 = ev.split_reads1[k], s2 = ev.split_reads2[k], d = ev.discordant_mates[k];
+		if (!(d + s1 == 0 || d + s2 == 0 || s1 + s2 == 0 || (overlaps_both(ev, ref, k) && (s1 == 0 || s2 == 0)))) continue;
+		const gene_rec& g1 = ref.genes[ev.gene1[k]]; const gene_rec& g2 = ref.genes[ev.gene2[k]];
+		if (!((g1.is_dummy || (g1.forward && ev.dir1[k] == UPSTREAM) || (!g1.forward && ev.dir1[k] == DOWNSTREAM)) && (g2.is_dummy || (g2.forward && ev.dir2[k] == UPSTREAM) || (!g2.forward && ev.dir2[k] == DOWNSTREAM)))) continue;
+		if (d < 10 || (ev.contig1[k] == ev.contig2[k] && std::abs(ev.bp1[k] - ev.bp2[k]) < 1000000) ||
+		    (ev.exonic1(k) && ev.exonic2(k) && intronic_fraction(ev.gene1[k]) > 0.66f && intronic_fraction(ev.gene2[k]) > 0.66f)) ev.filter[k] = F_end_to_end;
+	}
+	log_remaining("Filtering end-to-end fusions with low support");
+}
+
+void pipeline::filter_no_coverage() { // filter_no_coverage.cpp
+	const annot_view an = ref.host_view();
+	const int scan_range = 200;
+	for (u32 k = 0; k < ev.n; ++k) {
+		if (ev.filter[k] != F_none) continue;
+		const u32 s1 = ev.split_reads1[k], s2 = ev.split_reads2[k], d = ev.discordant_mates[k];
+		if (!ev.is_read_through(k)) {
+			if (s1 + s2 != 0 && s1 + d != 0 && s2 + d != 0) continue;
+			if (ev.spliced1(k) || ev.spliced2(k)) continue;
+		} else if (ev.spliced1(k) && ev.spliced2(k)) continue;
+		bool discard = false;
+		for (int side = 1; side <= 2 && !discard; ++side) {
+			const u16 contig = side == 1 ? ev.contig1[k] : ev.contig2[k]; const i32 bp = side == 1 ? ev.bp1[k] : ev.bp2[k];
+			const u32 gene = side == 1 ? ev.gene1[k] : ev.gene2[k]; const u32 dir = side == 1 ? ev.dir1[k] : ev.dir2[k]; const i32 anchor = side == 1 ? ev.anchor1[k] : ev.anchor2[k];
+			idset<64> exons; query_index(exon_index(an), contig, bp, bp, exons);
+			bool terminal = false;
+			for (u32 x = 0; x < exons.n && !terminal; ++x) { const exon_rec& ex = ref.exons[exons.v[x]]; if (ex.gene == gene && (ex.prev == -1 || ex.next == -1)) terminal = true; }
+			if (terminal) continue;
+			i32 start, end;
+			if (dir == UPSTREAM) { start = bp; if (s1 + s2 == 0) start -= scan_range; end = std::max(bp + scan_range, anchor); }
+			else { start = std::min(bp - scan_range, anchor); end = bp; if (s1 + s2 == 0) end += scan_range; }
+			if ((dir == UPSTREAM && !coverage.fragment_starts_here(contig, start, end)) || (dir == DOWNSTREAM && !coverage.fragment_ends_here(contig, start, end))) discard = true;
+		}
+		if (discard) ev.filter[k] = F_no_coverage;
+	}
+	log_remaining("Filtering fusions with no coverage around the breakpoints");
+}
+
+void pipeline::recover_isoforms() { // recover_isoforms.cpp
+	typedef std::tuple<u32, u32, bool, bool> pair_key;
+	std::map<pair_key, u32> fused; // last unfiltered candidate in iteration order wins
+	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; if (ev.filter[k] == F_none) fused[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])] = k; }
+	for (size_t q = 0; q < ev.order.size(); ++q) {
+		const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
+		if (fl == F_none) continue;
+		if (fl == F_merge_adjacent || fl == F_blacklist || fl == F_end_to_end || fl == F_duplicates || ev.gene1[k] == ev.gene2[k]) continue;
+		if (!(ev.spliced1(k) && ev.spliced2(k))) continue;
+		std::map<pair_key, u32>::iterator it = fused.find(pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]));
+		if (it != fused.end() && (std::abs(ev.bp1[it->second] - ev.bp1[k]) > 2 || std::abs(ev.bp2[it->second] - ev.bp2[k]) > 2)) ev.filter[k] = F_none;
+	}
+	log_remaining("Searching for additional isoforms");
+}
+
+void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no structural-variant input: closest_genomic_breakpoint = -1)
+	std::vector<std::vector<u32> > by_gene(ref.genes.size());
+	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; by_gene[ev.gene1[k]].push_back(k); by_gene[ev.gene2[k]].push_back(k); }
+	enum { LOW = 0, MEDIUM = 1, HIGH = 2 };
+	for (u32 k = 0; k < ev.n; ++k) {
+		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const float coverage_fraction = ((float) (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) / std::max(1, std::max(cov1, cov2));
+		if (ev.filter[k] != F_none) { ev.confidence[k] = LOW; continue; }
+		int conf = HIGH;
+		const u32 s1 = ev.split_reads1[k], s2 = ev.split_reads2[k], d = ev.discordant_mates[k], sup = s1 + s2 + d;
+		if (ev.evalue[k] > 0.3 || sup < 2) conf = LOW;
+		else if (ev.is_read_through(k)) {
+			conf = LOW;
+			if (((s1 > 0 && s2 > 0) || (s1 > 0 && d > 0) || (s2 > 0 && d > 0)) && sup >= 10) conf = (s1 + s2 >= 10 && coverage_fraction > 0.07) ? HIGH : MEDIUM;
+			else {
+				unsigned int deletions = 0;
+				for (int side = 0; side < 2; ++side) {
+					const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[k] : ev.gene2[k]];
+					for (size_t x = 0; x < v.size(); ++x) {
+						const u32 o = v[x];
+						if (ev.filter[o] == F_none && ev.split_reads1[o] + ev.split_reads2[o] > 0 && ev.dir1[o] == DOWNSTREAM && ev.dir2[o] == UPSTREAM &&
+						    ((ev.gene1[o] == ev.gene1[k] && ev.gene2[o] != ev.gene2[k]) || (ev.gene1[o] != ev.gene1[k] && ev.gene2[o] == ev.gene2[k])) &&
+						    (ev.bp1[o] != ev.bp1[k] || ev.bp2[o] != ev.bp2[k]) && ev.bp2[o] > ev.bp1[k] && ev.bp1[o] < ev.bp2[k]) ++deletions;
+					}
+				}
+				if (deletions >= 1) conf = MEDIUM;
+			}
+		} else if (overlaps_both(ev, ref, k) || ev.gene1[k] == ev.gene2[k]) {
+			conf = LOW;
+			if (s1 + s2 > 0) {
+				if (!ev.exonic1(k) && !ev.exonic2(k)) conf = (s1 > 0 && s2 > 0) ? HIGH : MEDIUM;
+				else if (!ev.exonic1(k) || !ev.exonic2(k)) conf = (s1 > 3 && s2 > 3) ? HIGH : MEDIUM;
+			}
+		}
+		if (conf == LOW && ev.gene1[k] == ev.gene2[k] && ev.exonic1(k) && ev.exonic2(k) && !ev.spliced1(k) && !ev.spliced2(k) && ev.bp2[k] - ev.bp1[k] < 100 && s1 > 0 && s2 > 0 && s1 + s2 >= 10 &&
+		    coverage_fraction > 0.15 && ev.dir1[k] == UPSTREAM && ev.dir2[k] == DOWNSTREAM) conf = MEDIUM;
+		if (conf < HIGH && ev.spliced1(k) && ev.spliced2(k) && !ev.is_read_through(k) && ev.gene1[k] != ev.gene2[k]) {
+			unsigned int n_spliced = 0;
+			for (int side = 0; side < 2; ++side) {
+				const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[k] : ev.gene2[k]];
+				for (size_t x = 0; x < v.size(); ++x) { const u32 o = v[x]; if (ev.gene1[o] == ev.gene1[k] && ev.gene2[o] == ev.gene2[k] && ev.spliced1(o) && ev.spliced2(o) && (std::abs(ev.bp1[o] - ev.bp1[k]) > 2 || std::abs(ev.bp2[o] - ev.bp2[k]) > 2)) ++n_spliced; }
+			}
+			if (n_spliced > 0) ++conf;
+		}
+		if (ev.gene1[k] != ev.gene2[k] && conf > LOW && !ev.spliced1(k) && !ev.spliced2(k)) --conf;
+		if (s1 > 20 && s2 > 20 && sup > 60) conf = HIGH;
+		if (conf > LOW) {
+			if (s1 + s2 == 0 || s1 + d == 0 || s2 + d == 0) --conf;
+			else if ((s1 + s2) * 20 < d) --conf;
+			else if (ev.evalue[k] > 0.2 || coverage_fraction < 0.01) conf = MEDIUM;
+		}
+		ev.confidence[k] = (u8) conf;
+	}
+	log += "Assigning confidence scores to events\n";
+}
+
+}} // namespace

@@ -110,4 +110,19 @@ int arb_pipeline_coverage(arb_pipeline* x, uint32_t contig, const uint16_t** cov
 	PIPE_END(x)
 }
 
+int arb_pipeline_events(arb_pipeline* x, int last_stage) { PIPE_BEGIN(x) x->p.events_until(last_stage); PIPE_END(x) }
+
+int arb_pipeline_candidates(arb_pipeline* x, arb_candidates* c, const uint32_t** order, const uint8_t** confidence, const uint8_t** labels) {
+	PIPE_BEGIN(x)
+	event_table& e = x->p.ev;
+	c->n = e.n; c->gene1 = e.gene1.data(); c->gene2 = e.gene2.data(); c->contig1 = e.contig1.data(); c->contig2 = e.contig2.data(); c->breakpoint1 = e.bp1.data(); c->breakpoint2 = e.bp2.data();
+	c->direction1 = e.dir1.data(); c->direction2 = e.dir2.data(); c->split_reads1 = e.split_reads1.data(); c->split_reads2 = e.split_reads2.data(); c->discordant_mates = e.discordant_mates.data();
+	c->filter = e.filter.data(); c->bits = e.bits.data(); c->bits2 = e.bits2.data(); c->anchor_start1 = e.anchor1.data(); c->anchor_start2 = e.anchor2.data(); c->evalue = e.evalue.data();
+	c->list1_off = e.list1_off.data(); c->list2_off = e.list2_off.data(); c->listd_off = e.listd_off.data(); c->list1 = e.list1.data(); c->list2 = e.list2.data(); c->listd = e.listd.data();
+	if (order) *order = e.order.data();
+	if (confidence) *confidence = e.confidence.data();
+	if (labels) *labels = x->p.labels.data();
+	PIPE_END(x)
+}
+
 } // extern "C"

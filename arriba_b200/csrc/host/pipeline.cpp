@@ -130,6 +130,34 @@ void pipeline::find_fusions() {
 	t_find_fusions = now_s() - t0;
 }
 
-void pipeline::run_all() { load_reference(); ingest(); annotate(); upload(); read_filters(); fragment_length(); find_fusions(); }
+void pipeline::events_until(int last) { // arriba.cpp:420-545, filters enabled by default
+	const u64 m = opt.params.filter_mask;
+	auto on = [&](int f) { return (m >> f) & 1; };
+	for (int s = events_done + 1; s <= last && s < EV_COUNT; ++s) {
+		switch (s) {
+			case EV_FETCH: fetch_candidates(); break;
+			case EV_MERGE_ADJACENT: if (on(F_merge_adjacent)) merge_adjacent(); break;
+			case EV_MULTIMAPPERS: if (on(F_multimappers)) filter_multimappers(); break;
+			case EV_EVALUE: estimate_evalues(); break;
+			case EV_NON_CODING_NEIGHBORS: if (on(F_non_coding_neighbors)) filter_non_coding_neighbors(); break;
+			case EV_INTRAGENIC_EXONIC: if (on(F_intragenic_exonic)) filter_intragenic_both_exonic(); break;
+			case EV_MIN_SUPPORT: if (on(F_min_support)) filter_min_support(); break;
+			case EV_RELATIVE_SUPPORT: if (on(F_relative_support)) filter_relative_support(); break;
+			case EV_ITD: if (on(F_internal_tandem_duplication)) recover_internal_tandem_duplication(); break;
+			case EV_INTRONIC: if (on(F_intronic)) filter_both_intronic(); break;
+			case EV_IN_VITRO: if (on(F_in_vitro)) filter_in_vitro(); break;
+			case EV_SPLICED: if (on(F_spliced)) recover_both_spliced(); break;
+			case EV_SELECT_BEST: if (on(F_select_best)) select_best(); break;
+			case EV_MARGINAL_READ_THROUGH: if (on(F_marginal_read_through)) filter_marginal_read_through(); break;
+			case EV_MANY_SPLICED: if (on(F_many_spliced)) recover_many_spliced(); break;
+			case EV_SHORT_ANCHOR: if (on(F_short_anchor)) filter_short_anchor(); break;
+			case EV_END_TO_END: if (on(F_end_to_end)) filter_end_to_end(); break;
+			case EV_NO_COVERAGE: if (on(F_no_coverage)) filter_no_coverage(); break;
+		}
+		events_done = s;
+	}
+}
+
+void pipeline::run_all() { load_reference(); ingest(); annotate(); upload(); read_filters(); fragment_length(); find_fusions(); events_until(EV_COUNT - 1); }
 
 }} // namespace

@@ -6,6 +6,7 @@
 #include <vector>
 #include "refdata.h"
 #include "ingest.h"
+#include "events.h"
 #include "../../../include/arriba_b200.h"
 
 namespace arb { namespace host {
@@ -27,9 +28,10 @@ struct pipeline {
 	arb_ctx* ctx;
 	int strandedness; i32 max_mate_gap; float read_length_mean, mate_gap_mean, mate_gap_stddev; bool fragment_length_ok;
 	std::vector<u8> labels, early;
+	event_table ev;
 	std::string log; // the reference's progress lines (arriba.cpp:61-66 style, without time stamps)
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
-	pipeline(): ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) {}
+	pipeline(): events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) {}
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -38,8 +40,22 @@ struct pipeline {
 	void read_filters();
 	void fragment_length();
 	void find_fusions();
+	// event level (events.cpp); device stages go through the C ABI
+	void fetch_candidates(); void push_candidate_state(); void pull_candidate_state(); void log_remaining(const char* what);
+	void merge_adjacent(); void filter_multimappers(); void estimate_evalues(); void filter_relative_support();
+	void filter_non_coding_neighbors(); void filter_intragenic_both_exonic(); void filter_min_support(); void recover_internal_tandem_duplication();
+	void filter_both_intronic(); void filter_in_vitro(); void recover_both_spliced(); void select_best(); void filter_marginal_read_through();
+	void recover_many_spliced(); void filter_short_anchor(); void filter_end_to_end(); void filter_no_coverage(); void recover_isoforms(); void assign_confidence();
+	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold);
+	unsigned int spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold);
+	float intronic_fraction(u32 gene);
+	void events_until(int last_stage); // runs the event-level chain up to and including `last_stage` (EV_* below)
+	int events_done;
 	void run_all();
 };
+
+enum { EV_FETCH = 0, EV_MERGE_ADJACENT, EV_MULTIMAPPERS, EV_EVALUE, EV_NON_CODING_NEIGHBORS, EV_INTRAGENIC_EXONIC, EV_MIN_SUPPORT, EV_RELATIVE_SUPPORT,
+       EV_ITD, EV_INTRONIC, EV_IN_VITRO, EV_SPLICED, EV_SELECT_BEST, EV_MARGINAL_READ_THROUGH, EV_MANY_SPLICED, EV_SHORT_ANCHOR, EV_END_TO_END, EV_NO_COVERAGE, EV_COUNT };
 
 int detect_strandedness(pipeline& p);
 void assign_strands(pipeline& p, int strandedness);

@@ -40,29 +40,58 @@ struct exec_ctx {
 #endif
 };
 
+// ------------------------------------------------------------------------------------------- device memory pool
+// Stage-local scratch buffers come and go many times per run; cudaMalloc/cudaFree would serialise the stream each time
+// (cudaFree synchronises the device). Freed blocks are kept in size classes and reused; everything is returned to the driver
+// by pool_trim() (context destruction).
+#ifdef ARB_DEVICE_BUILD
+struct device_pool {
+	std::vector<std::pair<size_t, void*> > free_blocks;
+	size_t held_bytes;
+	device_pool(): held_bytes(0) {}
+	static size_t size_class(size_t bytes) { size_t c = 512; while (c < bytes) c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); return c; }
+	void* get(size_t bytes, size_t& granted) {
+		granted = size_class(bytes);
+		for (size_t k = 0; k < free_blocks.size(); ++k) if (free_blocks[k].first == granted) {
+			void* p = free_blocks[k].second; free_blocks[k] = free_blocks.back(); free_blocks.pop_back(); held_bytes -= granted; return p;
+		}
+		void* p = NULL;
+		cudaError_t e = cudaMalloc(&p, granted);
+		if (e != cudaSuccess) { trim(); ARB_CUDA_CHECK(cudaMalloc(&p, granted)); }
+		return p;
+	}
+	void put(void* p, size_t granted) { free_blocks.push_back(std::make_pair(granted, p)); held_bytes += granted; }
+	void trim() { for (size_t k = 0; k < free_blocks.size(); ++k) cudaFree(free_blocks[k].second); free_blocks.clear(); held_bytes = 0; }
+};
+inline device_pool& pool() { static device_pool p; return p; }
+inline void pool_trim() { pool().trim(); }
+#else
+inline void pool_trim() {}
+#endif
+
 // ------------------------------------------------------------------------------------------- device buffer
 template <class T> class dbuf {
-	T* p_; size_t n_;
+	T* p_; size_t n_; size_t granted_;
 	dbuf(const dbuf&); dbuf& operator=(const dbuf&);
 public:
-	dbuf(): p_(NULL), n_(0) {}
-	explicit dbuf(size_t n): p_(NULL), n_(0) { alloc(n); }
+	dbuf(): p_(NULL), n_(0), granted_(0) {}
+	explicit dbuf(size_t n): p_(NULL), n_(0), granted_(0) { alloc(n); }
 	~dbuf() { release(); }
 	void release() {
 		if (!p_) return;
 #ifdef ARB_DEVICE_BUILD
-		cudaFree(p_);
+		pool().put(p_, granted_);
 #else
 		free(p_);
 #endif
-		p_ = NULL; n_ = 0;
+		p_ = NULL; n_ = 0; granted_ = 0;
 	}
 	void alloc(size_t n) {
 		release();
 		n_ = n;
 		size_t bytes = (n ? n : 1) * sizeof(T) + 64; // slack for vectorised tail reads
 #ifdef ARB_DEVICE_BUILD
-		ARB_CUDA_CHECK(cudaMalloc((void**) &p_, bytes));
+		p_ = (T*) pool().get(bytes, granted_);
 #else
 		p_ = (T*) malloc(bytes);
 		if (!p_) throw arb_error("out of memory");

@@ -237,6 +237,8 @@ class Context:
 
 # ------------------------------------------------------------------------------------------- whole-run driver
 STEP_LOAD_REFERENCE, STEP_INGEST, STEP_ANNOTATE, STEP_UPLOAD, STEP_READ_FILTERS, STEP_FRAGMENT_LENGTH, STEP_FIND_FUSIONS, STEP_COUNT = range(8)
+EV_NAMES = ["fetch", "merge_adjacent", "multimappers", "evalue", "non_coding_neighbors", "intragenic_exonic", "min_support", "relative_support", "internal_tandem_duplication",
+            "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage"]
 STEP_NAMES = ["load_reference", "ingest", "annotate", "upload", "read_filters", "fragment_length", "find_fusions"]
 
 
@@ -268,6 +270,8 @@ def _load_pipeline_api(lib):
     lib.arb_pipeline_fragments.argtypes = [C.c_void_p, _p(SoaChunk), _p(C.c_char_p), _p(_p(C.c_uint64))]
     lib.arb_pipeline_genes.argtypes = [C.c_void_p, _p(Annotation)]
     lib.arb_pipeline_coverage.argtypes = [C.c_void_p, C.c_uint32, _p(_p(C.c_uint16)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8)), _p(C.c_uint64)]
+    lib.arb_pipeline_events.argtypes = [C.c_void_p, C.c_int]
+    lib.arb_pipeline_candidates.argtypes = [C.c_void_p, _p(Candidates), _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8))]
     lib._pipeline_ready = True
 
 
@@ -341,6 +345,27 @@ class Pipeline:
         name_off = _np_from(off, n + 1, np.uint64)
         raw = C.string_at(C.cast(names, C.c_void_p), int(name_off[-1])) if n else b""
         out["name_off"] = name_off; out["names_blob"] = raw
+        return out
+
+    def events(self, last_stage):
+        self._check(self.lib.arb_pipeline_events(self.h, last_stage))
+
+    def candidates(self):
+        """Copy of the host candidate table (+ iteration order, confidence, current fragment labels)."""
+        c = Candidates(); order = _p(C.c_uint32)(); conf = _p(C.c_uint8)(); labels = _p(C.c_uint8)()
+        self._check(self.lib.arb_pipeline_candidates(self.h, C.byref(c), C.byref(order), C.byref(conf), C.byref(labels)))
+        n = c.n
+        out = {"n": n}
+        for k, dt in (("gene1", np.uint32), ("gene2", np.uint32), ("contig1", np.uint16), ("contig2", np.uint16), ("breakpoint1", np.int32), ("breakpoint2", np.int32),
+                      ("direction1", np.uint8), ("direction2", np.uint8), ("split_reads1", np.uint32), ("split_reads2", np.uint32), ("discordant_mates", np.uint32),
+                      ("filter", np.uint8), ("bits", np.uint8), ("bits2", np.uint8), ("anchor_start1", np.int32), ("anchor_start2", np.int32), ("evalue", np.float32)):
+            out[k] = _np_from(getattr(c, k), n, dt)
+        for k in ("list1_off", "list2_off", "listd_off"):
+            out[k] = _np_from(getattr(c, k), n + 1, np.uint32)
+        for k, o in (("list1", "list1_off"), ("list2", "list2_off"), ("listd", "listd_off")):
+            out[k] = _np_from(getattr(c, k), int(out[o][-1]) if n else 0, np.uint32)
+        out["order"] = _np_from(order, n, np.uint32); out["confidence"] = _np_from(conf, n, np.uint8)
+        out["labels"] = _np_from(labels, int(self.stats().n_fragments), np.uint8)
         return out
 
     def genes(self):

@@ -128,6 +128,30 @@ int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n_list1, uint64_t* 
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out /* caller-allocated to arb_candidates_size */);
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if MATE1/MATE2 were canonicalised (fusions.cpp:416-421) */);
 
+/* ---- event-level stages on the candidate table ------------------------------------------------------------------
+ * The mutable candidate columns (filter, read counts, e-value) travel between the host-side event logic and the device
+ * with arb_set/get_candidate_state; candidates are addressed by their id (first-insertion order). */
+int arb_set_candidate_state(arb_ctx* ctx, const uint8_t* filter, const uint32_t* split_reads1, const uint32_t* split_reads2, const uint32_t* discordant_mates, const float* evalue);
+int arb_get_candidate_state(arb_ctx* ctx, uint8_t* filter, uint32_t* split_reads1, uint32_t* split_reads2, uint32_t* discordant_mates, float* evalue);
+int arb_set_candidate_lists(arb_ctx* ctx, const uint32_t* list1_off, const uint32_t* list1, const uint32_t* list2_off, const uint32_t* list2);
+/* Replaces merge_adjacent_fusions (source/merge_adjacent_fusions.cpp:19). n_itd_merges: internal tandem duplications whose read
+ * lists must be concatenated by the caller; arb_get_merge_log returns (winner id, absorbed id, order key) triples. */
+int arb_merge_adjacent(arb_ctx* ctx, int32_t max_distance, uint32_t* n_itd_merges);
+int arb_get_merge_log(arb_ctx* ctx, uint32_t* triples /* 3*n */, uint32_t n);
+/* Replaces the per-candidate part of estimate_expected_fusions (source/filter_relative_support.cpp:130-206); the order-dependent
+ * global tallies (:19-127) and the pow() tables come from the caller so that the result is bit-identical to the reference's float. */
+typedef struct arb_evalue_inputs {
+	const int32_t* partner_count; uint32_t n_genes;
+	uint32_t spliced_breakpoints, exonic_breakpoints, intronic_breakpoints, exonic_intronic_breakpoints;
+	uint32_t intragenic_duplications, intragenic_inversions, spliced_same_gene, spliced_different_genes;
+	float read_through_fraction; uint64_t mapped_reads;
+	const double *pow_reads, *pow_intragenic, *pow_intergenic; uint32_t n_read_table;
+	const double *pow_spliced1000 /* 1000 */, *pow_spliced400 /* 400 */, *pow_read_through /* 400000 */, *pow_proximal /* 400000 */;
+	double read_through_penalty;
+} arb_evalue_inputs;
+int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
+int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
+
 /* ---- device timing (CUDA events recorded on the context's stream around each stage) ---------------------------------- */
 typedef struct arb_timings {
 	float duplicates_ms;        /* duplicate marking (key build + hash group-by + mark) */
@@ -185,6 +209,15 @@ int arb_pipeline_fragments(arb_pipeline* p, arb_soa_chunk* view, const char** na
 /* gene table after annotation (dummy genes included) and coverage windows of one contig */
 int arb_pipeline_genes(arb_pipeline* p, arb_annotation* view);
 int arb_pipeline_coverage(arb_pipeline* p, uint32_t contig, const uint16_t** coverage, const uint8_t** starts, const uint8_t** ends, uint64_t* n_windows);
+
+/* event-level chain (source/arriba.cpp:420-545): runs the stages up to and including `last_stage` (ARB_EV_*) */
+enum { ARB_EV_FETCH = 0, ARB_EV_MERGE_ADJACENT, ARB_EV_MULTIMAPPERS, ARB_EV_EVALUE, ARB_EV_NON_CODING_NEIGHBORS, ARB_EV_INTRAGENIC_EXONIC, ARB_EV_MIN_SUPPORT,
+       ARB_EV_RELATIVE_SUPPORT, ARB_EV_ITD, ARB_EV_INTRONIC, ARB_EV_IN_VITRO, ARB_EV_SPLICED, ARB_EV_SELECT_BEST, ARB_EV_MARGINAL_READ_THROUGH, ARB_EV_MANY_SPLICED,
+       ARB_EV_SHORT_ANCHOR, ARB_EV_END_TO_END, ARB_EV_NO_COVERAGE, ARB_EV_COUNT };
+int arb_pipeline_events(arb_pipeline* p, int last_stage);
+/* read-only view of the host candidate table: the arb_candidates pointers alias pipeline memory; `order` = the reference's
+   iteration order (candidate ids), `confidence` and the current fragment labels complete the state */
+int arb_pipeline_candidates(arb_pipeline* p, arb_candidates* view, const uint32_t** order, const uint8_t** confidence, const uint8_t** fragment_labels);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,61 @@
+"""Event-level chain: after every stage the candidate table (filter, read counts, e-value) must equal the oracle's."""
+import numpy as np
+import pytest
+import worldutil
+from arriba_b200 import lib as L
+from test_find_fusions import key_of
+
+
+def compare_stage(got, want, stage, check_evalue):
+    index = {key_of(want, i): i for i in range(len(want["gene1"]))}
+    perm = np.array([index[key_of(got, i)] for i in range(got["n"])])
+    for name in ("filter", "split_reads1", "split_reads2", "discordant_mates"):
+        w = want[name][perm]
+        bad = np.nonzero(got[name] != w)[0]
+        assert len(bad) == 0, (stage, name, len(bad), [key_of(got, i) for i in bad[:5]], got[name][bad[:5]], w[bad[:5]])
+    if check_evalue:
+        w = want["evalue"][perm]
+        bad = np.nonzero(got["evalue"].view(np.uint32) != w.view(np.uint32))[0]
+        assert len(bad) == 0, (stage, "evalue", len(bad), got["evalue"][bad[:5]], w[bad[:5]], [key_of(got, i) for i in bad[:5]])
+    for lname, oname in (("list1", "list1_off"), ("list2", "list2_off")):
+        gs = np.diff(got[oname].astype(np.int64)); ws = np.diff(want[oname].astype(np.int64))[perm]
+        assert np.array_equal(gs, ws), (stage, lname + " sizes")
+    return perm
+
+
+def check_events(world, lib_path, threads=4):
+    p = L.Pipeline(world.prefix + ".bam", world.prefix + ".gtf", world.prefix + ".fa", threads=threads, lib_path=lib_path)
+    p.run(L.STEP_FIND_FUSIONS)
+    p.events(0)
+    got = p.candidates()
+    ff = world.stage("find_fusions")
+    # the replayed unordered_map iteration order must be the reference's
+    want_keys = [key_of(ff, i) for i in range(len(ff["gene1"]))]
+    got_keys = [key_of(got, int(i)) for i in got["order"]]
+    assert got_keys == want_keys, "iteration order of the candidate table differs from the reference's unordered_map"
+    stages = ["merge_adjacent", "multimappers", "evalue", "non_coding_neighbors", "intragenic_exonic", "min_support", "relative_support", "internal_tandem_duplication",
+              "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage"]
+    seen_evalue = False
+    for s, name in enumerate(stages, start=1):
+        p.events(s)
+        got = p.candidates()
+        want = world.stage("ev_" + name)
+        seen_evalue = seen_evalue or name == "evalue"
+        compare_stage(got, want, name, seen_evalue)
+        if "frag_filter" in want:
+            assert np.array_equal(got["labels"], want["frag_filter"]), (name, "fragment labels")
+        assert int((got["filter"] == 0).sum()) == int(want["remaining"][0]) or name == "evalue", name
+    p.close()
+
+
+def test_events_hostsim(worlds, hostsim_lib):
+    check_events(worlds.get("small"), hostsim_lib)
+
+
+def test_events_hostsim_l151(worlds, hostsim_lib):
+    check_events(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_events_cuda(worlds, cuda_lib):
+    check_events(worlds.get("small"), cuda_lib)
