@@ -69,6 +69,11 @@ int arb_merge_adjacent(arb_ctx* ctx, int32_t max_distance, uint32_t* n) { ARB_AP
 int arb_get_merge_log(arb_ctx* ctx, uint32_t* triples, uint32_t n) { ARB_API_BEGIN(ctx) ctx->e.get_merge_log(triples, n); ARB_API_END(ctx) }
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in) { ARB_API_BEGIN(ctx) ctx->e.estimate_evalues(*in); ARB_API_END(ctx) }
 int arb_filter_relative_support(arb_ctx* ctx, float cutoff) { ARB_API_BEGIN(ctx) ctx->e.filter_relative_support(cutoff); ARB_API_END(ctx) }
+int arb_set_splice_sites(arb_ctx* ctx, const uint32_t* off, const int32_t* sites) { ARB_API_BEGIN(ctx) ctx->e.set_splice_sites(off, sites); ARB_API_END(ctx) }
+int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* start, const int32_t* end, uint32_t n, uint32_t nc, uint64_t* n_indexed) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.build_kmer_index(contig, start, end, n, nc); if (n_indexed) *n_indexed = k; ARB_API_END(ctx) }
+int arb_kmer_index_digest(arb_ctx* ctx, uint64_t* kmers, uint64_t* positions, uint64_t* checksum, uint32_t nc) { ARB_API_BEGIN(ctx) ctx->e.kmer_index_digest(kmers, positions, checksum, nc); ARB_API_END(ctx) }
+int arb_homolog_pairs(arb_ctx* ctx, const uint32_t* ga, const uint32_t* gb, uint32_t n, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.homolog_pairs(ga, gb, n, out); ARB_API_END(ctx) }
+int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.filter_mismappers(max_mate_gap); if (n) *n = k; ARB_API_END(ctx) }
 int arb_get_timings(arb_ctx* ctx, arb_timings* out) { ARB_API_BEGIN(ctx) *out = ctx->e.timings; ARB_API_END(ctx) }
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.get_slot_swaps(out); ARB_API_END(ctx) }
 

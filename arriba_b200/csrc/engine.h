@@ -109,6 +109,14 @@ public:
 	void estimate_evalues(const arb_evalue_inputs& in);
 	void filter_relative_support(float cutoff);
 	dbuf<u32> merge_log; u32 merge_log_n;
+	// k-mer index / re-alignment
+	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
+	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
+	void set_splice_sites(const u32* off, const i32* sites);
+	u64 build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs);
+	void kmer_index_digest(u64* kmers, u64* positions, u64* checksum, u32 n_contigs);
+	void homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out);
+	u64 filter_mismappers(i32 max_mate_gap);
 private:
 	read_filter_params make_filter_params();
 	unsigned long genome_size() const;

@@ -675,6 +675,119 @@ void pipeline::recover_isoforms() { // recover_isoforms.cpp
 	log_remaining("Searching for additional isoforms");
 }
 
+// ------------------------------------------------------------------------------------------- k-mer index, homologs, mismappers (device)
+void pipeline::make_kmer_index() { // windows of make_kmer_index (filter_mismappers.cpp:47-84); the device enumerates and sorts the positions
+	const annot_view an = ref.host_view();
+	std::vector<u8> wanted(ref.genes.size(), 0);
+	for (u32 k = 0; k < ev.n; ++k) if (ev.filter[k] == F_none && ev.gene1[k] != ev.gene2[k]) { wanted[ev.gene1[k]] = 1; wanted[ev.gene2[k]] = 1; }
+	int padding = max_mate_gap + 2 * read_length_mean; // int + float -> float -> int (arriba.cpp:552)
+	if (padding < 0) padding = 0;
+	struct iv { u32 contig; i32 start, end; };
+	std::vector<iv> ivs; u32 n_index_contigs = 0;
+	for (u32 g = 0; g < ref.genes.size(); ++g) if (wanted[g]) {
+		const gene_rec& G = ref.genes[g];
+		if (!ref.has_sequence(G.contig)) throw std::runtime_error("no sequence for a contig with fused genes");
+		const i32 gs = std::max(G.start - padding, 0), ge = std::min(G.end + padding, (i32) ref.seq_len[G.contig] - 1);
+		n_index_contigs = std::max(n_index_contigs, (u32) G.contig + 1);
+		if (gs + 8 < ge) { iv x = {G.contig, gs, ge - 8}; ivs.push_back(x); } // positions pos with pos + 8 < gene_end
+	}
+	std::sort(ivs.begin(), ivs.end(), [](const iv& a, const iv& b) { return a.contig != b.contig ? a.contig < b.contig : a.start < b.start; });
+	std::vector<u32> c; std::vector<i32> s, t;
+	for (size_t k = 0; k < ivs.size(); ++k) {
+		if (!c.empty() && c.back() == ivs[k].contig && ivs[k].start <= t.back()) { t.back() = std::max(t.back(), ivs[k].end); continue; }
+		c.push_back(ivs[k].contig); s.push_back(ivs[k].start); t.push_back(ivs[k].end);
+	}
+	// downstream splice sites per gene (filter_mismappers.cpp:16-31)
+	if (!splice_sites_ready) {
+		std::vector<u32> off(ref.genes.size() + 1, 0); std::vector<i32> sites;
+		const region_index& ix = ref.exon_index;
+		for (u32 g = 0; g < ref.genes.size(); ++g) {
+			const gene_rec& G = ref.genes[g];
+			const u32 lo = ix.begin[G.contig], hi = ix.begin[G.contig + 1];
+			for (u32 r = (u32) (std::lower_bound(ix.end.begin() + lo, ix.end.begin() + hi, G.start) - ix.end.begin()); r < hi && ix.end[r] <= G.end; ++r)
+				if (is_breakpoint_spliced(an, g, DOWNSTREAM, ix.end[r])) sites.push_back(ix.end[r]);
+			off[g + 1] = (u32) sites.size();
+		}
+		if (sites.empty()) sites.push_back(0);
+		check(ctx, arb_set_splice_sites(ctx, off.data(), sites.data()), "arb_set_splice_sites");
+		splice_sites_ready = true;
+	}
+	uint64_t n_indexed = 0;
+	if (c.empty()) { c.push_back(0); s.push_back(0); t.push_back(0); check(ctx, arb_build_kmer_index(ctx, c.data(), s.data(), t.data(), 0, n_index_contigs, &n_indexed), "arb_build_kmer_index"); }
+	else check(ctx, arb_build_kmer_index(ctx, c.data(), s.data(), t.data(), (uint32_t) c.size(), n_index_contigs, &n_indexed), "arb_build_kmer_index");
+	log += "Indexing gene sequences\n";
+}
+
+void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() itself is evaluated on the device in two batches
+	// remaining candidates in the reference's list order: push_front over the iteration order = reverse iteration order
+	std::vector<u32> rem;
+	for (size_t q = ev.order.size(); q-- > 0;) if (ev.filter[ev.order[q]] == F_none) rem.push_back(ev.order[q]);
+	// batch 1: the two genes of every remaining candidate
+	std::vector<u32> ga, gb; std::vector<u8> res;
+	for (size_t x = 0; x < rem.size(); ++x) { ga.push_back(ev.gene1[rem[x]]); gb.push_back(ev.gene2[rem[x]]); }
+	res.resize(ga.size() + 1);
+	if (!ga.empty()) check(ctx, arb_homolog_pairs(ctx, ga.data(), gb.data(), (uint32_t) ga.size(), res.data()), "arb_homolog_pairs");
+	std::vector<u8> self_homolog(res.begin(), res.begin() + ga.size());
+	// batch 2: partner genes of candidates that share a gene (a superset of what the sequential pass will ask for)
+	auto partner_genes = [&](u32 f, u32 o, u32& h1, u32& h2) { // which genes would be compared for the pair (f, o)?  (filter_homologs.cpp:97-113)
+		if (ev.gene1[f] == ev.gene1[o] && ev.bp2[f] != ev.bp2[o]) { h1 = ev.gene2[f]; h2 = ev.gene2[o]; return true; }
+		if (ev.gene1[f] == ev.gene2[o] && ev.bp2[f] != ev.bp1[o]) { h1 = ev.gene2[f]; h2 = ev.gene1[o]; return true; }
+		if (ev.gene2[f] == ev.gene1[o] && ev.bp1[f] != ev.bp2[o]) { h1 = ev.gene1[f]; h2 = ev.gene2[o]; return true; }
+		if (ev.gene2[f] == ev.gene2[o] && ev.bp1[f] != ev.bp1[o]) { h1 = ev.gene1[f]; h2 = ev.gene1[o]; return true; }
+		return false;
+	};
+	std::vector<std::vector<u32> > by_gene(ref.genes.size()); // positions in rem, ascending
+	for (size_t x = 0; x < rem.size(); ++x) { by_gene[ev.gene1[rem[x]]].push_back((u32) x); if (ev.gene2[rem[x]] != ev.gene1[rem[x]]) by_gene[ev.gene2[rem[x]]].push_back((u32) x); }
+	std::map<std::pair<u32, u32>, u32> pair_index; ga.clear(); gb.clear();
+	for (size_t x = 0; x < rem.size(); ++x) {
+		if (self_homolog[x]) continue;
+		const u32 f = rem[x];
+		for (int side = 0; side < 2; ++side) {
+			const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[f] : ev.gene2[f]];
+			for (size_t y = 0; y < v.size(); ++y) {
+				if (v[y] <= x) continue;
+				u32 h1, h2;
+				if (!partner_genes(f, rem[v[y]], h1, h2)) continue;
+				if (pair_index.insert(std::make_pair(std::make_pair(h1, h2), (u32) ga.size())).second) { ga.push_back(h1); gb.push_back(h2); }
+			}
+			if (ev.gene1[f] == ev.gene2[f]) break;
+		}
+	}
+	res.assign(ga.size() + 1, 0);
+	if (!ga.empty()) check(ctx, arb_homolog_pairs(ctx, ga.data(), gb.data(), (uint32_t) ga.size(), res.data()), "arb_homolog_pairs");
+	// sequential resolution, exactly in list order
+	for (size_t x = 0; x < rem.size(); ++x) {
+		const u32 f = rem[x];
+		if (ev.filter[f] != F_none) continue;
+		if (self_homolog[x]) { ev.filter[f] = F_homologs; continue; }
+		// later candidates that share a gene with f, in list order
+		std::vector<u32> later;
+		for (int side = 0; side < 2; ++side) { const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[f] : ev.gene2[f]]; for (size_t y = 0; y < v.size(); ++y) if (v[y] > x) later.push_back(v[y]); if (ev.gene1[f] == ev.gene2[f]) break; }
+		std::sort(later.begin(), later.end()); later.erase(std::unique(later.begin(), later.end()), later.end());
+		for (size_t y = 0; y < later.size(); ++y) {
+			const u32 o = rem[later[y]];
+			if (ev.filter[o] != F_none) continue;
+			u32 h1, h2;
+			if (!partner_genes(f, o, h1, h2)) continue;
+			const unsigned int a1 = (ev.split_reads1[f] > 0) + (ev.split_reads2[f] > 0) + (ev.discordant_mates[f] > 0), a2 = (ev.split_reads1[o] > 0) + (ev.split_reads2[o] > 0) + (ev.discordant_mates[o] > 0);
+			if (!res[pair_index.at(std::make_pair(h1, h2))]) continue;
+			if (a1 > a2 || (a1 == a2 && ev.supporting_reads(f) > ev.supporting_reads(o)) || (a1 == a2 && ev.supporting_reads(f) == ev.supporting_reads(o) && ev.evalue[f] <= ev.evalue[o])) ev.filter[o] = F_homologs;
+			else { ev.filter[f] = F_homologs; break; }
+		}
+	}
+	log_remaining("Filtering genes with >=30% identity");
+}
+
+void pipeline::filter_mismappers() { // filter_mismappers.cpp:272-359, on the device
+	check(ctx, arb_set_fragment_filters(ctx, labels.data()), "arb_set_fragment_filters");
+	push_candidate_state();
+	uint64_t n_items = 0;
+	check(ctx, arb_filter_mismappers(ctx, max_mate_gap, &n_items), "arb_filter_mismappers");
+	pull_candidate_state();
+	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
+	log_remaining("Re-aligning chimeric reads to filter fusions with >=80% mis-mappers");
+}
+
 void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no structural-variant input: closest_genomic_breakpoint = -1)
 	std::vector<std::vector<u32> > by_gene(ref.genes.size());
 	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; by_gene[ev.gene1[k]].push_back(k); by_gene[ev.gene2[k]].push_back(k); }

@@ -153,6 +153,12 @@ void pipeline::events_until(int last) { // arriba.cpp:420-545, filters enabled b
 			case EV_SHORT_ANCHOR: if (on(F_short_anchor)) filter_short_anchor(); break;
 			case EV_END_TO_END: if (on(F_end_to_end)) filter_end_to_end(); break;
 			case EV_NO_COVERAGE: if (on(F_no_coverage)) filter_no_coverage(); break;
+			case EV_KMER_INDEX: if (on(F_homologs) || on(F_mismappers)) make_kmer_index(); break;
+			case EV_HOMOLOGS: if (on(F_homologs)) filter_homologs(); break;
+			case EV_MISMAPPERS: if (on(F_mismappers)) filter_mismappers(); break;
+			case EV_SELECT_BEST2: if (on(F_many_spliced) && on(F_select_best)) select_best(); break; // arriba.cpp:573-579
+			case EV_ISOFORMS: if (on(F_isoforms)) recover_isoforms(); break;
+			case EV_CONFIDENCE: assign_confidence(); break;
 		}
 		events_done = s;
 	}

@@ -31,7 +31,7 @@ struct pipeline {
 	event_table ev;
 	std::string log; // the reference's progress lines (arriba.cpp:61-66 style, without time stamps)
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
-	pipeline(): events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) {}
+	pipeline(): splice_sites_ready(false), events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) {}
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -46,6 +46,7 @@ struct pipeline {
 	void filter_non_coding_neighbors(); void filter_intragenic_both_exonic(); void filter_min_support(); void recover_internal_tandem_duplication();
 	void filter_both_intronic(); void filter_in_vitro(); void recover_both_spliced(); void select_best(); void filter_marginal_read_through();
 	void recover_many_spliced(); void filter_short_anchor(); void filter_end_to_end(); void filter_no_coverage(); void recover_isoforms(); void assign_confidence();
+	void make_kmer_index(); void filter_homologs(); void filter_mismappers(); bool splice_sites_ready;
 	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold);
 	unsigned int spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold);
 	float intronic_fraction(u32 gene);
@@ -55,7 +56,8 @@ struct pipeline {
 };
 
 enum { EV_FETCH = 0, EV_MERGE_ADJACENT, EV_MULTIMAPPERS, EV_EVALUE, EV_NON_CODING_NEIGHBORS, EV_INTRAGENIC_EXONIC, EV_MIN_SUPPORT, EV_RELATIVE_SUPPORT,
-       EV_ITD, EV_INTRONIC, EV_IN_VITRO, EV_SPLICED, EV_SELECT_BEST, EV_MARGINAL_READ_THROUGH, EV_MANY_SPLICED, EV_SHORT_ANCHOR, EV_END_TO_END, EV_NO_COVERAGE, EV_COUNT };
+       EV_ITD, EV_INTRONIC, EV_IN_VITRO, EV_SPLICED, EV_SELECT_BEST, EV_MARGINAL_READ_THROUGH, EV_MANY_SPLICED, EV_SHORT_ANCHOR, EV_END_TO_END, EV_NO_COVERAGE,
+       EV_KMER_INDEX, EV_HOMOLOGS, EV_MISMAPPERS, EV_SELECT_BEST2, EV_ISOFORMS, EV_CONFIDENCE, EV_COUNT };
 
 int detect_strandedness(pipeline& p);
 void assign_strands(pipeline& p, int strandedness);

@@ -1,0 +1,105 @@
+// mismap.cu -- drivers of the k-mer index, gene homology and re-alignment stages (see mismap_hd.h).
+#include "engine.h"
+#include "mismap_hd.h"
+
+namespace arb {
+
+void engine::set_splice_sites(const u32* off, const i32* sites) {
+	splice_off.upload(ex, off, (size_t) annot.n_genes + 1);
+	splice_sites.upload(ex, sites, off[annot.n_genes]);
+	ex.sync();
+	has_splice_sites = true;
+}
+
+u64 engine::build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs) {
+	kmer_index_contigs = n_index_contigs; kmer_indexed = 0;
+	const size_t n_buckets = (size_t) n_index_contigs * 65536;
+	kmer_bucket_off.ensure(n_buckets + 2);
+	kmer_bucket_off.zero(ex, n_buckets + 2);
+	std::vector<u32> first((size_t) n + 1, 0);
+	for (u32 k = 0; k < n; ++k) { if (end[k] < start[k]) throw arb_error("arb_build_kmer_index: malformed interval"); const u64 t = (u64) first[k] + (u64) (end[k] - start[k]); if (t > 0xFFFFFFF0ull) throw arb_error("arb_build_kmer_index: more than 2^32 positions"); first[k + 1] = (u32) t; }
+	const u32 P = first[n];
+	if (P == 0) { ex.sync(); return 0; }
+	dbuf<u32> d_contig, d_first; dbuf<i32> d_start, d_end;
+	d_contig.upload(ex, contig, n); d_start.upload(ex, start, n); d_end.upload(ex, end, n); d_first.upload(ex, first.data(), (size_t) n + 1);
+	interval_view iv = {d_contig.ptr(), d_start.ptr(), d_end.ptr(), d_first.ptr(), n};
+	dbuf<u32> flag((size_t) P + 1);
+	kmer_flag_fn ff = {iv, annot.view(), flag.ptr()};
+	for_each(ex, P, ff);
+	exclusive_scan_u32(ex, flag.ptr(), flag.ptr(), P);
+	u32 K = 0; flag.download(ex, &K, 1, P);
+	kmer_indexed = K;
+	if (K == 0) return 0;
+	dbuf<u32> key(K), pos(K), tk(K), tv(K);
+	kmer_emit_fn ef = {iv, annot.view(), flag.ptr(), key.ptr(), pos.ptr()};
+	for_each(ex, P, ef);
+	u32 bits = 16; while (bits < 32 && ((u64) 1 << bits) < (u64) n_index_contigs * 65536) ++bits;
+	radix_sort_pairs_u32(ex, key.ptr(), pos.ptr(), tk.ptr(), tv.ptr(), K, bits); // stable: positions stay ascending inside a bucket
+	bucket_count_fn bc = {key.ptr(), kmer_bucket_off.ptr()};
+	for_each(ex, K, bc);
+	exclusive_scan_u32(ex, kmer_bucket_off.ptr(), kmer_bucket_off.ptr(), (u32) n_buckets);
+	kmer_pos.ensure(K);
+#ifdef ARB_DEVICE_BUILD
+	ARB_CUDA_CHECK(cudaMemcpyAsync(kmer_pos.ptr(), pos.ptr(), (size_t) K * 4, cudaMemcpyDeviceToDevice, ex.stream));
+#else
+	memcpy(kmer_pos.ptr(), pos.ptr(), (size_t) K * 4);
+#endif
+	ex.sync();
+	return K;
+}
+
+void engine::kmer_index_digest(u64* kmers, u64* positions, u64* checksum, u32 n_contigs) {
+	for (u32 c = 0; c < n_contigs; ++c) { kmers[c] = positions[c] = checksum[c] = 0; }
+	if (kmer_indexed == 0) return;
+	const size_t n_buckets = (size_t) kmer_index_contigs * 65536;
+	std::vector<u32> off(n_buckets + 1); std::vector<i32> pos(kmer_indexed);
+	kmer_bucket_off.download(ex, off.data(), n_buckets + 1); kmer_pos.download(ex, pos.data(), kmer_indexed);
+	for (u32 c = 0; c < kmer_index_contigs && c < n_contigs; ++c)
+		for (u32 k = 0; k < 65536; ++k) {
+			const u32 lo = off[(size_t) c * 65536 + k], hi = off[(size_t) c * 65536 + k + 1];
+			if (hi > lo) ++kmers[c];
+			for (u32 p = lo; p < hi; ++p) { ++positions[c]; checksum[c] += ((u64) k * 1000003ULL + (u64) pos[p]) * 0x9E3779B97F4A7C15ULL; }
+		}
+}
+
+void engine::homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out) {
+	if (n == 0) return;
+	dbuf<u32> a, b; dbuf<u8> o(n);
+	a.upload(ex, ga, n); b.upload(ex, gb, n);
+	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
+	homolog_pairs_fn fn = {annot.view(), ix, a.ptr(), b.ptr(), o.ptr(), params.max_homolog_identity};
+	for_each(ex, n, fn);
+	o.download(ex, out, n);
+}
+
+u64 engine::filter_mismappers(i32 max_mate_gap) {
+	if (!has_splice_sites) throw arb_error("arb_filter_mismappers: arb_set_splice_sites must be called first");
+	const u32 C = cands.n, N = frags.n;
+	if (C == 0) return 0;
+#ifdef ARB_DEVICE_BUILD
+	ARB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)); // realign() recurses at splice sites and at one deletion
+#endif
+	dbuf<u32> item_off((size_t) C + 1);
+	item_count_fn ic = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list2_off.ptr(), cands.listd_off.ptr(), item_off.ptr()};
+	for_each(ex, C, ic);
+	exclusive_scan_u32(ex, item_off.ptr(), item_off.ptr(), C);
+	u32 I = 0; item_off.download(ex, &I, 1, C);
+	dbuf<u32> item_cand(I), item_frag(I); dbuf<u8> item_kind(I), mism(N);
+	mism.zero(ex, N);
+	item_fill_fn ifn = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(), item_off.ptr(), item_cand.ptr(), item_frag.ptr(), item_kind.ptr()};
+	for_each(ex, C, ifn);
+	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
+	gene_splice_view sp = {splice_off.ptr(), splice_sites.ptr()};
+	mismap_params mp = {max_mate_gap, params.max_mismapper_fraction};
+	mismap_item_fn mi = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr()};
+	for_each(ex, I, mi);
+	mismap_apply_fn ma = {mism.ptr(), frags.filter.ptr()};
+	for_each(ex, N, ma);
+	mismap_count_fn mc = {frags.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(),
+	                      cands.split_reads1.ptr(), cands.split_reads2.ptr(), cands.discordant_mates.ptr(), cands.filter.ptr(), params.max_mismapper_fraction};
+	for_each(ex, C, mc);
+	ex.sync();
+	return I;
+}
+
+} // namespace arb

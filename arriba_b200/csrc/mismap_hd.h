@@ -1,0 +1,269 @@
+// mismap_hd.h -- k-mer index of fused genes, gene homology and re-alignment of supporting reads ("mismappers").
+//
+// Reference behaviour: make_kmer_index (filter_mismappers.cpp:47-84), kmer_to_int (:33-45), align (:86-187), align_both_strands
+// (:189-230), extend_split_read (:247-270), filter_mismappers (:272-359), is_homolog (filter_homologs.cpp:13-63).
+// The reference's per-contig unordered_map<kmer, vector<position>> becomes one position array sorted by (contig, 8-mer, position)
+// with a dense bucket-offset table (65,536 buckets per contig), so a lookup is two loads.
+#pragma once
+#include "model.h"
+#include "annot_hd.h"
+#include "prims.h"
+#include <math.h>
+
+namespace arb {
+
+ARB_HD u32 base2(char c) { return c == 'T' ? 0u : c == 'G' ? 1u : c == 'C' ? 2u : 3u; } // every other character (A, N, IUPAC) is 3
+ARB_HD char complement_char(char c) { switch (c) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; default: return c; } }
+
+struct kmer_index_view {
+	const i32* pos;          // positions sorted by (contig, 8-mer, position)
+	const u32* bucket_off;   // n_index_contigs * 65536 + 1
+	u32 n_index_contigs;     // contigs >= this have no index (kmer_indices.size() in the reference)
+	ARB_HD void bucket(u32 contig, u32 kmer, u32& lo, u32& hi) const { const u64 b = (u64) contig * 65536 + kmer; lo = bucket_off[b]; hi = bucket_off[b + 1]; }
+};
+
+// ---- index construction
+struct interval_view { const u32* contig; const i32* start; const i32* end /* exclusive */; const u32* first /* prefix sum of lengths, n+1 */; u32 n; };
+ARB_HD u32 interval_of(const interval_view& iv, u32 j) { u32 lo = 0, hi = iv.n; while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (iv.first[mid] <= j) lo = mid; else hi = mid; } return lo; }
+struct kmer_flag_fn { // candidate position j: is it indexed? (first base not 'N')
+	interval_view iv; annot_view an; u32* flag;
+	ARB_HD void operator()(u32 j) const {
+		const u32 t = interval_of(iv, j); const i32 p = iv.start[t] + (i32) (j - iv.first[t]);
+		flag[j] = an.assembly[an.contig_seq_off[iv.contig[t]] + (u32) p] != 'N';
+	}
+};
+struct kmer_emit_fn { // key = contig << 16 | 8-mer
+	interval_view iv; annot_view an; const u32* flag_scan; u32* key; u32* pos;
+	ARB_HD void operator()(u32 j) const {
+		if (flag_scan[j + 1] == flag_scan[j]) return;
+		const u32 t = interval_of(iv, j); const i32 p = iv.start[t] + (i32) (j - iv.first[t]);
+		const char* s = an.assembly + an.contig_seq_off[iv.contig[t]] + (u32) p;
+		u32 k = 0;
+		for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(s[b]);
+		key[flag_scan[j]] = iv.contig[t] << 16 | k; pos[flag_scan[j]] = (u32) p;
+	}
+};
+struct bucket_count_fn { const u32* key; u32* count; ARB_HD void operator()(u32 j) const { atomic_add_u32(&count[key[j]], 1); } };
+
+// ---- sequences to re-align: a slice of a stored read, optionally reverse-complemented, or a stretch of the reference
+struct read_slice {
+	const u8* nt16; u32 off; u32 len; bool rc;
+	ARB_HD char at(u32 i) const { return rc ? complement_char(nt16_char(nt16_at(nt16, off + len - 1 - i))) : nt16_char(nt16_at(nt16, off + i)); }
+};
+ARB_HD u32 kmer8(const read_slice& s, u32 p) { u32 k = 0; for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(s.at(p + b)); return k; }
+
+struct gene_window { u32 contig; i32 start, end; const i32* splice; u32 n_splice; }; // [start, end] = gene +- padding; downstream splice sites of the gene
+
+ARB_HD u32 lower_bound_i32(const i32* v, u32 lo, u32 hi, i32 x) { while (lo < hi) { u32 mid = lo + ((hi - lo) >> 1); if (v[mid] < x) lo = mid + 1; else hi = mid; } return lo; }
+
+// seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
+ARB_HD_RECURSIVE bool realign(int score, const read_slice& rs, int read_pos, const char* ref, int gene_pos, const gene_window& w, const kmer_index_view& ix, int min_score, int max_deletions) {
+	const int len = (int) rs.len;
+	int skipped = 0;
+	for (; read_pos + 8 < len && read_pos + min_score <= len + score + 16; ++read_pos, --score, ++skipped) {
+		u32 lo, hi; ix.bucket(w.contig, kmer8(rs, (u32) read_pos), lo, hi);
+		if (lo == hi) continue;
+		for (u32 h = lower_bound_i32(ix.pos, lo, hi, gene_pos); h < hi && ix.pos[h] < w.end; ++h) {
+			const int hit = ix.pos[h];
+			int ext = score + 8;
+			const bool leading = read_pos == skipped; // every base so far was skipped: no penalty for them (local alignment start)
+			if (leading) ext += skipped;
+			if (ext >= min_score) return true;
+			{ // extend to the left over the skipped bases, one mismatch allowed
+				int r = read_pos - 1, g = hit - 1; u32 mm = 0;
+				while (r >= read_pos - skipped && g >= w.start) {
+					if (rs.at((u32) r) == ref[g]) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
+					else if (++mm > 1) break;
+					--r; --g;
+				}
+			}
+			{ // extend to the right; try a spliced continuation at splice sites and one deletion at the first mismatch
+				int r = read_pos + 8, g = hit + 8; u32 mm = 0, consecutive = 0;
+				u32 ss = lower_bound_i32(w.splice, 0, w.n_splice, g - 1);
+				while (r < len && g <= w.end) {
+					if (ss < w.n_splice) {
+						if (g - 1 > w.splice[ss]) ++ss;
+						if (ss < w.n_splice && g - 1 == w.splice[ss] && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions)) return true;
+					}
+					if (rs.at((u32) r) == ref[g]) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
+					else {
+						if (++mm == 1 && max_deletions > 0 && len >= 30 && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions - 1)) return true;
+						--ext;
+						if (++consecutive >= 4) break;
+					}
+					++r; ++g;
+				}
+			}
+		}
+	}
+	return false;
+}
+
+struct gene_splice_view { const u32* off; const i32* sites; }; // per gene: sorted downstream splice sites (filter_mismappers.cpp:16-31)
+
+// filter_mismappers.cpp:189-230; `genes` = gene set of the OTHER segment
+ARB_HD bool realign_both_strands(const read_slice& fwd, int read_length, int max_mate_gap, bool same_contig, i32 aln_start, i32 aln_end, const u32* genes, u32 n_genes,
+                                 const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, float min_align_fraction) {
+	if (fwd.len >= 300) return false;
+#ifdef __CUDA_ARCH__
+	const int min_score = (int) ((double) __fmul_rn(min_align_fraction, (float) fwd.len) + 0.5);
+#else
+	volatile float prod = min_align_fraction * (float) fwd.len;
+	const int min_score = (int) ((double) prod + 0.5);
+#endif
+	for (u32 k = 0; k < n_genes; ++k) {
+		const u32 g = genes[k];
+		gene_window w; w.contig = an.gene_contig[g];
+		w.start = hd_max(an.gene_start[g] - max_mate_gap - read_length, 0);
+		w.end = hd_min(an.gene_end[g] + max_mate_gap + read_length, (i32) an.contig_len[w.contig] - 1);
+		if (same_contig && ((aln_start >= w.start && aln_start <= w.end) || (aln_end >= w.start && aln_end <= w.end))) continue;
+		if (w.contig >= ix.n_index_contigs) continue;
+		w.splice = sp.sites + sp.off[g]; w.n_splice = sp.off[g + 1] - sp.off[g];
+		const char* ref = an.assembly + an.contig_seq_off[w.contig];
+		if (realign(0, fwd, 0, ref, w.start, w, ix, min_score, 1)) return true;
+		read_slice rev = fwd; rev.rc = !fwd.rc;
+		if (realign(0, rev, 0, ref, w.start, w, ix, min_score, 1)) return true;
+	}
+	return false;
+}
+
+// filter_mismappers.cpp:247-270: can the clipped segment simply be extended along the reference?
+ARB_HD bool extends_linearly(const frag_view& f, const annot_view& an, u32 a /* SPLIT_READ */) {
+	const u8* seq = f.sq(a); const u32 len = f.seq_len[a];
+	const char* ref = an.assembly + an.contig_seq_off[f.contig[a]]; const i32 clen = (i32) an.contig_len[f.contig[a]];
+	int n; u32 matches = 0;
+	if (f.fwd(a)) {
+		const u32 pre = f.preclip(a);
+		n = hd_min((int) pre, f.start[a]);
+		for (int i = 0; i < n; ++i) if (nt16_char(nt16_at(seq, pre - n + i)) == ref[f.start[a] - n + i]) ++matches;
+	} else {
+		const u32 post = f.postclip(a);
+		n = hd_min((int) post, clen - f.end[a] - 2);
+		for (int i = 0; i < n; ++i) { const i32 g = f.end[a] + 1 + i; if (g < clen && nt16_char(nt16_at(seq, len - post + i)) == ref[g]) ++matches; }
+	}
+	if (n < 0) { // clipped segment runs over the contig end: the reference then compares the whole clipped segment (std::string::substr with a huge count)
+		const u32 post = f.postclip(a); n = (int) post;
+		for (int i = 0; i < n; ++i) { const i32 g = f.end[a] + 1 + i; if (g < clen && nt16_char(nt16_at(seq, len - post + i)) == ref[g]) ++matches; }
+	}
+#ifdef __CUDA_ARCH__
+	return (double) matches >= floor((double) __fmul_rn((float) (u32) n, 0.7f));
+#else
+	volatile float prod = (float) (u32) n * 0.7f;
+	return (double) matches >= floor((double) prod);
+#endif
+}
+
+struct mismap_params { i32 max_mate_gap; float max_mismapper_fraction; };
+
+// one work item = one (candidate, listed fragment) pair
+struct mismap_item_fn {
+	frag_view f; annot_view an; kmer_index_view ix; gene_splice_view sp; mismap_params p;
+	const u32* item_cand; const u32* item_frag; const u8* item_kind /* 0 split read, 1 discordant */; const u16* cand_contig1; const u16* cand_contig2; const u8* cand_filter;
+	u8* mismapper; // per fragment, set to 1 when any evaluation says "mis-mapped"
+	ARB_HD void operator()(u32 j) const {
+		const u32 cand = item_cand[j], i = item_frag[j];
+		if (cand_filter[cand] != F_none || f.filter[i] != F_none) return;
+		const bool same_contig = cand_contig1[cand] == cand_contig2[cand];
+		bool bad = false;
+		if (item_kind[j] == 0) {
+			const u32 m = f.idx(i, MATE1), s = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
+			const u32 slen = f.seq_len[s], mlen = f.seq_len[m];
+			read_slice clipped, anchor;
+			clipped.nt16 = f.sq(s); clipped.rc = false; anchor.nt16 = f.sq(m); anchor.rc = false;
+			if (f.fwd(s)) { clipped.off = 0; clipped.len = hd_min(f.preclip(s), slen); const u32 pre = hd_min(f.preclip(m), mlen); anchor.off = pre; anchor.len = mlen - pre; }
+			else { const u32 post = hd_min(f.postclip(s), slen); clipped.off = slen - post; clipped.len = post; const u32 mpost = hd_min(f.postclip(m), mlen); anchor.off = 0; anchor.len = mlen - mpost; }
+			bad = extends_linearly(f, an, s) ||
+			      realign_both_strands(clipped, (int) slen, p.max_mate_gap, same_contig, f.start[u], f.end[u], f.genes + f.genes_off[s], f.genes_cnt[s], an, ix, sp, 0.8f) ||
+			      realign_both_strands(anchor, (int) mlen, p.max_mate_gap, same_contig, f.start[m], f.end[m], f.genes + f.genes_off[u], f.genes_cnt[u], an, ix, sp, 0.8f);
+		} else {
+			const u32 a = f.idx(i, MATE1), b = f.idx(i, MATE2);
+			const float cf1 = ((float) f.preclip(a) + f.postclip(a)) / f.seq_len[a], cf2 = ((float) f.preclip(b) + f.postclip(b)) / f.seq_len[b];
+			const float fr1 = hd_min(0.8f, 0.8f * (1 - cf1)), fr2 = hd_min(0.8f, 0.8f * (1 - cf2));
+			read_slice ra = {f.sq(a), 0, f.seq_len[a], false}, rb = {f.sq(b), 0, f.seq_len[b], false};
+			bad = realign_both_strands(ra, (int) f.seq_len[a], p.max_mate_gap, same_contig, f.start[a], f.end[a], f.genes + f.genes_off[b], f.genes_cnt[b], an, ix, sp, fr1) ||
+			      realign_both_strands(rb, (int) f.seq_len[b], p.max_mate_gap, same_contig, f.start[b], f.end[b], f.genes + f.genes_off[a], f.genes_cnt[a], an, ix, sp, fr2);
+		}
+		if (bad) mismapper[i] = 1;
+	}
+};
+
+struct mismap_apply_fn { const u8* mismapper; u8* filter; ARB_HD void operator()(u32 i) const { if (mismapper[i] && filter[i] == F_none) filter[i] = F_mismappers; } };
+
+// filter_mismappers.cpp:232-244, 336-356: recount and discard candidates supported mostly by mis-mapped reads
+struct mismap_count_fn {
+	const u8* frag_filter; const u32* l1o; const u32* l1; const u32* l2o; const u32* l2; const u32* ldo; const u32* ld;
+	u32* sr1; u32* sr2; u32* dm; u8* cand_filter; float max_fraction;
+	ARB_HD void scan(const u32* off, const u32* list, u32 cand, u32& count, u32& mism, u32& total) const {
+		for (u32 p = off[cand]; p < off[cand + 1]; ++p) {
+			const u8 fl = frag_filter[list[p]];
+			if (fl == F_none) ++total;
+			else if (fl == F_mismappers) { ++total; ++mism; if (count > 0) --count; }
+		}
+	}
+	ARB_HD void operator()(u32 cand) const {
+		if (cand_filter[cand] != F_none) return;
+		u32 mism = 0, total = 0, a = sr1[cand], b = sr2[cand], c = dm[cand];
+		scan(l1o, l1, cand, a, mism, total); scan(l2o, l2, cand, b, mism, total); scan(ldo, ld, cand, c, mism, total);
+		sr1[cand] = a; sr2[cand] = b; dm[cand] = c;
+		mism &= 0xFFFF; total &= 0xFFFF; // the reference counts in unsigned short
+#ifdef __CUDA_ARCH__
+		const double limit = floor((double) __fmul_rn(max_fraction, (float) total));
+#else
+		volatile float prod = max_fraction * (float) total; const double limit = floor((double) prod);
+#endif
+		if (mism > 0 && (double) mism >= limit) cand_filter[cand] = F_mismappers;
+	}
+};
+
+// work items of the re-alignment: every listed fragment of every unfiltered candidate
+struct item_count_fn { const u8* cand_filter; const u32* l1o; const u32* l2o; const u32* ldo; u32* count; ARB_HD void operator()(u32 c) const { count[c] = cand_filter[c] != F_none ? 0 : (l1o[c + 1] - l1o[c]) + (l2o[c + 1] - l2o[c]) + (ldo[c + 1] - ldo[c]); } };
+struct item_fill_fn {
+	const u8* cand_filter; const u32* l1o; const u32* l1; const u32* l2o; const u32* l2; const u32* ldo; const u32* ld; const u32* item_off; u32* item_cand; u32* item_frag; u8* item_kind;
+	ARB_HD void operator()(u32 c) const {
+		if (cand_filter[c] != F_none) return;
+		u32 w = item_off[c];
+		for (u32 p = l1o[c]; p < l1o[c + 1]; ++p, ++w) { item_cand[w] = c; item_frag[w] = l1[p]; item_kind[w] = 0; }
+		for (u32 p = l2o[c]; p < l2o[c + 1]; ++p, ++w) { item_cand[w] = c; item_frag[w] = l2[p]; item_kind[w] = 0; }
+		for (u32 p = ldo[c]; p < ldo[c + 1]; ++p, ++w) { item_cand[w] = c; item_frag[w] = ld[p]; item_kind[w] = 1; }
+	}
+};
+
+// ---- gene homology (filter_homologs.cpp:13-63): fraction of the small gene's 8-mers (stride 8) that occur, with 8 more matching bases, in the big gene
+ARB_HD bool genes_are_homologs(const annot_view& an, const kmer_index_view& ix, u32 g1, u32 g2, float max_identity) {
+	if (g1 == g2) return false;
+	u32 sm = g1, bg = g2;
+	if ((u32) (an.gene_end[sm] - an.gene_start[sm]) > (u32) (an.gene_end[bg] - an.gene_start[bg])) { sm = g2; bg = g1; }
+	const u32 sc = an.gene_contig[sm], bc = an.gene_contig[bg];
+	const i32 ss = an.gene_start[sm], se = an.gene_end[sm], bs = an.gene_start[bg], be = an.gene_end[bg];
+	if (sc == bc && ((ss >= bs && ss <= be) || (se >= bs && se <= be))) return false;
+	if (bc >= ix.n_index_contigs) return false;
+	const u32 len = (u32) (se - ss);
+	const bool rc = an.gene_strand[sm] != an.gene_strand[bg];
+	const char* sref = an.assembly + an.contig_seq_off[sc]; const char* bref = an.assembly + an.contig_seq_off[bc]; const i32 blen = (i32) an.contig_len[bc];
+	// base i of the small gene's (possibly reverse-complemented) sequence
+	#define SMALL_AT(i) (rc ? complement_char(sref[ss + (i32) (len - 1 - (i))]) : sref[ss + (i32) (i)])
+#ifdef __CUDA_ARCH__
+	const float threshold = __fmul_rn((float) len, max_identity);
+#else
+	volatile float threshold_v = (float) len * max_identity; const float threshold = threshold_v;
+#endif
+	u32 matching = 0;
+	for (u32 pos = 0; pos + 16 < len; pos += 8) {
+		if ((float) (matching * 8 + (len - pos)) < threshold) return false;
+		u32 k = 0;
+		for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(SMALL_AT(pos + b));
+		u32 lo, hi; ix.bucket(bc, k, lo, hi);
+		for (u32 h = lower_bound_i32(ix.pos, lo, hi, bs); h < hi && ix.pos[h] <= be; ++h) {
+			const i32 hit = ix.pos[h];
+			if (!(sc != bc || hit < ss || hit > se)) continue;
+			bool same = true;
+			for (u32 b = 0; b < 8 && same; ++b) { const i32 g = hit + 8 + (i32) b; const char x = g < blen ? bref[g] : '\0'; if (x != SMALL_AT(pos + 8 + b)) same = false; }
+			if (same) { ++matching; if ((float) (matching * 8) >= threshold) return true; break; }
+		}
+	}
+	#undef SMALL_AT
+	return false;
+}
+struct homolog_pairs_fn { annot_view an; kmer_index_view ix; const u32* ga; const u32* gb; u8* out; float max_identity; ARB_HD void operator()(u32 j) const { out[j] = genes_are_homologs(an, ix, ga[j], gb[j], max_identity); } };
+
+} // namespace arb

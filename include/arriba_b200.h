@@ -152,6 +152,18 @@ typedef struct arb_evalue_inputs {
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
 
+/* ---- k-mer index of the fused genes, gene homology, re-alignment of supporting reads -----------------------------------
+ * arb_build_kmer_index replaces make_kmer_index (source/filter_mismappers.cpp:47): `intervals` are the disjoint, sorted unions of the
+ * gene windows [start - padding, end + padding) per contig, as [start, end_exclusive) of positions whose 8-mer is indexed.
+ * arb_homolog_pairs evaluates is_homolog (source/filter_homologs.cpp:13) for a batch of gene pairs; the order-dependent pairwise
+ * resolution of filter_homologs (:65-141) stays with the caller. arb_filter_mismappers replaces filter_mismappers
+ * (source/filter_mismappers.cpp:272); it needs current fragment labels (arb_set_fragment_filters) and candidate state. */
+int arb_set_splice_sites(arb_ctx* ctx, const uint32_t* off /* n_genes+1 */, const int32_t* sites); /* downstream splice sites per gene, ascending */
+int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* start, const int32_t* end_exclusive, uint32_t n_intervals, uint32_t n_index_contigs, uint64_t* n_indexed);
+int arb_kmer_index_digest(arb_ctx* ctx, uint64_t* kmers, uint64_t* positions, uint64_t* checksum, uint32_t n_contigs); /* per contig; checksum = sum((kmer*1000003+pos)*0x9E3779B97F4A7C15) */
+int arb_homolog_pairs(arb_ctx* ctx, const uint32_t* gene_a, const uint32_t* gene_b, uint32_t n, uint8_t* is_homolog_out);
+int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n_realigned);
+
 /* ---- device timing (CUDA events recorded on the context's stream around each stage) ---------------------------------- */
 typedef struct arb_timings {
 	float duplicates_ms;        /* duplicate marking (key build + hash group-by + mark) */
@@ -213,7 +225,8 @@ int arb_pipeline_coverage(arb_pipeline* p, uint32_t contig, const uint16_t** cov
 /* event-level chain (source/arriba.cpp:420-545): runs the stages up to and including `last_stage` (ARB_EV_*) */
 enum { ARB_EV_FETCH = 0, ARB_EV_MERGE_ADJACENT, ARB_EV_MULTIMAPPERS, ARB_EV_EVALUE, ARB_EV_NON_CODING_NEIGHBORS, ARB_EV_INTRAGENIC_EXONIC, ARB_EV_MIN_SUPPORT,
        ARB_EV_RELATIVE_SUPPORT, ARB_EV_ITD, ARB_EV_INTRONIC, ARB_EV_IN_VITRO, ARB_EV_SPLICED, ARB_EV_SELECT_BEST, ARB_EV_MARGINAL_READ_THROUGH, ARB_EV_MANY_SPLICED,
-       ARB_EV_SHORT_ANCHOR, ARB_EV_END_TO_END, ARB_EV_NO_COVERAGE, ARB_EV_COUNT };
+       ARB_EV_SHORT_ANCHOR, ARB_EV_END_TO_END, ARB_EV_NO_COVERAGE, ARB_EV_KMER_INDEX, ARB_EV_HOMOLOGS, ARB_EV_MISMAPPERS, ARB_EV_SELECT_BEST2, ARB_EV_ISOFORMS,
+       ARB_EV_CONFIDENCE, ARB_EV_COUNT };
 int arb_pipeline_events(arb_pipeline* p, int last_stage);
 /* read-only view of the host candidate table: the arb_candidates pointers alias pipeline memory; `order` = the reference's
    iteration order (candidate ids), `confidence` and the current fragment labels complete the state */

@@ -34,17 +34,24 @@ def check_events(world, lib_path, threads=4):
     got_keys = [key_of(got, int(i)) for i in got["order"]]
     assert got_keys == want_keys, "iteration order of the candidate table differs from the reference's unordered_map"
     stages = ["merge_adjacent", "multimappers", "evalue", "non_coding_neighbors", "intragenic_exonic", "min_support", "relative_support", "internal_tandem_duplication",
-              "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage"]
+              "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage",
+              "kmer_index", "homologs", "mismappers", "select_best", "isoforms", "confidence"]
+    occurrence = {}
     seen_evalue = False
     for s, name in enumerate(stages, start=1):
         p.events(s)
         got = p.candidates()
-        want = world.stage("ev_" + name)
+        if name == "kmer_index":
+            continue
+        occ = occurrence.get(name, 0); occurrence[name] = occ + 1
+        want = world.stage("ev_" + name, occ)
         seen_evalue = seen_evalue or name == "evalue"
         compare_stage(got, want, name, seen_evalue)
         if "frag_filter" in want:
             assert np.array_equal(got["labels"], want["frag_filter"]), (name, "fragment labels")
-        assert int((got["filter"] == 0).sum()) == int(want["remaining"][0]) or name == "evalue", name
+        assert int((got["filter"] == 0).sum()) == int(want["remaining"][0]) or name in ("evalue", "confidence"), name
+        if name == "confidence":
+            assert np.array_equal(got["confidence"], want["confidence"][compare_stage(got, want, name, True)])
     p.close()
 
 
