@@ -110,6 +110,7 @@ int arb_pipeline_coverage(arb_pipeline* x, uint32_t contig, const uint16_t** cov
 	PIPE_END(x)
 }
 
+int arb_pipeline_write_output(arb_pipeline* x) { PIPE_BEGIN(x) x->p.write_output(); PIPE_END(x) }
 int arb_pipeline_events(arb_pipeline* x, int last_stage) { PIPE_BEGIN(x) x->p.events_until(last_stage); PIPE_END(x) }
 
 int arb_pipeline_candidates(arb_pipeline* x, arb_candidates* c, const uint32_t** order, const uint8_t** confidence, const uint8_t** labels) {

@@ -1,0 +1,552 @@
+// output.cpp -- writer of fusions.tsv / fusions.discarded.tsv.
+// Behavioural contract: write_fusions_to_file and helpers (output_fusions.cpp:25-1261, without the optional gap filling -I),
+// get_fusion_peptide_sequence / is_in_frame / get_reading_frame / translate_reference_protein (annotate_protein_domains.cpp:164-446).
+// Tags (-t) and protein domains (-p) need database files that are not part of the reference repository; their columns are ".".
+#include "pipeline.h"
+#include "../annot_hd.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <tuple>
+
+namespace arb { namespace host {
+
+namespace {
+
+typedef std::map<i32, std::map<std::string, unsigned int> > pileup_t;
+
+char comp_char(char c) { // assembly.hpp:9-22
+	switch (c) {
+		case 'a': return 't'; case 't': return 'a'; case 'c': return 'g'; case 'g': return 'c';
+		case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C';
+		case '[': return ']'; case ']': return '['; default: return c;
+	}
+}
+std::string revcomp(const std::string& s) { std::string r; r.reserve(s.size()); for (size_t i = s.size(); i-- > 0;) r += comp_char(s[i]); return r; }
+
+struct writer {
+	pipeline& p; const event_table& e; const refdata& ref; const frag_view f; const u32 N;
+	explicit writer(pipeline& pl): p(pl), e(pl.ev), ref(pl.ref), f(pl.frags.view()), N(pl.frags.n) {}
+
+	std::string read_sequence(u32 frag, u32 slot) const {
+		const u32 a = f.idx(frag, slot); std::string s(f.seq_len[a], 'N'); const u8* q = f.sq(a);
+		for (u32 i = 0; i < f.seq_len[a]; ++i) s[i] = nt16_char(nt16_at(q, i));
+		return s;
+	}
+	bool has_assembly(u32 contig) const { return ref.has_sequence(contig); }
+
+	// ---- pileup of the supporting reads around one breakpoint (output_fusions.cpp:25-107)
+	void pileup_reads(const std::vector<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pileup_t& pileup) const {
+		std::map<std::pair<i32, i32>, unsigned int> introns;
+		for (u32 x = lo; x < hi; ++x) {
+			const u32 frag = list[x];
+			if (p.labels[frag] == F_duplicates) continue;
+			const u32 a = f.idx(frag, mate);
+			const bool fwd = f.fwd(a);
+			if (f.n_aln[frag] == 2 && !((direction == DOWNSTREAM && fwd && f.end[a] <= breakpoint + 2 && f.end[a] >= breakpoint - 200) || (direction == UPSTREAM && !fwd && f.start[a] >= breakpoint - 2 && f.start[a] <= breakpoint + 200))) continue;
+			if (f.n_aln[frag] == 3 && (mate == SPLIT_READ || mate == SUPPLEMENTARY) && f.start[a] != breakpoint && f.end[a] != breakpoint) continue;
+			std::string seq = read_sequence(frag, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
+			if (reverse_complement) seq = revcomp(seq);
+			i32 read_off = 0, ref_off = f.start[a]; int carry = 0; // carry: one base was already consumed by a preceding insertion
+			const u32* c = f.cig(a); const u32 nc = f.cigar_cnt[a];
+			auto piece = [&](i32 off, size_t n) { return (size_t) off <= seq.size() ? seq.substr(off, n) : std::string(); };
+			for (u32 k = 0; k < nc; ++k) {
+				const u32 op = cig_op(c[k]); const i32 len = (i32) cig_len(c[k]);
+				bool as_match = false;
+				switch (op) {
+					case C_I: ++pileup[ref_off][piece(read_off, len + 1)]; read_off += len + 1; ++ref_off; carry = 1; break;
+					case C_N: { const i32 s0 = ref_off; ref_off += len - carry; ++introns[std::make_pair(s0, ref_off - 1)]; carry = 0; break; }
+					case C_D: for (i32 b = 0; b < len - carry; ++b, ++ref_off) ++pileup[ref_off]["-"]; carry = 0; break;
+					case C_H: if (mate == SUPPLEMENTARY) read_off += len; break;
+					case C_S:
+						if (f.n_aln[frag] == 3 && mate == SPLIT_READ && ((k == 0 && fwd) || (k == nc - 1 && !fwd))) { if (k == 0 && fwd) ref_off -= len; as_match = true; } // clipped segment joins the pileup (non-template bases)
+						else read_off += len - carry;
+						break;
+					case C_M: case C_EQ: case C_X: as_match = true; break;
+					default: break;
+				}
+				if (as_match) { for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) ++pileup[ref_off][piece(read_off, 1)]; carry = 0; }
+			}
+		}
+		for (std::map<std::pair<i32, i32>, unsigned int>::iterator it = introns.begin(); it != introns.end(); ++it) {
+			pileup[it->first.first][">"] += it->second; pileup[it->first.second]["<"] += it->second;
+			for (i32 i = it->first.first + 1; i < it->first.second; ++i) pileup[i]["_"] += it->second;
+		}
+	}
+
+	// ---- consensus of a pileup (output_fusions.cpp:109-240)
+	void consensus(const pileup_t& pileup, i32 breakpoint, u32 direction, u32 gene, std::string& sequence, std::vector<i32>& positions, std::string& clipped) const {
+		unsigned int peak = 0;
+		for (pileup_t::const_iterator pos = pileup.begin(); pos != pileup.end(); ++pos) { unsigned int cov = 0; for (auto b = pos->second.begin(); b != pos->second.end(); ++b) cov += b->second; if (cov > peak) peak = cov; }
+		const float low_fraction = 0.10f;
+		pileup_t::const_iterator first = pileup.begin(), last = pileup.end();
+		for (pileup_t::const_iterator pos = pileup.begin(); pos != pileup.end(); ++pos) {
+			unsigned int cov = 0; for (auto b = pos->second.begin(); b != pos->second.end(); ++b) cov += b->second;
+			if (direction == DOWNSTREAM) { if (cov < peak * low_fraction) first = pos; else break; }
+			else if (cov > peak * low_fraction) last = pos;
+		}
+		if (last != pileup.end()) ++last;
+		bool intron_open = false, intron_closed = true;
+		const u32 contig = ref.genes[gene].contig;
+		for (pileup_t::const_iterator pos = first; pos != last; ++pos) {
+			if (pos != first && std::prev(pos)->first < pos->first - 1 && !intron_open) { sequence += "..."; positions.resize(positions.size() + 3, -1); }
+			std::string ref_base = "N";
+			if (has_assembly(contig) && (u32) pos->first < ref.seq_len[contig]) ref_base = std::string(1, ref.sequence(contig)[pos->first]);
+			auto best = pos->second.end(); unsigned int cov = 0;
+			for (auto b = pos->second.begin(); b != pos->second.end(); ++b) {
+				const bool is_intron = b->first == "_" || b->first == ">" || b->first == "<";
+				if (best == pos->second.end() || b->second > best->second ||
+				    (b->second == best->second && ((b->first == ref_base && best->first != "_" && best->first != ">" && best->first != "<") || (b->first == "<" && best->first != "_" && best->first != ">") || (b->first == "_" || b->first == ">")))) best = b;
+				if (!is_intron) cov += b->second;
+			}
+			std::string call = (((best->first == "_" || best->first == ">" || best->first == "<") && best->second >= cov) || best->second >= 0.75 * cov || best->first == ref_base) ? best->first : "?";
+			if (call == "_") { if (!intron_open) { sequence += "...___"; positions.resize(positions.size() + 6, -1); intron_open = true; intron_closed = false; } }
+			else if (call == ">") { if (!intron_open) { sequence += "___"; positions.resize(positions.size() + 3, -1); intron_open = true; intron_closed = false; } }
+			else if (call == "<") { if (!intron_open) { sequence += "...___"; positions.resize(positions.size() + 6, -1); } intron_open = true; intron_closed = true; }
+			else {
+				if (!intron_closed) { sequence += "..."; positions.resize(positions.size() + 3, -1); }
+				intron_open = false; intron_closed = true;
+				if (call.size() > 1 || (call != ref_base && ref_base != "N")) for (size_t i = 0; i < call.size(); ++i) call[i] = (char) tolower(call[i]);
+				if (call.size() > 1) { // insertion: [inserted]next
+					call = "[" + call.substr(0, call.size() - 1) + "]" + call[call.size() - 1];
+					positions.resize(positions.size() + call.size() - 1, -1);
+					if (toupper(call[call.size() - 1]) == ref_base[0]) call[call.size() - 1] = (char) toupper(call[call.size() - 1]);
+				}
+				if ((direction == UPSTREAM && pos->first < breakpoint) || (direction == DOWNSTREAM && pos->first > breakpoint)) clipped += call;
+				else { sequence += call; positions.push_back(pos->first); }
+			}
+		}
+	}
+
+	static bool lower_acgt(char c) { return c == 'a' || c == 't' || c == 'c' || c == 'g'; }
+
+	// ---- fusion transcript (output_fusions.cpp:242-466)
+	void transcript_sequence(u32 k, std::string& sequence, std::vector<i32>& positions) const {
+		const bool strands_ambiguous = e.bits[k] & CB_PSTRANDS_AMBIGUOUS, tstart_ambiguous = e.bits2[k] & 1;
+		if (strands_ambiguous || tstart_ambiguous) { sequence = "."; positions.push_back(-1); return; }
+		const u32 d1 = e.dir1[k], d2 = e.dir2[k]; const i32 bp1 = e.bp1[k], bp2 = e.bp2[k];
+		pileup_t pile1, pile2;
+		const u32 a1 = e.list1_off[k], b1 = e.list1_off[k + 1], a2 = e.list2_off[k], b2 = e.list2_off[k + 1], ad = e.listd_off[k], bd = e.listd_off[k + 1];
+		pileup_reads(e.list1, a1, b1, SPLIT_READ, false, d1, bp1, pile1);
+		pileup_reads(e.list1, a1, b1, MATE1, false, d1, bp1, pile1);
+		pileup_reads(e.list1, a1, b1, SUPPLEMENTARY, d1 == d2, d2, bp2, pile2);
+		pileup_reads(e.list2, a2, b2, SPLIT_READ, false, d2, bp2, pile2);
+		pileup_reads(e.list2, a2, b2, MATE1, false, d2, bp2, pile2);
+		pileup_reads(e.list2, a2, b2, SUPPLEMENTARY, d1 == d2, d1, bp1, pile1);
+		pileup_reads(e.listd, ad, bd, MATE1, false, d1, bp1, pile1);
+		pileup_reads(e.listd, ad, bd, MATE2, false, d1, bp1, pile1);
+		pileup_reads(e.listd, ad, bd, MATE1, false, d2, bp2, pile2);
+		pileup_reads(e.listd, ad, bd, MATE2, false, d2, bp2, pile2);
+		// non-template bases between the fused segments: most frequent surplus of clipped bases over the read length
+		unsigned int non_template = 0; std::map<unsigned int, unsigned int> count;
+		for (int which = 0; which < 2; ++which) {
+			const std::vector<u32>& list = which == 0 ? e.list1 : e.list2;
+			for (u32 x = which == 0 ? a1 : a2; x < (which == 0 ? b1 : b2); ++x) {
+				const u32 s = f.idx(list[x], SPLIT_READ), u = f.idx(list[x], SUPPLEMENTARY);
+				const unsigned int cs = f.fwd(s) ? f.preclip(s) : f.postclip(s), cu = f.fwd(u) ? f.postclip(u) : f.preclip(u);
+				if (cs + cu >= f.seq_len[s]) { const unsigned int unmapped = cs + cu - f.seq_len[s]; if (++count[unmapped] > count[non_template]) non_template = unmapped; }
+			}
+		}
+		std::string s1, s2, c1, c2; std::vector<i32> p1, p2;
+		consensus(pile1, bp1, d1, e.gene1[k], s1, p1, c1);
+		consensus(pile2, bp2, d2, e.gene2[k], s2, p2, c2);
+		if (e.n_list1(k) + e.n_list2(k) == 0) { // breakpoints are not known exactly
+			if (d1 == DOWNSTREAM) { s1 += "..."; p1.resize(p1.size() + 3, -1); } else { s1 = "..." + s1; p1.insert(p1.begin(), 3, -1); }
+			if (d2 == DOWNSTREAM) { s2 += "..."; p2.resize(p2.size() + 3, -1); } else { s2 = "..." + s2; p2.insert(p2.begin(), 3, -1); }
+		}
+		if (non_template > 0) {
+			auto lower = [](std::string& s) { for (size_t i = 0; i < s.size(); ++i) s[i] = (char) tolower(s[i]); };
+			if (c1.size() >= non_template) {
+				lower(c1);
+				if (d1 == UPSTREAM) { s1 = c1.substr(c1.size() - non_template) + s1; p1.insert(p1.begin(), non_template, -1); } else { s1 += c1.substr(0, non_template); p1.resize(p1.size() + non_template, -1); }
+			} else if (c2.size() >= non_template) {
+				lower(c2);
+				if (d2 == UPSTREAM) { s2 = c2.substr(c2.size() - non_template) + s2; p2.insert(p2.begin(), non_template, -1); } else { s2 += c2.substr(0, non_template); p2.resize(p2.size() + non_template, -1); }
+			}
+		}
+		// mismatching (lower-case) bases right at the junction are set off by a pipe
+		auto mark = [&](std::string& s, std::vector<i32>& pos, u32 direction) {
+			if (direction == UPSTREAM) {
+				int b = 0; while (b < (int) s.size() && lower_acgt(s[b])) ++b;
+				if (b > 0 && b < (int) s.size()) { s = s.substr(0, b) + "|" + s.substr(b); std::fill(pos.begin(), pos.begin() + b, -1); pos.insert(pos.begin() + b, -1); return true; }
+			} else {
+				int b = (int) s.size() - 1; while (b >= 0 && lower_acgt(s[b])) --b;
+				if (b + 1 < (int) s.size() && b >= 0) { s = s.substr(0, b + 1) + "|" + s.substr(b + 1); std::fill(pos.begin() + b + 1, pos.end(), -1); pos.insert(pos.begin() + b + 1, -1); return true; }
+			}
+			return false;
+		};
+		const bool nt1 = mark(s1, p1, d1), nt2 = mark(s2, p2, d2);
+		const bool ps1 = e.bits[k] & CB_PSTRAND1, ps2 = e.bits[k] & CB_PSTRAND2;
+		if (e.bits[k] & CB_TSTART_GENE1) {
+			sequence = ps1 ? s1 : revcomp(s1); if (!ps1) std::reverse(p1.begin(), p1.end()); positions = p1;
+			if (!nt1 || !nt2) { sequence += "|"; positions.push_back(-1); }
+			sequence += d2 == UPSTREAM ? s2 : revcomp(s2); if (d2 != UPSTREAM) std::reverse(p2.begin(), p2.end());
+			positions.insert(positions.end(), p2.begin(), p2.end());
+		} else {
+			sequence = ps2 ? s2 : revcomp(s2); if (!ps2) std::reverse(p2.begin(), p2.end()); positions = p2;
+			if (!nt2 || !nt1) { sequence += "|"; positions.push_back(-1); }
+			sequence += d1 == UPSTREAM ? s1 : revcomp(s1); if (d1 != UPSTREAM) std::reverse(p1.begin(), p1.end());
+			positions.insert(positions.end(), p1.begin(), p1.end());
+		}
+		// "...A..." and the like collapse to "..."
+		size_t e1 = 0, e2 = std::string::npos;
+		while ((e1 = sequence.find("...", e1)) < sequence.size()) {
+			if ((e2 = sequence.find("...", e1 + 3)) < e1 + 10 + 3 && sequence.find('|', e1 + 3) > e2) { sequence.replace(e1 + 3, e2 - e1, ""); positions.erase(positions.begin() + e1 + 3, positions.begin() + e2 + 3); }
+			else e1 += 3;
+		}
+		static const char* simplify[][2] = {{"...___|", "|"}, {"|___...", "|"}, {"___|", "...|"}, {"|___", "|..."}, {"______", "___"}, {"___...___", "___"}, {"...___...", "..."}, {"......", "..."}};
+		size_t at = std::string::npos;
+		do {
+			for (size_t r = 0; r < 8; ++r) {
+				const std::string from = simplify[r][0], to = simplify[r][1];
+				if ((at = sequence.find(from)) < sequence.size()) { sequence.replace(at, from.size(), to); if (from.size() > to.size()) positions.erase(positions.begin() + at, positions.begin() + at + from.size() - to.size()); break; }
+			}
+		} while (at != std::string::npos);
+		while (sequence.substr(0, 3) == "..." || sequence.substr(0, 3) == "___") { sequence = sequence.substr(3); positions.erase(positions.begin(), positions.begin() + 3); }
+		while (sequence.size() >= 3 && (sequence.substr(sequence.size() - 3) == "..." || sequence.substr(sequence.size() - 3) == "___")) { sequence = sequence.substr(0, sequence.size() - 3); positions.erase(positions.begin() + positions.size() - 3, positions.end()); }
+		if (sequence == "" || sequence == "|" || sequence == "...|" || sequence == "|..." || sequence == "...|...") { sequence = "."; positions.clear(); positions.push_back(-1); return; }
+		for (size_t i = 0; i < sequence.size(); ++i) if (sequence[i] == 'n' || sequence[i] == 'N') sequence[i] = '?';
+	}
+
+	// ---- annotated transcripts matching the transcribed bases (output_fusions.cpp:720-818)
+	void matching_transcripts(const std::string& seq, const std::vector<i32>& bases, u32 gene, bool strand, bool strand_ambiguous, int which_end, std::vector<i32>& best) const {
+		if (strand_ambiguous || strand != ref.genes[gene].forward) return;
+		size_t from, to, breakpoint;
+		if (which_end == 5) {
+			from = 0; to = seq.find('|'); if (to >= seq.size()) return;
+			while (to > 0 && bases[to] == -1) --to;
+			if (bases[to] == -1) return;
+			breakpoint = to;
+		} else {
+			from = seq.find_last_of('|');
+			while (from < seq.size() && bases[from] == -1) ++from;
+			if (from >= seq.size()) return;
+			breakpoint = from; to = seq.size() - 1;
+		}
+		if (bases[from] > bases[to]) std::swap(from, to);
+		std::map<u32, unsigned int> score, peak, utr; std::map<u32, bool> coding_at_bp;
+		const region_index& ix = ref.exon_index;
+		const u32 contig = ref.genes[gene].contig, lo = ix.begin[contig], hi = ix.begin[contig + 1];
+		size_t position = from;
+		const size_t pmin = std::min(from, to), pmax = std::max(from, to);
+		for (u32 r = (u32) (std::lower_bound(ix.end.begin() + lo, ix.end.begin() + hi, bases[from]) - ix.end.begin()); r < hi && position >= pmin && position <= pmax; ++r) {
+			i32 last_transcribed = bases[to];
+			while (position >= pmin && position <= pmax && bases[position] <= ix.end[r]) {
+				for (u32 x = ix.off[r]; x < ix.off[r + 1]; ++x) {
+					const u32 ex = ix.items[x]; const exon_rec& E = ref.exons[ex];
+					if (E.gene != gene || bases[position] < E.start || bases[position] > E.end) continue;
+					const transcript_rec& T = ref.transcripts[E.transcript];
+					++score[E.transcript]; last_transcribed = bases[position];
+					if ((i32) ex == T.first_exon || (i32) ex == T.last_exon) ++utr[E.transcript];
+					if (position == breakpoint) {
+						if (bases[position] >= E.cds_start && bases[position] <= E.cds_end) coding_at_bp[E.transcript] = true;
+						if ((std::abs(bases[position] - E.start) <= 2 && (i32) ex != T.first_exon) || (std::abs(bases[position] - E.end) <= 2 && (i32) ex != T.last_exon)) score[E.transcript] += 10;
+					}
+				}
+				position += (from <= to) ? +1 : -1;
+			}
+			for (u32 x = ix.off[r]; x < ix.off[r + 1]; ++x) {
+				const exon_rec& E = ref.exons[ix.items[x]];
+				if (E.gene != gene) continue;
+				peak[E.transcript] = std::max(score[E.transcript], peak[E.transcript]);
+				const i32 exon_start = r != lo ? ix.end[r - 1] : E.start - 1;
+				const unsigned int exon_length = std::min(ix.end[r], bases[to]) - std::max(last_transcribed + 1, exon_start) + 1;
+				score[E.transcript] -= std::min(exon_length, score[E.transcript]);
+			}
+		}
+		if (peak.empty()) return;
+		// the reference walks an unordered_map keyed by pointer; transcripts are visited in id order here
+		best.push_back((i32) peak.begin()->first);
+		for (std::map<u32, unsigned int>::iterator t = std::next(peak.begin()); t != peak.end(); ++t) {
+			const u32 b0 = (u32) best[0];
+			if (t->second == peak[b0] && coding_at_bp[b0] == coding_at_bp[t->first]) best.push_back((i32) t->first);
+			else if (t->second > peak[b0] || (!coding_at_bp[b0] && coding_at_bp[t->first] && (t->second == peak[b0] || (utr[t->first] > 0 && utr[b0] > 0 && t->second - utr[t->first] >= peak[b0] - utr[b0])))) { best.clear(); best.push_back((i32) t->first); }
+		}
+		if (peak[(u32) best[0]] == 0) best.clear();
+		std::sort(best.begin(), best.end(), [&](i32 x, i32 y) {
+			const transcript_rec& X = ref.transcripts[x]; const transcript_rec& Y = ref.transcripts[y];
+			const int lx = ref.exons[X.last_exon].end - ref.exons[X.first_exon].start, ly = ref.exons[Y.last_exon].end - ref.exons[Y.first_exon].start;
+			return X.coding_length > Y.coding_length || (X.coding_length == Y.coding_length && lx > ly) || (X.coding_length == Y.coding_length && lx == ly && X.id < Y.id);
+		});
+		if (best.size() > 1) best.push_back(best[0]);
+	}
+
+	// ---- peptide (annotate_protein_domains.cpp:164-400)
+	static char translate(const std::string& triplet) {
+		std::string t = triplet; for (size_t i = 0; i < t.size(); ++i) t[i] = (char) toupper(t[i]);
+		const std::string d = t.substr(0, 2);
+		if (d == "GC") return 'A'; if (t == "TGT" || t == "TGC") return 'C'; if (t == "GAT" || t == "GAC") return 'D'; if (t == "GAA" || t == "GAG") return 'E';
+		if (t == "TTT" || t == "TTC") return 'F'; if (d == "GG") return 'G'; if (t == "CAT" || t == "CAC") return 'H'; if (t == "ATT" || t == "ATC" || t == "ATA") return 'I';
+		if (t == "AAA" || t == "AAG") return 'K'; if (d == "CT" || t == "TTA" || t == "TTG") return 'L'; if (t == "ATG") return 'M'; if (t == "AAT" || t == "AAC") return 'N';
+		if (d == "CC") return 'P'; if (t == "CAA" || t == "CAG") return 'Q'; if (d == "CG" || t == "AGA" || t == "AGG") return 'R'; if (d == "TC" || t == "AGT" || t == "AGC") return 'S';
+		if (d == "AC") return 'T'; if (d == "GT") return 'V'; if (t == "TGG") return 'W'; if (t == "TAT" || t == "TAC") return 'Y'; if (t == "TAA" || t == "TAG" || t == "TGA") return '*';
+		return '?';
+	}
+	i32 next_in_transcript(i32 ex, bool forward) const { if (ex < 0) return -1; const i32 n = forward ? ref.exons[ex].next : ref.exons[ex].prev; return n >= 0 ? n : -1; }
+	void reference_protein(i32 start_exon, std::map<i32, char>& protein) const {
+		if (start_exon < 0) return;
+		const bool fwd = ref.genes[ref.exons[start_exon].gene].forward;
+		const char* seq = ref.sequence(ref.genes[ref.exons[start_exon].gene].contig);
+		std::string codon; bool reported = false;
+		for (i32 ex = start_exon; ex >= 0; ex = next_in_transcript(ex, fwd)) {
+			const exon_rec& E = ref.exons[ex];
+			for (i32 pos = fwd ? E.cds_start : E.cds_end; pos != -1 && pos >= E.cds_start && pos <= E.cds_end; pos += fwd ? +1 : -1) {
+				codon += fwd ? seq[pos] : comp_char(seq[pos]);
+				if (codon.size() == 3) {
+					protein[pos] = translate(codon); codon.clear();
+					if (!reported && pos < E.cds_end && pos > E.cds_start && protein[pos] == '*') {
+						std::cerr << "WARNING: encountered early stop codon in transcript " << ref.transcripts[E.transcript].name << " at amino acid " << protein.size() << " (error in GTF file?) => predicted peptide sequence may be wrong" << std::endl;
+						reported = true;
+					}
+				}
+			}
+		}
+	}
+	int reading_frame(const std::vector<i32>& bases, int from, int to, i32 transcript, u32 gene, i32& start_exon) const {
+		const bool fwd = ref.genes[gene].forward;
+		start_exon = transcript < 0 ? -1 : (fwd ? ref.transcripts[transcript].first_exon : ref.transcripts[transcript].last_exon);
+		while (start_exon >= 0 && ref.exons[start_exon].cds_start == -1) start_exon = next_in_transcript(start_exon, fwd);
+		if (start_exon < 0) return -1;
+		const u32 contig = ref.genes[gene].contig;
+		std::string first_codon;
+		{
+			const i64 at = fwd ? (i64) ref.exons[start_exon].cds_start : (i64) ref.exons[start_exon].cds_end - 2;
+			for (i64 x = at; x < at + 3; ++x) if (x >= 0 && x < (i64) ref.seq_len[contig]) first_codon += ref.sequence(contig)[x];
+			if (!fwd) first_codon = revcomp(first_codon);
+		}
+		if (first_codon != "ATG") return -1;
+		int frame = -1; i32 coding_base = -1;
+		for (i32 ex = start_exon; ex >= 0 && ref.exons[ex].cds_start != -1 && coding_base == -1; ex = next_in_transcript(ex, fwd)) {
+			const exon_rec& E = ref.exons[ex];
+			for (int pos = from; pos <= to && coding_base == -1; ++pos) if (E.cds_start <= bases[pos] && E.cds_end >= bases[pos]) coding_base = pos;
+			if (coding_base == -1) frame = (frame + E.cds_end - E.cds_start + 1) % 3;
+			else { frame += fwd ? bases[coding_base] - E.cds_start : E.cds_end - bases[coding_base]; frame = (frame + 1) % 3; }
+		}
+		if (coding_base == -1) return -1;
+		for (int pos = coding_base - 1; pos >= from; --pos) if (bases[pos] != -1) frame = frame == 0 ? 2 : frame - 1;
+		return frame;
+	}
+	std::string peptide(const std::string& seq, const std::vector<i32>& pos, u32 gene5, u32 gene3, i32 tr5, i32 tr3, bool strand3) const {
+		if (seq.empty() || seq == "." || seq.find("...|") < seq.size() || seq.find("|...") < seq.size()) return ".";
+		if (!has_assembly(ref.genes[gene5].contig) || !has_assembly(ref.genes[gene3].contig)) return ".";
+		size_t end5 = seq.find('|') - 1, start5 = seq.rfind("...", end5);
+		if (start5 >= seq.size()) start5 = 0; else while (pos[start5] == -1 && seq[start5] != '|') ++start5;
+		size_t nt_len = seq.find('|', end5 + 2);
+		if (nt_len >= seq.size()) nt_len = 0; else nt_len -= end5 + 2;
+		size_t start3 = end5 + 2; if (nt_len > 0) start3 += nt_len + 1;
+		size_t end3 = seq.find("...", start3);
+		if (end3 >= seq.size()) end3 = seq.size() - 1; else --end3;
+		i32 ex5 = -1, ex3 = -1;
+		int frame5 = reading_frame(pos, (int) start5, (int) end5, tr5, gene5, ex5);
+		if (frame5 == -1) return "."; else if (frame5 != 0) frame5 = 3 - frame5;
+		int frame3 = -1;
+		if (ref.genes[gene3].forward == strand3) frame3 = reading_frame(pos, (int) start3, (int) end3, tr3, gene3, ex3);
+		std::map<i32, char> prot5, prot3;
+		reference_protein(ex5, prot5); reference_protein(ex3, prot3);
+		std::string pep; int c5 = 0, c3 = 0; bool started = false; std::string codon;
+		const bool g5fwd = ref.genes[gene5].forward;
+		for (size_t i = start5 + frame5; i < end3; ++i) {
+			if (!started) {
+				if (pos[i] != -1 && ((g5fwd && pos[i] >= ref.exons[ex5].cds_start) || (!g5fwd && pos[i] <= ref.exons[ex5].cds_end))) started = true; else continue;
+			}
+			const char ch = seq[i];
+			if (ch == 'A' || ch == 'T' || ch == 'C' || ch == 'G' || ch == 'a' || ch == 't' || ch == 'c' || ch == 'g' || ch == '?') {
+				if (codon.empty()) { c5 = 0; c3 = 0; }
+				if (i <= end5) ++c5; else if (i >= start3) ++c3;
+				codon += ch;
+			}
+			if (codon.size() == 3) {
+				char aa = translate(codon);
+				const std::map<i32, char>& prot = i <= end5 ? prot5 : prot3;
+				std::map<i32, char>::const_iterator hit = prot.find(pos[i]);
+				if ((i > end5 && i < start3) || hit == prot.end() || aa != hit->second || (c5 != 3 && i <= end5) || (c3 != 3 && i >= start3) || (i >= start3 && frame3 == -1)) aa = (char) tolower(aa);
+				pep += aa; codon.clear();
+				if (c3 >= 2 && aa == '*') break;
+			}
+			if ((i == end5 && codon.size() <= 1) || (c5 == 2 && codon.size() == 0)) if (pep.empty() || pep[pep.size() - 1] != '|') pep += '|';
+			if (nt_len > 0 && ((i + 2 == start3 && codon.size() <= 1) || (c3 == 1 && codon.size() == 0))) if (pep.empty() || pep[pep.size() - 1] != '|') pep += '|';
+		}
+		return pep.empty() ? "." : pep;
+	}
+	static std::string frame_label(const std::string& pep) { // is_in_frame (annotate_protein_domains.cpp:402-446)
+		if (pep == "." || pep.empty() || pep[pep.size() - 1] == '|') return ".";
+		const size_t junction = pep.rfind('|'), stop = pep.rfind('*', junction);
+		size_t start_after = pep.find('m', stop); if (start_after >= junction) start_after = pep.find('M', stop);
+		if (stop < junction && start_after >= junction) return "stop-codon";
+		auto upper_in = [&](size_t a, size_t b) { for (size_t i = a; i < b; ++i) if (pep[i] >= 'A' && pep[i] <= 'Z') return true; return false; };
+		if (stop < junction && upper_in(0, stop) && !upper_in(stop + 1, junction)) return "stop-codon";
+		const bool in5 = upper_in(stop < junction ? stop + 1 : 0, junction), in3 = upper_in(junction + 1, pep.size());
+		return in5 && in3 ? "in-frame" : "out-of-frame";
+	}
+
+	// ---- small descriptive columns
+	std::string gene_name(u32 gene, u32 contig, i32 bp) const { // output_fusions.cpp:498-545
+		if (!ref.genes[gene].is_dummy) return ref.genes[gene].name;
+		const region_index& ix = ref.gene_index; const u32 lo = ix.begin[contig], hi = ix.begin[contig + 1];
+		const u32 hit = (u32) (std::lower_bound(ix.end.begin() + lo, ix.end.begin() + hi, bp) - ix.end.begin());
+		auto annotated = [&](u32 r) { return ix.off[r + 1] > ix.off[r] && !ref.genes[ix.items[ix.off[r]]].is_dummy; };
+		std::string result;
+		i64 up = (i64) hit - 1; while (up >= (i64) lo && !annotated((u32) up)) --up;
+		if (up >= (i64) lo) for (u32 x = ix.off[up]; x < ix.off[up + 1]; ++x) { const gene_rec& g = ref.genes[ix.items[x]]; if (g.is_dummy) continue; if (!result.empty()) result += ","; result += g.name + "(" + std::to_string((long long) (bp - g.end)) + ")"; }
+		u32 down = hit; while (down < hi && !annotated(down)) ++down;
+		if (down < hi) for (u32 x = ix.off[down]; x < ix.off[down + 1]; ++x) { const gene_rec& g = ref.genes[ix.items[x]]; if (g.is_dummy) continue; if (!result.empty()) result += ","; result += g.name + "(" + std::to_string((long long) (g.start - bp)) + ")"; }
+		return result.empty() ? "." : result;
+	}
+	std::string fusion_type(u32 k) const { // output_fusions.cpp:547-633
+		const gene_rec& g1 = ref.genes[e.gene1[k]]; const gene_rec& g2 = ref.genes[e.gene2[k]];
+		const u32 d1 = e.dir1[k], d2 = e.dir2[k]; const bool dummy = g1.is_dummy || g2.is_dummy;
+		if (e.contig1[k] != e.contig2[k]) {
+			if (dummy || (d1 == d2 && g1.forward != g2.forward) || (d1 != d2 && g1.forward == g2.forward)) return "translocation";
+			if (((d1 == UPSTREAM && g1.forward) || (d1 == DOWNSTREAM && !g1.forward)) && ((d2 == UPSTREAM && g2.forward) || (d2 == DOWNSTREAM && !g2.forward))) return "translocation/3'-3'";
+			return "translocation/5'-5'";
+		}
+		const bool rt = e.is_read_through(k);
+		if (d1 == DOWNSTREAM && d2 == UPSTREAM) {
+			if (dummy || g1.forward == g2.forward) return rt ? "deletion/read-through" : "deletion";
+			if (g1.forward || !g2.forward) return rt ? "deletion/read-through/5'-5'" : "deletion/5'-5'";
+			return rt ? "deletion/read-through/3'-3'" : "deletion/3'-3'";
+		}
+		if (d1 == d2) { if (dummy || g1.forward != g2.forward) return "inversion"; return (d1 == UPSTREAM && !g1.forward) ? "inversion/5'-5'" : "inversion/3'-3'"; }
+		if (dummy || g1.forward == g2.forward) {
+			if (e.gene1[k] == e.gene2[k] && e.spliced1(k) && e.spliced2(k)) return "duplication/non-canonical_splicing";
+			if (e.gene1[k] == e.gene2[k] && ((unsigned int) e.bp2[k] - (unsigned int) e.bp1[k]) < p.opt.params.max_itd_length && d1 == UPSTREAM && d2 == DOWNSTREAM) return "duplication/ITD";
+			return "duplication";
+		}
+		return !g1.forward ? "duplication/5'-5'" : "duplication/3'-3'";
+	}
+	std::string strand_column(bool strand, u32 gene, bool ambiguous) const { std::string r = ref.genes[gene].is_dummy ? "." : (ref.genes[gene].forward ? "+" : "-"); r += "/"; r += ambiguous ? "." : (strand ? "+" : "-"); return r; }
+	std::string site(u32 gene, bool spliced, bool exonic, u32 contig, i32 bp) const { // output_fusions.cpp:635-709
+		const gene_rec& g = ref.genes[gene];
+		if (g.is_dummy || bp < g.start || bp > g.end) return "intergenic";
+		if (!exonic) return "intron";
+		const annot_view an = const_cast<refdata&>(ref).host_view();
+		idset<64> exons; query_index(exon_index(an), contig, bp, bp, exons);
+		bool overlapping = false, utr = true; unsigned int end3 = 0, end5 = 0;
+		for (u32 x = 0; x < exons.n; ++x) {
+			const exon_rec& E = ref.exons[exons.v[x]];
+			if (E.gene != gene) continue;
+			overlapping = true;
+			if (E.cds_start <= bp && E.cds_end >= bp) utr = false;
+			if (utr && g.is_protein_coding) {
+				if (E.cds_start != -1 && E.cds_start > bp) { if (g.forward) ++end5; else ++end3; }
+				else if (E.cds_end != -1 && E.cds_end < bp) { if (!g.forward) ++end5; else ++end3; }
+				else {
+					i32 nx = E.next >= 0 ? E.next : -1; while (nx >= 0 && ref.exons[nx].cds_start == -1) nx = ref.exons[nx].next >= 0 ? ref.exons[nx].next : -1;
+					i32 pv = E.prev >= 0 ? E.prev : -1; while (pv >= 0 && ref.exons[pv].cds_start == -1) pv = ref.exons[pv].prev >= 0 ? ref.exons[pv].prev : -1;
+					if (pv >= 0 || nx >= 0) { if ((nx < 0) != (!g.forward)) ++end3; else ++end5; }
+				}
+			}
+		}
+		std::string s;
+		if (!overlapping) s = "intron";
+		else if (g.is_protein_coding) { if (utr) s = end3 > end5 ? "3'UTR" : end3 < end5 ? "5'UTR" : end3 + end5 == 0 ? "exon" : "UTR"; else s = "CDS"; }
+		else s = "exon";
+		if (spliced && s != "intron") s += "/splice-site";
+		return s;
+	}
+
+	bool by_support(u32 x, u32 y) const { // output_fusions.cpp:468-483
+		if (e.confidence[x] != e.confidence[y]) return e.confidence[x] > e.confidence[y];
+		if (e.supporting_reads(x) != e.supporting_reads(y)) return e.supporting_reads(x) > e.supporting_reads(y);
+		if (e.evalue[x] != e.evalue[y]) return e.evalue[x] < e.evalue[y];
+		if (e.gene1[x] != e.gene1[y]) return e.gene1[x] < e.gene1[y];
+		if (e.gene2[x] != e.gene2[y]) return e.gene2[x] < e.gene2[y];
+		if (e.bp1[x] != e.bp1[y]) return e.bp1[x] < e.bp1[y];
+		return e.bp2[x] < e.bp2[y];
+	}
+
+	void write(const std::string& path, bool discarded, bool extra_info) const {
+		std::vector<u32> rows;
+		for (size_t q = 0; q < e.order.size(); ++q) { const u32 k = e.order[q]; if (discarded != (e.filter[k] == F_none)) rows.push_back(k); }
+		if (!discarded) {
+			std::map<std::pair<u32, u32>, u32> best; // best-supported candidate per gene pair
+			for (size_t x = 0; x < rows.size(); ++x) {
+				std::pair<std::map<std::pair<u32, u32>, u32>::iterator, bool> ins = best.insert(std::make_pair(std::make_pair(e.gene1[rows[x]], e.gene2[rows[x]]), rows[x]));
+				if (!ins.second && by_support(rows[x], ins.first->second)) ins.first->second = rows[x];
+			}
+			std::sort(rows.begin(), rows.end(), [&](u32 x, u32 y) {
+				const u32 bx = best.at(std::make_pair(e.gene1[x], e.gene2[x])), by = best.at(std::make_pair(e.gene1[y], e.gene2[y]));
+				return bx != by ? by_support(bx, by) : by_support(x, y);
+			});
+		}
+		std::ofstream out(path.c_str());
+		if (!out.is_open()) throw std::runtime_error("failed to open output file");
+		out << "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers" << std::endl;
+		static const char* CONF[] = {"low", "medium", "high", "high"};
+		for (size_t x = 0; x < rows.size(); ++x) {
+			const u32 k = rows[x];
+			std::string site5 = site(e.gene1[k], e.spliced1(k), e.exonic1(k), e.contig1[k], e.bp1[k]), site3 = site(e.gene2[k], e.spliced2(k), e.exonic2(k), e.contig2[k], e.bp2[k]);
+			u32 g5 = e.gene1[k], g3 = e.gene2[k], c5 = e.contig1[k], c3 = e.contig2[k], d5 = e.dir1[k], d3 = e.dir2[k], s5 = e.split_reads1[k], s3 = e.split_reads2[k];
+			i32 b5 = e.bp1[k], b3 = e.bp2[k]; bool st5 = e.bits[k] & CB_PSTRAND1, st3 = e.bits[k] & CB_PSTRAND2;
+			const bool ambiguous = e.bits[k] & CB_PSTRANDS_AMBIGUOUS;
+			if (!(e.bits[k] & CB_TSTART_GENE1)) { std::swap(g5, g3); std::swap(c5, c3); std::swap(d5, d3); std::swap(s5, s3); std::swap(b5, b3); std::swap(st5, st3); std::swap(site5, site3); }
+			const int cov5 = p.coverage.get_coverage(c5, b5, d5 == UPSTREAM ? DOWNSTREAM : UPSTREAM), cov3 = p.coverage.get_coverage(c3, b3, d3 == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+			std::string tseq = ".", pep = ".", frame = "."; i32 tr5 = -1, tr3 = -1;
+			if (extra_info) {
+				std::vector<i32> positions;
+				transcript_sequence(k, tseq, positions);
+				std::vector<i32> t5, t3;
+				matching_transcripts(tseq, positions, g5, st5, ambiguous, 5, t5);
+				matching_transcripts(tseq, positions, g3, st3, ambiguous, 3, t3);
+				for (size_t i = 0; (t5.empty() || i < t5.size()) && frame != "in-frame"; ++i) { // try transcript pairs until one is in-frame
+					if (i < t5.size()) tr5 = t5[i];
+					for (size_t j = 0; (t3.empty() || j < t3.size()) && frame != "in-frame"; ++j) {
+						if (j < t3.size()) tr3 = t3[j];
+						pep = peptide(tseq, positions, g5, g3, tr5, tr3, st3); frame = frame_label(pep);
+						if (j >= t3.size()) break;
+					}
+					if (i >= t5.size() || t3.empty()) break;
+				}
+				if (frame == "stop-codon") pep = ".";
+			}
+			out << gene_name(g5, c5, b5) << "\t" << gene_name(g3, c3, b3) << "\t" << strand_column(st5, g5, ambiguous) << "\t" << strand_column(st3, g3, ambiguous) << "\t"
+			    << ref.original_names[c5] << ":" << (b5 + 1) << "\t" << ref.original_names[c3] << ":" << (b3 + 1) << "\t" << site5 << "\t" << site3 << "\t"
+			    << fusion_type(k) << "\t" << s5 << "\t" << s3 << "\t" << e.discordant_mates[k] << "\t"
+			    << (cov5 >= 0 ? std::to_string((long long) cov5) : ".") << "\t" << (cov3 >= 0 ? std::to_string((long long) cov3) : ".") << "\t" << CONF[e.confidence[k] & 3] << "\t" << frame
+			    << "\t.\t.\t.\t.";
+			std::map<std::string, unsigned int> filters;
+			if (e.filter[k] != F_none) filters[FILTER_NAMES[e.filter[k]]] = 0;
+			std::vector<u32> reads(e.list1.begin() + e.list1_off[k], e.list1.begin() + e.list1_off[k + 1]);
+			reads.insert(reads.end(), e.list2.begin() + e.list2_off[k], e.list2.begin() + e.list2_off[k + 1]);
+			reads.insert(reads.end(), e.listd.begin() + e.listd_off[k], e.listd.begin() + e.listd_off[k + 1]);
+			for (size_t r = 0; r < reads.size(); ++r) if (p.labels[reads[r]] != F_none) ++filters[FILTER_NAMES[p.labels[reads[r]]]];
+			out << "\t" << (ref.genes[g5].is_dummy ? "." : ref.genes[g5].gene_id) << "\t" << (ref.genes[g3].is_dummy ? "." : ref.genes[g3].gene_id)
+			    << "\t" << (tr5 < 0 ? "." : ref.transcripts[tr5].name) << "\t" << (tr3 < 0 ? "." : ref.transcripts[tr3].name)
+			    << "\t" << (d5 == UPSTREAM ? "upstream" : "downstream") << "\t" << (d3 == UPSTREAM ? "upstream" : "downstream") << "\t";
+			if (filters.empty()) out << ".";
+			else for (std::map<std::string, unsigned int>::iterator it = filters.begin(); it != filters.end(); ++it) { if (it != filters.begin()) out << ","; out << it->first; if (it->second != 0) out << "(" << it->second << ")"; }
+			out << "\t" << tseq << "\t" << pep << "\t";
+			if (extra_info && !reads.empty()) {
+				for (size_t r = 0; r < reads.size(); ++r) {
+					if (r) out << ",";
+					const char* nm = p.frags.names.data() + p.frags.name_off[reads[r]]; u64 len = p.frags.name_off[reads[r] + 1] - p.frags.name_off[reads[r]];
+					u64 cut = len; while (cut > 0 && nm[cut - 1] != ',') --cut;
+					out.write(nm, cut > 0 ? cut - 1 : len);
+				}
+			} else out << ".";
+			out << std::endl;
+		}
+		out.close();
+		if (out.bad()) throw std::runtime_error("failed to write to file");
+	}
+};
+
+} // namespace
+
+const char* const FILTER_NAMES[38] = {"", "duplicates", "inconsistently_clipped", "homopolymer", "read_through", "same_gene", "small_insert_size", "long_gap", "hairpin",
+	"multimappers", "mismatches", "mismappers", "relative_support", "intronic", "non_coding_neighbors", "intragenic_exonic", "internal_tandem_duplication", "min_support",
+	"known_fusions", "spliced", "blacklist", "end_to_end", "in_vitro", "merge_adjacent", "select_best", "marginal_read_through", "short_anchor", "no_coverage", "many_spliced",
+	"no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs", "genomic_support", "isoforms", "low_entropy", "homologs"};
+
+void pipeline::write_output() {
+	writer w(*this);
+	if (!opt.output_file.empty()) { log += "Writing fusions to file '" + opt.output_file + "'\n"; w.write(opt.output_file, false, true); }
+	if (!opt.discarded_output_file.empty()) { log += "Writing discarded fusions to file '" + opt.discarded_output_file + "'\n"; w.write(opt.discarded_output_file, true, opt.print_extra_info_for_discarded_fusions); }
+}
+
+}} // namespace

@@ -10,7 +10,7 @@ namespace arb { namespace host {
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 run_options::run_options(): interesting_contigs("1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 X Y AC_* NC_*"), viral_contigs("AC_* NC_*"),
-	strandedness(3), fragment_length(200), threads(1), device(0) { arb_default_params(&params); }
+	strandedness(3), fragment_length(200), threads(1), device(0), print_extra_info_for_discarded_fusions(false) { arb_default_params(&params); }
 
 pipeline::~pipeline() { if (ctx) arb_ctx_destroy(ctx); }
 
@@ -92,10 +92,7 @@ void pipeline::upload() {
 	t_upload = now_s() - t0;
 }
 
-static const char* FILTER_NAME[] = {"", "duplicates", "inconsistently_clipped", "homopolymer", "read_through", "same_gene", "small_insert_size", "long_gap", "hairpin",
-	"multimappers", "mismatches", "mismappers", "relative_support", "intronic", "non_coding_neighbors", "intragenic_exonic", "internal_tandem_duplication", "min_support",
-	"known_fusions", "spliced", "blacklist", "end_to_end", "in_vitro", "merge_adjacent", "select_best", "marginal_read_through", "short_anchor", "no_coverage", "many_spliced",
-	"no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs", "genomic_support", "isoforms", "low_entropy", "homologs"};
+
 
 void pipeline::read_filters() {
 	const double t0 = now_s();
@@ -110,7 +107,7 @@ void pipeline::read_filters() {
 	u64 remaining = frags.n;
 	std::ostringstream s;
 	// ITD-shaped fragments re-labelled by low_entropy keep their original stage unknown; the cumulative count is exact only when none were re-labelled
-	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "filter " << FILTER_NAME[order[k]] << " (labelled=" << counts[order[k]] << ")\n"; }
+	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "filter " << FILTER_NAMES[order[k]] << " (labelled=" << counts[order[k]] << ")\n"; }
 	s << "filter low_entropy (remaining=" << counts[F_none] << ")\n";
 	log += s.str();
 	t_read_filters = now_s() - t0;
@@ -164,6 +161,6 @@ void pipeline::events_until(int last) { // arriba.cpp:420-545, filters enabled b
 	}
 }
 
-void pipeline::run_all() { load_reference(); ingest(); annotate(); upload(); read_filters(); fragment_length(); find_fusions(); events_until(EV_COUNT - 1); }
+void pipeline::run_all() { load_reference(); ingest(); annotate(); upload(); read_filters(); fragment_length(); find_fusions(); events_until(EV_COUNT - 1); write_output(); }
 
 }} // namespace

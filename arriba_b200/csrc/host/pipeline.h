@@ -19,6 +19,7 @@ struct run_options { // options_t (options.hpp:25-69) restricted to what this im
 	unsigned fragment_length;  // -F 200
 	int threads;               // host threads for decode/annotation (the reference's -@ only affects BAM decoding)
 	int device;
+	bool print_extra_info_for_discarded_fusions; // -X
 	run_options();
 };
 
@@ -46,6 +47,7 @@ struct pipeline {
 	void filter_non_coding_neighbors(); void filter_intragenic_both_exonic(); void filter_min_support(); void recover_internal_tandem_duplication();
 	void filter_both_intronic(); void filter_in_vitro(); void recover_both_spliced(); void select_best(); void filter_marginal_read_through();
 	void recover_many_spliced(); void filter_short_anchor(); void filter_end_to_end(); void filter_no_coverage(); void recover_isoforms(); void assign_confidence();
+	void write_output();
 	void make_kmer_index(); void filter_homologs(); void filter_mismappers(); bool splice_sites_ready;
 	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold);
 	unsigned int spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold);
@@ -59,6 +61,7 @@ enum { EV_FETCH = 0, EV_MERGE_ADJACENT, EV_MULTIMAPPERS, EV_EVALUE, EV_NON_CODIN
        EV_ITD, EV_INTRONIC, EV_IN_VITRO, EV_SPLICED, EV_SELECT_BEST, EV_MARGINAL_READ_THROUGH, EV_MANY_SPLICED, EV_SHORT_ANCHOR, EV_END_TO_END, EV_NO_COVERAGE,
        EV_KMER_INDEX, EV_HOMOLOGS, EV_MISMAPPERS, EV_SELECT_BEST2, EV_ISOFORMS, EV_CONFIDENCE, EV_COUNT };
 
+extern const char* const FILTER_NAMES[38];
 int detect_strandedness(pipeline& p);
 void assign_strands(pipeline& p, int strandedness);
 void annotate_fragments(pipeline& p);

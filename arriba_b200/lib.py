@@ -238,7 +238,7 @@ class Context:
 # ------------------------------------------------------------------------------------------- whole-run driver
 STEP_LOAD_REFERENCE, STEP_INGEST, STEP_ANNOTATE, STEP_UPLOAD, STEP_READ_FILTERS, STEP_FRAGMENT_LENGTH, STEP_FIND_FUSIONS, STEP_COUNT = range(8)
 EV_NAMES = ["fetch", "merge_adjacent", "multimappers", "evalue", "non_coding_neighbors", "intragenic_exonic", "min_support", "relative_support", "internal_tandem_duplication",
-            "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage"]
+            "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage", "kmer_index", "homologs", "mismappers", "select_best2", "isoforms", "confidence"]
 STEP_NAMES = ["load_reference", "ingest", "annotate", "upload", "read_filters", "fragment_length", "find_fusions"]
 
 
@@ -271,6 +271,7 @@ def _load_pipeline_api(lib):
     lib.arb_pipeline_genes.argtypes = [C.c_void_p, _p(Annotation)]
     lib.arb_pipeline_coverage.argtypes = [C.c_void_p, C.c_uint32, _p(_p(C.c_uint16)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8)), _p(C.c_uint64)]
     lib.arb_pipeline_events.argtypes = [C.c_void_p, C.c_int]
+    lib.arb_pipeline_write_output.argtypes = [C.c_void_p]
     lib.arb_pipeline_candidates.argtypes = [C.c_void_p, _p(Candidates), _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8))]
     lib._pipeline_ready = True
 
@@ -284,13 +285,17 @@ def _np_from(pointer, n, dtype):
 class Pipeline:
     """One run of the hot path on files: the call a user of the library makes (the `arriba` CLI is a thin wrapper over it)."""
 
-    def __init__(self, bam, gtf, fasta, threads=1, device=0, lib_path=None, strandedness=3, params=None):
+    def __init__(self, bam, gtf, fasta, threads=1, device=0, lib_path=None, strandedness=3, params=None, output=None, discarded=None):
         self.lib = load(lib_path)
         _load_pipeline_api(self.lib)
         o = RunOptions()
         self.lib.arb_default_run_options(C.byref(o))
         self._strings = [bam.encode(), gtf.encode(), fasta.encode()]
         o.bam_file, o.gtf_file, o.assembly_file = self._strings
+        if output:
+            self._strings.append(output.encode()); o.output_file = self._strings[-1]
+        if discarded:
+            self._strings.append(discarded.encode()); o.discarded_output_file = self._strings[-1]
         o.threads = threads; o.device = device; o.strandedness = strandedness
         if params is not None:
             o.params = params
@@ -346,6 +351,12 @@ class Pipeline:
         raw = C.string_at(C.cast(names, C.c_void_p), int(name_off[-1])) if n else b""
         out["name_off"] = name_off; out["names_blob"] = raw
         return out
+
+    def write_output(self):
+        self._check(self.lib.arb_pipeline_write_output(self.h))
+
+    def run_all(self):
+        self._check(self.lib.arb_pipeline_run(self.h))
 
     def events(self, last_stage):
         self._check(self.lib.arb_pipeline_events(self.h, last_stage))

@@ -228,6 +228,8 @@ enum { ARB_EV_FETCH = 0, ARB_EV_MERGE_ADJACENT, ARB_EV_MULTIMAPPERS, ARB_EV_EVAL
        ARB_EV_SHORT_ANCHOR, ARB_EV_END_TO_END, ARB_EV_NO_COVERAGE, ARB_EV_KMER_INDEX, ARB_EV_HOMOLOGS, ARB_EV_MISMAPPERS, ARB_EV_SELECT_BEST2, ARB_EV_ISOFORMS,
        ARB_EV_CONFIDENCE, ARB_EV_COUNT };
 int arb_pipeline_events(arb_pipeline* p, int last_stage);
+/* Replaces write_fusions_to_file (source/output_fusions.cpp:1043): writes output_file / discarded_output_file of the run options */
+int arb_pipeline_write_output(arb_pipeline* p);
 /* read-only view of the host candidate table: the arb_candidates pointers alias pipeline memory; `order` = the reference's
    iteration order (candidate ids), `confidence` and the current fragment labels complete the state */
 int arb_pipeline_candidates(arb_pipeline* p, arb_candidates* view, const uint32_t** order, const uint8_t** confidence, const uint8_t** fragment_labels);

@@ -1,0 +1,35 @@
+"""End to end: BAM + GTF + FASTA in, fusions.tsv / fusions.discarded.tsv out, byte-identical to the reference's files."""
+import os
+import pytest
+import worldutil
+from arriba_b200 import lib as L
+
+
+def check_e2e(world, lib_path, tmp_path, threads=4):
+    out = os.path.join(str(tmp_path), "fusions.tsv"); disc = os.path.join(str(tmp_path), "fusions.discarded.tsv")
+    p = L.Pipeline(world.prefix + ".bam", world.prefix + ".gtf", world.prefix + ".fa", threads=threads, lib_path=lib_path, output=out, discarded=disc)
+    p.run_all()
+    p.close()
+    want = open(os.path.join(world.outdir, "fusions.tsv")).read().split("\n")
+    got = open(out).read().split("\n")
+    assert len(want) > 5
+    for i, (g, w) in enumerate(zip(got, want)):
+        if g != w:
+            gc, wc = g.split("\t"), w.split("\t")
+            cols = [j for j in range(min(len(gc), len(wc))) if gc[j] != wc[j]]
+            raise AssertionError("fusions.tsv line %d differs in columns %s:\n got  %s\n want %s" % (i + 1, cols, [gc[j][:200] for j in cols], [wc[j][:200] for j in cols]))
+    assert len(got) == len(want)
+    assert open(disc).read() == open(os.path.join(world.outdir, "fusions.discarded.tsv")).read(), "discarded file differs"
+
+
+def test_e2e_hostsim(worlds, hostsim_lib, tmp_path):
+    check_e2e(worlds.get("small"), hostsim_lib, tmp_path)
+
+
+def test_e2e_hostsim_l151(worlds, hostsim_lib, tmp_path):
+    check_e2e(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda(worlds, cuda_lib, tmp_path):
+    check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
