@@ -80,6 +80,15 @@ def build_product(force=False, verbose=False):
     return PRODUCT_LIB
 
 
+def build_cli(force=False):
+    """The `arriba` executable: a thin C++ front end over the C ABI of the product library."""
+    src = os.path.join(CSRC, "host", "cli_main.cpp")
+    if force or _newer(CLI_BIN, [src, PRODUCT_LIB]):
+        os.makedirs(os.path.dirname(CLI_BIN), exist_ok=True)
+        _run(["g++"] + GXX_FLAGS + ["-o", CLI_BIN, src, "-L", os.path.dirname(PRODUCT_LIB), "-larriba_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"])
+    return CLI_BIN
+
+
 def build_hostsim(force=False):
     """CPU test-suite stand-in: same rule functors, sequential primitives. Never loaded by the package or the bench."""
     if not force and not _newer(HOSTSIM_LIB, _all_sources()):
@@ -118,6 +127,6 @@ def build_oracle(force=False):
 
 
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["product", "hostsim", "tools", "oracle"]
+    what = sys.argv[1:] or ["product", "cli", "hostsim", "tools", "oracle"]
     for w in what:
-        print(w, "->", {"product": build_product, "hostsim": build_hostsim, "tools": build_tools, "oracle": build_oracle}[w](force=True))
+        print(w, "->", {"product": build_product, "cli": build_cli, "hostsim": build_hostsim, "tools": build_tools, "oracle": build_oracle}[w](force=True))

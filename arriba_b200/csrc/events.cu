@@ -38,6 +38,7 @@ u32 engine::merge_adjacent(i32 max_distance) {
 	const u32 C = cands.n;
 	merge_log_n = 0;
 	if (C == 0) return 0;
+	stage_timer t_all(ex);
 	dbuf<u32> n1(C), n2(C), flag((size_t) C + 1);
 	list_size_fn ls1 = {cands.list1_off.ptr(), n1.ptr()}, ls2 = {cands.list2_off.ptr(), n2.ptr()};
 	for_each(ex, C, ls1); for_each(ex, C, ls2);
@@ -73,6 +74,7 @@ u32 engine::merge_adjacent(i32 max_distance) {
 	u32 n_log = 0; log_count.download(ex, &n_log, 1);
 	if (n_log > capacity) throw arb_error("merge_adjacent: more internal tandem duplication merges than the log can hold");
 	merge_log_n = n_log;
+	timings.merge_adjacent_ms = t_all.stop();
 	return n_log;
 }
 
@@ -96,7 +98,9 @@ void engine::estimate_evalues(const arb_evalue_inputs& a) {
 	in.read_through_penalty = a.read_through_penalty; in.cutoff = 0; in.apply_filter = 0;
 	cand_state s = make_state(cands, NULL, NULL);
 	evalue_fn fn = {s, annot.view(), in};
+	stage_timer t_all(ex);
 	for_each(ex, C, fn);
+	timings.evalue_ms = t_all.stop();
 	ex.sync();
 }
 

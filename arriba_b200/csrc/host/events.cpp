@@ -61,7 +61,7 @@ static inline bool is_intragenic(const event_table& e, const refdata& r, u32 k) 
 }
 static u32 count_unfiltered(const event_table& e) { u32 c = 0; for (u32 k = 0; k < e.n; ++k) if (e.filter[k] == F_none) ++c; return c; }
 
-void pipeline::log_remaining(const char* what) { std::ostringstream s; s << what << " (remaining=" << count_unfiltered(ev) << ")\n"; log += s.str(); }
+void pipeline::log_remaining(const char* what) { std::ostringstream s; s << what << " (remaining=" << count_unfiltered(ev) << ")"; say(s.str()); }
 
 // ------------------------------------------------------------------------------------------- device <-> host state
 void pipeline::fetch_candidates() {
@@ -93,7 +93,7 @@ void pipeline::fetch_candidates() {
 		std::swap(frags.genes_off[a], frags.genes_off[b]); std::swap(frags.genes_cnt[a], frags.genes_cnt[b]);
 	}
 	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
-	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")\n"; log += s.str();
+	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")"; say(s.str());
 }
 
 void pipeline::push_candidate_state() {
@@ -296,7 +296,7 @@ void pipeline::estimate_evalues() {
 	push_candidate_state();
 	check(ctx, arb_estimate_evalues(ctx, &in), "arb_estimate_evalues");
 	pull_candidate_state();
-	log += "Estimating expected number of fusions by random chance (e-value)\n";
+	say("Estimating expected number of fusions by random chance (e-value)");
 }
 
 void pipeline::filter_relative_support() {
@@ -314,7 +314,7 @@ void pipeline::filter_non_coding_neighbors() { // filter_non_coding_neighbors.cp
 
 void pipeline::filter_intragenic_both_exonic() { // filter_intragenic_both_exonic.cpp
 	const annot_view an = ref.host_view();
-	const float exonic_fraction = 0.33f; // options.cpp:99
+	const float exonic_fraction = opt.exonic_fraction; // -e
 	for (u32 k = 0; k < ev.n; ++k) {
 		if (ev.filter[k] != F_none) continue;
 		if ((overlaps_both(ev, ref, k) || ev.gene1[k] == ev.gene2[k]) && ev.exonic1(k) && ev.exonic2(k) && !(ev.spliced1(k) && ev.spliced2(k))) {
@@ -327,7 +327,7 @@ void pipeline::filter_intragenic_both_exonic() { // filter_intragenic_both_exoni
 }
 
 void pipeline::filter_min_support() { // filter_min_support.cpp
-	const int min_support = 2; // options.cpp:84
+	const int min_support = opt.min_support; // -S
 	for (u32 k = 0; k < ev.n; ++k) {
 		if (ev.filter[k] != F_none) continue;
 		if ((int) ev.supporting_reads(k) < min_support || (overlaps_both(ev, ref, k) && (int) (ev.split_reads1[k] + ev.split_reads2[k]) < min_support)) ev.filter[k] = F_min_support;
@@ -337,8 +337,8 @@ void pipeline::filter_min_support() { // filter_min_support.cpp
 
 void pipeline::recover_internal_tandem_duplication() { // recover_internal_tandem_duplication.cpp
 	const annot_view an = ref.host_view();
-	const unsigned int max_itd_length = opt.params.max_itd_length, min_supporting_reads = 10, subsampling_threshold = opt.params.subsampling_threshold;
-	const float min_fraction_of_coverage = 0.07f; // options.cpp:105-106
+	const unsigned int max_itd_length = opt.params.max_itd_length, min_supporting_reads = opt.min_itd_support, subsampling_threshold = opt.params.subsampling_threshold;
+	const float min_fraction_of_coverage = opt.min_itd_allele_fraction; // -z, -Z
 	unsigned int duplicates = 0;
 	for (u32 i = 0; i < frags.n; ++i) if (labels[i] == F_duplicates) ++duplicates;
 	const float duplication_rate = 1.0 * duplicates / frags.n;
@@ -386,7 +386,7 @@ void pipeline::filter_both_intronic() { // filter_both_intronic.cpp
 }
 
 // chimeric read count per gene and the expression quantile (filter_in_vitro.cpp:48-83)
-void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold) {
+void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold, float quantile_f) {
 	const u32 N = frags.n;
 	reads_by_gene.assign(ref.genes.size(), 0); present.assign(ref.genes.size(), 0);
 	for (u32 i = 0; i < N; ++i) {
@@ -398,7 +398,6 @@ void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::ve
 	for (u32 g = 0; g < present.size(); ++g) if (present[g]) genes.push_back(g);
 	threshold = 0;
 	if (genes.empty()) return;
-	const float quantile_f = 0.998f; // options.cpp:98
 	unsigned int q = static_cast<int>(floor(quantile_f * genes.size()));
 	if (q >= genes.size()) q = genes.size() - 1;
 	// the q-th element under (reads, id) ordering is unique, whatever nth_element's internal order
@@ -416,7 +415,7 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 			++exonic_breakpoints[std::make_pair(ev.gene1[k], ev.gene2[k])]; ++exonic_breakpoints[std::make_pair(ev.gene2[k], ev.gene1[k])];
 		}
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
-	find_top_expressed_genes(reads_by_gene, present, threshold);
+	find_top_expressed_genes(reads_by_gene, present, threshold, opt.high_expression_quantile); // -Q
 	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
 		unsigned int highest = reads_by_gene[gene];
 		idset<64> genes; query_index(gene_index(an), contig, bp, bp, genes);
@@ -484,7 +483,7 @@ unsigned int pipeline::spliced_support(u32 k, const std::vector<u32>& reads_by_g
 void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	const unsigned int max_fusions_to_recover = 200;
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
-	find_top_expressed_genes(reads_by_gene, present, threshold);
+	find_top_expressed_genes(reads_by_gene, present, threshold, 0.998f); // fixed quantile (arriba.cpp:492)
 	typedef std::tuple<u32, u32, bool, bool> pair_key;
 	std::map<pair_key, std::vector<u32> > by_pair;
 	for (size_t q = 0; q < ev.order.size(); ++q) {
@@ -578,7 +577,7 @@ void pipeline::filter_marginal_read_through() { // filter_marginal_read_through.
 }
 
 void pipeline::recover_many_spliced() { // recover_many_spliced.cpp
-	const unsigned int min_spliced_events = 4; // options.cpp:94
+	const unsigned int min_spliced_events = opt.min_spliced_events; // -M
 	auto eligible_filter = [](u8 f) { return f == F_inconsistently_clipped || f == F_relative_support || f == F_min_support || f == F_select_best; };
 	std::map<std::pair<u32, u32>, std::set<std::pair<i32, i32> > > spliced;
 	for (u32 k = 0; k < ev.n; ++k)
@@ -593,7 +592,7 @@ void pipeline::recover_many_spliced() { // recover_many_spliced.cpp
 }
 
 void pipeline::filter_short_anchor() { // filter_short_anchor.cpp
-	const unsigned int min_length = 23; // options.cpp:87
+	const unsigned int min_length = opt.min_anchor_length; // -A
 	for (u32 k = 0; k < ev.n; ++k) {
 		if (ev.filter[k] != F_none) continue;
 		if (!(ev.spliced1(k) && ev.spliced2(k)) && ((unsigned int) std::abs(ev.anchor1[k] - ev.bp1[k]) < min_length || (unsigned int) std::abs(ev.anchor2[k] - ev.bp2[k]) < min_length)) ev.filter[k] = F_short_anchor;
@@ -715,7 +714,7 @@ void pipeline::make_kmer_index() { // windows of make_kmer_index (filter_mismapp
 	uint64_t n_indexed = 0;
 	if (c.empty()) { c.push_back(0); s.push_back(0); t.push_back(0); check(ctx, arb_build_kmer_index(ctx, c.data(), s.data(), t.data(), 0, n_index_contigs, &n_indexed), "arb_build_kmer_index"); }
 	else check(ctx, arb_build_kmer_index(ctx, c.data(), s.data(), t.data(), (uint32_t) c.size(), n_index_contigs, &n_indexed), "arb_build_kmer_index");
-	log += "Indexing gene sequences\n";
+	say("Indexing gene sequences");
 }
 
 void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() itself is evaluated on the device in two batches
@@ -842,7 +841,7 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 		}
 		ev.confidence[k] = (u8) conf;
 	}
-	log += "Assigning confidence scores to events\n";
+	say("Assigning confidence scores to events");
 }
 
 }} // namespace

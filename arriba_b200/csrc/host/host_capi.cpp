@@ -13,11 +13,18 @@ static std::string g_pipeline_create_error;
 
 extern "C" {
 
+void arb_struct_sizes(uint32_t out[9]) {
+	out[0] = sizeof(arb_contigs); out[1] = sizeof(arb_annotation); out[2] = sizeof(arb_params); out[3] = sizeof(arb_soa_chunk); out[4] = sizeof(arb_candidates);
+	out[5] = sizeof(arb_evalue_inputs); out[6] = sizeof(arb_timings); out[7] = sizeof(arb_run_options); out[8] = sizeof(arb_run_stats);
+}
+
 void arb_default_run_options(arb_run_options* o) {
 	if (!o) return;
 	memset(o, 0, sizeof(*o));
 	arb_default_params(&o->params);
 	o->strandedness = 3; o->fragment_length = 200; o->threads = 1; o->device = 0;
+	o->min_support = 2; o->min_anchor_length = 23; o->min_spliced_events = 4; o->high_expression_quantile = 0.998f; o->exonic_fraction = 0.33f;
+	o->min_itd_allele_fraction = 0.07f; o->min_itd_support = 10; o->print_extra_info_for_discarded_fusions = 0; o->echo_progress = 0;
 }
 
 int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
@@ -32,6 +39,9 @@ int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
 		if (o->discarded_output_file) r.discarded_output_file = o->discarded_output_file;
 		if (o->interesting_contigs) r.interesting_contigs = o->interesting_contigs;
 		if (o->viral_contigs) r.viral_contigs = o->viral_contigs;
+		r.min_support = o->min_support; r.min_anchor_length = o->min_anchor_length; r.min_spliced_events = o->min_spliced_events; r.high_expression_quantile = o->high_expression_quantile;
+		r.exonic_fraction = o->exonic_fraction; r.min_itd_allele_fraction = o->min_itd_allele_fraction; r.min_itd_support = o->min_itd_support;
+		r.print_extra_info_for_discarded_fusions = o->print_extra_info_for_discarded_fusions != 0; r.echo_progress = o->echo_progress != 0;
 		r.params = o->params; r.strandedness = o->strandedness; r.fragment_length = o->fragment_length; r.threads = o->threads; r.device = o->device;
 		*out = x;
 	} catch (const std::exception& e) { g_pipeline_create_error = e.what(); return 1; }
@@ -70,6 +80,9 @@ int arb_pipeline_stats(arb_pipeline* x, arb_run_stats* s) {
 	s->seconds[ARB_STEP_UPLOAD] = p.t_upload; s->seconds[ARB_STEP_READ_FILTERS] = p.t_read_filters; s->seconds[ARB_STEP_FRAGMENT_LENGTH] = p.t_fragment_length;
 	s->seconds[ARB_STEP_FIND_FUSIONS] = p.t_find_fusions;
 	s->t_inflate = p.istats.t_inflate; s->t_parse = p.istats.t_parse; s->t_finalize = p.istats.t_finalize;
+	for (int q = 0; q < 32 && q < EV_COUNT; ++q) s->event_seconds[q] = p.t_events[q];
+	s->output_seconds = p.t_output; s->n_candidates = p.ev.n;
+	for (arb::u32 q = 0; q < p.ev.n; ++q) if (p.ev.filter[q] == 0) ++s->n_unfiltered_candidates;
 	const arb::host::fragment_table& f = p.frags;
 	s->h2d_bytes = f.n_aln.size() + f.fflags.size() + f.filter.size() + f.aflags.size() + 2 * (f.contig.size() + f.cigar_cnt.size() + f.seq_len.size() + f.genes_cnt.size()) +
 	               4 * (f.start.size() + f.end.size() + f.cigar_off.size() + f.seq_off.size() + f.genes_off.size() + f.cigar.size() + f.genes.size()) + f.seq.size();

@@ -5,6 +5,7 @@
 #include "pipeline.h"
 #include "../annot_hd.h"
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -544,9 +545,11 @@ const char* const FILTER_NAMES[38] = {"", "duplicates", "inconsistently_clipped"
 	"no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs", "genomic_support", "isoforms", "low_entropy", "homologs"};
 
 void pipeline::write_output() {
+	const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	writer w(*this);
-	if (!opt.output_file.empty()) { log += "Writing fusions to file '" + opt.output_file + "'\n"; w.write(opt.output_file, false, true); }
-	if (!opt.discarded_output_file.empty()) { log += "Writing discarded fusions to file '" + opt.discarded_output_file + "'\n"; w.write(opt.discarded_output_file, true, opt.print_extra_info_for_discarded_fusions); }
+	if (!opt.output_file.empty()) { say("Writing fusions to file '" + opt.output_file + "'"); w.write(opt.output_file, false, true); }
+	if (!opt.discarded_output_file.empty()) { say("Writing discarded fusions to file '" + opt.discarded_output_file + "'"); w.write(opt.discarded_output_file, true, opt.print_extra_info_for_discarded_fusions); }
+	t_output = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
 }
 
 }} // namespace

@@ -1,6 +1,8 @@
 // pipeline.cpp -- see pipeline.h.
 #include "pipeline.h"
 #include <chrono>
+#include <ctime>
+#include <iostream>
 #include <sstream>
 #include <stdexcept>
 #include <algorithm>
@@ -10,7 +12,13 @@ namespace arb { namespace host {
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 run_options::run_options(): interesting_contigs("1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 X Y AC_* NC_*"), viral_contigs("AC_* NC_*"),
-	strandedness(3), fragment_length(200), threads(1), device(0), print_extra_info_for_discarded_fusions(false) { arb_default_params(&params); }
+	strandedness(3), fragment_length(200), threads(1), device(0), print_extra_info_for_discarded_fusions(false), min_support(2), min_anchor_length(23), min_spliced_events(4), min_itd_support(10),
+	high_expression_quantile(0.998f), exonic_fraction(0.33f), min_itd_allele_fraction(0.07f), echo_progress(false) { arb_default_params(&params); }
+
+void pipeline::say(const std::string& line) {
+	log += line; log += "\n";
+	if (opt.echo_progress) { time_t now = time(0); char buf[64]; strftime(buf, sizeof(buf), "[%Y-%m-%dT%X]", localtime(&now)); std::cout << buf << " " << line << std::endl; }
+}
 
 pipeline::~pipeline() { if (ctx) arb_ctx_destroy(ctx); }
 
@@ -35,8 +43,8 @@ void pipeline::ingest() {
 	ingest_options io; io.external_duplicate_marking = opt.params.external_duplicate_marking; io.max_itd_length = opt.params.max_itd_length;
 	io.interesting_contigs = opt.interesting_contigs; io.viral_contigs = opt.viral_contigs; io.threads = threads;
 	read_chimeric_alignments(opt.bam_file, ref, io, frags, coverage, istats);
-	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")\n";
-	log += s.str();
+	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")";
+	say(s.str());
 	t_ingest = now_s() - t0;
 }
 
@@ -53,11 +61,11 @@ void pipeline::annotate() {
 		const u64 sa = la > 0 ? la - 1 : a1 - a0, sb = lb > 0 ? lb - 1 : a2 - a1;
 		if (sa == sb && std::equal(frags.names.begin() + a0, frags.names.begin() + a0 + sa, frags.names.begin() + a1)) ++marked;
 	}
-	{ std::ostringstream s; s << "Marking multi-mapping alignments (marked=" << marked << ")\n"; log += s.str(); }
+	{ std::ostringstream s; s << "Marking multi-mapping alignments (marked=" << marked << ")"; say(s.str()); }
 	strandedness = opt.strandedness;
 	if (opt.strandedness == 3) {
 		strandedness = detect_strandedness(*this);
-		log += std::string("Detecting strandedness (") + (strandedness == 1 ? "yes" : strandedness == 2 ? "reverse" : "no") + ")\n";
+		say(std::string("Detecting strandedness (") + (strandedness == 1 ? "yes" : strandedness == 2 ? "reverse" : "no") + ")");
 	}
 	if (strandedness != 0) assign_strands(*this, strandedness);
 	annotate_fragments(*this);
@@ -107,9 +115,9 @@ void pipeline::read_filters() {
 	u64 remaining = frags.n;
 	std::ostringstream s;
 	// ITD-shaped fragments re-labelled by low_entropy keep their original stage unknown; the cumulative count is exact only when none were re-labelled
-	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "filter " << FILTER_NAMES[order[k]] << " (labelled=" << counts[order[k]] << ")\n"; }
-	s << "filter low_entropy (remaining=" << counts[F_none] << ")\n";
-	log += s.str();
+	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "Filtering " << FILTER_NAMES[order[k]] << " (remaining=" << remaining << ")\n"; }
+	s << "Filtering reads with low entropy (remaining=" << counts[F_none] << ")";
+	say(s.str());
 	t_read_filters = now_s() - t0;
 }
 
@@ -131,6 +139,7 @@ void pipeline::events_until(int last) { // arriba.cpp:420-545, filters enabled b
 	const u64 m = opt.params.filter_mask;
 	auto on = [&](int f) { return (m >> f) & 1; };
 	for (int s = events_done + 1; s <= last && s < EV_COUNT; ++s) {
+		const double t0 = now_s();
 		switch (s) {
 			case EV_FETCH: fetch_candidates(); break;
 			case EV_MERGE_ADJACENT: if (on(F_merge_adjacent)) merge_adjacent(); break;
@@ -157,6 +166,7 @@ void pipeline::events_until(int last) { // arriba.cpp:420-545, filters enabled b
 			case EV_ISOFORMS: if (on(F_isoforms)) recover_isoforms(); break;
 			case EV_CONFIDENCE: assign_confidence(); break;
 		}
+		t_events[s] = now_s() - t0;
 		events_done = s;
 	}
 }

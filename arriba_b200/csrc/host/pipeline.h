@@ -20,6 +20,7 @@ struct run_options { // options_t (options.hpp:25-69) restricted to what this im
 	int threads;               // host threads for decode/annotation (the reference's -@ only affects BAM decoding)
 	int device;
 	bool print_extra_info_for_discarded_fusions; // -X
+	int min_support; unsigned min_anchor_length, min_spliced_events, min_itd_support; float high_expression_quantile, exonic_fraction, min_itd_allele_fraction; bool echo_progress;
 	run_options();
 };
 
@@ -30,9 +31,11 @@ struct pipeline {
 	int strandedness; i32 max_mate_gap; float read_length_mean, mate_gap_mean, mate_gap_stddev; bool fragment_length_ok;
 	std::vector<u8> labels, early;
 	event_table ev;
+	void say(const std::string& line); // appends to `log`, echoes with a time stamp when opt.echo_progress
 	std::string log; // the reference's progress lines (arriba.cpp:61-66 style, without time stamps)
+	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
-	pipeline(): splice_sites_ready(false), events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) {}
+	pipeline(): splice_sites_ready(false), events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -49,7 +52,7 @@ struct pipeline {
 	void recover_many_spliced(); void filter_short_anchor(); void filter_end_to_end(); void filter_no_coverage(); void recover_isoforms(); void assign_confidence();
 	void write_output();
 	void make_kmer_index(); void filter_homologs(); void filter_mismappers(); bool splice_sites_ready;
-	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold);
+	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold, float quantile);
 	unsigned int spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold);
 	float intronic_fraction(u32 gene);
 	void events_until(int last_stage); // runs the event-level chain up to and including `last_stage` (EV_* below)

@@ -13,6 +13,7 @@ void engine::set_splice_sites(const u32* off, const i32* sites) {
 
 u64 engine::build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs) {
 	kmer_index_contigs = n_index_contigs; kmer_indexed = 0;
+	stage_timer t_all(ex);
 	const size_t n_buckets = (size_t) n_index_contigs * 65536;
 	kmer_bucket_off.ensure(n_buckets + 2);
 	kmer_bucket_off.zero(ex, n_buckets + 2);
@@ -44,6 +45,7 @@ u64 engine::build_kmer_index(const u32* contig, const i32* start, const i32* end
 #else
 	memcpy(kmer_pos.ptr(), pos.ptr(), (size_t) K * 4);
 #endif
+	timings.kmer_index_ms = t_all.stop(); timings.kmer_positions = K;
 	ex.sync();
 	return K;
 }
@@ -68,7 +70,9 @@ void engine::homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out) {
 	a.upload(ex, ga, n); b.upload(ex, gb, n);
 	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
 	homolog_pairs_fn fn = {annot.view(), ix, a.ptr(), b.ptr(), o.ptr(), params.max_homolog_identity};
+	stage_timer t_all(ex);
 	for_each(ex, n, fn);
+	timings.homologs_ms += t_all.stop();
 	o.download(ex, out, n);
 }
 
@@ -79,6 +83,7 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)); // realign() recurses at splice sites and at one deletion
 #endif
+	stage_timer t_all(ex);
 	dbuf<u32> item_off((size_t) C + 1);
 	item_count_fn ic = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list2_off.ptr(), cands.listd_off.ptr(), item_off.ptr()};
 	for_each(ex, C, ic);
@@ -98,6 +103,7 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	mismap_count_fn mc = {frags.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(),
 	                      cands.split_reads1.ptr(), cands.split_reads2.ptr(), cands.discordant_mates.ptr(), cands.filter.ptr(), params.max_mismapper_fraction};
 	for_each(ex, C, mc);
+	timings.mismappers_ms = t_all.stop(); timings.mismapper_items = I;
 	ex.sync();
 	return I;
 }

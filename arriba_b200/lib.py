@@ -61,7 +61,9 @@ class Candidates(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [("duplicates_ms", C.c_float), ("classify_ms", C.c_float), ("read_filters_ms", C.c_float), ("find_fusions_ms", C.c_float),
-                ("classify_algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("h2d_ms", C.c_float)]
+                ("classify_algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("h2d_ms", C.c_float),
+                ("merge_adjacent_ms", C.c_float), ("evalue_ms", C.c_float), ("kmer_index_ms", C.c_float), ("homologs_ms", C.c_float), ("mismappers_ms", C.c_float),
+                ("mismapper_items", C.c_uint64), ("kmer_positions", C.c_uint64)]
 
 
 _CTYPE = {np.dtype(np.uint8): C.c_uint8, np.dtype(np.uint16): C.c_uint16, np.dtype(np.uint32): C.c_uint32, np.dtype(np.int32): C.c_int32,
@@ -72,6 +74,15 @@ def ptr(a):
     """numpy array -> typed ctypes pointer (array must be C-contiguous and stay alive)."""
     assert a.flags["C_CONTIGUOUS"], "array must be contiguous"
     return a.ctypes.data_as(_p(_CTYPE[a.dtype]))
+
+
+class EvalueInputs(C.Structure):
+    _fields_ = [("partner_count", _p(C.c_int32)), ("n_genes", C.c_uint32), ("spliced_breakpoints", C.c_uint32), ("exonic_breakpoints", C.c_uint32),
+                ("intronic_breakpoints", C.c_uint32), ("exonic_intronic_breakpoints", C.c_uint32), ("intragenic_duplications", C.c_uint32),
+                ("intragenic_inversions", C.c_uint32), ("spliced_same_gene", C.c_uint32), ("spliced_different_genes", C.c_uint32),
+                ("read_through_fraction", C.c_float), ("mapped_reads", C.c_uint64), ("pow_reads", _p(C.c_double)), ("pow_intragenic", _p(C.c_double)),
+                ("pow_intergenic", _p(C.c_double)), ("n_read_table", C.c_uint32), ("pow_spliced1000", _p(C.c_double)), ("pow_spliced400", _p(C.c_double)),
+                ("pow_read_through", _p(C.c_double)), ("pow_proximal", _p(C.c_double)), ("read_through_penalty", C.c_double)]
 
 
 class ArbError(RuntimeError):
@@ -93,6 +104,11 @@ def load(path=None):
     lib.arb_last_error.restype = C.c_char_p
     lib.arb_last_error.argtypes = [C.c_void_p]
     lib.arb_kernel_launches.restype = C.c_uint64
+    sizes = (C.c_uint32 * 9)()
+    lib.arb_struct_sizes(sizes)
+    expect = [C.sizeof(x) for x in (Contigs, Annotation, Params, SoaChunk, Candidates, EvalueInputs, Timings, RunOptions, RunStats)]
+    if list(sizes) != expect:
+        raise ArbError("struct layout mismatch between include/arriba_b200.h and arriba_b200/lib.py: %s vs %s" % (list(sizes), expect))
     lib.arb_ctx_create.argtypes = [_p(C.c_void_p), C.c_int]
     lib.arb_ctx_destroy.argtypes = [C.c_void_p]
     lib.arb_default_params.argtypes = [_p(Params)]
@@ -245,7 +261,10 @@ STEP_NAMES = ["load_reference", "ingest", "annotate", "upload", "read_filters", 
 class RunOptions(C.Structure):
     _fields_ = [("bam_file", C.c_char_p), ("gtf_file", C.c_char_p), ("assembly_file", C.c_char_p), ("output_file", C.c_char_p),
                 ("discarded_output_file", C.c_char_p), ("interesting_contigs", C.c_char_p), ("viral_contigs", C.c_char_p),
-                ("params", Params), ("strandedness", C.c_int32), ("fragment_length", C.c_uint32), ("threads", C.c_int32), ("device", C.c_int32)]
+                ("params", Params), ("strandedness", C.c_int32), ("fragment_length", C.c_uint32), ("threads", C.c_int32), ("device", C.c_int32),
+                ("min_support", C.c_int32), ("min_anchor_length", C.c_uint32), ("min_spliced_events", C.c_uint32), ("high_expression_quantile", C.c_float),
+                ("exonic_fraction", C.c_float), ("min_itd_allele_fraction", C.c_float), ("min_itd_support", C.c_uint32),
+                ("print_extra_info_for_discarded_fusions", C.c_int32), ("echo_progress", C.c_int32)]
 
 
 class RunStats(C.Structure):
@@ -253,7 +272,7 @@ class RunStats(C.Structure):
                 ("strandedness", C.c_int32), ("max_mate_gap", C.c_int32), ("fragment_length_ok", C.c_int32),
                 ("mate_gap_mean", C.c_float), ("mate_gap_stddev", C.c_float), ("read_length_mean", C.c_float),
                 ("seconds", C.c_double * STEP_COUNT), ("t_inflate", C.c_double), ("t_parse", C.c_double), ("t_finalize", C.c_double),
-                ("h2d_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("event_seconds", C.c_double * 32), ("output_seconds", C.c_double), ("n_candidates", C.c_uint64), ("n_unfiltered_candidates", C.c_uint64)]
 
 
 def _load_pipeline_api(lib):

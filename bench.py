@@ -18,7 +18,7 @@ WORKLOADS = {
     "mid_1M_2x101_5k": dict(scale=0.02, genes=4000, breakpoints=5000, fragments=1000000, read_length=101),
     "tiny_20k": dict(scale=0.001, genes=400, breakpoints=200, fragments=20000, read_length=101),
 }
-SCOPE = "ingest..find_fusions"  # stages inside one step (grows as stages land); the reference arm is clocked over the same stages
+SCOPE = "ingest..fusions.tsv"  # one step = BAM ingest -> read filters -> candidates -> event filters -> fusions.tsv + discarded.tsv (reference loading excluded)
 
 
 def world_dir(name):
@@ -103,7 +103,7 @@ def reference_run(prefix, threads):
         return int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3))
     lines = r.stdout.splitlines()
     t_start = [stamp(l) for l in lines if "Reading chimeric alignments" in l][0]
-    after = [stamp(l) for l in lines if "Merging adjacent fusion breakpoints" in l or "Filtering multi-mapping fusions" in l or "Estimating expected number" in l]
+    after = [stamp(l) for l in lines if "Freeing resources" in l]
     t_end = after[0] if after else stamp(lines[-1])
     scope_s = max(1.0, float((t_end - t_start) % 86400))
     return n, scope_s, total
@@ -167,17 +167,22 @@ def main():
 
     def one_step():
         """ingest .. find_fusions through the public Pipeline API; returns (fragments, e2e seconds, device ms, stats, timings, d2h bytes)"""
-        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank)
+        outdir = os.path.join(world_dir(args.workload), "out_rank%d" % rank); os.makedirs(outdir, exist_ok=True)
+        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank,
+                       output=os.path.join(outdir, "fusions.tsv"), discarded=os.path.join(outdir, "fusions.discarded.tsv"))
         p.step(L.STEP_LOAD_REFERENCE)          # genome + annotation: loaded once per run in a real deployment, outside the timed region
         t0 = time.perf_counter()
         for s in range(L.STEP_INGEST, L.STEP_COUNT):
             p.step(s)
-        ctx = p.context()
-        cand = ctx.candidates()                # D2H of the result table
+        p.events(len(L.EV_NAMES) - 1)          # event-level chain incl. the device stages and the D2H of the candidate table
+        p.write_output()
         e2e_s = time.perf_counter() - t0
+        ctx = p.context()
         st = p.stats(); tm = ctx.timings()
-        d2h = sum(v.nbytes for v in cand.values() if hasattr(v, "nbytes")) + 2 * int(st.n_fragments)
-        res = (int(st.n_fragments), e2e_s, tm.read_filters_ms + tm.find_fusions_ms, st, tm, d2h, cand["n"])
+        n_cand = int(st.n_candidates)
+        d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
+        dev_ms = tm.read_filters_ms + tm.find_fusions_ms + tm.merge_adjacent_ms + tm.evalue_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms
+        res = (int(st.n_fragments), e2e_s, dev_ms, st, tm, d2h, n_cand)
         p.close()
         return res
 
@@ -217,12 +222,15 @@ def main():
             "clocks": sampler.summary(),
             "e2e": {"value": n_frag * world / e2e_s, "unit": "fragments/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
                     "seconds_per_step": e2e_s, "host_seconds": {n: round(st.seconds[i], 3) for i, n in enumerate(L.STEP_NAMES) if i > 0},
+                    "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_for_each<classify_fn> (fused read-level cascade)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(tm.classify_algorithmic_bytes), "kernel_ms": cls_ms,
-                         "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms}},
-            "candidates": int(results[-1][6]), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
+                         "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
+                                       "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms},
+                         "mismapper_items": int(tm.mismapper_items), "kmer_positions": int(tm.kmer_positions)},
+            "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
     if not args.no_cpu_baseline:
         sp = ensure_world(args.workload, sample_bp)
         n, scope_s, total = reference_run(sp, cores)

@@ -26,6 +26,9 @@ void arb_ctx_destroy(arb_ctx* ctx);
 const char* arb_last_error(arb_ctx* ctx);         /* ctx may be NULL: last error of arb_ctx_create */
 const char* arb_backend(void);                    /* "cuda-sm_100a" for the product library */
 uint64_t arb_kernel_launches(void);               /* kernels launched by this library since load */
+/* sizeof() of the public structs, for bindings to verify their layout: arb_contigs, arb_annotation, arb_params, arb_soa_chunk, arb_candidates,
+   arb_evalue_inputs, arb_timings, arb_run_options, arb_run_stats */
+void arb_struct_sizes(uint32_t out[9]);
 
 /* ---- reference genome and annotation --------------------------------------------------------------------
  * Replaces the in-memory products of load_assembly (source/assembly.cpp:28), read_annotation_gtf
@@ -173,6 +176,9 @@ typedef struct arb_timings {
 	uint64_t classify_algorithmic_bytes; /* bytes the cascade kernel must read/write once: every input column and pool + gathered reference bases + 2 label bytes per fragment */
 	uint64_t h2d_bytes;         /* bytes copied by the last arb_push_chunk */
 	float h2d_ms;               /* duration of those copies */
+	float merge_adjacent_ms, evalue_ms, kmer_index_ms, homologs_ms, mismappers_ms; /* candidate-level device stages */
+	uint64_t mismapper_items;   /* (candidate, read) pairs re-aligned */
+	uint64_t kmer_positions;    /* positions in the k-mer index */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 
@@ -194,6 +200,16 @@ typedef struct arb_run_options {
 	uint32_t fragment_length;        /* -F 200 */
 	int32_t threads;                 /* host threads */
 	int32_t device;                  /* CUDA device ordinal */
+	/* thresholds of the host-side event filters (defaults: source/options.cpp:71-107) */
+	int32_t min_support;             /* -S 2 */
+	uint32_t min_anchor_length;      /* -A 23 */
+	uint32_t min_spliced_events;     /* -M 4 */
+	float high_expression_quantile;  /* -Q 0.998 */
+	float exonic_fraction;           /* -e 0.33 */
+	float min_itd_allele_fraction;   /* -z 0.07 */
+	uint32_t min_itd_support;        /* -Z 10 */
+	int32_t print_extra_info_for_discarded_fusions; /* -X */
+	int32_t echo_progress;           /* print the reference's progress lines to stdout while running */
 } arb_run_options;
 void arb_default_run_options(arb_run_options* o);
 
@@ -207,6 +223,9 @@ typedef struct arb_run_stats {
 	double seconds[ARB_STEP_COUNT];      /* wall time per step */
 	double t_inflate, t_parse, t_finalize; /* inside ARB_STEP_INGEST */
 	uint64_t h2d_bytes;                  /* bytes copied host->device by ARB_STEP_UPLOAD */
+	double event_seconds[32];            /* wall time per event-level stage (ARB_EV_*) */
+	double output_seconds;               /* arb_pipeline_write_output */
+	uint64_t n_candidates, n_unfiltered_candidates;
 } arb_run_stats;
 
 int arb_pipeline_create(arb_pipeline** out, const arb_run_options* options);
