@@ -12,6 +12,6 @@ echo "== ncu launch list (mid)"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_mid.csv python bench.py --workload mid_1M_2x101_5k --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -2 gpurun_out/ncu_bench.log | cut -c1-300
 echo "== ncu full capture of the cascade kernel"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_for_each --kernel-name-base demangled -k regex:classify_fn -c 1 -o gpurun_out/prof_classify -f python bench.py --workload mid_1M_2x101_5k --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:classify_fn -c 1 -o gpurun_out/prof_classify -f python bench.py --workload mid_1M_2x101_5k --steps 1 --warmup 0 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log | cut -c1-300
 ls -la gpurun_out | head -30
