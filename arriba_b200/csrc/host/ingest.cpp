@@ -11,6 +11,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 #include <thread>
@@ -547,7 +549,11 @@ struct final_frag { u32 worker; u32 frag; u64 prefix0, prefix1; };
 void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const ingest_options& opt, fragment_table& out, coverage_windows& coverage, ingest_stats& stats) {
 	const int T = std::max(1, opt.threads);
 	double t0 = now_s();
+	const bool trace = getenv("ARB_TRACE") != NULL;
+	double tr_last = t0;
+	auto lap = [&](const char* what) { if (trace) { const double t = now_s(); fprintf(stderr, "[ingest] %-28s %.3f s\n", what, t - tr_last); tr_last = t; } };
 	bgzf_file bam; bam.open(bam_path);
+	lap("open + block table");
 	stats.t_inflate = stats.t_parse = stats.t_finalize = 0;
 
 	// chunks of ~128 MiB of decompressed data, each a whole number of BGZF blocks; a record that straddles a chunk
@@ -633,6 +639,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	}
 	if (!header_done) fail("failed to read SAM header");
 	(void) t0;
+	lap("inflate + scan + parse");
 
 	// ---- merge by-products ----
 	double tf = now_s();
@@ -654,6 +661,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		});
 		std::vector<std::vector<u16> >().swap(w.cov.coverage);
 	}
+	lap("merge by-products");
 	if (stats.mapped_reads == 0) fail("no normal reads found");
 
 	// ---- slot normalisation, rejection of malformed fragments ----
@@ -682,6 +690,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			}
 		}
 	});
+	lap("normalise slots");
 	for (int t = 0; t < T; ++t) stats.malformed += malformed_by_worker[t];
 	if (stats.malformed > 0) std::cerr << "WARNING: " << stats.malformed << " SAM records were malformed and ignored" << std::endl;
 	if (stats.no_chimeric_reads) fail("no split reads or discordant mates found (STAR must either be run with '--chimOutType WithinBAM' or the file 'Chimeric.out.sam' must be passed to Arriba via the argument -c)");
@@ -713,6 +722,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		}
 	}
 
+	lap("sort by name");
 	// ---- SoA columns ----
 	const u32 n = (u32) order.size();
 	out.n = n;
@@ -753,6 +763,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		}
 	});
 	out.seq_off.resize(2 * (size_t) n); out.seq_len.resize(2 * (size_t) n);
+	lap("SoA columns");
 
 	// ---- multimappers: neighbours in name order that share the name up to the last comma (read_chimeric_alignments.cpp:792-802) ----
 	auto stem_len = [&](u32 i) { const char* s = out.names.data() + out.name_off[i]; u64 l = out.name_off[i + 1] - out.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; return k > 0 ? k - 1 : l; };
@@ -761,6 +772,9 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		if (la == lb && memcmp(out.names.data() + out.name_off[i], out.names.data() + out.name_off[i + 1], la) == 0) { out.fflags[i] |= FF_MULTIMAPPER; out.fflags[i + 1] |= FF_MULTIMAPPER; }
 	}
 	stats.t_finalize = now_s() - tf;
+	lap("multimapper flags");
+	{ std::vector<worker>().swap(workers); }
+	lap("free worker state");
 }
 
 }} // namespace

@@ -18,6 +18,7 @@ import worldutil  # noqa: E402
 WORLDS = {
     "tiny": dict(scale=0.001, genes=400, breakpoints=60, fragments=3000, read_length=101, seed=0xA881BA),
     "tiny_l151_shuffled": dict(scale=0.001, genes=300, breakpoints=40, fragments=2500, read_length=151, seed=11, extra=("--shuffle", "--varnames")),
+    "tiny_mismapper_heavy": dict(scale=0.001, genes=300, breakpoints=60, fragments=4000, read_length=101, seed=5, extra=("--mismapper-frac", "0.3", "--paralog-frac", "0.15")),
 }
 
 

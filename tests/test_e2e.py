@@ -30,6 +30,17 @@ def test_e2e_hostsim_l151(worlds, hostsim_lib, tmp_path):
     check_e2e(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, tmp_path)
 
 
+def test_e2e_hostsim_mismapper_heavy(worlds, hostsim_lib, tmp_path):
+    from test_events import CFG5
+    check_e2e(worlds.get("cfg5", **CFG5), hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_mismapper_heavy(worlds, cuda_lib, tmp_path):
+    from test_events import CFG5
+    check_e2e(worlds.get("cfg5", **CFG5), cuda_lib, tmp_path, threads=8)
+
+
 @pytest.mark.gpu
 def test_e2e_cuda(worlds, cuda_lib, tmp_path):
     check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)

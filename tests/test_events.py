@@ -63,6 +63,23 @@ def test_events_hostsim_l151(worlds, hostsim_lib):
     check_events(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib)
 
 
+CFG5 = dict(scale=0.002, genes=800, breakpoints=400, fragments=40000, extra=("--mismapper-frac", "0.3", "--paralog-frac", "0.15"))
+
+
+def test_events_hostsim_mismapper_heavy(worlds, hostsim_lib):
+    """BASELINE.json configs[4] in miniature: homologous partners, clipped segments alignable in the donor, adjacent breakpoints, ITD merges."""
+    w = worlds.get("cfg5", **CFG5)
+    mm = w.stage("ev_mismappers")
+    assert (mm["frag_filter"] == 11).sum() > 1000 and (mm["filter"] == 11).sum() > 20 and (w.stage("ev_homologs")["filter"] == 37).sum() > 5
+    assert (w.stage("ev_merge_adjacent")["filter"] == 23).sum() > 20
+    check_events(w, hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_events_cuda_mismapper_heavy(worlds, cuda_lib):
+    check_events(worlds.get("cfg5", **CFG5), cuda_lib)
+
+
 @pytest.mark.gpu
 def test_events_cuda(worlds, cuda_lib):
     check_events(worlds.get("small"), cuda_lib)

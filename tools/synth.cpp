@@ -98,6 +98,7 @@ struct params_t {
 	double spliced_frac = 0.6; // fraction of breakpoint ends at exon boundaries
 	double mismapper_frac = 0.03; // fraction of breakpoints whose clipped segment is alignable in the donor
 	double paralog_frac = 0.05;
+	double satellite_frac = 0.25; // fraction of breakpoints with shifted "satellite" breakpoints (merge_adjacent)
 	double softclip_supp_frac = 0.2; // supplementary with soft instead of hard clip
 	double nonproper_split_frac = 0.3;
 	double deep_frac = 0.01; int deep_depth = 2000; int depth_cap = 280;
@@ -324,23 +325,37 @@ static void make_breakpoints(world_t& w, const params_t& P, rng_t& rng) {
 		}
 		if (B.contig1 == B.contig2 && B.pos1 == B.pos2) B.pos2 += 37;
 		B.depth = rng.chance(P.deep_frac) ? P.deep_depth : min(P.depth_cap, rng.poisson(mean_depth));
-		if (b < P.n_breakpoints * P.mismapper_frac && g1 != g2 && B.down1 && !B.down2) {
-			// mismapper: make the sequence right of pos2 (what the clipped segment aligns to) a copy of
-			// what follows pos1 in the donor, so that the clipped segment extends linearly in the donor
+		if (b < P.n_breakpoints * P.mismapper_frac && g1 != g2) {
+			// mismapper: the acceptor locus around pos2 becomes a diverged copy of the donor locus around pos1 (homologous partner), so the
+			// clipped segment of every split read is also alignable next to the breakpoint in the other gene
+			B.down1 = true; B.down2 = false;
 			string& s1 = w.seq[B.contig1]; string& s2 = w.seq[B.contig2];
-			int n = 160;
-			if (B.pos1 + 1 + n < (int) s1.size() && B.pos2 + n < (int) s2.size()) {
-				for (int i = 0; i < n; ++i) {
+			const int n = 170;
+			if (B.pos1 - n > 0 && B.pos1 + 1 + n < (int) s1.size() && B.pos2 - n > 0 && B.pos2 + n < (int) s2.size()) {
+				const double divergence = rng.chance(0.5) ? 0.02 : 0.12; // some copies are too diverged to re-align
+				for (int i = -n; i < n; ++i) {
 					char c = s1[B.pos1 + 1 + i];
 					if (c == 'N') c = 'A';
-					if (rng.chance(0.03)) c = BASES[rng.below(4)];
+					if (rng.chance(divergence)) c = BASES[rng.below(4)];
 					s2[B.pos2 + i] = c;
 				}
-				B.tr2 = -1; // walk contiguously so that the copied stretch is what reads see
+				B.tr1 = -1; B.tr2 = -1; // walk contiguously so that the copied stretch is what reads see
 				B.mismapper = true;
 			}
 		}
 		w.bps.push_back(B);
+		if (rng.chance(P.satellite_frac) && !B.mismapper) { // alternative alignments of the same junction: a few reads at a breakpoint shifted by <= 5 bp on both ends
+			const int n_sat = 1 + rng.below(2);
+			for (int k = 0; k < n_sat; ++k) {
+				breakpoint_t S = B;
+				int delta = 1 + rng.below(5); if (rng.chance(0.5)) delta = -delta;
+				S.pos1 = B.pos1 + delta;
+				S.pos2 = B.pos2 + delta * ((B.down1 == B.down2) ? -1 : +1); // keeps the pair mergeable (merge_adjacent_fusions.cpp:48,63)
+				if (rng.chance(0.15)) S.pos2 += 1; // ... or not
+				S.depth = 1 + rng.below(6);
+				if (S.pos1 > 1000 && S.pos2 > 1000 && S.pos1 < (int) w.seq[S.contig1].size() - 1000 && S.pos2 < (int) w.seq[S.contig2].size() - 1000) w.bps.push_back(S);
+			}
+		}
 	}
 }
 
@@ -876,6 +891,7 @@ int main(int argc, char** argv) {
 		else if (a == "--multimap-frac") P.multimap_frac = atof(NEXT);
 		else if (a == "--mismapper-frac") P.mismapper_frac = atof(NEXT);
 		else if (a == "--paralog-frac") P.paralog_frac = atof(NEXT);
+		else if (a == "--satellite-frac") P.satellite_frac = atof(NEXT);
 		else if (a == "--subst-rate") P.subst_rate = atof(NEXT);
 		else if (a == "--indel-frac") P.indel_frac = atof(NEXT);
 		else if (a == "--deep-frac") P.deep_frac = atof(NEXT);
