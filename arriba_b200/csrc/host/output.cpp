@@ -13,6 +13,7 @@
 #include <map>
 #include <sstream>
 #include <stdexcept>
+#include <thread>
 #include <tuple>
 
 namespace arb { namespace host {
@@ -461,26 +462,8 @@ struct writer {
 		return e.bp2[x] < e.bp2[y];
 	}
 
-	void write(const std::string& path, bool discarded, bool extra_info) const {
-		std::vector<u32> rows;
-		for (size_t q = 0; q < e.order.size(); ++q) { const u32 k = e.order[q]; if (discarded != (e.filter[k] == F_none)) rows.push_back(k); }
-		if (!discarded) {
-			std::map<std::pair<u32, u32>, u32> best; // best-supported candidate per gene pair
-			for (size_t x = 0; x < rows.size(); ++x) {
-				std::pair<std::map<std::pair<u32, u32>, u32>::iterator, bool> ins = best.insert(std::make_pair(std::make_pair(e.gene1[rows[x]], e.gene2[rows[x]]), rows[x]));
-				if (!ins.second && by_support(rows[x], ins.first->second)) ins.first->second = rows[x];
-			}
-			std::sort(rows.begin(), rows.end(), [&](u32 x, u32 y) {
-				const u32 bx = best.at(std::make_pair(e.gene1[x], e.gene2[x])), by = best.at(std::make_pair(e.gene1[y], e.gene2[y]));
-				return bx != by ? by_support(bx, by) : by_support(x, y);
-			});
-		}
-		std::ofstream out(path.c_str());
-		if (!out.is_open()) throw std::runtime_error("failed to open output file");
-		out << "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers" << std::endl;
-		static const char* CONF[] = {"low", "medium", "high", "high"};
-		for (size_t x = 0; x < rows.size(); ++x) {
-			const u32 k = rows[x];
+	void format_row(std::ostream& out, u32 k, bool extra_info) const {
+			static const char* CONF[] = {"low", "medium", "high", "high"};
 			std::string site5 = site(e.gene1[k], e.spliced1(k), e.exonic1(k), e.contig1[k], e.bp1[k]), site3 = site(e.gene2[k], e.spliced2(k), e.exonic2(k), e.contig2[k], e.bp2[k]);
 			u32 g5 = e.gene1[k], g3 = e.gene2[k], c5 = e.contig1[k], c3 = e.contig2[k], d5 = e.dir1[k], d3 = e.dir2[k], s5 = e.split_reads1[k], s3 = e.split_reads2[k];
 			i32 b5 = e.bp1[k], b3 = e.bp2[k]; bool st5 = e.bits[k] & CB_PSTRAND1, st3 = e.bits[k] & CB_PSTRAND2;
@@ -530,8 +513,37 @@ struct writer {
 					out.write(nm, cut > 0 ? cut - 1 : len);
 				}
 			} else out << ".";
-			out << std::endl;
+			out << "\n";
+	}
+
+	void write(const std::string& path, bool discarded, bool extra_info) const {
+		std::vector<u32> rows;
+		for (size_t q = 0; q < e.order.size(); ++q) { const u32 k = e.order[q]; if (discarded != (e.filter[k] == F_none)) rows.push_back(k); }
+		if (!discarded) {
+			std::map<std::pair<u32, u32>, u32> best; // best-supported candidate per gene pair
+			for (size_t x = 0; x < rows.size(); ++x) {
+				std::pair<std::map<std::pair<u32, u32>, u32>::iterator, bool> ins = best.insert(std::make_pair(std::make_pair(e.gene1[rows[x]], e.gene2[rows[x]]), rows[x]));
+				if (!ins.second && by_support(rows[x], ins.first->second)) ins.first->second = rows[x];
+			}
+			std::sort(rows.begin(), rows.end(), [&](u32 x, u32 y) {
+				const u32 bx = best.at(std::make_pair(e.gene1[x], e.gene2[x])), by = best.at(std::make_pair(e.gene1[y], e.gene2[y]));
+				return bx != by ? by_support(bx, by) : by_support(x, y);
+			});
 		}
+		std::ofstream out(path.c_str());
+		if (!out.is_open()) throw std::runtime_error("failed to open output file");
+		out << "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n";
+		// rows are independent: format slices of the row list on the host threads, then write the slices in order
+		const int T = std::max(1, std::min(p.threads, (int) (rows.size() / 64 + 1)));
+		std::vector<std::string> slices(T); std::vector<std::string> errors(T);
+		std::vector<std::thread> pool;
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+			try { std::ostringstream os; for (size_t x = rows.size() * t / T; x < rows.size() * (t + 1) / T; ++x) format_row(os, rows[x], extra_info); slices[t] = os.str(); }
+			catch (const std::exception& ex) { errors[t] = ex.what(); }
+		});
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
+		for (int t = 0; t < T; ++t) out.write(slices[t].data(), slices[t].size());
 		out.close();
 		if (out.bad()) throw std::runtime_error("failed to write to file");
 	}
