@@ -13,9 +13,19 @@
 #include <sstream>
 #include <stdexcept>
 #include <tuple>
+#include <thread>
 #include <unordered_map>
 
 namespace arb { namespace host {
+
+// candidates are independent in the predicate loops below (each writes only its own row): run slices on the host threads
+template <class F> static void parallel_rows(int threads, size_t n, F f) {
+	if (threads <= 1 || n < 4096) { for (size_t k = 0; k < n; ++k) f((u32) k); return; }
+	std::vector<std::thread> pool; std::vector<std::string> errors(threads);
+	for (int t = 0; t < threads; ++t) pool.emplace_back([&, t]() { try { for (size_t k = n * t / threads; k < n * (t + 1) / threads; ++k) f((u32) k); } catch (const std::exception& x) { errors[t] = x.what(); } });
+	for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+	for (int t = 0; t < threads; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
+}
 
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 
@@ -315,14 +325,14 @@ void pipeline::filter_non_coding_neighbors() { // filter_non_coding_neighbors.cp
 void pipeline::filter_intragenic_both_exonic() { // filter_intragenic_both_exonic.cpp
 	const annot_view an = ref.host_view();
 	const float exonic_fraction = opt.exonic_fraction; // -e
-	for (u32 k = 0; k < ev.n; ++k) {
-		if (ev.filter[k] != F_none) continue;
+	parallel_rows(threads, ev.n, [&](u32 k) {
+		if (ev.filter[k] != F_none) return;
 		if ((overlaps_both(ev, ref, k) || ev.gene1[k] == ev.gene2[k]) && ev.exonic1(k) && ev.exonic2(k) && !(ev.spliced1(k) && ev.spliced2(k))) {
 			const int sd = spliced_distance(an, ev.contig1[k], ev.bp1[k], ev.bp2[k], ev.gene1[k]);
 			const int distance = ev.bp2[k] - ev.bp1[k];
 			if (sd == distance || 1.0 * sd / distance < exonic_fraction) ev.filter[k] = F_intragenic_exonic;
 		}
-	}
+	});
 	log_remaining("Filtering intragenic fusions with both breakpoints in exonic regions");
 }
 
@@ -377,11 +387,11 @@ void pipeline::filter_both_intronic() { // filter_both_intronic.cpp
 		for (u32 p = lo; p < hi; ++p) { const u32 i = list[p]; if (labels[i] != F_none) continue; for (u32 s = 0; s < frags.n_aln[i]; ++s) if (frags.aflags[(size_t) s * N + i] & AF_EXONIC) return true; }
 		return false;
 	};
-	for (u32 k = 0; k < ev.n; ++k) {
-		if (ev.filter[k] != F_none) continue;
-		if ((ref.contig_flags[ev.contig1[k]] & CF_VIRAL) || (ref.contig_flags[ev.contig2[k]] & CF_VIRAL)) continue;
+	parallel_rows(threads, ev.n, [&](u32 k) {
+		if (ev.filter[k] != F_none) return;
+		if ((ref.contig_flags[ev.contig1[k]] & CF_VIRAL) || (ref.contig_flags[ev.contig2[k]] & CF_VIRAL)) return;
 		if (!has_exonic(ev.list1, ev.list1_off[k], ev.list1_off[k + 1]) && !has_exonic(ev.list2, ev.list2_off[k], ev.list2_off[k + 1]) && !has_exonic(ev.listd, ev.listd_off[k], ev.listd_off[k + 1])) ev.filter[k] = F_intronic;
-	}
+	});
 	log_remaining("Filtering fusions with both breakpoints in intronic/intergenic regions");
 }
 
@@ -422,10 +432,10 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 		for (u32 x = 0; x < genes.n; ++x) if (reads_by_gene[genes.v[x]] > highest) { highest = reads_by_gene[genes.v[x]]; gene = genes.v[x]; }
 		return gene;
 	};
-	auto pair_count = [&](u32 a, u32 b) { std::map<std::pair<u32, u32>, unsigned int>::iterator it = exonic_breakpoints.find(std::make_pair(a, b)); return it == exonic_breakpoints.end() ? 0u : it->second; };
-	for (u32 k = 0; k < ev.n; ++k) {
+	auto pair_count = [&](u32 a, u32 b) { std::map<std::pair<u32, u32>, unsigned int>::const_iterator it = exonic_breakpoints.find(std::make_pair(a, b)); return it == exonic_breakpoints.end() ? 0u : it->second; };
+	parallel_rows(threads, ev.n, [&](u32 k) {
 		const u8 fl = ev.filter[k];
-		if (fl != F_none && !((ev.spliced1(k) || ev.spliced2(k)) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) continue;
+		if (fl != F_none && !((ev.spliced1(k) || ev.spliced2(k)) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) return;
 		float rt = 0;
 		if (!ev.exonic1(k)) rt += 0.5; else if (!ev.spliced1(k)) rt += 1;
 		if (!ev.exonic2(k)) rt += 0.5; else if (!ev.spliced2(k)) rt += 1;
@@ -452,7 +462,7 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 		    !(sup >= 10 && ((int) sup * 4) >= std::max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup && (ev.spliced1(k) || ev.spliced2(k)) && ((ev.spliced1(k) || !ev.exonic1(k)) && (ev.spliced2(k) || !ev.exonic2(k)))) &&
 		    (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || exonic_bp > 8 || sup <= 1))
 			ev.filter[k] = F_in_vitro;
-	}
+	});
 	log_remaining("Filtering in vitro-generated fusions");
 }
 
@@ -791,11 +801,11 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 	std::vector<std::vector<u32> > by_gene(ref.genes.size());
 	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; by_gene[ev.gene1[k]].push_back(k); by_gene[ev.gene2[k]].push_back(k); }
 	enum { LOW = 0, MEDIUM = 1, HIGH = 2 };
-	for (u32 k = 0; k < ev.n; ++k) {
+	parallel_rows(threads, ev.n, [&](u32 k) {
 		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		const float coverage_fraction = ((float) (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) / std::max(1, std::max(cov1, cov2));
-		if (ev.filter[k] != F_none) { ev.confidence[k] = LOW; continue; }
+		if (ev.filter[k] != F_none) { ev.confidence[k] = LOW; return; }
 		int conf = HIGH;
 		const u32 s1 = ev.split_reads1[k], s2 = ev.split_reads2[k], d = ev.discordant_mates[k], sup = s1 + s2 + d;
 		if (ev.evalue[k] > 0.3 || sup < 2) conf = LOW;
@@ -840,7 +850,7 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 			else if (ev.evalue[k] > 0.2 || coverage_fraction < 0.01) conf = MEDIUM;
 		}
 		ev.confidence[k] = (u8) conf;
-	}
+	});
 	say("Assigning confidence scores to events");
 }
 

@@ -17,6 +17,7 @@ run_options::run_options(): interesting_contigs("1 2 3 4 5 6 7 8 9 10 11 12 13 1
 
 void pipeline::say(const std::string& line) {
 	log += line; log += "\n";
+	if (getenv("ARB_TRACE")) { static double last = now_s(); const double t = now_s(); fprintf(stderr, "[trace] +%8.1f ms  %s\n", (t - last) * 1e3, line.c_str()); last = t; }
 	if (opt.echo_progress) { time_t now = time(0); char buf[64]; strftime(buf, sizeof(buf), "[%Y-%m-%dT%X]", localtime(&now)); std::cout << buf << " " << line << std::endl; }
 }
 
