@@ -1,4 +1,6 @@
 // engine.cu -- stage drivers: uploads, duplicate marking, the fused read-level cascade.
+#include <cstdlib>
+#include <algorithm>
 #include "engine.h"
 #include "mismatch_table.h"
 
@@ -15,6 +17,9 @@ void default_params(arb_params& p) { // options.cpp:71-107
 engine::engine(): table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
+	mismap_budget = 4096; mismap_lanes = 256; // tuning hooks: ARB_MISMAP_BUDGET (0 = no second pass), ARB_MISMAP_LANES
+	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
+	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
 #endif

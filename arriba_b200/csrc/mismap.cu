@@ -1,4 +1,5 @@
 // mismap.cu -- drivers of the k-mer index, gene homology and re-alignment stages (see mismap_hd.h).
+#include <algorithm>
 #include "engine.h"
 #include "mismap_hd.h"
 
@@ -96,8 +97,24 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
 	gene_splice_view sp = {splice_off.ptr(), splice_sites.ptr()};
 	mismap_params mp = {max_mate_gap, params.max_mismapper_fraction};
-	mismap_item_fn mi = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr()};
+	mismap_items items = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr()};
+	// pass 1: a thread per item, bounded; pass 2: the few items stuck in repeats, `lanes` threads each (mismap_hd.h, realign_ctl)
+	dbuf<u32> heavy(I), n_heavy(1);
+	n_heavy.zero(ex, 1);
+	mismap_item_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
+	stage_timer t1(ex);
 	for_each(ex, I, mi);
+	timings.mismappers_pass1_ms = t1.stop();
+	u32 H = 0; n_heavy.download(ex, &H, 1);
+	stage_timer t2(ex);
+	for (u32 done = 0; done < H; ) { // launches of at most 2^31 threads
+		const u32 batch = std::min<u32>(H - done, 0x80000000u / mismap_lanes);
+		mismap_heavy_fn mh = {items, heavy.ptr() + done, mismap_lanes};
+		for_each(ex, batch * mismap_lanes, mh);
+		done += batch;
+	}
+	timings.mismappers_pass2_ms = t2.stop();
+	timings.mismapper_heavy_items = H;
 	mismap_apply_fn ma = {mism.ptr(), frags.filter.ptr()};
 	for_each(ex, N, ma);
 	mismap_count_fn mc = {frags.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(),

@@ -10,6 +10,14 @@
 #include "prims.h"
 #include <math.h>
 
+#ifdef ARB_COST_PROBE
+#include <stdio.h>
+static thread_local unsigned long long arb_cost_probe = 0;
+#define ARB_COST(x) (arb_cost_probe += (x))
+#else
+#define ARB_COST(x)
+#endif
+
 namespace arb {
 
 ARB_HD u32 base2(char c) { return c == 'T' ? 0u : c == 'G' ? 1u : c == 'C' ? 2u : 3u; } // every other character (A, N, IUPAC) is 3
@@ -56,15 +64,38 @@ struct gene_window { u32 contig; i32 start, end; const i32* splice; u32 n_splice
 
 ARB_HD u32 lower_bound_i32(const i32* v, u32 lo, u32 hi, i32 x) { while (lo < hi) { u32 mid = lo + ((hi - lo) >> 1); if (v[mid] < x) lo = mid + 1; else hi = mid; } return lo; }
 
+// Work control of one re-alignment. The reference's align() is a pure "does ANY placement reach min_score" search: the outcome is the OR over all
+// (read position, k-mer hit) pairs and over the recursive continuations, so the pairs may be visited in any order and by any number of threads.
+//  * budget: the one-thread-per-item pass gives up after `budget` steps (a few reads that fall into tandem repeats cost 10^5 times the median);
+//  * lanes/lane/counter: the cooperative pass deals the top-level hits round-robin to `lanes` threads of the same item;
+//  * stop: set as soon as any lane (or any other item of the same fragment) found a placement.
+struct realign_ctl {
+	int budget; bool limited;
+	u32 lanes, lane, counter;
+	const volatile u8* stop;
+	ARB_HD bool spend() { return limited && --budget < 0; }
+	ARB_HD bool exhausted() const { return limited && budget < 0; }
+};
+ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; return c; }
+
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
-ARB_HD_RECURSIVE bool realign(int score, const read_slice& rs, int read_pos, const char* ref, int gene_pos, const gene_window& w, const kmer_index_view& ix, int min_score, int max_deletions) {
+ARB_HD_RECURSIVE bool realign(int score, const read_slice& rs, int read_pos, const char* ref, int gene_pos, const gene_window& w, const kmer_index_view& ix, int min_score, int max_deletions, realign_ctl& ctl, bool top) {
 	const int len = (int) rs.len;
 	int skipped = 0;
 	for (; read_pos + 8 < len && read_pos + min_score <= len + score + 16; ++read_pos, --score, ++skipped) {
 		u32 lo, hi; ix.bucket(w.contig, kmer8(rs, (u32) read_pos), lo, hi);
 		if (lo == hi) continue;
-		for (u32 h = lower_bound_i32(ix.pos, lo, hi, gene_pos); h < hi && ix.pos[h] < w.end; ++h) {
+		u32 h = lower_bound_i32(ix.pos, lo, hi, gene_pos), step = 1;
+		if (top && ctl.lanes > 1) { // deal this position's hits to the lanes, continuing the round-robin of the previous positions
+			if (ctl.stop && *ctl.stop) return false;
+			const u32 n_hits = lower_bound_i32(ix.pos, h, hi, w.end) - h;
+			h += (ctl.lane + ctl.lanes - ctl.counter % ctl.lanes) % ctl.lanes; step = ctl.lanes;
+			ctl.counter += n_hits;
+		}
+		for (; h < hi && ix.pos[h] < w.end; h += step) {
+			if (ctl.spend()) return false;
 			const int hit = ix.pos[h];
+			ARB_COST(1);
 			int ext = score + 8;
 			const bool leading = read_pos == skipped; // every base so far was skipped: no penalty for them (local alignment start)
 			if (leading) ext += skipped;
@@ -81,13 +112,15 @@ ARB_HD_RECURSIVE bool realign(int score, const read_slice& rs, int read_pos, con
 				int r = read_pos + 8, g = hit + 8; u32 mm = 0, consecutive = 0;
 				u32 ss = lower_bound_i32(w.splice, 0, w.n_splice, g - 1);
 				while (r < len && g <= w.end) {
+					ARB_COST(1);
+					if (ctl.spend()) return false;
 					if (ss < w.n_splice) {
 						if (g - 1 > w.splice[ss]) ++ss;
-						if (ss < w.n_splice && g - 1 == w.splice[ss] && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions)) return true;
+						if (ss < w.n_splice && g - 1 == w.splice[ss] && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions, ctl, false)) return true;
 					}
 					if (rs.at((u32) r) == ref[g]) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
 					else {
-						if (++mm == 1 && max_deletions > 0 && len >= 30 && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions - 1)) return true;
+						if (++mm == 1 && max_deletions > 0 && len >= 30 && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions - 1, ctl, false)) return true;
 						--ext;
 						if (++consecutive >= 4) break;
 					}
@@ -103,7 +136,7 @@ struct gene_splice_view { const u32* off; const i32* sites; }; // per gene: sort
 
 // filter_mismappers.cpp:189-230; `genes` = gene set of the OTHER segment
 ARB_HD bool realign_both_strands(const read_slice& fwd, int read_length, int max_mate_gap, bool same_contig, i32 aln_start, i32 aln_end, const u32* genes, u32 n_genes,
-                                 const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, float min_align_fraction) {
+                                 const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, float min_align_fraction, realign_ctl& ctl) {
 	if (fwd.len >= 300) return false;
 #ifdef __CUDA_ARCH__
 	const int min_score = (int) ((double) __fmul_rn(min_align_fraction, (float) fwd.len) + 0.5);
@@ -120,9 +153,9 @@ ARB_HD bool realign_both_strands(const read_slice& fwd, int read_length, int max
 		if (w.contig >= ix.n_index_contigs) continue;
 		w.splice = sp.sites + sp.off[g]; w.n_splice = sp.off[g + 1] - sp.off[g];
 		const char* ref = an.assembly + an.contig_seq_off[w.contig];
-		if (realign(0, fwd, 0, ref, w.start, w, ix, min_score, 1)) return true;
+		if (realign(0, fwd, 0, ref, w.start, w, ix, min_score, 1, ctl, true)) return true;
 		read_slice rev = fwd; rev.rc = !fwd.rc;
-		if (realign(0, rev, 0, ref, w.start, w, ix, min_score, 1)) return true;
+		if (realign(0, rev, 0, ref, w.start, w, ix, min_score, 1, ctl, true)) return true;
 	}
 	return false;
 }
@@ -156,15 +189,14 @@ ARB_HD bool extends_linearly(const frag_view& f, const annot_view& an, u32 a /* 
 struct mismap_params { i32 max_mate_gap; float max_mismapper_fraction; };
 
 // one work item = one (candidate, listed fragment) pair
-struct mismap_item_fn {
+struct mismap_items {
 	frag_view f; annot_view an; kmer_index_view ix; gene_splice_view sp; mismap_params p;
 	const u32* item_cand; const u32* item_frag; const u8* item_kind /* 0 split read, 1 discordant */; const u16* cand_contig1; const u16* cand_contig2; const u8* cand_filter;
 	u8* mismapper; // per fragment, set to 1 when any evaluation says "mis-mapped"
-	ARB_HD void operator()(u32 j) const {
+	ARB_HD bool skip(u32 j) const { return cand_filter[item_cand[j]] != F_none || f.filter[item_frag[j]] != F_none; }
+	ARB_HD bool evaluate(u32 j, realign_ctl& ctl, bool with_linear_extension) const {
 		const u32 cand = item_cand[j], i = item_frag[j];
-		if (cand_filter[cand] != F_none || f.filter[i] != F_none) return;
 		const bool same_contig = cand_contig1[cand] == cand_contig2[cand];
-		bool bad = false;
 		if (item_kind[j] == 0) {
 			const u32 m = f.idx(i, MATE1), s = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
 			const u32 slen = f.seq_len[s], mlen = f.seq_len[m];
@@ -172,18 +204,47 @@ struct mismap_item_fn {
 			clipped.nt16 = f.sq(s); clipped.rc = false; anchor.nt16 = f.sq(m); anchor.rc = false;
 			if (f.fwd(s)) { clipped.off = 0; clipped.len = hd_min(f.preclip(s), slen); const u32 pre = hd_min(f.preclip(m), mlen); anchor.off = pre; anchor.len = mlen - pre; }
 			else { const u32 post = hd_min(f.postclip(s), slen); clipped.off = slen - post; clipped.len = post; const u32 mpost = hd_min(f.postclip(m), mlen); anchor.off = 0; anchor.len = mlen - mpost; }
-			bad = extends_linearly(f, an, s) ||
-			      realign_both_strands(clipped, (int) slen, p.max_mate_gap, same_contig, f.start[u], f.end[u], f.genes + f.genes_off[s], f.genes_cnt[s], an, ix, sp, 0.8f) ||
-			      realign_both_strands(anchor, (int) mlen, p.max_mate_gap, same_contig, f.start[m], f.end[m], f.genes + f.genes_off[u], f.genes_cnt[u], an, ix, sp, 0.8f);
+			return (with_linear_extension && extends_linearly(f, an, s)) ||
+			       realign_both_strands(clipped, (int) slen, p.max_mate_gap, same_contig, f.start[u], f.end[u], f.genes + f.genes_off[s], f.genes_cnt[s], an, ix, sp, 0.8f, ctl) ||
+			       realign_both_strands(anchor, (int) mlen, p.max_mate_gap, same_contig, f.start[m], f.end[m], f.genes + f.genes_off[u], f.genes_cnt[u], an, ix, sp, 0.8f, ctl);
 		} else {
 			const u32 a = f.idx(i, MATE1), b = f.idx(i, MATE2);
 			const float cf1 = ((float) f.preclip(a) + f.postclip(a)) / f.seq_len[a], cf2 = ((float) f.preclip(b) + f.postclip(b)) / f.seq_len[b];
 			const float fr1 = hd_min(0.8f, 0.8f * (1 - cf1)), fr2 = hd_min(0.8f, 0.8f * (1 - cf2));
 			read_slice ra = {f.sq(a), 0, f.seq_len[a], false}, rb = {f.sq(b), 0, f.seq_len[b], false};
-			bad = realign_both_strands(ra, (int) f.seq_len[a], p.max_mate_gap, same_contig, f.start[a], f.end[a], f.genes + f.genes_off[b], f.genes_cnt[b], an, ix, sp, fr1) ||
-			      realign_both_strands(rb, (int) f.seq_len[b], p.max_mate_gap, same_contig, f.start[b], f.end[b], f.genes + f.genes_off[a], f.genes_cnt[a], an, ix, sp, fr2);
+			return realign_both_strands(ra, (int) f.seq_len[a], p.max_mate_gap, same_contig, f.start[a], f.end[a], f.genes + f.genes_off[b], f.genes_cnt[b], an, ix, sp, fr1, ctl) ||
+			       realign_both_strands(rb, (int) f.seq_len[b], p.max_mate_gap, same_contig, f.start[b], f.end[b], f.genes + f.genes_off[a], f.genes_cnt[a], an, ix, sp, fr2, ctl);
 		}
-		if (bad) mismapper[i] = 1;
+	}
+};
+
+// pass 1: one thread per item with a step budget; items that run out of budget undecided are queued for pass 2
+struct mismap_item_fn {
+	mismap_items it; int budget; u32* heavy; u32* n_heavy;
+	ARB_HD void operator()(u32 j) const {
+		if (it.skip(j)) return;
+		const u32 i = it.item_frag[j];
+		if (((const volatile u8*) it.mismapper)[i]) return; // another candidate's evaluation of this fragment already decided (the label is an OR)
+		realign_ctl ctl = unlimited_ctl(); ctl.limited = budget > 0; ctl.budget = budget;
+		const bool bad = it.evaluate(j, ctl, true);
+		if (bad) it.mismapper[i] = 1;
+		else if (ctl.exhausted()) heavy[atomic_add_u32(n_heavy, 1)] = j;
+#ifdef ARB_COST_PROBE
+		fprintf(stderr, "COST %u %u %u %llu %d\n", j, it.item_cand[j], (unsigned) it.item_kind[j], arb_cost_probe, (int) bad); arb_cost_probe = 0;
+#endif
+	}
+};
+// pass 2: `lanes` threads per queued item share the top-level k-mer hits
+struct mismap_heavy_fn {
+	mismap_items it; const u32* heavy; u32 lanes;
+	ARB_HD void operator()(u32 t) const {
+		const u32 j = heavy[t / lanes], i = it.item_frag[j];
+		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
+		if (*ctl.stop) return;
+		if (it.evaluate(j, ctl, false)) it.mismapper[i] = 1;
+#ifdef ARB_COST_PROBE
+		fprintf(stderr, "HEAVY %u %u %llu\n", j, ctl.lane, arb_cost_probe); arb_cost_probe = 0;
+#endif
 	}
 };
 

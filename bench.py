@@ -228,8 +228,9 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_for_each<classify_fn> (fused read-level cascade)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(tm.classify_algorithmic_bytes), "kernel_ms": cls_ms,
                          "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
-                                       "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms},
-                         "mismapper_items": int(tm.mismapper_items), "kmer_positions": int(tm.kmer_positions)},
+                                       "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
+                                       "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},
+                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "kmer_positions": int(tm.kmer_positions)},
             "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
     if not args.no_cpu_baseline:
         sp = ensure_world(args.workload, sample_bp)

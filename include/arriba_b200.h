@@ -179,6 +179,8 @@ typedef struct arb_timings {
 	float merge_adjacent_ms, evalue_ms, kmer_index_ms, homologs_ms, mismappers_ms; /* candidate-level device stages */
 	uint64_t mismapper_items;   /* (candidate, read) pairs re-aligned */
 	uint64_t kmer_positions;    /* positions in the k-mer index */
+	uint64_t mismapper_heavy_items; /* pairs that exhausted the one-thread budget and were re-aligned cooperatively */
+	float mismappers_pass1_ms, mismappers_pass2_ms;
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 

@@ -23,7 +23,7 @@ def compare_stage(got, want, stage, check_evalue):
     return perm
 
 
-def check_events(world, lib_path, threads=4):
+def check_events(world, lib_path, threads=4, keep=False):
     p = L.Pipeline(world.prefix + ".bam", world.prefix + ".gtf", world.prefix + ".fa", threads=threads, lib_path=lib_path)
     p.run(L.STEP_FIND_FUSIONS)
     p.events(0)
@@ -52,6 +52,8 @@ def check_events(world, lib_path, threads=4):
         assert int((got["filter"] == 0).sum()) == int(want["remaining"][0]) or name in ("evalue", "confidence"), name
         if name == "confidence":
             assert np.array_equal(got["confidence"], want["confidence"][compare_stage(got, want, name, True)])
+    if keep:
+        return p
     p.close()
 
 
@@ -75,8 +77,23 @@ def test_events_hostsim_mismapper_heavy(worlds, hostsim_lib):
     check_events(w, hostsim_lib)
 
 
+def test_events_hostsim_cooperative_realignment(worlds, hostsim_lib, monkeypatch):
+    """A tiny step budget pushes almost every (candidate, read) pair through the cooperative second pass; labels must not change."""
+    monkeypatch.setenv("ARB_MISMAP_BUDGET", "24"); monkeypatch.setenv("ARB_MISMAP_LANES", "7")
+    p = check_events(worlds.get("cfg5", **CFG5), hostsim_lib, keep=True)
+    tm = p.context().timings(); p.close()
+    assert tm.mismapper_heavy_items > 0.2 * tm.mismapper_items
+
+
 @pytest.mark.gpu
 def test_events_cuda_mismapper_heavy(worlds, cuda_lib):
+    check_events(worlds.get("cfg5", **CFG5), cuda_lib)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("budget,lanes", [("16", "32"), ("200", "256"), ("0", "1")])
+def test_events_cuda_cooperative_realignment(worlds, cuda_lib, monkeypatch, budget, lanes):
+    monkeypatch.setenv("ARB_MISMAP_BUDGET", budget); monkeypatch.setenv("ARB_MISMAP_LANES", lanes)
     check_events(worlds.get("cfg5", **CFG5), cuda_lib)
 
 
