@@ -17,13 +17,27 @@ void default_params(arb_params& p) { // options.cpp:71-107
 engine::engine(): table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
-	mismap_budget = 4096; mismap_lanes = 256; // tuning hooks: ARB_MISMAP_BUDGET (0 = no second pass), ARB_MISMAP_LANES
+	mismap_budget = 4096; mismap_lanes = 1024; // tuning hooks: ARB_MISMAP_BUDGET (0 = no second pass), ARB_MISMAP_LANES
 	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
 	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
 #endif
 }
+
+// reference bases as nt16 codes, eight per word: the mismatch rule compares eight read bases per XOR (read_filters.h)
+struct pack_assembly_fn {
+	const char* bases; u32 length; u32* packed; u32* exotic; // one contig; bases and packed start at the contig's (64-base aligned) offset
+	ARB_HD void operator()(u32 w) const {
+		u32 word = 0;
+		for (u32 b = 0; b < 8 && w * 8 + b < length; ++b) {
+			const u32 code = nt16_of_char(bases[w * 8 + b]);
+			if (code > 15) { *exotic = 1; continue; }
+			word |= code << (28 - 4 * b);
+		}
+		packed[w] = word;
+	}
+};
 
 void engine::set_contigs(const arb_contigs& c) {
 	annot.n_contigs = c.n_contigs;
@@ -50,6 +64,18 @@ void engine::set_contigs(const arb_contigs& c) {
 	annot.contig_flags.upload(ex, annot.h_contig_flags.data(), c.n_contigs);
 	annot.contig_len.upload(ex, annot.h_contig_len.data(), c.n_contigs);
 	annot.contig_seq_off.upload(ex, off.data(), c.n_contigs);
+	{
+		const u64 n_words = total / 8 + 9; // windows read one word past the last base
+		annot.assembly4.ensure(n_words); annot.assembly4.zero(ex, n_words);
+		dbuf<u32> exotic(1); exotic.zero(ex, 1);
+		for (u32 k = 0; k < c.n_contigs; ++k) {
+			if (annot.h_contig_len[k] == 0) continue;
+			pack_assembly_fn pf = {annot.assembly.ptr() + off[k], annot.h_contig_len[k], annot.assembly4.ptr() + off[k] / 8, exotic.ptr()};
+			for_each(ex, (annot.h_contig_len[k] + 7) / 8, pf);
+		}
+		u32 flag = 0; exotic.download(ex, &flag, 1);
+		annot.assembly4_ok = flag == 0;
+	}
 	ex.sync();
 	has_contigs = true;
 	table_n = 0; // mismatch table depends on the genome size
@@ -91,10 +117,14 @@ void engine::push_chunk(const arb_soa_chunk& c) {
 	frags.max_seq_len = max_len;
 	timings.h2d_ms = t_h2d.stop();
 	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 1 + 4 + 2 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes + c.n_genes * 4;
-	// bytes the fused cascade has to touch once: all per-fragment/per-alignment columns, the three pools, the reference bases under the
-	// two alignments the mismatch rule walks (~ one read length each), and the two label bytes it writes
-	timings.classify_algorithmic_bytes = timings.h2d_bytes + (u64) n * 2;
-	for (size_t k = 0; k < 2 * (size_t) n; ++k) timings.classify_algorithmic_bytes += c.seq_len[k];
+	// Column budget of SURVEY.md section 8(d): every column read once at its compact width -- 11 B per alignment {contig u16, start, end, flags u8}, CIGAR ops and
+	// gene ids with a 4-byte offset per alignment, 6 B per fragment {rank, flags, label}; sequences at 3 bit/base, gathered reference bases at 2 bit/base.
+	u64 n_alignments = 0, bases = 0;
+	for (size_t k = 0; k < n; ++k) n_alignments += c.n_aln[k];
+	for (size_t k = 0; k < 2 * (size_t) n; ++k) bases += c.seq_len[k];
+	head_bytes = n_alignments * 11 + ((u64) c.n_cigar + n_alignments) * 4 + ((u64) c.n_genes + n_alignments) * 4 + (u64) n * 6;
+	sequence_bytes = bases * 3 / 8 + bases * 2 / 8 + ((u64) c.n_cigar + n_alignments) * 4 + n_alignments * 11 + (u64) n * 2;
+	timings.classify_algorithmic_bytes = head_bytes + sequence_bytes;
 	ex.sync();
 	filters_done = false;
 	cands.n = 0;
@@ -147,15 +177,42 @@ struct dup_external_fn {
 	ARB_HD void operator()(u32 i) const { if (f.filter[i] == F_none && (f.fflags[i] & FF_DUPLICATE)) f.filter[i] = F_duplicates; }
 };
 
-// ------------------------------------------------------------------------------------------- fused cascade
-struct classify_fn {
-	read_filter_params p; frag_view f; annot_view an; u8* early;
+// ------------------------------------------------------------------------------------------- the cascade, two kernels
+struct cascade_head_fn {
+	read_filter_params p; frag_view f; annot_view an; u8* early; u32* queue; u32* n_queued;
 	ARB_HD void operator()(u32 i) const {
-		u8 e;
-		const u8 label = classify_fragment(p, f, an, i, e);
+		u8 e; bool more;
+		const u8 label = classify_head(p, f, an, i, e, more);
 		f.filter[i] = label; early[i] = e;
+		if (more) queue[append_slot(n_queued)] = i;
 	}
 };
+struct cascade_sequences_fn {
+	read_filter_params p; frag_view f; annot_view an; const u32* queue;
+	ARB_HD void operator()(u32 j, u32* scratch, u32 stride) const { const u32 i = queue[j]; f.filter[i] = classify_sequences(p, f, an, i, scratch, stride); }
+};
+
+// test hook: (mismatches, compared bases) of the two alignments the mismatch rule walks, on the packed reference and base by base
+struct mismatch_probe_fn {
+	frag_view f; annot_view packed, plain; u32* out; // 8 per fragment
+	ARB_HD void operator()(u32 i) const {
+		const u32 n = f.n_aln[i], a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
+		const u32 y = n == 2 ? a1 : a2; const bool rc = n == 3 && f.fwd(a2) != f.fwd(a1);
+		u32* o = out + (size_t) i * 8;
+		count_mismatches(f, packed, a0, f.sq(a0), f.seq_len[a0], false, o[0], o[1]);
+		count_mismatches(f, packed, y, f.sq(a1), f.seq_len[a1], rc, o[2], o[3]);
+		count_mismatches(f, plain, a0, f.sq(a0), f.seq_len[a0], false, o[4], o[5]);
+		count_mismatches(f, plain, y, f.sq(a1), f.seq_len[a1], rc, o[6], o[7]);
+	}
+};
+void engine::probe_mismatch_counts(u32* out) {
+	if (!annot.assembly4_ok) throw arb_error("the packed reference is disabled (characters outside the nt16 alphabet)");
+	dbuf<u32> d((size_t) frags.n * 8);
+	annot_view plain = annot.view(); plain.assembly4 = 0;
+	mismatch_probe_fn fn = {frags.view(), annot.view(), plain, d.ptr()};
+	for_each(ex, frags.n, fn);
+	d.download(ex, out, (size_t) frags.n * 8);
+}
 
 struct count_labels_fn {
 	const u8* filter; u32* counts;
@@ -187,11 +244,24 @@ void engine::run_read_filters() {
 	}
 	timings.duplicates_ms = t_dup.stop();
 	}
-	classify_fn cf = {p, f, annot.view(), frags.early.ptr()};
 	{
+		dbuf<u32> queue(n), n_queued(1);
+		n_queued.zero(ex, 1);
 		stage_timer t_cls(ex);
-		for_each(ex, n, cf);
+		stage_timer t_head(ex);
+		cascade_head_fn hf = {p, f, annot.view(), frags.early.ptr(), queue.ptr(), n_queued.ptr()};
+		for_each(ex, n, hf);
+		timings.cascade_head_ms = t_head.stop();
+		u32 q = 0; n_queued.download(ex, &q, 1);
+		stage_timer t_seq(ex);
+		cascade_sequences_fn sf = {p, f, annot.view(), queue.ptr()};
+		for_each_scratch<64>(ex, q, sf);
+		timings.cascade_sequences_ms = t_seq.stop();
 		timings.classify_ms = t_cls.stop();
+		timings.cascade_queued = q;
+		timings.cascade_algorithmic_bytes[0] = head_bytes;
+		timings.cascade_algorithmic_bytes[1] = n ? (u64) ((double) sequence_bytes * q / n) : 0;
+		timings.classify_algorithmic_bytes = timings.cascade_algorithmic_bytes[0] + timings.cascade_algorithmic_bytes[1];
 	}
 	timings.read_filters_ms = t_all.stop();
 	ex.sync();

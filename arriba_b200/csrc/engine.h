@@ -49,11 +49,11 @@ struct annot_store {
 	dbuf<u32> exon_gene; dbuf<i32> exon_start, exon_end, exon_cds_start, exon_cds_end, exon_next_start; dbuf<u8> exon_flags;
 	dbuf<u32> exon_region_begin, exon_region_off, exon_region_items, gene_region_begin, gene_region_off, gene_region_items;
 	dbuf<i32> exon_region_end, gene_region_end;
-	dbuf<u8> contig_flags; dbuf<u64> contig_seq_off; dbuf<u32> contig_len; dbuf<char> assembly;
+	dbuf<u8> contig_flags; dbuf<u64> contig_seq_off; dbuf<u32> contig_len; dbuf<char> assembly; dbuf<u32> assembly4; bool assembly4_ok;
 	std::vector<u8> h_contig_flags; std::vector<u32> h_contig_len;
 	// host mirrors needed by host-side steps
 	std::vector<u16> h_gene_contig; std::vector<i32> h_gene_start, h_gene_end; std::vector<u8> h_gene_strand, h_gene_flags;
-	annot_store(): n_genes(0), n_exons(0), n_contigs(0) {}
+	annot_store(): n_genes(0), n_exons(0), n_contigs(0), assembly4_ok(false) {}
 	annot_view view() const {
 		annot_view v;
 		v.n_genes = n_genes; v.gene_contig = gene_contig.ptr(); v.gene_start = gene_start.ptr(); v.gene_end = gene_end.ptr();
@@ -63,7 +63,7 @@ struct annot_store {
 		v.n_contigs = n_contigs;
 		v.exon_region_begin = exon_region_begin.ptr(); v.exon_region_end = exon_region_end.ptr(); v.exon_region_off = exon_region_off.ptr(); v.exon_region_items = exon_region_items.ptr();
 		v.gene_region_begin = gene_region_begin.ptr(); v.gene_region_end = gene_region_end.ptr(); v.gene_region_off = gene_region_off.ptr(); v.gene_region_items = gene_region_items.ptr();
-		v.contig_flags = contig_flags.ptr(); v.contig_seq_off = contig_seq_off.ptr(); v.contig_len = contig_len.ptr(); v.assembly = assembly.ptr();
+		v.contig_flags = contig_flags.ptr(); v.contig_seq_off = contig_seq_off.ptr(); v.contig_len = contig_len.ptr(); v.assembly = assembly.ptr(); v.assembly4 = assembly4_ok ? assembly4.ptr() : 0;
 		return v;
 	}
 };
@@ -111,6 +111,7 @@ public:
 	dbuf<u32> merge_log; u32 merge_log_n;
 	// k-mer index / re-alignment
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
+	u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
 	int mismap_budget; u32 mismap_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
 	void set_splice_sites(const u32* off, const i32* sites);
@@ -118,6 +119,7 @@ public:
 	void kmer_index_digest(u64* kmers, u64* positions, u64* checksum, u32 n_contigs);
 	void homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out);
 	u64 filter_mismappers(i32 max_mate_gap);
+	void probe_mismatch_counts(u32* out); // test hook (arb_selftest_mismatch_counts)
 private:
 	read_filter_params make_filter_params();
 	unsigned long genome_size() const;

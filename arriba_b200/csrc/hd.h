@@ -61,6 +61,53 @@ ARB_HD u32 nt16_complement(u32 code) {
 	switch (code) { case NT_A: return NT_T; case NT_T: return NT_A; case NT_C: return NT_G; case NT_G: return NT_C; default: return code; }
 }
 ARB_HD u32 nt16_at(const u8* seq, u32 i) { return (seq[i >> 1] >> ((~i & 1) << 2)) & 0xf; }
+// nt16 code of a reference character; 16 = not in the alphabet (such a base never equals a read base)
+ARB_HD u32 nt16_of_char(char c) {
+	switch (c) {
+		case '=': return 0; case 'A': return 1; case 'C': return 2; case 'M': return 3; case 'G': return 4; case 'R': return 5; case 'S': return 6; case 'V': return 7;
+		case 'T': return 8; case 'W': return 9; case 'Y': return 10; case 'H': return 11; case 'K': return 12; case 'D': return 13; case 'B': return 14; case 'N': return 15;
+		default: return 16;
+	}
+}
+
+// ---- bit tricks on words of eight 4-bit bases, first base in the most significant nibble
+ARB_HD u32 bswap32(u32 x) {
+#ifdef __CUDA_ARCH__
+	return __byte_perm(x, 0, 0x0123);
+#else
+	return __builtin_bswap32(x);
+#endif
+}
+ARB_HD u32 brev32(u32 x) {
+#ifdef __CUDA_ARCH__
+	return __brev(x);
+#else
+	x = (x >> 1 & 0x55555555u) | (x & 0x55555555u) << 1; x = (x >> 2 & 0x33333333u) | (x & 0x33333333u) << 2; x = (x >> 4 & 0x0f0f0f0fu) | (x & 0x0f0f0f0fu) << 4;
+	return __builtin_bswap32(x);
+#endif
+}
+ARB_HD u32 popc32(u32 x) {
+#ifdef __CUDA_ARCH__
+	return (u32) __popc(x);
+#else
+	return (u32) __builtin_popcount(x);
+#endif
+}
+// words of a BAM-order nt16 sequence (two bases per byte, first base in the high nibble); the sequence is padded to whole words
+ARB_HD u32 nt16_word(const u8* seq, u32 k, u32 n_words) { return k < n_words ? bswap32(((const u32*) seq)[k]) : 0u; }
+// eight bases starting at base `start` (>= -7; bases before the sequence read as 0)
+ARB_HD u32 nt16_window(const u8* seq, u32 n_words, i32 start) {
+	if (start < 0) return nt16_word(seq, 0, n_words) >> (4 * (u32) -start);
+	const u32 k = (u32) start >> 3, sh = ((u32) start & 7) * 4;
+	const u32 hi = nt16_word(seq, k, n_words);
+	return sh ? hi << sh | nt16_word(seq, k + 1, n_words) >> (32 - sh) : hi;
+}
+// same for the packed reference (native words, first base in the most significant nibble)
+ARB_HD u32 packed_window(const u32* words, u64 start) {
+	const u64 k = start >> 3; const u32 sh = ((u32) start & 7) * 4;
+	const u32 hi = words[k];
+	return sh ? hi << sh | words[k + 1] >> (32 - sh) : hi;
+}
 
 template <class T> ARB_HD T hd_min(T a, T b) { return a < b ? a : b; }
 template <class T> ARB_HD T hd_max(T a, T b) { return a > b ? a : b; }

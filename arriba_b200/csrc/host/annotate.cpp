@@ -14,7 +14,8 @@
 
 namespace arb { namespace host {
 
-typedef idset<64> gset;
+typedef idset<1024> gset;       // gene set of one alignment (an alignment with a long intron gap spans many genes)
+typedef idset<16384> eset;     // exons under one alignment
 
 template <class F> static void parallel_ranges(int threads, size_t n, F f) {
 	if (threads <= 1 || n < 1024) { f(0, (size_t) 0, n); return; }
@@ -33,11 +34,11 @@ struct gene_refs {
 	void load(size_t a, gset& s) const { s.clear(); s.assign(get(a), cnt[a]); }
 };
 
-static void check_overflow(const gset& s) { if (s.overflow) throw std::runtime_error("more than 64 overlapping genes at one locus are not supported"); }
+template <int CAP> static void check_overflow(const idset<CAP>& s) { if (s.overflow) throw std::runtime_error("more than " + std::to_string(CAP) + " overlapping genes or exons under one alignment are not supported"); }
 
 // gene set and strand of one alignment from the exon index (annotation.cpp:431-503)
 static void annotate_alignment(const annot_view& an, const frag_view& f, u32 a, gset& genes) {
-	gset exons_hit;
+	eset exons_hit;
 	query_index(exon_index(an), f.contig[a], f.start[a], f.end[a], exons_hit); check_overflow(exons_hit);
 	genes.clear();
 	for (u32 k = 0; k < exons_hit.n; ++k) genes.insert(an.exon_gene[exons_hit.v[k]]);

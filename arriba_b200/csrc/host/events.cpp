@@ -359,8 +359,8 @@ void pipeline::recover_internal_tandem_duplication() { // recover_internal_tande
 		if (fl != F_relative_support && fl != F_intragenic_exonic && fl != F_hairpin && fl != F_inconsistently_clipped && fl != F_mismatches) continue;
 		if (!(ev.gene1[k] == ev.gene2[k] && ev.exonic1(k) && ev.exonic2(k) && ev.dir1[k] == UPSTREAM && ev.dir2[k] == DOWNSTREAM && ref.genes[ev.gene1[k]].is_protein_coding &&
 		      ((unsigned int) ev.bp2[k] - (unsigned int) ev.bp1[k]) < max_itd_length)) continue;
-		idset<64> exons;
-		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp2[k], exons);
+		idset<4096> exons;
+		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp2[k], exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		bool coding = false;
 		for (u32 x = 0; x < exons.n; ++x) {
 			const exon_rec& ex = ref.exons[exons.v[x]];
@@ -428,7 +428,7 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 	find_top_expressed_genes(reads_by_gene, present, threshold, opt.high_expression_quantile); // -Q
 	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
 		unsigned int highest = reads_by_gene[gene];
-		idset<64> genes; query_index(gene_index(an), contig, bp, bp, genes);
+		idset<1024> genes; query_index(gene_index(an), contig, bp, bp, genes); if (genes.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		for (u32 x = 0; x < genes.n; ++x) if (reads_by_gene[genes.v[x]] > highest) { highest = reads_by_gene[genes.v[x]]; gene = genes.v[x]; }
 		return gene;
 	};
@@ -476,10 +476,10 @@ unsigned int pipeline::spliced_support(u32 k, const std::vector<u32>& reads_by_g
 		const unsigned int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		const unsigned int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		if (cov1 + cov2 > ev.supporting_reads(k) * max_coverage) return 0;
-		idset<64> exons;
-		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp1[k], exons);
+		idset<4096> exons;
+		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp1[k], exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
-		query_index(exon_index(an), ev.contig2[k], ev.bp2[k], ev.bp2[k], exons);
+		query_index(exon_index(an), ev.contig2[k], ev.bp2[k], ev.bp2[k], exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
 	}
 	unsigned int multi = 0, unique = 0;
@@ -655,7 +655,7 @@ void pipeline::filter_no_coverage() { // filter_no_coverage.cpp
 		for (int side = 1; side <= 2 && !discard; ++side) {
 			const u16 contig = side == 1 ? ev.contig1[k] : ev.contig2[k]; const i32 bp = side == 1 ? ev.bp1[k] : ev.bp2[k];
 			const u32 gene = side == 1 ? ev.gene1[k] : ev.gene2[k]; const u32 dir = side == 1 ? ev.dir1[k] : ev.dir2[k]; const i32 anchor = side == 1 ? ev.anchor1[k] : ev.anchor2[k];
-			idset<64> exons; query_index(exon_index(an), contig, bp, bp, exons);
+			idset<4096> exons; query_index(exon_index(an), contig, bp, bp, exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 			bool terminal = false;
 			for (u32 x = 0; x < exons.n && !terminal; ++x) { const exon_rec& ex = ref.exons[exons.v[x]]; if (ex.gene == gene && (ex.prev == -1 || ex.next == -1)) terminal = true; }
 			if (terminal) continue;

@@ -302,10 +302,11 @@ struct worker {
 	bool extract_read_through(const std::string& name, const rec_t* a, const rec_t* b) {
 		const rec_t* fm = a; const rec_t* rm = b;
 		if (fm->reverse()) { const rec_t* t = fm; fm = rm; rm = t; }
-		idset<32> fg, rg, common;
+		idset<1024> fg, rg, common;
 		const region_index_view gix = gene_index(an);
 		if (fm) query_index(gix, (u32) fm->tid, fm->pos, fm->pos, fg); else query_index(gix, (u32) rm->tid, rm->pos, rm->pos, fg);
 		if (rm) query_index(gix, (u32) rm->tid, rm->endpos(), rm->endpos(), rg); else query_index(gix, (u32) fm->tid, fm->endpos(), fm->endpos(), rg);
+		if (fg.overflow || rg.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		combine_sets(fg.v, fg.n, rg.v, rg.n, common, false);
 		if (!(common.n == 0 && !(fg.n == 0 && rg.n == 0))) return false;
 		i32 fgs, fge, rgs, rge;

@@ -427,7 +427,7 @@ struct writer {
 		if (g.is_dummy || bp < g.start || bp > g.end) return "intergenic";
 		if (!exonic) return "intron";
 		const annot_view an = const_cast<refdata&>(ref).host_view();
-		idset<64> exons; query_index(exon_index(an), contig, bp, bp, exons);
+		idset<4096> exons; query_index(exon_index(an), contig, bp, bp, exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		bool overlapping = false, utr = true; unsigned int end3 = 0, end5 = 0;
 		for (u32 x = 0; x < exons.n; ++x) {
 			const exon_rec& E = ref.exons[exons.v[x]];

@@ -64,6 +64,7 @@ struct annot_view {
 	u64* contig_seq_off;     // offset of the contig's sequence in assembly[]; ~0 if the sequence is not loaded
 	u32* contig_len;
 	const char* assembly;    // upper-cased reference bases, 1 byte per base
+	const u32* assembly4;    // the same bases as nt16 codes, 8 per word (first base in the top nibble), same base offsets; 0 if a character outside the nt16 alphabet occurs
 };
 enum { GF_DUMMY = 1, GF_CODING = 2, EF_HAS_PREV = 1, EF_HAS_NEXT = 2, CF_INTERESTING = 1, CF_VIRAL = 2 };
 

@@ -144,8 +144,23 @@ template <class F> void for_each(const exec_ctx& ex, u32 n, const F& f) {
 	ARB_CUDA_CHECK(cudaGetLastError());
 	++stats().kernels;
 }
+// functor with a private scratch array of WORDS 32-bit words per thread, kept in shared memory and interleaved by thread
+// (word k of thread t at [k * BLOCK + t]: dynamically indexed, yet free of bank conflicts); f(i, scratch, stride)
+template <u32 WORDS, u32 BLOCK, class F> __global__ void __launch_bounds__(BLOCK) k_for_each_scratch(u32 n, F f) {
+	__shared__ u32 scratch[WORDS * BLOCK];
+	u32 i = blockIdx.x * BLOCK + threadIdx.x;
+	if (i < n) f(i, scratch + threadIdx.x, BLOCK);
+}
+template <u32 WORDS, class F> void for_each_scratch(const exec_ctx& ex, u32 n, const F& f) {
+	if (n == 0) return;
+	const u32 BLOCK = 128;
+	k_for_each_scratch<WORDS, BLOCK, F><<<(n + BLOCK - 1) / BLOCK, BLOCK, 0, ex.stream>>>(n, f);
+	ARB_CUDA_CHECK(cudaGetLastError());
+	++stats().kernels;
+}
 #else
 template <class F> void for_each(const exec_ctx&, u32 n, const F& f) { for (u32 i = 0; i < n; ++i) f(i); ++stats().kernels; }
+template <u32 WORDS, class F> void for_each_scratch(const exec_ctx&, u32 n, const F& f) { u32 scratch[WORDS]; for (u32 i = 0; i < n; ++i) f(i, scratch, 1); ++stats().kernels; }
 #endif
 
 // ------------------------------------------------------------------------------------------- atomics usable from HD functors
@@ -168,6 +183,19 @@ ARB_HD u32 atomic_add_u32(u32* p, u32 v) {
 	return atomicAdd(p, v);
 #else
 	u32 old = *p; *p = old + v; return old;
+#endif
+}
+// next free slot of an append-only list; on the device one atomic per warp (the active lanes take consecutive slots)
+ARB_HD u32 append_slot(u32* counter) {
+#ifdef __CUDA_ARCH__
+	const unsigned active = __activemask();
+	const unsigned lane = threadIdx.x & 31u, leader = (unsigned) __ffs((int) active) - 1u;
+	u32 base = 0;
+	if (lane == leader) base = atomicAdd(counter, (u32) __popc(active));
+	base = __shfl_sync(active, base, (int) leader);
+	return base + (u32) __popc(active & ((1u << lane) - 1u));
+#else
+	return (*counter)++;
 #endif
 }
 ARB_HD u32 atomic_or_u32(u32* p, u32 v) {

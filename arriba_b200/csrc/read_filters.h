@@ -88,6 +88,8 @@ ARB_HD void count_mismatches(const frag_view& f, const annot_view& an, u32 a, co
 	const bool fwd = f.fwd(a);
 	const u64 base = an.contig_seq_off[f.contig[a]];
 	const u32 clen = an.contig_len[f.contig[a]];
+	const u32* g4 = an.assembly4 ? an.assembly4 + base / 8 : 0; // contig offsets are multiples of 64 bases
+	const u32 n_words = ((seq_len + 31) / 32) * 4;               // sequences are stored in 16-byte units
 	i32 ref = f.start[a]; u32 rp = 0;
 	for (u32 k = 0; k < n; ++k) {
 		const u32 op = cig_op(c[k]), len = cig_len(c[k]);
@@ -101,6 +103,29 @@ ARB_HD void count_mismatches(const frag_view& f, const annot_view& an, u32 a, co
 			case C_N: ref += (i32) len; break;
 			case C_I: ++mismatches; rp += len; break;
 			case C_M: case C_EQ: case C_X:
+				if (g4 && ref >= 0 && (u32) ref + len <= clen && rp + len <= seq_len) { // eight bases per step on the packed reference
+					for (u32 j = 0; j < len; j += 8) {
+						const u32 cnt = hd_min(8u, len - j);
+						const u32 valid = 0x11111111u << (4 * (8 - cnt));
+						const u32 r = revcomp ? brev32(nt16_window(seq, n_words, (i32) (seq_len - 1 - (rp + j)) - 7)) : nt16_window(seq, n_words, (i32) (rp + j));
+						if (revcomp) { // bit reversal complements A/C/G/T/N; ambiguity codes stay as they are in the reference (assembly.hpp:9-22): take the slow road
+							const u32 s = (r & 0x55555555u) + (r >> 1 & 0x55555555u), c4 = (s & 0x33333333u) + (s >> 2 & 0x33333333u);
+							if ((c4 >> 1) & ~(c4 >> 2) & valid) {
+								for (u32 t = 0; t < cnt; ++t) {
+									const u32 code = nt16_complement(nt16_at(seq, seq_len - 1 - (rp + j + t)));
+									if (code != NT_N) { if (nt16_char(code) != an.assembly[base + (u32) ref + j + t]) ++mismatches; ++aligned; }
+								}
+								continue;
+							}
+						}
+						const u32 g = packed_window(g4, (u64) (u32) ref + j);
+						const u32 is_n = r & r >> 1 & r >> 2 & r >> 3, ok = valid & ~is_n;
+						const u32 x = r ^ g, differs = x | x >> 1 | x >> 2 | x >> 3;
+						mismatches += popc32(differs & ok); aligned += popc32(ok);
+					}
+					ref += (i32) len; rp += len;
+					break;
+				}
 				for (u32 j = 0; j < len; ++j, ++ref, ++rp) {
 					if (rp >= seq_len) continue; // malformed record: nothing to compare
 					u32 code = revcomp ? nt16_complement(nt16_at(seq, seq_len - 1 - rp)) : nt16_at(seq, rp);
@@ -152,7 +177,9 @@ ARB_HD bool is_itd_shaped(const frag_view& f, u32 i, u32 max_itd_length) {
 	return f.end[s] > f.start[u] && f.end[s] <= f.start[u] + (i32) max_itd_length;
 }
 
-ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content) {
+// `counters`: 64 words (word k at counters[k * stride]), one per 3-mer: occurrences in the whole read (bits 0-9), in the first aligned part (10-19) and in
+// the second (20-29); reads of more than 3,000 bases would overflow the fields.
+ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content, u32* counters, u32 stride) {
 	for (u32 mate = MATE1; mate <= MATE2; ++mate) {
 		const u32 a = f.idx(i, mate);
 		const u32 len = f.seq_len[a];
@@ -173,16 +200,24 @@ ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content) {
 		const u32 max_all = kmer_threshold(len, kmer_content);
 		const u32 max_1 = kmer_threshold(e1 - s1, kmer_content);
 		const u32 max_2 = kmer_threshold(e2 - s2, kmer_content);
-		u8 cnt[64], cnt1[64], cnt2[64]; u16 prev[64];
-		for (u32 k = 0; k < 64; ++k) { cnt[k] = cnt1[k] = cnt2[k] = 0; prev[k] = 0; }
+		for (u32 k = 0; k < 64; ++k) counters[k * stride] = 0;
+		// 2-bit code of a base: T=0 G=1 C=2, anything else 3 (filter_mismappers.cpp:33-45), looked up in a 32-bit constant indexed by the nt16 code
+		const u32 code2 = ~(3u << 16 | 2u << 8 | 1u << 4); // entries 8 (T), 4 (G), 2 (C) hold 0, 1, 2 -- every other entry 3
+		const u32 n_words = ((len + 31) / 32) * 4;
+		u32 word = nt16_word(seq, 0, n_words);
+		u32 km = (code2 >> 2 * (word >> 28) & 3) << 2 | (code2 >> 2 * (word >> 24 & 15) & 3); // bases 0 and 1
+		// a k-mer overlapping a counted occurrence of itself is skipped; with k=3 only the occurrences one and two positions back can overlap
+		u32 km_1 = 64, km_2 = 64; // k-mers COUNTED at pos-1 and pos-2 (64 = none)
 		for (u32 pos = 0; pos + 3 < len; ++pos) { // the last k-mer of the read is never examined (filter_low_entropy.cpp:77)
-			const u32 km = kmer3(seq, pos);
-			if (prev[km] > pos) continue; // overlaps the previous occurrence of the same k-mer
-			prev[km] = (u16) (pos + 3);
-			u32 c0 = ++cnt[km], c1 = cnt1[km], c2 = cnt2[km];
-			if (pos + 1 >= s1 && pos < e1) c1 = ++cnt1[km];
-			if (pos + 1 >= s2 && pos < e2) c2 = ++cnt2[km];
-			if (c0 >= max_all || c1 >= max_1 || c2 >= max_2) return true;
+			const u32 b = pos + 2;
+			if ((b & 7) == 0) word = nt16_word(seq, b >> 3, n_words);
+			km = (km << 2 | (code2 >> 2 * (word >> (28 - 4 * (b & 7)) & 15) & 3)) & 63;
+			if (km == km_1 || km == km_2) { km_2 = km_1; km_1 = 64; continue; }
+			km_2 = km_1; km_1 = km;
+			const u32 in1 = pos + 1 >= s1 && pos < e1, in2 = pos + 1 >= s2 && pos < e2;
+			const u32 w = counters[km * stride] + (1u | in1 << 10 | in2 << 20);
+			counters[km * stride] = w;
+			if ((w & 1023) >= max_all || (w >> 10 & 1023) >= max_1 || (w >> 20) >= max_2) return true;
 		}
 	}
 	return false;
@@ -192,7 +227,9 @@ ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content) {
 // Evaluates rules [uninteresting_contigs .. low_entropy] for fragment i given its current label
 // (F_none or F_duplicates from the duplicate pass). Returns the final label. `early` receives the label the
 // fragment had after the contig rules (what estimate_fragment_length sees, read_stats.cpp:23).
-ARB_HD u8 classify_fragment(const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, u8& early) {
+// The cascade runs as two kernels: classify_head evaluates the rules that look at coordinates, CIGARs and gene sets only; the fragments that are still
+// unlabelled (or ITD-shaped, see below) are queued and classify_sequences evaluates the two rules that read the bases.
+ARB_HD u8 classify_head(const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, u8& early, bool& needs_sequences) {
 	u8 label = f.filter[i];
 	const u32 n = f.n_aln[i];
 	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
@@ -284,6 +321,16 @@ ARB_HD u8 classify_fragment(const read_filter_params& p, const frag_view& f, con
 			}
 		}
 	}
+	// ITD-shaped split reads are examined for low entropy even when an earlier rule (other than duplicates) already discarded them (filter_low_entropy.cpp:17-31)
+	needs_sequences = (label == F_none && (p.enabled(F_mismatches) || p.enabled(F_low_entropy))) ||
+	                  (label != F_none && label != F_duplicates && p.enabled(F_low_entropy) && is_itd_shaped(f, i, p.max_itd_length));
+	return label;
+}
+
+ARB_HD u8 classify_sequences(const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, u32* scratch, u32 stride) {
+	u8 label = f.filter[i];
+	const u32 n = f.n_aln[i];
+	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
 	if (label == F_none && p.enabled(F_mismatches)) {
 		const bool multi = f.fflags[i] & FF_MULTIMAPPER;
 		const u32 y = n == 2 ? a1 : a2;
@@ -296,9 +343,8 @@ ARB_HD u8 classify_fragment(const read_filter_params& p, const frag_view& f, con
 		if (bad) label = F_mismatches;
 	}
 	if (p.enabled(F_low_entropy)) {
-		// ITD-shaped split reads are examined even when an earlier rule (other than duplicates) already discarded them (filter_low_entropy.cpp:17-31)
 		const bool examine = label == F_none || (label != F_duplicates && is_itd_shaped(f, i, p.max_itd_length));
-		if (examine && low_entropy(f, i, p.max_kmer_content)) label = F_low_entropy;
+		if (examine && low_entropy(f, i, p.max_kmer_content, scratch, stride)) label = F_low_entropy;
 	}
 	return label;
 }

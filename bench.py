@@ -205,7 +205,7 @@ def main():
     n_frag = results[0][0]
     dev_ms = sum(r[2] for r in results) / len(results)
     e2e_s = sum(r[1] for r in results) / len(results)
-    cls_ms = sum(r[4].classify_ms for r in results) / len(results)
+    cls_ms = sum(r[4].cascade_head_ms + r[4].cascade_sequences_ms for r in results) / len(results)
     if dist:
         t = torch.tensor([dev_ms, e2e_s, cls_ms, wall], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -225,8 +225,10 @@ def main():
                     "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_for_each<classify_fn> (fused read-level cascade)", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "roofline": {"bound": "hbm", "kernel": "read-level cascade: k_for_each<cascade_head_fn> + k_for_each_scratch<cascade_sequences_fn>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(tm.classify_algorithmic_bytes), "kernel_ms": cls_ms,
+                         "cascade": {"head_ms": tm.cascade_head_ms, "sequences_ms": tm.cascade_sequences_ms, "queued": int(tm.cascade_queued),
+                                     "head_bytes": int(tm.cascade_algorithmic_bytes[0]), "sequences_bytes": int(tm.cascade_algorithmic_bytes[1])},
                          "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
                                        "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
                                        "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},

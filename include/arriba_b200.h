@@ -181,6 +181,9 @@ typedef struct arb_timings {
 	uint64_t kmer_positions;    /* positions in the k-mer index */
 	uint64_t mismapper_heavy_items; /* pairs that exhausted the one-thread budget and were re-aligned cooperatively */
 	float mismappers_pass1_ms, mismappers_pass2_ms;
+	float cascade_head_ms, cascade_sequences_ms; /* the two launches of the read-level cascade (classify_ms spans both) */
+	uint64_t cascade_queued;    /* fragments the sequence rules (mismatches, low entropy) looked at */
+	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 

@@ -37,3 +37,46 @@ def test_read_filters_cuda(worlds, cuda_lib):
 @pytest.mark.gpu
 def test_read_filters_cuda_l151(worlds, cuda_lib):
     check_read_filters(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), cuda_lib)
+
+
+def check_packed_mismatch_counts(world, lib_path):
+    """The eight-bases-per-step comparison on the 4-bit reference must count exactly like the base-by-base walk, also with ambiguity
+    codes in reads and reference, reverse-complemented split reads, N bases and blocks running over the contig end."""
+    import ctypes as C
+    from arriba_b200 import lib
+    rng = np.random.default_rng(5)
+    names, flags, seqs = worldutil.contigs_from_world(world)
+    iupac = np.frombuffer(b"=ACMGRSVTWYHKDBN", np.uint8)
+    seqs2 = []
+    for s in seqs:
+        a = np.frombuffer(s, np.uint8).copy()
+        hit = rng.random(len(a)) < 0.02
+        a[hit] = iupac[rng.integers(0, 16, int(hit.sum()))]
+        seqs2.append(a.tobytes())
+    ch = worldutil.chunk_from_dump(world.stage("annotated"))
+    n = ch["n_fragments"]
+    seq = ch["seq"]
+    hit = rng.random(len(seq)) < 0.05                       # random nibbles: all 16 codes
+    seq[hit] = rng.integers(0, 256, int(hit.sum()), dtype=np.uint8)
+    flip = rng.random(n) < 0.5                              # supplementary on the other strand -> reverse-complemented comparison
+    ch["aflags"][2 * n:][flip] ^= 8
+    shift = rng.random(n) < 0.01                            # a few alignments hanging over the contig start
+    ch["start"][:n][shift] = -3
+    ctx = lib.Context(0, lib_path)
+    ctx.set_contigs(flags, seqs2)
+    ctx.set_annotation(worldutil.annotation_from_dump(world.stage("fragment_length"), len(names)))
+    ctx.push_chunk(ch)
+    out = np.zeros((n, 8), np.uint32)
+    assert ctx.lib.arb_selftest_mismatch_counts(ctx.h, lib.ptr(out)) == 0
+    assert np.array_equal(out[:, :4], out[:, 4:])
+    assert out[:, 1].sum() > 50 * n and (out[:, 0] > 0).mean() > 0.5
+    ctx.close()
+
+
+def test_packed_mismatch_counts_hostsim(worlds, hostsim_lib):
+    check_packed_mismatch_counts(worlds.get("small"), hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_packed_mismatch_counts_cuda(worlds, cuda_lib):
+    check_packed_mismatch_counts(worlds.get("small"), cuda_lib)
