@@ -7,7 +7,12 @@ using namespace arb;
 struct arb_ctx { engine e; };
 static std::string g_create_error;
 
-#define ARB_API_BEGIN(ctx) if (!(ctx)) return 2; try {
+#ifdef ARB_DEVICE_BUILD
+#define ARB_BIND_DEVICE(ctx) ARB_CUDA_CHECK(cudaSetDevice((ctx)->e.device));
+#else
+#define ARB_BIND_DEVICE(ctx)
+#endif
+#define ARB_API_BEGIN(ctx) if (!(ctx)) return 2; try { ARB_BIND_DEVICE(ctx)
 #define ARB_API_END(ctx) } catch (const std::exception& x) { (ctx)->e.last_error = x.what(); return 1; } catch (...) { (ctx)->e.last_error = "unknown error"; return 1; } return 0;
 
 extern "C" {
@@ -38,12 +43,24 @@ int arb_ctx_create(arb_ctx** out, int device) {
 #else
 		(void) device;
 #endif
+#ifdef ARB_DEVICE_BUILD
+		cudaSetDeviceFlags(cudaDeviceLmemResizeToMax); cudaGetLastError(); // keep the local-memory arena of the recursive re-alignment kernels between launches (best effort)
+		ARB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)); // realign() recurses at splice sites and at one deletion (mismap_hd.h)
+#endif
 		*out = new arb_ctx();
+		(*out)->e.device = device;
 	} catch (const std::exception& x) { g_create_error = x.what(); return 1; }
 	return 0;
 }
 
-void arb_ctx_destroy(arb_ctx* ctx) { delete ctx; pool_trim(); }
+void arb_ctx_destroy(arb_ctx* ctx) {
+	if (!ctx) return;
+#ifdef ARB_DEVICE_BUILD
+	cudaSetDevice(ctx->e.device);
+#endif
+	delete ctx; // device blocks go back to the pool, not to the driver: the next context on this device reuses them
+}
+void arb_release_device_memory(void) { pool_trim(); }
 const char* arb_last_error(arb_ctx* ctx) { return ctx ? ctx->e.last_error.c_str() : g_create_error.c_str(); }
 
 void arb_default_params(arb_params* p) { if (p) default_params(*p); }

@@ -112,6 +112,7 @@ public:
 	// k-mer index / re-alignment
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
 	u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
+	int device;
 	int mismap_budget; u32 mismap_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
 	void set_splice_sites(const u32* off, const i32* sites);

@@ -727,27 +727,39 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	// ---- SoA columns ----
 	const u32 n = (u32) order.size();
 	out.n = n;
-	out.n_aln.assign(n, 0); out.fflags.assign(n, 0); out.filter.assign(n, 0);
-	out.contig.assign(3 * (size_t) n, 0); out.start.assign(3 * (size_t) n, 0); out.end.assign(3 * (size_t) n, 0); out.aflags.assign(3 * (size_t) n, 0);
-	out.cigar_off.assign(3 * (size_t) n, 0); out.cigar_cnt.assign(3 * (size_t) n, 0); out.seq_off.assign(3 * (size_t) n, 0); out.seq_len.assign(3 * (size_t) n, 0);
-	out.genes_off.assign(3 * (size_t) n, 0); out.genes_cnt.assign(3 * (size_t) n, 0);
-	out.name_off.assign((size_t) n + 1, 0);
-	// pool offsets: prefix sums over the fragments in name order
-	std::vector<u64> cig_at((size_t) n + 1, 0), seq_at((size_t) n + 1, 0);
-	for (u32 i = 0; i < n; ++i) {
-		const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
-		u64 nc = 0, ns = 0;
-		for (u32 s = 0; s < fb.count; ++s) { const aln_build& a = w.alns[fb.head + s]; nc += a.cigar_cnt; if (s < 2) ns += ((a.seq_len + 1) / 2 + 15) / 16; }
-		cig_at[i + 1] = cig_at[i] + nc; seq_at[i + 1] = seq_at[i] + ns; out.name_off[i + 1] = out.name_off[i] + fb.name_len;
-	}
-	if (cig_at[n] > 0xFFFFFFFFull || seq_at[n] > 0xFFFFFFFFull) fail("chunk too large: more than 2^32 CIGAR operations or 64 GiB of sequence");
-	out.cigar.assign(cig_at[n] + 1, 0); out.seq.assign(seq_at[n] * 16 + 16, 0); out.names.resize(out.name_off[n]);
+	// columns are sized without being touched; each thread zeroes and fills its own range (parallel first touch)
+	out.n_aln.resize(n); out.fflags.resize(n); out.filter.resize(n);
+	out.contig.resize(3 * (size_t) n); out.start.resize(3 * (size_t) n); out.end.resize(3 * (size_t) n); out.aflags.resize(3 * (size_t) n);
+	out.cigar_off.resize(3 * (size_t) n); out.cigar_cnt.resize(3 * (size_t) n); out.seq_off.resize(3 * (size_t) n); out.seq_len.resize(3 * (size_t) n);
+	out.genes_off.resize(3 * (size_t) n); out.genes_cnt.resize(3 * (size_t) n);
+	out.name_off.resize((size_t) n + 1);
+	// pool offsets: prefix sums over the fragments in name order (sizes in parallel, scan serial over contiguous arrays)
+	column<u64> cig_at((size_t) n + 1), seq_at((size_t) n + 1);
+	cig_at[0] = seq_at[0] = 0; out.name_off[0] = 0;
 	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
 			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
-			out.n_aln[i] = (u8) fb.count; out.fflags[i] = (fb.single_end ? FF_SINGLE_END : 0) | (fb.duplicate ? FF_DUPLICATE : 0);
+			u64 nc = 0, ns = 0;
+			for (u32 s = 0; s < fb.count; ++s) { const aln_build& a = w.alns[fb.head + s]; nc += a.cigar_cnt; if (s < 2) ns += ((a.seq_len + 1) / 2 + 15) / 16; }
+			cig_at[i + 1] = nc; seq_at[i + 1] = ns; out.name_off[i + 1] = fb.name_len;
+		}
+	});
+	for (u32 i = 0; i < n; ++i) { cig_at[i + 1] += cig_at[i]; seq_at[i + 1] += seq_at[i]; out.name_off[i + 1] += out.name_off[i]; }
+	if (cig_at[n] > 0xFFFFFFFFull || seq_at[n] > 0xFFFFFFFFull) fail("chunk too large: more than 2^32 CIGAR operations or 64 GiB of sequence");
+	out.cigar.resize(cig_at[n] + 1); out.seq.resize(seq_at[n] * 16 + 16); out.names.resize(out.name_off[n]);
+	out.cigar[cig_at[n]] = 0; memset(&out.seq[seq_at[n] * 16], 0, 16);
+	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
+		for (size_t i = lo; i < hi; ++i) {
+			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
+			out.n_aln[i] = (u8) fb.count; out.fflags[i] = (fb.single_end ? FF_SINGLE_END : 0) | (fb.duplicate ? FF_DUPLICATE : 0); out.filter[i] = 0;
 			memcpy(&out.names[out.name_off[i]], w.names.data() + fb.name_off, fb.name_len);
 			u64 c = cig_at[i], sq = seq_at[i];
+			if (seq_at[i + 1] > sq) memset(&out.seq[sq * 16], 0, (seq_at[i + 1] - sq) * 16); // padding of the 16-byte units
+			for (u32 s = fb.count; s < 3; ++s) { // unused slot
+				const size_t x = (size_t) s * n + i;
+				out.contig[x] = 0; out.start[x] = 0; out.end[x] = 0; out.aflags[x] = 0; out.cigar_off[x] = 0; out.cigar_cnt[x] = 0; out.seq_off[x] = 0; out.seq_len[x] = 0;
+			}
+			for (u32 s = 0; s < 3; ++s) { const size_t x = (size_t) s * n + i; out.genes_off[x] = 0; out.genes_cnt[x] = 0; if (s == 2) { out.seq_off[x] = 0; out.seq_len[x] = 0; } }
 			for (u32 s = 0; s < fb.count; ++s) {
 				const aln_build& a = w.alns[fb.head + s];
 				const size_t x = (size_t) s * n + i;
@@ -774,6 +786,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	}
 	stats.t_finalize = now_s() - tf;
 	lap("multimapper flags");
+	parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) { worker empty; std::swap(workers[t], empty); } }); // unmap the per-worker pools concurrently
 	{ std::vector<worker>().swap(workers); }
 	lap("free worker state");
 }

@@ -6,6 +6,9 @@
 #pragma once
 #include <string>
 #include <vector>
+#include <memory>
+#include <utility>
+#include <new>
 #include "refdata.h"
 
 namespace arb { namespace host {
@@ -19,14 +22,24 @@ struct coverage_windows { // 20 bp windows (read_stats.hpp:14)
 	int get_coverage(u32 contig, i32 position, u32 direction) const;
 };
 
+// vector whose resize() leaves new elements uninitialised: the large columns are first touched (and zeroed) by the threads that fill them
+template <class T> struct default_init_allocator: std::allocator<T> {
+	template <class U> struct rebind { typedef default_init_allocator<U> other; };
+	default_init_allocator() {}
+	template <class U> default_init_allocator(const default_init_allocator<U>&) {}
+	template <class U> void construct(U* p) { ::new ((void*) p) U; }
+	template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*) p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+};
+template <class T> using column = std::vector<T, default_init_allocator<T> >;
+
 struct fragment_table { // host image of arb_soa_chunk + names
 	u32 n;
-	std::vector<u8> n_aln, fflags, filter, aflags;
-	std::vector<u16> contig, cigar_cnt, seq_len, genes_cnt;
-	std::vector<i32> start, end;
-	std::vector<u32> cigar_off, seq_off, genes_off, cigar, genes;
-	std::vector<u8> seq;
-	std::vector<char> names; std::vector<u64> name_off; // "<qname>,<HI>[ITD]" per fragment, name order
+	column<u8> n_aln, fflags, filter, aflags;
+	column<u16> contig, cigar_cnt, seq_len, genes_cnt;
+	column<i32> start, end;
+	column<u32> cigar_off, seq_off, genes_off, cigar, genes;
+	column<u8> seq;
+	column<char> names; column<u64> name_off; // "<qname>,<HI>[ITD]" per fragment, name order
 	fragment_table(): n(0) {}
 	frag_view view();
 	std::string name(u32 i) const { return std::string(names.data() + name_off[i], names.data() + name_off[i + 1]); }

@@ -81,9 +81,6 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	if (!has_splice_sites) throw arb_error("arb_filter_mismappers: arb_set_splice_sites must be called first");
 	const u32 C = cands.n, N = frags.n;
 	if (C == 0) return 0;
-#ifdef ARB_DEVICE_BUILD
-	ARB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, 16 * 1024)); // realign() recurses at splice sites and at one deletion
-#endif
 	stage_timer t_all(ex);
 	dbuf<u32> item_off((size_t) C + 1);
 	item_count_fn ic = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list2_off.ptr(), cands.listd_off.ptr(), item_off.ptr()};

@@ -53,16 +53,32 @@ struct kmer_emit_fn { // key = contig << 16 | 8-mer
 };
 struct bucket_count_fn { const u32* key; u32* count; ARB_HD void operator()(u32 j) const { atomic_add_u32(&count[key[j]], 1); } };
 
-// ---- sequences to re-align: a slice of a stored read, optionally reverse-complemented, or a stretch of the reference
-struct read_slice {
-	const u8* nt16; u32 off; u32 len; bool rc;
-	ARB_HD char at(u32 i) const { return rc ? complement_char(nt16_char(nt16_at(nt16, off + len - 1 - i))) : nt16_char(nt16_at(nt16, off + i)); }
-};
-ARB_HD u32 kmer8(const read_slice& s, u32 p) { u32 k = 0; for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(s.at(p + b)); return k; }
-
-struct gene_window { u32 contig; i32 start, end; const i32* splice; u32 n_splice; }; // [start, end] = gene +- padding; downstream splice sites of the gene
+// ---- sequences to re-align: a slice of a stored read, optionally reverse-complemented
+struct read_slice { const u8* nt16; u32 off; u32 len; bool rc; };
 
 ARB_HD u32 lower_bound_i32(const i32* v, u32 lo, u32 hi, i32 x) { while (lo < hi) { u32 mid = lo + ((hi - lo) >> 1); if (v[mid] < x) lo = mid + 1; else hi = mid; } return lo; }
+
+// complement of an nt16 code the way the reference complements characters (A<->T, C<->G, everything else unchanged; assembly.hpp:9-22)
+ARB_HD u32 nt16_comp(u32 code) { return (u32) (0xFEDCBA9176523480ull >> (4 * code)) & 15u; }
+// 2-bit code of a base for the 8-mer index: T=0 G=1 C=2, anything else 3 (filter_mismappers.cpp:33-45); table indexed by the nt16 code
+ARB_HD u32 nt16_base2(u32 code) { return 0xFFFCFDEFu >> (2 * code) & 3u; }
+
+// Everything one re-alignment keeps fixed across its recursion levels. realign() copies what it needs into registers on entry.
+struct realign_env {
+	const u8* seq; u32 off, len; bool rc;        // the read slice
+	const i32* pos; const u32* bucket;           // k-mer hits and the 65,536 bucket offsets of the window's contig
+	const i32* splice; u32 n_splice;             // downstream splice sites of the gene
+	i32 wstart, wend;                            // gene +- padding
+	int min_score;
+	const u32* g4; const char* ref;              // reference of the contig: packed nt16 codes, or characters when g4 == 0
+};
+ARB_HD u32 env_code(const u8* seq, u32 off, u32 len, bool rc, u32 r) { // nt16 code of base r of the (possibly reverse-complemented) slice
+	const u32 code = nt16_at(seq, rc ? off + len - 1 - r : off + r);
+	return rc ? nt16_comp(code) : code;
+}
+ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
+	return g4 ? (g4[(u32) g >> 3] >> (28 - 4 * ((u32) g & 7)) & 15u) == code : ref[g] == nt16_char(code);
+}
 
 // Work control of one re-alignment. The reference's align() is a pure "does ANY placement reach min_score" search: the outcome is the OR over all
 // (read position, k-mer hit) pairs and over the recursive continuations, so the pairs may be visited in any order and by any number of threads.
@@ -73,63 +89,87 @@ struct realign_ctl {
 	int budget; bool limited;
 	u32 lanes, lane, counter;
 	const volatile u8* stop;
-	ARB_HD bool spend() { return limited && --budget < 0; }
 	ARB_HD bool exhausted() const { return limited && budget < 0; }
 };
 ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; return c; }
 
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
-ARB_HD_RECURSIVE bool realign(int score, const read_slice& rs, int read_pos, const char* ref, int gene_pos, const gene_window& w, const kmer_index_view& ix, int min_score, int max_deletions, realign_ctl& ctl, bool top) {
-	const int len = (int) rs.len;
+ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_deletions, const realign_env& env, realign_ctl& ctl, bool top) {
+	const u8* const seq = env.seq; const u32 off = env.off; const bool rc = env.rc; const int len = (int) env.len;
+	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
+	const i32 wstart = env.wstart, wend = env.wend; const int min_score = env.min_score;
+	const u32* const g4 = env.g4; const char* const ref = env.ref;
+	const bool limited = ctl.limited;
+	int budget = ctl.budget; // spent locally, written back on every way out
+	#define REALIGN_RETURN(x) do { ctl.budget = budget; return (x); } while (0)
+	if (!(read_pos + 8 < len && read_pos + min_score <= len + score + 16)) return false;
+	u32 km = 0;
+	for (u32 b = 0; b < 8; ++b) km = km << 2 | nt16_base2(env_code(seq, off, (u32) len, rc, (u32) read_pos + b));
 	int skipped = 0;
-	for (; read_pos + 8 < len && read_pos + min_score <= len + score + 16; ++read_pos, --score, ++skipped) {
-		u32 lo, hi; ix.bucket(w.contig, kmer8(rs, (u32) read_pos), lo, hi);
-		if (lo == hi) continue;
-		u32 h = lower_bound_i32(ix.pos, lo, hi, gene_pos), step = 1;
-		if (top && ctl.lanes > 1) { // deal this position's hits to the lanes, continuing the round-robin of the previous positions
-			if (ctl.stop && *ctl.stop) return false;
-			const u32 n_hits = lower_bound_i32(ix.pos, h, hi, w.end) - h;
-			h += (ctl.lane + ctl.lanes - ctl.counter % ctl.lanes) % ctl.lanes; step = ctl.lanes;
-			ctl.counter += n_hits;
-		}
-		for (; h < hi && ix.pos[h] < w.end; h += step) {
-			if (ctl.spend()) return false;
-			const int hit = ix.pos[h];
-			ARB_COST(1);
-			int ext = score + 8;
+	for (;;) {
+		const u32 lo = bucket[km], hi = bucket[km + 1];
+		if (lo != hi) {
+			u32 h = lower_bound_i32(pos, lo, hi, gene_pos), step = 1;
+			if (top && ctl.lanes > 1) { // deal this position's hits to the lanes, continuing the round-robin of the previous positions
+				if (ctl.stop && *ctl.stop) REALIGN_RETURN(false);
+				const u32 n_hits = lower_bound_i32(pos, h, hi, wend) - h;
+				h += (ctl.lane + ctl.lanes - ctl.counter % ctl.lanes) % ctl.lanes; step = ctl.lanes;
+				ctl.counter += n_hits;
+			}
 			const bool leading = read_pos == skipped; // every base so far was skipped: no penalty for them (local alignment start)
-			if (leading) ext += skipped;
-			if (ext >= min_score) return true;
-			{ // extend to the left over the skipped bases, one mismatch allowed
-				int r = read_pos - 1, g = hit - 1; u32 mm = 0;
-				while (r >= read_pos - skipped && g >= w.start) {
-					if (rs.at((u32) r) == ref[g]) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
-					else if (++mm > 1) break;
-					--r; --g;
+			for (; h < hi; h += step) {
+				const int hit = pos[h];
+				if (hit >= wend) break;
+				if (limited && --budget < 0) REALIGN_RETURN(false);
+				ARB_COST(1);
+				int ext = score + 8;
+				if (leading) ext += skipped;
+				if (ext >= min_score) REALIGN_RETURN(true);
+				{ // extend to the left over the skipped bases, one mismatch allowed
+					int r = read_pos - 1, g = hit - 1; u32 mm = 0;
+					while (r >= read_pos - skipped && g >= wstart) {
+						if (env_ref_equals(g4, ref, g, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) REALIGN_RETURN(true); }
+						else if (++mm > 1) break;
+						--r; --g;
+					}
 				}
-			}
-			{ // extend to the right; try a spliced continuation at splice sites and one deletion at the first mismatch
-				int r = read_pos + 8, g = hit + 8; u32 mm = 0, consecutive = 0;
-				u32 ss = lower_bound_i32(w.splice, 0, w.n_splice, g - 1);
-				while (r < len && g <= w.end) {
-					ARB_COST(1);
-					if (ctl.spend()) return false;
-					if (ss < w.n_splice) {
-						if (g - 1 > w.splice[ss]) ++ss;
-						if (ss < w.n_splice && g - 1 == w.splice[ss] && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions, ctl, false)) return true;
+				{ // extend to the right; try a spliced continuation at splice sites and one deletion at the first mismatch
+					int r = read_pos + 8, g = hit + 8; u32 mm = 0, consecutive = 0;
+					u32 ss = lower_bound_i32(env.splice, 0, env.n_splice, g - 1);
+					i32 next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff;
+					while (r < len && g <= wend) {
+						ARB_COST(1);
+						if (limited && --budget < 0) REALIGN_RETURN(false);
+						if (g - 1 >= next_site) {
+							if (g - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
+							if (g - 1 == next_site) {
+								ctl.budget = budget;
+								if (realign(ext, r, g, max_deletions, env, ctl, false)) return true;
+								budget = ctl.budget;
+							}
+						}
+						if (env_ref_equals(g4, ref, g, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) REALIGN_RETURN(true); consecutive = 0; }
+						else {
+							if (++mm == 1 && max_deletions > 0 && len >= 30) {
+								ctl.budget = budget;
+								if (realign(ext, r, g, max_deletions - 1, env, ctl, false)) return true;
+								budget = ctl.budget;
+							}
+							--ext;
+							if (++consecutive >= 4) break;
+						}
+						++r; ++g;
 					}
-					if (rs.at((u32) r) == ref[g]) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
-					else {
-						if (++mm == 1 && max_deletions > 0 && len >= 30 && realign(ext, rs, r, ref, g, w, ix, min_score, max_deletions - 1, ctl, false)) return true;
-						--ext;
-						if (++consecutive >= 4) break;
-					}
-					++r; ++g;
 				}
 			}
 		}
+		// next read position
+		if (!(read_pos + 9 < len && read_pos + 1 + min_score <= len + score - 1 + 16)) break;
+		km = (km << 2 | nt16_base2(env_code(seq, off, (u32) len, rc, (u32) read_pos + 8))) & 0xffffu;
+		++read_pos; --score; ++skipped;
 	}
-	return false;
+	REALIGN_RETURN(false);
+	#undef REALIGN_RETURN
 }
 
 struct gene_splice_view { const u32* off; const i32* sites; }; // per gene: sorted downstream splice sites (filter_mismappers.cpp:16-31)
@@ -146,16 +186,20 @@ ARB_HD bool realign_both_strands(const read_slice& fwd, int read_length, int max
 #endif
 	for (u32 k = 0; k < n_genes; ++k) {
 		const u32 g = genes[k];
-		gene_window w; w.contig = an.gene_contig[g];
-		w.start = hd_max(an.gene_start[g] - max_mate_gap - read_length, 0);
-		w.end = hd_min(an.gene_end[g] + max_mate_gap + read_length, (i32) an.contig_len[w.contig] - 1);
-		if (same_contig && ((aln_start >= w.start && aln_start <= w.end) || (aln_end >= w.start && aln_end <= w.end))) continue;
-		if (w.contig >= ix.n_index_contigs) continue;
-		w.splice = sp.sites + sp.off[g]; w.n_splice = sp.off[g + 1] - sp.off[g];
-		const char* ref = an.assembly + an.contig_seq_off[w.contig];
-		if (realign(0, fwd, 0, ref, w.start, w, ix, min_score, 1, ctl, true)) return true;
-		read_slice rev = fwd; rev.rc = !fwd.rc;
-		if (realign(0, rev, 0, ref, w.start, w, ix, min_score, 1, ctl, true)) return true;
+		const u32 contig = an.gene_contig[g];
+		realign_env env;
+		env.wstart = hd_max(an.gene_start[g] - max_mate_gap - read_length, 0);
+		env.wend = hd_min(an.gene_end[g] + max_mate_gap + read_length, (i32) an.contig_len[contig] - 1);
+		if (same_contig && ((aln_start >= env.wstart && aln_start <= env.wend) || (aln_end >= env.wstart && aln_end <= env.wend))) continue;
+		if (contig >= ix.n_index_contigs) continue;
+		env.seq = fwd.nt16; env.off = fwd.off; env.len = fwd.len; env.rc = fwd.rc;
+		env.pos = ix.pos; env.bucket = ix.bucket_off + (u64) contig * 65536;
+		env.splice = sp.sites + sp.off[g]; env.n_splice = sp.off[g + 1] - sp.off[g];
+		env.min_score = min_score;
+		env.g4 = an.assembly4 ? an.assembly4 + an.contig_seq_off[contig] / 8 : 0; env.ref = an.assembly + an.contig_seq_off[contig];
+		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
+		env.rc = !fwd.rc;
+		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
 	}
 	return false;
 }

@@ -12,6 +12,8 @@
 #include <stdexcept>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <algorithm>
 #include <algorithm>
 
 #ifdef ARB_DEVICE_BUILD
@@ -41,27 +43,40 @@ struct exec_ctx {
 };
 
 // ------------------------------------------------------------------------------------------- device memory pool
-// Stage-local scratch buffers come and go many times per run; cudaMalloc/cudaFree would serialise the stream each time
-// (cudaFree synchronises the device). Freed blocks are kept in size classes and reused; everything is returned to the driver
-// by pool_trim() (context destruction).
+// Stage-local scratch buffers come and go many times per run; cudaMalloc/cudaFree would serialise the stream each time (cudaFree synchronises the
+// device, cudaMalloc costs up to a millisecond). Blocks are carved out of large slabs, one list of free blocks per size class (steps of at most 25 %),
+// per device; slabs go back to the driver only through pool_trim() (arb_release_device_memory) or when an allocation fails.
 #ifdef ARB_DEVICE_BUILD
 struct device_pool {
-	std::vector<std::pair<size_t, void*> > free_blocks;
-	size_t held_bytes;
-	device_pool(): held_bytes(0) {}
+	struct slab { char* base; size_t size, used; };
+	struct per_device { std::vector<std::pair<size_t, void*> > free_blocks; std::vector<slab> slabs; size_t outstanding; per_device(): outstanding(0) {} };
+	std::vector<per_device> dev; std::mutex lock;
 	static size_t size_class(size_t bytes) { size_t c = 512; while (c < bytes) c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); return c; }
+	per_device& current() { int d = 0; ARB_CUDA_CHECK(cudaGetDevice(&d)); if ((size_t) d >= dev.size()) dev.resize((size_t) d + 1); return dev[(size_t) d]; }
 	void* get(size_t bytes, size_t& granted) {
+		std::lock_guard<std::mutex> g(lock);
+		per_device& d = current();
 		granted = size_class(bytes);
-		for (size_t k = 0; k < free_blocks.size(); ++k) if (free_blocks[k].first == granted) {
-			void* p = free_blocks[k].second; free_blocks[k] = free_blocks.back(); free_blocks.pop_back(); held_bytes -= granted; return p;
+		++d.outstanding;
+		for (size_t k = d.free_blocks.size(); k-- > 0; ) if (d.free_blocks[k].first == granted) {
+			void* p = d.free_blocks[k].second; d.free_blocks[k] = d.free_blocks.back(); d.free_blocks.pop_back(); return p;
 		}
-		void* p = NULL;
-		cudaError_t e = cudaMalloc(&p, granted);
-		if (e != cudaSuccess) { trim(); ARB_CUDA_CHECK(cudaMalloc(&p, granted)); }
-		return p;
+		for (size_t k = d.slabs.size(); k-- > 0; ) if (d.slabs[k].size - d.slabs[k].used >= granted) { void* p = d.slabs[k].base + d.slabs[k].used; d.slabs[k].used += granted; return p; }
+		slab s; s.size = std::max<size_t>(granted, (size_t) 512 << 20); s.used = granted; s.base = NULL;
+		cudaError_t e = cudaMalloc((void**) &s.base, s.size);
+		if (e != cudaSuccess) { cudaGetLastError(); s.size = granted; e = cudaMalloc((void**) &s.base, s.size); }
+		if (e != cudaSuccess) { --d.outstanding; cudaGetLastError(); throw arb_error(std::string("out of device memory (") + cudaGetErrorString(e) + ")"); }
+		d.slabs.push_back(s);
+		return s.base;
 	}
-	void put(void* p, size_t granted) { free_blocks.push_back(std::make_pair(granted, p)); held_bytes += granted; }
-	void trim() { for (size_t k = 0; k < free_blocks.size(); ++k) cudaFree(free_blocks[k].second); free_blocks.clear(); held_bytes = 0; }
+	void put(void* p, size_t granted) { std::lock_guard<std::mutex> g(lock); per_device& d = current(); d.free_blocks.push_back(std::make_pair(granted, p)); --d.outstanding; }
+	void trim() { // only when nothing is handed out on the current device (blocks point into the slabs)
+		std::lock_guard<std::mutex> g(lock);
+		per_device& d = current();
+		if (d.outstanding != 0) return;
+		for (size_t k = 0; k < d.slabs.size(); ++k) cudaFree(d.slabs[k].base);
+		d.slabs.clear(); d.free_blocks.clear();
+	}
 };
 inline device_pool& pool() { static device_pool p; return p; }
 inline void pool_trim() { pool().trim(); }

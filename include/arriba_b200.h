@@ -186,6 +186,9 @@ typedef struct arb_timings {
 	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
+/* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver
+ * (no-op while a context on the current device still holds blocks). */
+void arb_release_device_memory(void);
 
 /* ---- whole-run driver ---------------------------------------------------------------------------------------
  * What the `arriba` executable does (source/arriba.cpp:79-631): reference + annotation loading, BAM ingest
