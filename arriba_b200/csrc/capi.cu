@@ -93,6 +93,9 @@ int arb_homolog_pairs(arb_ctx* ctx, const uint32_t* ga, const uint32_t* gb, uint
 int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.filter_mismappers(max_mate_gap); if (n) *n = k; ARB_API_END(ctx) }
 int arb_get_timings(arb_ctx* ctx, arb_timings* out) { ARB_API_BEGIN(ctx) *out = ctx->e.timings; ARB_API_END(ctx) }
 int arb_selftest_mismatch_counts(arb_ctx* ctx, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.probe_mismatch_counts(out); ARB_API_END(ctx) } // tests only, not declared in the public header
+int arb_set_candidates(arb_ctx* ctx, const arb_candidates* c) { ARB_API_BEGIN(ctx) if (!c) throw arb_error("null table"); ctx->e.set_candidates(*c); ARB_API_END(ctx) }
+int arb_apply_slot_swaps(arb_ctx* ctx, const uint8_t* swapped) { ARB_API_BEGIN(ctx) ctx->e.apply_slot_swaps(swapped); ARB_API_END(ctx) }
+int arb_get_candidate_first_fragments(arb_ctx* ctx, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.get_first_fragments(out); ARB_API_END(ctx) }
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.get_slot_swaps(out); ARB_API_END(ctx) }
 
 } // extern "C"

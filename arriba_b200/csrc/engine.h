@@ -72,6 +72,7 @@ struct cand_store {
 	u32 n; u64 n_list1, n_list2, n_listd;
 	dbuf<u32> gene1, gene2, split_reads1, split_reads2, discordant_mates, list1_off, list2_off, listd_off, list1, list2, listd;
 	dbuf<u16> contig1, contig2; dbuf<i32> bp1, bp2, anchor1, anchor2; dbuf<u8> dir1, dir2, filter, bits, bits2; dbuf<float> evalue;
+	dbuf<u32> first_frag; // fragment whose record created the candidate (merge key of the sharded run)
 	cand_store(): n(0), n_list1(0), n_list2(0), n_listd(0) {}
 };
 
@@ -113,13 +114,14 @@ public:
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
 	u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
 	int device;
-	int mismap_budget; u32 mismap_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
+	int mismap_budget, mismap_spawn_budget; u32 mismap_lanes, mismap_task_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
 	void set_splice_sites(const u32* off, const i32* sites);
 	u64 build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs);
 	void kmer_index_digest(u64* kmers, u64* positions, u64* checksum, u32 n_contigs);
 	void homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out);
 	u64 filter_mismappers(i32 max_mate_gap);
+	void set_candidates(const arb_candidates& c); void apply_slot_swaps(const u8* swapped); void get_first_fragments(u32* out);
 	void probe_mismatch_counts(u32* out); // test hook (arb_selftest_mismatch_counts)
 private:
 	read_filter_params make_filter_params();

@@ -44,6 +44,10 @@ void engine::find_fusions(i32 max_mate_gap) {
 	segment_offsets_fn so = {cand_of.ptr(), seg_off.ptr(), R, C};
 	for_each(ex, R, so);
 
+	cands.first_frag.ensure(C);
+	first_fragment_fn ff = {r.frag, perm.ptr(), seg_off.ptr(), cands.first_frag.ptr()};
+	for_each(ex, C, ff);
+
 	// 4. pass A
 	cands.n = C;
 	cands.gene1.ensure(C); cands.gene2.ensure(C); cands.contig1.ensure(C); cands.contig2.ensure(C); cands.bp1.ensure(C); cands.bp2.ensure(C);
@@ -128,5 +132,33 @@ void engine::get_candidates(arb_candidates& o) {
 }
 
 void engine::get_slot_swaps(u8* out) { frags.swapped.download(ex, out, frags.n); }
+void engine::get_first_fragments(u32* out) { cands.first_frag.download(ex, out, cands.n); }
+
+// installs a candidate table produced elsewhere (the merged shards of a multi-GPU run) in place of find_fusions' product
+void engine::set_candidates(const arb_candidates& c) {
+	const u32 C = c.n;
+	cands.n = C;
+	cands.gene1.upload(ex, c.gene1, C); cands.gene2.upload(ex, c.gene2, C); cands.contig1.upload(ex, c.contig1, C); cands.contig2.upload(ex, c.contig2, C);
+	cands.bp1.upload(ex, c.breakpoint1, C); cands.bp2.upload(ex, c.breakpoint2, C); cands.dir1.upload(ex, c.direction1, C); cands.dir2.upload(ex, c.direction2, C);
+	cands.split_reads1.upload(ex, c.split_reads1, C); cands.split_reads2.upload(ex, c.split_reads2, C); cands.discordant_mates.upload(ex, c.discordant_mates, C);
+	cands.filter.upload(ex, c.filter, C); cands.bits.upload(ex, c.bits, C); cands.bits2.upload(ex, c.bits2, C);
+	cands.anchor1.upload(ex, c.anchor_start1, C); cands.anchor2.upload(ex, c.anchor_start2, C); cands.evalue.upload(ex, c.evalue, C);
+	cands.list1_off.upload(ex, c.list1_off, (size_t) C + 1); cands.list2_off.upload(ex, c.list2_off, (size_t) C + 1); cands.listd_off.upload(ex, c.listd_off, (size_t) C + 1);
+	cands.n_list1 = c.list1_off[C]; cands.n_list2 = c.list2_off[C]; cands.n_listd = c.listd_off[C];
+	cands.list1.upload(ex, c.list1, cands.n_list1); cands.list2.upload(ex, c.list2, cands.n_list2); cands.listd.upload(ex, c.listd, cands.n_listd);
+	cands.first_frag.ensure(C); cands.first_frag.zero(ex, C);
+	ex.sync();
+}
+
+// exchanges MATE1/MATE2 of the flagged fragments, as find_fusions does for listed discordant mates (fusions.cpp:414-421)
+void engine::apply_slot_swaps(const u8* swapped) {
+	const u32 n = frags.n;
+	std::vector<u32> need(n);
+	for (u32 i = 0; i < n; ++i) need[i] = swapped[i] ? 1u : 0u;
+	dbuf<u32> need_swap; need_swap.upload(ex, need.data(), n);
+	swap_mates_fn sm = {frags.view(), need_swap.ptr(), frags.swapped.ptr()};
+	for_each(ex, n, sm);
+	ex.sync();
+}
 
 } // namespace arb

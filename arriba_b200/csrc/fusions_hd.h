@@ -219,6 +219,8 @@ struct walk_b_fn {
 	}
 };
 
+struct first_fragment_fn { const u32* rec_frag; const u32* perm; const u32* seg_off; u32* out; ARB_HD void operator()(u32 c) const { out[c] = rec_frag[perm[seg_off[c]]]; } };
+
 // exchange slots 0 and 1 of flagged fragments (all per-alignment columns)
 struct swap_mates_fn {
 	frag_view f; const u32* need_swap; u8* swapped;

@@ -77,6 +77,7 @@ void pipeline::upload() {
 	const double t0 = now_s();
 	if (!ctx) { if (arb_ctx_create(&ctx, opt.device) != 0) throw std::runtime_error(arb_last_error(NULL)); }
 	check(ctx, arb_set_params(ctx, &opt.params), "arb_set_params");
+	if (!reference_on_device) {
 	const u32 nc = (u32) ref.contig_ids.size();
 	std::vector<const char*> seqs(nc, (const char*) NULL);
 	for (u32 c = 0; c < nc; ++c) if (ref.has_sequence(c)) seqs[c] = ref.sequence(c);
@@ -91,6 +92,9 @@ void pipeline::upload() {
 	a.exon_region_begin = ref.exon_index.begin.data(); a.exon_region_end = ref.exon_index.end.data(); a.exon_region_off = ref.exon_index.off.data(); a.exon_region_items = ref.exon_index.items.data();
 	a.gene_region_begin = ref.gene_index.begin.data(); a.gene_region_end = ref.gene_index.end.data(); a.gene_region_off = ref.gene_index.off.data(); a.gene_region_items = ref.gene_index.items.data();
 	check(ctx, arb_set_annotation(ctx, &a), "arb_set_annotation");
+	reference_on_device = true;
+	}
+	fragment_table& frags = shard_world > 1 ? local : this->frags; // a sharded run uploads its own part only
 	arb_soa_chunk c;
 	c.n_fragments = frags.n; c.n_aln = frags.n_aln.data(); c.fflags = frags.fflags.data(); c.filter = frags.filter.data();
 	c.contig = frags.contig.data(); c.start = frags.start.data(); c.end = frags.end.data(); c.aflags = frags.aflags.data();
@@ -98,6 +102,7 @@ void pipeline::upload() {
 	c.genes_off = frags.genes_off.data(); c.genes_cnt = frags.genes_cnt.data();
 	c.cigar = frags.cigar.data(); c.n_cigar = frags.cigar.size(); c.seq = frags.seq.data(); c.n_seq_bytes = frags.seq.size(); c.genes = frags.genes.data(); c.n_genes = frags.genes.size();
 	check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+	frags_on_device = true;
 	t_upload = now_s() - t0;
 }
 
@@ -106,11 +111,21 @@ void pipeline::upload() {
 void pipeline::read_filters() {
 	const double t0 = now_s();
 	check(ctx, arb_run_read_filters(ctx), "arb_run_read_filters");
-	labels.resize(frags.n); early.resize(frags.n);
-	check(ctx, arb_get_fragment_filters(ctx, labels.data(), early.data()), "arb_get_fragment_filters");
+	if (shard_world > 1) { // labels of the shard only; the global picture arrives with the label exchange (shard.cpp)
+		local_labels.resize(local.n); local_early.resize(local.n);
+		check(ctx, arb_get_fragment_filters(ctx, local_labels.data(), local_early.data()), "arb_get_fragment_filters");
+	} else {
+		labels.resize(frags.n); early.resize(frags.n);
+		check(ctx, arb_get_fragment_filters(ctx, labels.data(), early.data()), "arb_get_fragment_filters");
+		say_read_filter_counts();
+	}
+	t_read_filters = now_s() - t0;
+}
+
+void pipeline::say_read_filter_counts() {
 	// `(remaining=N)` of every stage follows from the label histogram, because the first hit wins and the order is fixed (arriba.cpp:327-409)
-	uint32_t counts[ARB_N_FILTERS];
-	check(ctx, arb_get_filter_counts(ctx, counts), "arb_get_filter_counts");
+	u64 counts[ARB_N_FILTERS]; for (int k = 0; k < ARB_N_FILTERS; ++k) counts[k] = 0;
+	for (size_t i = 0; i < labels.size(); ++i) ++counts[labels[i] < ARB_N_FILTERS ? labels[i] : 0];
 	static const int order[] = {F_duplicates, F_uninteresting_contigs, F_viral_contigs, F_top_expressed_viral_contigs, F_low_coverage_viral_contigs, F_read_through,
 		F_inconsistently_clipped, F_homopolymer, F_small_insert_size, F_long_gap, F_same_gene, F_hairpin, F_mismatches};
 	u64 remaining = frags.n;
@@ -119,7 +134,6 @@ void pipeline::read_filters() {
 	for (size_t k = 0; k < sizeof(order) / sizeof(order[0]); ++k) if (opt.params.filter_mask >> order[k] & 1) { remaining -= counts[order[k]]; s << "Filtering " << FILTER_NAMES[order[k]] << " (remaining=" << remaining << ")\n"; }
 	s << "Filtering reads with low entropy (remaining=" << counts[F_none] << ")";
 	say(s.str());
-	t_read_filters = now_s() - t0;
 }
 
 void pipeline::fragment_length() {

@@ -35,7 +35,7 @@ struct pipeline {
 	std::string log; // the reference's progress lines (arriba.cpp:61-66 style, without time stamps)
 	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
-	pipeline(): splice_sites_ready(false), events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
+	pipeline(): shard_rank(0), shard_world(1), frags_on_device(false), reference_on_device(false), splice_sites_ready(false), events_done(-1), ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -58,6 +58,13 @@ struct pipeline {
 	void events_until(int last_stage); // runs the event-level chain up to and including `last_stage` (EV_* below)
 	int events_done;
 	void run_all();
+	// one sample on several GPUs (shard.cpp): fragments partitioned by contig pair, two exchanges (labels, candidates) carried by the caller
+	int shard_rank, shard_world; std::vector<std::vector<u32> > shard_members; fragment_table local; std::vector<u8> local_labels, local_early, export_blob;
+	bool frags_on_device, reference_on_device;
+	void set_shard(int rank, int world);
+	void export_shard(int what, const void** blob, u64* bytes);
+	void import_shards(int what, const void* const* blobs, const u64* bytes, u32 n_blobs);
+	void say_read_filter_counts();
 };
 
 enum { EV_FETCH = 0, EV_MERGE_ADJACENT, EV_MULTIMAPPERS, EV_EVALUE, EV_NON_CODING_NEIGHBORS, EV_INTRAGENIC_EXONIC, EV_MIN_SUPPORT, EV_RELATIVE_SUPPORT,

@@ -85,13 +85,25 @@ ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
 //  * budget: the one-thread-per-item pass gives up after `budget` steps (a few reads that fall into tandem repeats cost 10^5 times the median);
 //  * lanes/lane/counter: the cooperative pass deals the top-level hits round-robin to `lanes` threads of the same item;
 //  * stop: set as soon as any lane (or any other item of the same fragment) found a placement.
+//  * spawn: in the cooperative passes a continuation (the recursive call at a splice site or at the first mismatch) gets `spawn_budget` steps; one that
+//    runs out undecided is written to `queue` as a task of its own and the caller goes on as if it had failed -- the next round deals the task's own
+//    hits to a group of lanes. A read stuck in a tandem repeat has thousands of hits per position on both recursion levels.
+struct realign_task { u32 item; u16 gene_k; u8 segment, rc; i32 score, read_pos, gene_pos, max_deletions; };
 struct realign_ctl {
 	int budget; bool limited;
 	u32 lanes, lane, counter;
 	const volatile u8* stop;
+	int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap; realign_task proto; // proto: item / segment / gene / strand of the running alignment
 	ARB_HD bool exhausted() const { return limited && budget < 0; }
+	ARB_HD bool spawn(int score, int read_pos, int gene_pos, int max_deletions) {
+		const u32 slot = atomic_add_u32(n_queue, 1);
+		if (slot >= queue_cap) return false; // queue full: the caller runs the continuation itself
+		realign_task t = proto; t.score = score; t.read_pos = read_pos; t.gene_pos = gene_pos; t.max_deletions = max_deletions;
+		queue[slot] = t;
+		return true;
+	}
 };
-ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; return c; }
+ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.queue = 0; c.n_queue = 0; c.queue_cap = 0; return c; }
 
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
 ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_deletions, const realign_env& env, realign_ctl& ctl, bool top) {
@@ -102,6 +114,18 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 	const bool limited = ctl.limited;
 	int budget = ctl.budget; // spent locally, written back on every way out
 	#define REALIGN_RETURN(x) do { ctl.budget = budget; return (x); } while (0)
+	#define REALIGN_CONTINUATION(sc, rp, gp, md) { \
+		if (top && ctl.spawn_budget > 0) { /* bounded attempt; undecided -> a task for the next round */ \
+			const bool was_limited = ctl.limited; ctl.limited = true; ctl.budget = ctl.spawn_budget; \
+			bool found = realign(sc, rp, gp, md, env, ctl, false); \
+			const bool ran_out = ctl.budget < 0; ctl.limited = was_limited; \
+			if (!found && ran_out && !ctl.spawn(sc, rp, gp, md)) { ctl.budget = 0; found = realign(sc, rp, gp, md, env, ctl, false); } \
+			if (found) return true; \
+		} else { \
+			ctl.budget = budget; \
+			if (realign(sc, rp, gp, md, env, ctl, false)) return true; \
+			budget = ctl.budget; \
+		} }
 	if (!(read_pos + 8 < len && read_pos + min_score <= len + score + 16)) return false;
 	u32 km = 0;
 	for (u32 b = 0; b < 8; ++b) km = km << 2 | nt16_base2(env_code(seq, off, (u32) len, rc, (u32) read_pos + b));
@@ -142,19 +166,11 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 						if (limited && --budget < 0) REALIGN_RETURN(false);
 						if (g - 1 >= next_site) {
 							if (g - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
-							if (g - 1 == next_site) {
-								ctl.budget = budget;
-								if (realign(ext, r, g, max_deletions, env, ctl, false)) return true;
-								budget = ctl.budget;
-							}
+							if (g - 1 == next_site) REALIGN_CONTINUATION(ext, r, g, max_deletions)
 						}
 						if (env_ref_equals(g4, ref, g, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) REALIGN_RETURN(true); consecutive = 0; }
 						else {
-							if (++mm == 1 && max_deletions > 0 && len >= 30) {
-								ctl.budget = budget;
-								if (realign(ext, r, g, max_deletions - 1, env, ctl, false)) return true;
-								budget = ctl.budget;
-							}
+							if (++mm == 1 && max_deletions > 0 && len >= 30) REALIGN_CONTINUATION(ext, r, g, max_deletions - 1)
 							--ext;
 							if (++consecutive >= 4) break;
 						}
@@ -169,36 +185,48 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 		++read_pos; --score; ++skipped;
 	}
 	REALIGN_RETURN(false);
+	#undef REALIGN_CONTINUATION
 	#undef REALIGN_RETURN
 }
 
 struct gene_splice_view { const u32* off; const i32* sites; }; // per gene: sorted downstream splice sites (filter_mismappers.cpp:16-31)
 
-// filter_mismappers.cpp:189-230; `genes` = gene set of the OTHER segment
-ARB_HD bool realign_both_strands(const read_slice& fwd, int read_length, int max_mate_gap, bool same_contig, i32 aln_start, i32 aln_end, const u32* genes, u32 n_genes,
-                                 const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, float min_align_fraction, realign_ctl& ctl) {
-	if (fwd.len >= 300) return false;
+// One of the two sequences of a work item that is re-aligned against the genes of the OTHER breakpoint (filter_mismappers.cpp:189-230, :296-333)
+struct realign_segment {
+	read_slice read; int read_length; bool same_contig; i32 aln_start, aln_end; const u32* genes; u32 n_genes; float min_align_fraction;
+	ARB_HD int min_score() const {
 #ifdef __CUDA_ARCH__
-	const int min_score = (int) ((double) __fmul_rn(min_align_fraction, (float) fwd.len) + 0.5);
+		return (int) ((double) __fmul_rn(min_align_fraction, (float) read.len) + 0.5);
 #else
-	volatile float prod = min_align_fraction * (float) fwd.len;
-	const int min_score = (int) ((double) prod + 0.5);
+		volatile float prod = min_align_fraction * (float) read.len;
+		return (int) ((double) prod + 0.5);
 #endif
-	for (u32 k = 0; k < n_genes; ++k) {
-		const u32 g = genes[k];
-		const u32 contig = an.gene_contig[g];
+	}
+};
+// window, index and splice sites of gene k of the segment; false if the reference skips this gene (:204-214)
+ARB_HD bool segment_env(const realign_segment& s, u32 k, int max_mate_gap, const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, realign_env& env) {
+	const u32 g = s.genes[k];
+	const u32 contig = an.gene_contig[g];
+	env.wstart = hd_max(an.gene_start[g] - max_mate_gap - s.read_length, 0);
+	env.wend = hd_min(an.gene_end[g] + max_mate_gap + s.read_length, (i32) an.contig_len[contig] - 1);
+	if (s.same_contig && ((s.aln_start >= env.wstart && s.aln_start <= env.wend) || (s.aln_end >= env.wstart && s.aln_end <= env.wend))) return false;
+	if (contig >= ix.n_index_contigs) return false;
+	env.seq = s.read.nt16; env.off = s.read.off; env.len = s.read.len; env.rc = s.read.rc;
+	env.pos = ix.pos; env.bucket = ix.bucket_off + (u64) contig * 65536;
+	env.splice = sp.sites + sp.off[g]; env.n_splice = sp.off[g + 1] - sp.off[g];
+	env.min_score = s.min_score();
+	env.g4 = an.assembly4 ? an.assembly4 + an.contig_seq_off[contig] / 8 : 0; env.ref = an.assembly + an.contig_seq_off[contig];
+	return true;
+}
+ARB_HD bool realign_both_strands(const realign_segment& s, u32 segment, int max_mate_gap, const annot_view& an, const kmer_index_view& ix, const gene_splice_view& sp, realign_ctl& ctl) {
+	if (s.read.len >= 300) return false;
+	for (u32 k = 0; k < s.n_genes; ++k) {
 		realign_env env;
-		env.wstart = hd_max(an.gene_start[g] - max_mate_gap - read_length, 0);
-		env.wend = hd_min(an.gene_end[g] + max_mate_gap + read_length, (i32) an.contig_len[contig] - 1);
-		if (same_contig && ((aln_start >= env.wstart && aln_start <= env.wend) || (aln_end >= env.wstart && aln_end <= env.wend))) continue;
-		if (contig >= ix.n_index_contigs) continue;
-		env.seq = fwd.nt16; env.off = fwd.off; env.len = fwd.len; env.rc = fwd.rc;
-		env.pos = ix.pos; env.bucket = ix.bucket_off + (u64) contig * 65536;
-		env.splice = sp.sites + sp.off[g]; env.n_splice = sp.off[g + 1] - sp.off[g];
-		env.min_score = min_score;
-		env.g4 = an.assembly4 ? an.assembly4 + an.contig_seq_off[contig] / 8 : 0; env.ref = an.assembly + an.contig_seq_off[contig];
+		if (!segment_env(s, k, max_mate_gap, an, ix, sp, env)) continue;
+		ctl.proto.segment = (u8) segment; ctl.proto.gene_k = (u16) k;
+		ctl.proto.rc = 0;
 		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
-		env.rc = !fwd.rc;
+		env.rc = !s.read.rc; ctl.proto.rc = 1;
 		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
 	}
 	return false;
@@ -238,27 +266,40 @@ struct mismap_items {
 	const u32* item_cand; const u32* item_frag; const u8* item_kind /* 0 split read, 1 discordant */; const u16* cand_contig1; const u16* cand_contig2; const u8* cand_filter;
 	u8* mismapper; // per fragment, set to 1 when any evaluation says "mis-mapped"
 	ARB_HD bool skip(u32 j) const { return cand_filter[item_cand[j]] != F_none || f.filter[item_frag[j]] != F_none; }
-	ARB_HD bool evaluate(u32 j, realign_ctl& ctl, bool with_linear_extension) const {
+	// segment 0 / 1 of item j: split read -> clipped part vs. the genes of the split read's anchor side, then mate1 (+ aligned part) vs. the genes of the
+	// supplementary; discordant mates -> each mate vs. the genes of the other (filter_mismappers.cpp:296-333)
+	ARB_HD realign_segment segment(u32 j, u32 x) const {
 		const u32 cand = item_cand[j], i = item_frag[j];
-		const bool same_contig = cand_contig1[cand] == cand_contig2[cand];
+		realign_segment s;
+		s.same_contig = cand_contig1[cand] == cand_contig2[cand];
+		s.read.rc = false;
 		if (item_kind[j] == 0) {
-			const u32 m = f.idx(i, MATE1), s = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
-			const u32 slen = f.seq_len[s], mlen = f.seq_len[m];
-			read_slice clipped, anchor;
-			clipped.nt16 = f.sq(s); clipped.rc = false; anchor.nt16 = f.sq(m); anchor.rc = false;
-			if (f.fwd(s)) { clipped.off = 0; clipped.len = hd_min(f.preclip(s), slen); const u32 pre = hd_min(f.preclip(m), mlen); anchor.off = pre; anchor.len = mlen - pre; }
-			else { const u32 post = hd_min(f.postclip(s), slen); clipped.off = slen - post; clipped.len = post; const u32 mpost = hd_min(f.postclip(m), mlen); anchor.off = 0; anchor.len = mlen - mpost; }
-			return (with_linear_extension && extends_linearly(f, an, s)) ||
-			       realign_both_strands(clipped, (int) slen, p.max_mate_gap, same_contig, f.start[u], f.end[u], f.genes + f.genes_off[s], f.genes_cnt[s], an, ix, sp, 0.8f, ctl) ||
-			       realign_both_strands(anchor, (int) mlen, p.max_mate_gap, same_contig, f.start[m], f.end[m], f.genes + f.genes_off[u], f.genes_cnt[u], an, ix, sp, 0.8f, ctl);
+			const u32 m = f.idx(i, MATE1), sr = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
+			const u32 slen = f.seq_len[sr], mlen = f.seq_len[m];
+			s.min_align_fraction = 0.8f;
+			if (x == 0) {
+				s.read.nt16 = f.sq(sr);
+				if (f.fwd(sr)) { s.read.off = 0; s.read.len = hd_min(f.preclip(sr), slen); } else { const u32 post = hd_min(f.postclip(sr), slen); s.read.off = slen - post; s.read.len = post; }
+				s.read_length = (int) slen; s.aln_start = f.start[u]; s.aln_end = f.end[u]; s.genes = f.genes + f.genes_off[sr]; s.n_genes = f.genes_cnt[sr];
+			} else {
+				s.read.nt16 = f.sq(m);
+				if (f.fwd(sr)) { const u32 pre = hd_min(f.preclip(m), mlen); s.read.off = pre; s.read.len = mlen - pre; } else { const u32 mpost = hd_min(f.postclip(m), mlen); s.read.off = 0; s.read.len = mlen - mpost; }
+				s.read_length = (int) mlen; s.aln_start = f.start[m]; s.aln_end = f.end[m]; s.genes = f.genes + f.genes_off[u]; s.n_genes = f.genes_cnt[u];
+			}
 		} else {
-			const u32 a = f.idx(i, MATE1), b = f.idx(i, MATE2);
-			const float cf1 = ((float) f.preclip(a) + f.postclip(a)) / f.seq_len[a], cf2 = ((float) f.preclip(b) + f.postclip(b)) / f.seq_len[b];
-			const float fr1 = hd_min(0.8f, 0.8f * (1 - cf1)), fr2 = hd_min(0.8f, 0.8f * (1 - cf2));
-			read_slice ra = {f.sq(a), 0, f.seq_len[a], false}, rb = {f.sq(b), 0, f.seq_len[b], false};
-			return realign_both_strands(ra, (int) f.seq_len[a], p.max_mate_gap, same_contig, f.start[a], f.end[a], f.genes + f.genes_off[b], f.genes_cnt[b], an, ix, sp, fr1, ctl) ||
-			       realign_both_strands(rb, (int) f.seq_len[b], p.max_mate_gap, same_contig, f.start[b], f.end[b], f.genes + f.genes_off[a], f.genes_cnt[a], an, ix, sp, fr2, ctl);
+			const u32 a = f.idx(i, x == 0 ? MATE1 : MATE2), b = f.idx(i, x == 0 ? MATE2 : MATE1);
+			const float clipped = ((float) f.preclip(a) + f.postclip(a)) / f.seq_len[a];
+			s.min_align_fraction = hd_min(0.8f, 0.8f * (1 - clipped));
+			s.read.nt16 = f.sq(a); s.read.off = 0; s.read.len = f.seq_len[a];
+			s.read_length = (int) f.seq_len[a]; s.aln_start = f.start[a]; s.aln_end = f.end[a]; s.genes = f.genes + f.genes_off[b]; s.n_genes = f.genes_cnt[b];
 		}
+		return s;
+	}
+	ARB_HD bool evaluate(u32 j, realign_ctl& ctl, bool with_linear_extension) const {
+		ctl.proto.item = j;
+		if (with_linear_extension && item_kind[j] == 0 && extends_linearly(f, an, f.idx(item_frag[j], SPLIT_READ))) return true;
+		for (u32 x = 0; x < 2; ++x) if (realign_both_strands(segment(j, x), x, p.max_mate_gap, an, ix, sp, ctl)) return true;
+		return false;
 	}
 };
 
@@ -278,16 +319,36 @@ struct mismap_item_fn {
 #endif
 	}
 };
-// pass 2: `lanes` threads per queued item share the top-level k-mer hits
+// pass 2: `lanes` threads per queued item share the top-level k-mer hits; continuations that are expensive themselves become tasks
 struct mismap_heavy_fn {
-	mismap_items it; const u32* heavy; u32 lanes;
+	mismap_items it; const u32* heavy; u32 lanes; int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap;
 	ARB_HD void operator()(u32 t) const {
 		const u32 j = heavy[t / lanes], i = it.item_frag[j];
 		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
+		ctl.spawn_budget = spawn_budget; ctl.queue = queue; ctl.n_queue = n_queue; ctl.queue_cap = queue_cap;
 		if (*ctl.stop) return;
 		if (it.evaluate(j, ctl, false)) it.mismapper[i] = 1;
 #ifdef ARB_COST_PROBE
 		fprintf(stderr, "HEAVY %u %u %llu\n", j, ctl.lane, arb_cost_probe); arb_cost_probe = 0;
+#endif
+	}
+};
+// task rounds: `lanes` threads per queued continuation; what they cannot finish goes to the queue of the next round
+struct mismap_task_fn {
+	mismap_items it; const realign_task* tasks; u32 lanes; int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap;
+	ARB_HD void operator()(u32 t) const {
+		const realign_task task = tasks[t / lanes];
+		const u32 i = it.item_frag[task.item];
+		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
+		ctl.spawn_budget = spawn_budget; ctl.queue = queue; ctl.n_queue = n_queue; ctl.queue_cap = queue_cap; ctl.proto = task;
+		if (*ctl.stop) return;
+		const realign_segment s = it.segment(task.item, task.segment);
+		realign_env env;
+		if (!segment_env(s, task.gene_k, it.p.max_mate_gap, it.an, it.ix, it.sp, env)) return;
+		if (task.rc) env.rc = !s.read.rc;
+		if (realign(task.score, task.read_pos, task.gene_pos, task.max_deletions, env, ctl, true)) it.mismapper[i] = 1;
+#ifdef ARB_COST_PROBE
+		fprintf(stderr, "TASK %u %u %llu\n", t / lanes, ctl.lane, arb_cost_probe); arb_cost_probe = 0;
 #endif
 	}
 };

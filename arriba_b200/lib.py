@@ -64,7 +64,7 @@ class Timings(C.Structure):
                 ("classify_algorithmic_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("h2d_ms", C.c_float),
                 ("merge_adjacent_ms", C.c_float), ("evalue_ms", C.c_float), ("kmer_index_ms", C.c_float), ("homologs_ms", C.c_float), ("mismappers_ms", C.c_float),
                 ("mismapper_items", C.c_uint64), ("kmer_positions", C.c_uint64), ("mismapper_heavy_items", C.c_uint64),
-                ("mismappers_pass1_ms", C.c_float), ("mismappers_pass2_ms", C.c_float),
+                ("mismappers_pass1_ms", C.c_float), ("mismappers_pass2_ms", C.c_float), ("mismapper_tasks", C.c_uint64), ("mismapper_rounds", C.c_uint32),
                 ("cascade_head_ms", C.c_float), ("cascade_sequences_ms", C.c_float), ("cascade_queued", C.c_uint64), ("cascade_algorithmic_bytes", C.c_uint64 * 2)]
 
 
@@ -257,6 +257,7 @@ class Context:
 STEP_LOAD_REFERENCE, STEP_INGEST, STEP_ANNOTATE, STEP_UPLOAD, STEP_READ_FILTERS, STEP_FRAGMENT_LENGTH, STEP_FIND_FUSIONS, STEP_COUNT = range(8)
 EV_NAMES = ["fetch", "merge_adjacent", "multimappers", "evalue", "non_coding_neighbors", "intragenic_exonic", "min_support", "relative_support", "internal_tandem_duplication",
             "intronic", "in_vitro", "spliced", "select_best", "marginal_read_through", "many_spliced", "short_anchor", "end_to_end", "no_coverage", "kmer_index", "homologs", "mismappers", "select_best2", "isoforms", "confidence"]
+EXCHANGE_LABELS, EXCHANGE_CANDIDATES = 0, 1
 STEP_NAMES = ["load_reference", "ingest", "annotate", "upload", "read_filters", "fragment_length", "find_fusions"]
 
 
@@ -294,6 +295,10 @@ def _load_pipeline_api(lib):
     lib.arb_pipeline_events.argtypes = [C.c_void_p, C.c_int]
     lib.arb_pipeline_write_output.argtypes = [C.c_void_p]
     lib.arb_pipeline_candidates.argtypes = [C.c_void_p, _p(Candidates), _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8))]
+    lib.arb_pipeline_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.arb_pipeline_shard_members.argtypes = [C.c_void_p, C.c_int, _p(_p(C.c_uint32)), _p(C.c_uint64)]
+    lib.arb_pipeline_export_shard.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64)]
+    lib.arb_pipeline_import_shards.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64), C.c_uint32]
     lib._pipeline_ready = True
 
 
@@ -345,6 +350,26 @@ class Pipeline:
     def run(self, upto=STEP_COUNT - 1):
         for s in range(upto + 1):
             self.step(s)
+
+    # ---- one sample on several GPUs (include/arriba_b200.h, "One sample on several GPUs"); the transport is the caller's, see sharded.py
+    def set_shard(self, rank, world):
+        self._check(self.lib.arb_pipeline_set_shard(self.h, rank, world))
+
+    def shard_members(self, rank):
+        m = _p(C.c_uint32)(); n = C.c_uint64()
+        self._check(self.lib.arb_pipeline_shard_members(self.h, rank, C.byref(m), C.byref(n)))
+        return _np_from(m, int(n.value), np.uint32)
+
+    def export_shard(self, what):
+        blob = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.arb_pipeline_export_shard(self.h, what, C.byref(blob), C.byref(n)))
+        return np.ctypeslib.as_array(C.cast(blob, _p(C.c_uint8)), shape=(int(n.value),)).copy()
+
+    def import_shards(self, what, blobs):
+        blobs = [np.ascontiguousarray(b, np.uint8) for b in blobs]
+        ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
+        sizes = (C.c_uint64 * len(blobs))(*[b.size for b in blobs])
+        self._check(self.lib.arb_pipeline_import_shards(self.h, what, ptrs, sizes, len(blobs)))
 
     def stats(self):
         s = RunStats()

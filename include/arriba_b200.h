@@ -129,6 +129,11 @@ typedef struct arb_candidates {
 int arb_find_fusions(arb_ctx* ctx, int32_t max_mate_gap);
 int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n_list1, uint64_t* n_list2, uint64_t* n_listd);
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out /* caller-allocated to arb_candidates_size */);
+/* Multi-GPU runs shard the fragments by contig pair: every rank finds the candidates of its shard, the tables are exchanged
+ * and merged by (first fragment, local id) -- the order the reference would have inserted them -- and installed with arb_set_candidates. */
+int arb_get_candidate_first_fragments(arb_ctx* ctx, uint32_t* first_fragment_out /* n candidates: fragment that created the candidate */);
+int arb_set_candidates(arb_ctx* ctx, const arb_candidates* table); /* replaces the resident candidate table */
+int arb_apply_slot_swaps(arb_ctx* ctx, const uint8_t* swapped /* n fragments */); /* canonical mate order of another rank's find_fusions */
 int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if MATE1/MATE2 were canonicalised (fusions.cpp:416-421) */);
 
 /* ---- event-level stages on the candidate table ------------------------------------------------------------------
@@ -181,6 +186,7 @@ typedef struct arb_timings {
 	uint64_t kmer_positions;    /* positions in the k-mer index */
 	uint64_t mismapper_heavy_items; /* pairs that exhausted the one-thread budget and were re-aligned cooperatively */
 	float mismappers_pass1_ms, mismappers_pass2_ms;
+	uint64_t mismapper_tasks; uint32_t mismapper_rounds; /* continuations re-aligned as tasks of their own, and the rounds that took */
 	float cascade_head_ms, cascade_sequences_ms; /* the two launches of the read-level cascade (classify_ms spans both) */
 	uint64_t cascade_queued;    /* fragments the sequence rules (mismatches, low entropy) looked at */
 	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */
@@ -240,6 +246,16 @@ int arb_pipeline_create(arb_pipeline** out, const arb_run_options* options);
 void arb_pipeline_destroy(arb_pipeline* p);
 const char* arb_pipeline_error(arb_pipeline* p);   /* p may be NULL: error of arb_pipeline_create */
 int arb_pipeline_step(arb_pipeline* p, int step);  /* steps must be run in order */
+/* One sample on several GPUs (arriba_b200/csrc/host/shard.cpp). Every rank ingests the BAM, then keeps the fragments of the contig
+ * pairs assigned to it (arb_pipeline_set_shard, before ARB_STEP_UPLOAD). Two exchanges follow, carried by the caller (e.g. NCCL all-gather of byte buffers):
+ *   after ARB_STEP_READ_FILTERS:  export ARB_EXCHANGE_LABELS, all-gather, import    (fragment-length estimation needs all labels in name order)
+ *   after ARB_STEP_FIND_FUSIONS:  export ARB_EXCHANGE_CANDIDATES, all-gather, import (merges the tables; the rank then holds the complete state)
+ * After the second import every rank continues exactly like a single-GPU run; outputs are byte-identical for any world size. */
+enum { ARB_EXCHANGE_LABELS = 0, ARB_EXCHANGE_CANDIDATES = 1 };
+int arb_pipeline_set_shard(arb_pipeline* p, int rank, int world);
+int arb_pipeline_shard_members(arb_pipeline* p, int rank, const uint32_t** fragments, uint64_t* n); /* name ranks assigned to `rank`, ascending (any rank may ask) */
+int arb_pipeline_export_shard(arb_pipeline* p, int what, const void** blob, uint64_t* bytes); /* blob stays valid until the next export */
+int arb_pipeline_import_shards(arb_pipeline* p, int what, const void* const* blobs, const uint64_t* bytes, uint32_t n_blobs /* = world, rank order */);
 int arb_pipeline_run(arb_pipeline* p);             /* all steps */
 arb_ctx* arb_pipeline_ctx(arb_pipeline* p);        /* device context (valid after ARB_STEP_UPLOAD) */
 int arb_pipeline_stats(arb_pipeline* p, arb_run_stats* out);

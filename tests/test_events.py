@@ -80,9 +80,11 @@ def test_events_hostsim_mismapper_heavy(worlds, hostsim_lib):
 def test_events_hostsim_cooperative_realignment(worlds, hostsim_lib, monkeypatch):
     """A tiny step budget pushes almost every (candidate, read) pair through the cooperative second pass; labels must not change."""
     monkeypatch.setenv("ARB_MISMAP_BUDGET", "24"); monkeypatch.setenv("ARB_MISMAP_LANES", "7")
+    monkeypatch.setenv("ARB_MISMAP_SPAWN", "6"); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", "3")
     p = check_events(worlds.get("cfg5", **CFG5), hostsim_lib, keep=True)
     tm = p.context().timings(); p.close()
     assert tm.mismapper_heavy_items > 0.2 * tm.mismapper_items
+    assert tm.mismapper_tasks > 1000 and tm.mismapper_rounds >= 2   # continuations of continuations were queued as well
 
 
 @pytest.mark.gpu
@@ -91,9 +93,10 @@ def test_events_cuda_mismapper_heavy(worlds, cuda_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("budget,lanes", [("16", "32"), ("200", "256"), ("0", "1")])
-def test_events_cuda_cooperative_realignment(worlds, cuda_lib, monkeypatch, budget, lanes):
+@pytest.mark.parametrize("budget,lanes,spawn,task_lanes", [("16", "32", "4", "32"), ("200", "256", "0", "1"), ("0", "1", "0", "1"), ("64", "8", "16", "5")])
+def test_events_cuda_cooperative_realignment(worlds, cuda_lib, monkeypatch, budget, lanes, spawn, task_lanes):
     monkeypatch.setenv("ARB_MISMAP_BUDGET", budget); monkeypatch.setenv("ARB_MISMAP_LANES", lanes)
+    monkeypatch.setenv("ARB_MISMAP_SPAWN", spawn); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", task_lanes)
     check_events(worlds.get("cfg5", **CFG5), cuda_lib)
 
 
