@@ -19,6 +19,7 @@
 namespace arb { namespace host {
 
 namespace {
+static thread_local std::string* warning_sink = NULL; // set by the formatting threads of writer::write
 
 typedef std::map<i32, std::map<std::string, unsigned int> > pileup_t;
 
@@ -302,7 +303,8 @@ struct writer {
 				if (codon.size() == 3) {
 					protein[pos] = translate(codon); codon.clear();
 					if (!reported && pos < E.cds_end && pos > E.cds_start && protein[pos] == '*') {
-						std::cerr << "WARNING: encountered early stop codon in transcript " << ref.transcripts[E.transcript].name << " at amino acid " << protein.size() << " (error in GTF file?) => predicted peptide sequence may be wrong" << std::endl;
+						std::ostringstream w; w << "WARNING: encountered early stop codon in transcript " << ref.transcripts[E.transcript].name << " at amino acid " << protein.size() << " (error in GTF file?) => predicted peptide sequence may be wrong\n";
+						if (warning_sink) *warning_sink += w.str(); else std::cerr << w.str();
 						reported = true;
 					}
 				}
@@ -535,15 +537,16 @@ struct writer {
 		out << "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n";
 		// rows are independent: format slices of the row list on the host threads, then write the slices in order
 		const int T = std::max(1, std::min(p.threads, (int) (rows.size() / 64 + 1)));
-		std::vector<std::string> slices(T); std::vector<std::string> errors(T);
+		std::vector<std::string> slices(T), warnings(T); std::vector<std::string> errors(T);
 		std::vector<std::thread> pool;
 		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+			warning_sink = &warnings[t]; // warnings of a slice are printed after it, in row order like the reference's
 			try { std::ostringstream os; for (size_t x = rows.size() * t / T; x < rows.size() * (t + 1) / T; ++x) format_row(os, rows[x], extra_info); slices[t] = os.str(); }
 			catch (const std::exception& ex) { errors[t] = ex.what(); }
 		});
 		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
-		for (int t = 0; t < T; ++t) out.write(slices[t].data(), slices[t].size());
+		for (int t = 0; t < T; ++t) { out.write(slices[t].data(), slices[t].size()); if (!warnings[t].empty()) std::cerr << warnings[t] << std::flush; }
 		out.close();
 		if (out.bad()) throw std::runtime_error("failed to write to file");
 	}

@@ -26,9 +26,11 @@ def all_gather_bytes(blob):
     return [host[r * longest:r * longest + sizes[r]] for r in range(world)]
 
 
-def run_sharded(pipeline, rank, world, last_event=None, write_output=True, gather=all_gather_bytes):
+def run_sharded(pipeline, rank, world, last_event=None, write_output=True, gather=all_gather_bytes, reference_loaded=False):
     """Runs `pipeline` (an arriba_b200.lib.Pipeline) as rank `rank` of `world`; every rank ends with the complete result, rank 0 writes the files."""
     for s in (L.STEP_LOAD_REFERENCE, L.STEP_INGEST, L.STEP_ANNOTATE):
+        if s == L.STEP_LOAD_REFERENCE and reference_loaded:
+            continue
         pipeline.step(s)
     pipeline.set_shard(rank, world)
     pipeline.step(L.STEP_UPLOAD)

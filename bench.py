@@ -119,6 +119,9 @@ def main():
     ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
     ap.add_argument("--sample-breakpoints", type=int, default=0, help="cpu baseline sample size in breakpoints (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded-extra", action="store_true", help="N>1, mode samples: skip the additional one-sample-over-all-ranks step")
+    ap.add_argument("--mode", choices=["samples", "sharded"], default="samples",
+                    help="N>1: 'samples' = one independent sample per GPU (weak scaling, no collective); 'sharded' = ONE sample partitioned by contig pair with two NCCL all-gathers (strong scaling)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -165,18 +168,25 @@ def main():
         dist.barrier()
     prefix = ensure_world(args.workload)
 
-    def one_step():
-        """ingest .. find_fusions through the public Pipeline API; returns (fragments, e2e seconds, device ms, stats, timings, d2h bytes)"""
+    def one_step(sharded=False):
+        """ingest .. fusions.tsv through the public Pipeline API; returns (fragments, e2e seconds, device ms, stats, timings, d2h bytes)"""
         outdir = os.path.join(world_dir(args.workload), "out_rank%d" % rank); os.makedirs(outdir, exist_ok=True)
         p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank,
                        output=os.path.join(outdir, "fusions.tsv"), discarded=os.path.join(outdir, "fusions.discarded.tsv"))
         p.step(L.STEP_LOAD_REFERENCE)          # genome + annotation: loaded once per run in a real deployment, outside the timed region
-        t0 = time.perf_counter()
-        for s in range(L.STEP_INGEST, L.STEP_COUNT):
-            p.step(s)
-        p.events(len(L.EV_NAMES) - 1)          # event-level chain incl. the device stages and the D2H of the candidate table
-        p.write_output()
-        e2e_s = time.perf_counter() - t0
+        if sharded:
+            from arriba_b200 import sharded as S
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            S.run_sharded(p, rank, world, reference_loaded=True)   # two NCCL all-gathers inside; rank 0 writes the files
+            e2e_s = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            for s in range(L.STEP_INGEST, L.STEP_COUNT):
+                p.step(s)
+            p.events(len(L.EV_NAMES) - 1)          # event-level chain incl. the device stages and the D2H of the candidate table
+            p.write_output()
+            e2e_s = time.perf_counter() - t0
         ctx = p.context()
         st = p.stats(); tm = ctx.timings()
         n_cand = int(st.n_candidates)
@@ -186,20 +196,29 @@ def main():
         p.close()
         return res
 
+    sharded = args.mode == "sharded" and world > 1
+    if sharded:
+        config["sharding"] = "ONE sample, fragments partitioned by contig pair over the ranks (LPT), two NCCL all-gathers (labels, candidates); every rank decodes the BAM"
     launches0 = L.load().arb_kernel_launches()
     for _ in range(args.warmup):
-        one_step()
+        one_step(sharded)
     if dist:
         dist.barrier()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank); sampler.start()
     launches1 = L.load().arb_kernel_launches()
     t_begin = time.perf_counter()
-    results = [one_step() for _ in range(args.steps)]
+    results = [one_step(sharded) for _ in range(args.steps)]
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
     wall = time.perf_counter() - t_begin
+    extra_sharded = None
+    if dist and not sharded and not args.no_sharded_extra:   # the same sample once more as ONE job over all ranks: exercises the two all-gathers
+        r = one_step(True)
+        t = torch.tensor([r[1]], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extra_sharded = {"e2e_seconds": float(t[0]), "e2e_value": r[0] / float(t[0]), "unit": "fragments/s", "scaling": "strong",
+                         "note": "one sample partitioned by contig pair over all ranks, 2 NCCL all-gathers; host decode is replicated, so this mode buys device memory and device time, not host time"}
     sampler.stop_flag = True; sampler.join(timeout=2)
     launches = L.load().arb_kernel_launches() - launches1
     n_frag = results[0][0]
@@ -217,10 +236,11 @@ def main():
     st, tm = results[-1][3], results[-1][4]
     peak, peak_src = measured_peak()
     achieved = tm.classify_algorithmic_bytes / (cls_ms * 1e-3) / 1e9
-    line = {"metric": metric, "value": n_frag * world / (dev_ms * 1e-3), "unit": "fragments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+    jobs = 1 if sharded else world
+    line = {"metric": metric, "value": n_frag * jobs / (dev_ms * 1e-3), "unit": "fragments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": n_frag * world / e2e_s, "unit": "fragments/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
+            "e2e": {"value": n_frag * jobs / e2e_s, "unit": "fragments/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
                     "seconds_per_step": e2e_s, "host_seconds": {n: round(st.seconds[i], 3) for i, n in enumerate(L.STEP_NAMES) if i > 0},
                     "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
@@ -234,6 +254,8 @@ def main():
                                        "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},
                          "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "kmer_positions": int(tm.kmer_positions)},
             "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
+    if extra_sharded:
+        line["sharded_single_sample"] = extra_sharded
     if not args.no_cpu_baseline:
         sp = ensure_world(args.workload, sample_bp)
         n, scope_s, total = reference_run(sp, cores)
