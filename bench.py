@@ -193,6 +193,10 @@ def main():
         d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
         dev_ms = tm.read_filters_ms + tm.find_fusions_ms + tm.merge_adjacent_ms + tm.evalue_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms
         res = (int(st.n_fragments), e2e_s, dev_ms, st, tm, d2h, n_cand)
+        if rank == 0:   # progress on stderr: a run that is cut off still says where the time went
+            ev = {n: round(st.event_seconds[i], 2) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.5}
+            print("[bench] step: e2e %.2f s, device %.1f ms, ingest %.2f, annotate %.2f, upload %.2f, output %.2f, events >= 0.5 s: %s" %
+                  (e2e_s, dev_ms, st.seconds[L.STEP_INGEST], st.seconds[L.STEP_ANNOTATE], st.seconds[L.STEP_UPLOAD], st.output_seconds, ev), file=sys.stderr, flush=True)
         p.close()
         return res
 
@@ -252,7 +256,7 @@ def main():
                          "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
                                        "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
                                        "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},
-                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "kmer_positions": int(tm.kmer_positions)},
+                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "mismapper_tasks": int(tm.mismapper_tasks), "mismapper_rounds": int(tm.mismapper_rounds), "kmer_positions": int(tm.kmer_positions)},
             "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
     if extra_sharded:
         line["sharded_single_sample"] = extra_sharded
