@@ -251,27 +251,41 @@ void pipeline::filter_multimappers() {
 // ------------------------------------------------------------------------------------------- e-value (filter_relative_support.cpp)
 void pipeline::estimate_evalues() {
 	event_table& e = ev;
-	// order-dependent global statistics, visited in the reference's iteration order (filter_relative_support.cpp:19-127)
-	std::unordered_map<u32, std::vector<u32> > partners; // sorted unique gene ids
+	// global statistics (filter_relative_support.cpp:19-127). Fusion partners of every gene: of the candidates that share (gene, breakpoint1, breakpoint2)
+	// -- the same breakpoints annotated with overlapping partner genes -- only the one the reference visits FIRST contributes its partner
+	// (`overlap_duplicates`, :22-30). First = smallest rank in the replayed iteration order; found by sorting instead of a hash map per candidate.
+	std::vector<u64> pairs;
 	{
-		struct key3 { u32 g; i32 a, b; bool operator==(const key3& o) const { return g == o.g && a == o.a && b == o.b; } };
-		struct key3_hash { size_t operator()(const key3& k) const { return ((size_t) k.g * 0x9E3779B97F4A7C15ULL) ^ ((size_t) (u32) k.a << 21) ^ (size_t) (u32) k.b; } };
-		std::unordered_map<key3, char, key3_hash> seen;
-		auto add = [](std::vector<u32>& v, u32 g) { std::vector<u32>::iterator it = std::lower_bound(v.begin(), v.end(), g); if (it == v.end() || *it != g) v.insert(it, g); };
-		for (size_t q = 0; q < e.order.size(); ++q) {
-			const u32 k = e.order[q];
-			if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
-			key3 a = {e.gene2[k], e.bp1[k], e.bp2[k]}; if (!seen[a]++) add(partners[e.gene2[k]], e.gene1[k]);
-			key3 b = {e.gene1[k], e.bp1[k], e.bp2[k]}; if (!seen[b]++) add(partners[e.gene1[k]], e.gene2[k]);
-		}
+		struct occurrence { u32 gene; i32 bp1, bp2; u32 rank; u32 partner; };
+		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
+		const size_t n_order = e.order.size();
+		std::vector<std::vector<occurrence> > part(threads);
+		std::vector<std::thread> pool;
+		for (int t = 0; t < threads; ++t) pool.emplace_back([&, t]() {
+			std::vector<occurrence>& v = part[t];
+			for (size_t q = n_order * t / threads; q < n_order * (t + 1) / threads; ++q) {
+				const u32 k = e.order[q];
+				if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
+				const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
+				v.push_back(a); v.push_back(b);
+			}
+			std::sort(v.begin(), v.end(), before);
+		});
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+		std::vector<occurrence> all;
+		for (int t = 0; t < threads; ++t) { const size_t mid = all.size(); all.insert(all.end(), part[t].begin(), part[t].end()); std::inplace_merge(all.begin(), all.begin() + mid, all.end(), before); std::vector<occurrence>().swap(part[t]); }
+		for (size_t x = 0; x < all.size(); ++x)
+			if (x == 0 || all[x].gene != all[x - 1].gene || all[x].bp1 != all[x - 1].bp1 || all[x].bp2 != all[x - 1].bp2) pairs.push_back((u64) all[x].gene << 32 | all[x].partner);
+		std::sort(pairs.begin(), pairs.end()); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
 	}
+	std::vector<u32> n_partners(ref.genes.size(), 0);
+	for (size_t x = 0; x < pairs.size(); ++x) ++n_partners[pairs[x] >> 32];
+	// a gene's count = its partners that have no more partners than the gene itself
 	std::vector<i32> partner_count(ref.genes.size(), 0);
-	for (std::unordered_map<u32, std::vector<u32> >::iterator p1 = partners.begin(); p1 != partners.end(); ++p1)
-		for (size_t j = 0; j < p1->second.size(); ++j)
-			if (p1->second.size() >= partners[p1->second[j]].size()) ++partner_count[p1->first];
+	for (size_t x = 0; x < pairs.size(); ++x) { const u32 g = (u32) (pairs[x] >> 32), partner = (u32) pairs[x]; if (n_partners[g] >= n_partners[partner]) ++partner_count[g]; }
 	arb_evalue_inputs in; memset(&in, 0, sizeof(in));
 	u32 spliced = 0, exonic = 0, intronic = 0, mixed = 0, dups = 0, invs = 0, same = 0, diff = 0;
-	std::set<u32> genes_with_fusions, genes_with_read_through;
+	std::vector<u8> with_fusion(ref.genes.size(), 0), with_read_through(ref.genes.size(), 0);
 	for (u32 k = 0; k < e.n; ++k) {
 		const bool dummy = ref.genes[e.gene1[k]].is_dummy || ref.genes[e.gene2[k]].is_dummy;
 		const u32 split = e.split_reads1[k] + e.split_reads2[k];
@@ -281,14 +295,16 @@ void pipeline::estimate_evalues() {
 		if (e.filter[k] == F_none && e.gene1[k] == e.gene2[k] && split >= 2) { if (e.dir1[k] == UPSTREAM && e.dir2[k] == DOWNSTREAM) ++dups; else if (e.dir1[k] == e.dir2[k]) ++invs; }
 		if (e.spliced1(k) && e.spliced2(k)) { if (e.gene1[k] == e.gene2[k]) ++same; else ++diff; }
 		if (!dummy && split > 0) {
-			genes_with_fusions.insert(e.gene1[k]); genes_with_fusions.insert(e.gene2[k]);
-			if (e.is_read_through(k)) { genes_with_read_through.insert(e.gene1[k]); genes_with_read_through.insert(e.gene2[k]); }
+			with_fusion[e.gene1[k]] = with_fusion[e.gene2[k]] = 1;
+			if (e.is_read_through(k)) with_read_through[e.gene1[k]] = with_read_through[e.gene2[k]] = 1;
 		}
 	}
 	if (spliced + exonic + intronic + mixed < 100 || spliced == 0 || exonic == 0 || intronic == 0 || mixed == 0) { spliced = 10; exonic = 65; intronic = 10; mixed = 15; }
 	if (invs + dups < 100) { invs = 1; dups = 1; }
 	if (same + diff < 100) { same = 0; diff = 100; }
-	const float rt_fraction = genes_with_fusions.empty() ? 0 : 1.0 * genes_with_read_through.size() / genes_with_fusions.size();
+	size_t genes_with_fusions = 0, genes_with_read_through = 0;
+	for (size_t g = 0; g < with_fusion.size(); ++g) { genes_with_fusions += with_fusion[g]; genes_with_read_through += with_read_through[g]; }
+	const float rt_fraction = genes_with_fusions == 0 ? 0 : 1.0 * genes_with_read_through / genes_with_fusions;
 	// pow() tables over the integer domains of the reference's expressions (filter_relative_support.cpp:143-205), same libm
 	u32 max_reads = 0; for (u32 k = 0; k < e.n; ++k) max_reads = std::max(max_reads, e.supporting_reads(k));
 	std::vector<double> t_reads(max_reads + 2), t_intra(max_reads + 2), t_inter(max_reads + 2), t_s1000(1000), t_s400(400), t_rt(400000), t_prox(400000);
@@ -494,44 +510,56 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	const unsigned int max_fusions_to_recover = 200;
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
 	find_top_expressed_genes(reads_by_gene, present, threshold, 0.998f); // fixed quantile (arriba.cpp:492)
-	typedef std::tuple<u32, u32, bool, bool> pair_key;
-	std::map<pair_key, std::vector<u32> > by_pair;
-	for (size_t q = 0; q < ev.order.size(); ++q) {
-		const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
-		if (fl == F_merge_adjacent) continue;
-		if (fl == F_none || fl == F_in_vitro || fl == F_intronic || fl == F_relative_support || fl == F_min_support || (fl == F_inconsistently_clipped && both_spliced(ev, ref, k)))
-			if (spliced_support(k, reads_by_gene, threshold) > 0) by_pair[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])].push_back(k);
-	}
+	// spliced support of every candidate that may back another one up (recover_both_spliced.cpp:104-118); a pure function of the candidate: host threads
+	const u32 NOT_ELIGIBLE = 0xFFFFFFFFu;
+	std::vector<u32> support(ev.n, NOT_ELIGIBLE);
+	parallel_rows(threads, ev.n, [&](u32 k) {
+		const u8 fl = ev.filter[k];
+		if (fl == F_merge_adjacent) return;
+		if (fl == F_none || fl == F_in_vitro || fl == F_intronic || fl == F_relative_support || fl == F_min_support || (fl == F_inconsistently_clipped && both_spliced(ev, ref, k))) {
+			const unsigned int s = spliced_support(k, reads_by_gene, threshold);
+			if (s > 0) support[k] = s;
+		}
+	});
+	// group them by (gene1, gene2, direction1, direction2): sorted keys instead of the reference's map of vectors (only sums over a group are taken)
+	auto key_of = [&](u32 k, bool flip) { return (u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) ((ev.dir1[k] != 0) != flip) << 1 | (u64) ((ev.dir2[k] != 0) != flip); };
+	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
+	std::vector<std::pair<u64, u32> > grouped;
+	for (u32 k = 0; k < ev.n; ++k) if (support[k] != NOT_ELIGIBLE) grouped.push_back(std::make_pair(key_of(k, false), k));
+	std::sort(grouped.begin(), grouped.end());
+	auto group_of = [&](u64 key, size_t& lo, size_t& hi) {
+		lo = std::lower_bound(grouped.begin(), grouped.end(), std::make_pair(key, (u32) 0)) - grouped.begin();
+		hi = lo; while (hi < grouped.size() && grouped[hi].first == key) ++hi;
+	};
+	// reads that back each discarded, both-spliced candidate up (recover_both_spliced.cpp:123-160); independent per candidate
+	std::vector<u32> backing(ev.n, 0);
+	parallel_rows(threads, ev.n, [&](u32 k) {
+		const u8 fl = ev.filter[k];
+		if (fl == F_none) return;
+		if (!both_spliced(ev, ref, k)) return;
+		if (ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) return;
+		if (ev.is_read_through(k)) return;
+		if (fl != F_relative_support && fl != F_min_support && fl != F_in_vitro) return;
+		unsigned int sum = 0;
+		size_t lo, hi;
+		group_of(key_of(k, false), lo, hi);
+		for (size_t x = lo; x < hi; ++x) sum += support[grouped[x].second];
+		group_of(key_of(k, true), lo, hi); // the reciprocal orientation
+		for (size_t x = lo; x < hi; ++x) {
+			const u32 o = grouped[x].second;
+			if (ev.is_read_through(o)) continue;
+			if (both_spliced(ev, ref, o) || (((ev.dir1[k] == DOWNSTREAM) != (ev.bp1[k] > ev.bp1[o])) && ((ev.dir2[k] == DOWNSTREAM) != (ev.bp2[k] > ev.bp2[o])))) sum += support[o];
+		}
+		backing[k] = sum;
+	});
+	// at most ~200 candidates are recovered: raise the read threshold until fewer would be (recover_both_spliced.cpp:162-175), then recover
 	std::map<unsigned int, unsigned int> recovered_by_reads;
-	unsigned int min_supporting_reads = 1;
-	for (int mode = 0; mode <= 1; ++mode) {
-		for (size_t q = 0; q < ev.order.size(); ++q) {
-			const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
-			if (fl == F_none) continue;
-			if (!both_spliced(ev, ref, k)) continue;
-			if (ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) continue;
-			if (ev.is_read_through(k)) continue;
-			if (fl != F_relative_support && fl != F_min_support && fl != F_in_vitro) continue;
-			unsigned int sum = 0;
-			std::map<pair_key, std::vector<u32> >::iterator same = by_pair.find(pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]));
-			if (same != by_pair.end()) for (size_t x = 0; x < same->second.size(); ++x) sum += spliced_support(same->second[x], reads_by_gene, threshold);
-			std::map<pair_key, std::vector<u32> >::iterator rec = by_pair.find(pair_key(ev.gene1[k], ev.gene2[k], !(bool) ev.dir1[k], !(bool) ev.dir2[k]));
-			if (rec != by_pair.end()) for (size_t x = 0; x < rec->second.size(); ++x) {
-				const u32 o = rec->second[x];
-				if (ev.is_read_through(o)) continue;
-				if (both_spliced(ev, ref, o) || (((ev.dir1[k] == DOWNSTREAM) != (ev.bp1[k] > ev.bp1[o])) && ((ev.dir2[k] == DOWNSTREAM) != (ev.bp2[k] > ev.bp2[o])))) sum += spliced_support(o, reads_by_gene, threshold);
-			}
-			if (sum >= 2) {
-				if (mode == 1) {
-					const unsigned int proximal = (ev.contig1[k] == ev.contig2[k] && std::abs(ev.bp1[k] - ev.bp2[k]) < 1000000) ? 1 : 0;
-					if (ev.supporting_reads(k) >= min_supporting_reads + proximal) ev.filter[k] = F_none;
-				} else ++recovered_by_reads[ev.supporting_reads(k)];
-			}
-		}
-		if (mode == 0) {
-			unsigned int would = 0;
-			for (std::map<unsigned int, unsigned int>::reverse_iterator it = recovered_by_reads.rbegin(); it != recovered_by_reads.rend(); ++it) { would += it->second; if (would >= max_fusions_to_recover) { min_supporting_reads = it->first + 1; break; } }
-		}
+	for (u32 k = 0; k < ev.n; ++k) if (backing[k] >= 2) ++recovered_by_reads[ev.supporting_reads(k)];
+	unsigned int min_supporting_reads = 1, would = 0;
+	for (std::map<unsigned int, unsigned int>::reverse_iterator it = recovered_by_reads.rbegin(); it != recovered_by_reads.rend(); ++it) { would += it->second; if (would >= max_fusions_to_recover) { min_supporting_reads = it->first + 1; break; } }
+	for (u32 k = 0; k < ev.n; ++k) if (backing[k] >= 2) {
+		const unsigned int proximal = (ev.contig1[k] == ev.contig2[k] && std::abs(ev.bp1[k] - ev.bp2[k]) < 1000000) ? 1 : 0;
+		if (ev.supporting_reads(k) >= min_supporting_reads + proximal) ev.filter[k] = F_none;
 	}
 	log_remaining("Searching for fusions with spliced split reads");
 }

@@ -19,7 +19,9 @@
 namespace arb { namespace host {
 
 namespace {
-static thread_local std::string* warning_sink = NULL; // set by the formatting threads of writer::write
+static thread_local std::string* warning_sink = NULL;
+static int filters_by_name[38]; // filter ids in alphabetical order of their names (the reference keeps them in a std::map<string, ...>)
+static void sort_filters_by_name() { for (int f = 0; f < 38; ++f) filters_by_name[f] = f; std::sort(filters_by_name, filters_by_name + 38, [](int a, int b) { return strcmp(FILTER_NAMES[a], FILTER_NAMES[b]) < 0; }); } // set by the formatting threads of writer::write
 
 typedef std::map<i32, std::map<std::string, unsigned int> > pileup_t;
 
@@ -495,30 +497,43 @@ struct writer {
 			    << fusion_type(k) << "\t" << s5 << "\t" << s3 << "\t" << e.discordant_mates[k] << "\t"
 			    << (cov5 >= 0 ? std::to_string((long long) cov5) : ".") << "\t" << (cov3 >= 0 ? std::to_string((long long) cov3) : ".") << "\t" << CONF[e.confidence[k] & 3] << "\t" << frame
 			    << "\t.\t.\t.\t.";
-			std::map<std::string, unsigned int> filters;
-			if (e.filter[k] != F_none) filters[FILTER_NAMES[e.filter[k]]] = 0;
-			std::vector<u32> reads(e.list1.begin() + e.list1_off[k], e.list1.begin() + e.list1_off[k + 1]);
-			reads.insert(reads.end(), e.list2.begin() + e.list2_off[k], e.list2.begin() + e.list2_off[k + 1]);
-			reads.insert(reads.end(), e.listd.begin() + e.listd_off[k], e.listd.begin() + e.listd_off[k + 1]);
-			for (size_t r = 0; r < reads.size(); ++r) if (p.labels[reads[r]] != F_none) ++filters[FILTER_NAMES[p.labels[reads[r]]]];
+			// filters column: the candidate's own filter and, with counts, the filters of its supporting reads, in alphabetical order (output_fusions.cpp:1187-1213)
+			unsigned int filter_count[38]; bool filter_present[38];
+			for (int f = 0; f < 38; ++f) { filter_count[f] = 0; filter_present[f] = false; }
+			if (e.filter[k] != F_none) filter_present[e.filter[k]] = true;
+			auto tally = [&](const std::vector<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
+			tally(e.list1, e.list1_off[k], e.list1_off[k + 1]); tally(e.list2, e.list2_off[k], e.list2_off[k + 1]); tally(e.listd, e.listd_off[k], e.listd_off[k + 1]);
 			out << "\t" << (ref.genes[g5].is_dummy ? "." : ref.genes[g5].gene_id) << "\t" << (ref.genes[g3].is_dummy ? "." : ref.genes[g3].gene_id)
 			    << "\t" << (tr5 < 0 ? "." : ref.transcripts[tr5].name) << "\t" << (tr3 < 0 ? "." : ref.transcripts[tr3].name)
 			    << "\t" << (d5 == UPSTREAM ? "upstream" : "downstream") << "\t" << (d3 == UPSTREAM ? "upstream" : "downstream") << "\t";
-			if (filters.empty()) out << ".";
-			else for (std::map<std::string, unsigned int>::iterator it = filters.begin(); it != filters.end(); ++it) { if (it != filters.begin()) out << ","; out << it->first; if (it->second != 0) out << "(" << it->second << ")"; }
+			bool any = false;
+			for (int x = 0; x < 38; ++x) {
+				const int f = filters_by_name[x];
+				if (f == F_none || !filter_present[f]) continue;
+				if (any) out << ",";
+				out << FILTER_NAMES[f]; if (filter_count[f] != 0) out << "(" << filter_count[f] << ")";
+				any = true;
+			}
+			if (!any) out << ".";
 			out << "\t" << tseq << "\t" << pep << "\t";
-			if (extra_info && !reads.empty()) {
-				for (size_t r = 0; r < reads.size(); ++r) {
-					if (r) out << ",";
-					const char* nm = p.frags.names.data() + p.frags.name_off[reads[r]]; u64 len = p.frags.name_off[reads[r] + 1] - p.frags.name_off[reads[r]];
-					u64 cut = len; while (cut > 0 && nm[cut - 1] != ',') --cut;
-					out.write(nm, cut > 0 ? cut - 1 : len);
-				}
+			if (extra_info && e.n_list1(k) + e.n_list2(k) + e.n_listd(k) > 0) {
+				bool first_name = true;
+				auto names = [&](const std::vector<u32>& list, u32 lo, u32 hi) {
+					for (u32 r = lo; r < hi; ++r) {
+						if (!first_name) out << ",";
+						first_name = false;
+						const char* nm = p.frags.names.data() + p.frags.name_off[list[r]]; u64 len = p.frags.name_off[list[r] + 1] - p.frags.name_off[list[r]];
+						u64 cut = len; while (cut > 0 && nm[cut - 1] != ',') --cut;
+						out.write(nm, cut > 0 ? cut - 1 : len);
+					}
+				};
+				names(e.list1, e.list1_off[k], e.list1_off[k + 1]); names(e.list2, e.list2_off[k], e.list2_off[k + 1]); names(e.listd, e.listd_off[k], e.listd_off[k + 1]);
 			} else out << ".";
 			out << "\n";
 	}
 
 	void write(const std::string& path, bool discarded, bool extra_info) const {
+		sort_filters_by_name();
 		std::vector<u32> rows;
 		for (size_t q = 0; q < e.order.size(); ++q) { const u32 k = e.order[q]; if (discarded != (e.filter[k] == F_none)) rows.push_back(k); }
 		if (!discarded) {
