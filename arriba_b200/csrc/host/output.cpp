@@ -15,6 +15,7 @@
 #include <stdexcept>
 #include <thread>
 #include <tuple>
+#include <unordered_map>
 
 namespace arb { namespace host {
 
@@ -283,6 +284,18 @@ struct writer {
 
 	// ---- peptide (annotate_protein_domains.cpp:164-400)
 	static char translate(const std::string& triplet) {
+		// all three letters plain bases: table built once from the general rule below
+		static char table[64]; static bool ready = false;
+		auto code = [](char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return -1; } };
+		if (!ready) { // benign race: every thread writes the same values
+			static const char L[] = "ACGT";
+			for (int x = 0; x < 64; ++x) { std::string t3; t3 += L[x >> 4]; t3 += L[x >> 2 & 3]; t3 += L[x & 3]; table[x] = translate_general(t3); }
+			ready = true;
+		}
+		if (triplet.size() == 3) { const int a = code(triplet[0]), b = code(triplet[1]), c = code(triplet[2]); if (a >= 0 && b >= 0 && c >= 0) return table[a << 4 | b << 2 | c]; }
+		return translate_general(triplet);
+	}
+	static char translate_general(const std::string& triplet) {
 		std::string t = triplet; for (size_t i = 0; i < t.size(); ++i) t[i] = (char) toupper(t[i]);
 		const std::string d = t.substr(0, 2);
 		if (d == "GC") return 'A'; if (t == "TGT" || t == "TGC") return 'C'; if (t == "GAT" || t == "GAC") return 'D'; if (t == "GAA" || t == "GAG") return 'E';
@@ -293,6 +306,25 @@ struct writer {
 		return '?';
 	}
 	i32 next_in_transcript(i32 ex, bool forward) const { if (ex < 0) return -1; const i32 n = forward ? ref.exons[ex].next : ref.exons[ex].prev; return n >= 0 ? n : -1; }
+	// amino acid at the genomic position of the last base of every codon of a transcript, with the warning the reference prints while translating it
+	struct protein_t {
+		std::vector<std::pair<i32, char> > by_pos; std::string warning;
+		const char* find(i32 pos) const { std::vector<std::pair<i32, char> >::const_iterator it = std::lower_bound(by_pos.begin(), by_pos.end(), std::make_pair(pos, (char) 0)); return it != by_pos.end() && it->first == pos ? &it->second : NULL; }
+	};
+	const protein_t& cached_protein(i32 start_exon) const { // per thread; the same transcripts recur in consecutive rows
+		static thread_local std::unordered_map<i32, protein_t> cache; static thread_local const void* owner = NULL;
+		if (owner != this || cache.size() > 512) { cache.clear(); owner = this; }
+		std::unordered_map<i32, protein_t>::iterator it = cache.find(start_exon);
+		if (it == cache.end()) {
+			protein_t pr; std::map<i32, char> m; std::string* const outer = warning_sink; warning_sink = &pr.warning;
+			reference_protein(start_exon, m);
+			warning_sink = outer;
+			pr.by_pos.assign(m.begin(), m.end());
+			it = cache.insert(std::make_pair(start_exon, pr)).first;
+		}
+		if (!it->second.warning.empty()) { if (warning_sink) *warning_sink += it->second.warning; else std::cerr << it->second.warning; } // printed on every use, like the reference
+		return it->second;
+	}
 	void reference_protein(i32 start_exon, std::map<i32, char>& protein) const {
 		if (start_exon < 0) return;
 		const bool fwd = ref.genes[ref.exons[start_exon].gene].forward;
@@ -352,8 +384,7 @@ struct writer {
 		if (frame5 == -1) return "."; else if (frame5 != 0) frame5 = 3 - frame5;
 		int frame3 = -1;
 		if (ref.genes[gene3].forward == strand3) frame3 = reading_frame(pos, (int) start3, (int) end3, tr3, gene3, ex3);
-		std::map<i32, char> prot5, prot3;
-		reference_protein(ex5, prot5); reference_protein(ex3, prot3);
+		const protein_t& prot5 = cached_protein(ex5); const protein_t& prot3 = cached_protein(ex3);
 		std::string pep; int c5 = 0, c3 = 0; bool started = false; std::string codon;
 		const bool g5fwd = ref.genes[gene5].forward;
 		for (size_t i = start5 + frame5; i < end3; ++i) {
@@ -368,9 +399,9 @@ struct writer {
 			}
 			if (codon.size() == 3) {
 				char aa = translate(codon);
-				const std::map<i32, char>& prot = i <= end5 ? prot5 : prot3;
-				std::map<i32, char>::const_iterator hit = prot.find(pos[i]);
-				if ((i > end5 && i < start3) || hit == prot.end() || aa != hit->second || (c5 != 3 && i <= end5) || (c3 != 3 && i >= start3) || (i >= start3 && frame3 == -1)) aa = (char) tolower(aa);
+				const protein_t& prot = i <= end5 ? prot5 : prot3;
+				const char* hit = prot.find(pos[i]);
+				if ((i > end5 && i < start3) || hit == NULL || aa != *hit || (c5 != 3 && i <= end5) || (c3 != 3 && i >= start3) || (i >= start3 && frame3 == -1)) aa = (char) tolower(aa);
 				pep += aa; codon.clear();
 				if (c3 >= 2 && aa == '*') break;
 			}

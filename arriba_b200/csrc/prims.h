@@ -51,7 +51,7 @@ struct device_pool {
 	struct slab { char* base; size_t size, used; };
 	struct per_device { std::vector<std::pair<size_t, void*> > free_blocks; std::vector<slab> slabs; size_t outstanding; per_device(): outstanding(0) {} };
 	std::vector<per_device> dev; std::mutex lock;
-	static size_t size_class(size_t bytes) { size_t c = 512; while (c < bytes) c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); return c; }
+	static size_t size_class(size_t bytes) { size_t c = 512; while (c < bytes) { c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); c = (c + 511) & ~(size_t) 511; } return c; } // multiples of 512: blocks are carved back to back
 	per_device& current() { int d = 0; ARB_CUDA_CHECK(cudaGetDevice(&d)); if ((size_t) d >= dev.size()) dev.resize((size_t) d + 1); return dev[(size_t) d]; }
 	void* get(size_t bytes, size_t& granted) {
 		std::lock_guard<std::mutex> g(lock);
