@@ -548,7 +548,7 @@ frag_view fragment_table::view() {
 struct final_frag { u32 worker; u32 frag; u64 prefix0, prefix1; };
 
 void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const ingest_options& opt, fragment_table& out, coverage_windows& coverage, ingest_stats& stats) {
-	const int T = std::max(1, opt.threads);
+	const int T = std::min(255, std::max(1, opt.threads)); // shard ids are bytes
 	double t0 = now_s();
 	const bool trace = getenv("ARB_TRACE") != NULL;
 	double tr_last = t0;
@@ -560,23 +560,30 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	// chunks of ~128 MiB of decompressed data, each a whole number of BGZF blocks; a record that straddles a chunk
 	// boundary is carried over to the front of the next buffer
 	const u64 chunk_target = 128ull << 20;
-	std::vector<u8> buf; size_t carry = 0;
 	std::vector<worker> workers(T);
 	std::vector<u16> tid_to_contig; std::vector<u8> interesting_contig, viral_contig;
 	bool header_done = false;
-	std::vector<u64> rec_off; std::vector<u8> rec_shard;
-	size_t b0 = 0;
 	u64 total_records = 0;
-	while (b0 < bam.blocks.size() || carry > 0) {
+	// A chunk is inflated, cut into records and sharded ("prepare") while the workers still parse the previous one ("process").
+	struct chunk_t { std::vector<u8> buf; std::vector<u64> rec_off; std::vector<u8> rec_shard; size_t consumed; bool last; chunk_t(): consumed(0), last(false) {} };
+	chunk_t chunks[2];
+	size_t b0 = 0;
+	double t_inflate = 0, t_scan = 0; // written by the preparing thread only
+	auto prepare = [&](chunk_t& c, const chunk_t* prev) {
+		const size_t carry = prev ? prev->buf.size() - prev->consumed : 0;
 		size_t b1 = b0; u64 bytes = 0;
 		while (b1 < bam.blocks.size() && (bytes == 0 || bytes + bam.blocks[b1].out_len <= chunk_target)) bytes += bam.blocks[b1++].out_len;
 		if (b1 == b0 && carry > 0) fail("failed to load alignments"); // truncated file
+		std::vector<u8>& buf = c.buf;
 		buf.resize(carry + bytes);
+		if (carry) memcpy(buf.data(), prev->buf.data() + prev->consumed, carry);
 		double ti = now_s();
 		const u64 base_out = b0 < bam.blocks.size() ? bam.blocks[b0].out_off : 0;
-		parallel_for(T, b1 - b0, [&](int, size_t lo, size_t hi) { for (size_t b = b0 + lo; b < b0 + hi; ++b) bam.inflate_block(bam.blocks[b], buf.data() + carry + (bam.blocks[b].out_off - base_out)); });
-		stats.t_inflate += now_s() - ti;
+		const size_t first = b0;
+		parallel_for(T, b1 - first, [&](int, size_t lo, size_t hi) { for (size_t b = first + lo; b < first + hi; ++b) bam.inflate_block(bam.blocks[b], buf.data() + carry + (bam.blocks[b].out_off - base_out)); });
+		t_inflate += now_s() - ti;
 		b0 = b1;
+		c.last = b0 >= bam.blocks.size();
 		size_t p = 0;
 		if (!header_done) {
 			if (buf.size() < 12 || memcmp(buf.data(), "BAM\1", 4) != 0) fail("failed to read SAM header");
@@ -613,31 +620,57 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			}
 			header_done = true;
 		}
-		// record boundaries (sequential hop) and shard of every record (hash of the read name)
+		// record boundaries: a sequential hop over the block_size fields; the shard of every record (hash of the read name) is then computed by all threads
 		double tp = now_s();
-		rec_off.clear(); rec_shard.clear();
+		std::vector<u64>& rec_off = c.rec_off; std::vector<u8>& rec_shard = c.rec_shard;
+		rec_off.clear();
 		while (p + 4 <= buf.size()) {
 			const u32 bs = rd32(buf.data() + p);
 			if (p + 4 + bs > buf.size()) break;
 			if (bs < 33) fail("failed to load alignments");
-			const u8* q = buf.data() + p + 4 + 32; const u32 lq = buf[p + 4 + 8];
-			u64 h = 1469598103934665603ULL;
-			for (u32 k = 0; k + 1 < lq && q[k]; ++k) { h ^= q[k]; h *= 1099511628211ULL; }
-			rec_off.push_back(p); rec_shard.push_back((u8) ((h >> 20) % (u64) T));
+			rec_off.push_back(p);
 			p += 4 + bs;
 		}
-		total_records += rec_off.size();
-		parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) {
-			for (size_t t = lo; t < hi; ++t) {
-				worker& w = workers[t];
-				for (size_t k = 0; k < rec_off.size(); ++k) if (rec_shard[k] == t) w.process(buf.data() + rec_off[k] + 4, rd32(buf.data() + rec_off[k]));
+		c.consumed = p;
+		rec_shard.resize(rec_off.size());
+		parallel_for(T, rec_off.size(), [&](int, size_t lo, size_t hi) {
+			for (size_t k = lo; k < hi; ++k) {
+				const u8* rec = buf.data() + rec_off[k] + 4;
+				const u8* q = rec + 32; const u32 lq = rec[8];
+				u64 h = 1469598103934665603ULL;
+				for (u32 x = 0; x + 1 < lq && q[x]; ++x) { h ^= q[x]; h *= 1099511628211ULL; }
+				rec_shard[k] = (u8) ((h >> 20) % (u64) T);
 			}
 		});
+		t_scan += now_s() - tp;
+		if (c.last && c.consumed != buf.size()) fail("failed to load alignments");
+	};
+	if (bam.blocks.empty()) fail("failed to read SAM header");
+	prepare(chunks[0], NULL);
+	for (int cur = 0;; cur ^= 1) {
+		chunk_t& c = chunks[cur];
+		std::string prepare_error; std::thread next;
+		if (!c.last) next = std::thread([&]() { try { prepare(chunks[cur ^ 1], &c); } catch (const std::exception& x) { prepare_error = x.what(); if (prepare_error.empty()) prepare_error = "failed to load alignments"; } });
+		const double tp = now_s();
+		std::string process_error;
+		try {
+			total_records += c.rec_off.size();
+			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) {
+				for (size_t t = lo; t < hi; ++t) {
+					worker& w = workers[t];
+					const u8* base = c.buf.data();
+					for (size_t k = 0; k < c.rec_off.size(); ++k) if (c.rec_shard[k] == t) w.process(base + c.rec_off[k] + 4, rd32(base + c.rec_off[k]));
+				}
+			});
+		} catch (const std::exception& x) { process_error = x.what(); }
 		stats.t_parse += now_s() - tp;
-		carry = buf.size() - p;
-		if (carry) memmove(buf.data(), buf.data() + p, carry);
-		if (b0 >= bam.blocks.size()) { if (carry) fail("failed to load alignments"); break; }
+		if (next.joinable()) next.join();
+		if (!process_error.empty()) fail(process_error);
+		if (!prepare_error.empty()) fail(prepare_error);
+		if (c.last) break;
 	}
+	stats.t_inflate = t_inflate; stats.t_parse += t_scan;
+	{ chunk_t a, b; std::swap(chunks[0], a); std::swap(chunks[1], b); }
 	if (!header_done) fail("failed to read SAM header");
 	(void) t0;
 	lap("inflate + scan + parse");
