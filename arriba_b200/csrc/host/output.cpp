@@ -24,7 +24,31 @@ static thread_local std::string* warning_sink = NULL;
 static int filters_by_name[38]; // filter ids in alphabetical order of their names (the reference keeps them in a std::map<string, ...>)
 static void sort_filters_by_name() { for (int f = 0; f < 38; ++f) filters_by_name[f] = f; std::sort(filters_by_name, filters_by_name + 38, [](int a, int b) { return strcmp(FILTER_NAMES[a], FILTER_NAMES[b]) < 0; }); } // set by the formatting threads of writer::write
 
-typedef std::map<i32, std::map<std::string, unsigned int> > pileup_t;
+// Pileup column: what the reads show at one reference position -- a base, "-" (deleted), "_" / ">" / "<" (inside / start / end of an intron) or, for
+// an insertion, the inserted bases plus the following one. The reference keeps a map<string, count> per position (output_fusions.cpp:22); almost all keys are
+// single characters of a small alphabet, which get counters in an array; everything else goes to the map. entries() restores the map's iteration order.
+struct pile_column {
+	static const char* symbols() { return "-<=>ABCDGHKMNRSTVWY_"; } // ascending ASCII
+	enum { N_SYMBOLS = 20 };
+	unsigned int single[N_SYMBOLS]; std::map<std::string, unsigned int> other;
+	pile_column() { for (int k = 0; k < N_SYMBOLS; ++k) single[k] = 0; }
+	static int index_of(char c) { static signed char table[256]; static bool ready = false; if (!ready) { for (int k = 0; k < 256; ++k) table[k] = -1; for (int k = 0; k < N_SYMBOLS; ++k) table[(unsigned char) symbols()[k]] = (signed char) k; ready = true; } return table[(unsigned char) c]; }
+	void add(char c, unsigned int n = 1) { const int x = index_of(c); if (x >= 0) single[x] += n; else other[std::string(1, c)] += n; }
+	void add(const std::string& s, unsigned int n = 1) { if (s.size() == 1) add(s[0], n); else other[s] += n; }
+	unsigned int total() const { unsigned int t = 0; for (int k = 0; k < N_SYMBOLS; ++k) t += single[k]; for (std::map<std::string, unsigned int>::const_iterator it = other.begin(); it != other.end(); ++it) t += it->second; return t; }
+	void entries(std::vector<std::pair<std::string, unsigned int> >& out) const { // ascending by key, like the reference's map
+		out.clear();
+		std::map<std::string, unsigned int>::const_iterator it = other.begin();
+		for (int k = 0; k < N_SYMBOLS; ++k) {
+			if (single[k] == 0) continue;
+			const std::string key(1, symbols()[k]);
+			while (it != other.end() && it->first < key) { out.push_back(*it); ++it; }
+			out.push_back(std::make_pair(key, single[k]));
+		}
+		for (; it != other.end(); ++it) out.push_back(*it);
+	}
+};
+typedef std::map<i32, pile_column> pileup_t;
 
 char comp_char(char c) { // assembly.hpp:9-22
 	switch (c) {
@@ -56,18 +80,20 @@ struct writer {
 			const bool fwd = f.fwd(a);
 			if (f.n_aln[frag] == 2 && !((direction == DOWNSTREAM && fwd && f.end[a] <= breakpoint + 2 && f.end[a] >= breakpoint - 200) || (direction == UPSTREAM && !fwd && f.start[a] >= breakpoint - 2 && f.start[a] <= breakpoint + 200))) continue;
 			if (f.n_aln[frag] == 3 && (mate == SPLIT_READ || mate == SUPPLEMENTARY) && f.start[a] != breakpoint && f.end[a] != breakpoint) continue;
-			std::string seq = read_sequence(frag, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
-			if (reverse_complement) seq = revcomp(seq);
+			// bases are decoded on the fly (reverse-complemented when the supplementary lies on the other strand): no per-read strings
+			const u32 sa = f.idx(frag, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
+			const u8* const packed = f.sq(sa); const size_t seq_size = f.seq_len[sa];
+			auto base_at = [&](size_t off) { return reverse_complement ? comp_char(nt16_char(nt16_at(packed, (u32) (seq_size - 1 - off)))) : nt16_char(nt16_at(packed, (u32) off)); };
 			i32 read_off = 0, ref_off = f.start[a]; int carry = 0; // carry: one base was already consumed by a preceding insertion
 			const u32* c = f.cig(a); const u32 nc = f.cigar_cnt[a];
-			auto piece = [&](i32 off, size_t n) { return (size_t) off <= seq.size() ? seq.substr(off, n) : std::string(); };
+			auto piece = [&](i32 off, size_t n) { std::string s; if ((size_t) off <= seq_size) for (size_t x = (size_t) off; x < seq_size && x < (size_t) off + n; ++x) s += base_at(x); return s; };
 			for (u32 k = 0; k < nc; ++k) {
 				const u32 op = cig_op(c[k]); const i32 len = (i32) cig_len(c[k]);
 				bool as_match = false;
 				switch (op) {
-					case C_I: ++pileup[ref_off][piece(read_off, len + 1)]; read_off += len + 1; ++ref_off; carry = 1; break;
+					case C_I: pileup[ref_off].add(piece(read_off, len + 1)); read_off += len + 1; ++ref_off; carry = 1; break;
 					case C_N: { const i32 s0 = ref_off; ref_off += len - carry; ++introns[std::make_pair(s0, ref_off - 1)]; carry = 0; break; }
-					case C_D: for (i32 b = 0; b < len - carry; ++b, ++ref_off) ++pileup[ref_off]["-"]; carry = 0; break;
+					case C_D: for (i32 b = 0; b < len - carry; ++b, ++ref_off) pileup[ref_off].add('-'); carry = 0; break;
 					case C_H: if (mate == SUPPLEMENTARY) read_off += len; break;
 					case C_S:
 						if (f.n_aln[frag] == 3 && mate == SPLIT_READ && ((k == 0 && fwd) || (k == nc - 1 && !fwd))) { if (k == 0 && fwd) ref_off -= len; as_match = true; } // clipped segment joins the pileup (non-template bases)
@@ -76,37 +102,47 @@ struct writer {
 					case C_M: case C_EQ: case C_X: as_match = true; break;
 					default: break;
 				}
-				if (as_match) { for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) ++pileup[ref_off][piece(read_off, 1)]; carry = 0; }
+				if (as_match) { // consecutive positions: walk the map instead of searching it for every base
+					pileup_t::iterator at = pileup.end();
+					for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) {
+						if (at != pileup.end()) { ++at; if (at == pileup.end() || at->first != ref_off) at = pileup.end(); }
+						if (at == pileup.end()) at = pileup.try_emplace(ref_off).first;
+						if ((size_t) read_off < seq_size) at->second.add(base_at((size_t) read_off)); else at->second.add(std::string());
+					}
+					carry = 0;
+				}
 			}
 		}
 		for (std::map<std::pair<i32, i32>, unsigned int>::iterator it = introns.begin(); it != introns.end(); ++it) {
-			pileup[it->first.first][">"] += it->second; pileup[it->first.second]["<"] += it->second;
-			for (i32 i = it->first.first + 1; i < it->first.second; ++i) pileup[i]["_"] += it->second;
+			pileup[it->first.first].add('>', it->second); pileup[it->first.second].add('<', it->second);
+			for (i32 i = it->first.first + 1; i < it->first.second; ++i) pileup[i].add('_', it->second);
 		}
 	}
 
 	// ---- consensus of a pileup (output_fusions.cpp:109-240)
 	void consensus(const pileup_t& pileup, i32 breakpoint, u32 direction, u32 gene, std::string& sequence, std::vector<i32>& positions, std::string& clipped) const {
 		unsigned int peak = 0;
-		for (pileup_t::const_iterator pos = pileup.begin(); pos != pileup.end(); ++pos) { unsigned int cov = 0; for (auto b = pos->second.begin(); b != pos->second.end(); ++b) cov += b->second; if (cov > peak) peak = cov; }
+		for (pileup_t::const_iterator pos = pileup.begin(); pos != pileup.end(); ++pos) { const unsigned int cov = pos->second.total(); if (cov > peak) peak = cov; }
 		const float low_fraction = 0.10f;
 		pileup_t::const_iterator first = pileup.begin(), last = pileup.end();
 		for (pileup_t::const_iterator pos = pileup.begin(); pos != pileup.end(); ++pos) {
-			unsigned int cov = 0; for (auto b = pos->second.begin(); b != pos->second.end(); ++b) cov += b->second;
+			const unsigned int cov = pos->second.total();
 			if (direction == DOWNSTREAM) { if (cov < peak * low_fraction) first = pos; else break; }
 			else if (cov > peak * low_fraction) last = pos;
 		}
 		if (last != pileup.end()) ++last;
 		bool intron_open = false, intron_closed = true;
 		const u32 contig = ref.genes[gene].contig;
+		std::vector<std::pair<std::string, unsigned int> > column;
 		for (pileup_t::const_iterator pos = first; pos != last; ++pos) {
 			if (pos != first && std::prev(pos)->first < pos->first - 1 && !intron_open) { sequence += "..."; positions.resize(positions.size() + 3, -1); }
 			std::string ref_base = "N";
 			if (has_assembly(contig) && (u32) pos->first < ref.seq_len[contig]) ref_base = std::string(1, ref.sequence(contig)[pos->first]);
-			auto best = pos->second.end(); unsigned int cov = 0;
-			for (auto b = pos->second.begin(); b != pos->second.end(); ++b) {
+			pos->second.entries(column);
+			auto best = column.end(); unsigned int cov = 0;
+			for (auto b = column.begin(); b != column.end(); ++b) {
 				const bool is_intron = b->first == "_" || b->first == ">" || b->first == "<";
-				if (best == pos->second.end() || b->second > best->second ||
+				if (best == column.end() || b->second > best->second ||
 				    (b->second == best->second && ((b->first == ref_base && best->first != "_" && best->first != ">" && best->first != "<") || (b->first == "<" && best->first != "_" && best->first != ">") || (b->first == "_" || b->first == ">")))) best = b;
 				if (!is_intron) cov += b->second;
 			}
