@@ -129,20 +129,38 @@ struct worker {
 	refdata* ref; const ingest_options* opt; const std::vector<u16>* tid_to_contig; const std::vector<u8>* interesting_contig; const std::vector<u8>* viral_contig;
 	annot_view an;
 	std::vector<char> names; std::vector<u32> cigars; std::vector<u8> seqs; std::vector<aln_build> alns; std::vector<frag_build> frags;
-	std::unordered_map<std::string, u32, name_hash> frag_by_name;
+	std::vector<u32> name_slots; // open-addressing index of `frags` by name: fragment id + 1, 0 = empty; names are compared in the `names` pool
 	std::unordered_map<std::string, std::vector<u8>, name_hash> pending; // first mate of a proper pair, waiting for the second
-	coverage_windows cov; bool own_cov;
+	coverage_windows* cov; // shared by all workers: saturating counters and flags are updated atomically, the result does not depend on the order
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
 	std::string key;
-	worker(): own_cov(false), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
+	worker(): cov(NULL), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
 
 	u32 fragment(const std::string& name, bool* created = NULL) {
-		std::unordered_map<std::string, u32, name_hash>::iterator it = frag_by_name.find(name);
-		if (it != frag_by_name.end()) { if (created) *created = false; return it->second; }
+		if (name_slots.empty()) name_slots.assign(1u << 12, 0);
+		u64 h = 1469598103934665603ULL; for (size_t i = 0; i < name.size(); ++i) { h ^= (u8) name[i]; h *= 1099511628211ULL; }
+		h ^= h >> 29; // the low bits of the same hash chose the worker
+		size_t mask = name_slots.size() - 1, at = (size_t) h & mask;
+		for (; name_slots[at] != 0; at = (at + 1) & mask) {
+			const frag_build& f = frags[name_slots[at] - 1];
+			if (f.name_len == name.size() && memcmp(names.data() + f.name_off, name.data(), name.size()) == 0) { if (created) *created = false; return name_slots[at] - 1; }
+		}
 		frag_build f; f.name_off = names.size(); f.name_len = (u32) name.size(); f.head = f.tail = -1; f.count = 0; f.single_end = 0; f.duplicate = 0;
 		names.insert(names.end(), name.begin(), name.end());
-		const u32 id = (u32) frags.size(); frags.push_back(f); frag_by_name.emplace(name, id);
+		const u32 id = (u32) frags.size(); frags.push_back(f);
+		name_slots[at] = id + 1;
 		if (created) *created = true;
+		if (frags.size() * 2 > name_slots.size()) { // keep the load below one half
+			std::vector<u32> bigger(name_slots.size() * 2, 0); mask = bigger.size() - 1;
+			for (size_t k = 0; k < frags.size(); ++k) {
+				const frag_build& g = frags[k];
+				u64 hh = 1469598103934665603ULL; for (u32 i = 0; i < g.name_len; ++i) { hh ^= (u8) names[g.name_off + i]; hh *= 1099511628211ULL; }
+				hh ^= hh >> 29;
+				size_t slot = (size_t) hh & mask; while (bigger[slot] != 0) slot = (slot + 1) & mask;
+				bigger[slot] = (u32) k + 1;
+			}
+			name_slots.swap(bigger);
+		}
 		return id;
 	}
 	void link(u32 frag, const aln_build& a) {
@@ -189,10 +207,12 @@ struct worker {
 	void add_coverage(const rec_t& m1, const rec_t* m2p, bool is_chimeric, bool flags_cleared) {
 		const rec_t& m2 = m2p ? *m2p : m1;
 		const u16 f1 = flags_cleared ? 0 : m1.flag;
+		coverage_windows& cov = *this->cov;
+		auto flag = [](u8& x) { __atomic_store_n(&x, (u8) 1, __ATOMIC_RELAXED); };
 		if ((u32) m1.tid >= cov.starts.size() || cov.starts[m1.tid].empty() || (u32) m2.tid >= cov.starts.size() || cov.starts[m2.tid].empty()) return;
 		if ((f1 & BF_PAIRED) && !(f1 & BF_PROPER)) is_chimeric = true; // the reference's soft-clip tests can never fire (bam_cigar_type() is 0..3)
 		if (!is_chimeric) {
-			if (!(f1 & BF_REVERSE) || !(f1 & BF_PAIRED)) cov.starts[m1.tid][m1.pos / 20] = 1; else cov.starts[m2.tid][m2.pos / 20] = 1;
+			if (!(f1 & BF_REVERSE) || !(f1 & BF_PAIRED)) flag(cov.starts[m1.tid][m1.pos / 20]); else flag(cov.starts[m2.tid][m2.pos / 20]);
 		}
 		i32 p1 = m1.pos, p2 = m2.pos, position = std::min(p1, p2);
 		int window = position / 20;
@@ -210,13 +230,16 @@ struct worker {
 			if (consumes_query) {
 				std::vector<u16>& cv = cov.coverage[contig];
 				while (window <= position / 20) {
-					if (cv[window] < 65535 && position - window * 20 >= 10) ++cv[window];
+					if (position - window * 20 >= 10) { // saturating increment
+						u16 seen = __atomic_load_n(&cv[window], __ATOMIC_RELAXED);
+						while (seen < 65535 && !__atomic_compare_exchange_n(&cv[window], &seen, (u16) (seen + 1), true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+					}
 					++window;
 				}
 			} else window = position / 20;
 		}
 		if (!is_chimeric) {
-			if ((f1 & BF_REVERSE) || !(f1 & BF_PAIRED)) cov.ends[m1.tid][(p1 - 1) / 20] = 1; else cov.ends[m2.tid][(p2 - 1) / 20] = 1;
+			if ((f1 & BF_REVERSE) || !(f1 & BF_PAIRED)) flag(cov.ends[m1.tid][(p1 - 1) / 20]); else flag(cov.ends[m2.tid][(p2 - 1) / 20]);
 		}
 	}
 
@@ -615,8 +638,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 				worker& w = workers[t];
 				w.ref = &ref; w.opt = &opt; w.tid_to_contig = &tid_to_contig; w.interesting_contig = &interesting_contig; w.viral_contig = &viral_contig;
 				w.an = ref.host_view(); w.viral_reads.assign(nc, 0);
-				if (t == 0) w.cov.coverage.swap(coverage.coverage), w.cov.starts.swap(coverage.starts), w.cov.ends.swap(coverage.ends);
-				else w.cov.resize(ref);
+				w.cov = &coverage;
 			}
 			header_done = true;
 		}
@@ -683,17 +705,6 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		worker& w = workers[t];
 		stats.mapped_reads += w.mapped_reads; stats.malformed += w.malformed; stats.missing_hi_tag += w.missing_hi; stats.no_chimeric_reads = stats.no_chimeric_reads && w.no_chimeric;
 		for (size_t c = 0; c < w.viral_reads.size(); ++c) stats.mapped_viral_reads_by_contig[c] += w.viral_reads[c];
-	}
-	coverage.coverage.swap(workers[0].cov.coverage); coverage.starts.swap(workers[0].cov.starts); coverage.ends.swap(workers[0].cov.ends);
-	for (int t = 1; t < T; ++t) {
-		worker& w = workers[t];
-		parallel_for(T, coverage.coverage.size(), [&](int, size_t lo, size_t hi) {
-			for (size_t c = lo; c < hi; ++c) for (size_t k = 0; k < coverage.coverage[c].size(); ++k) {
-				const u32 s = (u32) coverage.coverage[c][k] + w.cov.coverage[c][k];
-				coverage.coverage[c][k] = (u16) std::min(s, 65535u); coverage.starts[c][k] |= w.cov.starts[c][k]; coverage.ends[c][k] |= w.cov.ends[c][k];
-			}
-		});
-		std::vector<std::vector<u16> >().swap(w.cov.coverage);
 	}
 	lap("merge by-products");
 	if (stats.mapped_reads == 0) fail("no normal reads found");

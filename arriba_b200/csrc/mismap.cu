@@ -100,7 +100,8 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	n_heavy.zero(ex, 1);
 	mismap_item_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
 	stage_timer t1(ex);
-	for_each(ex, I, mi);
+	auto launch = [&](u32 n, const auto& fn) { if (mismap_min_blocks >= 4) for_each_occ<4>(ex, n, fn); else if (mismap_min_blocks == 3) for_each_occ<3>(ex, n, fn); else for_each(ex, n, fn); };
+	launch(I, mi);
 	timings.mismappers_pass1_ms = t1.stop();
 	u32 H = 0; n_heavy.download(ex, &H, 1);
 	stage_timer t2(ex);
@@ -111,7 +112,7 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	for (u32 done = 0; done < H; ) { // launches of at most 2^31 threads
 		const u32 batch = std::min<u32>(H - done, 0x80000000u / mismap_lanes);
 		mismap_heavy_fn mh = {items, heavy.ptr() + done, mismap_lanes, mismap_spawn_budget, queue_a.ptr(), n_tasks.ptr(), queue_cap};
-		for_each(ex, batch * mismap_lanes, mh);
+		launch(batch * mismap_lanes, mh);
 		done += batch;
 	}
 	u64 spawned = 0; u32 rounds = 0;
@@ -125,7 +126,7 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 		for (u32 done = 0; done < Q; ) {
 			const u32 batch = std::min<u32>(Q - done, 0x80000000u / mismap_task_lanes);
 			mismap_task_fn mt = {items, from + done, mismap_task_lanes, mismap_spawn_budget, to, n_tasks.ptr(), queue_cap};
-			for_each(ex, batch * mismap_task_lanes, mt);
+			launch(batch * mismap_task_lanes, mt);
 			done += batch;
 		}
 		std::swap(from, to);

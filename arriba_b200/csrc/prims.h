@@ -159,6 +159,17 @@ template <class F> void for_each(const exec_ctx& ex, u32 n, const F& f) {
 	ARB_CUDA_CHECK(cudaGetLastError());
 	++stats().kernels;
 }
+// same, with a register cap: at least MIN_BLOCKS resident 256-thread blocks per SM (the recursive re-alignment kernels trade spills for occupancy)
+template <int MIN_BLOCKS, class F> __global__ void __launch_bounds__(256, MIN_BLOCKS) k_for_each_occ(u32 n, F f) {
+	u32 i = blockIdx.x * 256u + threadIdx.x;
+	if (i < n) f(i);
+}
+template <int MIN_BLOCKS, class F> void for_each_occ(const exec_ctx& ex, u32 n, const F& f) {
+	if (n == 0) return;
+	k_for_each_occ<MIN_BLOCKS, F><<<(n + 255) / 256, 256, 0, ex.stream>>>(n, f);
+	ARB_CUDA_CHECK(cudaGetLastError());
+	++stats().kernels;
+}
 // functor with a private scratch array of WORDS 32-bit words per thread, kept in shared memory and interleaved by thread
 // (word k of thread t at [k * BLOCK + t]: dynamically indexed, yet free of bank conflicts); f(i, scratch, stride)
 template <u32 WORDS, u32 BLOCK, class F> __global__ void __launch_bounds__(BLOCK) k_for_each_scratch(u32 n, F f) {
@@ -175,6 +186,7 @@ template <u32 WORDS, class F> void for_each_scratch(const exec_ctx& ex, u32 n, c
 }
 #else
 template <class F> void for_each(const exec_ctx&, u32 n, const F& f) { for (u32 i = 0; i < n; ++i) f(i); ++stats().kernels; }
+template <int MIN_BLOCKS, class F> void for_each_occ(const exec_ctx& ex, u32 n, const F& f) { for_each(ex, n, f); }
 template <u32 WORDS, class F> void for_each_scratch(const exec_ctx&, u32 n, const F& f) { u32 scratch[WORDS]; for (u32 i = 0; i < n; ++i) f(i, scratch, 1); ++stats().kernels; }
 #endif
 

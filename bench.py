@@ -126,7 +126,7 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    threads = args.threads or max(1, min(32, cores // max(1, world)))
+    threads = args.threads or max(1, min(64, cores // max(1, world)))
     wl = WORKLOADS[args.workload]
     sample_bp = args.sample_breakpoints or max(50, int(wl["breakpoints"] * 400000 / wl["fragments"]))  # ~400 k fragments: 10-30 s of reference CPU time
     metric = "chimeric fragments/s, " + SCOPE
