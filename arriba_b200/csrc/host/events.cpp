@@ -27,6 +27,20 @@ template <class F> static void parallel_rows(int threads, size_t n, F f) {
 	for (int t = 0; t < threads; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 }
 
+// sort on the host threads: slices sorted concurrently, then merged pairwise (log2(threads) rounds)
+template <class T, class Less> static void parallel_sort(std::vector<T>& v, Less less, int threads) {
+	const size_t n = v.size();
+	if (threads <= 1 || n < 65536) { std::sort(v.begin(), v.end(), less); return; }
+	int parts = 1; while (parts * 2 <= threads) parts *= 2;
+	std::vector<size_t> cut(parts + 1); for (int t = 0; t <= parts; ++t) cut[t] = n * t / parts;
+	{ std::vector<std::thread> pool; for (int t = 0; t < parts; ++t) pool.emplace_back([&, t]() { std::sort(v.begin() + cut[t], v.begin() + cut[t + 1], less); }); for (size_t t = 0; t < pool.size(); ++t) pool[t].join(); }
+	for (int width = 1; width < parts; width *= 2) {
+		std::vector<std::thread> pool;
+		for (int t = 0; t + width < parts; t += 2 * width) pool.emplace_back([&, t, width]() { std::inplace_merge(v.begin() + cut[t], v.begin() + cut[t + width], v.begin() + cut[std::min(parts, t + 2 * width)], less); });
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+	}
+}
+
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 
 // ------------------------------------------------------------------------------------------- iteration order
@@ -48,12 +62,48 @@ struct cand_key_hash { // value-identical to the reference's recursive tuple has
 };
 }
 
+// The reference inserts the candidates, in the order the device numbers them, into a std::unordered_map and later ITERATES it. libstdc++ keeps all nodes in
+// one singly linked list; a bucket stores the node BEFORE its first node; a new node goes to the front of its bucket, or to the front of the whole list if
+// the bucket was empty; growing re-threads the list in its current order (bits/hashtable.h: _M_insert_bucket_begin, _M_rehash_aux). Replaying that with
+// index arrays instead of a real map gives the same order without one heap node per candidate; bucket counts come from the library's own policy object.
 void event_table::replay_iteration_order() {
-	std::unordered_map<cand_key, u32, cand_key_hash> m;
-	for (u32 k = 0; k < n; ++k) m.insert(std::make_pair(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k]), k));
-	if (m.size() != n) throw std::runtime_error("candidate keys are not unique");
+	const u32 NONE = 0xFFFFFFFFu, BEFORE_BEGIN = n; // list positions: 0..n-1 candidates, n = the list head sentinel
+	std::vector<size_t> code(n);
+	cand_key_hash hasher;
+	for (u32 k = 0; k < n; ++k) code[k] = hasher(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k]));
+	std::vector<u32> next((size_t) n + 1, NONE);
+	std::vector<u32> bucket(1, NONE); // node before the first node of the bucket
+	std::__detail::_Prime_rehash_policy policy;
+	size_t n_buckets = 1;
+	for (u32 k = 0; k < n; ++k) {
+		const std::pair<bool, size_t> grow = policy._M_need_rehash(n_buckets, k, 1);
+		if (grow.first) {
+			std::vector<u32> fresh(grow.second, NONE);
+			u32 p = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = NONE;
+			size_t first_bucket = 0;
+			while (p != NONE) {
+				const u32 following = next[p];
+				const size_t b = code[p] % grow.second;
+				if (fresh[b] == NONE) {
+					next[p] = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = p; fresh[b] = BEFORE_BEGIN;
+					if (next[p] != NONE) fresh[first_bucket] = p;
+					first_bucket = b;
+				} else { next[p] = next[fresh[b]]; next[fresh[b]] = p; }
+				p = following;
+			}
+			bucket.swap(fresh); n_buckets = grow.second;
+		}
+		const size_t b = code[k] % n_buckets;
+		if (bucket[b] != NONE) { next[k] = next[bucket[b]]; next[bucket[b]] = k; }
+		else {
+			next[k] = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = k;
+			if (next[k] != NONE) bucket[code[next[k]] % n_buckets] = k;
+			bucket[b] = BEFORE_BEGIN;
+		}
+	}
 	order.clear(); order.reserve(n);
-	for (std::unordered_map<cand_key, u32, cand_key_hash>::const_iterator it = m.begin(); it != m.end(); ++it) order.push_back(it->second);
+	for (u32 p = next[BEFORE_BEGIN]; p != NONE; p = next[p]) order.push_back(p);
+	if (order.size() != n) throw std::runtime_error("candidate keys are not unique");
 }
 
 // ------------------------------------------------------------------------------------------- helpers on (table, reference)
@@ -208,12 +258,17 @@ void pipeline::filter_multimappers() {
 	};
 	const u32 NONE = 0xFFFFFFFFu;
 	std::vector<u32> best(N, NONE); // most supported candidate per multimapping fragment
-	auto consider = [&](u32 cand, u32 frag) { if (!(frags.fflags[frag] & FF_MULTIMAPPER)) return; if (best[frag] == NONE || better(cand, best[frag])) best[frag] = cand; };
-	for (u32 k = 0; k < e.n; ++k) {
+	// `better` is a total order, so the best candidate of a fragment does not depend on the visiting order: candidates in parallel, compare-and-swap per fragment
+	auto consider = [&](u32 cand, u32 frag) {
+		if (!(frags.fflags[frag] & FF_MULTIMAPPER)) return;
+		u32 seen = __atomic_load_n(&best[frag], __ATOMIC_RELAXED);
+		while ((seen == NONE || better(cand, seen)) && !__atomic_compare_exchange_n(&best[frag], &seen, cand, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+	};
+	parallel_rows(threads, e.n, [&](u32 k) {
 		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) consider(k, e.list1[p]);
 		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) consider(k, e.list2[p]);
 		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) consider(k, e.listd[p]);
-	}
+	});
 	auto more_support = [&](u32 fa, u32 fb) { // fusion_has_more_support(most_supported[fa], most_supported[fb]) with NULL handling
 		const u32 x = best[fa], y = best[fb];
 		if (x == NONE) return false;
@@ -224,6 +279,7 @@ void pipeline::filter_multimappers() {
 	auto stem = [&](u32 i, u64& len) { const char* s = frags.names.data() + frags.name_off[i]; u64 l = frags.name_off[i + 1] - frags.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; len = k > 0 ? k - 1 : l; return s; };
 	u32 i = 0;
 	while (i < N) {
+		if (!(frags.fflags[i] & FF_MULTIMAPPER)) { ++i; continue; } // the flag marks exactly the fragments that share their stem with a neighbour (ingest)
 		u64 li; const char* si = stem(i, li);
 		u32 j = i + 1;
 		for (; j < N; ++j) { u64 lj; const char* sj = stem(j, lj); if (lj != li || memcmp(si, sj, li) != 0) break; }
@@ -238,13 +294,13 @@ void pipeline::filter_multimappers() {
 		}
 		i = j;
 	}
-	for (u32 k = 0; k < e.n; ++k) {
-		if (e.filter[k] != F_none || e.supporting_reads(k) == 0) continue;
+	parallel_rows(threads, e.n, [&](u32 k) {
+		if (e.filter[k] != F_none || e.supporting_reads(k) == 0) return;
 		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) if (labels[e.list1[p]] == F_multimappers && e.split_reads1[k] > 0) --e.split_reads1[k];
 		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) if (labels[e.list2[p]] == F_multimappers && e.split_reads2[k] > 0) --e.split_reads2[k];
 		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) if (labels[e.listd[p]] == F_multimappers && e.discordant_mates[k] > 0) --e.discordant_mates[k];
 		if (e.supporting_reads(k) == 0) e.filter[k] = F_multimappers;
-	}
+	});
 	log_remaining("Filtering multi-mapping fusions by alignment score and read support");
 }
 
@@ -414,11 +470,23 @@ void pipeline::filter_both_intronic() { // filter_both_intronic.cpp
 // chimeric read count per gene and the expression quantile (filter_in_vitro.cpp:48-83)
 void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold, float quantile_f) {
 	const u32 N = frags.n;
-	reads_by_gene.assign(ref.genes.size(), 0); present.assign(ref.genes.size(), 0);
-	for (u32 i = 0; i < N; ++i) {
-		const size_t a = i, b = (size_t) (frags.n_aln[i] == 2 ? 1 : 2) * N + i;
-		for (u32 g = 0; g < frags.genes_cnt[a]; ++g) { ++reads_by_gene[frags.genes[frags.genes_off[a] + g]]; present[frags.genes[frags.genes_off[a] + g]] = 1; }
-		for (u32 g = 0; g < frags.genes_cnt[b]; ++g) { ++reads_by_gene[frags.genes[frags.genes_off[b] + g]]; present[frags.genes[frags.genes_off[b] + g]] = 1; }
+	const size_t G = ref.genes.size();
+	reads_by_gene.assign(G, 0); present.assign(G, 0);
+	{ // per-thread histograms over the fragments' gene sets, then summed
+		const int T = std::max(1, std::min(threads, (int) (N / 65536 + 1)));
+		std::vector<std::vector<u32> > part(T, std::vector<u32>(G, 0));
+		std::vector<std::thread> pool;
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+			std::vector<u32>& h = part[t];
+			for (size_t i = (size_t) N * t / T; i < (size_t) N * (t + 1) / T; ++i) {
+				const size_t a = i, b = (size_t) (frags.n_aln[i] == 2 ? 1 : 2) * N + i;
+				for (u32 g = 0; g < frags.genes_cnt[a]; ++g) ++h[frags.genes[frags.genes_off[a] + g]];
+				for (u32 g = 0; g < frags.genes_cnt[b]; ++g) ++h[frags.genes[frags.genes_off[b] + g]];
+			}
+		});
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+		for (int t = 0; t < T; ++t) for (size_t g = 0; g < G; ++g) reads_by_gene[g] += part[t][g];
+		for (size_t g = 0; g < G; ++g) present[g] = reads_by_gene[g] > 0;
 	}
 	std::vector<u32> genes;
 	for (u32 g = 0; g < present.size(); ++g) if (present[g]) genes.push_back(g);
@@ -435,11 +503,12 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 	const annot_view an = ref.host_view();
 	const u32 N = frags.n;
 	const frag_view f = frags.view();
-	std::map<std::pair<u32, u32>, unsigned int> exonic_breakpoints;
+	std::vector<u64> exonic_breakpoints; // one (gene, partner) key per exonic, unspliced breakpoint pair, sorted: a count is the width of an equal range
 	for (u32 k = 0; k < ev.n; ++k)
 		if (ev.gene1[k] != ev.gene2[k] && !ev.spliced1(k) && !ev.spliced2(k) && ev.exonic1(k) && ev.exonic2(k) && ev.n_list1(k) + ev.n_list2(k) > 0 && ev.filter[k] != F_merge_adjacent && ev.filter[k] != F_uninteresting_contigs) {
-			++exonic_breakpoints[std::make_pair(ev.gene1[k], ev.gene2[k])]; ++exonic_breakpoints[std::make_pair(ev.gene2[k], ev.gene1[k])];
+			exonic_breakpoints.push_back((u64) ev.gene1[k] << 32 | ev.gene2[k]); exonic_breakpoints.push_back((u64) ev.gene2[k] << 32 | ev.gene1[k]);
 		}
+	parallel_sort(exonic_breakpoints, [](u64 a, u64 b) { return a < b; }, threads);
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
 	find_top_expressed_genes(reads_by_gene, present, threshold, opt.high_expression_quantile); // -Q
 	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
@@ -448,7 +517,7 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 		for (u32 x = 0; x < genes.n; ++x) if (reads_by_gene[genes.v[x]] > highest) { highest = reads_by_gene[genes.v[x]]; gene = genes.v[x]; }
 		return gene;
 	};
-	auto pair_count = [&](u32 a, u32 b) { std::map<std::pair<u32, u32>, unsigned int>::const_iterator it = exonic_breakpoints.find(std::make_pair(a, b)); return it == exonic_breakpoints.end() ? 0u : it->second; };
+	auto pair_count = [&](u32 a, u32 b) { const u64 key = (u64) a << 32 | b; const std::pair<std::vector<u64>::const_iterator, std::vector<u64>::const_iterator> r = std::equal_range(exonic_breakpoints.begin(), exonic_breakpoints.end(), key); return (unsigned int) (r.second - r.first); };
 	parallel_rows(threads, ev.n, [&](u32 k) {
 		const u8 fl = ev.filter[k];
 		if (fl != F_none && !((ev.spliced1(k) || ev.spliced2(k)) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) return;
@@ -566,32 +635,46 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 
 void pipeline::select_best() { // select_best.cpp
 	auto rank = [&](u32 k) { const bool s1 = ev.split_reads1[k] != 0, s2 = ev.split_reads2[k] != 0, d = ev.discordant_mates[k] != 0; return (s1 && s2) ? 3u : ((s1 || s2) && d) ? 2u : (s1 || s2) ? 1u : 0u; };
-	typedef std::tuple<u32, u32, bool, bool> pair_key;
-	std::map<pair_key, u32> best;
+	// candidates of one (gene1, gene2, direction1, direction2) compete in the order the reference visits them (the comparison is not a total order, so the
+	// order matters): sort by (key, iteration rank) instead of the reference's map, then every group is an independent sequential scan
+	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
+	struct entry { u64 key; u32 rank, cand; };
+	std::vector<entry> entries;
 	for (size_t q = 0; q < ev.order.size(); ++q) {
 		const u32 k = ev.order[q];
 		if (ev.filter[k] != F_none) continue;
-		const pair_key key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]);
-		std::map<pair_key, u32>::iterator it = best.find(key);
-		if (it == best.end()) { best[key] = k; continue; }
-		const u32 b = it->second;
-		bool take = false;
-		if (rank(k) > rank(b)) take = true;
-		else if (rank(k) == rank(b)) {
-			if (ev.supporting_reads(k) > ev.supporting_reads(b)) take = true;
-			else if (ev.supporting_reads(k) == ev.supporting_reads(b)) {
-				if ((ev.exonic1(k) && !ev.exonic1(b)) || (ev.exonic2(k) && !ev.exonic2(b))) take = true;
-				else if ((!ev.exonic1(b) || ev.exonic1(k) == ev.exonic1(b)) && (!ev.exonic2(b) || ev.exonic2(k) == ev.exonic2(b))) {
-					if ((ev.dir1[k] == DOWNSTREAM && ev.bp1[k] > ev.bp1[b]) || (ev.dir1[k] == UPSTREAM && ev.bp1[k] < ev.bp1[b])) take = true;
-					else if (ev.bp1[k] == ev.bp1[b]) { if ((ev.dir2[k] == DOWNSTREAM && ev.bp2[k] > ev.bp2[b]) || (ev.dir2[k] == UPSTREAM && ev.bp2[k] < ev.bp2[b])) take = true; }
-				}
-			}
-		}
-		if (take) it->second = k;
+		const entry x = {(u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) (ev.dir1[k] != 0) << 1 | (u64) (ev.dir2[k] != 0), (u32) q, k};
+		entries.push_back(x);
 	}
-	for (u32 k = 0; k < ev.n; ++k) {
-		if (ev.filter[k] != F_none) continue;
-		if (best[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])] != k) ev.filter[k] = F_select_best;
+	parallel_sort(entries, [](const entry& a, const entry& b) { return a.key != b.key ? a.key < b.key : a.rank < b.rank; }, threads);
+	auto challenger_wins = [&](u32 k, u32 b) { // select_best.cpp:22-60
+		if (rank(k) > rank(b)) return true;
+		if (rank(k) != rank(b)) return false;
+		if (ev.supporting_reads(k) > ev.supporting_reads(b)) return true;
+		if (ev.supporting_reads(k) != ev.supporting_reads(b)) return false;
+		if ((ev.exonic1(k) && !ev.exonic1(b)) || (ev.exonic2(k) && !ev.exonic2(b))) return true;
+		if ((!ev.exonic1(b) || ev.exonic1(k) == ev.exonic1(b)) && (!ev.exonic2(b) || ev.exonic2(k) == ev.exonic2(b))) {
+			if ((ev.dir1[k] == DOWNSTREAM && ev.bp1[k] > ev.bp1[b]) || (ev.dir1[k] == UPSTREAM && ev.bp1[k] < ev.bp1[b])) return true;
+			if (ev.bp1[k] == ev.bp1[b]) return (ev.dir2[k] == DOWNSTREAM && ev.bp2[k] > ev.bp2[b]) || (ev.dir2[k] == UPSTREAM && ev.bp2[k] < ev.bp2[b]);
+		}
+		return false;
+	};
+	// a thread takes the groups that START in its slice
+	{
+		const size_t n_entries = entries.size();
+		const int T = std::max(1, std::min(threads, (int) (n_entries / 4096 + 1)));
+		std::vector<std::thread> pool;
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+			size_t x = n_entries * t / T; const size_t stop = n_entries * (t + 1) / T;
+			while (x < stop && x > 0 && entries[x].key == entries[x - 1].key) ++x; // the group belongs to the previous slice
+			while (x < stop) {
+				size_t y = x + 1; u32 best = entries[x].cand;
+				for (; y < n_entries && entries[y].key == entries[x].key; ++y) if (challenger_wins(entries[y].cand, best)) best = entries[y].cand;
+				for (size_t z = x; z < y; ++z) if (entries[z].cand != best) ev.filter[entries[z].cand] = F_select_best;
+				x = y;
+			}
+		});
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 	}
 	log_remaining("Selecting best breakpoints from genes with multiple breakpoints");
 }
