@@ -133,7 +133,7 @@ struct worker {
 	std::unordered_map<std::string, std::vector<u8>, name_hash> pending; // first mate of a proper pair, waiting for the second
 	coverage_windows* cov; // shared by all workers: saturating counters and flags are updated atomically, the result does not depend on the order
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
-	std::string key;
+	std::string key, clip_chars;
 	worker(): cov(NULL), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
 
 	u32 fragment(const std::string& name, bool* created = NULL) {
@@ -274,11 +274,15 @@ struct worker {
 		const u64 contig_len = ref->seq_len[r.tid];
 		// unsigned comparison on purpose (the reference compares an int sum with a size_t)
 		if ((u64) (u32) ((u32) win_end + max_dup + clip_len + 1u) >= contig_len || win_start <= (int) (max_dup + clip_len + 1)) return false;
+		// the clipped bases as characters, decoded once: the window scan below compares them ~10^3 times per read
+		clip_chars.resize(clip_len);
+		for (u32 k = 0; k < clip_len; ++k) clip_chars[k] = nt16_char(r.base_code(clip_pos + k));
+		const char* const clip = clip_chars.data();
 		// can the read simply be extended linearly? then it is no tandem duplication
 		u32 ext_matches = 0;
 		for (u32 k = 0; k < clip_len; ++k) {
 			const i64 g = (i64) ext_start + k;
-			if (g >= 0 && (u64) g < contig_len && contig_seq[g] == nt16_char(r.base_code(clip_pos + k))) ++ext_matches;
+			if (g >= 0 && (u64) g < contig_len && contig_seq[g] == clip[k]) ++ext_matches;
 		}
 		if (1.0 * ext_matches / clip_len >= 0.7f) return false;
 		for (int cp = win_start; cp <= win_end; ++cp) {
@@ -286,7 +290,7 @@ struct worker {
 			i64 t_start = (i64) contig_len; i64 t_end = -1;
 			for (u32 i = 0; i < clip_len; ++i) {
 				const int rp2 = direction == +1 ? (int) i : (int) (clip_len - 1 - i);
-				if (contig_seq[cp + rp2] == nt16_char(r.base_code(clip_pos + rp2))) {
+				if (contig_seq[cp + rp2] == clip[rp2]) {
 					++matches;
 					if (cp + rp2 < t_start) t_start = cp + rp2;
 					if (cp + rp2 > t_end) t_end = cp + rp2;
@@ -691,6 +695,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		if (!prepare_error.empty()) fail(prepare_error);
 		if (c.last) break;
 	}
+	if (trace) fprintf(stderr, "[ingest]   of which inflate %.3f s, record scan + name hashing %.3f s (both overlap with) record processing %.3f s\n", t_inflate, t_scan, stats.t_parse);
 	stats.t_inflate = t_inflate; stats.t_parse += t_scan;
 	{ chunk_t a, b; std::swap(chunks[0], a); std::swap(chunks[1], b); }
 	if (!header_done) fail("failed to read SAM header");
