@@ -200,7 +200,14 @@ ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content, u32* coun
 		const u32 max_all = kmer_threshold(len, kmer_content);
 		const u32 max_1 = kmer_threshold(e1 - s1, kmer_content);
 		const u32 max_2 = kmer_threshold(e2 - s2, kmer_content);
-		for (u32 k = 0; k < 64; ++k) counters[k * stride] = 0;
+		// Counters start at 512 - threshold, so "count >= threshold" is bit 9 of the field: one AND per counted k-mer instead of three compares. A zero
+		// threshold (empty aligned part) fires at the first counted k-mer, as in the reference. Reads beyond 1,500 bases take the plain compares.
+		const bool biased = len <= 1500;
+		const u32 start_value = biased ? (512 - max_all) | (512 - max_1) << 10 | (512 - max_2) << 20 : 0;
+		const u32 reached = 1u << 9 | 1u << 19 | 1u << 29;
+		for (u32 k = 0; k < 64; ++k) counters[k * stride] = start_value;
+		// "pos + 1 >= s && pos < e" as one unsigned comparison: pos - (s - 1) < e - (s - 1)
+		const u32 lo1 = s1 - 1, span1 = e1 + 1 > s1 ? e1 - lo1 : 0, lo2 = s2 - 1, span2 = e2 + 1 > s2 ? e2 - lo2 : 0;
 		// 2-bit code of a base: T=0 G=1 C=2, anything else 3 (filter_mismappers.cpp:33-45), looked up in a 32-bit constant indexed by the nt16 code
 		const u32 code2 = ~(3u << 16 | 2u << 8 | 1u << 4); // entries 8 (T), 4 (G), 2 (C) hold 0, 1, 2 -- every other entry 3
 		const u32 n_words = ((len + 31) / 32) * 4;
@@ -214,10 +221,10 @@ ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content, u32* coun
 			km = (km << 2 | (code2 >> 2 * (word >> (28 - 4 * (b & 7)) & 15) & 3)) & 63;
 			if (km == km_1 || km == km_2) { km_2 = km_1; km_1 = 64; continue; }
 			km_2 = km_1; km_1 = km;
-			const u32 in1 = pos + 1 >= s1 && pos < e1, in2 = pos + 1 >= s2 && pos < e2;
+			const u32 in1 = pos - lo1 < span1, in2 = pos - lo2 < span2;
 			const u32 w = counters[km * stride] + (1u | in1 << 10 | in2 << 20);
 			counters[km * stride] = w;
-			if ((w & 1023) >= max_all || (w >> 10 & 1023) >= max_1 || (w >> 20) >= max_2) return true;
+			if (biased ? (w & reached) != 0 : ((w & 1023) >= max_all || (w >> 10 & 1023) >= max_1 || (w >> 20) >= max_2)) return true;
 		}
 	}
 	return false;
