@@ -239,7 +239,14 @@ def main():
         return
     st, tm = results[-1][3], results[-1][4]
     peak, peak_src = measured_peak()
-    achieved = tm.classify_algorithmic_bytes / (cls_ms * 1e-3) / 1e9
+    cascade_bytes = int(tm.cascade_algorithmic_bytes[0]) + int(tm.cascade_algorithmic_bytes[1])   # of the fragments the two launches actually saw (a shard, in sharded mode)
+    achieved = cascade_bytes / (cls_ms * 1e-3) / 1e9
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the two cascade launches on this workload, from the committed `ncu --set full` capture
+    try:
+        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
+        traffic = t.get(args.workload, {}).get("cascade_dram_bytes_per_step")
+    except Exception:
+        pass
     jobs = 1 if sharded else world
     line = {"metric": metric, "value": n_frag * jobs / (dev_ms * 1e-3), "unit": "fragments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
@@ -250,7 +257,7 @@ def main():
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "read-level cascade: k_for_each<cascade_head_fn> + k_for_each_scratch<cascade_sequences_fn>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(tm.classify_algorithmic_bytes), "kernel_ms": cls_ms,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": cascade_bytes, "kernel_ms": cls_ms,
                          "cascade": {"head_ms": tm.cascade_head_ms, "sequences_ms": tm.cascade_sequences_ms, "queued": int(tm.cascade_queued),
                                      "head_bytes": int(tm.cascade_algorithmic_bytes[0]), "sequences_bytes": int(tm.cascade_algorithmic_bytes[1])},
                          "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,

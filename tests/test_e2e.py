@@ -44,3 +44,17 @@ def test_e2e_cuda_mismapper_heavy(worlds, cuda_lib, tmp_path):
 @pytest.mark.gpu
 def test_e2e_cuda(worlds, cuda_lib, tmp_path):
     check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
+
+
+@pytest.mark.gpu
+def test_cli_cuda(worlds, tmp_path):
+    """The drop-in executable: same command line as the reference (run_arriba.sh:38-48), byte-identical files."""
+    import subprocess
+    from arriba_b200 import _build
+    w = worlds.get("small")
+    out = str(tmp_path / "fusions.tsv"); disc = str(tmp_path / "fusions.discarded.tsv")
+    r = subprocess.run([_build.build_cli(), "-x", w.prefix + ".bam", "-g", w.prefix + ".gtf", "-a", w.prefix + ".fa", "-o", out, "-O", disc, "-f", "blacklist", "-@", "4"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out, "rb").read() == open(os.path.join(w.outdir, "fusions.tsv"), "rb").read()
+    assert open(disc, "rb").read() == open(os.path.join(w.outdir, "fusions.discarded.tsv"), "rb").read()
