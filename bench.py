@@ -151,6 +151,7 @@ def main():
         print(json.dumps(line))
         return
 
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only (NCCL prints its version banner where NCCL_DEBUG=VERSION)
     import torch
     from arriba_b200 import lib as L, _build
     if not torch.cuda.is_available():
