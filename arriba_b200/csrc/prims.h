@@ -46,12 +46,14 @@ struct exec_ctx {
 // Stage-local scratch buffers come and go many times per run; cudaMalloc/cudaFree would serialise the stream each time (cudaFree synchronises the
 // device, cudaMalloc costs up to a millisecond). Blocks are carved out of large slabs, one list of free blocks per size class (steps of at most 25 %),
 // per device; slabs go back to the driver only through pool_trim() (arb_release_device_memory) or when an allocation fails.
+// size classes of the pool: steps of at most 25 %, every class a multiple of 512 bytes because blocks are carved back to back out of a slab
+inline size_t pool_size_class(size_t bytes) { size_t c = 512; while (c < bytes) { c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); c = (c + 511) & ~(size_t) 511; } return c; }
 #ifdef ARB_DEVICE_BUILD
 struct device_pool {
 	struct slab { char* base; size_t size, used; };
 	struct per_device { std::vector<std::pair<size_t, void*> > free_blocks; std::vector<slab> slabs; size_t outstanding; per_device(): outstanding(0) {} };
 	std::vector<per_device> dev; std::mutex lock;
-	static size_t size_class(size_t bytes) { size_t c = 512; while (c < bytes) { c += c < (1u << 20) ? c : c / 4 >= (1u << 20) ? c / 4 : (1u << 20); c = (c + 511) & ~(size_t) 511; } return c; } // multiples of 512: blocks are carved back to back
+	static size_t size_class(size_t bytes) { return pool_size_class(bytes); }
 	per_device& current() { int d = 0; ARB_CUDA_CHECK(cudaGetDevice(&d)); if ((size_t) d >= dev.size()) dev.resize((size_t) d + 1); return dev[(size_t) d]; }
 	void* get(size_t bytes, size_t& granted) {
 		std::lock_guard<std::mutex> g(lock);

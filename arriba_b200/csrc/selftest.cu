@@ -8,6 +8,9 @@ struct u32_key_ops { const u32* k; ARB_HD u64 hash(u32 i) const { u64 h = k[i] *
 
 extern "C" {
 
+uint64_t arb_selftest_pool_size_class(uint64_t bytes) { return pool_size_class((size_t) bytes); }
+
+
 int arb_selftest_scan(const uint32_t* in, uint32_t* out /* n+1 */, uint32_t n) {
 	try {
 		exec_ctx ex;

@@ -48,3 +48,17 @@ def test_prims_hostsim(hostsim_lib):
 @pytest.mark.gpu
 def test_prims_cuda(cuda_lib):
     check_prims(cuda_lib, [0, 1, 2, 33, 255, 256, 2047, 2048, 2049, 8192, 8193, 100000, 3000001])
+
+
+def test_pool_size_classes(hostsim_lib):
+    """Blocks are carved back to back out of slabs: every size class must keep the next block 512-byte aligned (a 20,000,000-byte class once did not)."""
+    import ctypes as C
+    lib = L.load(hostsim_lib)
+    lib.arb_selftest_pool_size_class.argtypes = [C.c_uint64]; lib.arb_selftest_pool_size_class.restype = C.c_uint64
+    rng = np.random.default_rng(3)
+    sizes = np.unique(np.concatenate([np.arange(1, 5000, 37), (10 ** rng.uniform(3, 10.5, 4000)).astype(np.int64), 2 ** np.arange(9, 35)]))
+    prev = 0
+    for s in sizes:
+        c = int(lib.arb_selftest_pool_size_class(int(s)))
+        assert c >= s and c % 512 == 0 and c <= max(512, int(s) * 2), (s, c)
+        assert c >= prev; prev = c
