@@ -88,8 +88,24 @@ ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
 //  * spawn: in the cooperative passes a continuation (the recursive call at a splice site or at the first mismatch) gets `spawn_budget` steps; one that
 //    runs out undecided is written to `queue` as a task of its own and the caller goes on as if it had failed -- the next round deals the task's own
 //    hits to a group of lanes. A read stuck in a tandem repeat has thousands of hits per position on both recursion levels.
+//  * memo: a continuation is a pure function of (score, read position, deletions left, lower bound of the hits) and it only ever looks at hits at or
+//    above the lower bound. Once it has failed for a bound g it fails for every bound >= g. In a tandem repeat thousands of hits reach the same
+//    (score, read position) with ascending bounds: the first one pays, the others are answered from a small per-thread table.
 struct realign_task { u32 item; u16 gene_k; u8 segment, rc; i32 score, read_pos, gene_pos, max_deletions; };
+struct realign_memo { i32 score, read_pos, max_deletions, fail_from; };
 struct realign_ctl {
+	enum { MEMO_SLOTS = 16 };
+	realign_memo memo[MEMO_SLOTS]; u32 memo_n, memo_next;
+	ARB_HD void forget() { memo_n = 0; memo_next = 0; } // new gene window or strand: different function
+	ARB_HD bool known_to_fail(int score, int read_pos, int max_deletions, int gene_pos) const {
+		for (u32 k = 0; k < memo_n; ++k) if (memo[k].score == score && memo[k].read_pos == read_pos && memo[k].max_deletions == max_deletions) return gene_pos >= memo[k].fail_from;
+		return false;
+	}
+	ARB_HD void remember_failure(int score, int read_pos, int max_deletions, int gene_pos) {
+		for (u32 k = 0; k < memo_n; ++k) if (memo[k].score == score && memo[k].read_pos == read_pos && memo[k].max_deletions == max_deletions) { if (gene_pos < memo[k].fail_from) memo[k].fail_from = gene_pos; return; }
+		const u32 slot = memo_n < MEMO_SLOTS ? memo_n++ : (memo_next++ % MEMO_SLOTS);
+		memo[slot].score = score; memo[slot].read_pos = read_pos; memo[slot].max_deletions = max_deletions; memo[slot].fail_from = gene_pos;
+	}
 	int budget; bool limited;
 	u32 lanes, lane, counter;
 	const volatile u8* stop;
@@ -103,7 +119,7 @@ struct realign_ctl {
 		return true;
 	}
 };
-ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.queue = 0; c.n_queue = 0; c.queue_cap = 0; return c; }
+ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.forget(); c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.queue = 0; c.n_queue = 0; c.queue_cap = 0; return c; }
 
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
 ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_deletions, const realign_env& env, realign_ctl& ctl, bool top) {
@@ -115,16 +131,19 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 	int budget = ctl.budget; // spent locally, written back on every way out
 	#define REALIGN_RETURN(x) do { ctl.budget = budget; return (x); } while (0)
 	#define REALIGN_CONTINUATION(sc, rp, gp, md) { \
-		if (top && ctl.spawn_budget > 0) { /* bounded attempt; undecided -> a task for the next round */ \
+		if (ctl.known_to_fail(sc, rp, md, gp)) { /* an identical continuation with a lower or equal bound already failed (or is queued as a task) */ } \
+		else if (top && ctl.spawn_budget > 0) { /* bounded attempt; undecided -> a task for the next round */ \
 			const bool was_limited = ctl.limited; ctl.limited = true; ctl.budget = ctl.spawn_budget; \
 			bool found = realign(sc, rp, gp, md, env, ctl, false); \
 			const bool ran_out = ctl.budget < 0; ctl.limited = was_limited; \
 			if (!found && ran_out && !ctl.spawn(sc, rp, gp, md)) { ctl.budget = 0; found = realign(sc, rp, gp, md, env, ctl, false); } \
 			if (found) return true; \
+			ctl.remember_failure(sc, rp, md, gp); \
 		} else { \
 			ctl.budget = budget; \
 			if (realign(sc, rp, gp, md, env, ctl, false)) return true; \
 			budget = ctl.budget; \
+			if (!(limited && budget < 0)) ctl.remember_failure(sc, rp, md, gp); \
 		} }
 	if (!(read_pos + 8 < len && read_pos + min_score <= len + score + 16)) return false;
 	u32 km = 0;
@@ -224,9 +243,9 @@ ARB_HD bool realign_both_strands(const realign_segment& s, u32 segment, int max_
 		realign_env env;
 		if (!segment_env(s, k, max_mate_gap, an, ix, sp, env)) continue;
 		ctl.proto.segment = (u8) segment; ctl.proto.gene_k = (u16) k;
-		ctl.proto.rc = 0;
+		ctl.proto.rc = 0; ctl.forget();
 		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
-		env.rc = !s.read.rc; ctl.proto.rc = 1;
+		env.rc = !s.read.rc; ctl.proto.rc = 1; ctl.forget();
 		if (realign(0, 0, env.wstart, 1, env, ctl, true)) return true;
 	}
 	return false;
