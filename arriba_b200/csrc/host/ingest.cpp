@@ -835,8 +835,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	}
 	stats.t_finalize = now_s() - tf;
 	lap("multimapper flags");
-	parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) { worker empty; std::swap(workers[t], empty); } }); // unmap the per-worker pools concurrently
-	{ std::vector<worker>().swap(workers); }
+	// the per-worker pools (gigabytes) are handed to a helper thread: unmapping them costs most of a second and nothing below needs to wait for it
+	{
+		std::vector<worker>* doomed = new std::vector<worker>();
+		doomed->swap(workers);
+		std::thread([doomed]() { delete doomed; }).detach();
+	}
 	lap("free worker state");
 }
 

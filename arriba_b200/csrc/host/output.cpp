@@ -5,6 +5,7 @@
 #include "pipeline.h"
 #include "../annot_hd.h"
 #include <algorithm>
+#include <atomic>
 #include <fcntl.h>
 #include <unistd.h>
 #include <chrono>
@@ -619,36 +620,49 @@ struct writer {
 		const std::string header = "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n";
 		// rows are independent: every host thread formats a slice of the row list, then writes it at its offset of the file (the discarded file of a large
 		// sample is a gigabyte; one writer would spend seconds copying into the page cache)
-		const int T = std::max(1, std::min(p.threads, (int) (rows.size() / 64 + 1)));
-		std::vector<std::string> slices(T), warnings(T); std::vector<std::string> errors(T);
+		// Rows cost very different amounts (the best-supported fusions come first and carry hundreds of reads each): threads draw small chunks of rows from
+		// a shared counter; every chunk is formatted into its own string and later written at its offset of the file.
+		const size_t CHUNK = 32;
+		const size_t n_chunks = (rows.size() + CHUNK - 1) / CHUNK;
+		const int T = std::max(1, std::min(p.threads, (int) (n_chunks ? n_chunks : 1)));
+		std::vector<std::string> slices(n_chunks), warnings(n_chunks); std::vector<std::string> errors(T);
 		{
+			std::atomic<size_t> next_chunk(0);
 			std::vector<std::thread> pool;
 			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
-				warning_sink = &warnings[t]; // warnings of a slice are printed after it, in row order like the reference's
-				try { std::ostringstream os; for (size_t x = rows.size() * t / T; x < rows.size() * (t + 1) / T; ++x) format_row(os, rows[x], extra_info); slices[t] = os.str(); }
-				catch (const std::exception& ex) { errors[t] = ex.what(); }
+				try {
+					for (;;) {
+						const size_t c = next_chunk.fetch_add(1);
+						if (c >= n_chunks) break;
+						warning_sink = &warnings[c]; // warnings of a chunk are printed after it, in row order like the reference's
+						std::ostringstream os;
+						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(os, rows[x], extra_info);
+						slices[c] = os.str();
+					}
+				} catch (const std::exception& ex) { errors[t] = ex.what(); }
+				warning_sink = NULL;
 			});
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 		}
 		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 		const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
 		if (fd < 0) throw std::runtime_error("failed to open output file");
-		std::vector<u64> at(T + 1); at[0] = header.size(); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + slices[t].size();
+		std::vector<u64> at(n_chunks + 1); at[0] = header.size(); for (size_t c = 0; c < n_chunks; ++c) at[c + 1] = at[c] + slices[c].size();
 		auto write_at = [&](const char* data, size_t n, u64 off) { while (n > 0) { const ssize_t w = ::pwrite(fd, data, n, (off_t) off); if (w <= 0) return false; data += w; n -= (size_t) w; off += (u64) w; } return true; };
 		bool ok = true;
 		if (::lseek(fd, 0, SEEK_CUR) == (off_t) -1) { // not seekable (a pipe, /dev/stdout): one sequential writer
 			auto write_all = [&](const char* data, size_t n) { while (n > 0) { const ssize_t w = ::write(fd, data, n); if (w <= 0) return false; data += w; n -= (size_t) w; } return true; };
 			ok = write_all(header.data(), header.size());
-			for (int t = 0; t < T && ok; ++t) ok = write_all(slices[t].data(), slices[t].size());
+			for (size_t c = 0; c < n_chunks && ok; ++c) ok = write_all(slices[c].data(), slices[c].size());
 		} else {
 			ok = write_at(header.data(), header.size(), 0);
 			std::vector<std::thread> pool; std::vector<u8> good(T, 1);
-			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { good[t] = write_at(slices[t].data(), slices[t].size(), at[t]); });
+			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (size_t c = n_chunks * t / T; c < n_chunks * (t + 1) / T; ++c) if (!write_at(slices[c].data(), slices[c].size(), at[c])) good[t] = 0; });
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 			for (int t = 0; t < T; ++t) ok = ok && good[t];
 		}
 		ok = ::close(fd) == 0 && ok;
-		for (int t = 0; t < T; ++t) if (!warnings[t].empty()) std::cerr << warnings[t] << std::flush;
+		for (size_t c = 0; c < n_chunks; ++c) if (!warnings[c].empty()) std::cerr << warnings[c] << std::flush;
 		if (!ok) throw std::runtime_error("failed to write to file");
 	}
 };
