@@ -18,10 +18,11 @@ engine::engine(): device(0), table_n(0), table_k(0), has_contigs(false), has_ann
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
-	mismap_budget = 4096; mismap_lanes = 1024; mismap_spawn_budget = 512; mismap_task_lanes = 32;
+	mismap_budget = 4096; mismap_lanes = 1024; mismap_spawn_budget = 0; mismap_task_lanes = 32;
 	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
 	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));
 	if (const char* s = getenv("ARB_MISMAP_SPAWN")) mismap_spawn_budget = atoi(s);
+	mismap_table_slots = 256; if (const char* s = getenv("ARB_MISMAP_TABLE")) mismap_table_slots = (u32) std::max(1, atoi(s)); // continuation registry slots per cooperative item
 	mismap_min_blocks = 4; if (const char* s = getenv("ARB_MISMAP_OCC")) mismap_min_blocks = atoi(s); // resident 256-thread blocks per SM the re-alignment kernels are compiled for
 	if (const char* s = getenv("ARB_MISMAP_TASK_LANES")) mismap_task_lanes = (u32) std::max(1, atoi(s));
 #ifdef ARB_DEVICE_BUILD

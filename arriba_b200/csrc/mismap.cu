@@ -105,31 +105,31 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	timings.mismappers_pass1_ms = t1.stop();
 	u32 H = 0; n_heavy.download(ex, &H, 1);
 	stage_timer t2(ex);
-	// pass 2 and the task rounds: continuations that are expensive on their own travel through two alternating queues
-	const u32 queue_cap = H ? 1u << 22 : 1;
-	dbuf<realign_task> queue_a(queue_cap), queue_b(queue_cap); dbuf<u32> n_tasks(1);
-	n_tasks.zero(ex, 1);
+	// pass 2 and the task rounds: continuations are registered per item (mismap_hd.h, realign_ctl::table) and run as tasks, one per distinct continuation
+	const u32 K = mismap_table_slots;
+	if ((u64) H * K >= 0x80000000ull) throw arb_error("too many reads need the cooperative re-alignment");
+	dbuf<continuation_slot> tables((size_t) H * K + 1); dbuf<realign_task> tasks((size_t) H * K + 1); dbuf<u32> n_tasks(1);
+	if (H) { continuation_init_fn ci = {tables.ptr()}; for_each(ex, H * K, ci); }
 	for (u32 done = 0; done < H; ) { // launches of at most 2^31 threads
 		const u32 batch = std::min<u32>(H - done, 0x80000000u / mismap_lanes);
-		mismap_heavy_fn mh = {items, heavy.ptr() + done, mismap_lanes, mismap_spawn_budget, queue_a.ptr(), n_tasks.ptr(), queue_cap};
+		mismap_heavy_fn mh = {items, heavy.ptr() + done, mismap_lanes, mismap_spawn_budget, tables.ptr() + (size_t) done * K, K};
 		launch(batch * mismap_lanes, mh);
 		done += batch;
 	}
 	u64 spawned = 0; u32 rounds = 0;
-	realign_task* from = queue_a.ptr(); realign_task* to = queue_b.ptr();
-	for (;;) {
-		u32 Q = 0; if (H) n_tasks.download(ex, &Q, 1);
-		Q = std::min(Q, queue_cap);
+	while (H) {
+		n_tasks.zero(ex, 1);
+		continuation_collect_fn cc = {tables.ptr(), K, heavy.ptr(), item_frag.ptr(), mism.ptr(), tasks.ptr(), n_tasks.ptr()};
+		for_each(ex, H * K, cc);
+		u32 Q = 0; n_tasks.download(ex, &Q, 1);
 		if (Q == 0) break;
 		spawned += Q; ++rounds;
-		n_tasks.zero(ex, 1);
 		for (u32 done = 0; done < Q; ) {
 			const u32 batch = std::min<u32>(Q - done, 0x80000000u / mismap_task_lanes);
-			mismap_task_fn mt = {items, from + done, mismap_task_lanes, mismap_spawn_budget, to, n_tasks.ptr(), queue_cap};
+			mismap_task_fn mt = {items, tasks.ptr() + done, mismap_task_lanes, mismap_spawn_budget, tables.ptr(), K};
 			launch(batch * mismap_task_lanes, mt);
 			done += batch;
 		}
-		std::swap(from, to);
 	}
 	timings.mismapper_tasks = spawned; timings.mismapper_rounds = rounds;
 	timings.mismappers_pass2_ms = t2.stop();

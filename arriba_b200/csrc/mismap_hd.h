@@ -85,13 +85,24 @@ ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
 //  * budget: the one-thread-per-item pass gives up after `budget` steps (a few reads that fall into tandem repeats cost 10^5 times the median);
 //  * lanes/lane/counter: the cooperative pass deals the top-level hits round-robin to `lanes` threads of the same item;
 //  * stop: set as soon as any lane (or any other item of the same fragment) found a placement.
-//  * spawn: in the cooperative passes a continuation (the recursive call at a splice site or at the first mismatch) gets `spawn_budget` steps; one that
-//    runs out undecided is written to `queue` as a task of its own and the caller goes on as if it had failed -- the next round deals the task's own
-//    hits to a group of lanes. A read stuck in a tandem repeat has thousands of hits per position on both recursion levels.
+//  * table: in the cooperative passes a continuation (the recursive call at a splice site or at the first mismatch) is not run by the thread that meets
+//    it. It is REGISTERED in a small hash table of its item under (segment, gene, strand, score, read position, deletions left) with the smallest lower
+//    bound requested so far, and the caller goes on as if it had failed (valid: the answer is an OR). After the pass, every entry whose bound went down
+//    becomes one task; a group of lanes deals that task's hits and registers what IT cannot finish. A continuation only looks at hits at or above its
+//    bound, so the entry with the smallest bound answers for all the others: a read in a tandem repeat reaches the same (score, read position) from
+//    thousands of hits, and that is one task instead of thousands of identical searches.
 //  * memo: a continuation is a pure function of (score, read position, deletions left, lower bound of the hits) and it only ever looks at hits at or
 //    above the lower bound. Once it has failed for a bound g it fails for every bound >= g. In a tandem repeat thousands of hits reach the same
 //    (score, read position) with ascending bounds: the first one pays, the others are answered from a small per-thread table.
-struct realign_task { u32 item; u16 gene_k; u8 segment, rc; i32 score, read_pos, gene_pos, max_deletions; };
+struct realign_task { u32 item; u16 gene_k; u8 segment, rc; i32 score, read_pos, gene_pos, max_deletions; u32 item_slot; };
+struct continuation_slot { u64 key; i32 want /* smallest lower bound requested */, done /* bound already turned into a task */; };
+ARB_HD u64 continuation_key(const realign_task& t) { // never 0
+	return 1ull << 63 | (u64) t.segment << 51 | (u64) t.rc << 50 | (u64) (u32) t.max_deletions << 48 | (u64) t.gene_k << 32 | (u64) (u16) (t.score + 32768) << 16 | (u64) (u16) t.read_pos;
+}
+ARB_HD void continuation_unpack(u64 key, realign_task& t) {
+	t.segment = (u8) (key >> 51 & 1); t.rc = (u8) (key >> 50 & 1); t.max_deletions = (i32) (key >> 48 & 3); t.gene_k = (u16) (key >> 32);
+	t.score = (i32) (u16) (key >> 16) - 32768; t.read_pos = (i32) (u16) key;
+}
 struct realign_memo { i32 score, read_pos, max_deletions, fail_from; };
 struct realign_ctl {
 	enum { MEMO_SLOTS = 16 };
@@ -109,17 +120,22 @@ struct realign_ctl {
 	int budget; bool limited;
 	u32 lanes, lane, counter;
 	const volatile u8* stop;
-	int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap; realign_task proto; // proto: item / segment / gene / strand of the running alignment
+	int spawn_budget; continuation_slot* table; u32 table_slots; realign_task proto; // table: the item's registry; proto: item / segment / gene / strand of the running alignment
 	ARB_HD bool exhausted() const { return limited && budget < 0; }
-	ARB_HD bool spawn(int score, int read_pos, int gene_pos, int max_deletions) {
-		const u32 slot = atomic_add_u32(n_queue, 1);
-		if (slot >= queue_cap) return false; // queue full: the caller runs the continuation itself
-		realign_task t = proto; t.score = score; t.read_pos = read_pos; t.gene_pos = gene_pos; t.max_deletions = max_deletions;
-		queue[slot] = t;
-		return true;
+	ARB_HD bool spawn(int score, int read_pos, int gene_pos, int max_deletions) { // registers the continuation; false if the item's table is full (the caller then runs it itself)
+		if (score < -32768 || score > 32767 || read_pos < 0 || read_pos > 65535) return false;
+		realign_task t = proto; t.score = score; t.read_pos = read_pos; t.max_deletions = max_deletions;
+		const u64 key = continuation_key(t);
+		u64 h = key * 0x9E3779B97F4A7C15ULL; h ^= h >> 32;
+		for (u32 probe = 0; probe < table_slots; ++probe) {
+			continuation_slot& s = table[(h + probe) % table_slots];
+			const u64 seen = atomic_cas_u64(&s.key, 0, key);
+			if (seen == 0 || seen == key) { atomic_min_i32(&s.want, gene_pos); return true; }
+		}
+		return false;
 	}
 };
-ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.forget(); c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.queue = 0; c.n_queue = 0; c.queue_cap = 0; return c; }
+ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.forget(); c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.table = 0; c.table_slots = 0; return c; }
 
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
 ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_deletions, const realign_env& env, realign_ctl& ctl, bool top) {
@@ -132,11 +148,14 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 	#define REALIGN_RETURN(x) do { ctl.budget = budget; return (x); } while (0)
 	#define REALIGN_CONTINUATION(sc, rp, gp, md) { \
 		if (ctl.known_to_fail(sc, rp, md, gp)) { /* an identical continuation with a lower or equal bound already failed (or is queued as a task) */ } \
-		else if (top && ctl.spawn_budget > 0) { /* bounded attempt; undecided -> a task for the next round */ \
-			const bool was_limited = ctl.limited; ctl.limited = true; ctl.budget = ctl.spawn_budget; \
-			bool found = realign(sc, rp, gp, md, env, ctl, false); \
-			const bool ran_out = ctl.budget < 0; ctl.limited = was_limited; \
-			if (!found && ran_out && !ctl.spawn(sc, rp, gp, md)) { ctl.budget = 0; found = realign(sc, rp, gp, md, env, ctl, false); } \
+		else if (top && ctl.table) { /* cooperative passes: optional bounded attempt, then the item's registry */ \
+			bool found = false, undecided = true; \
+			if (ctl.spawn_budget > 0) { \
+				const bool was_limited = ctl.limited; ctl.limited = true; ctl.budget = ctl.spawn_budget; \
+				found = realign(sc, rp, gp, md, env, ctl, false); \
+				undecided = !found && ctl.budget < 0; ctl.limited = was_limited; \
+			} \
+			if (!found && undecided && !ctl.spawn(sc, rp, gp, md)) { ctl.budget = 0; found = realign(sc, rp, gp, md, env, ctl, false); } \
 			if (found) return true; \
 			ctl.remember_failure(sc, rp, md, gp); \
 		} else { \
@@ -338,13 +357,13 @@ struct mismap_item_fn {
 #endif
 	}
 };
-// pass 2: `lanes` threads per queued item share the top-level k-mer hits; continuations that are expensive themselves become tasks
+// pass 2: `lanes` threads per queued item share the top-level k-mer hits; continuations go to the item's registry
 struct mismap_heavy_fn {
-	mismap_items it; const u32* heavy; u32 lanes; int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap;
+	mismap_items it; const u32* heavy; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots;
 	ARB_HD void operator()(u32 t) const {
-		const u32 j = heavy[t / lanes], i = it.item_frag[j];
+		const u32 slot = t / lanes, j = heavy[slot], i = it.item_frag[j];
 		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
-		ctl.spawn_budget = spawn_budget; ctl.queue = queue; ctl.n_queue = n_queue; ctl.queue_cap = queue_cap;
+		ctl.spawn_budget = spawn_budget; ctl.table = tables + (size_t) slot * table_slots; ctl.table_slots = table_slots; ctl.proto.item_slot = slot;
 		if (*ctl.stop) return;
 		if (it.evaluate(j, ctl, false)) it.mismapper[i] = 1;
 #ifdef ARB_COST_PROBE
@@ -352,14 +371,29 @@ struct mismap_heavy_fn {
 #endif
 	}
 };
-// task rounds: `lanes` threads per queued continuation; what they cannot finish goes to the queue of the next round
+struct continuation_init_fn { continuation_slot* tables; ARB_HD void operator()(u32 k) const { tables[k].key = 0; tables[k].want = 0x7fffffff; tables[k].done = 0x7fffffff; } };
+// between rounds: every registered continuation whose bound went down since it last ran becomes a task
+struct continuation_collect_fn {
+	continuation_slot* tables; u32 table_slots; const u32* heavy; const u32* item_frag; const u8* mismapper; realign_task* tasks; u32* n_tasks;
+	ARB_HD void operator()(u32 k) const {
+		continuation_slot& s = tables[k];
+		if (s.key == 0 || s.want >= s.done) return;
+		s.done = s.want;
+		const u32 slot = k / table_slots, j = heavy[slot];
+		if (mismapper[item_frag[j]]) return; // already decided
+		realign_task t; t.item = j; t.item_slot = slot; t.gene_pos = s.want;
+		continuation_unpack(s.key, t);
+		tasks[append_slot(n_tasks)] = t;
+	}
+};
+// task rounds: `lanes` threads per registered continuation
 struct mismap_task_fn {
-	mismap_items it; const realign_task* tasks; u32 lanes; int spawn_budget; realign_task* queue; u32* n_queue; u32 queue_cap;
+	mismap_items it; const realign_task* tasks; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots;
 	ARB_HD void operator()(u32 t) const {
 		const realign_task task = tasks[t / lanes];
 		const u32 i = it.item_frag[task.item];
 		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
-		ctl.spawn_budget = spawn_budget; ctl.queue = queue; ctl.n_queue = n_queue; ctl.queue_cap = queue_cap; ctl.proto = task;
+		ctl.spawn_budget = spawn_budget; ctl.table = tables + (size_t) task.item_slot * table_slots; ctl.table_slots = table_slots; ctl.proto = task;
 		if (*ctl.stop) return;
 		const realign_segment s = it.segment(task.item, task.segment);
 		realign_env env;

@@ -227,6 +227,20 @@ ARB_HD u32 append_slot(u32* counter) {
 	return (*counter)++;
 #endif
 }
+ARB_HD u64 atomic_cas_u64(u64* p, u64 expected, u64 desired) {
+#ifdef __CUDA_ARCH__
+	return (u64) atomicCAS((unsigned long long*) p, (unsigned long long) expected, (unsigned long long) desired);
+#else
+	const u64 old = *p; if (old == expected) *p = desired; return old;
+#endif
+}
+ARB_HD i32 atomic_min_i32(i32* p, i32 v) {
+#ifdef __CUDA_ARCH__
+	return atomicMin(p, v);
+#else
+	const i32 old = *p; if (v < old) *p = v; return old;
+#endif
+}
 ARB_HD u32 atomic_or_u32(u32* p, u32 v) {
 #ifdef __CUDA_ARCH__
 	return atomicOr(p, v);

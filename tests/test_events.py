@@ -84,7 +84,15 @@ def test_events_hostsim_cooperative_realignment(worlds, hostsim_lib, monkeypatch
     p = check_events(worlds.get("cfg5", **CFG5), hostsim_lib, keep=True)
     tm = p.context().timings(); p.close()
     assert tm.mismapper_heavy_items > 0.2 * tm.mismapper_items
-    assert tm.mismapper_tasks > 1000 and tm.mismapper_rounds >= 2   # continuations of continuations were queued as well
+    assert tm.mismapper_tasks > 1000 and tm.mismapper_rounds >= 2   # continuations of continuations were registered as well
+
+
+@pytest.mark.parametrize("spawn,table", [("0", "256"), ("0", "3"), ("5", "1")])
+def test_events_hostsim_continuation_registry(worlds, hostsim_lib, monkeypatch, spawn, table):
+    """No bounded attempts (every continuation is registered), and registries so small that most registrations fail over to the in-line search."""
+    monkeypatch.setenv("ARB_MISMAP_BUDGET", "24"); monkeypatch.setenv("ARB_MISMAP_LANES", "5")
+    monkeypatch.setenv("ARB_MISMAP_SPAWN", spawn); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", "4"); monkeypatch.setenv("ARB_MISMAP_TABLE", table)
+    check_events(worlds.get("cfg5", **CFG5), hostsim_lib)
 
 
 @pytest.mark.gpu
@@ -93,7 +101,7 @@ def test_events_cuda_mismapper_heavy(worlds, cuda_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("budget,lanes,spawn,task_lanes", [("16", "32", "4", "32"), ("200", "256", "0", "1"), ("0", "1", "0", "1"), ("64", "8", "16", "5")])
+@pytest.mark.parametrize("budget,lanes,spawn,task_lanes", [("16", "32", "4", "32"), ("200", "256", "0", "32"), ("0", "1", "0", "1"), ("64", "8", "16", "5")])
 def test_events_cuda_cooperative_realignment(worlds, cuda_lib, monkeypatch, budget, lanes, spawn, task_lanes):
     monkeypatch.setenv("ARB_MISMAP_BUDGET", budget); monkeypatch.setenv("ARB_MISMAP_LANES", lanes)
     monkeypatch.setenv("ARB_MISMAP_SPAWN", spawn); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", task_lanes)
