@@ -650,12 +650,63 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		double tp = now_s();
 		std::vector<u64>& rec_off = c.rec_off; std::vector<u8>& rec_shard = c.rec_shard;
 		rec_off.clear();
-		while (p + 4 <= buf.size()) {
-			const u32 bs = rd32(buf.data() + p);
-			if (p + 4 + bs > buf.size()) break;
-			if (bs < 33) fail("failed to load alignments");
-			rec_off.push_back(p);
-			p += 4 + bs;
+		{
+			// A record can only be found from the one before it. To walk the chain on all threads, every piece of the buffer guesses its first record
+			// (first offset from which a few consecutive records look sane) and hops from there; the guesses are then VERIFIED: the chain of piece s must
+			// arrive exactly at the guess of piece s+1. Where it does not, the walk simply continues serially through the next piece.
+			const u8* const B = buf.data(); const size_t end = buf.size();
+			const i32 n_ref = (i32) tid_to_contig.size();
+			auto plausible = [&](size_t q) { // a BAM record could start at q (SAMv1 4.2); a necessary condition only
+				if (q + 36 > end) return false;
+				const u32 bs = rd32(B + q);
+				if (bs < 33 || bs > (1u << 26) || q + 4 + bs > end) return false;
+				const i32 tid = (i32) rd32(B + q + 4), pos = (i32) rd32(B + q + 8), mtid = (i32) rd32(B + q + 24), mpos = (i32) rd32(B + q + 28);
+				const u32 lq = B[q + 12], nc = rd16(B + q + 16); const i32 ls = (i32) rd32(B + q + 20);
+				if (tid < -1 || tid >= n_ref || mtid < -1 || mtid >= n_ref || pos < -1 || mpos < -1 || lq == 0 || ls < 0) return false;
+				if (32ull + lq + 4ull * nc + ((u64) ls + 1) / 2 + (u64) ls > bs) return false;
+				return B[q + 36 + lq - 1] == 0;
+			};
+			const size_t span = end > p ? end - p : 0;
+			const size_t min_span = getenv("ARB_SCAN_MIN_BYTES") ? (size_t) atol(getenv("ARB_SCAN_MIN_BYTES")) : (size_t) 16 << 20; // test hook
+			const int pieces = span > min_span ? T : 1;
+			std::vector<size_t> guess(pieces + 1, end), stop_at(pieces, 0);
+			std::vector<std::vector<u64> > found(pieces);
+			guess[0] = p;
+			auto hop = [&](size_t q, size_t limit, std::vector<u64>& out) { // records starting before `limit`; returns where the chain stands afterwards
+				while (q < limit && q + 4 <= end) {
+					const u32 bs = rd32(B + q);
+					if (q + 4 + bs > end) break;
+					if (bs < 33) fail("failed to load alignments");
+					out.push_back(q);
+					q += 4 + bs;
+				}
+				return q;
+			};
+			if (pieces > 1) {
+				parallel_for(T, (size_t) pieces, [&](int, size_t lo, size_t hi) {
+					for (size_t s = lo; s < hi; ++s) {
+						if (s > 0) { // guess: first offset of the piece from which three records in a row look sane
+							size_t q = p + span * s / pieces; const size_t give_up = std::min(end, q + (4u << 20));
+							for (; q < give_up; ++q) {
+								if (!plausible(q)) continue;
+								const size_t q2 = q + 4 + rd32(B + q); if (q2 < end && !plausible(q2)) continue;
+								const size_t q3 = q2 < end ? q2 + 4 + rd32(B + q2) : end; if (q3 < end && q3 + 36 <= end && !plausible(q3)) continue;
+								break;
+							}
+							guess[s] = q < give_up ? q : end;
+						}
+					}
+				});
+				parallel_for(T, (size_t) pieces, [&](int, size_t lo, size_t hi) { for (size_t s = lo; s < hi; ++s) if (guess[s] < end) stop_at[s] = hop(guess[s], guess[s + 1], found[s]); else stop_at[s] = end; });
+			}
+			// stitch: follow the true chain; a piece whose guess the chain hits exactly contributes its whole list
+			size_t q = p;
+			for (int s = 0; s < pieces; ++s) {
+				if (pieces > 1 && q == guess[s] && guess[s] < end) { rec_off.insert(rec_off.end(), found[s].begin(), found[s].end()); q = stop_at[s]; }
+				else q = hop(q, pieces > 1 ? guess[s + 1] : end, rec_off); // wrong or missing guess: walk this stretch
+			}
+			q = hop(q, end, rec_off); // whatever lies beyond the last verified piece
+			p = q;
 		}
 		c.consumed = p;
 		rec_shard.resize(rec_off.size());
