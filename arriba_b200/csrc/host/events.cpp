@@ -14,6 +14,7 @@
 #include <stdexcept>
 #include <tuple>
 #include <thread>
+#include <chrono>
 #include <unordered_map>
 
 namespace arb { namespace host {
@@ -40,6 +41,14 @@ template <class T, class Less> static void parallel_sort(std::vector<T>& v, Less
 		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 	}
 }
+
+// ARB_TRACE=1: wall time of the parts of a stage, on stderr
+struct stage_laps {
+	const char* stage; bool on; double last;
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	explicit stage_laps(const char* s): stage(s), on(getenv("ARB_TRACE") != NULL), last(now()) {}
+	void lap(const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[laps] %-22s %-34s %8.1f ms\n", stage, what, (t - last) * 1e3); last = t; }
+};
 
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 
@@ -139,9 +148,12 @@ void pipeline::fetch_candidates() {
 	c.direction1 = e.dir1.data(); c.direction2 = e.dir2.data(); c.split_reads1 = e.split_reads1.data(); c.split_reads2 = e.split_reads2.data(); c.discordant_mates = e.discordant_mates.data();
 	c.filter = e.filter.data(); c.bits = e.bits.data(); c.bits2 = e.bits2.data(); c.anchor_start1 = e.anchor1.data(); c.anchor_start2 = e.anchor2.data(); c.evalue = e.evalue.data();
 	c.list1_off = e.list1_off.data(); c.list2_off = e.list2_off.data(); c.listd_off = e.listd_off.data(); c.list1 = e.list1.data(); c.list2 = e.list2.data(); c.listd = e.listd.data();
+	stage_laps laps("fetch");
 	check(ctx, arb_get_candidates(ctx, &c), "arb_get_candidates");
+	laps.lap("device -> host");
 	e.list1.resize(n1); e.list2.resize(n2); e.listd.resize(nd);
 	e.replay_iteration_order();
+	laps.lap("iteration order");
 	// mirror the canonical mate order the device established for listed discordant mates (fusions.cpp:414-421)
 	std::vector<u8> swapped(frags.n);
 	check(ctx, arb_get_slot_swaps(ctx, swapped.data()), "arb_get_slot_swaps");
@@ -153,6 +165,7 @@ void pipeline::fetch_candidates() {
 		std::swap(frags.genes_off[a], frags.genes_off[b]); std::swap(frags.genes_cnt[a], frags.genes_cnt[b]);
 	}
 	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
+	laps.lap("mate swaps + labels");
 	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")"; say(s.str());
 }
 
@@ -307,6 +320,7 @@ void pipeline::filter_multimappers() {
 // ------------------------------------------------------------------------------------------- e-value (filter_relative_support.cpp)
 void pipeline::estimate_evalues() {
 	event_table& e = ev;
+	stage_laps laps("evalue");
 	// global statistics (filter_relative_support.cpp:19-127). Fusion partners of every gene: of the candidates that share (gene, breakpoint1, breakpoint2)
 	// -- the same breakpoints annotated with overlapping partner genes -- only the one the reference visits FIRST contributes its partner
 	// (`overlap_duplicates`, :22-30). First = smallest rank in the replayed iteration order; found by sorting instead of a hash map per candidate.
@@ -334,6 +348,7 @@ void pipeline::estimate_evalues() {
 			if (x == 0 || all[x].gene != all[x - 1].gene || all[x].bp1 != all[x - 1].bp1 || all[x].bp2 != all[x - 1].bp2) pairs.push_back((u64) all[x].gene << 32 | all[x].partner);
 		std::sort(pairs.begin(), pairs.end()); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
 	}
+	laps.lap("partner pairs");
 	std::vector<u32> n_partners(ref.genes.size(), 0);
 	for (size_t x = 0; x < pairs.size(); ++x) ++n_partners[pairs[x] >> 32];
 	// a gene's count = its partners that have no more partners than the gene itself
@@ -375,9 +390,11 @@ void pipeline::estimate_evalues() {
 	in.pow_reads = t_reads.data(); in.pow_intragenic = t_intra.data(); in.pow_intergenic = t_inter.data(); in.n_read_table = (uint32_t) t_reads.size();
 	in.pow_spliced1000 = t_s1000.data(); in.pow_spliced400 = t_s400.data(); in.pow_read_through = t_rt.data(); in.pow_proximal = t_prox.data();
 	in.read_through_penalty = 1 + pow((rt_fraction - 0.25) * 20, 2);
+	laps.lap("tallies + pow tables");
 	push_candidate_state();
 	check(ctx, arb_estimate_evalues(ctx, &in), "arb_estimate_evalues");
 	pull_candidate_state();
+	laps.lap("device + state copies");
 	say("Estimating expected number of fusions by random chance (e-value)");
 }
 
@@ -503,14 +520,17 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 	const annot_view an = ref.host_view();
 	const u32 N = frags.n;
 	const frag_view f = frags.view();
+	stage_laps laps("in_vitro");
 	std::vector<u64> exonic_breakpoints; // one (gene, partner) key per exonic, unspliced breakpoint pair, sorted: a count is the width of an equal range
 	for (u32 k = 0; k < ev.n; ++k)
 		if (ev.gene1[k] != ev.gene2[k] && !ev.spliced1(k) && !ev.spliced2(k) && ev.exonic1(k) && ev.exonic2(k) && ev.n_list1(k) + ev.n_list2(k) > 0 && ev.filter[k] != F_merge_adjacent && ev.filter[k] != F_uninteresting_contigs) {
 			exonic_breakpoints.push_back((u64) ev.gene1[k] << 32 | ev.gene2[k]); exonic_breakpoints.push_back((u64) ev.gene2[k] << 32 | ev.gene1[k]);
 		}
 	parallel_sort(exonic_breakpoints, [](u64 a, u64 b) { return a < b; }, threads);
+	laps.lap("exonic breakpoint pairs");
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
 	find_top_expressed_genes(reads_by_gene, present, threshold, opt.high_expression_quantile); // -Q
+	laps.lap("top expressed genes");
 	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
 		unsigned int highest = reads_by_gene[gene];
 		idset<1024> genes; query_index(gene_index(an), contig, bp, bp, genes); if (genes.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
@@ -548,6 +568,7 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 		    (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || exonic_bp > 8 || sup <= 1))
 			ev.filter[k] = F_in_vitro;
 	});
+	laps.lap("candidates");
 	log_remaining("Filtering in vitro-generated fusions");
 }
 

@@ -1,5 +1,6 @@
 // mismap.cu -- drivers of the k-mer index, gene homology and re-alignment stages (see mismap_hd.h).
 #include <algorithm>
+#include <cstdlib>
 #include "engine.h"
 #include "mismap_hd.h"
 
@@ -106,13 +107,16 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	u32 H = 0; n_heavy.download(ex, &H, 1);
 	stage_timer t2(ex);
 	// pass 2 and the task rounds: continuations are registered per item (mismap_hd.h, realign_ctl::table) and run as tasks, one per distinct continuation
-	const u32 K = mismap_table_slots;
-	if ((u64) H * K >= 0x80000000ull) throw arb_error("too many reads need the cooperative re-alignment");
-	dbuf<continuation_slot> tables((size_t) H * K + 1); dbuf<realign_task> tasks((size_t) H * K + 1); dbuf<u32> n_tasks(1);
-	if (H) { continuation_init_fn ci = {tables.ptr()}; for_each(ex, H * K, ci); }
+	// one table for all cooperative items (a read in a long repeat registers thousands of continuations, most reads a handful): 2^20 .. 2^26 slots of 16 bytes
+	u32 K = 1u << 20; while (K < (1u << 26) && (u64) K < (u64) H * mismap_table_slots) K <<= 1;
+	if (const char* s = getenv("ARB_MISMAP_TABLE_TOTAL")) { K = 1; while (K < (u32) std::max(1, atoi(s))) K <<= 1; } // test hook: a table that overflows
+	if (H >= (1u << 24)) throw arb_error("too many reads need the cooperative re-alignment");
+	dbuf<continuation_slot> tables((size_t) K + 1); dbuf<realign_task> tasks((size_t) K + 1); dbuf<u32> n_tasks(1), overflow(1);
+	overflow.zero(ex, 1);
+	if (H) { continuation_init_fn ci = {tables.ptr()}; for_each(ex, K, ci); }
 	for (u32 done = 0; done < H; ) { // launches of at most 2^31 threads
 		const u32 batch = std::min<u32>(H - done, 0x80000000u / mismap_lanes);
-		mismap_heavy_fn mh = {items, heavy.ptr() + done, mismap_lanes, mismap_spawn_budget, tables.ptr() + (size_t) done * K, K};
+		mismap_heavy_fn mh = {items, heavy.ptr(), mismap_lanes, mismap_spawn_budget, tables.ptr(), K, done, overflow.ptr()};
 		launch(batch * mismap_lanes, mh);
 		done += batch;
 	}
@@ -120,18 +124,19 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	while (H) {
 		n_tasks.zero(ex, 1);
 		continuation_collect_fn cc = {tables.ptr(), K, heavy.ptr(), item_frag.ptr(), mism.ptr(), tasks.ptr(), n_tasks.ptr()};
-		for_each(ex, H * K, cc);
+		for_each(ex, K, cc);
 		u32 Q = 0; n_tasks.download(ex, &Q, 1);
 		if (Q == 0) break;
 		spawned += Q; ++rounds;
 		for (u32 done = 0; done < Q; ) {
 			const u32 batch = std::min<u32>(Q - done, 0x80000000u / mismap_task_lanes);
-			mismap_task_fn mt = {items, tasks.ptr() + done, mismap_task_lanes, mismap_spawn_budget, tables.ptr(), K};
+			mismap_task_fn mt = {items, tasks.ptr() + done, mismap_task_lanes, mismap_spawn_budget, tables.ptr(), K, overflow.ptr()};
 			launch(batch * mismap_task_lanes, mt);
 			done += batch;
 		}
 	}
 	timings.mismapper_tasks = spawned; timings.mismapper_rounds = rounds;
+	{ u32 o = 0; overflow.download(ex, &o, 1); timings.mismapper_overflow = o; timings.mismapper_table_slots = K; }
 	timings.mismappers_pass2_ms = t2.stop();
 	timings.mismapper_heavy_items = H;
 	mismap_apply_fn ma = {mism.ptr(), frags.filter.ptr()};

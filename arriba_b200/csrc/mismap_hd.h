@@ -86,7 +86,7 @@ ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
 //  * lanes/lane/counter: the cooperative pass deals the top-level hits round-robin to `lanes` threads of the same item;
 //  * stop: set as soon as any lane (or any other item of the same fragment) found a placement.
 //  * table: in the cooperative passes a continuation (the recursive call at a splice site or at the first mismatch) is not run by the thread that meets
-//    it. It is REGISTERED in a small hash table of its item under (segment, gene, strand, score, read position, deletions left) with the smallest lower
+//    it. It is REGISTERED in a hash table under (item, segment, gene, strand, score, read position, deletions left) with the smallest lower
 //    bound requested so far, and the caller goes on as if it had failed (valid: the answer is an OR). After the pass, every entry whose bound went down
 //    becomes one task; a group of lanes deals that task's hits and registers what IT cannot finish. A continuation only looks at hits at or above its
 //    bound, so the entry with the smallest bound answers for all the others: a read in a tandem repeat reaches the same (score, read position) from
@@ -96,12 +96,15 @@ ARB_HD bool env_ref_equals(const u32* g4, const char* ref, i32 g, u32 code) {
 //    (score, read position) with ascending bounds: the first one pays, the others are answered from a small per-thread table.
 struct realign_task { u32 item; u16 gene_k; u8 segment, rc; i32 score, read_pos, gene_pos, max_deletions; u32 item_slot; };
 struct continuation_slot { u64 key; i32 want /* smallest lower bound requested */, done /* bound already turned into a task */; };
-ARB_HD u64 continuation_key(const realign_task& t) { // never 0
-	return 1ull << 63 | (u64) t.segment << 51 | (u64) t.rc << 50 | (u64) (u32) t.max_deletions << 48 | (u64) t.gene_k << 32 | (u64) (u16) (t.score + 32768) << 16 | (u64) (u16) t.read_pos;
+// key of a continuation: cooperative item (24 bits) | segment | strand | deletions left (2) | gene of the segment (10) | score + 512 (10) | read position (9); never 0
+ARB_HD bool continuation_key(const realign_task& t, u64& key) {
+	if (t.item_slot >= (1u << 24) || t.gene_k >= 1024 || t.score < -512 || t.score > 511 || t.read_pos < 0 || t.read_pos > 511 || t.max_deletions < 0 || t.max_deletions > 3) return false;
+	key = 1ull << 63 | (u64) t.item_slot << 33 | (u64) t.segment << 32 | (u64) t.rc << 31 | (u64) (u32) t.max_deletions << 29 | (u64) t.gene_k << 19 | (u64) (u32) (t.score + 512) << 9 | (u64) (u32) t.read_pos;
+	return true;
 }
 ARB_HD void continuation_unpack(u64 key, realign_task& t) {
-	t.segment = (u8) (key >> 51 & 1); t.rc = (u8) (key >> 50 & 1); t.max_deletions = (i32) (key >> 48 & 3); t.gene_k = (u16) (key >> 32);
-	t.score = (i32) (u16) (key >> 16) - 32768; t.read_pos = (i32) (u16) key;
+	t.item_slot = (u32) (key >> 33) & 0xFFFFFFu; t.segment = (u8) (key >> 32 & 1); t.rc = (u8) (key >> 31 & 1); t.max_deletions = (i32) (key >> 29 & 3); t.gene_k = (u16) (key >> 19 & 1023);
+	t.score = (i32) (key >> 9 & 1023) - 512; t.read_pos = (i32) (key & 511);
 }
 struct realign_memo { i32 score, read_pos, max_deletions, fail_from; };
 struct realign_ctl {
@@ -120,22 +123,23 @@ struct realign_ctl {
 	int budget; bool limited;
 	u32 lanes, lane, counter;
 	const volatile u8* stop;
-	int spawn_budget; continuation_slot* table; u32 table_slots; realign_task proto; // table: the item's registry; proto: item / segment / gene / strand of the running alignment
+	int spawn_budget; continuation_slot* table; u32 table_slots; u32* overflow /* registrations that did not fit */; realign_task proto; // table: the item's registry; proto: item / segment / gene / strand of the running alignment
 	ARB_HD bool exhausted() const { return limited && budget < 0; }
-	ARB_HD bool spawn(int score, int read_pos, int gene_pos, int max_deletions) { // registers the continuation; false if the item's table is full (the caller then runs it itself)
-		if (score < -32768 || score > 32767 || read_pos < 0 || read_pos > 65535) return false;
+	ARB_HD bool spawn(int score, int read_pos, int gene_pos, int max_deletions) { // registers the continuation; false if it cannot be (the caller then runs it itself)
 		realign_task t = proto; t.score = score; t.read_pos = read_pos; t.max_deletions = max_deletions;
-		const u64 key = continuation_key(t);
-		u64 h = key * 0x9E3779B97F4A7C15ULL; h ^= h >> 32;
-		for (u32 probe = 0; probe < table_slots; ++probe) {
-			continuation_slot& s = table[(h + probe) % table_slots];
+		u64 key;
+		if (!continuation_key(t, key)) return false;
+		u64 h = key * 0x9E3779B97F4A7C15ULL; h ^= h >> 29;
+		for (u32 probe = 0; probe < 256; ++probe) { // table_slots is a power of two
+			continuation_slot& s = table[(h + probe) & (table_slots - 1)];
 			const u64 seen = atomic_cas_u64(&s.key, 0, key);
 			if (seen == 0 || seen == key) { atomic_min_i32(&s.want, gene_pos); return true; }
 		}
+		if (overflow) atomic_add_u32(overflow, 1);
 		return false;
 	}
 };
-ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.forget(); c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.table = 0; c.table_slots = 0; return c; }
+ARB_HD realign_ctl unlimited_ctl() { realign_ctl c; c.forget(); c.budget = 0; c.limited = false; c.lanes = 1; c.lane = 0; c.counter = 0; c.stop = 0; c.spawn_budget = 0; c.table = 0; c.table_slots = 0; c.overflow = 0; return c; }
 
 // seed-and-extend re-alignment (filter_mismappers.cpp:86-187): true as soon as a placement reaches min_score
 ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_deletions, const realign_env& env, realign_ctl& ctl, bool top) {
@@ -359,11 +363,11 @@ struct mismap_item_fn {
 };
 // pass 2: `lanes` threads per queued item share the top-level k-mer hits; continuations go to the item's registry
 struct mismap_heavy_fn {
-	mismap_items it; const u32* heavy; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots;
+	mismap_items it; const u32* heavy; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots; u32 first_slot; u32* overflow;
 	ARB_HD void operator()(u32 t) const {
-		const u32 slot = t / lanes, j = heavy[slot], i = it.item_frag[j];
+		const u32 slot = first_slot + t / lanes, j = heavy[slot], i = it.item_frag[j];
 		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
-		ctl.spawn_budget = spawn_budget; ctl.table = tables + (size_t) slot * table_slots; ctl.table_slots = table_slots; ctl.proto.item_slot = slot;
+		ctl.spawn_budget = spawn_budget; ctl.table = tables; ctl.table_slots = table_slots; ctl.overflow = overflow; ctl.proto.item_slot = slot;
 		if (*ctl.stop) return;
 		if (it.evaluate(j, ctl, false)) it.mismapper[i] = 1;
 #ifdef ARB_COST_PROBE
@@ -379,21 +383,21 @@ struct continuation_collect_fn {
 		continuation_slot& s = tables[k];
 		if (s.key == 0 || s.want >= s.done) return;
 		s.done = s.want;
-		const u32 slot = k / table_slots, j = heavy[slot];
-		if (mismapper[item_frag[j]]) return; // already decided
-		realign_task t; t.item = j; t.item_slot = slot; t.gene_pos = s.want;
+		realign_task t; t.gene_pos = s.want;
 		continuation_unpack(s.key, t);
+		t.item = heavy[t.item_slot];
+		if (mismapper[item_frag[t.item]]) return; // already decided
 		tasks[append_slot(n_tasks)] = t;
 	}
 };
 // task rounds: `lanes` threads per registered continuation
 struct mismap_task_fn {
-	mismap_items it; const realign_task* tasks; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots;
+	mismap_items it; const realign_task* tasks; u32 lanes; int spawn_budget; continuation_slot* tables; u32 table_slots; u32* overflow;
 	ARB_HD void operator()(u32 t) const {
 		const realign_task task = tasks[t / lanes];
 		const u32 i = it.item_frag[task.item];
 		realign_ctl ctl = unlimited_ctl(); ctl.lanes = lanes; ctl.lane = t % lanes; ctl.stop = it.mismapper + i;
-		ctl.spawn_budget = spawn_budget; ctl.table = tables + (size_t) task.item_slot * table_slots; ctl.table_slots = table_slots; ctl.proto = task;
+		ctl.spawn_budget = spawn_budget; ctl.table = tables; ctl.table_slots = table_slots; ctl.overflow = overflow; ctl.proto = task;
 		if (*ctl.stop) return;
 		const realign_segment s = it.segment(task.item, task.segment);
 		realign_env env;

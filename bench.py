@@ -264,7 +264,7 @@ def main():
                          "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
                                        "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
                                        "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},
-                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "mismapper_tasks": int(tm.mismapper_tasks), "mismapper_rounds": int(tm.mismapper_rounds), "kmer_positions": int(tm.kmer_positions)},
+                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "mismapper_tasks": int(tm.mismapper_tasks), "mismapper_rounds": int(tm.mismapper_rounds), "mismapper_registry": {"slots": int(tm.mismapper_table_slots), "overflow": int(tm.mismapper_overflow)}, "kmer_positions": int(tm.kmer_positions)},
             "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
     if extra_sharded:
         line["sharded_single_sample"] = extra_sharded

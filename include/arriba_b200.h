@@ -186,7 +186,7 @@ typedef struct arb_timings {
 	uint64_t kmer_positions;    /* positions in the k-mer index */
 	uint64_t mismapper_heavy_items; /* pairs that exhausted the one-thread budget and were re-aligned cooperatively */
 	float mismappers_pass1_ms, mismappers_pass2_ms;
-	uint64_t mismapper_tasks; uint32_t mismapper_rounds; /* continuations re-aligned as tasks of their own, and the rounds that took */
+	uint64_t mismapper_tasks; uint32_t mismapper_rounds, mismapper_overflow, mismapper_table_slots; /* continuations re-aligned as tasks of their own, and the rounds that took */
 	float cascade_head_ms, cascade_sequences_ms; /* the two launches of the read-level cascade (classify_ms spans both) */
 	uint64_t cascade_queued;    /* fragments the sequence rules (mismatches, low entropy) looked at */
 	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */

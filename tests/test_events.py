@@ -87,11 +87,11 @@ def test_events_hostsim_cooperative_realignment(worlds, hostsim_lib, monkeypatch
     assert tm.mismapper_tasks > 1000 and tm.mismapper_rounds >= 2   # continuations of continuations were registered as well
 
 
-@pytest.mark.parametrize("spawn,table", [("0", "256"), ("0", "3"), ("5", "1")])
+@pytest.mark.parametrize("spawn,table", [("0", "1048576"), ("0", "64"), ("5", "1")])
 def test_events_hostsim_continuation_registry(worlds, hostsim_lib, monkeypatch, spawn, table):
     """No bounded attempts (every continuation is registered), and registries so small that most registrations fail over to the in-line search."""
     monkeypatch.setenv("ARB_MISMAP_BUDGET", "24"); monkeypatch.setenv("ARB_MISMAP_LANES", "5")
-    monkeypatch.setenv("ARB_MISMAP_SPAWN", spawn); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", "4"); monkeypatch.setenv("ARB_MISMAP_TABLE", table)
+    monkeypatch.setenv("ARB_MISMAP_SPAWN", spawn); monkeypatch.setenv("ARB_MISMAP_TASK_LANES", "4"); monkeypatch.setenv("ARB_MISMAP_TABLE_TOTAL", table)
     check_events(worlds.get("cfg5", **CFG5), hostsim_lib)
 
 
