@@ -329,21 +329,14 @@ void pipeline::estimate_evalues() {
 		struct occurrence { u32 gene; i32 bp1, bp2; u32 rank; u32 partner; };
 		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
 		const size_t n_order = e.order.size();
-		std::vector<std::vector<occurrence> > part(threads);
-		std::vector<std::thread> pool;
-		for (int t = 0; t < threads; ++t) pool.emplace_back([&, t]() {
-			std::vector<occurrence>& v = part[t];
-			for (size_t q = n_order * t / threads; q < n_order * (t + 1) / threads; ++q) {
-				const u32 k = e.order[q];
-				if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
-				const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
-				v.push_back(a); v.push_back(b);
-			}
-			std::sort(v.begin(), v.end(), before);
-		});
-		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 		std::vector<occurrence> all;
-		for (int t = 0; t < threads; ++t) { const size_t mid = all.size(); all.insert(all.end(), part[t].begin(), part[t].end()); std::inplace_merge(all.begin(), all.begin() + mid, all.end(), before); std::vector<occurrence>().swap(part[t]); }
+		for (size_t q = 0; q < n_order; ++q) {
+			const u32 k = e.order[q];
+			if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
+			const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
+			all.push_back(a); all.push_back(b);
+		}
+		parallel_sort(all, before, threads);
 		for (size_t x = 0; x < all.size(); ++x)
 			if (x == 0 || all[x].gene != all[x - 1].gene || all[x].bp1 != all[x - 1].bp1 || all[x].bp2 != all[x - 1].bp2) pairs.push_back((u64) all[x].gene << 32 | all[x].partner);
 		std::sort(pairs.begin(), pairs.end()); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
@@ -544,6 +537,13 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 		float rt = 0;
 		if (!ev.exonic1(k)) rt += 0.5; else if (!ev.spliced1(k)) rt += 1;
 		if (!ev.exonic2(k)) rt += 0.5; else if (!ev.spliced2(k)) rt += 1;
+		// The verdict is one boolean expression (filter_in_vitro.cpp:196-222); its terms are evaluated cheapest first and the expensive ones (supporting
+		// mates that are clipped at the breakpoints, the most expressed gene at either breakpoint, exonic breakpoint pairs) only while they can still matter.
+		const unsigned int own_split = ev.split_reads1[k] + ev.split_reads2[k];
+		if (own_split > 2 && own_split * 2 > ev.discordant_mates[k]) return; // total_split >= own_split: "total_split * 2 <= discordant_mates || total_split <= 2" cannot hold
+		const u32 g1 = higher_expressed(ev.contig1[k], ev.bp1[k], ev.gene1[k]), g2 = higher_expressed(ev.contig2[k], ev.bp2[k], ev.gene2[k]);
+		const unsigned int x1 = reads_by_gene[g1], x2 = reads_by_gene[g2];
+		if (!(x1 + x2 > threshold)) return; // only breakpoints in highly expressed genes are suspected: most candidates leave here
 		unsigned int clipped1 = 0, clipped2 = 0;
 		for (u32 p = ev.listd_off[k]; p < ev.listd_off[k + 1]; ++p) {
 			const u32 i = ev.listd[p];
@@ -554,18 +554,17 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 				else if (!f.fwd(a) && f.preclip(a) >= 3) { if (f.contig[a] == ev.contig1[k] && f.start[a] == ev.bp1[k]) ++clipped1; else if (f.contig[a] == ev.contig2[k] && f.start[a] == ev.bp2[k]) ++clipped2; }
 			}
 		}
-		const unsigned int total_split = std::min(clipped1, clipped2) + ev.split_reads1[k] + ev.split_reads2[k];
-		const u32 g1 = higher_expressed(ev.contig1[k], ev.bp1[k], ev.gene1[k]), g2 = higher_expressed(ev.contig2[k], ev.bp2[k], ev.gene2[k]);
-		const unsigned int x1 = reads_by_gene[g1], x2 = reads_by_gene[g2];
-		const unsigned int exonic_bp = std::max(pair_count(g1, g2), pair_count(ev.gene1[k], ev.gene2[k]));
-		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
-		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+		const unsigned int total_split = std::min(clipped1, clipped2) + own_split;
+		if (!(total_split * 2 <= ev.discordant_mates[k] || total_split <= 2)) return;
+		if (!(total_split <= 2 + 0.0001 * (x1 + x2))) return;
 		const unsigned int sup = ev.supporting_reads(k);
-		if (total_split <= 2 + 0.0001 * (x1 + x2) &&
-		    (total_split * 2 <= ev.discordant_mates[k] || total_split <= 2) &&
-		    x1 + x2 > threshold &&
-		    !(sup >= 10 && ((int) sup * 4) >= std::max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup && (ev.spliced1(k) || ev.spliced2(k)) && ((ev.spliced1(k) || !ev.exonic1(k)) && (ev.spliced2(k) || !ev.exonic2(k)))) &&
-		    (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || exonic_bp > 8 || sup <= 1))
+		if (sup >= 10 && (ev.spliced1(k) || ev.spliced2(k)) && ((ev.spliced1(k) || !ev.exonic1(k)) && (ev.spliced2(k) || !ev.exonic2(k)))) {
+			const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+			const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+			if (((int) sup * 4) >= std::max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup) return; // well covered on both sides: kept
+		}
+		if (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || sup <= 1 ||
+		    std::max(pair_count(g1, g2), pair_count(ev.gene1[k], ev.gene2[k])) > 8)
 			ev.filter[k] = F_in_vitro;
 	});
 	laps.lap("candidates");

@@ -7,6 +7,8 @@
 #include <algorithm>
 #include <atomic>
 #include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
 #include <unistd.h>
 #include <chrono>
 #include <cmath>
@@ -24,6 +26,12 @@ namespace arb { namespace host {
 
 namespace {
 static thread_local std::string* warning_sink = NULL;
+struct output_laps { // ARB_TRACE=1: wall time of the parts of the writer, on stderr
+	bool on; double last;
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	output_laps(): on(getenv("ARB_TRACE") != NULL), last(now()) {}
+	void lap(const char* file, const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[laps] output %-10s %-34s %8.1f ms\n", file, what, (t - last) * 1e3); last = t; }
+};
 static int filters_by_name[38]; // filter ids in alphabetical order of their names (the reference keeps them in a std::map<string, ...>)
 static void sort_filters_by_name() { for (int f = 0; f < 38; ++f) filters_by_name[f] = f; std::sort(filters_by_name, filters_by_name + 38, [](int a, int b) { return strcmp(FILTER_NAMES[a], FILTER_NAMES[b]) < 0; }); } // set by the formatting threads of writer::write
 
@@ -604,6 +612,7 @@ struct writer {
 
 	void write(const std::string& path, bool discarded, bool extra_info) const {
 		sort_filters_by_name();
+		output_laps laps; const char* const which = discarded ? "discarded" : "fusions";
 		std::vector<u32> rows;
 		for (size_t q = 0; q < e.order.size(); ++q) { const u32 k = e.order[q]; if (discarded != (e.filter[k] == F_none)) rows.push_back(k); }
 		if (!discarded) {
@@ -645,23 +654,31 @@ struct writer {
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 		}
 		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
-		const int fd = ::open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+		laps.lap(which, "rows formatted");
+		const int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
 		if (fd < 0) throw std::runtime_error("failed to open output file");
 		std::vector<u64> at(n_chunks + 1); at[0] = header.size(); for (size_t c = 0; c < n_chunks; ++c) at[c + 1] = at[c] + slices[c].size();
-		auto write_at = [&](const char* data, size_t n, u64 off) { while (n > 0) { const ssize_t w = ::pwrite(fd, data, n, (off_t) off); if (w <= 0) return false; data += w; n -= (size_t) w; off += (u64) w; } return true; };
 		bool ok = true;
-		if (::lseek(fd, 0, SEEK_CUR) == (off_t) -1) { // not seekable (a pipe, /dev/stdout): one sequential writer
+		const u64 total = at[n_chunks];
+		// a regular file is sized once and filled through a shared mapping by all threads (buffered write() calls to ONE file serialise on its inode lock);
+		// anything else (a pipe, /dev/stdout) gets one sequential writer
+		void* map = MAP_FAILED;
+		struct stat st;
+		if (::fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && total > 0 && ::ftruncate(fd, (off_t) total) == 0) map = ::mmap(NULL, total, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+		if (map != MAP_FAILED) {
+			char* const out = (char*) map;
+			memcpy(out, header.data(), header.size());
+			std::vector<std::thread> pool;
+			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (size_t c = n_chunks * t / T; c < n_chunks * (t + 1) / T; ++c) memcpy(out + at[c], slices[c].data(), slices[c].size()); });
+			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+			ok = ::munmap(map, total) == 0;
+		} else {
 			auto write_all = [&](const char* data, size_t n) { while (n > 0) { const ssize_t w = ::write(fd, data, n); if (w <= 0) return false; data += w; n -= (size_t) w; } return true; };
 			ok = write_all(header.data(), header.size());
 			for (size_t c = 0; c < n_chunks && ok; ++c) ok = write_all(slices[c].data(), slices[c].size());
-		} else {
-			ok = write_at(header.data(), header.size(), 0);
-			std::vector<std::thread> pool; std::vector<u8> good(T, 1);
-			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (size_t c = n_chunks * t / T; c < n_chunks * (t + 1) / T; ++c) if (!write_at(slices[c].data(), slices[c].size(), at[c])) good[t] = 0; });
-			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-			for (int t = 0; t < T; ++t) ok = ok && good[t];
 		}
 		ok = ::close(fd) == 0 && ok;
+		laps.lap(which, "file written");
 		for (size_t c = 0; c < n_chunks; ++c) if (!warnings[c].empty()) std::cerr << warnings[c] << std::flush;
 		if (!ok) throw std::runtime_error("failed to write to file");
 	}
