@@ -330,11 +330,23 @@ void pipeline::estimate_evalues() {
 		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
 		const size_t n_order = e.order.size();
 		std::vector<occurrence> all;
-		for (size_t q = 0; q < n_order; ++q) {
-			const u32 k = e.order[q];
-			if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
-			const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
-			all.push_back(a); all.push_back(b);
+		{ // collected by slices of the iteration order, concatenated in slice order
+			const int T = std::max(1, std::min(threads, (int) (n_order / 65536 + 1)));
+			std::vector<std::vector<occurrence> > part(T);
+			std::vector<std::thread> pool;
+			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+				std::vector<occurrence>& v = part[t];
+				for (size_t q = n_order * t / T; q < n_order * (t + 1) / T; ++q) {
+					const u32 k = e.order[q];
+					if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
+					const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
+					v.push_back(a); v.push_back(b);
+				}
+			});
+			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+			size_t total = 0; for (int t = 0; t < T; ++t) total += part[t].size();
+			all.reserve(total);
+			for (int t = 0; t < T; ++t) all.insert(all.end(), part[t].begin(), part[t].end());
 		}
 		parallel_sort(all, before, threads);
 		for (size_t x = 0; x < all.size(); ++x)

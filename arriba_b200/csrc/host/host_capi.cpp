@@ -1,4 +1,5 @@
 // host_capi.cpp -- C ABI of the whole-run driver (include/arriba_b200.h, "whole-run driver" section).
+#include <malloc.h>
 #include "pipeline.h"
 #include <cstring>
 #include <stdexcept>
@@ -27,7 +28,17 @@ void arb_default_run_options(arb_run_options* o) {
 	o->min_itd_allele_fraction = 0.07f; o->min_itd_support = 10; o->print_extra_info_for_discarded_fusions = 0; o->echo_progress = 0;
 }
 
+// Dozens of host threads allocate and free at the same time (record parsing, annotation, row formatting). glibc gives every thread its own arena, but arenas
+// hand memory back to the kernel and map new chunks all the time, and those calls serialise on the process's address-space lock: keep what was obtained.
+static void tune_allocator() {
+	static bool done = false;
+	if (done) return;
+	done = true;
+	mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20);
+}
+
 int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
+	tune_allocator();
 	if (!out || !o) return 2;
 	*out = NULL;
 	try {

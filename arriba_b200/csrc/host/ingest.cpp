@@ -133,8 +133,9 @@ struct worker {
 	std::unordered_map<std::string, std::vector<u8>, name_hash> pending; // first mate of a proper pair, waiting for the second
 	coverage_windows* cov; // shared by all workers: saturating counters and flags are updated atomically, the result does not depend on the order
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
-	std::string key, clip_chars;
-	worker(): cov(NULL), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
+	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size;
+	void park_waiting() { if (waiting_ptr) { pending.emplace(waiting_key, std::vector<u8>(waiting_ptr, waiting_ptr + waiting_size)); waiting_ptr = NULL; } } // before the chunk buffer is recycled
+	worker(): waiting_ptr(NULL), waiting_size(0), cov(NULL), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
 
 	u32 fragment(const std::string& name, bool* created = NULL) {
 		if (name_slots.empty()) name_slots.assign(1u << 12, 0);
@@ -409,10 +410,16 @@ struct worker {
 		rec_t mate; mate.base = NULL;
 		std::vector<u8> mate_bytes;
 		if (r.flag & BF_PAIRED) {
-			std::unordered_map<std::string, std::vector<u8>, name_hash>::iterator it = pending.find(key);
-			if (it == pending.end()) { pending.emplace(key, std::vector<u8>(p, p + size)); return; } // first mate: wait for the second
-			mate_bytes.swap(it->second); pending.erase(it);
-			parse_record(mate_bytes.data(), (u32) mate_bytes.size(), mate);
+			// The first mate of a proper pair waits for the second. Mates are neighbours in a collated BAM: the most recent waiting record is only
+			// remembered by its address in the chunk buffer and moves into the map (a copy) when another name arrives or the chunk ends.
+			if (waiting_ptr && waiting_key == key) {
+				parse_record(waiting_ptr, waiting_size, mate); waiting_ptr = NULL;
+			} else {
+				std::unordered_map<std::string, std::vector<u8>, name_hash>::iterator it = pending.find(key);
+				if (it == pending.end()) { park_waiting(); waiting_ptr = p; waiting_size = size; waiting_key = key; return; }
+				mate_bytes.swap(it->second); pending.erase(it);
+				parse_record(mate_bytes.data(), (u32) mate_bytes.size(), mate);
+			}
 			mate.tid = (*tid_to_contig)[mate.tid];
 		}
 		const rec_t* m = mate.valid() ? &mate : NULL;
@@ -737,6 +744,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 					worker& w = workers[t];
 					const u8* base = c.buf.data();
 					for (size_t k = 0; k < c.rec_off.size(); ++k) if (c.rec_shard[k] == t) w.process(base + c.rec_off[k] + 4, rd32(base + c.rec_off[k]));
+					w.park_waiting();
 				}
 			});
 		} catch (const std::exception& x) { process_error = x.what(); }

@@ -16,6 +16,7 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <memory_resource>
 #include <sstream>
 #include <stdexcept>
 #include <thread>
@@ -59,7 +60,9 @@ struct pile_column {
 		for (; it != other.end(); ++it) out.push_back(*it);
 	}
 };
-typedef std::map<i32, pile_column> pileup_t;
+// nodes come from a per-thread arena that is rewound after every row: hundreds of map nodes per row from 64 threads would otherwise meet in malloc
+typedef std::pmr::map<i32, pile_column> pileup_t;
+static std::pmr::monotonic_buffer_resource& row_arena() { static thread_local std::pmr::monotonic_buffer_resource arena(1 << 20); return arena; }
 
 char comp_char(char c) { // assembly.hpp:9-22
 	switch (c) {
@@ -183,7 +186,7 @@ struct writer {
 		const bool strands_ambiguous = e.bits[k] & CB_PSTRANDS_AMBIGUOUS, tstart_ambiguous = e.bits2[k] & 1;
 		if (strands_ambiguous || tstart_ambiguous) { sequence = "."; positions.push_back(-1); return; }
 		const u32 d1 = e.dir1[k], d2 = e.dir2[k]; const i32 bp1 = e.bp1[k], bp2 = e.bp2[k];
-		pileup_t pile1, pile2;
+		pileup_t pile1(&row_arena()), pile2(&row_arena());
 		const u32 a1 = e.list1_off[k], b1 = e.list1_off[k + 1], a2 = e.list2_off[k], b2 = e.list2_off[k + 1], ad = e.listd_off[k], bd = e.listd_off[k + 1];
 		pileup_reads(e.list1, a1, b1, SPLIT_READ, false, d1, bp1, pile1);
 		pileup_reads(e.list1, a1, b1, MATE1, false, d1, bp1, pile1);
@@ -645,7 +648,7 @@ struct writer {
 						if (c >= n_chunks) break;
 						warning_sink = &warnings[c]; // warnings of a chunk are printed after it, in row order like the reference's
 						std::ostringstream os;
-						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(os, rows[x], extra_info);
+						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) { format_row(os, rows[x], extra_info); row_arena().release(); }
 						slices[c] = os.str();
 					}
 				} catch (const std::exception& ex) { errors[t] = ex.what(); }
