@@ -125,7 +125,9 @@ void annotate_fragments(pipeline& p) {
 	fragment_table& ft = p.frags;
 	const u32 n = ft.n;
 	const int T = std::max(1, p.threads);
+	stage_laps laps("annotate");
 	gene_refs refs; refs.init(3 * (size_t) n, T);
+	laps.lap("reference table");
 	{
 		const annot_view an = ref.host_view(); const frag_view f = ft.view();
 		// pass 1: exon-based annotation, mate-aware strand inference, gene-level fallback (arriba.cpp:186-205)
@@ -167,6 +169,7 @@ void annotate_fragments(pipeline& p) {
 		});
 	}
 
+	laps.lap("pass 1 (exons, strands)");
 	// dummy genes for breakpoints outside annotated genes: one dummy gene per 10 kb cluster (arriba.cpp:207-260)
 	struct unmapped_t { u16 contig; i32 pos; };
 	std::vector<unmapped_t> unmapped;
@@ -203,8 +206,10 @@ void annotate_fragments(pipeline& p) {
 		}
 	}
 	(void) first_dummy;
+	laps.lap("dummy genes");
 	ref.build_gene_index();
 	ref.flatten();
+	laps.lap("gene index rebuilt");
 
 	// pass 2: map still unannotated breakpoints to the dummy genes, then collapse multi-dummy annotations (arriba.cpp:262-319)
 	{
@@ -247,6 +252,7 @@ void annotate_fragments(pipeline& p) {
 		});
 	}
 
+	laps.lap("pass 2 (dummy genes)");
 	// final CSR gene columns
 	std::vector<u64> at(3 * (size_t) n + 1, 0);
 	for (size_t a = 0; a < 3 * (size_t) n; ++a) at[a + 1] = at[a] + refs.cnt[a];
@@ -255,6 +261,7 @@ void annotate_fragments(pipeline& p) {
 	parallel_ranges(T, 3 * (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t a = lo; a < hi; ++a) { ft.genes_off[a] = (u32) at[a]; ft.genes_cnt[a] = refs.cnt[a]; if (refs.cnt[a]) memcpy(&ft.genes[at[a]], refs.get(a), 4ull * refs.cnt[a]); }
 	});
+	laps.lap("gene columns");
 }
 
 // ------------------------------------------------------------------------------------------- fragment length

@@ -42,14 +42,6 @@ template <class T, class Less> static void parallel_sort(std::vector<T>& v, Less
 	}
 }
 
-// ARB_TRACE=1: wall time of the parts of a stage, on stderr
-struct stage_laps {
-	const char* stage; bool on; double last;
-	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
-	explicit stage_laps(const char* s): stage(s), on(getenv("ARB_TRACE") != NULL), last(now()) {}
-	void lap(const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[laps] %-22s %-34s %8.1f ms\n", stage, what, (t - last) * 1e3); last = t; }
-};
-
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 
 // ------------------------------------------------------------------------------------------- iteration order

@@ -2,6 +2,9 @@
 // (through the public C ABI only), event-level logic and output. Mirrors the call sequence of the reference's
 // main (arriba.cpp:79-631).
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "refdata.h"
@@ -10,6 +13,14 @@
 #include "../../../include/arriba_b200.h"
 
 namespace arb { namespace host {
+
+// ARB_TRACE=1: wall time of the parts of a stage, on stderr
+struct stage_laps {
+	const char* stage; bool on; double last;
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	explicit stage_laps(const char* s): stage(s), on(getenv("ARB_TRACE") != NULL), last(now()) {}
+	void lap(const char* what) { if (!on) return; const double t = now(); fprintf(stderr, "[laps] %-22s %-34s %8.1f ms\n", stage, what, (t - last) * 1e3); last = t; }
+};
 
 struct run_options { // options_t (options.hpp:25-69) restricted to what this implementation consumes
 	std::string bam_file, gtf_file, assembly_file, output_file, discarded_output_file;
