@@ -60,9 +60,56 @@ struct pile_column {
 		for (; it != other.end(); ++it) out.push_back(*it);
 	}
 };
-// nodes come from a per-thread arena that is rewound after every row: hundreds of map nodes per row from 64 threads would otherwise meet in malloc
-typedef std::pmr::map<i32, pile_column> pileup_t;
-static std::pmr::monotonic_buffer_resource& row_arena() { static thread_local std::pmr::monotonic_buffer_resource arena(1 << 20); return arena; }
+// A pileup under construction. Per position only counters: 16-bit, one per symbol of pile_column (a candidate has at most a few hundred reads); positions
+// within WINDOW bases of the breakpoint sit in a flat array (nearly all bases), the rest -- the inside of introns, filled position by position like the
+// reference does -- in an open-addressing table; multi-base insertion strings are rare and kept aside. flatten() hands the columns over in ascending
+// position as pile_column objects, which is all the consensus needs (the reference keeps a map of maps per pileup, output_fusions.cpp:22).
+typedef std::vector<std::pair<i32, pile_column> > pileup_t;
+struct pile_builder {
+	enum { WINDOW = 2048 };
+	struct cell { u16 n[pile_column::N_SYMBOLS]; };
+	i32 lo; std::vector<cell> dense; std::vector<u8> used; std::vector<u32> used_list;
+	std::vector<i32> far_pos; std::vector<cell> far_cell; std::vector<u32> far_slot; // far_slot: open addressing, index + 1 into far_pos / far_cell, 0 = empty
+	std::map<i32, std::map<std::string, unsigned int> > other;
+	pile_builder(): lo(0), dense(2 * WINDOW), used(2 * WINDOW, 0), far_slot(1 << 12, 0) { memset(dense.data(), 0, dense.size() * sizeof(cell)); }
+	void reset(i32 breakpoint) { // only what the previous pileup touched is cleaned
+		for (size_t k = 0; k < used_list.size(); ++k) { memset(&dense[used_list[k]], 0, sizeof(cell)); used[used_list[k]] = 0; }
+		used_list.clear(); other.clear(); lo = breakpoint - WINDOW;
+		if (!far_pos.empty()) { if (far_slot.size() > (1u << 16)) far_slot.assign(1 << 12, 0); else std::fill(far_slot.begin(), far_slot.end(), 0u); far_pos.clear(); far_cell.clear(); }
+	}
+	cell& at(i32 pos) {
+		const i64 x = (i64) pos - lo;
+		if (x >= 0 && x < 2 * WINDOW) { if (!used[x]) { used[x] = 1; used_list.push_back((u32) x); } return dense[x]; }
+		if ((far_pos.size() + 1) * 2 > far_slot.size()) { // grow and re-insert
+			std::vector<u32> bigger(far_slot.size() * 2, 0); const size_t mask = bigger.size() - 1;
+			for (size_t k = 0; k < far_pos.size(); ++k) { size_t h = ((u32) far_pos[k] * 2654435761u) & mask; while (bigger[h]) h = (h + 1) & mask; bigger[h] = (u32) k + 1; }
+			far_slot.swap(bigger);
+		}
+		const size_t mask = far_slot.size() - 1; size_t h = ((u32) pos * 2654435761u) & mask;
+		for (; far_slot[h]; h = (h + 1) & mask) if (far_pos[far_slot[h] - 1] == pos) return far_cell[far_slot[h] - 1];
+		far_pos.push_back(pos); cell c; memset(&c, 0, sizeof(c)); far_cell.push_back(c); far_slot[h] = (u32) far_pos.size();
+		return far_cell.back();
+	}
+	void add(i32 pos, char symbol, unsigned int n = 1) { const int x = pile_column::index_of(symbol); if (x >= 0) at(pos).n[x] = (u16) (at(pos).n[x] + n); else other[pos][std::string(1, symbol)] += n; }
+	void add(i32 pos, const std::string& s) { if (s.size() == 1) add(pos, s[0]); else { at(pos); other[pos][s] += 1; } }
+	void flatten(pileup_t& out) const {
+		out.clear();
+		std::vector<std::pair<i32, u32> > far; far.reserve(far_pos.size());
+		for (size_t k = 0; k < far_pos.size(); ++k) far.push_back(std::make_pair(far_pos[k], (u32) k));
+		std::sort(far.begin(), far.end());
+		auto column_of = [&](i32 pos, const cell& c) {
+			std::pair<i32, pile_column> col; col.first = pos;
+			for (int k = 0; k < pile_column::N_SYMBOLS; ++k) col.second.single[k] = c.n[k];
+			std::map<i32, std::map<std::string, unsigned int> >::const_iterator o = other.find(pos);
+			if (o != other.end()) col.second.other = o->second;
+			return col;
+		};
+		size_t k = 0;
+		for (; k < far.size() && far[k].first < lo; ++k) out.push_back(column_of(far[k].first, far_cell[far[k].second]));
+		for (u32 x = 0; x < 2 * WINDOW; ++x) if (used[x]) out.push_back(column_of(lo + (i32) x, dense[x]));
+		for (; k < far.size(); ++k) out.push_back(column_of(far[k].first, far_cell[far[k].second]));
+	}
+};
 
 char comp_char(char c) { // assembly.hpp:9-22
 	switch (c) {
@@ -85,7 +132,7 @@ struct writer {
 	bool has_assembly(u32 contig) const { return ref.has_sequence(contig); }
 
 	// ---- pileup of the supporting reads around one breakpoint (output_fusions.cpp:25-107)
-	void pileup_reads(const std::vector<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pileup_t& pileup) const {
+	void pileup_reads(const std::vector<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pile_builder& pileup) const {
 		std::map<std::pair<i32, i32>, unsigned int> introns;
 		for (u32 x = lo; x < hi; ++x) {
 			const u32 frag = list[x];
@@ -97,6 +144,8 @@ struct writer {
 			// bases are decoded on the fly (reverse-complemented when the supplementary lies on the other strand): no per-read strings
 			const u32 sa = f.idx(frag, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
 			const u8* const packed = f.sq(sa); const size_t seq_size = f.seq_len[sa];
+			static const struct symbol_table { u8 v[32]; symbol_table() { for (u32 c = 0; c < 16; ++c) { v[c] = (u8) pile_column::index_of(nt16_char(c)); v[16 + c] = (u8) pile_column::index_of(comp_char(nt16_char(c))); } } } symbols;
+			const u8* const symbol_of_code = symbols.v; // counter index of a base code, as read (0-15) and reverse-complemented (16-31)
 			auto base_at = [&](size_t off) { return reverse_complement ? comp_char(nt16_char(nt16_at(packed, (u32) (seq_size - 1 - off)))) : nt16_char(nt16_at(packed, (u32) off)); };
 			i32 read_off = 0, ref_off = f.start[a]; int carry = 0; // carry: one base was already consumed by a preceding insertion
 			const u32* c = f.cig(a); const u32 nc = f.cigar_cnt[a];
@@ -105,9 +154,9 @@ struct writer {
 				const u32 op = cig_op(c[k]); const i32 len = (i32) cig_len(c[k]);
 				bool as_match = false;
 				switch (op) {
-					case C_I: pileup[ref_off].add(piece(read_off, len + 1)); read_off += len + 1; ++ref_off; carry = 1; break;
+					case C_I: pileup.add(ref_off, piece(read_off, len + 1)); read_off += len + 1; ++ref_off; carry = 1; break;
 					case C_N: { const i32 s0 = ref_off; ref_off += len - carry; ++introns[std::make_pair(s0, ref_off - 1)]; carry = 0; break; }
-					case C_D: for (i32 b = 0; b < len - carry; ++b, ++ref_off) pileup[ref_off].add('-'); carry = 0; break;
+					case C_D: for (i32 b = 0; b < len - carry; ++b, ++ref_off) pileup.add(ref_off, '-'); carry = 0; break;
 					case C_H: if (mate == SUPPLEMENTARY) read_off += len; break;
 					case C_S:
 						if (f.n_aln[frag] == 3 && mate == SPLIT_READ && ((k == 0 && fwd) || (k == nc - 1 && !fwd))) { if (k == 0 && fwd) ref_off -= len; as_match = true; } // clipped segment joins the pileup (non-template bases)
@@ -116,20 +165,19 @@ struct writer {
 					case C_M: case C_EQ: case C_X: as_match = true; break;
 					default: break;
 				}
-				if (as_match) { // consecutive positions: walk the map instead of searching it for every base
-					pileup_t::iterator at = pileup.end();
-					for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) {
-						if (at != pileup.end()) { ++at; if (at == pileup.end() || at->first != ref_off) at = pileup.end(); }
-						if (at == pileup.end()) at = pileup.try_emplace(ref_off).first;
-						if ((size_t) read_off < seq_size) at->second.add(base_at((size_t) read_off)); else at->second.add(std::string());
+				if (as_match) {
+					for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) { // the hot loop of the writer: one counter per base
+						if ((size_t) read_off < seq_size) ++pileup.at(ref_off).n[symbol_of_code[reverse_complement ? nt16_at(packed, (u32) (seq_size - 1 - read_off)) + 16 : nt16_at(packed, (u32) read_off)]];
+						else pileup.add(ref_off, std::string());
 					}
 					carry = 0;
 				}
 			}
 		}
 		for (std::map<std::pair<i32, i32>, unsigned int>::iterator it = introns.begin(); it != introns.end(); ++it) {
-			pileup[it->first.first].add('>', it->second); pileup[it->first.second].add('<', it->second);
-			for (i32 i = it->first.first + 1; i < it->first.second; ++i) pileup[i].add('_', it->second);
+			pileup.add(it->first.first, '>', it->second); pileup.add(it->first.second, '<', it->second);
+			const int inside = pile_column::index_of('_');
+			for (i32 i = it->first.first + 1; i < it->first.second; ++i) { u16& n = pileup.at(i).n[inside]; n = (u16) (n + it->second); }
 		}
 	}
 
@@ -186,7 +234,9 @@ struct writer {
 		const bool strands_ambiguous = e.bits[k] & CB_PSTRANDS_AMBIGUOUS, tstart_ambiguous = e.bits2[k] & 1;
 		if (strands_ambiguous || tstart_ambiguous) { sequence = "."; positions.push_back(-1); return; }
 		const u32 d1 = e.dir1[k], d2 = e.dir2[k]; const i32 bp1 = e.bp1[k], bp2 = e.bp2[k];
-		pileup_t pile1(&row_arena()), pile2(&row_arena());
+		static thread_local pile_builder build1, build2;
+		pile_builder& pile1 = build1; pile_builder& pile2 = build2;
+		pile1.reset(bp1); pile2.reset(bp2);
 		const u32 a1 = e.list1_off[k], b1 = e.list1_off[k + 1], a2 = e.list2_off[k], b2 = e.list2_off[k + 1], ad = e.listd_off[k], bd = e.listd_off[k + 1];
 		pileup_reads(e.list1, a1, b1, SPLIT_READ, false, d1, bp1, pile1);
 		pileup_reads(e.list1, a1, b1, MATE1, false, d1, bp1, pile1);
@@ -209,8 +259,9 @@ struct writer {
 			}
 		}
 		std::string s1, s2, c1, c2; std::vector<i32> p1, p2;
-		consensus(pile1, bp1, d1, e.gene1[k], s1, p1, c1);
-		consensus(pile2, bp2, d2, e.gene2[k], s2, p2, c2);
+		pileup_t columns;
+		pile1.flatten(columns); consensus(columns, bp1, d1, e.gene1[k], s1, p1, c1);
+		pile2.flatten(columns); consensus(columns, bp2, d2, e.gene2[k], s2, p2, c2);
 		if (e.n_list1(k) + e.n_list2(k) == 0) { // breakpoints are not known exactly
 			if (d1 == DOWNSTREAM) { s1 += "..."; p1.resize(p1.size() + 3, -1); } else { s1 = "..." + s1; p1.insert(p1.begin(), 3, -1); }
 			if (d2 == DOWNSTREAM) { s2 += "..."; p2.resize(p2.size() + 3, -1); } else { s2 = "..." + s2; p2.insert(p2.begin(), 3, -1); }
@@ -648,7 +699,7 @@ struct writer {
 						if (c >= n_chunks) break;
 						warning_sink = &warnings[c]; // warnings of a chunk are printed after it, in row order like the reference's
 						std::ostringstream os;
-						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) { format_row(os, rows[x], extra_info); row_arena().release(); }
+						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(os, rows[x], extra_info);
 						slices[c] = os.str();
 					}
 				} catch (const std::exception& ex) { errors[t] = ex.what(); }
