@@ -490,6 +490,10 @@ struct bgzf_file {
 	}
 	void inflate_block(const block& b, u8* dst) const {
 		if (b.out_len == 0) return;
+		// STAR is run with --outBAMcompression 0 (run_arriba.sh:34): every BGZF block then holds ONE stored deflate block -- header byte 0x01 (final, type 00),
+		// LEN, ~LEN, the bytes (RFC 1951 3.2.4). Those are copied; anything else goes through zlib.
+		const u8* const in = data + b.in_off;
+		if (b.in_len == 5ull + b.out_len && in[0] == 0x01 && rd16(in + 1) == (u16) b.out_len && (u16) (rd16(in + 1) ^ rd16(in + 3)) == 0xFFFF) { memcpy(dst, in + 5, b.out_len); return; }
 		z_stream zs; memset(&zs, 0, sizeof(zs));
 		if (inflateInit2(&zs, -15) != Z_OK) fail("failed to load alignments");
 		zs.next_in = (Bytef*) (data + b.in_off); zs.avail_in = b.in_len; zs.next_out = dst; zs.avail_out = b.out_len;

@@ -126,13 +126,20 @@ def main():
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    threads = args.threads or max(1, min(64, cores // max(1, world)))
+    usable = cores   # CPUs the container may actually burn: the cgroup quota, where one is set (the GPU boxes show 128 CPUs and grant 16)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            usable = min(cores, max(1.0, float(quota) / float(period)))
+    except Exception:
+        pass
+    threads = args.threads or max(2, min(64, int(round(2 * usable / max(1, world)))))   # 2 threads per usable CPU measured best (profiles/r01i)
     wl = WORKLOADS[args.workload]
     sample_bp = args.sample_breakpoints or max(50, int(wl["breakpoints"] * 400000 / wl["fragments"]))  # ~400 k fragments: 10-30 s of reference CPU time
     metric = "chimeric fragments/s, " + SCOPE
     config = {"workload": "synthetic %s: %d fragments 2x%d bp, %d breakpoints, genome %.0f%% of hg38 size (synthetic), %d genes" %
               (args.workload, wl["fragments"], wl["read_length"], wl["breakpoints"], wl["scale"] * 100, wl["genes"]),
-              "scope": SCOPE, "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "sharding": "one independent BAM per rank (weak)"}
+              "scope": SCOPE, "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable, "sharding": "one independent BAM per rank (weak)"}
 
     if args.impl == "reference":
         if rank != 0:
