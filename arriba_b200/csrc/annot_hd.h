@@ -21,9 +21,24 @@ ARB_HD u32 region_lower_bound(const i32* region_end, u32 lo, u32 hi, i32 pos) {
 	return lo;
 }
 
-struct region_index_view { const u32* begin; const i32* end; const u32* off; const u32* items; u32 n_contigs; };
-ARB_HD region_index_view exon_index(const annot_view& a) { region_index_view v = {a.exon_region_begin, a.exon_region_end, a.exon_region_off, a.exon_region_items, a.n_contigs}; return v; }
-ARB_HD region_index_view gene_index(const annot_view& a) { region_index_view v = {a.gene_region_begin, a.gene_region_end, a.gene_region_off, a.gene_region_items, a.n_contigs}; return v; }
+// grid (optional, host side): per contig one entry per 4,096-base bin = first region whose end is >= the bin's first position, plus a final entry; it narrows
+// the binary search from the whole contig to the regions of one bin
+enum { REGION_GRID_SHIFT = 12 };
+struct region_index_view { const u32* begin; const i32* end; const u32* off; const u32* items; u32 n_contigs; const u32* grid; const u32* grid_begin; };
+ARB_HD region_index_view exon_index(const annot_view& a) { region_index_view v = {a.exon_region_begin, a.exon_region_end, a.exon_region_off, a.exon_region_items, a.n_contigs, a.exon_grid, a.exon_grid_begin}; return v; }
+ARB_HD region_index_view gene_index(const annot_view& a) { region_index_view v = {a.gene_region_begin, a.gene_region_end, a.gene_region_off, a.gene_region_items, a.n_contigs, a.gene_grid, a.gene_grid_begin}; return v; }
+// region_lower_bound over the contig's regions [lo, hi), through the grid where there is one
+ARB_HD u32 region_find(const region_index_view& ix, u32 contig, u32 lo, u32 hi, i32 pos) {
+	if (ix.grid) {
+		const u32 g0 = ix.grid_begin[contig], bins = ix.grid_begin[contig + 1] - g0 - 1;
+		u32 b = pos < 0 ? 0u : (u32) pos >> REGION_GRID_SHIFT;
+		if (b >= bins) b = bins - 1;
+		const u32 first = ix.grid[g0 + b], last = ix.grid[g0 + b + 1];
+		if (first > lo) lo = first;
+		if (last + 1 < hi) hi = last + 1;
+	}
+	return region_lower_bound(ix.end, lo, hi, pos);
+}
 
 // fixed-capacity sorted id set used inside kernels (gene sets are tiny; overflow is reported, never silently dropped)
 template <int CAP> struct idset {
@@ -66,13 +81,13 @@ template <int CAP> ARB_HD void query_index(const region_index_view& ix, u32 cont
 	if (contig >= ix.n_contigs) return;
 	const u32 lo = ix.begin[contig], hi = ix.begin[contig + 1];
 	if (start == end) {
-		u32 r = region_lower_bound(ix.end, lo, hi, start);
+		u32 r = region_find(ix, contig, lo, hi, start);
 		if (r < hi) out.assign(ix.items + ix.off[r], ix.off[r + 1] - ix.off[r]);
 		return;
 	}
 	if (start > end) { i32 t = start; start = end; end = t; }
 	idset<CAP> rs, re;
-	u32 r = region_lower_bound(ix.end, lo, hi, start);
+	u32 r = region_find(ix, contig, lo, hi, start);
 	if (r < hi) {
 		rs.assign(ix.items + ix.off[r], ix.off[r + 1] - ix.off[r]);
 		if (ix.end[r] - start <= 2) { // the region ends within 2 bp of the start: also take the next region
@@ -80,7 +95,7 @@ template <int CAP> ARB_HD void query_index(const region_index_view& ix, u32 cont
 			if (r < hi) for (u32 k = ix.off[r]; k < ix.off[r + 1]; ++k) rs.insert(ix.items[k]);
 		}
 	}
-	r = region_lower_bound(ix.end, lo, hi, end);
+	r = region_find(ix, contig, lo, hi, end);
 	if (r < hi) re.assign(ix.items + ix.off[r], ix.off[r + 1] - ix.off[r]);
 	if (r != lo && hi > lo) {
 		--r;

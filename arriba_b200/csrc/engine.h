@@ -63,6 +63,7 @@ struct annot_store {
 		v.n_contigs = n_contigs;
 		v.exon_region_begin = exon_region_begin.ptr(); v.exon_region_end = exon_region_end.ptr(); v.exon_region_off = exon_region_off.ptr(); v.exon_region_items = exon_region_items.ptr();
 		v.gene_region_begin = gene_region_begin.ptr(); v.gene_region_end = gene_region_end.ptr(); v.gene_region_off = gene_region_off.ptr(); v.gene_region_items = gene_region_items.ptr();
+		v.exon_grid = 0; v.exon_grid_begin = 0; v.gene_grid = 0; v.gene_grid_begin = 0;
 		v.contig_flags = contig_flags.ptr(); v.contig_seq_off = contig_seq_off.ptr(); v.contig_len = contig_len.ptr(); v.assembly = assembly.ptr(); v.assembly4 = assembly4_ok ? assembly4.ptr() : 0;
 		return v;
 	}

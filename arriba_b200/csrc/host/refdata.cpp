@@ -1,5 +1,6 @@
 // refdata.cpp -- see refdata.h for the behavioural contract and reference citations.
 #include "refdata.h"
+#include "../annot_hd.h"
 #include <zlib.h>
 #include <algorithm>
 #include <cstring>
@@ -348,6 +349,17 @@ template <class REC> static void build_index(const std::vector<REC>& recs, size_
 	}
 	for (size_t r = 0; r < lists.size(); ++r) { ix.items.insert(ix.items.end(), lists[r].begin(), lists[r].end()); ix.off.push_back((u32) ix.items.size()); }
 	if (ix.items.empty()) ix.items.push_back(0);
+	// search grid: per contig, for every 4,096-base bin the first region that ends at or after the bin's first position
+	ix.grid.clear(); ix.grid_begin.assign(n_contigs + 1, 0);
+	for (size_t c = 0; c < n_contigs; ++c) {
+		ix.grid_begin[c] = (u32) ix.grid.size();
+		const u32 lo = ix.begin[c], hi = ix.begin[c + 1];
+		const u32 bins = (hi > lo && ix.end[hi - 1] >= 0 ? ((u32) ix.end[hi - 1] >> REGION_GRID_SHIFT) : 0u) + 1;
+		u32 r = lo;
+		for (u32 b = 0; b < bins; ++b) { const i64 first_pos = (i64) b << REGION_GRID_SHIFT; while (r < hi && ix.end[r] < first_pos) ++r; ix.grid.push_back(r); }
+		ix.grid.push_back(hi);
+	}
+	ix.grid_begin[n_contigs] = (u32) ix.grid.size();
 	if (ix.end.empty()) ix.end.push_back(0);
 }
 
@@ -404,6 +416,7 @@ annot_view refdata::host_view() {
 	v.n_contigs = (u32) contig_ids.size();
 	v.exon_region_begin = exon_index.begin.data(); v.exon_region_end = exon_index.end.data(); v.exon_region_off = exon_index.off.data(); v.exon_region_items = exon_index.items.data();
 	v.gene_region_begin = gene_index.begin.data(); v.gene_region_end = gene_index.end.data(); v.gene_region_off = gene_index.off.data(); v.gene_region_items = gene_index.items.data();
+	v.exon_grid = exon_index.grid.data(); v.exon_grid_begin = exon_index.grid_begin.data(); v.gene_grid = gene_index.grid.data(); v.gene_grid_begin = gene_index.grid_begin.data();
 	v.contig_flags = contig_flags.data(); v.contig_seq_off = f_seq_off.data(); v.contig_len = seq_len.data(); v.assembly = assembly.data();
 	return v;
 }

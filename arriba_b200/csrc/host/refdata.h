@@ -26,6 +26,7 @@ struct exon_rec {
 
 struct region_index { // disjoint regions per contig; region r covers (end[r-1], end[r]]
 	std::vector<u32> begin; std::vector<i32> end; std::vector<u32> off; std::vector<u32> items;
+	std::vector<u32> grid, grid_begin; // annot_hd.h region_find
 };
 
 struct refdata {

@@ -59,6 +59,7 @@ struct annot_view {
 	i32* exon_region_end; u32* exon_region_off; u32* exon_region_items;   // items: exon ids ascending
 	u32* gene_region_begin;
 	i32* gene_region_end; u32* gene_region_off; u32* gene_region_items;   // items: gene ids ascending
+	const u32* exon_grid; const u32* exon_grid_begin; const u32* gene_grid; const u32* gene_grid_begin; // host-side search accelerators (annot_hd.h region_find); 0 on the device
 	// contig properties
 	u8* contig_flags;        // bit0 interesting, bit1 viral
 	u64* contig_seq_off;     // offset of the contig's sequence in assembly[]; ~0 if the sequence is not loaded
