@@ -286,7 +286,19 @@ struct worker {
 			if (g >= 0 && (u64) g < contig_len && contig_seq[g] == clip[k]) ++ext_matches;
 		}
 		if (1.0 * ext_matches / clip_len >= 0.7f) return false;
+		// Quick rejection of a window: the 7th to 14th compared base (positions 6..13 in visiting order) sit in eight consecutive reference bytes. Two
+		// mismatches among them end the exact loop below by its 14th step with at most 12 matches -- fewer than min_aligned, and matches + mismatches
+		// stays below clip_len when clip_len > 14 -- so such a window cannot be accepted. Random sequence passes this test once in ~2,500 windows.
+		const bool prefilter = clip_len > max_non_template + 8 && max_mismatches == 1 && min_aligned > max_non_template + 8 - 2;
+		const u32 probe_at = direction == +1 ? max_non_template : clip_len - max_non_template - 8;
+		u64 probe = 0; if (prefilter) memcpy(&probe, clip + probe_at, 8);
 		for (int cp = win_start; cp <= win_end; ++cp) {
+			if (prefilter) {
+				u64 refw; memcpy(&refw, contig_seq + cp + probe_at, 8);
+				const u64 x = refw ^ probe;
+				const u64 nonzero = ((x & 0x7F7F7F7F7F7F7F7FULL) + 0x7F7F7F7F7F7F7F7FULL | x) & 0x8080808080808080ULL; // 0x80 in every byte that differs
+				if ((nonzero & (nonzero - 1)) != 0) continue; // at least two bytes differ
+			}
 			u32 matches = 0, mismatches = 0;
 			i64 t_start = (i64) contig_len; i64 t_end = -1;
 			for (u32 i = 0; i < clip_len; ++i) {
