@@ -798,8 +798,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			std::vector<norm_aln> m;
 			for (size_t f = 0; f < w.frags.size(); ++f) {
 				frag_build& fb = w.frags[f];
-				m.clear();
-				for (i32 a = fb.head; a >= 0; a = w.alns[a].next) { norm_aln x; x.a = w.alns[a]; x.cigar.assign(w.cigars.begin() + x.a.cigar_off, w.cigars.begin() + x.a.cigar_off + x.a.cigar_cnt); m.push_back(x); }
+				size_t count = 0; // the scratch alignments keep their CIGAR storage from fragment to fragment
+				for (i32 a = fb.head; a >= 0; a = w.alns[a].next, ++count) {
+					if (m.size() <= count) m.resize(count + 1);
+					m[count].a = w.alns[a]; m[count].cigar.assign(w.cigars.begin() + m[count].a.cigar_off, w.cigars.begin() + m[count].a.cigar_off + m[count].a.cigar_cnt);
+				}
+				m.resize(count);
 				if (!normalise_fragment(m, fb.single_end)) { ++malformed_by_worker[t]; fb.count = 0; continue; }
 				// write the normalised alignments back (fresh CIGAR storage; slots become contiguous)
 				fb.head = (i32) w.alns.size(); fb.count = (u32) m.size();
@@ -904,9 +908,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 
 	// ---- multimappers: neighbours in name order that share the name up to the last comma (read_chimeric_alignments.cpp:792-802) ----
 	auto stem_len = [&](u32 i) { const char* s = out.names.data() + out.name_off[i]; u64 l = out.name_off[i + 1] - out.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; return k > 0 ? k - 1 : l; };
-	for (u32 i = 0; i + 1 < n; ++i) {
-		const u64 la = stem_len(i), lb = stem_len(i + 1);
-		if (la == lb && memcmp(out.names.data() + out.name_off[i], out.names.data() + out.name_off[i + 1], la) == 0) { out.fflags[i] |= FF_MULTIMAPPER; out.fflags[i + 1] |= FF_MULTIMAPPER; }
+	{ // pairs (i, i+1) tested on all threads; a fragment is flagged from either side, so the flags are set after the tests (no two threads write one byte)
+		std::vector<u8> same(n, 0);
+		parallel_for(T, n > 0 ? (size_t) n - 1 : 0, [&](int, size_t lo, size_t hi) {
+			for (size_t i = lo; i < hi; ++i) { const u64 la = stem_len((u32) i), lb = stem_len((u32) i + 1); same[i] = la == lb && memcmp(out.names.data() + out.name_off[i], out.names.data() + out.name_off[i + 1], la) == 0; }
+		});
+		parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) if (same[i] || (i > 0 && same[i - 1])) out.fflags[i] |= FF_MULTIMAPPER; });
 	}
 	stats.t_finalize = now_s() - tf;
 	lap("multimapper flags");
