@@ -67,11 +67,10 @@ struct cand_key_hash { // value-identical to the reference's recursive tuple has
 // one singly linked list; a bucket stores the node BEFORE its first node; a new node goes to the front of its bucket, or to the front of the whole list if
 // the bucket was empty; growing re-threads the list in its current order (bits/hashtable.h: _M_insert_bucket_begin, _M_rehash_aux). Replaying that with
 // index arrays instead of a real map gives the same order without one heap node per candidate; bucket counts come from the library's own policy object.
-void event_table::replay_iteration_order() {
+void event_table::replay_iteration_order(int hash_threads) {
 	const u32 NONE = 0xFFFFFFFFu, BEFORE_BEGIN = n; // list positions: 0..n-1 candidates, n = the list head sentinel
 	std::vector<size_t> code(n);
-	cand_key_hash hasher;
-	for (u32 k = 0; k < n; ++k) code[k] = hasher(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k]));
+	parallel_rows(hash_threads, n, [&](u32 k) { code[k] = cand_key_hash()(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k])); });
 	std::vector<u32> next((size_t) n + 1, NONE);
 	std::vector<u32> bucket(1, NONE); // node before the first node of the bucket
 	std::__detail::_Prime_rehash_policy policy;
@@ -126,6 +125,7 @@ void pipeline::log_remaining(const char* what) { std::ostringstream s; s << what
 
 // ------------------------------------------------------------------------------------------- device <-> host state
 void pipeline::fetch_candidates() {
+	stage_laps laps("fetch");
 	uint32_t n; uint64_t n1, n2, nd;
 	check(ctx, arb_candidates_size(ctx, &n, &n1, &n2, &nd), "arb_candidates_size");
 	event_table& e = ev;
@@ -140,11 +140,11 @@ void pipeline::fetch_candidates() {
 	c.direction1 = e.dir1.data(); c.direction2 = e.dir2.data(); c.split_reads1 = e.split_reads1.data(); c.split_reads2 = e.split_reads2.data(); c.discordant_mates = e.discordant_mates.data();
 	c.filter = e.filter.data(); c.bits = e.bits.data(); c.bits2 = e.bits2.data(); c.anchor_start1 = e.anchor1.data(); c.anchor_start2 = e.anchor2.data(); c.evalue = e.evalue.data();
 	c.list1_off = e.list1_off.data(); c.list2_off = e.list2_off.data(); c.listd_off = e.listd_off.data(); c.list1 = e.list1.data(); c.list2 = e.list2.data(); c.listd = e.listd.data();
-	stage_laps laps("fetch");
+	laps.lap("host columns sized");
 	check(ctx, arb_get_candidates(ctx, &c), "arb_get_candidates");
 	laps.lap("device -> host");
 	e.list1.resize(n1); e.list2.resize(n2); e.listd.resize(nd);
-	e.replay_iteration_order();
+	e.replay_iteration_order(threads);
 	laps.lap("iteration order");
 	// mirror the canonical mate order the device established for listed discordant mates (fusions.cpp:414-421)
 	std::vector<u8> swapped(frags.n);
