@@ -128,6 +128,7 @@ void pipeline::fetch_candidates() {
 	stage_laps laps("fetch");
 	uint32_t n; uint64_t n1, n2, nd;
 	check(ctx, arb_candidates_size(ctx, &n, &n1, &n2, &nd), "arb_candidates_size");
+	laps.lap("sizes");
 	event_table& e = ev;
 	e.n = n;
 	e.gene1.resize(n); e.gene2.resize(n); e.contig1.resize(n); e.contig2.resize(n); e.bp1.resize(n); e.bp2.resize(n); e.dir1.resize(n); e.dir2.resize(n);
@@ -189,7 +190,7 @@ void pipeline::merge_adjacent() {
 			l1[es[k].winner].insert(l1[es[k].winner].end(), l1[es[k].loser].begin(), l1[es[k].loser].end());
 			l2[es[k].winner].insert(l2[es[k].winner].end(), l2[es[k].loser].begin(), l2[es[k].loser].end());
 		}
-		std::vector<u32> o1((size_t) ev.n + 1, 0), o2((size_t) ev.n + 1, 0), n1, n2;
+		column<u32> o1((size_t) ev.n + 1, 0), o2((size_t) ev.n + 1, 0), n1, n2;
 		for (u32 k = 0; k < ev.n; ++k) {
 			if (touched[k]) { n1.insert(n1.end(), l1[k].begin(), l1[k].end()); n2.insert(n2.end(), l2[k].begin(), l2[k].end()); }
 			else { n1.insert(n1.end(), ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); n2.insert(n2.end(), ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]); }
@@ -469,7 +470,7 @@ void pipeline::recover_internal_tandem_duplication() { // recover_internal_tande
 
 void pipeline::filter_both_intronic() { // filter_both_intronic.cpp
 	const u32 N = frags.n;
-	auto has_exonic = [&](const std::vector<u32>& list, u32 lo, u32 hi) {
+	auto has_exonic = [&](const column<u32>& list, u32 lo, u32 hi) {
 		for (u32 p = lo; p < hi; ++p) { const u32 i = list[p]; if (labels[i] != F_none) continue; for (u32 s = 0; s < frags.n_aln[i]; ++s) if (frags.aflags[(size_t) s * N + i] & AF_EXONIC) return true; }
 		return false;
 	};
@@ -592,7 +593,7 @@ unsigned int pipeline::spliced_support(u32 k, const std::vector<u32>& reads_by_g
 		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
 	}
 	unsigned int multi = 0, unique = 0;
-	auto scan = [&](const std::vector<u32>& list, u32 lo, u32 hi) { for (u32 p = lo; p < hi; ++p) { if (frags.fflags[list[p]] & FF_MULTIMAPPER) ++multi; else if (labels[list[p]] == F_none) ++unique; } };
+	auto scan = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 p = lo; p < hi; ++p) { if (frags.fflags[list[p]] & FF_MULTIMAPPER) ++multi; else if (labels[list[p]] == F_none) ++unique; } };
 	scan(ev.list1, ev.list1_off[k], ev.list1_off[k + 1]); scan(ev.list2, ev.list2_off[k], ev.list2_off[k + 1]); scan(ev.listd, ev.listd_off[k], ev.listd_off[k + 1]);
 	if (multi >= 0.5 * (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) return 0;
 	if (unique == 0) return 1;

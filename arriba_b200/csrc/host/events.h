@@ -16,12 +16,13 @@ namespace arb { namespace host {
 
 struct event_table {
 	u32 n;
-	std::vector<u32> gene1, gene2, split_reads1, split_reads2, discordant_mates;
-	std::vector<u16> contig1, contig2;
-	std::vector<i32> bp1, bp2, anchor1, anchor2;
-	std::vector<u8> dir1, dir2, filter, bits, bits2, confidence;
-	std::vector<float> evalue;
-	std::vector<u32> list1_off, list2_off, listd_off, list1, list2, listd; // CSR, fragment indices in name order
+	// column<T>: resize() does not touch new elements (they are all written by the device-to-host copies that follow)
+	column<u32> gene1, gene2, split_reads1, split_reads2, discordant_mates;
+	column<u16> contig1, contig2;
+	column<i32> bp1, bp2, anchor1, anchor2;
+	column<u8> dir1, dir2, filter, bits, bits2, confidence;
+	column<float> evalue;
+	column<u32> list1_off, list2_off, listd_off, list1, list2, listd; // CSR, fragment indices in name order
 	std::vector<u32> order; // order[k] = candidate visited k-th by the reference's loops
 	event_table(): n(0) {}
 

@@ -132,7 +132,7 @@ struct writer {
 	bool has_assembly(u32 contig) const { return ref.has_sequence(contig); }
 
 	// ---- pileup of the supporting reads around one breakpoint (output_fusions.cpp:25-107)
-	void pileup_reads(const std::vector<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pile_builder& pileup) const {
+	void pileup_reads(const column<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pile_builder& pileup) const {
 		std::map<std::pair<i32, i32>, unsigned int> introns;
 		for (u32 x = lo; x < hi; ++x) {
 			const u32 frag = list[x];
@@ -251,7 +251,7 @@ struct writer {
 		// non-template bases between the fused segments: most frequent surplus of clipped bases over the read length
 		unsigned int non_template = 0; std::map<unsigned int, unsigned int> count;
 		for (int which = 0; which < 2; ++which) {
-			const std::vector<u32>& list = which == 0 ? e.list1 : e.list2;
+			const column<u32>& list = which == 0 ? e.list1 : e.list2;
 			for (u32 x = which == 0 ? a1 : a2; x < (which == 0 ? b1 : b2); ++x) {
 				const u32 s = f.idx(list[x], SPLIT_READ), u = f.idx(list[x], SUPPLEMENTARY);
 				const unsigned int cs = f.fwd(s) ? f.preclip(s) : f.postclip(s), cu = f.fwd(u) ? f.postclip(u) : f.preclip(u);
@@ -633,7 +633,7 @@ struct writer {
 			unsigned int filter_count[38]; bool filter_present[38];
 			for (int f = 0; f < 38; ++f) { filter_count[f] = 0; filter_present[f] = false; }
 			if (e.filter[k] != F_none) filter_present[e.filter[k]] = true;
-			auto tally = [&](const std::vector<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
+			auto tally = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
 			tally(e.list1, e.list1_off[k], e.list1_off[k + 1]); tally(e.list2, e.list2_off[k], e.list2_off[k + 1]); tally(e.listd, e.listd_off[k], e.listd_off[k + 1]);
 			out << "\t" << (ref.genes[g5].is_dummy ? "." : ref.genes[g5].gene_id) << "\t" << (ref.genes[g3].is_dummy ? "." : ref.genes[g3].gene_id)
 			    << "\t" << (tr5 < 0 ? "." : ref.transcripts[tr5].name) << "\t" << (tr3 < 0 ? "." : ref.transcripts[tr3].name)
@@ -650,7 +650,7 @@ struct writer {
 			out << "\t" << tseq << "\t" << pep << "\t";
 			if (extra_info && e.n_list1(k) + e.n_list2(k) + e.n_listd(k) > 0) {
 				bool first_name = true;
-				auto names = [&](const std::vector<u32>& list, u32 lo, u32 hi) {
+				auto names = [&](const column<u32>& list, u32 lo, u32 hi) {
 					for (u32 r = lo; r < hi; ++r) {
 						if (!first_name) out << ",";
 						first_name = false;
