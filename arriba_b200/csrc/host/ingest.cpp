@@ -16,9 +16,44 @@
 #include <iostream>
 #include <stdexcept>
 #include <thread>
+#include <mutex>
 #include <unordered_map>
 
 namespace arb { namespace host {
+
+// ------------------------------------------------------------------------------------------- recycled host blocks (ingest.h)
+namespace {
+struct host_block_pool {
+	std::mutex lock; std::vector<std::pair<size_t, void*> > free_blocks; size_t held;
+	host_block_pool(): held(0) {}
+};
+host_block_pool& block_pool() { static host_block_pool* p = new host_block_pool(); return *p; } // never destroyed: blocks may be returned during static destruction
+}
+void* host_block_get(size_t bytes, size_t& granted) {
+	granted = bytes;
+	host_block_pool& pool = block_pool();
+	{
+		std::lock_guard<std::mutex> g(pool.lock);
+		for (size_t k = pool.free_blocks.size(); k-- > 0; ) if (pool.free_blocks[k].first == bytes) {
+			void* p = pool.free_blocks[k].second; pool.free_blocks[k] = pool.free_blocks.back(); pool.free_blocks.pop_back(); pool.held -= bytes; return p;
+		}
+	}
+	return malloc(bytes);
+}
+void host_block_put(void* p, size_t granted) {
+	host_block_pool& pool = block_pool();
+	{
+		std::lock_guard<std::mutex> g(pool.lock);
+		if (pool.held + granted <= ((size_t) 64 << 30)) { pool.free_blocks.push_back(std::make_pair(granted, p)); pool.held += granted; return; }
+	}
+	free(p);
+}
+void host_block_trim() {
+	host_block_pool& pool = block_pool();
+	std::lock_guard<std::mutex> g(pool.lock);
+	for (size_t k = 0; k < pool.free_blocks.size(); ++k) free(pool.free_blocks[k].second);
+	pool.free_blocks.clear(); pool.held = 0;
+}
 
 static void fail(const std::string& m) { throw std::runtime_error(m); }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

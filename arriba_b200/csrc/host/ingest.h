@@ -6,6 +6,7 @@
 #pragma once
 #include <string>
 #include <vector>
+#include <cstdlib>
 #include <memory>
 #include <utility>
 #include <new>
@@ -22,13 +23,33 @@ struct coverage_windows { // 20 bp windows (read_stats.hpp:14)
 	int get_coverage(u32 contig, i32 position, u32 direction) const;
 };
 
-// vector whose resize() leaves new elements uninitialised: the large columns are first touched (and zeroed) by the threads that fill them
-template <class T> struct default_init_allocator: std::allocator<T> {
+// Large host blocks are recycled inside the process: the first touch of fresh pages costs ~2 us per 4 KiB page on the measured hosts (more than filling
+// them), and a process that runs sample after sample would pay it for gigabytes of columns every time. Blocks of 1 MiB and more go back to a free list per
+// size class (steps of 25 %) instead of the C library; host_block_trim() (arb_release_host_memory) hands them to the system.
+void* host_block_get(size_t bytes, size_t& granted);
+void host_block_put(void* p, size_t granted);
+void host_block_trim();
+
+// vector whose resize() leaves new elements uninitialised: the large columns are first touched (and zeroed where needed) by the threads that fill them
+template <class T> struct default_init_allocator {
+	typedef T value_type;
 	template <class U> struct rebind { typedef default_init_allocator<U> other; };
 	default_init_allocator() {}
 	template <class U> default_init_allocator(const default_init_allocator<U>&) {}
+	static size_t class_of(size_t bytes) { size_t c = (size_t) 1 << 20; while (c < bytes) c += c / 4; return c; }
+	T* allocate(size_t n) {
+		const size_t bytes = n * sizeof(T);
+		void* p;
+		if (bytes >= ((size_t) 1 << 20)) { size_t granted; p = host_block_get(class_of(bytes), granted); }
+		else p = malloc(bytes ? bytes : 1);
+		if (!p) throw std::bad_alloc();
+		return (T*) p;
+	}
+	void deallocate(T* p, size_t n) { const size_t bytes = n * sizeof(T); if (bytes >= ((size_t) 1 << 20)) host_block_put(p, class_of(bytes)); else free(p); }
 	template <class U> void construct(U* p) { ::new ((void*) p) U; }
 	template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new ((void*) p) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+	template <class U> bool operator==(const default_init_allocator<U>&) const { return true; }
+	template <class U> bool operator!=(const default_init_allocator<U>&) const { return false; }
 };
 template <class T> using column = std::vector<T, default_init_allocator<T> >;
 

@@ -195,6 +195,8 @@ int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 /* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver
  * (no-op while a context on the current device still holds blocks). */
 void arb_release_device_memory(void);
+/* Large host columns are recycled the same way (first touch of fresh pages is what costs); this returns the free ones to the system. */
+void arb_release_host_memory(void);
 
 /* ---- whole-run driver ---------------------------------------------------------------------------------------
  * What the `arriba` executable does (source/arriba.cpp:79-631): reference + annotation loading, BAM ingest
