@@ -18,6 +18,7 @@ WORKLOADS = {
     "mid_1M_2x101_5k": dict(scale=0.02, genes=4000, breakpoints=5000, fragments=1000000, read_length=101),
     "tiny_20k": dict(scale=0.001, genes=400, breakpoints=200, fragments=20000, read_length=101),
 }
+UNIT = "reads/s"   # chimeric fragments per second
 SCOPE = "ingest..fusions.tsv"  # one step = BAM ingest -> read filters -> candidates -> event filters -> fusions.tsv + discarded.tsv (reference loading excluded)
 
 
@@ -136,10 +137,10 @@ def main():
     threads = args.threads or max(2, min(64, int(round(2 * usable / max(1, world)))))   # 2 threads per usable CPU measured best (profiles/r01i)
     wl = WORKLOADS[args.workload]
     sample_bp = args.sample_breakpoints or max(50, int(wl["breakpoints"] * 400000 / wl["fragments"]))  # ~400 k fragments: 10-30 s of reference CPU time
-    metric = "chimeric fragments/s, " + SCOPE
+    metric = "chimeric reads/sec end-to-end (ingest→fusions.tsv)"   # BASELINE.json; a "read" is one chimeric fragment (read pair + supplementary), the unit the reference counts
     config = {"workload": "synthetic %s: %d fragments 2x%d bp, %d breakpoints, genome %.0f%% of hg38 size (synthetic), %d genes" %
               (args.workload, wl["fragments"], wl["read_length"], wl["breakpoints"], wl["scale"] * 100, wl["genes"]),
-              "scope": SCOPE, "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable, "sharding": "one independent BAM per rank (weak)"}
+              "scope": SCOPE, "value_is": "device-resident stages (CUDA events, fragment table in HBM)", "e2e_is": "BAM on disk -> both TSV files on disk through the public Pipeline API (the headline)", "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable, "sharding": "one independent BAM per rank (weak)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -150,11 +151,11 @@ def main():
             n, scope_s, total = reference_run(prefix, cores)
             vals.append((n / scope_s, n, scope_s, total))
         v, n, scope_s, total = max(vals)
-        line = {"impl": "reference", "metric": metric, "value": v, "unit": "fragments/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": scope_s * 1e3,
+        line = {"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": scope_s * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "fragments/s", "cores": 1, "kind": "reference",
+                "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
                                  "sample": "first %d breakpoints of the workload at full depth = %d fragments; reference's own time stamps over %s (1 s resolution); decode threads -@ %d have no effect in the shim build" % (sample_bp, n, SCOPE, cores)},
-                "e2e": {"value": v, "unit": "fragments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         print(json.dumps(line))
         return
 
@@ -229,7 +230,7 @@ def main():
     if dist and not sharded and not args.no_sharded_extra:   # the same sample once more as ONE job over all ranks: exercises the two all-gathers
         r = one_step(True)
         t = torch.tensor([r[1]], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        extra_sharded = {"e2e_seconds": float(t[0]), "e2e_value": r[0] / float(t[0]), "unit": "fragments/s", "scaling": "strong",
+        extra_sharded = {"e2e_seconds": float(t[0]), "e2e_value": r[0] / float(t[0]), "unit": UNIT, "scaling": "strong",
                          "note": "one sample partitioned by contig pair over all ranks, 2 NCCL all-gathers; host decode is replicated, so this mode buys device memory and device time, not host time"}
     sampler.stop_flag = True; sampler.join(timeout=2)
     launches = L.load().arb_kernel_launches() - launches1
@@ -256,10 +257,10 @@ def main():
     except Exception:
         pass
     jobs = 1 if sharded else world
-    line = {"metric": metric, "value": n_frag * jobs / (dev_ms * 1e-3), "unit": "fragments/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": metric, "value": n_frag * jobs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": n_frag * jobs / e2e_s, "unit": "fragments/s", "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
+            "e2e": {"value": n_frag * jobs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
                     "seconds_per_step": e2e_s, "host_seconds": {n: round(st.seconds[i], 3) for i, n in enumerate(L.STEP_NAMES) if i > 0},
                     "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
@@ -278,7 +279,7 @@ def main():
     if not args.no_cpu_baseline:
         sp = ensure_world(args.workload, sample_bp)
         n, scope_s, total = reference_run(sp, cores)
-        line["cpu_baseline"] = {"value": n / scope_s, "unit": "fragments/s", "cores": 1, "kind": "reference",
+        line["cpu_baseline"] = {"value": n / scope_s, "unit": UNIT, "cores": 1, "kind": "reference",
                                 "sample": "first %d breakpoints of the workload at full depth = %d fragments; unmodified reference (oracle/_ref/arriba), its own time stamps over %s" % (sample_bp, n, SCOPE),
                                 "whole_run_seconds": total, "host_cores_available": cores}
     print(json.dumps(line))
