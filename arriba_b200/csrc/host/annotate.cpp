@@ -27,8 +27,11 @@ template <class F> static void parallel_ranges(int threads, size_t n, F f) {
 
 // gene sets under construction: per alignment a reference into one of the per-thread pools
 struct gene_refs {
-	std::vector<std::vector<u32> > pools; std::vector<u64> off; std::vector<u16> cnt; std::vector<u8> pool;
-	void init(size_t n_aln, int threads) { pools.assign(threads, std::vector<u32>()); off.assign(n_aln, 0); cnt.assign(n_aln, 0); pool.assign(n_aln, 0); }
+	std::vector<std::vector<u32> > pools; column<u64> off; column<u16> cnt; column<u8> pool;
+	void init(size_t n_aln, int threads) { // only `cnt` has to start at zero; it is cleared by the threads that will write it
+		pools.assign(threads, std::vector<u32>()); off.resize(n_aln); cnt.resize(n_aln); pool.resize(n_aln);
+		parallel_ranges(threads, n_aln, [&](int, size_t lo, size_t hi) { memset(cnt.data() + lo, 0, (hi - lo) * sizeof(u16)); });
+	}
 	const u32* get(size_t a) const { return cnt[a] ? pools[pool[a]].data() + off[a] : NULL; }
 	void set(size_t a, int thread, const u32* g, u32 n) { std::vector<u32>& p = pools[thread]; off[a] = p.size(); cnt[a] = (u16) n; pool[a] = (u8) thread; p.insert(p.end(), g, g + n); }
 	void load(size_t a, gset& s) const { s.clear(); s.assign(get(a), cnt[a]); }
@@ -175,16 +178,22 @@ void annotate_fragments(pipeline& p) {
 	std::vector<unmapped_t> unmapped;
 	{
 		const frag_view f = ft.view();
-		for (u32 i = 0; i < n; ++i) {
-			if (f.n_aln[i] == 3) {
-				const u32 s = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
-				if (refs.cnt[s] == 0) { unmapped_t x = {f.contig[s], f.fwd(s) ? f.start[s] : f.end[s]}; unmapped.push_back(x); }
-				if (refs.cnt[u] == 0) { unmapped_t x = {f.contig[u], f.fwd(u) ? f.end[u] : f.start[u]}; unmapped.push_back(x); }
-			} else for (u32 s = 0; s < 2; ++s) {
-				const u32 a = f.idx(i, s);
-				if (refs.cnt[a] == 0) { unmapped_t x = {f.contig[a], f.fwd(a) ? f.end[a] : f.start[a]}; unmapped.push_back(x); }
+		std::vector<std::vector<unmapped_t> > part(T);
+		parallel_ranges(T, n, [&](int t, size_t lo, size_t hi) {
+			std::vector<unmapped_t>& out = part[t];
+			for (size_t k = lo; k < hi; ++k) {
+				const u32 i = (u32) k;
+				if (f.n_aln[i] == 3) {
+					const u32 s = f.idx(i, SPLIT_READ), u = f.idx(i, SUPPLEMENTARY);
+					if (refs.cnt[s] == 0) { unmapped_t x = {f.contig[s], f.fwd(s) ? f.start[s] : f.end[s]}; out.push_back(x); }
+					if (refs.cnt[u] == 0) { unmapped_t x = {f.contig[u], f.fwd(u) ? f.end[u] : f.start[u]}; out.push_back(x); }
+				} else for (u32 s = 0; s < 2; ++s) {
+					const u32 a = f.idx(i, s);
+					if (refs.cnt[a] == 0) { unmapped_t x = {f.contig[a], f.fwd(a) ? f.end[a] : f.start[a]}; out.push_back(x); }
+				}
 			}
-		}
+		});
+		for (int t = 0; t < T; ++t) unmapped.insert(unmapped.end(), part[t].begin(), part[t].end());
 	}
 	const size_t first_dummy = ref.genes.size();
 	if (!unmapped.empty()) {
@@ -254,10 +263,16 @@ void annotate_fragments(pipeline& p) {
 
 	laps.lap("pass 2 (dummy genes)");
 	// final CSR gene columns
-	std::vector<u64> at(3 * (size_t) n + 1, 0);
-	for (size_t a = 0; a < 3 * (size_t) n; ++a) at[a + 1] = at[a] + refs.cnt[a];
-	if (at.back() > 0xFFFFFFFFull) throw std::runtime_error("gene pool exceeds 2^32 entries");
-	ft.genes.assign(at.back() + 1, 0);
+	// offsets: per-slice sums on the threads, slice bases serially, then the prefix inside every slice
+	const size_t A = 3 * (size_t) n;
+	column<u64> at(A + 1);
+	std::vector<u64> slice_sum(T + 1, 0);
+	parallel_ranges(T, A, [&](int t, size_t lo, size_t hi) { u64 s = 0; for (size_t a = lo; a < hi; ++a) s += refs.cnt[a]; slice_sum[t + 1] = s; });
+	for (int t = 0; t < T; ++t) slice_sum[t + 1] += slice_sum[t];
+	parallel_ranges(T, A, [&](int t, size_t lo, size_t hi) { u64 s = slice_sum[t]; for (size_t a = lo; a < hi; ++a) { at[a] = s; s += refs.cnt[a]; } });
+	at[A] = slice_sum[T];
+	if (at[A] > 0xFFFFFFFFull) throw std::runtime_error("gene pool exceeds 2^32 entries");
+	ft.genes.resize(at[A] + 1); ft.genes[at[A]] = 0;
 	parallel_ranges(T, 3 * (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t a = lo; a < hi; ++a) { ft.genes_off[a] = (u32) at[a]; ft.genes_cnt[a] = refs.cnt[a]; if (refs.cnt[a]) memcpy(&ft.genes[at[a]], refs.get(a), 4ull * refs.cnt[a]); }
 	});
