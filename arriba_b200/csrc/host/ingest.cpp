@@ -170,7 +170,7 @@ struct worker {
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
 	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size;
 	void park_waiting() { if (waiting_ptr) { pending.emplace(waiting_key, std::vector<u8>(waiting_ptr, waiting_ptr + waiting_size)); waiting_ptr = NULL; } } // before the chunk buffer is recycled
-	worker(): waiting_ptr(NULL), waiting_size(0), cov(NULL), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
+	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
 
 	u32 fragment(const std::string& name, bool* created = NULL) {
 		if (name_slots.empty()) name_slots.assign(1u << 12, 0);

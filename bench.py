@@ -227,7 +227,10 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - t_begin
     extra_sharded = None
-    if dist and not sharded and not args.no_sharded_extra:   # the same sample once more as ONE job over all ranks: exercises the two all-gathers
+    slowest = torch.tensor([max(r[1] for r in results)], device="cuda", dtype=torch.float64)
+    if dist:
+        dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
+    if dist and not sharded and not args.no_sharded_extra and float(slowest[0]) < 60.0:   # the same sample once more as ONE job over all ranks: exercises the two all-gathers (skipped when a step takes more than a minute)
         r = one_step(True)
         t = torch.tensor([r[1]], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         extra_sharded = {"e2e_seconds": float(t[0]), "e2e_value": r[0] / float(t[0]), "unit": UNIT, "scaling": "strong",
