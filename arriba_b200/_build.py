@@ -89,6 +89,18 @@ def build_cli(force=False):
     return CLI_BIN
 
 
+HOSTSIM_CLI = os.path.join(ROOT, "tests", "hostsim", "arriba_hostsim")
+
+
+def build_cli_hostsim(force=False):
+    """The same `arriba` front end linked against the CPU stand-in: lets the CPU test-suite drive the command line. Test-only, lives under tests/."""
+    lib = build_hostsim()
+    src = os.path.join(CSRC, "host", "cli_main.cpp")
+    if force or _newer(HOSTSIM_CLI, [src, lib]):
+        _run(["g++"] + GXX_FLAGS + ["-o", HOSTSIM_CLI, src, "-L", os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath,$ORIGIN", "-lpthread"])
+    return HOSTSIM_CLI
+
+
 def build_hostsim(force=False):
     """CPU test-suite stand-in: same rule functors, sequential primitives. Never loaded by the package or the bench."""
     if not force and not _newer(HOSTSIM_LIB, _all_sources()):

@@ -524,7 +524,7 @@ struct bgzf_file {
 		u64 off = 0, out = 0;
 		while (off + 18 <= size) {
 			const u8* h = data + off;
-			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fail("failed to load alignments"); // not BGZF (SAM text / CRAM are not supported)
+			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fail(off == 0 ? "failed to read SAM header" : "failed to load alignments"); // not BGZF (SAM text / CRAM are not supported); at the start of the file no header can be read (arriba.cpp:122)
 			const u32 xlen = rd16(h + 10);
 			u32 bsize = 0; bool found = false;
 			for (u32 x = 0; x + 4 <= xlen;) { const u8* e = h + 12 + x; const u32 slen = rd16(e + 2); if (e[0] == 'B' && e[1] == 'C' && slen == 2) { bsize = rd16(e + 4) + 1u; found = true; } x += 4 + slen; }

@@ -1,0 +1,58 @@
+"""The command line of the reference, option by option: the drop-in executable (here linked against the CPU stand-in) must write the same two files as
+the reference run with the same arguments (options.cpp:270-485; defaults options.cpp:71-107)."""
+import os
+import subprocess
+import pytest
+import worldutil
+from arriba_b200 import _build
+
+OPTION_SETS = [
+    ("-X",),                                        # extra columns for discarded fusions
+    ("-s", "yes"), ("-s", "reverse"), ("-s", "no"),
+    ("-u",),                                        # duplicates marked by the aligner
+    ("-f", "blacklist,duplicates,mismatches"), ("-f", "blacklist,homologs,mismappers,merge_adjacent"), ("-f", "blacklist,low_entropy,homopolymer,read_through,select_best"),
+    ("-E", "0.05", "-S", "3"), ("-m", "0.5", "-L", "0.1"), ("-H", "4", "-R", "5000"), ("-A", "30", "-M", "2"),
+    ("-K", "0.3", "-V", "0.05"), ("-F", "300", "-U", "50"), ("-Q", "0.9", "-e", "0.5"), ("-l", "50", "-z", "0.2", "-Z", "5"),
+    ("-i", "1,2,3,4,5,X"),
+]
+
+
+@pytest.fixture(scope="module")
+def cli():
+    return _build.build_cli_hostsim()
+
+
+@pytest.mark.parametrize("extra", OPTION_SETS, ids=lambda o: " ".join(o))
+def test_cli_option_parity(worlds, cli, tmp_path, extra):
+    base = ("-f", "blacklist")
+    args = tuple(extra) if "-f" in extra else base + tuple(extra)
+    w = worlds.get("small", oracle_args=args)
+    out = str(tmp_path / "fusions.tsv"); disc = str(tmp_path / "fusions.discarded.tsv")
+    r = subprocess.run([cli, "-x", w.prefix + ".bam", "-g", w.prefix + ".gtf", "-a", w.prefix + ".fa", "-o", out, "-O", disc, "-@", "3"] + list(args), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out, "rb").read() == open(os.path.join(w.outdir, "fusions.tsv"), "rb").read(), "fusions.tsv differs with options %s" % (args,)
+    assert open(disc, "rb").read() == open(os.path.join(w.outdir, "fusions.discarded.tsv"), "rb").read(), "fusions.discarded.tsv differs with options %s" % (args,)
+
+
+def test_cli_error_parity(worlds, cli, tmp_path):
+    """Unusable inputs: same ERROR line and exit code as the reference (common.hpp:330, read_chimeric_alignments.cpp:566-609, annotation.cpp, assembly.cpp)."""
+    w = worlds.get("small")
+    oracle = _build.build_oracle()
+    d = str(tmp_path)
+    bam = open(w.prefix + ".bam", "rb").read()
+    gtf = open(w.prefix + ".gtf").read().split("\n")
+    fa = open(w.prefix + ".fa").read().split(">")
+    open(d + "/truncated.bam", "wb").write(bam[:len(bam) // 2 + 777])
+    open(d + "/empty.bam", "wb").write(b"")
+    open(d + "/garbage.bam", "wb").write(b"not a bam file at all" * 100)
+    open(d + "/empty.gtf", "w").write("")
+    open(d + "/no_exons.gtf", "w").write("\n".join(l for l in gtf if "\texon\t" not in l))
+    open(d + "/two_contigs.fa", "w").write(">" + ">".join(fa[1:3]))
+    cases = [(d + "/truncated.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/empty.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/garbage.bam", w.prefix + ".gtf", w.prefix + ".fa"),
+             (w.prefix + ".bam", d + "/empty.gtf", w.prefix + ".fa"), (w.prefix + ".bam", d + "/no_exons.gtf", w.prefix + ".fa"), (w.prefix + ".bam", w.prefix + ".gtf", d + "/two_contigs.fa")]
+    for b, g, a in cases:
+        seen = []
+        for exe in (oracle, cli):
+            r = subprocess.run([exe, "-x", b, "-g", g, "-a", a, "-o", d + "/o.tsv", "-O", d + "/d.tsv", "-f", "blacklist"] + (["-@", "2"] if exe == cli else []), capture_output=True, text=True, timeout=300)
+            seen.append((r.returncode, [l for l in r.stderr.split("\n") if l.startswith("ERROR")]))
+        assert seen[0][0] == 1 and seen[0] == seen[1], (b, g, a, seen)
