@@ -58,3 +58,24 @@ def test_cli_cuda(worlds, tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(out, "rb").read() == open(os.path.join(w.outdir, "fusions.tsv"), "rb").read()
     assert open(disc, "rb").read() == open(os.path.join(w.outdir, "fusions.discarded.tsv"), "rb").read()
+
+
+def test_e2e_hostsim_compressed_chr_names_normal_pairs(worlds, hostsim_lib, tmp_path):
+    """Deflate-compressed BGZF blocks (zlib path instead of the stored-block copy), `chr`-prefixed contig names in the BAM header (remove_chr, arriba.cpp:52-58),
+    and as many proper pairs as chimeric fragments (mate pairing, coverage, read-through extraction on normal reads)."""
+    check_e2e(worlds.get("zchr", seed=11, extra=("--compress", "6", "--chr", "--normal-frac", "0.5")), hostsim_lib, tmp_path, threads=3)
+
+
+def test_e2e_hostsim_deep_breakpoints(worlds, hostsim_lib, tmp_path):
+    """A few breakpoints far beyond the subsampling threshold of 300 supporting reads (-U; fusions.cpp:423-441)."""
+    check_e2e(worlds.get("deep", seed=12, breakpoints=300, extra=("--deep-frac", "0.02", "--deep-depth", "1500")), hostsim_lib, tmp_path, threads=5)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_compressed_chr_names_normal_pairs(worlds, cuda_lib, tmp_path):
+    check_e2e(worlds.get("zchr", seed=11, extra=("--compress", "6", "--chr", "--normal-frac", "0.5")), cuda_lib, tmp_path, threads=8)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_deep_breakpoints(worlds, cuda_lib, tmp_path):
+    check_e2e(worlds.get("deep", seed=12, breakpoints=300, extra=("--deep-frac", "0.02", "--deep-depth", "1500")), cuda_lib, tmp_path, threads=8)
