@@ -166,6 +166,16 @@ struct writer {
 					default: break;
 				}
 				if (as_match) {
+					const i32 run = len - carry;
+					const i64 x0 = (i64) ref_off - pileup.lo;
+					if (run > 0 && read_off >= 0 && (size_t) read_off + (size_t) run <= seq_size && x0 >= 0 && x0 + run <= 2 * pile_builder::WINDOW) {
+						// the whole block lies in the flat window and inside the read: claim the cells once, then one counter per base without any checks
+						for (i32 b = 0; b < run; ++b) if (!pileup.used[x0 + b]) { pileup.used[x0 + b] = 1; pileup.used_list.push_back((u32) (x0 + b)); }
+						pile_builder::cell* const cells = &pileup.dense[x0];
+						if (reverse_complement) for (i32 b = 0; b < run; ++b) ++cells[b].n[symbol_of_code[16 + nt16_at(packed, (u32) (seq_size - 1 - (size_t) (read_off + b)))]];
+						else for (i32 b = 0; b < run; ++b) ++cells[b].n[symbol_of_code[nt16_at(packed, (u32) (read_off + b))]];
+						read_off += run; ref_off += run;
+					} else
 					for (i32 b = 0; b < len - carry; ++b, ++read_off, ++ref_off) { // the hot loop of the writer: one counter per base
 						if ((size_t) read_off < seq_size) ++pileup.at(ref_off).n[symbol_of_code[reverse_complement ? nt16_at(packed, (u32) (seq_size - 1 - read_off)) + 16 : nt16_at(packed, (u32) read_off)]];
 						else pileup.add(ref_off, std::string());
