@@ -27,11 +27,8 @@ template <class F> static void parallel_ranges(int threads, size_t n, F f) {
 
 // gene sets under construction: per alignment a reference into one of the per-thread pools
 struct gene_refs {
-	std::vector<std::vector<u32> > pools; column<u64> off; column<u16> cnt; column<u8> pool;
-	void init(size_t n_aln, int threads) { // only `cnt` has to start at zero; it is cleared by the threads that will write it
-		pools.assign(threads, std::vector<u32>()); off.resize(n_aln); cnt.resize(n_aln); pool.resize(n_aln);
-		parallel_ranges(threads, n_aln, [&](int, size_t lo, size_t hi) { memset(cnt.data() + lo, 0, (hi - lo) * sizeof(u16)); });
-	}
+	std::vector<std::vector<u32> > pools; column<u64> off; std::vector<u16> cnt; column<u8> pool;
+	void init(size_t n_aln, int threads) { pools.assign(threads, std::vector<u32>()); off.resize(n_aln); cnt.assign(n_aln, 0); pool.resize(n_aln); } // only `cnt` has to start at zero
 	const u32* get(size_t a) const { return cnt[a] ? pools[pool[a]].data() + off[a] : NULL; }
 	void set(size_t a, int thread, const u32* g, u32 n) { std::vector<u32>& p = pools[thread]; off[a] = p.size(); cnt[a] = (u16) n; pool[a] = (u8) thread; p.insert(p.end(), g, g + n); }
 	void load(size_t a, gset& s) const { s.clear(); s.assign(get(a), cnt[a]); }
