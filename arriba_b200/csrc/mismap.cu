@@ -71,9 +71,17 @@ void engine::homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out) {
 	dbuf<u32> a, b; dbuf<u8> o(n);
 	a.upload(ex, ga, n); b.upload(ex, gb, n);
 	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
-	homolog_pairs_fn fn = {annot.view(), ix, a.ptr(), b.ptr(), o.ptr(), params.max_homolog_identity};
 	stage_timer t_all(ex);
-	for_each(ex, n, fn);
+	if (homolog_lanes > 1 && (u64) n * homolog_lanes < 0x80000000ull) { // a few pairs of long, similar genes dominate: lanes per pair (mismap_hd.h, homolog_count_fn)
+		dbuf<u32> count(n); count.zero(ex, n);
+		homolog_count_fn cf = {annot.view(), ix, a.ptr(), b.ptr(), count.ptr(), homolog_lanes, params.max_homolog_identity};
+		for_each(ex, n * homolog_lanes, cf);
+		homolog_decide_fn df = {annot.view(), ix, a.ptr(), b.ptr(), count.ptr(), o.ptr(), params.max_homolog_identity};
+		for_each(ex, n, df);
+	} else {
+		homolog_pairs_fn fn = {annot.view(), ix, a.ptr(), b.ptr(), o.ptr(), params.max_homolog_identity};
+		for_each(ex, n, fn);
+	}
 	timings.homologs_ms += t_all.stop();
 	o.download(ex, out, n);
 }

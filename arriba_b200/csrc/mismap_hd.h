@@ -452,41 +452,75 @@ struct item_fill_fn {
 };
 
 // ---- gene homology (filter_homologs.cpp:13-63): fraction of the small gene's 8-mers (stride 8) that occur, with 8 more matching bases, in the big gene
-ARB_HD bool genes_are_homologs(const annot_view& an, const kmer_index_view& ix, u32 g1, u32 g2, float max_identity) {
-	if (g1 == g2) return false;
+struct homolog_pair { // the comparison of one gene pair, set up once
+	bool comparable; u32 sc, bc, len; i32 ss, se, bs, be, blen; bool rc; const char* sref; const char* bref; float threshold;
+	ARB_HD char small_at(u32 i) const { return rc ? complement_char(sref[ss + (i32) (len - 1 - i)]) : sref[ss + (i32) i]; } // base i of the small gene's (possibly reverse-complemented) sequence
+};
+ARB_HD homolog_pair homolog_setup(const annot_view& an, const kmer_index_view& ix, u32 g1, u32 g2, float max_identity) {
+	homolog_pair p; p.comparable = false;
+	if (g1 == g2) return p;
 	u32 sm = g1, bg = g2;
 	if ((u32) (an.gene_end[sm] - an.gene_start[sm]) > (u32) (an.gene_end[bg] - an.gene_start[bg])) { sm = g2; bg = g1; }
-	const u32 sc = an.gene_contig[sm], bc = an.gene_contig[bg];
-	const i32 ss = an.gene_start[sm], se = an.gene_end[sm], bs = an.gene_start[bg], be = an.gene_end[bg];
-	if (sc == bc && ((ss >= bs && ss <= be) || (se >= bs && se <= be))) return false;
-	if (bc >= ix.n_index_contigs) return false;
-	const u32 len = (u32) (se - ss);
-	const bool rc = an.gene_strand[sm] != an.gene_strand[bg];
-	const char* sref = an.assembly + an.contig_seq_off[sc]; const char* bref = an.assembly + an.contig_seq_off[bc]; const i32 blen = (i32) an.contig_len[bc];
-	// base i of the small gene's (possibly reverse-complemented) sequence
-	#define SMALL_AT(i) (rc ? complement_char(sref[ss + (i32) (len - 1 - (i))]) : sref[ss + (i32) (i)])
+	p.sc = an.gene_contig[sm]; p.bc = an.gene_contig[bg];
+	p.ss = an.gene_start[sm]; p.se = an.gene_end[sm]; p.bs = an.gene_start[bg]; p.be = an.gene_end[bg];
+	if (p.sc == p.bc && ((p.ss >= p.bs && p.ss <= p.be) || (p.se >= p.bs && p.se <= p.be))) return p;
+	if (p.bc >= ix.n_index_contigs) return p;
+	p.len = (u32) (p.se - p.ss);
+	p.rc = an.gene_strand[sm] != an.gene_strand[bg];
+	p.sref = an.assembly + an.contig_seq_off[p.sc]; p.bref = an.assembly + an.contig_seq_off[p.bc]; p.blen = (i32) an.contig_len[p.bc];
 #ifdef __CUDA_ARCH__
-	const float threshold = __fmul_rn((float) len, max_identity);
+	p.threshold = __fmul_rn((float) p.len, max_identity);
 #else
-	volatile float threshold_v = (float) len * max_identity; const float threshold = threshold_v;
+	volatile float threshold_v = (float) p.len * max_identity; p.threshold = threshold_v;
 #endif
-	u32 matching = 0;
-	for (u32 pos = 0; pos + 16 < len; pos += 8) {
-		if ((float) (matching * 8 + (len - pos)) < threshold) return false;
-		u32 k = 0;
-		for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(SMALL_AT(pos + b));
-		u32 lo, hi; ix.bucket(bc, k, lo, hi);
-		for (u32 h = lower_bound_i32(ix.pos, lo, hi, bs); h < hi && ix.pos[h] <= be; ++h) {
-			const i32 hit = ix.pos[h];
-			if (!(sc != bc || hit < ss || hit > se)) continue;
-			bool same = true;
-			for (u32 b = 0; b < 8 && same; ++b) { const i32 g = hit + 8 + (i32) b; const char x = g < blen ? bref[g] : '\0'; if (x != SMALL_AT(pos + 8 + b)) same = false; }
-			if (same) { ++matching; if ((float) (matching * 8) >= threshold) return true; break; }
-		}
+	p.comparable = true;
+	return p;
+}
+// does the 8-mer at `pos` of the small gene occur in the big gene followed by the same 8 bases? (filter_homologs.cpp:36-55)
+ARB_HD bool homolog_position_matches(const homolog_pair& p, const kmer_index_view& ix, u32 pos) {
+	u32 k = 0;
+	for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(p.small_at(pos + b));
+	u32 lo, hi; ix.bucket(p.bc, k, lo, hi);
+	for (u32 h = lower_bound_i32(ix.pos, lo, hi, p.bs); h < hi && ix.pos[h] <= p.be; ++h) {
+		const i32 hit = ix.pos[h];
+		if (!(p.sc != p.bc || hit < p.ss || hit > p.se)) continue;
+		bool same = true;
+		for (u32 b = 0; b < 8 && same; ++b) { const i32 g = hit + 8 + (i32) b; const char x = g < p.blen ? p.bref[g] : '\0'; if (x != p.small_at(pos + 8 + b)) same = false; }
+		if (same) return true;
 	}
-	#undef SMALL_AT
+	return false;
+}
+ARB_HD bool genes_are_homologs(const annot_view& an, const kmer_index_view& ix, u32 g1, u32 g2, float max_identity) {
+	const homolog_pair p = homolog_setup(an, ix, g1, g2, max_identity);
+	if (!p.comparable) return false;
+	u32 matching = 0;
+	for (u32 pos = 0; pos + 16 < p.len; pos += 8) {
+		if ((float) (matching * 8 + (p.len - pos)) < p.threshold) return false;
+		if (homolog_position_matches(p, ix, pos)) { ++matching; if ((float) (matching * 8) >= p.threshold) return true; }
+	}
 	return false;
 }
 struct homolog_pairs_fn { annot_view an; kmer_index_view ix; const u32* ga; const u32* gb; u8* out; float max_identity; ARB_HD void operator()(u32 j) const { out[j] = genes_are_homologs(an, ix, ga[j], gb[j], max_identity); } };
+// The same verdict from `lanes` threads per pair. The sequential loop above answers "does the number of matching positions, times 8, reach the threshold":
+// its early `false` only fires when even a match at every remaining position could not reach it, its early `true` when the count has reached it. So the
+// positions may be counted in any order: lane l takes positions 8 * (l + lanes * i), the counts are added up, one more thread per pair decides.
+struct homolog_count_fn {
+	annot_view an; kmer_index_view ix; const u32* ga; const u32* gb; u32* count; u32 lanes; float max_identity;
+	ARB_HD void operator()(u32 t) const {
+		const u32 j = t / lanes, lane = t % lanes;
+		const homolog_pair p = homolog_setup(an, ix, ga[j], gb[j], max_identity);
+		if (!p.comparable) return;
+		u32 matching = 0;
+		for (u32 pos = 8 * lane; pos + 16 < p.len; pos += 8 * lanes) if (homolog_position_matches(p, ix, pos)) ++matching;
+		if (matching) atomic_add_u32(&count[j], matching);
+	}
+};
+struct homolog_decide_fn {
+	annot_view an; kmer_index_view ix; const u32* ga; const u32* gb; const u32* count; u8* out; float max_identity;
+	ARB_HD void operator()(u32 j) const {
+		const homolog_pair p = homolog_setup(an, ix, ga[j], gb[j], max_identity);
+		out[j] = p.comparable && count[j] > 0 && (float) (count[j] * 8) >= p.threshold;
+	}
+};
 
 } // namespace arb

@@ -95,6 +95,20 @@ def test_events_hostsim_continuation_registry(worlds, hostsim_lib, monkeypatch, 
     check_events(worlds.get("cfg5", **CFG5), hostsim_lib)
 
 
+@pytest.mark.parametrize("lanes", ["1", "7"])
+def test_events_hostsim_homolog_lanes(worlds, hostsim_lib, monkeypatch, lanes):
+    """filter_homologs' identity test with one thread per gene pair and with lanes that split the positions: same verdicts."""
+    monkeypatch.setenv("ARB_HOMOLOG_LANES", lanes)
+    check_events(worlds.get("cfg5", **CFG5), hostsim_lib)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("lanes", ["1", "32"])
+def test_events_cuda_homolog_lanes(worlds, cuda_lib, monkeypatch, lanes):
+    monkeypatch.setenv("ARB_HOMOLOG_LANES", lanes)
+    check_events(worlds.get("cfg5", **CFG5), cuda_lib)
+
+
 @pytest.mark.gpu
 def test_events_cuda_mismapper_heavy(worlds, cuda_lib):
     check_events(worlds.get("cfg5", **CFG5), cuda_lib)
