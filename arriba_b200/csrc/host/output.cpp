@@ -64,10 +64,28 @@ struct pile_column {
 // within WINDOW bases of the breakpoint sit in a flat array (nearly all bases), the rest -- the inside of introns, filled position by position like the
 // reference does -- in an open-addressing table; multi-base insertion strings are rare and kept aside. flatten() hands the columns over in ascending
 // position as pile_column objects, which is all the consensus needs (the reference keeps a map of maps per pileup, output_fusions.cpp:22).
-typedef std::vector<std::pair<i32, pile_column> > pileup_t;
+struct pile_cell { u16 n[pile_column::N_SYMBOLS]; };
+struct column_ref { // one position of a finished pileup: the counters and, rarely, the multi-base keys; same iteration order as the reference's map
+	const pile_cell* c; const std::map<std::string, unsigned int>* other;
+	unsigned int total() const { unsigned int t = 0; for (int k = 0; k < pile_column::N_SYMBOLS; ++k) t += c->n[k]; if (other) for (std::map<std::string, unsigned int>::const_iterator it = other->begin(); it != other->end(); ++it) t += it->second; return t; }
+	void entries(std::vector<std::pair<std::string, unsigned int> >& out) const {
+		out.clear();
+		static const std::map<std::string, unsigned int> none;
+		const std::map<std::string, unsigned int>& o = other ? *other : none;
+		std::map<std::string, unsigned int>::const_iterator it = o.begin();
+		for (int k = 0; k < pile_column::N_SYMBOLS; ++k) {
+			if (c->n[k] == 0) continue;
+			const std::string key(1, pile_column::symbols()[k]);
+			while (it != o.end() && it->first < key) { out.push_back(*it); ++it; }
+			out.push_back(std::make_pair(key, (unsigned int) c->n[k]));
+		}
+		for (; it != o.end(); ++it) out.push_back(*it);
+	}
+};
+typedef std::vector<std::pair<i32, column_ref> > pileup_t;
 struct pile_builder {
 	enum { WINDOW = 2048 };
-	struct cell { u16 n[pile_column::N_SYMBOLS]; };
+	typedef pile_cell cell;
 	i32 lo; std::vector<cell> dense; std::vector<u8> used; std::vector<u32> used_list;
 	std::vector<i32> far_pos; std::vector<cell> far_cell; std::vector<u32> far_slot; // far_slot: open addressing, index + 1 into far_pos / far_cell, 0 = empty
 	std::map<i32, std::map<std::string, unsigned int> > other;
@@ -92,21 +110,20 @@ struct pile_builder {
 	}
 	void add(i32 pos, char symbol, unsigned int n = 1) { const int x = pile_column::index_of(symbol); if (x >= 0) at(pos).n[x] = (u16) (at(pos).n[x] + n); else other[pos][std::string(1, symbol)] += n; }
 	void add(i32 pos, const std::string& s) { if (s.size() == 1) add(pos, s[0]); else { at(pos); other[pos][s] += 1; } }
-	void flatten(pileup_t& out) const {
+	void flatten(pileup_t& out) { // views into this builder, valid until the next reset()
 		out.clear();
 		std::vector<std::pair<i32, u32> > far; far.reserve(far_pos.size());
 		for (size_t k = 0; k < far_pos.size(); ++k) far.push_back(std::make_pair(far_pos[k], (u32) k));
 		std::sort(far.begin(), far.end());
+		std::sort(used_list.begin(), used_list.end());
 		auto column_of = [&](i32 pos, const cell& c) {
-			std::pair<i32, pile_column> col; col.first = pos;
-			for (int k = 0; k < pile_column::N_SYMBOLS; ++k) col.second.single[k] = c.n[k];
-			std::map<i32, std::map<std::string, unsigned int> >::const_iterator o = other.find(pos);
-			if (o != other.end()) col.second.other = o->second;
-			return col;
+			column_ref r; r.c = &c; r.other = NULL;
+			if (!other.empty()) { std::map<i32, std::map<std::string, unsigned int> >::const_iterator o = other.find(pos); if (o != other.end()) r.other = &o->second; }
+			return std::make_pair(pos, r);
 		};
 		size_t k = 0;
 		for (; k < far.size() && far[k].first < lo; ++k) out.push_back(column_of(far[k].first, far_cell[far[k].second]));
-		for (u32 x = 0; x < 2 * WINDOW; ++x) if (used[x]) out.push_back(column_of(lo + (i32) x, dense[x]));
+		for (size_t x = 0; x < used_list.size(); ++x) out.push_back(column_of(lo + (i32) used_list[x], dense[used_list[x]]));
 		for (; k < far.size(); ++k) out.push_back(column_of(far[k].first, far_cell[far[k].second]));
 	}
 };
