@@ -168,11 +168,18 @@ struct worker {
 	std::unordered_map<std::string, std::vector<u8>, name_hash> pending; // first mate of a proper pair, waiting for the second
 	coverage_windows* cov; // shared by all workers: saturating counters and flags are updated atomically, the result does not depend on the order
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
-	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size;
+	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size; u32 last_fragment;
 	void park_waiting() { if (waiting_ptr) { pending.emplace(waiting_key, std::vector<u8>(waiting_ptr, waiting_ptr + waiting_size)); waiting_ptr = NULL; } } // before the chunk buffer is recycled
-	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
+	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), last_fragment(0xFFFFFFFFu), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
 
 	u32 fragment(const std::string& name, bool* created = NULL) {
+		// the records of one fragment follow each other in a collated BAM: remember the last answer before walking the table
+		if (last_fragment != 0xFFFFFFFFu) { const frag_build& f = frags[last_fragment]; if (f.name_len == name.size() && memcmp(names.data() + f.name_off, name.data(), name.size()) == 0) { if (created) *created = false; return last_fragment; } }
+		const u32 id = fragment_lookup(name, created);
+		last_fragment = id;
+		return id;
+	}
+	u32 fragment_lookup(const std::string& name, bool* created) {
 		if (name_slots.empty()) name_slots.assign(1u << 12, 0);
 		u64 h = 1469598103934665603ULL; for (size_t i = 0; i < name.size(); ++i) { h ^= (u8) name[i]; h *= 1099511628211ULL; }
 		h ^= h >> 29; // the low bits of the same hash chose the worker
@@ -206,7 +213,7 @@ struct worker {
 		f.tail = id; ++f.count;
 	}
 	u64 store_seq(const rec_t& r) { // nt16 nibbles copied verbatim, 16-byte aligned
-		while (seqs.size() % 16) seqs.push_back(0);
+		seqs.resize((seqs.size() + 15) & ~(size_t) 15, 0);
 		const u64 off = seqs.size();
 		seqs.insert(seqs.end(), r.seq, r.seq + (r.l_seq + 1) / 2);
 		return off;
