@@ -93,6 +93,7 @@ void event_table::replay_iteration_order(int hash_threads) {
 			}
 			bucket.swap(fresh); n_buckets = grow.second;
 		}
+		if (k + 16 < n) __builtin_prefetch(&bucket[code[k + 16] % n_buckets]);
 		const size_t b = code[k] % n_buckets;
 		if (bucket[b] != NONE) { next[k] = next[bucket[b]]; next[bucket[b]] = k; }
 		else {
@@ -262,6 +263,7 @@ void pipeline::filter_multimappers() {
 		if (e.gene1[x] != e.gene1[y]) return e.gene1[x] < e.gene1[y];
 		return e.gene2[x] < e.gene2[y];
 	};
+	stage_laps laps("multimappers");
 	const u32 NONE = 0xFFFFFFFFu;
 	std::vector<u32> best(N, NONE); // most supported candidate per multimapping fragment
 	// `better` is a total order, so the best candidate of a fragment does not depend on the visiting order: candidates in parallel, compare-and-swap per fragment
@@ -275,6 +277,7 @@ void pipeline::filter_multimappers() {
 		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) consider(k, e.list2[p]);
 		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) consider(k, e.listd[p]);
 	});
+	laps.lap("best candidate per fragment");
 	auto more_support = [&](u32 fa, u32 fb) { // fusion_has_more_support(most_supported[fa], most_supported[fb]) with NULL handling
 		const u32 x = best[fa], y = best[fb];
 		if (x == NONE) return false;
@@ -283,23 +286,37 @@ void pipeline::filter_multimappers() {
 	};
 	// clusters = maximal runs of fragments sharing the name up to the last comma
 	auto stem = [&](u32 i, u64& len) { const char* s = frags.names.data() + frags.name_off[i]; u64 l = frags.name_off[i + 1] - frags.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; len = k > 0 ? k - 1 : l; return s; };
-	u32 i = 0;
-	while (i < N) {
-		if (!(frags.fflags[i] & FF_MULTIMAPPER)) { ++i; continue; } // the flag marks exactly the fragments that share their stem with a neighbour (ingest)
-		u64 li; const char* si = stem(i, li);
-		u32 j = i + 1;
-		for (; j < N; ++j) { u64 lj; const char* sj = stem(j, lj); if (lj != li || memcmp(si, sj, li) != 0) break; }
-		if (j - i > 1) {
-			u32 best_frag = NONE; int best_score = INT_MIN;
-			for (u32 x = i; x < j; ++x) {
-				const int s = alignment_score(f, an, x);
-				if (best_score < s) { best_frag = x; best_score = s; }
-				else if (best_score == s && more_support(x, best_frag)) best_frag = x;
-			}
-			for (u32 x = i; x < j; ++x) if (x != best_frag && labels[x] == F_none) labels[x] = F_multimappers;
-		}
-		i = j;
+	// clusters are independent: a thread takes the clusters that START in its slice of the name order (a cluster may run on into the next slice)
+	{
+		const int T = std::max(1, std::min(threads, (int) (N / 4096 + 1)));
+		std::vector<std::thread> pool; std::vector<std::string> errors(T);
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
+			try {
+				u32 i = (u32) ((u64) N * t / T); const u32 stop = (u32) ((u64) N * (t + 1) / T);
+				// skip the tail of a cluster that started in the previous slice
+				if (i > 0 && i < N && (frags.fflags[i] & FF_MULTIMAPPER)) { u64 lp; const char* sp = stem(i - 1, lp); for (; i < N; ++i) { u64 li; const char* si = stem(i, li); if (li != lp || memcmp(sp, si, lp) != 0) break; } }
+				while (i < stop) {
+					if (!(frags.fflags[i] & FF_MULTIMAPPER)) { ++i; continue; } // the flag marks exactly the fragments that share their stem with a neighbour (ingest)
+					u64 li; const char* si = stem(i, li);
+					u32 j = i + 1;
+					for (; j < N; ++j) { u64 lj; const char* sj = stem(j, lj); if (lj != li || memcmp(si, sj, li) != 0) break; }
+					if (j - i > 1) {
+						u32 best_frag = NONE; int best_score = INT_MIN;
+						for (u32 x = i; x < j; ++x) {
+							const int s = alignment_score(f, an, x);
+							if (best_score < s) { best_frag = x; best_score = s; }
+							else if (best_score == s && more_support(x, best_frag)) best_frag = x;
+						}
+						for (u32 x = i; x < j; ++x) if (x != best_frag && labels[x] == F_none) labels[x] = F_multimappers;
+					}
+					i = j;
+				}
+			} catch (const std::exception& x) { errors[t] = x.what(); }
+		});
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 	}
+	laps.lap("clusters");
 	parallel_rows(threads, e.n, [&](u32 k) {
 		if (e.filter[k] != F_none || e.supporting_reads(k) == 0) return;
 		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) if (labels[e.list1[p]] == F_multimappers && e.split_reads1[k] > 0) --e.split_reads1[k];
@@ -307,6 +324,7 @@ void pipeline::filter_multimappers() {
 		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) if (labels[e.listd[p]] == F_multimappers && e.discordant_mates[k] > 0) --e.discordant_mates[k];
 		if (e.supporting_reads(k) == 0) e.filter[k] = F_multimappers;
 	});
+	laps.lap("read counts");
 	log_remaining("Filtering multi-mapping fusions by alignment score and read support");
 }
 
@@ -604,6 +622,7 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	const unsigned int max_fusions_to_recover = 200;
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
 	find_top_expressed_genes(reads_by_gene, present, threshold, 0.998f); // fixed quantile (arriba.cpp:492)
+	stage_laps laps("spliced");
 	// spliced support of every candidate that may back another one up (recover_both_spliced.cpp:104-118); a pure function of the candidate: host threads
 	const u32 NOT_ELIGIBLE = 0xFFFFFFFFu;
 	std::vector<u32> support(ev.n, NOT_ELIGIBLE);
@@ -620,7 +639,9 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
 	std::vector<std::pair<u64, u32> > grouped;
 	for (u32 k = 0; k < ev.n; ++k) if (support[k] != NOT_ELIGIBLE) grouped.push_back(std::make_pair(key_of(k, false), k));
-	std::sort(grouped.begin(), grouped.end());
+	laps.lap("support of eligible candidates");
+	parallel_sort(grouped, [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b) { return a < b; }, threads);
+	laps.lap("grouped by gene pair");
 	auto group_of = [&](u64 key, size_t& lo, size_t& hi) {
 		lo = std::lower_bound(grouped.begin(), grouped.end(), std::make_pair(key, (u32) 0)) - grouped.begin();
 		hi = lo; while (hi < grouped.size() && grouped[hi].first == key) ++hi;
@@ -646,6 +667,7 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 		}
 		backing[k] = sum;
 	});
+	laps.lap("backing per candidate");
 	// at most ~200 candidates are recovered: raise the read threshold until fewer would be (recover_both_spliced.cpp:162-175), then recover
 	std::map<unsigned int, unsigned int> recovered_by_reads;
 	for (u32 k = 0; k < ev.n; ++k) if (backing[k] >= 2) ++recovered_by_reads[ev.supporting_reads(k)];
