@@ -31,7 +31,7 @@ template <class F> static void parallel_rows(int threads, size_t n, F f) {
 // sort on the host threads: slices sorted concurrently, then merged pairwise (log2(threads) rounds)
 template <class T, class Less> static void parallel_sort(std::vector<T>& v, Less less, int threads) {
 	const size_t n = v.size();
-	if (threads <= 1 || n < 65536) { std::sort(v.begin(), v.end(), less); return; }
+	if (threads <= 1 || n < 8192) { std::sort(v.begin(), v.end(), less); return; }
 	int parts = 1; while (parts * 2 <= threads) parts *= 2;
 	std::vector<size_t> cut(parts + 1); for (int t = 0; t <= parts; ++t) cut[t] = n * t / parts;
 	{ std::vector<std::thread> pool; for (int t = 0; t < parts; ++t) pool.emplace_back([&, t]() { std::sort(v.begin() + cut[t], v.begin() + cut[t + 1], less); }); for (size_t t = 0; t < pool.size(); ++t) pool[t].join(); }
@@ -342,7 +342,7 @@ void pipeline::estimate_evalues() {
 		const size_t n_order = e.order.size();
 		std::vector<occurrence> all;
 		{ // collected by slices of the iteration order, concatenated in slice order
-			const int T = std::max(1, std::min(threads, (int) (n_order / 65536 + 1)));
+			const int T = std::max(1, std::min(threads, (int) (n_order / 4096 + 1)));
 			std::vector<std::vector<occurrence> > part(T);
 			std::vector<std::thread> pool;
 			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
@@ -506,7 +506,7 @@ void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::ve
 	const size_t G = ref.genes.size();
 	reads_by_gene.assign(G, 0); present.assign(G, 0);
 	{ // per-thread histograms over the fragments' gene sets, then summed
-		const int T = std::max(1, std::min(threads, (int) (N / 65536 + 1)));
+		const int T = std::max(1, std::min(threads, (int) (N / 8192 + 1)));
 		std::vector<std::vector<u32> > part(T, std::vector<u32>(G, 0));
 		std::vector<std::thread> pool;
 		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
