@@ -175,10 +175,10 @@ int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n_realig
 /* ---- device timing (CUDA events recorded on the context's stream around each stage) ---------------------------------- */
 typedef struct arb_timings {
 	float duplicates_ms;        /* duplicate marking (key build + hash group-by + mark) */
-	float classify_ms;          /* the fused read-level cascade kernel, one launch */
+	float classify_ms;          /* the read-level cascade: both launches and the queue hand-over between them */
 	float read_filters_ms;      /* whole arb_run_read_filters */
 	float find_fusions_ms;      /* whole arb_find_fusions */
-	uint64_t classify_algorithmic_bytes; /* bytes the cascade kernel must read/write once: every input column and pool + gathered reference bases + 2 label bytes per fragment */
+	uint64_t classify_algorithmic_bytes; /* SURVEY.md section 8(d) column budget of the cascade for the resident chunk (see cascade_algorithmic_bytes for what the launches actually saw) */
 	uint64_t h2d_bytes;         /* bytes copied by the last arb_push_chunk */
 	float h2d_ms;               /* duration of those copies */
 	float merge_adjacent_ms, evalue_ms, kmer_index_ms, homologs_ms, mismappers_ms; /* candidate-level device stages */
