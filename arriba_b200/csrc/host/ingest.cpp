@@ -164,6 +164,7 @@ struct worker {
 	refdata* ref; const ingest_options* opt; const std::vector<u16>* tid_to_contig; const std::vector<u8>* interesting_contig; const std::vector<u8>* viral_contig;
 	annot_view an;
 	std::vector<char> names; std::vector<u32> cigars; std::vector<u8> seqs; std::vector<aln_build> alns; std::vector<frag_build> frags;
+	std::vector<aln_build> norm_alns; std::vector<u32> norm_cigars; // the fragments' alignments after slot normalisation, contiguous per fragment
 	std::vector<u32> name_slots; // open-addressing index of `frags` by name: fragment id + 1, 0 = empty; names are compared in the `names` pool
 	std::unordered_map<std::string, std::vector<u8>, name_hash> pending; // first mate of a proper pair, waiting for the second
 	coverage_windows* cov; // shared by all workers: saturating counters and flags are updated atomically, the result does not depend on the order
@@ -520,7 +521,7 @@ struct bgzf_file {
 	std::vector<block> blocks; u64 total_out;
 	bgzf_file(): data(NULL), size(0), fd(-1), total_out(0) {}
 	~bgzf_file() { if (data) munmap((void*) data, size); if (fd >= 0) close(fd); }
-	void open(const std::string& path) {
+	void open(const std::string& path, int threads) {
 		fd = ::open(path.c_str(), O_RDONLY);
 		if (fd < 0) fail("failed to open SAM file");
 		struct stat st; fstat(fd, &st); size = st.st_size;
@@ -528,18 +529,61 @@ struct bgzf_file {
 		data = (const u8*) mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
 		if (data == MAP_FAILED) { data = NULL; fail("failed to open SAM file"); }
 		madvise((void*) data, size, MADV_SEQUENTIAL);
-		u64 off = 0, out = 0;
-		while (off + 18 <= size) {
+		// Block table. A block is found from the one before it (its size sits in its header), and every header read faults a page of the mapping in: a
+		// 7 GB file of stored blocks costs a quarter of a second on one thread. So every piece of the file guesses its first block (two well-formed
+		// headers in a row), walks from there, and the guesses are VERIFIED: the chain of piece s must arrive exactly at the guess of piece s+1; where it
+		// does not, that stretch is walked serially. Errors are raised by the serial walk only, at the same offsets as before.
+		auto header = [&](u64 off, u32& bsize, u32& xlen) { // well-formed BGZF header at off (SAMv1 4.1)?
+			if (off + 18 > size) return false;
 			const u8* h = data + off;
-			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) fail(off == 0 ? "failed to read SAM header" : "failed to load alignments"); // not BGZF (SAM text / CRAM are not supported); at the start of the file no header can be read (arriba.cpp:122)
-			const u32 xlen = rd16(h + 10);
-			u32 bsize = 0; bool found = false;
+			if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+			xlen = rd16(h + 10);
+			if (off + 12 + xlen > size) return false;
+			bool found = false;
 			for (u32 x = 0; x + 4 <= xlen;) { const u8* e = h + 12 + x; const u32 slen = rd16(e + 2); if (e[0] == 'B' && e[1] == 'C' && slen == 2) { bsize = rd16(e + 4) + 1u; found = true; } x += 4 + slen; }
-			if (!found || off + bsize > size) fail("failed to load alignments");
-			block b; b.in_off = off + 12 + xlen; b.in_len = bsize - 12 - xlen - 8; b.out_len = rd32(h + bsize - 4); b.out_off = out;
-			blocks.push_back(b);
-			out += b.out_len; off += bsize;
-		}
+			return found && bsize >= 12 + xlen + 8 && off + bsize <= size;
+		};
+		auto walk = [&](u64 off, u64 limit, std::vector<block>& out, bool strict) { // blocks starting before `limit`; returns where the chain stands
+			while (off < limit && off + 18 <= size) {
+				u32 bsize = 0, xlen = 0;
+				if (!header(off, bsize, xlen)) {
+					if (!strict) break;
+					const u8* h = data + off;
+					const bool magic = h[0] == 0x1f && h[1] == 0x8b && h[2] == 8 && (h[3] & 4);
+					fail(!magic && off == 0 ? "failed to read SAM header" : "failed to load alignments"); // not BGZF (SAM text / CRAM are not supported); at the start of the file no header can be read (arriba.cpp:122)
+				}
+				block b; b.in_off = off + 12 + xlen; b.in_len = bsize - 12 - xlen - 8; b.out_len = rd32(data + off + bsize - 4); b.out_off = 0;
+				out.push_back(b);
+				off += bsize;
+			}
+			return off;
+		};
+		const size_t min_bytes = getenv("ARB_SCAN_MIN_BYTES") ? (size_t) atol(getenv("ARB_SCAN_MIN_BYTES")) : (size_t) 64 << 20; // test hook
+		const int pieces = threads > 1 && size > min_bytes ? threads : 1;
+		if (pieces > 1) {
+			std::vector<u64> guess(pieces + 1, size), stop_at(pieces, 0);
+			std::vector<std::vector<block> > found(pieces);
+			guess[0] = 0;
+			std::vector<std::thread> pool;
+			for (int s = 1; s < pieces; ++s) pool.emplace_back([&, s]() {
+				u64 q = (u64) size * s / pieces; const u64 give_up = std::min<u64>(size, q + (256u << 10));
+				for (; q < give_up; ++q) { u32 b1 = 0, x1 = 0, b2 = 0, x2 = 0; if (header(q, b1, x1) && (q + b1 + 18 > size || header(q + b1, b2, x2))) break; }
+				guess[s] = q < give_up ? q : size;
+			});
+			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+			pool.clear();
+			for (int s = 1; s < pieces; ++s) pool.emplace_back([&, s]() { stop_at[s] = guess[s] < size ? walk(guess[s], guess[s + 1], found[s], false) : size; });
+			stop_at[0] = walk(0, guess[1], found[0], false);
+			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+			u64 q = 0;
+			for (int s = 0; s < pieces; ++s) {
+				if (q == guess[s] && guess[s] < size) { blocks.insert(blocks.end(), found[s].begin(), found[s].end()); q = stop_at[s]; }
+				if (q < guess[s + 1]) q = walk(q, guess[s + 1], blocks, true); // wrong or missing guess, or a chain that broke off: walk (and diagnose) this stretch
+			}
+			walk(q, size, blocks, true);
+		} else walk(0, size, blocks, true);
+		u64 out = 0;
+		for (size_t b = 0; b < blocks.size(); ++b) { blocks[b].out_off = out; out += blocks[b].out_len; }
 		total_out = out;
 	}
 	void inflate_block(const block& b, u8* dst) const {
@@ -645,7 +689,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	const bool trace = getenv("ARB_TRACE") != NULL;
 	double tr_last = t0;
 	auto lap = [&](const char* what) { if (trace) { const double t = now_s(); fprintf(stderr, "[ingest] %-28s %.3f s\n", what, t - tr_last); tr_last = t; } };
-	bgzf_file bam; bam.open(bam_path);
+	bgzf_file bam; bam.open(bam_path, T);
 	lap("open + block table");
 	stats.t_inflate = stats.t_parse = stats.t_finalize = 0;
 
@@ -657,7 +701,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	bool header_done = false;
 	u64 total_records = 0;
 	// A chunk is inflated, cut into records and sharded ("prepare") while the workers still parse the previous one ("process").
-	struct chunk_t { std::vector<u8> buf; std::vector<u64> rec_off; std::vector<u8> rec_shard; size_t consumed; bool last; chunk_t(): consumed(0), last(false) {} };
+	struct chunk_t { std::vector<u8> buf; std::vector<u64> rec_off; std::vector<u8> rec_shard; std::vector<u32> shard_items, shard_begin; size_t consumed; bool last; chunk_t(): consumed(0), last(false) {} };
 	chunk_t chunks[2];
 	size_t b0 = 0;
 	double t_inflate = 0, t_scan = 0; // written by the preparing thread only
@@ -784,6 +828,18 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 				rec_shard[k] = (u8) ((h >> 20) % (u64) T);
 			}
 		});
+		{ // the records of every shard, in file order (a stable counting sort by shard over slices of the record list): a worker then walks its own list only
+			const size_t n_rec = rec_off.size();
+			if (n_rec > 0xFFFFFFFFull) fail("failed to load alignments");
+			std::vector<u32> counts((size_t) T * T, 0); // [slice][shard]
+			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t sl = lo; sl < hi; ++sl) { u32* cnt = &counts[sl * T]; for (size_t k = n_rec * sl / T; k < n_rec * (sl + 1) / T; ++k) ++cnt[rec_shard[k]]; } });
+			c.shard_begin.assign(T + 1, 0);
+			u32 at = 0;
+			for (int sh = 0; sh < T; ++sh) { c.shard_begin[sh] = at; for (int sl = 0; sl < T; ++sl) { const u32 n = counts[(size_t) sl * T + sh]; counts[(size_t) sl * T + sh] = at; at += n; } }
+			c.shard_begin[T] = at;
+			c.shard_items.resize(n_rec);
+			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t sl = lo; sl < hi; ++sl) { u32* pos = &counts[sl * T]; for (size_t k = n_rec * sl / T; k < n_rec * (sl + 1) / T; ++k) c.shard_items[pos[rec_shard[k]]++] = (u32) k; } });
+		}
 		t_scan += now_s() - tp;
 		if (c.last && c.consumed != buf.size()) fail("failed to load alignments");
 	};
@@ -801,7 +857,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 				for (size_t t = lo; t < hi; ++t) {
 					worker& w = workers[t];
 					const u8* base = c.buf.data();
-					for (size_t k = 0; k < c.rec_off.size(); ++k) if (c.rec_shard[k] == t) w.process(base + c.rec_off[k] + 4, rd32(base + c.rec_off[k]));
+					const u32* const mine = c.shard_items.data(); const u32 stop = c.shard_begin[t + 1];
+					for (u32 x = c.shard_begin[t]; x < stop; ++x) {
+						if (x + 3 < stop) { const u8* ahead = base + c.rec_off[mine[x + 3]]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); } // fixed fields + name, and where the tags of a 2x101 / 2x151 record start
+						const u64 off = c.rec_off[mine[x]];
+						w.process(base + off + 4, rd32(base + off));
+					}
 					w.park_waiting();
 				}
 			});
@@ -838,7 +899,14 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		for (size_t t = lo; t < hi; ++t) {
 			worker& w = workers[t];
 			std::vector<norm_aln> m;
-			for (size_t f = 0; f < w.frags.size(); ++f) {
+			const size_t n_frags = w.frags.size(); // fixed: only alignments and CIGARs are appended below
+			keep[t].reserve(n_frags);
+			w.norm_alns.reserve(w.alns.size()); w.norm_cigars.reserve(w.cigars.size()); // normalisation drops alignments, it never adds one: no regrowth, and the parsed pools are not copied
+			for (size_t f = 0; f < n_frags; ++f) {
+				// a fragment's alignments were stored as its records arrived, far apart: the chain of the fragments a few steps ahead is requested early
+				if (f + 12 < n_frags && w.frags[f + 12].head >= 0) { __builtin_prefetch(&w.alns[w.frags[f + 12].head]); __builtin_prefetch(w.names.data() + w.frags[f + 12].name_off); }
+				if (f + 8 < n_frags && w.frags[f + 8].head >= 0) { const aln_build& a = w.alns[w.frags[f + 8].head]; __builtin_prefetch(&w.cigars[a.cigar_off]); if (a.next >= 0) __builtin_prefetch(&w.alns[a.next]); }
+				if (f + 4 < n_frags && w.frags[f + 4].head >= 0) { const i32 second = w.alns[w.frags[f + 4].head].next; if (second >= 0) { const aln_build& a = w.alns[second]; __builtin_prefetch(&w.cigars[a.cigar_off]); if (a.next >= 0) __builtin_prefetch(&w.alns[a.next]); } }
 				frag_build& fb = w.frags[f];
 				size_t count = 0; // the scratch alignments keep their CIGAR storage from fragment to fragment
 				for (i32 a = fb.head; a >= 0; a = w.alns[a].next, ++count) {
@@ -848,11 +916,11 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 				m.resize(count);
 				if (!normalise_fragment(m, fb.single_end)) { ++malformed_by_worker[t]; fb.count = 0; continue; }
 				// write the normalised alignments back (fresh CIGAR storage; slots become contiguous)
-				fb.head = (i32) w.alns.size(); fb.count = (u32) m.size();
+				fb.head = (i32) w.norm_alns.size(); fb.count = (u32) m.size();
 				for (size_t s = 0; s < m.size(); ++s) {
-					m[s].a.cigar_off = (u32) w.cigars.size(); m[s].a.cigar_cnt = (u32) m[s].cigar.size();
-					w.cigars.insert(w.cigars.end(), m[s].cigar.begin(), m[s].cigar.end());
-					w.alns.push_back(m[s].a);
+					m[s].a.cigar_off = (u32) w.norm_cigars.size(); m[s].a.cigar_cnt = (u32) m[s].cigar.size();
+					w.norm_cigars.insert(w.norm_cigars.end(), m[s].cigar.begin(), m[s].cigar.end());
+					w.norm_alns.push_back(m[s].a);
 				}
 				final_frag ff; ff.worker = (u32) t; ff.frag = (u32) f; ff.prefix0 = ff.prefix1 = 0;
 				const char* nm = w.names.data() + fb.name_off;
@@ -868,8 +936,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	if (stats.missing_hi_tag > 0) std::cerr << "WARNING: " << stats.missing_hi_tag << " secondary alignments lack the 'HI' tag and were ignored (STAR must be run with '--outSAMattributes HI' for Arriba to make use of multi-mapping reads for fusion detection)" << std::endl;
 
 	// ---- name order: std::string::compare semantics == unsigned byte-wise comparison, shorter string first on a common prefix ----
-	std::vector<final_frag> order;
-	{ size_t total = 0; for (int t = 0; t < T; ++t) total += keep[t].size(); order.reserve(total); for (int t = 0; t < T; ++t) order.insert(order.end(), keep[t].begin(), keep[t].end()); }
+	std::vector<final_frag, default_init_allocator<final_frag> > order;
+	{ // every worker's list goes to its own stretch of the table, copied (and first touched) by its own thread
+		std::vector<size_t> at(T + 1, 0); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + keep[t].size();
+		order.resize(at[T]);
+		parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) { std::copy(keep[t].begin(), keep[t].end(), order.begin() + at[t]); std::vector<final_frag>().swap(keep[t]); } });
+	}
 	auto name_less = [&](const final_frag& a, const final_frag& b) {
 		if (a.prefix0 != b.prefix0) return a.prefix0 < b.prefix0;
 		if (a.prefix1 != b.prefix1) return a.prefix1 < b.prefix1;
@@ -879,18 +951,35 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		if (c != 0) return c < 0;
 		return fa.name_len < fb.name_len;
 	};
-	{ // parallel sort: sort T slices, then merge pairwise
+	{ // parallel sort: T sorted slices, then rounds of pairwise merges; every merge is itself cut into independent pieces (by output rank), so all threads
+	  // stay busy down to the last round, where one merge spans the whole table
 		const size_t n = order.size();
 		std::vector<size_t> cut(T + 1); for (int t = 0; t <= T; ++t) cut[t] = n * t / T;
 		parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) std::sort(order.begin() + cut[t], order.begin() + cut[t + 1], name_less); });
+		std::vector<final_frag, default_init_allocator<final_frag> > spare(T > 1 ? n : 0);
+		final_frag* src = order.data(); final_frag* dst = spare.data();
+		// how many elements of A = src[a, m) precede output rank r of merge(A, B = src[m, b)); equal keys take A first (names are unique anyway)
+		auto split = [&](const final_frag* A, size_t nA, const final_frag* B, size_t nB, size_t r) {
+			size_t lo = r > nB ? r - nB : 0, hi = std::min(r, nA);
+			while (lo < hi) { const size_t i = lo + (hi - lo) / 2, j = r - i; if (j == 0 || name_less(B[j - 1], A[i])) hi = i; else lo = i + 1; }
+			return lo;
+		};
 		for (int width = 1; width < T; width *= 2) {
 			std::vector<std::thread> pool;
-			for (int t = 0; t + width < T; t += 2 * width) {
-				const size_t a = cut[t], m = cut[t + width], b = cut[std::min(T, t + 2 * width)];
-				pool.emplace_back([&, a, m, b]() { std::inplace_merge(order.begin() + a, order.begin() + m, order.begin() + b, name_less); });
+			for (int t = 0; t < T; t += 2 * width) {
+				const size_t a = cut[t], m = cut[std::min(T, t + width)], b = cut[std::min(T, t + 2 * width)];
+				const int parts = std::min(T - t, 2 * width); // as many threads as the merge has slices
+				for (int k = 0; k < parts; ++k) pool.emplace_back([&, a, m, b, k, parts]() {
+					const final_frag* A = src + a; const final_frag* B = src + m; const size_t nA = m - a, nB = b - m;
+					const size_t r0 = (b - a) * k / parts, r1 = (b - a) * (k + 1) / parts;
+					const size_t i0 = split(A, nA, B, nB, r0), i1 = split(A, nA, B, nB, r1);
+					std::merge(A + i0, A + i1, B + (r0 - i0), B + (r1 - i1), dst + a + r0, name_less);
+				});
 			}
 			for (size_t k = 0; k < pool.size(); ++k) pool[k].join();
+			std::swap(src, dst);
 		}
+		if (src != order.data()) parallel_for(T, n, [&](int, size_t lo, size_t hi) { std::copy(src + lo, src + hi, order.data() + lo); });
 	}
 
 	lap("sort by name");
@@ -908,9 +997,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	cig_at[0] = seq_at[0] = 0; out.name_off[0] = 0;
 	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
+			// fragments in name order lie all over the workers' pools: the records of the ones a few steps ahead are requested early
+			if (i + 16 < hi) __builtin_prefetch(&workers[order[i + 16].worker].frags[order[i + 16].frag]);
+			if (i + 8 < hi) { const worker& w8 = workers[order[i + 8].worker]; __builtin_prefetch(&w8.norm_alns[w8.frags[order[i + 8].frag].head]); }
 			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
 			u64 nc = 0, ns = 0;
-			for (u32 s = 0; s < fb.count; ++s) { const aln_build& a = w.alns[fb.head + s]; nc += a.cigar_cnt; if (s < 2) ns += ((a.seq_len + 1) / 2 + 15) / 16; }
+			for (u32 s = 0; s < fb.count; ++s) { const aln_build& a = w.norm_alns[fb.head + s]; nc += a.cigar_cnt; if (s < 2) ns += ((a.seq_len + 1) / 2 + 15) / 16; }
 			cig_at[i + 1] = nc; seq_at[i + 1] = ns; out.name_off[i + 1] = fb.name_len;
 		}
 	});
@@ -920,6 +1012,15 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	out.cigar[cig_at[n]] = 0; memset(&out.seq[seq_at[n] * 16], 0, 16);
 	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
+			if (i + 16 < hi) __builtin_prefetch(&workers[order[i + 16].worker].frags[order[i + 16].frag]);
+			if (i + 8 < hi) {
+				const worker& w8 = workers[order[i + 8].worker]; const frag_build& f8 = w8.frags[order[i + 8].frag];
+				__builtin_prefetch(&w8.norm_alns[f8.head]); __builtin_prefetch(&w8.norm_alns[f8.head] + 2); __builtin_prefetch(w8.names.data() + f8.name_off);
+			}
+			if (i + 4 < hi) {
+				const worker& w4 = workers[order[i + 4].worker]; const frag_build& f4 = w4.frags[order[i + 4].frag];
+				for (u32 s = 0; s < f4.count; ++s) { const aln_build& a = w4.norm_alns[f4.head + s]; __builtin_prefetch(&w4.norm_cigars[a.cigar_off]); if (s < 2 && a.seq_len) { __builtin_prefetch(&w4.seqs[a.seq_off]); __builtin_prefetch(&w4.seqs[a.seq_off] + 48); } }
+			}
 			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
 			out.n_aln[i] = (u8) fb.count; out.fflags[i] = (fb.single_end ? FF_SINGLE_END : 0) | (fb.duplicate ? FF_DUPLICATE : 0); out.filter[i] = 0;
 			memcpy(&out.names[out.name_off[i]], w.names.data() + fb.name_off, fb.name_len);
@@ -931,12 +1032,12 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			}
 			for (u32 s = 0; s < 3; ++s) { const size_t x = (size_t) s * n + i; out.genes_off[x] = 0; out.genes_cnt[x] = 0; if (s == 2) { out.seq_off[x] = 0; out.seq_len[x] = 0; } }
 			for (u32 s = 0; s < fb.count; ++s) {
-				const aln_build& a = w.alns[fb.head + s];
+				const aln_build& a = w.norm_alns[fb.head + s];
 				const size_t x = (size_t) s * n + i;
 				out.contig[x] = a.contig; out.start[x] = a.start; out.end[x] = a.end;
 				out.aflags[x] = (a.supplementary ? AF_SUPPLEMENTARY : 0) | (a.first_in_pair ? AF_FIRST_IN_PAIR : 0) | (a.forward ? AF_FORWARD : 0) | AF_PRED_AMBIGUOUS;
 				out.cigar_off[x] = (u32) c; out.cigar_cnt[x] = (u16) a.cigar_cnt;
-				memcpy(&out.cigar[c], &w.cigars[a.cigar_off], 4ull * a.cigar_cnt); c += a.cigar_cnt;
+				memcpy(&out.cigar[c], &w.norm_cigars[a.cigar_off], 4ull * a.cigar_cnt); c += a.cigar_cnt;
 				if (s < 2) {
 					out.seq_off[x] = (u32) sq; out.seq_len[x] = (u16) a.seq_len;
 					if (a.seq_len) memcpy(&out.seq[sq * 16], &w.seqs[a.seq_off], (a.seq_len + 1) / 2);

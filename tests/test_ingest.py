@@ -120,3 +120,31 @@ def test_front_end_hostsim_parallel_record_scan(worlds, hostsim_lib, monkeypatch
     """Record boundaries found by several threads from guessed starts (verified against the true chain), down to pieces smaller than a record."""
     monkeypatch.setenv("ARB_SCAN_MIN_BYTES", min_bytes)
     check_front_end(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, threads=threads)
+
+
+@pytest.mark.parametrize("threads,min_bytes", [(6, "5000"), (13, "100")])
+def test_front_end_hostsim_parallel_block_table_compressed(worlds, hostsim_lib, monkeypatch, threads, min_bytes):
+    """The BGZF block table is found piecewise too (guessed block starts, verified against the true chain): deflate-compressed blocks, whose payload is
+    arbitrary bytes, and pieces smaller than one block."""
+    monkeypatch.setenv("ARB_SCAN_MIN_BYTES", min_bytes)
+    check_front_end(worlds.get("zsmall", seed=5, extra=("--compress", "6")), hostsim_lib, threads=threads)
+
+
+def test_block_table_errors_are_the_serial_ones(worlds, hostsim_lib, monkeypatch, tmp_path):
+    """A file cut inside a block, or with a damaged block header in the middle, fails with the message of the one-thread walk."""
+    from arriba_b200 import lib as L
+    world = worlds.get("small")
+    raw = open(world.prefix + ".bam", "rb").read()
+    damaged = bytearray(raw); mid = raw.find(b"\x1f\x8b\x08\x04", len(raw) // 2); damaged[mid + 1] = 0
+    cases = {"cut": raw[:len(raw) * 2 // 3], "damaged": bytes(damaged)}
+    for name, data in cases.items():
+        path = str(tmp_path / (name + ".bam")); open(path, "wb").write(data)
+        messages = []
+        for min_bytes, threads in (("1000000000", 1), ("1000", 9)):
+            monkeypatch.setenv("ARB_SCAN_MIN_BYTES", min_bytes)
+            p = L.Pipeline(path, world.prefix + ".gtf", world.prefix + ".fa", threads=threads, lib_path=hostsim_lib)
+            p.step(L.STEP_LOAD_REFERENCE)
+            with pytest.raises(L.ArbError) as err:
+                p.step(L.STEP_INGEST)
+            messages.append(str(err.value)); p.close()
+        assert messages[0] == messages[1] and "failed to load alignments" in messages[0], (name, messages)
