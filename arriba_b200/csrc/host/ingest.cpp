@@ -194,18 +194,33 @@ struct worker {
 		const u32 id = (u32) frags.size(); frags.push_back(f);
 		name_slots[at] = id + 1;
 		if (created) *created = true;
-		if (frags.size() * 2 > name_slots.size()) { // keep the load below one half
-			std::vector<u32> bigger(name_slots.size() * 2, 0); mask = bigger.size() - 1;
-			for (size_t k = 0; k < frags.size(); ++k) {
-				const frag_build& g = frags[k];
-				u64 hh = 1469598103934665603ULL; for (u32 i = 0; i < g.name_len; ++i) { hh ^= (u8) names[g.name_off + i]; hh *= 1099511628211ULL; }
-				hh ^= hh >> 29;
-				size_t slot = (size_t) hh & mask; while (bigger[slot] != 0) slot = (slot + 1) & mask;
-				bigger[slot] = (u32) k + 1;
-			}
-			name_slots.swap(bigger);
-		}
+		if (frags.size() * 2 > name_slots.size()) resize_name_slots(name_slots.size() * 2); // keep the load below one half
 		return id;
+	}
+	void resize_name_slots(size_t slots) { // a power of two
+		std::vector<u32> bigger(slots, 0); const size_t mask = bigger.size() - 1;
+		for (size_t k = 0; k < frags.size(); ++k) {
+			const frag_build& g = frags[k];
+			u64 hh = 1469598103934665603ULL; for (u32 i = 0; i < g.name_len; ++i) { hh ^= (u8) names[g.name_off + i]; hh *= 1099511628211ULL; }
+			hh ^= hh >> 29;
+			size_t slot = (size_t) hh & mask; while (bigger[slot] != 0) slot = (slot + 1) & mask;
+			bigger[slot] = (u32) k + 1;
+		}
+		name_slots.swap(bigger);
+	}
+	// After the first chunk the final size of every pool can be estimated from the share of the file seen so far. Growing a pool by doubling copies it again
+	// and again into fresh pages (gigabytes per worker on a large sample); one reservation up front is virtual memory until it is used. A hint only: the
+	// pools still grow by themselves where the estimate falls short; `cap_bytes` bounds what one pool may reserve.
+	void reserve_ahead(double factor, size_t cap_bytes) {
+		auto grow = [&](auto& v) {
+			typedef typename std::remove_reference<decltype(v)>::type::value_type value_type;
+			const size_t want = std::min((size_t) ((double) v.size() * factor) + 1024, std::max(v.size(), cap_bytes / sizeof(value_type)));
+			if (want > v.capacity()) { try { v.reserve(want); } catch (const std::bad_alloc&) {} } // a hint: no address space, no reservation
+		};
+		grow(names); grow(cigars); grow(seqs); grow(alns); grow(frags);
+		const size_t expected = std::min((size_t) ((double) frags.size() * factor), std::max(frags.size(), cap_bytes / sizeof(frag_build)));
+		size_t slots = std::max<size_t>(name_slots.size(), 1u << 12); while (slots < 2 * expected + 16) slots <<= 1;
+		if (slots > name_slots.size()) resize_name_slots(slots);
 	}
 	void link(u32 frag, const aln_build& a) {
 		const i32 id = (i32) alns.size(); alns.push_back(a); alns.back().next = -1;
@@ -695,7 +710,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 
 	// chunks of ~128 MiB of decompressed data, each a whole number of BGZF blocks; a record that straddles a chunk
 	// boundary is carried over to the front of the next buffer
-	const u64 chunk_target = 128ull << 20;
+	const u64 chunk_target = getenv("ARB_CHUNK_BYTES") ? (u64) atoll(getenv("ARB_CHUNK_BYTES")) : 128ull << 20; // env: test hook (many small chunks)
 	std::vector<worker> workers(T);
 	std::vector<u16> tid_to_contig; std::vector<u8> interesting_contig, viral_contig;
 	bool header_done = false;
@@ -845,6 +860,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	};
 	if (bam.blocks.empty()) fail("failed to read SAM header");
 	prepare(chunks[0], NULL);
+	bool reserved_ahead = false;
 	for (int cur = 0;; cur ^= 1) {
 		chunk_t& c = chunks[cur];
 		std::string prepare_error; std::thread next;
@@ -868,6 +884,11 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			});
 		} catch (const std::exception& x) { process_error = x.what(); }
 		stats.t_parse += now_s() - tp;
+		if (cur == 0 && !reserved_ahead && !c.last && process_error.empty() && c.consumed > 0) { // once, after the first chunk
+			reserved_ahead = true;
+			const double factor = 1.03 * (double) bam.total_out / (double) c.consumed;
+			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) workers[t].reserve_ahead(factor, (size_t) (1.5 * (double) bam.total_out / T)); });
+		}
 		if (next.joinable()) next.join();
 		if (!process_error.empty()) fail(process_error);
 		if (!prepare_error.empty()) fail(prepare_error);

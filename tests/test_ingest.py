@@ -148,3 +148,13 @@ def test_block_table_errors_are_the_serial_ones(worlds, hostsim_lib, monkeypatch
                 p.step(L.STEP_INGEST)
             messages.append(str(err.value)); p.close()
         assert messages[0] == messages[1] and "failed to load alignments" in messages[0], (name, messages)
+
+
+@pytest.mark.parametrize("threads,chunk_bytes,extra", [(4, "70000", ()), (3, "300000", ("--compress", "6")), (9, "1", ("--shuffle", "--varnames"))])
+def test_front_end_hostsim_many_chunks(worlds, hostsim_lib, monkeypatch, threads, chunk_bytes, extra):
+    """The file is read in chunks (128 MiB in production): records that straddle a chunk boundary are carried over, mates that wait for their partner
+    survive the recycling of the buffer, and the workers' pools are reserved ahead after the first chunk. Here: chunks of one to a few BGZF blocks."""
+    monkeypatch.setenv("ARB_CHUNK_BYTES", chunk_bytes)
+    name = "chunks_" + "_".join(x.strip("-") for x in extra) if extra else "small"
+    kw = dict(seed=5, extra=extra) if extra else {}
+    check_front_end(worlds.get(name, **kw), hostsim_lib, threads=threads)
