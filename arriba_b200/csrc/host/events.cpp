@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <set>
@@ -28,18 +29,45 @@ template <class F> static void parallel_rows(int threads, size_t n, F f) {
 	for (int t = 0; t < threads; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 }
 
-// sort on the host threads: slices sorted concurrently, then merged pairwise (log2(threads) rounds)
-template <class T, class Less> static void parallel_sort(std::vector<T>& v, Less less, int threads) {
+// sort on the host threads: slices sorted concurrently, then rounds of pairwise merges between the vector and a spare buffer; every merge is cut into
+// independent pieces by output rank, so all threads work down to the last round. For plain-data elements (the spare buffer is raw storage).
+template <class V, class Less> static void parallel_sort(V& v, Less less, int threads) {
+	typedef typename V::value_type T;
 	const size_t n = v.size();
 	if (threads <= 1 || n < 8192) { std::sort(v.begin(), v.end(), less); return; }
-	int parts = 1; while (parts * 2 <= threads) parts *= 2;
+	const int parts = std::min(threads, 256);
 	std::vector<size_t> cut(parts + 1); for (int t = 0; t <= parts; ++t) cut[t] = n * t / parts;
 	{ std::vector<std::thread> pool; for (int t = 0; t < parts; ++t) pool.emplace_back([&, t]() { std::sort(v.begin() + cut[t], v.begin() + cut[t + 1], less); }); for (size_t t = 0; t < pool.size(); ++t) pool[t].join(); }
+	T* const spare = (T*) malloc(n * sizeof(T));
+	if (!spare) throw std::bad_alloc();
+	T* src = v.data(); T* dst = spare;
+	// how many elements of A precede output rank r of merge(A, B); equal elements take A first
+	auto split = [&](const T* A, size_t nA, const T* B, size_t nB, size_t r) {
+		size_t lo = r > nB ? r - nB : 0, hi = std::min(r, nA);
+		while (lo < hi) { const size_t i = lo + (hi - lo) / 2, j = r - i; if (j == 0 || less(B[j - 1], A[i])) hi = i; else lo = i + 1; }
+		return lo;
+	};
 	for (int width = 1; width < parts; width *= 2) {
 		std::vector<std::thread> pool;
-		for (int t = 0; t + width < parts; t += 2 * width) pool.emplace_back([&, t, width]() { std::inplace_merge(v.begin() + cut[t], v.begin() + cut[t + width], v.begin() + cut[std::min(parts, t + 2 * width)], less); });
+		for (int t = 0; t < parts; t += 2 * width) {
+			const size_t a = cut[t], m = cut[std::min(parts, t + width)], b = cut[std::min(parts, t + 2 * width)];
+			const int pieces = std::min(parts - t, 2 * width);
+			for (int k = 0; k < pieces; ++k) pool.emplace_back([&, a, m, b, k, pieces]() {
+				const T* A = src + a; const T* B = src + m; const size_t nA = m - a, nB = b - m;
+				const size_t r0 = (b - a) * k / pieces, r1 = (b - a) * (k + 1) / pieces;
+				const size_t i0 = split(A, nA, B, nB, r0), i1 = split(A, nA, B, nB, r1);
+				std::merge(A + i0, A + i1, B + (r0 - i0), B + (r1 - i1), dst + a + r0, less);
+			});
+		}
+		for (size_t k = 0; k < pool.size(); ++k) pool[k].join();
+		std::swap(src, dst);
+	}
+	if (src != v.data()) {
+		std::vector<std::thread> pool;
+		for (int t = 0; t < parts; ++t) pool.emplace_back([&, t]() { std::copy(src + cut[t], src + cut[t + 1], v.data() + cut[t]); });
 		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 	}
+	free(spare);
 }
 
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
@@ -340,7 +368,7 @@ void pipeline::estimate_evalues() {
 		struct occurrence { u32 gene; i32 bp1, bp2; u32 rank; u32 partner; };
 		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
 		const size_t n_order = e.order.size();
-		std::vector<occurrence> all;
+		std::vector<occurrence, default_init_allocator<occurrence> > all;
 		{ // collected by slices of the iteration order, concatenated in slice order
 			const int T = std::max(1, std::min(threads, (int) (n_order / 4096 + 1)));
 			std::vector<std::vector<occurrence> > part(T);
@@ -355,9 +383,11 @@ void pipeline::estimate_evalues() {
 				}
 			});
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-			size_t total = 0; for (int t = 0; t < T; ++t) total += part[t].size();
-			all.reserve(total);
-			for (int t = 0; t < T; ++t) all.insert(all.end(), part[t].begin(), part[t].end());
+			std::vector<size_t> at(T + 1, 0); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + part[t].size();
+			all.resize(at[T]);
+			pool.clear();
+			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { std::copy(part[t].begin(), part[t].end(), all.begin() + at[t]); });
+			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 		}
 		parallel_sort(all, before, threads);
 		for (size_t x = 0; x < all.size(); ++x)

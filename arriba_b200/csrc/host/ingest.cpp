@@ -1019,8 +1019,8 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
 			// fragments in name order lie all over the workers' pools: the records of the ones a few steps ahead are requested early
-			if (i + 16 < hi) __builtin_prefetch(&workers[order[i + 16].worker].frags[order[i + 16].frag]);
-			if (i + 8 < hi) { const worker& w8 = workers[order[i + 8].worker]; __builtin_prefetch(&w8.norm_alns[w8.frags[order[i + 8].frag].head]); }
+			if (i + 32 < hi) __builtin_prefetch(&workers[order[i + 32].worker].frags[order[i + 32].frag]);
+			if (i + 16 < hi) { const worker& w8 = workers[order[i + 16].worker]; __builtin_prefetch(&w8.norm_alns[w8.frags[order[i + 16].frag].head]); }
 			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
 			u64 nc = 0, ns = 0;
 			for (u32 s = 0; s < fb.count; ++s) { const aln_build& a = w.norm_alns[fb.head + s]; nc += a.cigar_cnt; if (s < 2) ns += ((a.seq_len + 1) / 2 + 15) / 16; }
@@ -1033,13 +1033,13 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	out.cigar[cig_at[n]] = 0; memset(&out.seq[seq_at[n] * 16], 0, 16);
 	parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) {
 		for (size_t i = lo; i < hi; ++i) {
-			if (i + 16 < hi) __builtin_prefetch(&workers[order[i + 16].worker].frags[order[i + 16].frag]);
-			if (i + 8 < hi) {
-				const worker& w8 = workers[order[i + 8].worker]; const frag_build& f8 = w8.frags[order[i + 8].frag];
+			if (i + 32 < hi) __builtin_prefetch(&workers[order[i + 32].worker].frags[order[i + 32].frag]);
+			if (i + 16 < hi) {
+				const worker& w8 = workers[order[i + 16].worker]; const frag_build& f8 = w8.frags[order[i + 16].frag];
 				__builtin_prefetch(&w8.norm_alns[f8.head]); __builtin_prefetch(&w8.norm_alns[f8.head] + 2); __builtin_prefetch(w8.names.data() + f8.name_off);
 			}
-			if (i + 4 < hi) {
-				const worker& w4 = workers[order[i + 4].worker]; const frag_build& f4 = w4.frags[order[i + 4].frag];
+			if (i + 8 < hi) {
+				const worker& w4 = workers[order[i + 8].worker]; const frag_build& f4 = w4.frags[order[i + 8].frag];
 				for (u32 s = 0; s < f4.count; ++s) { const aln_build& a = w4.norm_alns[f4.head + s]; __builtin_prefetch(&w4.norm_cigars[a.cigar_off]); if (s < 2 && a.seq_len) { __builtin_prefetch(&w4.seqs[a.seq_off]); __builtin_prefetch(&w4.seqs[a.seq_off] + 48); } }
 			}
 			const worker& w = workers[order[i].worker]; const frag_build& fb = w.frags[order[i].frag];
