@@ -152,6 +152,17 @@ struct writer {
 	void pileup_reads(const column<u32>& list, u32 lo, u32 hi, u32 mate, bool reverse_complement, u32 direction, i32 breakpoint, pile_builder& pileup) const {
 		std::map<std::pair<i32, i32>, unsigned int> introns;
 		for (u32 x = lo; x < hi; ++x) {
+			// the supporting fragments of a candidate lie all over the fragment table: the columns of the ones a few steps ahead are requested early, then
+			// (once the offsets have arrived) their CIGAR and sequence
+			if (x + 8 < hi) {
+				const u32 g = list[x + 8], ga = f.idx(g, mate), gs = f.idx(g, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
+				__builtin_prefetch(&p.labels[g]); __builtin_prefetch(&f.n_aln[g]); __builtin_prefetch(&f.start[ga]); __builtin_prefetch(&f.end[ga]); __builtin_prefetch(&f.aflags[ga]);
+				__builtin_prefetch(&f.cigar_off[ga]); __builtin_prefetch(&f.cigar_cnt[ga]); __builtin_prefetch(&f.seq_off[gs]); __builtin_prefetch(&f.seq_len[gs]);
+			}
+			if (x + 4 < hi) {
+				const u32 g = list[x + 4], ga = f.idx(g, mate), gs = f.idx(g, mate == SUPPLEMENTARY ? SPLIT_READ : mate);
+				__builtin_prefetch(f.cig(ga)); __builtin_prefetch(f.sq(gs)); __builtin_prefetch(f.sq(gs) + 48);
+			}
 			const u32 frag = list[x];
 			if (p.labels[frag] == F_duplicates) continue;
 			const u32 a = f.idx(frag, mate);
@@ -660,7 +671,7 @@ struct writer {
 			unsigned int filter_count[38]; bool filter_present[38];
 			for (int f = 0; f < 38; ++f) { filter_count[f] = 0; filter_present[f] = false; }
 			if (e.filter[k] != F_none) filter_present[e.filter[k]] = true;
-			auto tally = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
+			auto tally = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { if (r + 8 < hi) __builtin_prefetch(&p.labels[list[r + 8]]); const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
 			tally(e.list1, e.list1_off[k], e.list1_off[k + 1]); tally(e.list2, e.list2_off[k], e.list2_off[k + 1]); tally(e.listd, e.listd_off[k], e.listd_off[k + 1]);
 			out << "\t" << (ref.genes[g5].is_dummy ? "." : ref.genes[g5].gene_id) << "\t" << (ref.genes[g3].is_dummy ? "." : ref.genes[g3].gene_id)
 			    << "\t" << (tr5 < 0 ? "." : ref.transcripts[tr5].name) << "\t" << (tr3 < 0 ? "." : ref.transcripts[tr3].name)
@@ -679,6 +690,8 @@ struct writer {
 				bool first_name = true;
 				auto names = [&](const column<u32>& list, u32 lo, u32 hi) {
 					for (u32 r = lo; r < hi; ++r) {
+						if (r + 8 < hi) __builtin_prefetch(&p.frags.name_off[list[r + 8]]);
+						if (r + 4 < hi) __builtin_prefetch(p.frags.names.data() + p.frags.name_off[list[r + 4]]);
 						if (!first_name) out << ",";
 						first_name = false;
 						const char* nm = p.frags.names.data() + p.frags.name_off[list[r]]; u64 len = p.frags.name_off[list[r] + 1] - p.frags.name_off[list[r]];
