@@ -5,6 +5,7 @@
 // (assign_strands_from_strandedness). Gene sets are ordered by gene id (creation order), see refdata.h.
 #include "pipeline.h"
 #include "../annot_hd.h"
+#include "index_query.h"
 #include <algorithm>
 #include <cmath>
 #include <iostream>
@@ -15,7 +16,7 @@
 namespace arb { namespace host {
 
 typedef idset<1024> gset;       // gene set of one alignment (an alignment with a long intron gap spans many genes)
-typedef idset<16384> eset;     // exons under one alignment
+enum { EXON_SET_CAPACITY = 16384 }; // exons under one alignment (reached through index_query: a small set first)
 
 template <class F> static void parallel_ranges(int threads, size_t n, F f) {
 	if (threads <= 1 || n < 1024) { f(0, (size_t) 0, n); return; }
@@ -38,10 +39,9 @@ template <int CAP> static void check_overflow(const idset<CAP>& s) { if (s.overf
 
 // gene set and strand of one alignment from the exon index (annotation.cpp:431-503)
 static void annotate_alignment(const annot_view& an, const frag_view& f, u32 a, gset& genes) {
-	eset exons_hit;
-	query_index(exon_index(an), f.contig[a], f.start[a], f.end[a], exons_hit); check_overflow(exons_hit);
 	genes.clear();
-	for (u32 k = 0; k < exons_hit.n; ++k) genes.insert(an.exon_gene[exons_hit.v[k]]);
+	index_query<EXON_SET_CAPACITY>(exon_index(an), f.contig[a], f.start[a], f.end[a], [&](const u32* exons_hit, u32 n) { for (u32 k = 0; k < n; ++k) genes.insert(an.exon_gene[exons_hit[k]]); },
+	                               "more than 16384 overlapping genes or exons under one alignment are not supported");
 	check_overflow(genes);
 	const bool ambiguous_strand = f.aflags[a] & AF_PRED_AMBIGUOUS;
 	if (!(f.cigar_cnt[a] > 1 && (genes.n > 1 || ambiguous_strand))) return;

@@ -4,6 +4,7 @@
 // Tags (-t) and protein domains (-p) need database files that are not part of the reference repository; their columns are ".".
 #include "pipeline.h"
 #include "../annot_hd.h"
+#include "index_query.h"
 #include <algorithm>
 #include <atomic>
 #include <fcntl.h>
@@ -601,10 +602,10 @@ struct writer {
 		if (g.is_dummy || bp < g.start || bp > g.end) return "intergenic";
 		if (!exonic) return "intron";
 		const annot_view an = const_cast<refdata&>(ref).host_view();
-		idset<4096> exons; query_index(exon_index(an), contig, bp, bp, exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
 		bool overlapping = false, utr = true; unsigned int end3 = 0, end5 = 0;
-		for (u32 x = 0; x < exons.n; ++x) {
-			const exon_rec& E = ref.exons[exons.v[x]];
+		index_query<4096>(exon_index(an), contig, bp, bp, [&](const u32* exons, u32 n_exons) {
+		for (u32 x = 0; x < n_exons; ++x) {
+			const exon_rec& E = ref.exons[exons[x]];
 			if (E.gene != gene) continue;
 			overlapping = true;
 			if (E.cds_start <= bp && E.cds_end >= bp) utr = false;
@@ -618,6 +619,7 @@ struct writer {
 				}
 			}
 		}
+		}, "too many overlapping annotation records at one locus");
 		std::string s;
 		if (!overlapping) s = "intron";
 		else if (g.is_protein_coding) { if (utr) s = end3 > end5 ? "3'UTR" : end3 < end5 ? "5'UTR" : end3 + end5 == 0 ? "exon" : "UTR"; else s = "CDS"; }
