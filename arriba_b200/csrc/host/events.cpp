@@ -4,6 +4,7 @@
 // Each function cites the reference file it reproduces.
 #include "pipeline.h"
 #include "../annot_hd.h"
+#include "index_query.h"
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -579,8 +580,8 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 	laps.lap("top expressed genes");
 	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
 		unsigned int highest = reads_by_gene[gene];
-		idset<1024> genes; query_index(gene_index(an), contig, bp, bp, genes); if (genes.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
-		for (u32 x = 0; x < genes.n; ++x) if (reads_by_gene[genes.v[x]] > highest) { highest = reads_by_gene[genes.v[x]]; gene = genes.v[x]; }
+		index_query<1024>(gene_index(an), contig, bp, bp, [&](const u32* genes, u32 n) { for (u32 x = 0; x < n; ++x) if (reads_by_gene[genes[x]] > highest) { highest = reads_by_gene[genes[x]]; gene = genes[x]; } },
+		                  "too many overlapping annotation records at one locus");
 		return gene;
 	};
 	auto pair_count = [&](u32 a, u32 b) { const u64 key = (u64) a << 32 | b; const std::pair<std::vector<u64>::const_iterator, std::vector<u64>::const_iterator> r = std::equal_range(exonic_breakpoints.begin(), exonic_breakpoints.end(), key); return (unsigned int) (r.second - r.first); };

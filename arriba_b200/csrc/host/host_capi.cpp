@@ -1,6 +1,7 @@
 // host_capi.cpp -- C ABI of the whole-run driver (include/arriba_b200.h, "whole-run driver" section).
 #include <malloc.h>
 #include "pipeline.h"
+#include "index_query.h"
 #include <cstring>
 #include <stdexcept>
 
@@ -161,6 +162,28 @@ int arb_pipeline_candidates(arb_pipeline* x, arb_candidates* c, const uint32_t**
 	if (confidence) *confidence = e.confidence.data();
 	if (labels) *labels = x->p.labels.data();
 	PIPE_END(x)
+}
+
+/* tests only (tests/test_prims.py), not part of the public header: the small-set-first front end of the annotation queries (index_query.h) against the plain
+   query with a large set, on a hand-made index whose loci hold up to `crowd` records; returns the number of queries that differ */
+int arb_selftest_index_query(uint32_t crowd) {
+	using namespace arb;
+	// regions (ends ascending): a crowded one, a second crowded one ending 1 bp later (range queries merge neighbours within 2 bp), then sparse ones
+	std::vector<i32> end; std::vector<u32> off(1, 0), items;
+	auto region = [&](i32 e, u32 first, u32 n) { end.push_back(e); for (u32 k = 0; k < n; ++k) items.push_back(first + k); off.push_back((u32) items.size()); };
+	region(100, 0, crowd); region(101, crowd / 2, crowd); region(500, 5, 1); region(900, 7, 3); region(2000, 2 * crowd, 2);
+	const u32 begin[2] = {0, (u32) end.size()};
+	region_index_view ix; ix.begin = begin; ix.end = end.data(); ix.off = off.data(); ix.items = items.data(); ix.n_contigs = 1; ix.grid = NULL; ix.grid_begin = NULL;
+	int differing = 0;
+	const i32 points[] = {0, 50, 99, 100, 101, 102, 300, 498, 500, 501, 899, 900, 1500, 2000, 2001};
+	for (size_t a = 0; a < sizeof(points) / sizeof(points[0]); ++a)
+		for (size_t b = 0; b < sizeof(points) / sizeof(points[0]); ++b) {
+			idset<4096> want; query_index(ix, 0, points[a], points[b], want);
+			std::vector<u32> got;
+			host::index_query<4096>(ix, 0, points[a], points[b], [&](const u32* v, u32 n) { got.assign(v, v + n); }, "overflow");
+			if (want.overflow || got.size() != want.n || !std::equal(got.begin(), got.end(), want.v)) ++differing;
+		}
+	return differing;
 }
 
 } // extern "C"

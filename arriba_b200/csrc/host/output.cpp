@@ -6,6 +6,7 @@
 #include "../annot_hd.h"
 #include "index_query.h"
 #include <algorithm>
+#include <charconv>
 #include <atomic>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -127,6 +128,24 @@ struct pile_builder {
 		for (size_t x = 0; x < used_list.size(); ++x) out.push_back(column_of(lo + (i32) used_list[x], dense[used_list[x]]));
 		for (; k < far.size(); ++k) out.push_back(column_of(far[k].first, far_cell[far[k].second]));
 	}
+};
+
+// The text of a slice of rows: what the writer needs of an output stream (operator<< for strings, characters and integers, write()), appending to one string.
+// A std::ostringstream spends more time in its sentries and locale facets than the rows' own logic does (millions of discarded rows are pure formatting).
+struct row_buffer {
+	std::string s;
+	row_buffer& operator<<(const char* x) { s.append(x); return *this; }
+	row_buffer& operator<<(const std::string& x) { s.append(x); return *this; }
+	row_buffer& operator<<(char c) { s.push_back(c); return *this; }
+	row_buffer& operator<<(int v) { return number((long long) v); }
+	row_buffer& operator<<(unsigned int v) { return number((unsigned long long) v); }
+	row_buffer& operator<<(long v) { return number((long long) v); }
+	row_buffer& operator<<(unsigned long v) { return number((unsigned long long) v); }
+	row_buffer& operator<<(long long v) { return number(v); }
+	row_buffer& operator<<(unsigned long long v) { return number(v); }
+	void write(const char* p, size_t n) { s.append(p, n); }
+private:
+	template <class I> row_buffer& number(I v) { char b[24]; const std::to_chars_result r = std::to_chars(b, b + sizeof(b), v); s.append(b, (size_t) (r.ptr - b)); return *this; }
 };
 
 char comp_char(char c) { // assembly.hpp:9-22
@@ -638,7 +657,7 @@ struct writer {
 		return e.bp2[x] < e.bp2[y];
 	}
 
-	void format_row(std::ostream& out, u32 k, bool extra_info) const {
+	void format_row(row_buffer& out, u32 k, bool extra_info) const {
 			static const char* CONF[] = {"low", "medium", "high", "high"};
 			std::string site5 = site(e.gene1[k], e.spliced1(k), e.exonic1(k), e.contig1[k], e.bp1[k]), site3 = site(e.gene2[k], e.spliced2(k), e.exonic2(k), e.contig2[k], e.bp2[k]);
 			u32 g5 = e.gene1[k], g3 = e.gene2[k], c5 = e.contig1[k], c3 = e.contig2[k], d5 = e.dir1[k], d3 = e.dir2[k], s5 = e.split_reads1[k], s3 = e.split_reads2[k];
@@ -740,9 +759,9 @@ struct writer {
 						const size_t c = next_chunk.fetch_add(1);
 						if (c >= n_chunks) break;
 						warning_sink = &warnings[c]; // warnings of a chunk are printed after it, in row order like the reference's
-						std::ostringstream os;
-						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(os, rows[x], extra_info);
-						slices[c] = os.str();
+						row_buffer text; text.s.reserve(CHUNK * (extra_info ? 4096 : 256));
+						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(text, rows[x], extra_info);
+						slices[c].swap(text.s);
 					}
 				} catch (const std::exception& ex) { errors[t] = ex.what(); }
 				warning_sink = NULL;

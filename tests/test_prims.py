@@ -62,3 +62,12 @@ def test_pool_size_classes(hostsim_lib):
         c = int(lib.arb_selftest_pool_size_class(int(s)))
         assert c >= s and c % 512 == 0 and c <= max(512, int(s) * 2), (s, c)
         assert c >= prev; prev = c
+
+
+def test_annotation_query_front_end(hostsim_lib):
+    """index_query.h asks with a 48-entry set first and repeats the query with the large set where that overflows: same answers as the plain query, for
+    loci below, at and far above the small capacity."""
+    lib = C.CDLL(hostsim_lib)
+    lib.arb_selftest_index_query.argtypes = [C.c_uint32]
+    for crowd in (3, 24, 47, 48, 49, 96, 1000):
+        assert lib.arb_selftest_index_query(crowd) == 0, crowd
