@@ -657,6 +657,21 @@ struct writer {
 		return e.bp2[x] < e.bp2[y];
 	}
 
+	// Rows are written in the reference's order (support, or the hash order of its candidate map), candidates and their reads therefore lie all over the
+	// tables: the columns of a row a few rows ahead are requested early, then (once the list offsets have arrived) its first read lists and their labels.
+	void prefetch_candidate(u32 k) const {
+		__builtin_prefetch(&e.gene1[k]); __builtin_prefetch(&e.gene2[k]); __builtin_prefetch(&e.contig1[k]); __builtin_prefetch(&e.contig2[k]); __builtin_prefetch(&e.bp1[k]); __builtin_prefetch(&e.bp2[k]);
+		__builtin_prefetch(&e.dir1[k]); __builtin_prefetch(&e.dir2[k]); __builtin_prefetch(&e.bits[k]); __builtin_prefetch(&e.filter[k]); __builtin_prefetch(&e.confidence[k]);
+		__builtin_prefetch(&e.split_reads1[k]); __builtin_prefetch(&e.split_reads2[k]); __builtin_prefetch(&e.discordant_mates[k]);
+		__builtin_prefetch(&e.list1_off[k]); __builtin_prefetch(&e.list2_off[k]); __builtin_prefetch(&e.listd_off[k]);
+	}
+	void prefetch_lists(u32 k) const { __builtin_prefetch(&e.list1[e.list1_off[k]]); __builtin_prefetch(&e.list2[e.list2_off[k]]); __builtin_prefetch(&e.listd[e.listd_off[k]]); __builtin_prefetch(&ref.genes[e.gene1[k]]); __builtin_prefetch(&ref.genes[e.gene2[k]]); }
+	void prefetch_labels(u32 k) const {
+		for (u32 r = e.list1_off[k]; r < e.list1_off[k + 1] && r < e.list1_off[k] + 8; ++r) __builtin_prefetch(&p.labels[e.list1[r]]);
+		for (u32 r = e.list2_off[k]; r < e.list2_off[k + 1] && r < e.list2_off[k] + 8; ++r) __builtin_prefetch(&p.labels[e.list2[r]]);
+		for (u32 r = e.listd_off[k]; r < e.listd_off[k + 1] && r < e.listd_off[k] + 8; ++r) __builtin_prefetch(&p.labels[e.listd[r]]);
+	}
+
 	void format_row(row_buffer& out, u32 k, bool extra_info) const {
 			static const char* CONF[] = {"low", "medium", "high", "high"};
 			std::string site5 = site(e.gene1[k], e.spliced1(k), e.exonic1(k), e.contig1[k], e.bp1[k]), site3 = site(e.gene2[k], e.spliced2(k), e.exonic2(k), e.contig2[k], e.bp2[k]);
@@ -692,7 +707,7 @@ struct writer {
 			unsigned int filter_count[38]; bool filter_present[38];
 			for (int f = 0; f < 38; ++f) { filter_count[f] = 0; filter_present[f] = false; }
 			if (e.filter[k] != F_none) filter_present[e.filter[k]] = true;
-			auto tally = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { if (r + 8 < hi) __builtin_prefetch(&p.labels[list[r + 8]]); const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
+			auto tally = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 r = lo; r < hi; ++r) { if (r + 32 < hi) __builtin_prefetch(&p.labels[list[r + 32]]); const u8 l = p.labels[list[r]]; if (l != F_none && l < 38) { filter_present[l] = true; ++filter_count[l]; } } };
 			tally(e.list1, e.list1_off[k], e.list1_off[k + 1]); tally(e.list2, e.list2_off[k], e.list2_off[k + 1]); tally(e.listd, e.listd_off[k], e.listd_off[k + 1]);
 			out << "\t" << (ref.genes[g5].is_dummy ? "." : ref.genes[g5].gene_id) << "\t" << (ref.genes[g3].is_dummy ? "." : ref.genes[g3].gene_id)
 			    << "\t" << (tr5 < 0 ? "." : ref.transcripts[tr5].name) << "\t" << (tr3 < 0 ? "." : ref.transcripts[tr3].name)
@@ -760,7 +775,12 @@ struct writer {
 						if (c >= n_chunks) break;
 						warning_sink = &warnings[c]; // warnings of a chunk are printed after it, in row order like the reference's
 						row_buffer text; text.s.reserve(CHUNK * (extra_info ? 4096 : 256));
-						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) format_row(text, rows[x], extra_info);
+						for (size_t x = c * CHUNK; x < rows.size() && x < (c + 1) * CHUNK; ++x) {
+							if (x + 6 < rows.size()) prefetch_candidate(rows[x + 6]);
+							if (x + 4 < rows.size()) prefetch_lists(rows[x + 4]);
+							if (x + 2 < rows.size()) prefetch_labels(rows[x + 2]);
+							format_row(text, rows[x], extra_info);
+						}
 						slices[c].swap(text.s);
 					}
 				} catch (const std::exception& ex) { errors[t] = ex.what(); }
