@@ -279,7 +279,7 @@ def main():
             "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
     if extra_sharded:
         line["sharded_single_sample"] = extra_sharded
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU reference beside the GPU number: rank 0 at N=1 only
         sp = ensure_world(args.workload, sample_bp)
         n, scope_s, total = reference_run(sp, cores)
         line["cpu_baseline"] = {"value": n / scope_s, "unit": UNIT, "cores": 1, "kind": "reference",
