@@ -175,8 +175,12 @@ void pipeline::fetch_candidates() {
 	check(ctx, arb_get_candidates(ctx, &c), "arb_get_candidates");
 	laps.lap("device -> host");
 	e.list1.resize(n1); e.list2.resize(n2); e.listd.resize(nd);
-	e.replay_iteration_order(threads);
-	laps.lap("iteration order");
+	// the order needs the candidate keys only, which no later stage changes: it is replayed (one thread, after the hashes) beside the stages up to the e-value
+	if (order_thread.joinable()) order_thread.join();
+	order_error.clear();
+	e.order.clear();
+	order_thread = std::thread([this]() { try { ev.replay_iteration_order(threads); } catch (const std::exception& x) { order_error = x.what(); if (order_error.empty()) order_error = "iteration order"; } });
+	laps.lap("iteration order started");
 	// mirror the canonical mate order the device established for listed discordant mates (fusions.cpp:414-421)
 	std::vector<u8> swapped(frags.n);
 	check(ctx, arb_get_slot_swaps(ctx, swapped.data()), "arb_get_slot_swaps");
@@ -190,6 +194,11 @@ void pipeline::fetch_candidates() {
 	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
 	laps.lap("mate swaps + labels");
 	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")"; say(s.str());
+}
+
+void pipeline::order_ready() {
+	if (order_thread.joinable()) order_thread.join();
+	if (!order_error.empty()) { const std::string what = order_error; order_error.clear(); throw std::runtime_error(what); }
 }
 
 void pipeline::push_candidate_state() {
@@ -361,6 +370,8 @@ void pipeline::filter_multimappers() {
 void pipeline::estimate_evalues() {
 	event_table& e = ev;
 	stage_laps laps("evalue");
+	order_ready(); // first stage that visits candidates in the reference's order
+	laps.lap("iteration order joined");
 	// global statistics (filter_relative_support.cpp:19-127). Fusion partners of every gene: of the candidates that share (gene, breakpoint1, breakpoint2)
 	// -- the same breakpoints annotated with overlapping partner genes -- only the one the reference visits FIRST contributes its partner
 	// (`overlap_duplicates`, :22-30). First = smallest rank in the replayed iteration order; found by sorting instead of a hash map per candidate.

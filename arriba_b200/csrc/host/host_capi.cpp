@@ -153,6 +153,7 @@ int arb_pipeline_events(arb_pipeline* x, int last_stage) { PIPE_BEGIN(x) x->p.ev
 
 int arb_pipeline_candidates(arb_pipeline* x, arb_candidates* c, const uint32_t** order, const uint8_t** confidence, const uint8_t** labels) {
 	PIPE_BEGIN(x)
+	x->p.order_ready();
 	event_table& e = x->p.ev;
 	c->n = e.n; c->gene1 = e.gene1.data(); c->gene2 = e.gene2.data(); c->contig1 = e.contig1.data(); c->contig2 = e.contig2.data(); c->breakpoint1 = e.bp1.data(); c->breakpoint2 = e.bp2.data();
 	c->direction1 = e.dir1.data(); c->direction2 = e.dir2.data(); c->split_reads1 = e.split_reads1.data(); c->split_reads2 = e.split_reads2.data(); c->discordant_mates = e.discordant_mates.data();

@@ -827,6 +827,7 @@ const char* const FILTER_NAMES[38] = {"", "duplicates", "inconsistently_clipped"
 	"no_genomic_support", "uninteresting_contigs", "viral_contigs", "top_expressed_viral_contigs", "low_coverage_viral_contigs", "genomic_support", "isoforms", "low_entropy", "homologs"};
 
 void pipeline::write_output() {
+	order_ready();
 	const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	writer w(*this);
 	if (!opt.output_file.empty()) { say("Writing fusions to file '" + opt.output_file + "'"); w.write(opt.output_file, false, true); }
