@@ -740,7 +740,9 @@ struct writer {
 			out << "\n";
 	}
 
-	void write(const std::string& path, bool discarded, bool extra_info) const {
+	// A file is produced in two steps, so that the (lock-bound) copy of one file into the page cache can run beside the (CPU-bound) formatting of the other
+	struct formatted { std::string header; std::vector<std::string> slices, warnings; };
+	void format_rows(bool discarded, bool extra_info, formatted& out) const {
 		sort_filters_by_name();
 		output_laps laps; const char* const which = discarded ? "discarded" : "fusions";
 		std::vector<u32> rows;
@@ -757,14 +759,14 @@ struct writer {
 			});
 		}
 		const std::string header = "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n";
-		// rows are independent: every host thread formats a slice of the row list, then writes it at its offset of the file (the discarded file of a large
-		// sample is a gigabyte; one writer would spend seconds copying into the page cache)
-		// Rows cost very different amounts (the best-supported fusions come first and carry hundreds of reads each): threads draw small chunks of rows from
-		// a shared counter; every chunk is formatted into its own string and later written at its offset of the file.
+		// Rows are independent and cost very different amounts (the best-supported fusions come first and carry hundreds of reads each): threads draw small
+		// chunks of rows from a shared counter; every chunk is formatted into its own string and later copied to its offset of the file (flush_rows).
 		const size_t CHUNK = 32;
 		const size_t n_chunks = (rows.size() + CHUNK - 1) / CHUNK;
 		const int T = std::max(1, std::min(p.threads, (int) (n_chunks ? n_chunks : 1)));
-		std::vector<std::string> slices(n_chunks), warnings(n_chunks); std::vector<std::string> errors(T);
+		out.header = header;
+		std::vector<std::string>& slices = out.slices; std::vector<std::string>& warnings = out.warnings;
+		slices.assign(n_chunks, std::string()); warnings.assign(n_chunks, std::string()); std::vector<std::string> errors(T);
 		{
 			std::atomic<size_t> next_chunk(0);
 			std::vector<std::thread> pool;
@@ -790,8 +792,17 @@ struct writer {
 		}
 		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 		laps.lap(which, "rows formatted");
+	}
+	static int open_output(const std::string& path) {
 		const int fd = ::open(path.c_str(), O_RDWR | O_CREAT | O_TRUNC, 0666);
 		if (fd < 0) throw std::runtime_error("failed to open output file");
+		return fd;
+	}
+	void flush_rows(int fd, const formatted& text, bool discarded) const { // writes and closes; the warnings of the rows go to stderr afterwards
+		output_laps laps; const char* const which = discarded ? "discarded" : "fusions";
+		const std::string& header = text.header; const std::vector<std::string>& slices = text.slices; const std::vector<std::string>& warnings = text.warnings;
+		const size_t n_chunks = slices.size();
+		const int T = std::max(1, std::min(p.threads, (int) (n_chunks ? n_chunks : 1)));
 		std::vector<u64> at(n_chunks + 1); at[0] = header.size(); for (size_t c = 0; c < n_chunks; ++c) at[c + 1] = at[c] + slices[c].size();
 		bool ok = true;
 		const u64 total = at[n_chunks];
@@ -830,8 +841,33 @@ void pipeline::write_output() {
 	order_ready();
 	const double t0 = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 	writer w(*this);
-	if (!opt.output_file.empty()) { say("Writing fusions to file '" + opt.output_file + "'"); w.write(opt.output_file, false, true); }
-	if (!opt.discarded_output_file.empty()) { say("Writing discarded fusions to file '" + opt.discarded_output_file + "'"); w.write(opt.discarded_output_file, true, opt.print_extra_info_for_discarded_fusions); }
+	const bool fusions = !opt.output_file.empty(), discarded = !opt.discarded_output_file.empty();
+	// files are opened and announced in the reference's order (output_fusions.cpp:1043, arriba.cpp:601-612)
+	int fd_fusions = -1, fd_discarded = -1;
+	if (fusions) fd_fusions = writer::open_output(opt.output_file);
+	if (discarded) { try { fd_discarded = writer::open_output(opt.discarded_output_file); } catch (...) { if (fd_fusions >= 0) ::close(fd_fusions); throw; } }
+	writer::formatted text_fusions, text_discarded;
+	std::thread copier; std::string copier_error;
+	// The discarded file (a gigabyte on a large sample) is formatted first and copied into the page cache by a helper WHILE the rows of the fusions file, which
+	// cost pileups and consensus sequences, are formatted. Only without -X: with it the discarded rows print warnings too, and stderr keeps the reference's order.
+	const bool overlap = fusions && discarded && !opt.print_extra_info_for_discarded_fusions;
+	try {
+		if (fusions) say("Writing fusions to file '" + opt.output_file + "'");
+		if (overlap) {
+			w.format_rows(true, false, text_discarded);
+			const int fd = fd_discarded; fd_discarded = -1; // closed by the helper
+			copier = std::thread([&, fd]() { try { w.flush_rows(fd, text_discarded, true); } catch (const std::exception& x) { copier_error = x.what(); } });
+		}
+		if (fusions) { w.format_rows(false, true, text_fusions); const int fd = fd_fusions; fd_fusions = -1; w.flush_rows(fd, text_fusions, false); }
+		if (discarded) say("Writing discarded fusions to file '" + opt.discarded_output_file + "'");
+		if (overlap) { copier.join(); if (!copier_error.empty()) throw std::runtime_error(copier_error); }
+		else if (discarded) { w.format_rows(true, opt.print_extra_info_for_discarded_fusions, text_discarded); const int fd = fd_discarded; fd_discarded = -1; w.flush_rows(fd, text_discarded, true); }
+	} catch (...) {
+		if (copier.joinable()) copier.join();
+		if (fd_fusions >= 0) ::close(fd_fusions);
+		if (fd_discarded >= 0) ::close(fd_discarded);
+		throw;
+	}
 	t_output = std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count() - t0;
 }
 
