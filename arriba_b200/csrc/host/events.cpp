@@ -6,6 +6,7 @@
 #include "../annot_hd.h"
 #include "index_query.h"
 #include <algorithm>
+#include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -25,7 +26,12 @@ namespace arb { namespace host {
 template <class F> static void parallel_rows(int threads, size_t n, F f) {
 	if (threads <= 1 || n < 4096) { for (size_t k = 0; k < n; ++k) f((u32) k); return; }
 	std::vector<std::thread> pool; std::vector<std::string> errors(threads);
-	for (int t = 0; t < threads; ++t) pool.emplace_back([&, t]() { try { for (size_t k = n * t / threads; k < n * (t + 1) / threads; ++k) f((u32) k); } catch (const std::exception& x) { errors[t] = x.what(); } });
+	// rows cost very different amounts (a candidate with thousands of supporting reads next to thousands with one): blocks of rows are drawn from a counter
+	const size_t BLOCK = 2048; std::atomic<size_t> next(0);
+	for (int t = 0; t < threads; ++t) pool.emplace_back([&, t]() {
+		try { for (;;) { const size_t lo = next.fetch_add(BLOCK); if (lo >= n) break; const size_t hi = std::min(n, lo + BLOCK); for (size_t k = lo; k < hi; ++k) f((u32) k); } }
+		catch (const std::exception& x) { errors[t] = x.what(); next.store(n); }
+	});
 	for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 	for (int t = 0; t < threads; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
 }
