@@ -410,7 +410,7 @@ void pipeline::estimate_evalues() {
 		parallel_sort(all, before, threads);
 		for (size_t x = 0; x < all.size(); ++x)
 			if (x == 0 || all[x].gene != all[x - 1].gene || all[x].bp1 != all[x - 1].bp1 || all[x].bp2 != all[x - 1].bp2) pairs.push_back((u64) all[x].gene << 32 | all[x].partner);
-		std::sort(pairs.begin(), pairs.end()); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
+		parallel_sort(pairs, [](u64 a, u64 b) { return a < b; }, threads); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
 	}
 	laps.lap("partner pairs");
 	std::vector<u32> n_partners(ref.genes.size(), 0);
