@@ -191,12 +191,13 @@ void pipeline::fetch_candidates() {
 	std::vector<u8> swapped(frags.n);
 	check(ctx, arb_get_slot_swaps(ctx, swapped.data()), "arb_get_slot_swaps");
 	const size_t N = frags.n;
-	for (size_t i = 0; i < N; ++i) if (swapped[i]) {
+	parallel_rows(threads, N, [&](u32 i) {
+		if (!swapped[i]) return;
 		const size_t a = i, b = N + i;
 		std::swap(frags.contig[a], frags.contig[b]); std::swap(frags.start[a], frags.start[b]); std::swap(frags.end[a], frags.end[b]); std::swap(frags.aflags[a], frags.aflags[b]);
 		std::swap(frags.cigar_off[a], frags.cigar_off[b]); std::swap(frags.cigar_cnt[a], frags.cigar_cnt[b]); std::swap(frags.seq_off[a], frags.seq_off[b]); std::swap(frags.seq_len[a], frags.seq_len[b]);
 		std::swap(frags.genes_off[a], frags.genes_off[b]); std::swap(frags.genes_cnt[a], frags.genes_cnt[b]);
-	}
+	});
 	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
 	laps.lap("mate swaps + labels");
 	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")"; say(s.str());
