@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -443,11 +444,18 @@ void pipeline::estimate_evalues() {
 	const float rt_fraction = genes_with_fusions == 0 ? 0 : 1.0 * genes_with_read_through / genes_with_fusions;
 	// pow() tables over the integer domains of the reference's expressions (filter_relative_support.cpp:143-205), same libm
 	u32 max_reads = 0; for (u32 k = 0; k < e.n; ++k) max_reads = std::max(max_reads, e.supporting_reads(k));
-	std::vector<double> t_reads(max_reads + 2), t_intra(max_reads + 2), t_inter(max_reads + 2), t_s1000(1000), t_s400(400), t_rt(400000), t_prox(400000);
+	std::vector<double> t_reads(max_reads + 2), t_intra(max_reads + 2), t_inter(max_reads + 2), t_s1000(1000), t_s400(400);
+	// the two distance tables (400,000 entries each) do not depend on the sample: filled once per process, on all threads
+	static std::vector<double> t_rt, t_prox; static std::once_flag distance_tables;
+	std::call_once(distance_tables, [&]() {
+		t_rt.resize(400000); t_prox.resize(400000);
+		const int T = std::max(1, threads); std::vector<std::thread> pool;
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (int d = 400000 / T * t; d < (t + 1 == T ? 400000 : 400000 / T * (t + 1)); ++d) { t_rt[d] = pow(std::max(1, d) / 400000.0, -0.63); t_prox[d] = pow(std::max(1, d) / 400000.0, -1.53); } });
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+	});
 	for (unsigned int nr = 0; nr < t_reads.size(); ++nr) { t_reads[nr] = pow(0.02, nr - 2); t_intra[nr] = pow(nr - 0.42, -2.11) * pow(10, -1.11); t_inter[nr] = pow(nr - 0.73, -2.28) * pow(10, -1.75); }
 	for (int d = 0; d < 1000; ++d) t_s1000[d] = pow(std::max(400, d) / 1000.0, -2);
 	for (int d = 0; d < 400; ++d) t_s400[d] = pow(std::max(1, d) / 400.0, -4.58);
-	for (int d = 0; d < 400000; ++d) { t_rt[d] = pow(std::max(1, d) / 400000.0, -0.63); t_prox[d] = pow(std::max(1, d) / 400000.0, -1.53); }
 	in.partner_count = partner_count.data(); in.n_genes = (uint32_t) partner_count.size();
 	in.spliced_breakpoints = spliced; in.exonic_breakpoints = exonic; in.intronic_breakpoints = intronic; in.exonic_intronic_breakpoints = mixed;
 	in.intragenic_duplications = dups; in.intragenic_inversions = invs; in.spliced_same_gene = same; in.spliced_different_genes = diff;
