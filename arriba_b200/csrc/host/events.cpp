@@ -1070,3 +1070,18 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 }
 
 }} // namespace
+
+// tests only (tests/test_prims.py), not part of the public header: parallel_sort against std::sort on pseudo-random records with many equal keys;
+// returns 0 when the two orders are identical (the comparison is total, so there is exactly one sorted order)
+extern "C" int arb_selftest_host_sort(uint32_t n, int threads, uint32_t seed) {
+	struct rec { uint32_t key, rank; };
+	std::vector<rec> a(n);
+	uint64_t x = seed * 2654435761ull + 1;
+	for (uint32_t i = 0; i < n; ++i) { x = x * 6364136223846793005ull + 1442695040888963407ull; a[i].key = (uint32_t) (x >> 40) % (n / 4 + 1); a[i].rank = i; }
+	std::vector<rec> b(a);
+	auto less = [](const rec& p, const rec& q) { return p.key != q.key ? p.key < q.key : p.rank < q.rank; };
+	arb::host::parallel_sort(a, less, threads);
+	std::sort(b.begin(), b.end(), less);
+	for (uint32_t i = 0; i < n; ++i) if (a[i].key != b[i].key || a[i].rank != b[i].rank) return 1;
+	return 0;
+}

@@ -71,3 +71,13 @@ def test_annotation_query_front_end(hostsim_lib):
     lib.arb_selftest_index_query.argtypes = [C.c_uint32]
     for crowd in (3, 24, 47, 48, 49, 96, 1000):
         assert lib.arb_selftest_index_query(crowd) == 0, crowd
+
+
+def test_host_sort_split_merges(hostsim_lib):
+    """The host sort of the event stages (slice sorts, then merges cut by output rank through a spare buffer) against std::sort: thread counts that are not
+    powers of two, sizes around the serial threshold, many equal keys."""
+    lib = C.CDLL(hostsim_lib)
+    lib.arb_selftest_host_sort.argtypes = [C.c_uint32, C.c_int, C.c_uint32]
+    for threads in (1, 2, 3, 5, 8, 13, 32):
+        for n in (0, 1, 100, 8191, 8192, 8193, 50_000, 300_001):
+            assert lib.arb_selftest_host_sort(n, threads, 7 + n) == 0, (threads, n)
