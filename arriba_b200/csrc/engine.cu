@@ -26,8 +26,15 @@ engine::engine(): device(0), table_n(0), table_k(0), has_contigs(false), has_ann
 	mismap_table_slots = 4096; if (const char* s = getenv("ARB_MISMAP_TABLE")) mismap_table_slots = (u32) std::max(1, atoi(s)); // continuation registry: slots provisioned per cooperative item (the table is shared, 2^20..2^25 slots)
 	mismap_min_blocks = 4; if (const char* s = getenv("ARB_MISMAP_OCC")) mismap_min_blocks = atoi(s); // resident 256-thread blocks per SM the re-alignment kernels are compiled for
 	if (const char* s = getenv("ARB_MISMAP_TASK_LANES")) mismap_task_lanes = (u32) std::max(1, atoi(s));
+	ex.scratch = &scratch;
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
+#endif
+}
+
+engine::~engine() { // arb_ctx_destroy has made the context's device current; buffers go back to that device's pool after the stream has drained
+#ifdef ARB_DEVICE_BUILD
+	if (ex.stream) { cudaStreamSynchronize(ex.stream); cudaStreamDestroy(ex.stream); ex.stream = 0; }
 #endif
 }
 

@@ -79,6 +79,7 @@ struct cand_store {
 
 class engine {
 public:
+	scratch_set scratch; // scan / radix-sort scratch of this context (its device, its stream)
 	exec_ctx ex;
 	std::string last_error;
 	arb_params params;
@@ -92,6 +93,7 @@ public:
 	arb_timings timings;
 
 	engine();
+	~engine();
 	void set_contigs(const arb_contigs& c);
 	void set_annotation(const arb_annotation& a);
 	void set_params(const arb_params& p) { params = p; }

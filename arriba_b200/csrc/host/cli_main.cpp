@@ -1,6 +1,6 @@
 // cli_main.cpp -- the `arriba` command line of arriba-b200: same option letters, defaults and error texts as the reference
 // (options.cpp:270-485, usage options.cpp:109-268), driving the pipeline through the public C ABI only.
-// Not supported (fail loudly): -c Chimeric.out.sam, -d structural variants, -b/-k/-t/-p database files, -G, -I, viral heuristics -T/-C.
+// Not supported (fail loudly): -c Chimeric.out.sam, -d structural variants, -b/-k/-t/-p database files, -G, -I, -D.
 #include <getopt.h>
 #include <unistd.h>
 #include <sys/resource.h>
@@ -63,7 +63,7 @@ int main(int argc, char** argv) {
 			case 'o': out = optarg; break;
 			case 'O': discarded = optarg; break;
 			case 'b': blacklist = optarg; break;
-			case 'c': case 'd': case 't': case 'p': case 'k': case 'G': case 'I': case 'T': case 'C': case 'D':
+			case 'c': case 'd': case 't': case 'p': case 'k': case 'G': case 'I': case 'D':
 				crash(true, "option " + opt + " is not supported by arriba-b200 (see DESIGN.md, out of scope)"); break;
 			case 's': { const std::string m = optarg; o.strandedness = m == "auto" ? 3 : m == "yes" ? 1 : m == "no" ? 0 : m == "reverse" ? 2 : -1; crash(o.strandedness < 0, "invalid type of strandedness: " + m); break; }
 			case 'i': interesting = optarg; std::replace(interesting.begin(), interesting.end(), ',', ' '); break;
@@ -91,6 +91,8 @@ int main(int argc, char** argv) {
 			case 'l': crash(!int_in(optarg, 1, INT_MAX, iv), "argument to " + opt + " must be an integer greater than 0"); o.params.max_itd_length = (uint32_t) iv; break;
 			case 'z': crash(!float_in(optarg, 0, 1, o.min_itd_allele_fraction), "argument to " + opt + " must be between 0 and 1"); break;
 			case 'Z': crash(!int_in(optarg, 1, INT_MAX, iv), "argument to " + opt + " must be an integer greater than 0"); o.min_itd_support = (uint32_t) iv; break;
+			case 'T': crash(!int_in(optarg, 1, INT_MAX, iv), "invalid argument to " + opt); o.top_viral_contigs = (uint32_t) iv; break; // options.cpp:432
+			case 'C': crash(!float_in(optarg, 0, 1, o.viral_contig_min_covered_fraction), "argument to " + opt + " must be between 0 and 1"); break; // options.cpp:435
 			case '@': crash(!int_in(optarg, 1, INT_MAX, iv), "argument to " + opt + " must be an integer greater than 0"); o.threads = (int32_t) iv; threads_given = true; break;
 			case 'u': o.params.external_duplicate_marking = 1; break;
 			case 'X': o.print_extra_info_for_discarded_fusions = 1; break;

@@ -27,6 +27,7 @@ void arb_default_run_options(arb_run_options* o) {
 	o->strandedness = 3; o->fragment_length = 200; o->threads = 1; o->device = 0;
 	o->min_support = 2; o->min_anchor_length = 23; o->min_spliced_events = 4; o->high_expression_quantile = 0.998f; o->exonic_fraction = 0.33f;
 	o->min_itd_allele_fraction = 0.07f; o->min_itd_support = 10; o->print_extra_info_for_discarded_fusions = 0; o->echo_progress = 0;
+	o->top_viral_contigs = 5; o->viral_contig_min_covered_fraction = 0.05f;
 }
 
 // Dozens of host threads allocate and free at the same time (record parsing, annotation, row formatting). glibc gives every thread its own arena, but arenas
@@ -56,6 +57,7 @@ int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
 		r.min_support = o->min_support; r.min_anchor_length = o->min_anchor_length; r.min_spliced_events = o->min_spliced_events; r.high_expression_quantile = o->high_expression_quantile;
 		r.exonic_fraction = o->exonic_fraction; r.min_itd_allele_fraction = o->min_itd_allele_fraction; r.min_itd_support = o->min_itd_support;
 		r.print_extra_info_for_discarded_fusions = o->print_extra_info_for_discarded_fusions != 0; r.echo_progress = o->echo_progress != 0;
+		r.top_viral_contigs = o->top_viral_contigs; r.viral_contig_min_covered_fraction = o->viral_contig_min_covered_fraction;
 		r.params = o->params; r.strandedness = o->strandedness; r.fragment_length = o->fragment_length; r.threads = o->threads; r.device = o->device;
 		*out = x;
 	} catch (const std::exception& e) { g_pipeline_create_error = e.what(); return 1; }

@@ -13,7 +13,7 @@ static double now_s() { return std::chrono::duration<double>(std::chrono::steady
 
 run_options::run_options(): interesting_contigs("1 2 3 4 5 6 7 8 9 10 11 12 13 14 15 16 17 18 19 20 21 22 X Y AC_* NC_*"), viral_contigs("AC_* NC_*"),
 	strandedness(3), fragment_length(200), threads(1), device(0), print_extra_info_for_discarded_fusions(false), min_support(2), min_anchor_length(23), min_spliced_events(4), min_itd_support(10),
-	high_expression_quantile(0.998f), exonic_fraction(0.33f), min_itd_allele_fraction(0.07f), echo_progress(false) { arb_default_params(&params); }
+	high_expression_quantile(0.998f), exonic_fraction(0.33f), min_itd_allele_fraction(0.07f), echo_progress(false), top_viral_contigs(5), viral_contig_min_covered_fraction(0.05f) { arb_default_params(&params); }
 
 void pipeline::say(const std::string& line) {
 	log += line; log += "\n";
@@ -70,6 +70,7 @@ void pipeline::annotate() {
 	}
 	if (strandedness != 0) assign_strands(*this, strandedness);
 	annotate_fragments(*this);
+	viral_contig_decisions(*this); // per-contig verdicts of the two viral heuristics; no-op without viral contigs
 	t_annotate = now_s() - t0;
 }
 

@@ -33,6 +33,7 @@ struct run_options { // options_t (options.hpp:25-69) restricted to what this im
 	int device;
 	bool print_extra_info_for_discarded_fusions; // -X
 	int min_support; unsigned min_anchor_length, min_spliced_events, min_itd_support; float high_expression_quantile, exonic_fraction, min_itd_allele_fraction; bool echo_progress;
+	unsigned top_viral_contigs; float viral_contig_min_covered_fraction; // -T 5, -C 0.05
 	run_options();
 };
 
@@ -92,6 +93,7 @@ extern const char* const FILTER_NAMES[38];
 int detect_strandedness(pipeline& p);
 void assign_strands(pipeline& p, int strandedness);
 void annotate_fragments(pipeline& p);
+void viral_contig_decisions(pipeline& p); // viral.cpp
 bool estimate_fragment_length(pipeline& p, const u8* early, float& gap_mean, float& gap_stddev, float& read_length_mean);
 
 }} // namespace

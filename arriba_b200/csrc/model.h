@@ -67,7 +67,8 @@ struct annot_view {
 	const char* assembly;    // upper-cased reference bases, 1 byte per base
 	const u32* assembly4;    // the same bases as nt16 codes, 8 per word (first base in the top nibble), same base offsets; 0 if a character outside the nt16 alphabet occurs
 };
-enum { GF_DUMMY = 1, GF_CODING = 2, EF_HAS_PREV = 1, EF_HAS_NEXT = 2, CF_INTERESTING = 1, CF_VIRAL = 2 };
+enum { GF_DUMMY = 1, GF_CODING = 2, EF_HAS_PREV = 1, EF_HAS_NEXT = 2, CF_INTERESTING = 1, CF_VIRAL = 2,
+       CF_VIRAL_LOW_EXPRESSION = 4, CF_VIRAL_FOCAL_COVERAGE = 8 }; // per-sample verdicts of the two viral-contig heuristics (host/viral.cpp)
 
 enum { UPSTREAM = 1, DOWNSTREAM = 0 }; // direction_t (common.hpp:229-231)
 

@@ -110,10 +110,9 @@ static void scan_level(const exec_ctx& ex, const u32* in, u32* out, u32 n, u32* 
 	ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels;
 }
 
-static dbuf<u32>& scan_scratch() { static dbuf<u32> s; return s; }
-
 void exclusive_scan_u32(const exec_ctx& ex, const u32* in, u32* out, u32 n) {
-	dbuf<u32>& scratch = scan_scratch();
+	if (!ex.scratch) throw arb_error("exclusive_scan_u32: the execution context has no scratch set");
+	dbuf<u32>& scratch = ex.scratch->scan;
 	scratch.ensure((size_t) n / SCAN_TILE * 2 + 8192);
 	scan_level(ex, in, out, n, scratch.ptr(), out + n);
 }
@@ -180,12 +179,11 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u32* __restr
 	}
 }
 
-static dbuf<u32>& radix_scratch() { static dbuf<u32> s; return s; }
-
 void radix_sort_pairs_u32(const exec_ctx& ex, u32* keys, u32* vals, u32* keys_tmp, u32* vals_tmp, u32 n, u32 bits) {
 	if (n <= 1 || bits == 0) return;
 	const u32 nblocks = (n + RS_TILE - 1) / RS_TILE;
-	dbuf<u32>& hist = radix_scratch();
+	if (!ex.scratch) throw arb_error("radix_sort_pairs_u32: the execution context has no scratch set");
+	dbuf<u32>& hist = ex.scratch->radix;
 	hist.ensure((size_t) 256 * nblocks + 1);
 	u32 *ki = keys, *vi = vals, *ko = keys_tmp, *vo = vals_tmp;
 	for (u32 shift = 0; shift < bits; shift += 8) {

@@ -13,7 +13,7 @@
 #include <string>
 #include <vector>
 #include <mutex>
-#include <algorithm>
+#include <atomic>
 #include <algorithm>
 
 #ifdef ARB_DEVICE_BUILD
@@ -29,15 +29,18 @@ struct arb_error: public std::runtime_error { explicit arb_error(const std::stri
 #endif
 
 // launch statistics (bench.py reports gpu_launches from here)
-struct launch_stats { u64 kernels; };
-inline launch_stats& stats() { static launch_stats s = {0}; return s; }
+struct launch_stats { std::atomic<u64> kernels; launch_stats(): kernels(0) {} }; // contexts on several threads count into the same total
+inline launch_stats& stats() { static launch_stats s; return s; }
 
+struct scratch_set; // per-context scratch of the scan and the radix sort (defined after dbuf)
 struct exec_ctx {
+	scratch_set* scratch; // owned by the context (engine): a context is bound to one device and one stream, so is its scratch
 #ifdef ARB_DEVICE_BUILD
 	cudaStream_t stream;
-	exec_ctx(): stream(0) {}
+	exec_ctx(): scratch(0), stream(0) {}
 	void sync() const { ARB_CUDA_CHECK(cudaStreamSynchronize(stream)); }
 #else
+	exec_ctx(): scratch(0) {}
 	void sync() const {}
 #endif
 };
@@ -148,6 +151,8 @@ public:
 	}
 	std::vector<T> to_host(const exec_ctx& ex, size_t n) const { std::vector<T> v(n); download(ex, v.data(), n); return v; }
 };
+
+struct scratch_set { dbuf<u32> scan, radix; };
 
 // ------------------------------------------------------------------------------------------- for_each
 #ifdef ARB_DEVICE_BUILD

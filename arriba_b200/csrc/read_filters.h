@@ -5,6 +5,7 @@
 // Behavioural contract per rule (reference location):
 //   duplicates key ............... filter_duplicates.cpp:26-47
 //   uninteresting / viral contigs  filter_uninteresting_contigs.cpp:13-24, filter_viral_contigs.cpp:13-23
+//   top_expressed / low_coverage viral contigs  per-contig verdicts from host/viral.cpp, per-fragment rule here
 //   read_through ................. filter_proximal_read_through.cpp:15-42
 //   inconsistently_clipped ....... filter_inconsistently_clipped.cpp:13-19
 //   homopolymer .................. filter_homopolymer.cpp:7-14,22-54
@@ -248,6 +249,14 @@ ARB_HD u8 classify_head(const read_filter_params& p, const frag_view& f, const a
 		bool all_viral = true;
 		for (u32 s = 0; s < n; ++s) if (!(an.contig_flags[f.contig[f.idx(i, s)]] & CF_VIRAL)) { all_viral = false; break; }
 		if (all_viral) label = F_viral_contigs;
+	}
+	// the two heuristics on viral contigs decide per contig (host/viral.cpp); a fragment goes when any of its mates lies on such a contig
+	// (filter_top_expressed_viral_contigs.cpp:133-152, filter_low_coverage_viral_contigs.cpp:32-50)
+	if (label == F_none && p.enabled(F_top_expressed_viral_contigs)) {
+		for (u32 s = 0; s < n; ++s) { const u8 cf = an.contig_flags[f.contig[f.idx(i, s)]]; if ((cf & CF_VIRAL) && (cf & CF_VIRAL_LOW_EXPRESSION)) { label = F_top_expressed_viral_contigs; break; } }
+	}
+	if (label == F_none && p.enabled(F_low_coverage_viral_contigs)) {
+		for (u32 s = 0; s < n; ++s) { const u8 cf = an.contig_flags[f.contig[f.idx(i, s)]]; if ((cf & CF_VIRAL) && (cf & CF_VIRAL_FOCAL_COVERAGE)) { label = F_low_coverage_viral_contigs; break; } }
 	}
 	early = label;
 

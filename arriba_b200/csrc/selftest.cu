@@ -13,7 +13,7 @@ uint64_t arb_selftest_pool_size_class(uint64_t bytes) { return pool_size_class((
 
 int arb_selftest_scan(const uint32_t* in, uint32_t* out /* n+1 */, uint32_t n) {
 	try {
-		exec_ctx ex;
+		scratch_set scratch; exec_ctx ex; ex.scratch = &scratch;
 		dbuf<u32> d((size_t) n + 1);
 		d.upload(ex, in, n);
 		exclusive_scan_u32(ex, d.ptr(), d.ptr(), n);
@@ -24,7 +24,7 @@ int arb_selftest_scan(const uint32_t* in, uint32_t* out /* n+1 */, uint32_t n) {
 
 int arb_selftest_sort(uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t bits) {
 	try {
-		exec_ctx ex;
+		scratch_set scratch; exec_ctx ex; ex.scratch = &scratch;
 		dbuf<u32> k(n), v(n), kt(n), vt(n);
 		k.upload(ex, keys, n); v.upload(ex, vals, n);
 		radix_sort_pairs_u32(ex, k.ptr(), v.ptr(), kt.ptr(), vt.ptr(), n, bits);
@@ -35,7 +35,7 @@ int arb_selftest_sort(uint32_t* keys, uint32_t* vals, uint32_t n, uint32_t bits)
 
 int arb_selftest_group(const uint32_t* keys, uint32_t* first, uint32_t n) {
 	try {
-		exec_ctx ex;
+		scratch_set scratch; exec_ctx ex; ex.scratch = &scratch;
 		dbuf<u32> k(n), slot(n), f(n);
 		k.upload(ex, keys, n);
 		hash_index t;

@@ -267,7 +267,8 @@ class RunOptions(C.Structure):
                 ("params", Params), ("strandedness", C.c_int32), ("fragment_length", C.c_uint32), ("threads", C.c_int32), ("device", C.c_int32),
                 ("min_support", C.c_int32), ("min_anchor_length", C.c_uint32), ("min_spliced_events", C.c_uint32), ("high_expression_quantile", C.c_float),
                 ("exonic_fraction", C.c_float), ("min_itd_allele_fraction", C.c_float), ("min_itd_support", C.c_uint32),
-                ("print_extra_info_for_discarded_fusions", C.c_int32), ("echo_progress", C.c_int32)]
+                ("print_extra_info_for_discarded_fusions", C.c_int32), ("echo_progress", C.c_int32),
+                ("top_viral_contigs", C.c_uint32), ("viral_contig_min_covered_fraction", C.c_float)]
 
 
 class RunStats(C.Structure):

@@ -1,25 +1,32 @@
 #!/usr/bin/env python
-"""bench.py -- chimeric fragments per second of the hot path (BAM ingest -> read-level cascade -> candidate generation ...).
+"""bench.py -- chimeric fragments per second of the hot path, end to end (BAM ingest -> fusions.tsv + fusions.discarded.tsv).
 
-One "step" = one pass of the whole path over one synthetic chimeric BAM (BASELINE.json configs[1]: 10 M fragments, 2x101 bp,
+One "step" = one pass of the whole path over one synthetic chimeric BAM (default: BASELINE.json configs[1], 10 M fragments, 2x101 bp,
 50 k breakpoints; the genome is a synthetic stand-in for hg38 at 1:10 scale because no reference genome exists offline).
-  value : fragments/s of the device-resident stages, CUDA-event timed, inputs already in HBM
-  e2e   : fragments/s through the public Pipeline API from the BAM file on disk (host decode, H2D, kernels, D2H of results)
+  value / e2e   : fragments/s through the public Pipeline API, BAM file on disk -> both TSV files on disk (host decode, pinned H2D, kernels,
+                  D2H of the results, host event logic, writer) -- what the metric names
+  device_stages : fragments/s of the device-resident stages alone (CUDA events), as an explanation of the above, never the headline
+  roofline      : the time-dominant kernel of the step (and the others, under "kernels")
   --impl reference : the unmodified reference (oracle/_ref/arriba) on the host cores, bounded sample of the same world
-See DESIGN.md section "Measurement" for the definitions of the roofline numbers."""
+N > 1 (torchrun): --mode sharded (default) = ONE sample divided over the ranks (strong scaling); --mode samples = one sample per GPU (weak).
+The last line of stdout is the JSON line. See DESIGN.md section "Measurement"."""
 import argparse, json, os, subprocess, sys, time, threading, hashlib, re
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: synth parameters
+    # name: synth parameters (tools/synth.cpp)
     "cfg2_10M_2x101_50k": dict(scale=0.1, genes=20000, breakpoints=50000, fragments=10000000, read_length=101),
+    "cfg3_15M_2x151_75k": dict(scale=0.1, genes=20000, breakpoints=75000, fragments=15000000, read_length=151),
+    "cfg5_10M_mismapper": dict(scale=0.1, genes=20000, breakpoints=50000, fragments=10000000, read_length=101, extra=["--mismapper-frac", "0.3", "--paralog-frac", "0.15"]),
     "mid_1M_2x101_5k": dict(scale=0.02, genes=4000, breakpoints=5000, fragments=1000000, read_length=101),
+    "mid5_1M_mismapper": dict(scale=0.02, genes=4000, breakpoints=5000, fragments=1000000, read_length=101, extra=["--mismapper-frac", "0.3", "--paralog-frac", "0.15"]),
     "tiny_20k": dict(scale=0.001, genes=400, breakpoints=200, fragments=20000, read_length=101),
 }
 UNIT = "reads/s"   # chimeric fragments per second
 SCOPE = "ingest..fusions.tsv"  # one step = BAM ingest -> read filters -> candidates -> event filters -> fusions.tsv + discarded.tsv (reference loading excluded)
+GOLDEN_MD5 = os.path.join(ROOT, "tests", "golden", "full_size_md5.json")   # md5 of the reference's two output files per workload (tests/golden/make_full_size_md5.py)
 
 
 def world_dir(name):
@@ -35,7 +42,7 @@ def ensure_world(name, sample_breakpoints=None):
     d = world_dir(name); os.makedirs(d, exist_ok=True)
     prefix = os.path.join(d, "w")
     common = [synth, "--seed", str(0xA881BA), "--scale", str(p["scale"]), "--genes", str(p["genes"]), "--breakpoints", str(p["breakpoints"]),
-              "--fragments", str(p["fragments"]), "--read-length", str(p["read_length"])]
+              "--fragments", str(p["fragments"]), "--read-length", str(p["read_length"])] + p.get("extra", [])
     if not os.path.exists(prefix + ".done"):
         subprocess.run(common + ["--prefix", prefix], check=True, stderr=subprocess.DEVNULL)
         open(prefix + ".done", "w").write("ok")
@@ -59,7 +66,7 @@ class ClockSampler(threading.Thread):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, text=True, timeout=5).stdout
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q, "--format=csv,noheader,nounits"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 6:
                     self.samples.append(f)
@@ -85,6 +92,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def md5_of(path):
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for block in iter(lambda: f.read(1 << 24), b""):
+            h.update(block)
+    return h.hexdigest()
+
+
 def reference_run(prefix, threads):
     """Runs the unmodified reference CLI; returns (fragments, seconds over SCOPE, total seconds)."""
     from arriba_b200 import _build
@@ -98,7 +113,7 @@ def reference_run(prefix, threads):
     if r.returncode != 0:
         raise RuntimeError("reference run failed: " + r.stderr[-500:])
     n = int(re.search(r"\(total=(\d+)\)", r.stdout).group(1))
-    # time stamps of the reference's own progress lines (1 s resolution): start of BAM reading .. first line after find_fusions
+    # time stamps of the reference's own progress lines (1 s resolution): start of BAM reading .. first line after the writer
     def stamp(line):
         m = re.match(r"\[\d+-\d+-\d+T(\d+):(\d+):(\d+)\]", line)
         return int(m.group(1)) * 3600 + int(m.group(2)) * 60 + int(m.group(3))
@@ -110,6 +125,30 @@ def reference_run(prefix, threads):
     return n, scope_s, total
 
 
+# full-size run of the unmodified reference on the default workload, measured once on the development container (profiles/cfg2_full_size_parity.txt):
+# the sample above flatters the reference (its std::map / unordered_map walks get slower per fragment as the containers grow)
+REFERENCE_FULL_SIZE = {"cfg2_10M_2x101_50k": {"fragments": 11810114, "seconds": 1535.0, "value": 11810114 / 1535.0, "cores": 1, "where": "development container, profiles/cfg2_full_size_parity.txt (25 min 35 s)"}}
+
+
+class QuietStderr:
+    """The library prints the reference's per-row warnings on stderr (thousands per step on the synthetic GTF). They go to a log file; the few progress
+    lines of this script go to the real stderr."""
+    def __init__(self, path):
+        self.path = path; self.saved = None
+    def __enter__(self):
+        sys.stderr.flush()
+        self.saved = os.dup(2)
+        fd = os.open(self.path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+        os.dup2(fd, 2); os.close(fd)
+        self.real = os.fdopen(os.dup(self.saved), "w")
+        return self
+    def say(self, text):
+        self.real.write(text + "\n"); self.real.flush()
+    def __exit__(self, *a):
+        sys.stderr.flush()
+        os.dup2(self.saved, 2); os.close(self.saved); self.real.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -117,17 +156,18 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2_10M_2x101_50k", choices=sorted(WORKLOADS))
-    ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = cores / ranks)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads per rank (0 = 2 per usable CPU / ranks)")
     ap.add_argument("--sample-breakpoints", type=int, default=0, help="cpu baseline sample size in breakpoints (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sharded-extra", action="store_true", help="N>1, mode samples: skip the additional one-sample-over-all-ranks step")
-    ap.add_argument("--mode", choices=["samples", "sharded"], default="samples",
-                    help="N>1: 'samples' = one independent sample per GPU (weak scaling, no collective); 'sharded' = ONE sample partitioned by contig pair with two NCCL all-gathers (strong scaling)")
+    ap.add_argument("--no-secondary", action="store_true", help="N>1: skip the additional line of the other multi-GPU mode")
+    ap.add_argument("--mode", choices=["samples", "sharded"], default="sharded",
+                    help="N>1: 'sharded' = ONE sample divided over the ranks (strong scaling, NCCL exchanges); 'samples' = one independent sample per GPU (weak scaling, no collective)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the md5 comparison of the output files with the reference's")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    usable = cores   # CPUs the container may actually burn: the cgroup quota, where one is set (the GPU boxes show 128 CPUs and grant 16)
+    usable = cores   # CPUs the container may actually burn: the cgroup quota, where one is set (the 1-GPU boxes show 128 CPUs and grant 16)
     try:
         quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
         if quota != "max":
@@ -140,7 +180,8 @@ def main():
     metric = "chimeric reads/sec end-to-end (ingest→fusions.tsv)"   # BASELINE.json; a "read" is one chimeric fragment (read pair + supplementary), the unit the reference counts
     config = {"workload": "synthetic %s: %d fragments 2x%d bp, %d breakpoints, genome %.0f%% of hg38 size (synthetic), %d genes" %
               (args.workload, wl["fragments"], wl["read_length"], wl["breakpoints"], wl["scale"] * 100, wl["genes"]),
-              "scope": SCOPE, "value_is": "device-resident stages (CUDA events, fragment table in HBM)", "e2e_is": "BAM on disk -> both TSV files on disk through the public Pipeline API (the headline)", "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable, "sharding": "one independent BAM per rank (weak)"}
+              "scope": SCOPE, "value_is": "end to end: BAM on disk -> both TSV files on disk through the public Pipeline API, host<->device copies inside the timed region",
+              "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable}
 
     if args.impl == "reference":
         if rank != 0:
@@ -154,12 +195,12 @@ def main():
         line = {"impl": "reference", "metric": metric, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": scope_s * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
-                                 "sample": "first %d breakpoints of the workload at full depth = %d fragments; reference's own time stamps over %s (1 s resolution); decode threads -@ %d have no effect in the shim build" % (sample_bp, n, SCOPE, cores)},
+                                 "sample": "first %d breakpoints of the workload at full depth = %d fragments; reference's own time stamps over %s (1 s resolution); decode threads -@ %d have no effect in the shim build" % (sample_bp, n, SCOPE, cores),
+                                 "full_size": REFERENCE_FULL_SIZE.get(args.workload)},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
         return
 
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only (NCCL prints its version banner where NCCL_DEBUG=VERSION)
     import torch
     from arriba_b200 import lib as L, _build
     if not torch.cuda.is_available():
@@ -176,118 +217,155 @@ def main():
     if dist:
         dist.barrier()
     prefix = ensure_world(args.workload)
+    outdir = os.path.join(world_dir(args.workload), "out_rank%d" % rank); os.makedirs(outdir, exist_ok=True)
+    out_tsv, out_disc = os.path.join(outdir, "fusions.tsv"), os.path.join(outdir, "fusions.discarded.tsv")
+    quiet = QuietStderr(os.path.join(outdir, "library_stderr.log")); quiet.__enter__()
+    say = (lambda s: quiet.say(s)) if rank == 0 else (lambda s: None)
 
-    def one_step(sharded=False):
-        """ingest .. fusions.tsv through the public Pipeline API; returns (fragments, e2e seconds, device ms, stats, timings, d2h bytes)"""
-        outdir = os.path.join(world_dir(args.workload), "out_rank%d" % rank); os.makedirs(outdir, exist_ok=True)
-        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank,
-                       output=os.path.join(outdir, "fusions.tsv"), discarded=os.path.join(outdir, "fusions.discarded.tsv"))
+    def one_step(sharded):
+        """ingest .. fusions.tsv through the public Pipeline API; returns a dict of what the step measured"""
+        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank, output=out_tsv, discarded=out_disc)
         p.step(L.STEP_LOAD_REFERENCE)          # genome + annotation: loaded once per run in a real deployment, outside the timed region
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
         if sharded:
             from arriba_b200 import sharded as S
-            dist.barrier(); torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            S.run_sharded(p, rank, world, reference_loaded=True)   # two NCCL all-gathers inside; rank 0 writes the files
-            e2e_s = time.perf_counter() - t0
+            S.run_sharded(p, rank, world, reference_loaded=True)   # NCCL exchanges inside; rank 0 writes the files
         else:
-            t0 = time.perf_counter()
             for s in range(L.STEP_INGEST, L.STEP_COUNT):
                 p.step(s)
             p.events(len(L.EV_NAMES) - 1)          # event-level chain incl. the device stages and the D2H of the candidate table
             p.write_output()
-            e2e_s = time.perf_counter() - t0
+        e2e_s = time.perf_counter() - t0
         ctx = p.context()
         st = p.stats(); tm = ctx.timings()
         n_cand = int(st.n_candidates)
         d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
         dev_ms = tm.read_filters_ms + tm.find_fusions_ms + tm.merge_adjacent_ms + tm.evalue_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms
-        res = (int(st.n_fragments), e2e_s, dev_ms, st, tm, d2h, n_cand)
-        if rank == 0:   # progress on stderr: a run that is cut off still says where the time went
-            ev = {n: round(st.event_seconds[i], 2) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.5}
-            print("[bench] step: e2e %.2f s, device %.1f ms, ingest %.2f, annotate %.2f, upload %.2f, output %.2f, events >= 0.5 s: %s" %
-                  (e2e_s, dev_ms, st.seconds[L.STEP_INGEST], st.seconds[L.STEP_ANNOTATE], st.seconds[L.STEP_UPLOAD], st.output_seconds, ev), file=sys.stderr, flush=True)
+        ev = {n: round(st.event_seconds[i], 2) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.2}
+        say("[bench] step: e2e %.2f s, device %.1f ms, ingest %.2f, annotate %.2f, upload %.2f, output %.2f, events >= 0.2 s: %s" %
+            (e2e_s, dev_ms, st.seconds[L.STEP_INGEST], st.seconds[L.STEP_ANNOTATE], st.seconds[L.STEP_UPLOAD], st.output_seconds, ev))
         p.close()
-        return res
+        return {"n": int(st.n_fragments), "e2e_s": e2e_s, "dev_ms": dev_ms, "st": st, "tm": tm, "d2h": d2h, "n_cand": n_cand}
+
+    def timed(sharded, warmup, steps):
+        for _ in range(warmup):
+            one_step(sharded)
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_begin = time.perf_counter()
+        results = [one_step(sharded) for _ in range(steps)]
+        torch.cuda.synchronize()
+        if dist:
+            dist.barrier()
+        wall = time.perf_counter() - t_begin
+        e2e_s = sum(r["e2e_s"] for r in results) / len(results)
+        dev_ms = sum(r["dev_ms"] for r in results) / len(results)
+        if dist:   # a step ends when its slowest rank ends
+            t = torch.tensor([e2e_s, dev_ms, wall], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s, dev_ms, wall = [float(x) for x in t.tolist()]
+        return results, e2e_s, dev_ms, wall
 
     sharded = args.mode == "sharded" and world > 1
-    if sharded:
-        config["sharding"] = "ONE sample, fragments partitioned by contig pair over the ranks (LPT), two NCCL all-gathers (labels, candidates); every rank decodes the BAM"
-    launches0 = L.load().arb_kernel_launches()
+    config["sharding"] = ("ONE sample divided over the ranks (strong scaling): see DESIGN.md section 7" if sharded else
+                          "one independent BAM per rank (weak scaling, no collective on the data path)" if world > 1 else "single GPU")
+    sampler = ClockSampler(local_rank); sampler.start()
+    launches1 = None
+    lib = L.load()
     for _ in range(args.warmup):
         one_step(sharded)
-    if dist:
-        dist.barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank); sampler.start()
-    launches1 = L.load().arb_kernel_launches()
-    t_begin = time.perf_counter()
-    results = [one_step(sharded) for _ in range(args.steps)]
-    torch.cuda.synchronize()
-    if dist:
-        dist.barrier()
-    wall = time.perf_counter() - t_begin
-    extra_sharded = None
-    slowest = torch.tensor([max(r[1] for r in results)], device="cuda", dtype=torch.float64)
-    if dist:
-        dist.all_reduce(slowest, op=dist.ReduceOp.MAX)
-    if dist and not sharded and not args.no_sharded_extra and float(slowest[0]) < 60.0:   # the same sample once more as ONE job over all ranks: exercises the two all-gathers (skipped when a step takes more than a minute)
-        r = one_step(True)
-        t = torch.tensor([r[1]], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        extra_sharded = {"e2e_seconds": float(t[0]), "e2e_value": r[0] / float(t[0]), "unit": UNIT, "scaling": "strong",
-                         "note": "one sample partitioned by contig pair over all ranks, 2 NCCL all-gathers; host decode is replicated, so this mode buys device memory and device time, not host time"}
+    launches1 = lib.arb_kernel_launches()
+    results, e2e_s, dev_ms, wall = timed(sharded, 0, args.steps)
+    launches = lib.arb_kernel_launches() - launches1
     sampler.stop_flag = True; sampler.join(timeout=2)
-    launches = L.load().arb_kernel_launches() - launches1
-    n_frag = results[0][0]
-    dev_ms = sum(r[2] for r in results) / len(results)
-    e2e_s = sum(r[1] for r in results) / len(results)
-    cls_ms = sum(r[4].cascade_head_ms + r[4].cascade_sequences_ms for r in results) / len(results)
-    if dist:
-        t = torch.tensor([dev_ms, e2e_s, cls_ms, wall], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, e2e_s, cls_ms, wall = [float(x) for x in t.tolist()]
+
+    # parity of the very files the timed steps wrote: md5 against the unmodified reference's output for this workload (committed; made on the CPU box)
+    parity = {"checked": False}
+    if rank == 0 and not args.no_parity:
+        try:
+            golden = json.load(open(GOLDEN_MD5)).get(args.workload)
+        except Exception:
+            golden = None
+        if golden:
+            got = {"fusions.tsv": md5_of(out_tsv), "fusions.discarded.tsv": md5_of(out_disc)}
+            parity = {"checked": True, "ok": got == {k: golden[k] for k in got}, "md5": got, "reference_md5": {k: golden[k] for k in got}, "source": golden.get("source")}
+        else:
+            parity = {"checked": False, "reason": "no committed reference md5 for this workload"}
+
+    secondary = None
+    if dist and not args.no_secondary and e2e_s < 40.0:   # the other multi-GPU mode, a few steps
+        other = not sharded
+        r2, e2, d2, _ = timed(other, 1, 2)
+        jobs2 = 1 if other else world
+        secondary = {"mode": "sharded" if other else "samples", "scaling": "strong" if other else "weak", "value": r2[0]["n"] * jobs2 / e2, "unit": UNIT, "seconds_per_step": e2, "steps": 2, "warmup": 1,
+                     "note": "ONE sample divided over all ranks" if other else "one independent sample per GPU, no collective on the data path"}
+    quiet.__exit__()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
         return
-    st, tm = results[-1][3], results[-1][4]
+    n_frag = results[0]["n"]
+    st, tm = results[-1]["st"], results[-1]["tm"]
     peak, peak_src = measured_peak()
-    cascade_bytes = int(tm.cascade_algorithmic_bytes[0]) + int(tm.cascade_algorithmic_bytes[1])   # of the fragments the two launches actually saw (a shard, in sharded mode)
-    achieved = cascade_bytes / (cls_ms * 1e-3) / 1e9
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of the two cascade launches on this workload, from the committed `ncu --set full` capture
-    try:
-        t = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")))
-        traffic = t.get(args.workload, {}).get("cascade_dram_bytes_per_step")
-    except Exception:
-        pass
-    jobs = 1 if sharded else world
-    line = {"metric": metric, "value": n_frag * jobs / (dev_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
+    jobs = 1 if (sharded or world == 1) else world
+
+    def kernel_entry(name, ms, alg_bytes, unit_note, traffic_key):
+        traffic = None
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            traffic = t.get(args.workload, {}).get(traffic_key)
+        except Exception:
+            pass
+        ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": ms, "algorithmic_bytes_are": unit_note}
+
+    mean = lambda f: sum(f(r["tm"]) for r in results) / len(results)
+    kernels = [
+        kernel_entry("cascade_head (all coordinate / CIGAR / gene-set rules, one launch)", mean(lambda t: t.cascade_head_ms), int(tm.cascade_algorithmic_bytes[0]),
+                     "SURVEY 8(d) column budget of the fragments the launch saw", "cascade_head_dram_bytes"),
+        kernel_entry("cascade_sequences (mismatches + low entropy, one launch)", mean(lambda t: t.cascade_sequences_ms), int(tm.cascade_algorithmic_bytes[1]),
+                     "SURVEY 8(d): sequences 3 bit/base + gathered reference 2 bit/base + CIGARs + 11 B/alignment of the queued fragments", "cascade_sequences_dram_bytes"),
+        kernel_entry("mismappers pass 1 (re-alignment, one launch)", mean(lambda t: t.mismappers_pass1_ms), int(getattr(tm, "mismapper_algorithmic_bytes", 0)),
+                     "SURVEY 8(d): per re-aligned sequence 3l/8 + 8(l-8) + 4*hits + l/2", "mismappers_pass1_dram_bytes"),
+    ]
+    dominant = max(kernels, key=lambda k: k["kernel_ms"])
+    device_ms = {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
+                 "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
+                 "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms}
+    roofline = dict(dominant)
+    roofline.update({"kernels": kernels, "device_ms": device_ms,
+                     "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "mismapper_tasks": int(tm.mismapper_tasks), "mismapper_rounds": int(tm.mismapper_rounds),
+                     "mismapper_registry": {"slots": int(tm.mismapper_table_slots), "overflow": int(tm.mismapper_overflow)}, "kmer_positions": int(tm.kmer_positions), "cascade_queued": int(tm.cascade_queued)})
+    line = {"metric": metric, "value": n_frag * jobs / e2e_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": e2e_s * 1e3, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": n_frag * jobs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1][5]),
+            "e2e": {"value": n_frag * jobs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1]["d2h"]),
                     "seconds_per_step": e2e_s, "host_seconds": {n: round(st.seconds[i], 3) for i, n in enumerate(L.STEP_NAMES) if i > 0},
                     "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "read-level cascade: k_for_each<cascade_head_fn> + k_for_each_scratch<cascade_sequences_fn>", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": cascade_bytes, "kernel_ms": cls_ms,
-                         "cascade": {"head_ms": tm.cascade_head_ms, "sequences_ms": tm.cascade_sequences_ms, "queued": int(tm.cascade_queued),
-                                     "head_bytes": int(tm.cascade_algorithmic_bytes[0]), "sequences_bytes": int(tm.cascade_algorithmic_bytes[1])},
-                         "device_ms": {"duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
-                                       "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
-                                       "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms},
-                         "mismapper_items": int(tm.mismapper_items), "mismapper_heavy_items": int(tm.mismapper_heavy_items), "mismapper_tasks": int(tm.mismapper_tasks), "mismapper_rounds": int(tm.mismapper_rounds), "mismapper_registry": {"slots": int(tm.mismapper_table_slots), "overflow": int(tm.mismapper_overflow)}, "kmer_positions": int(tm.kmer_positions)},
-            "candidates": int(results[-1][6]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
-    if extra_sharded:
-        line["sharded_single_sample"] = extra_sharded
+            "device_stages": {"value": n_frag * jobs / (dev_ms * 1e-3), "unit": UNIT, "ms_per_step": dev_ms, "is": "sum of the CUDA-event times of the device stages, fragment table resident in HBM (not the headline)"},
+            "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "parity_md5_ok": parity.get("ok"),
+            "candidates": int(results[-1]["n_cand"]), "unfiltered_candidates": int(st.n_unfiltered_candidates), "fragments_per_step": n_frag, "wall_seconds_timed_region": wall}
+    if secondary:
+        line["secondary_mode"] = secondary
     if not args.no_cpu_baseline and world == 1:   # the CPU reference beside the GPU number: rank 0 at N=1 only
         sp = ensure_world(args.workload, sample_bp)
         n, scope_s, total = reference_run(sp, cores)
         line["cpu_baseline"] = {"value": n / scope_s, "unit": UNIT, "cores": 1, "kind": "reference",
                                 "sample": "first %d breakpoints of the workload at full depth = %d fragments; unmodified reference (oracle/_ref/arriba), its own time stamps over %s" % (sample_bp, n, SCOPE),
-                                "whole_run_seconds": total, "host_cores_available": cores}
-    print(json.dumps(line))
+                                "whole_run_seconds": total, "host_cores_available": cores, "full_size": REFERENCE_FULL_SIZE.get(args.workload)}
     if dist:
         dist.destroy_process_group()
+    sys.stderr.flush()
+    print(json.dumps(line), flush=True)
+    if parity.get("checked") and not parity.get("ok"):
+        sys.stderr.write("bench.py: output files differ from the reference's (md5), see \"parity\" in the line above\n")
+        sys.exit(1)
 
 
 if __name__ == "__main__":

@@ -226,6 +226,8 @@ typedef struct arb_run_options {
 	uint32_t min_itd_support;        /* -Z 10 */
 	int32_t print_extra_info_for_discarded_fusions; /* -X */
 	int32_t echo_progress;           /* print the reference's progress lines to stdout while running */
+	uint32_t top_viral_contigs;      /* -T 5 */
+	float viral_contig_min_covered_fraction; /* -C 0.05 */
 } arb_run_options;
 void arb_default_run_options(arb_run_options* o);
 

@@ -20,9 +20,7 @@ def hostsim_lib():
 @pytest.fixture(scope="session")
 def cuda_lib():
     from arriba_b200 import _build
-    if not os.path.exists(_build.PRODUCT_LIB):
-        _build.build_product()
-    return _build.PRODUCT_LIB
+    return _build.build_product()   # no-op when the library is newer than every source
 
 
 @pytest.fixture(scope="session")

@@ -14,6 +14,10 @@ OPTION_SETS = [
     ("-E", "0.05", "-S", "3"), ("-m", "0.5", "-L", "0.1"), ("-H", "4", "-R", "5000"), ("-A", "30", "-M", "2"),
     ("-K", "0.3", "-V", "0.05"), ("-F", "300", "-U", "50"), ("-Q", "0.9", "-e", "0.5"), ("-l", "50", "-z", "0.2", "-Z", "5"),
     ("-i", "1,2,3,4,5,X"),
+    # viral contigs: the two per-contig heuristics (top expressed, focal coverage) and the "only viral" rule; the synthetic worlds have no viral
+    # genomes, so ordinary chromosomes are declared viral
+    ("-v", "21,22"), ("-v", "19,20,21,22,X,Y", "-T", "2"), ("-v", "1,2,3,21,22", "-C", "0.5", "-T", "1"), ("-v", "20,21,22", "-f", "blacklist,top_expressed_viral_contigs"),
+    ("-v", "20,21,22", "-f", "blacklist,low_coverage_viral_contigs"),
 ]
 
 

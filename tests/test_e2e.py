@@ -47,13 +47,16 @@ def test_e2e_cuda(worlds, cuda_lib, tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_cuda(worlds, tmp_path):
-    """The drop-in executable: same command line as the reference (run_arriba.sh:38-48), byte-identical files."""
+@pytest.mark.parametrize("extra", [(), ("-v", "19,20,21,22,X,Y", "-T", "2")], ids=["default", "viral_contigs"])
+def test_cli_cuda(worlds, tmp_path, extra):
+    """The drop-in executable: same command line as the reference (run_arriba.sh:38-48), byte-identical files; with contigs declared viral the two
+    per-contig heuristics and their device rules (filter_top_expressed_viral_contigs, filter_low_coverage_viral_contigs) take part."""
     import subprocess
     from arriba_b200 import _build
-    w = worlds.get("small")
+    args = ("-f", "blacklist") + tuple(extra)
+    w = worlds.get("small", oracle_args=args)
     out = str(tmp_path / "fusions.tsv"); disc = str(tmp_path / "fusions.discarded.tsv")
-    r = subprocess.run([_build.build_cli(), "-x", w.prefix + ".bam", "-g", w.prefix + ".gtf", "-a", w.prefix + ".fa", "-o", out, "-O", disc, "-f", "blacklist", "-@", "4"],
+    r = subprocess.run([_build.build_cli(), "-x", w.prefix + ".bam", "-g", w.prefix + ".gtf", "-a", w.prefix + ".fa", "-o", out, "-O", disc, "-@", "4"] + list(args),
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     assert open(out, "rb").read() == open(os.path.join(w.outdir, "fusions.tsv"), "rb").read()
