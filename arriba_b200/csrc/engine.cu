@@ -14,7 +14,7 @@ void default_params(arb_params& p) { // options.cpp:71-107
 	p.max_mismapper_fraction = 0.8f; p.max_homolog_identity = 0.3f;
 }
 
-engine::engine(): device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
+engine::engine(): cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
@@ -128,6 +128,15 @@ void engine::push_chunk(const arb_soa_chunk& c) {
 	u32 max_len = 0;
 	for (size_t k = 0; k < 2 * (size_t) n; ++k) if (c.seq_len[k] > max_len) max_len = c.seq_len[k];
 	frags.max_seq_len = max_len;
+	// canonical pool layout (what ingest writes): sequences in fragment order, slot 0 then slot 1, back to back in 16-byte units; the sequence kernel then
+	// stages a tile of fragments with one bulk copy (k_cascade_sequences). Any other layout is read in place.
+	frags.n_seq_bytes = c.n_seq_bytes;
+	{
+		bool canonical = n > 0 && c.n_seq_bytes % 16 == 0; u64 at = n ? c.seq_off[0] : 0;
+		for (size_t i = 0; i < n && canonical; ++i)
+			for (u32 s = 0; s < 2; ++s) { const size_t a = s * (size_t) n + i; if (c.seq_off[a] != at) { canonical = false; break; } at += ((c.seq_len[a] + 1) / 2 + 15) / 16; }
+		frags.canonical_seq_layout = canonical && at * 16 <= c.n_seq_bytes;
+	}
 	timings.h2d_ms = t_h2d.stop();
 	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 1 + 4 + 2 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes + c.n_genes * 4;
 	// Column budget of SURVEY.md section 8(d): every column read once at its compact width -- 11 B per alignment {contig u16, start, end, flags u8}, CIGAR ops and
@@ -192,18 +201,80 @@ struct dup_external_fn {
 
 // ------------------------------------------------------------------------------------------- the cascade, two kernels
 struct cascade_head_fn {
-	read_filter_params p; frag_view f; annot_view an; u8* early; u32* queue; u32* n_queued;
+	read_filter_params p; frag_view f; annot_view an; u8* early; u8* needs_sequences; u32* n_queued;
 	ARB_HD void operator()(u32 i) const {
 		u8 e; bool more;
 		const u8 label = classify_head(p, f, an, i, e, more);
 		f.filter[i] = label; early[i] = e;
-		if (more) queue[append_slot(n_queued)] = i;
+		needs_sequences[i] = more;
+		if (more) append_slot(n_queued); // one atomic per warp: how many fragments the sequence rules will look at
 	}
 };
-struct cascade_sequences_fn {
-	read_filter_params p; frag_view f; annot_view an; const u32* queue;
-	ARB_HD void operator()(u32 j, u32* scratch, u32 stride) const { const u32 i = queue[j]; f.filter[i] = classify_sequences(p, f, an, i, scratch, stride); }
+struct cascade_sequences_fn { // one thread per fragment: host build only (the device runs k_cascade_sequences)
+	read_filter_params p; frag_view f; annot_view an; const u8* needs_sequences;
+	ARB_HD void operator()(u32 i, u32* scratch, u32 stride) const { if (needs_sequences[i]) f.filter[i] = classify_sequences(p, f, an, i, scratch, stride); }
 };
+
+#ifdef ARB_DEVICE_BUILD
+// The sequence rules (mismatches, low entropy) for a tile of fragments per block iteration: CASCADE_LANES lanes per fragment.
+//  * the tile's read sequences are one contiguous stretch of the sequence pool (fragments lie in name order, slots 0 and 1 back to back): ONE bulk copy
+//    (cp.async.bulk, completion on an mbarrier) brings it to shared memory while the threads fetch the tile's columns; a chunk whose pool is laid out
+//    differently (arb_push_chunk accepts any offsets) is read in place;
+//  * the lanes of a group take the 8-base words of a read in turn: reference words are read 32 bytes per group and load, 3-mers are counted with
+//    shared-memory atomics into the group's 64 counters (read_filters.h, classify_sequences_group).
+// Persistent grid: blocks stride over the tiles.
+static const u32 CASCADE_LANES = 8, CASCADE_THREADS = 256, CASCADE_GROUPS = CASCADE_THREADS / CASCADE_LANES;
+struct cascade_tile_params { u32 group_words /* 64 counters + dense codes, per group */; u32 seq_capacity_units /* 16-byte units of staging room, 0 = read in place */; u32 n_seq_units /* size of the sequence pool */; };
+
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+	asm volatile("{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(CASCADE_THREADS) k_cascade_sequences(read_filter_params p, frag_view f, annot_view an, const u8* __restrict__ needs_sequences, cascade_tile_params tp) {
+	extern __shared__ __align__(128) u8 smem[];
+	u8* const staged = smem;                                                        // sequences of the tile
+	u32* const group_scratch = (u32*) (smem + (size_t) tp.seq_capacity_units * 16); // counters + dense codes per group
+	__shared__ __align__(8) u64 bar;
+	__shared__ u32 s_lo, s_units;
+	const u32 group = threadIdx.x / CASCADE_LANES;
+	lane_group g; g.lane = threadIdx.x % CASCADE_LANES; g.lanes = CASCADE_LANES; g.mask = ((1u << CASCADE_LANES) - 1u) << ((threadIdx.x & 31u) / CASCADE_LANES * CASCADE_LANES);
+	u32* const counters = group_scratch + (size_t) group * tp.group_words;
+	if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	__syncthreads();
+	u32 parity = 0;
+	const u32 n_tiles = (f.n + CASCADE_GROUPS - 1) / CASCADE_GROUPS;
+	for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+		const u32 first = tile * CASCADE_GROUPS, end = hd_min(first + CASCADE_GROUPS, f.n);
+		if (threadIdx.x == 0) {
+			u32 units = 0, lo = 0;
+			if (tp.seq_capacity_units) { // canonical pool: the tile's sequences end where the next fragment's begin
+				lo = f.seq_off[first];
+				const u32 hi = end < f.n ? f.seq_off[end] : tp.n_seq_units;
+				if (hi > lo && hi - lo <= tp.seq_capacity_units) { units = hi - lo; mbar_expect_tx(&bar, units * 16); bulk_g2s(staged, f.seq + (size_t) lo * 16, units * 16, &bar); }
+			}
+			s_lo = lo; s_units = units;
+		}
+		__syncthreads();
+		const u32 lo = s_lo, units = s_units;
+		const u32 i = first + group;
+		const bool mine = i < end && needs_sequences[i];
+		if (units) { mbar_wait(&bar, parity); parity ^= 1; }
+		if (mine) {
+			fragment_inputs in = fragment_inputs_of(f, i);
+			if (units) { in.seq0 = staged + (size_t) (f.seq_off[f.idx(i, 0)] - lo) * 16; in.seq1 = staged + (size_t) (f.seq_off[f.idx(i, 1)] - lo) * 16; }
+			const u8 label = classify_sequences_group(g, p, f, an, i, in, counters, counters + 64);
+			if (g.lane == 0) f.filter[i] = label;
+		}
+		__syncthreads(); // the staging buffer is free again
+	}
+}
+#endif
 
 // test hook: (mismatches, compared bases) of the two alignments the mismatch rule walks, on the packed reference and base by base
 struct mismatch_probe_fn {
@@ -258,19 +329,45 @@ void engine::run_read_filters() {
 	timings.duplicates_ms = t_dup.stop();
 	}
 	{
-		dbuf<u32> queue(n), n_queued(1);
+		dbuf<u32> n_queued(1); dbuf<u8> needs(n);
 		n_queued.zero(ex, 1);
 		stage_timer t_cls(ex);
 		stage_timer t_head(ex);
-		cascade_head_fn hf = {p, f, annot.view(), frags.early.ptr(), queue.ptr(), n_queued.ptr()};
+		cascade_head_fn hf = {p, f, annot.view(), frags.early.ptr(), needs.ptr(), n_queued.ptr()};
 		for_each(ex, n, hf);
 		timings.cascade_head_ms = t_head.stop();
-		u32 q = 0; n_queued.download(ex, &q, 1);
 		stage_timer t_seq(ex);
-		cascade_sequences_fn sf = {p, f, annot.view(), queue.ptr()};
-		for_each_scratch<64>(ex, q, sf);
+#ifdef ARB_DEVICE_BUILD
+		if (n) {
+			// shared memory per block: staging room for the tile's sequences + per group 64 counters and one word of dense codes per 8 bases (reads beyond 500 bases
+			// are counted exactly by one lane and need no dense codes)
+			const u32 len_cap = std::min<u32>(frags.max_seq_len, 500);
+			cascade_tile_params tp;
+			tp.group_words = (64 + (len_cap + 7) / 8 + 2) | 1; // odd: the groups' counters start in different banks
+			const u32 units_per_read = ((frags.max_seq_len + 1) / 2 + 15) / 16;
+			tp.seq_capacity_units = frags.canonical_seq_layout && (size_t) units_per_read * 2 * CASCADE_GROUPS * 16 <= 96 * 1024 ? units_per_read * 2 * CASCADE_GROUPS : 0;
+			tp.n_seq_units = (u32) (frags.n_seq_bytes / 16);
+			const size_t shared_bytes = (size_t) tp.seq_capacity_units * 16 + (size_t) tp.group_words * 4 * CASCADE_GROUPS;
+			if (shared_bytes != cascade_smem_bytes) { // function attributes and occupancy are per device: cached in the context
+				ARB_CUDA_CHECK(cudaFuncSetAttribute(k_cascade_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(shared_bytes, 48 * 1024)));
+				int per_sm = 0, n_sm = 0;
+				ARB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cascade_sequences, (int) CASCADE_THREADS, shared_bytes));
+				ARB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+				cascade_resident_blocks = (u32) std::max(1, per_sm) * (u32) n_sm; cascade_smem_bytes = shared_bytes;
+			}
+			const u32 n_tiles = (n + CASCADE_GROUPS - 1) / CASCADE_GROUPS;
+			const u32 grid = std::min<u32>(n_tiles, cascade_resident_blocks); // persistent: SM count x resident blocks per SM
+			k_cascade_sequences<<<grid, CASCADE_THREADS, shared_bytes, ex.stream>>>(p, f, annot.view(), needs.ptr(), tp);
+			ARB_CUDA_CHECK(cudaGetLastError());
+			++stats().kernels;
+		}
+#else
+		cascade_sequences_fn sf = {p, f, annot.view(), needs.ptr()};
+		for_each_scratch<256>(ex, n, sf); // 64 counters + dense codes of reads up to 500 bases
+#endif
 		timings.cascade_sequences_ms = t_seq.stop();
 		timings.classify_ms = t_cls.stop();
+		u32 q = 0; n_queued.download(ex, &q, 1);
 		timings.cascade_queued = q;
 		timings.cascade_algorithmic_bytes[0] = head_bytes;
 		timings.cascade_algorithmic_bytes[1] = n ? (u64) ((double) sequence_bytes * q / n) : 0;

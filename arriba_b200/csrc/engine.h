@@ -27,12 +27,12 @@ struct stage_timer {
 
 
 struct frag_store {
-	u32 n; u32 max_seq_len;
+	u32 n; u32 max_seq_len; bool canonical_seq_layout; u64 n_seq_bytes;
 	dbuf<u8> n_aln, fflags, filter, early, aflags, seq, swapped;
 	dbuf<u16> contig, cigar_cnt, seq_len, genes_cnt;
 	dbuf<i32> start, end;
 	dbuf<u32> cigar_off, seq_off, genes_off, cigar, genes;
-	frag_store(): n(0), max_seq_len(0) {}
+	frag_store(): n(0), max_seq_len(0), canonical_seq_layout(false), n_seq_bytes(0) {}
 	frag_view view() const {
 		frag_view v;
 		v.n = n; v.n_aln = n_aln.ptr(); v.fflags = fflags.ptr(); v.filter = filter.ptr();
@@ -116,6 +116,7 @@ public:
 	// k-mer index / re-alignment
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
 	u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
+	size_t cascade_smem_bytes; u32 cascade_resident_blocks; // launch shape of the sequence kernel on this context's device
 	int device;
 	int mismap_budget, mismap_spawn_budget, mismap_min_blocks; u32 mismap_lanes, mismap_task_lanes, mismap_table_slots, homolog_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;

@@ -178,59 +178,6 @@ ARB_HD bool is_itd_shaped(const frag_view& f, u32 i, u32 max_itd_length) {
 	return f.end[s] > f.start[u] && f.end[s] <= f.start[u] + (i32) max_itd_length;
 }
 
-// `counters`: 64 words (word k at counters[k * stride]), one per 3-mer: occurrences in the whole read (bits 0-9), in the first aligned part (10-19) and in
-// the second (20-29); reads of more than 3,000 bases would overflow the fields.
-ARB_HD bool low_entropy(const frag_view& f, u32 i, float kmer_content, u32* counters, u32 stride) {
-	for (u32 mate = MATE1; mate <= MATE2; ++mate) {
-		const u32 a = f.idx(i, mate);
-		const u32 len = f.seq_len[a];
-		if (len < 3) continue;
-		const u8* seq = f.sq(a);
-		// aligned (not soft-clipped) parts; hard clips do not count (filter_low_entropy.cpp:40-46 tests BAM_CSOFT_CLIP only)
-		const u32* c = f.cig(a); const u32 nc = f.cigar_cnt[a];
-		u32 s1 = cig_op(c[0]) == C_S ? cig_len(c[0]) : 0;
-		u32 e1 = len; if (cig_op(c[nc - 1]) == C_S) e1 -= cig_len(c[nc - 1]);
-		u32 s2 = s1, e2 = e1;
-		if (f.n_aln[i] == 3 && mate == SPLIT_READ) {
-			const u32 u = f.idx(i, SUPPLEMENTARY);
-			const u32* cu = f.cig(u); const u32 nu = f.cigar_cnt[u];
-			s2 = cig_op(cu[0]) == C_S ? cig_len(cu[0]) : 0;
-			e2 = len; if (cig_op(cu[nu - 1]) == C_S) e2 -= cig_len(cu[nu - 1]);
-			if (f.fwd(u) != f.fwd(a)) { u32 ns = len - e2, ne = len - s2; s2 = ns; e2 = ne; }
-		}
-		const u32 max_all = kmer_threshold(len, kmer_content);
-		const u32 max_1 = kmer_threshold(e1 - s1, kmer_content);
-		const u32 max_2 = kmer_threshold(e2 - s2, kmer_content);
-		// Counters start at 512 - threshold, so "count >= threshold" is bit 9 of the field: one AND per counted k-mer instead of three compares. A zero
-		// threshold (empty aligned part) fires at the first counted k-mer, as in the reference. Reads beyond 1,500 bases take the plain compares.
-		const bool biased = len <= 1500;
-		const u32 start_value = biased ? (512 - max_all) | (512 - max_1) << 10 | (512 - max_2) << 20 : 0;
-		const u32 reached = 1u << 9 | 1u << 19 | 1u << 29;
-		for (u32 k = 0; k < 64; ++k) counters[k * stride] = start_value;
-		// "pos + 1 >= s && pos < e" as one unsigned comparison: pos - (s - 1) < e - (s - 1)
-		const u32 lo1 = s1 - 1, span1 = e1 + 1 > s1 ? e1 - lo1 : 0, lo2 = s2 - 1, span2 = e2 + 1 > s2 ? e2 - lo2 : 0;
-		// 2-bit code of a base: T=0 G=1 C=2, anything else 3 (filter_mismappers.cpp:33-45), looked up in a 32-bit constant indexed by the nt16 code
-		const u32 code2 = ~(3u << 16 | 2u << 8 | 1u << 4); // entries 8 (T), 4 (G), 2 (C) hold 0, 1, 2 -- every other entry 3
-		const u32 n_words = ((len + 31) / 32) * 4;
-		u32 word = nt16_word(seq, 0, n_words);
-		u32 km = (code2 >> 2 * (word >> 28) & 3) << 2 | (code2 >> 2 * (word >> 24 & 15) & 3); // bases 0 and 1
-		// a k-mer overlapping a counted occurrence of itself is skipped; with k=3 only the occurrences one and two positions back can overlap
-		u32 km_1 = 64, km_2 = 64; // k-mers COUNTED at pos-1 and pos-2 (64 = none)
-		for (u32 pos = 0; pos + 3 < len; ++pos) { // the last k-mer of the read is never examined (filter_low_entropy.cpp:77)
-			const u32 b = pos + 2;
-			if ((b & 7) == 0) word = nt16_word(seq, b >> 3, n_words);
-			km = (km << 2 | (code2 >> 2 * (word >> (28 - 4 * (b & 7)) & 15) & 3)) & 63;
-			if (km == km_1 || km == km_2) { km_2 = km_1; km_1 = 64; continue; }
-			km_2 = km_1; km_1 = km;
-			const u32 in1 = pos - lo1 < span1, in2 = pos - lo2 < span2;
-			const u32 w = counters[km * stride] + (1u | in1 << 10 | in2 << 20);
-			counters[km * stride] = w;
-			if (biased ? (w & reached) != 0 : ((w & 1023) >= max_all || (w >> 10 & 1023) >= max_1 || (w >> 20) >= max_2)) return true;
-		}
-	}
-	return false;
-}
-
 // ------------------------------------------------------------------------------------------- the cascade
 // Evaluates rules [uninteresting_contigs .. low_entropy] for fragment i given its current label
 // (F_none or F_duplicates from the duplicate pass). Returns the final label. `early` receives the label the
@@ -343,7 +290,224 @@ ARB_HD u8 classify_head(const read_filter_params& p, const frag_view& f, const a
 	return label;
 }
 
-ARB_HD u8 classify_sequences(const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, u32* scratch, u32 stride) {
+// ------------------------------------------------------------------------------------------- the sequence rules, evaluated by a GROUP of lanes per fragment
+// One thread per fragment streams its own reads: every load of a warp touches 32 different cache lines and the k-mer loop is a chain of dependent shared-memory
+// updates. The rules below are written for a group of `lanes` (power of two, <= 32, inside one warp) that owns one fragment: the lanes take the 8-base words of a
+// read in turn (coalesced), count mismatches by popcount and 3-mers with shared-memory atomics, and combine with shuffles. With lanes == 1 (host build, tests)
+// the same code is the sequential rule.
+struct lane_group {
+	u32 lane, lanes;
+	u32 mask; // device: the group's lanes inside the warp
+	ARB_HD u32 sum(u32 v) const {
+#ifdef __CUDA_ARCH__
+		for (u32 d = lanes >> 1; d; d >>= 1) v += __shfl_xor_sync(mask, v, d);
+#endif
+		return v;
+	}
+	ARB_HD bool any(bool p) const {
+#ifdef __CUDA_ARCH__
+		return (__ballot_sync(mask, p) & mask) != 0;
+#else
+		return p;
+#endif
+	}
+	ARB_HD void sync() const {
+#ifdef __CUDA_ARCH__
+		__syncwarp(mask);
+#endif
+	}
+};
+ARB_HD void group_add(u32* p, u32 v) { // counter shared by the lanes of a group
+#ifdef __CUDA_ARCH__
+	atomicAdd(p, v);
+#else
+	*p += v;
+#endif
+}
+
+// 2-bit codes (T=0 G=1 C=2, anything else 3; filter_mismappers.cpp:33-45) of the eight nt16 bases of a word, first base in bits 15..14
+ARB_HD u32 nt16_dense2(u32 w) {
+	const u32 a = w >> 3, b = w >> 2, c = w >> 1, m = 0x11111111u;
+	const u32 nd = ~w & m;                                  // bit 0 of the nibble clear
+	const u32 is_t = a & ~b & ~c & nd, is_g = ~a & b & ~c & nd, is_c = ~a & ~b & c & nd; // nibble == 8, 4, 2
+	const u32 lo = ~(is_t | is_c) & m, hi = ~(is_t | is_g) & m;
+	u32 x = lo | hi << 1;                                    // one code per nibble
+	x = (x | x >> 2) & 0x0f0f0f0fu; x = (x | x >> 4) & 0x00ff00ffu; x = (x | x >> 8) & 0xffffu;
+	return x;
+}
+
+// CIGAR walk against the reference by a group: the lanes split every aligned block into 8-base chunks. Returns the same (mismatches, compared bases) as count_mismatches.
+ARB_HD void count_mismatches_group(const lane_group& g, const frag_view& f, const annot_view& an, u32 a, const u32* c /* CIGAR of a */, const u8* seq, u32 seq_len, bool revcomp, u32& mismatches, u32& aligned) {
+	u32 mm_all = 0, mm = 0, al = 0; // counted once / by this lane
+	const u32 n = f.cigar_cnt[a];
+	const bool fwd = f.fwd(a);
+	const u64 base = an.contig_seq_off[f.contig[a]];
+	const u32 clen = an.contig_len[f.contig[a]];
+	const u32* g4 = an.assembly4 ? an.assembly4 + base / 8 : 0;
+	const u32 n_words = ((seq_len + 31) / 32) * 4;
+	i32 ref = f.start[a]; u32 rp = 0;
+	for (u32 k = 0; k < n; ++k) {
+		const u32 op = cig_op(c[k]), len = cig_len(c[k]);
+		switch (op) {
+			case C_S: case C_H:
+				rp += len;
+				if (!((k == 0 && !fwd) || (k == n - 1 && fwd))) ++mm_all;
+				break;
+			case C_D: ++mm_all; ref += (i32) len; break;
+			case C_N: ref += (i32) len; break;
+			case C_I: ++mm_all; rp += len; break;
+			case C_M: case C_EQ: case C_X:
+				if (g4 && ref >= 0 && (u32) ref + len <= clen && rp + len <= seq_len) {
+					for (u32 j = 8 * g.lane; j < len; j += 8 * g.lanes) {
+						const u32 cnt = hd_min(8u, len - j);
+						const u32 valid = 0x11111111u << (4 * (8 - cnt));
+						const u32 r = revcomp ? brev32(nt16_window(seq, n_words, (i32) (seq_len - 1 - (rp + j)) - 7)) : nt16_window(seq, n_words, (i32) (rp + j));
+						if (revcomp) { // ambiguity codes are not complemented by the reference (assembly.hpp:9-22): base by base
+							const u32 s = (r & 0x55555555u) + (r >> 1 & 0x55555555u), c4 = (s & 0x33333333u) + (s >> 2 & 0x33333333u);
+							if ((c4 >> 1) & ~(c4 >> 2) & valid) {
+								for (u32 t = 0; t < cnt; ++t) {
+									const u32 code = nt16_complement(nt16_at(seq, seq_len - 1 - (rp + j + t)));
+									if (code != NT_N) { if (nt16_char(code) != an.assembly[base + (u32) ref + j + t]) ++mm; ++al; }
+								}
+								continue;
+							}
+						}
+						const u32 gw = packed_window(g4, (u64) (u32) ref + j);
+						const u32 is_n = r & r >> 1 & r >> 2 & r >> 3, ok = valid & ~is_n;
+						const u32 x = r ^ gw, differs = x | x >> 1 | x >> 2 | x >> 3;
+						mm += popc32(differs & ok); al += popc32(ok);
+					}
+				} else {
+					for (u32 j = g.lane; j < len; j += g.lanes) {
+						if (rp + j >= seq_len) continue;
+						const u32 code = revcomp ? nt16_complement(nt16_at(seq, seq_len - 1 - (rp + j))) : nt16_at(seq, rp + j);
+						if (code != NT_N) {
+							const i32 q = ref + (i32) j;
+							const char r = ((u32) q < clen) ? an.assembly[base + (u32) q] : '\0';
+							if (nt16_char(code) != r) ++mm;
+							++al;
+						}
+					}
+				}
+				ref += (i32) len; rp += len;
+				break;
+			default: break;
+		}
+	}
+	mismatches = mm_all + g.sum(mm); aligned = g.sum(al);
+}
+
+ARB_HD bool too_many_mismatches_group(const lane_group& g, const read_filter_params& p, const frag_view& f, const annot_view& an, u32 a, const u32* cig, const u8* seq, u32 seq_len, bool revcomp, bool multimapper_penalty) {
+	u32 mm, n;
+	count_mismatches_group(g, f, an, a, cig, seq, seq_len, revcomp, mm, n);
+	if (multimapper_penalty) mm += 2;
+	if (n >= p.table_n) n = p.table_n - 1;
+	if (mm >= p.table_k) mm = p.table_k - 1;
+	return p.mismatch_table[n * p.table_k + mm] != 0;
+}
+
+// scopes of the 3-mer counts of one mate (filter_low_entropy.cpp:40-69): the whole read and two aligned windows
+struct entropy_scopes { u32 len, s1, e1, s2, e2, max_all, max_1, max_2; };
+ARB_HD entropy_scopes entropy_scopes_of(const frag_view& f, u32 i, u32 mate, const u32* c /* CIGAR of the mate */, const u32* cu /* of the supplementary */, float kmer_content) {
+	entropy_scopes sc;
+	const u32 a = f.idx(i, mate);
+	const u32 len = f.seq_len[a]; const u32 nc = f.cigar_cnt[a];
+	sc.len = len;
+	sc.s1 = cig_op(c[0]) == C_S ? cig_len(c[0]) : 0;
+	sc.e1 = len; if (cig_op(c[nc - 1]) == C_S) sc.e1 -= cig_len(c[nc - 1]);
+	sc.s2 = sc.s1; sc.e2 = sc.e1;
+	if (f.n_aln[i] == 3 && mate == SPLIT_READ) {
+		const u32 u = f.idx(i, SUPPLEMENTARY); const u32 nu = f.cigar_cnt[u];
+		sc.s2 = cig_op(cu[0]) == C_S ? cig_len(cu[0]) : 0;
+		sc.e2 = len; if (cig_op(cu[nu - 1]) == C_S) sc.e2 -= cig_len(cu[nu - 1]);
+		if (f.fwd(u) != f.fwd(a)) { const u32 ns = len - sc.e2, ne = len - sc.s2; sc.s2 = ns; sc.e2 = ne; }
+	}
+	sc.max_all = kmer_threshold(len, kmer_content); sc.max_1 = kmer_threshold(sc.e1 - sc.s1, kmer_content); sc.max_2 = kmer_threshold(sc.e2 - sc.s2, kmer_content);
+	return sc;
+}
+
+// the reference's sequential count of one mate: identical 3-mers that overlap a counted occurrence are skipped (filter_low_entropy.cpp:74-103)
+ARB_HD bool low_entropy_mate_exact(const entropy_scopes& sc, const u8* seq, u32* counters, u32 stride) {
+	const u32 len = sc.len;
+	const bool biased = len <= 1500;
+	const u32 start_value = biased ? (512 - sc.max_all) | (512 - sc.max_1) << 10 | (512 - sc.max_2) << 20 : 0;
+	const u32 reached = 1u << 9 | 1u << 19 | 1u << 29;
+	for (u32 k = 0; k < 64; ++k) counters[k * stride] = start_value;
+	const u32 lo1 = sc.s1 - 1, span1 = sc.e1 + 1 > sc.s1 ? sc.e1 - lo1 : 0, lo2 = sc.s2 - 1, span2 = sc.e2 + 1 > sc.s2 ? sc.e2 - lo2 : 0;
+	const u32 code2 = ~(3u << 16 | 2u << 8 | 1u << 4);
+	const u32 n_words = ((len + 31) / 32) * 4;
+	u32 word = nt16_word(seq, 0, n_words);
+	u32 km = (code2 >> 2 * (word >> 28) & 3) << 2 | (code2 >> 2 * (word >> 24 & 15) & 3);
+	u32 km_1 = 64, km_2 = 64;
+	for (u32 pos = 0; pos + 3 < len; ++pos) {
+		const u32 b = pos + 2;
+		if ((b & 7) == 0) word = nt16_word(seq, b >> 3, n_words);
+		km = (km << 2 | (code2 >> 2 * (word >> (28 - 4 * (b & 7)) & 15) & 3)) & 63;
+		if (km == km_1 || km == km_2) { km_2 = km_1; km_1 = 64; continue; }
+		km_2 = km_1; km_1 = km;
+		const u32 in1 = pos - lo1 < span1, in2 = pos - lo2 < span2;
+		const u32 w = counters[km * stride] + (1u | in1 << 10 | in2 << 20);
+		counters[km * stride] = w;
+		if (biased ? (w & reached) != 0 : ((w & 1023) >= sc.max_all || (w >> 10 & 1023) >= sc.max_1 || (w >> 20) >= sc.max_2)) return true;
+	}
+	return false;
+}
+
+// Group version. Pass 1 counts EVERY occurrence (overlapping ones too) with the lanes in parallel: an upper bound of the reference's counts, so a mate whose
+// bound stays below all three thresholds is not of low entropy. The few mates that reach a threshold are counted exactly by one lane.
+// `counters`: 64 words of the group, `dense`: one word per 8 bases of the longest read (+1).
+ARB_HD bool low_entropy_mate_group(const lane_group& g, const entropy_scopes& sc, const u8* seq, u32* counters, u32* dense) {
+	const u32 len = sc.len;
+	if (len < 3) return false;
+	bool suspicious = len > 500; // every occurrence is counted here: a 10-bit field (512 - threshold + count) must not wrap. Longer reads: exact count only
+	if (!suspicious) {
+		const u32 start_value = (512 - sc.max_all) | (512 - sc.max_1) << 10 | (512 - sc.max_2) << 20, reached = 1u << 9 | 1u << 19 | 1u << 29;
+		const u32 n_words = ((len + 31) / 32) * 4, used_words = (len + 7) / 8;
+		for (u32 k = g.lane; k < 64; k += g.lanes) counters[k] = start_value;
+		for (u32 w = g.lane; w <= used_words; w += g.lanes) dense[w] = nt16_dense2(nt16_word(seq, w, n_words));
+		g.sync();
+		// positions of window x: a_x <= pos < b_x (pos + 1 >= s && pos < e)
+		const i32 a1 = (i32) hd_max(sc.s1, 1u) - 1, b1 = sc.e1 + 1 > sc.s1 ? (i32) sc.e1 : 0, a2 = (i32) hd_max(sc.s2, 1u) - 1, b2 = sc.e2 + 1 > sc.s2 ? (i32) sc.e2 : 0;
+		const i32 last = (i32) len - 3; // positions 0 .. last-1 are examined (the last k-mer never is, filter_low_entropy.cpp:77)
+		for (u32 w = g.lane; (i32) (8 * w) < last; w += g.lanes) {
+			const i32 p0 = (i32) (8 * w);
+			const u32 d = dense[w] << 16 | dense[w + 1]; // bases p0 .. p0+15, two bits each, first base on top
+			const u32 v = (u32) hd_min(8, last - p0);   // examined positions of this word
+			#define ARB_RANGE_MASK(a_, b_) ((((1u << (u32) hd_min(hd_max((b_) - p0, 0), 8)) - 1u) & ~((1u << (u32) hd_min(hd_max((a_) - p0, 0), 8)) - 1u)))
+			const u32 m = ARB_RANGE_MASK(a1, b1) | ARB_RANGE_MASK(a2, b2) << 10; // bit j: position p0+j in window 1, bit 10+j: in window 2
+			#undef ARB_RANGE_MASK
+			#pragma unroll
+			for (u32 j = 0; j < 8; ++j) {
+				if (j < v) {
+					const u32 km = d >> (26 - 2 * j) & 63u;
+					group_add(&counters[km], 1u + ((m >> j & 0x401u) << 10));
+				}
+			}
+		}
+		g.sync();
+		u32 acc = 0;
+		for (u32 k = g.lane; k < 64; k += g.lanes) acc |= counters[k];
+		suspicious = g.any((acc & reached) != 0);
+		g.sync();
+	}
+	if (!suspicious) return false;
+	bool hit = false;
+	if (g.lane == 0) hit = low_entropy_mate_exact(sc, seq, counters, 1);
+	hit = g.any(hit);
+	g.sync();
+	return hit;
+}
+
+// pointers of the fragment's data as the kernel staged them (shared memory) or where they lie (global memory)
+struct fragment_inputs { const u8* seq0; const u8* seq1; const u32* cig0; const u32* cig1; const u32* cig2; };
+ARB_HD fragment_inputs fragment_inputs_of(const frag_view& f, u32 i) {
+	fragment_inputs in;
+	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
+	in.seq0 = f.sq(a0); in.seq1 = f.sq(a1); in.cig0 = f.cig(a0); in.cig1 = f.cig(a1); in.cig2 = f.cig(a2);
+	return in;
+}
+
+ARB_HD u8 classify_sequences_group(const lane_group& g, const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, const fragment_inputs& in, u32* counters, u32* dense) {
 	u8 label = f.filter[i];
 	const u32 n = f.n_aln[i];
 	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
@@ -351,18 +515,32 @@ ARB_HD u8 classify_sequences(const read_filter_params& p, const frag_view& f, co
 		const bool multi = f.fflags[i] & FF_MULTIMAPPER;
 		const u32 y = n == 2 ? a1 : a2;
 		const bool viral0 = an.contig_flags[f.contig[a0]] & CF_VIRAL, viraly = an.contig_flags[f.contig[y]] & CF_VIRAL;
-		bool bad = !viral0 && too_many_mismatches(p, f, an, a0, f.sq(a0), f.seq_len[a0], false, multi && !viraly);
+		bool bad = !viral0 && too_many_mismatches_group(g, p, f, an, a0, in.cig0, in.seq0, f.seq_len[a0], false, multi && !viraly);
 		if (!bad && !viraly) {
-			if (n == 2) bad = too_many_mismatches(p, f, an, a1, f.sq(a1), f.seq_len[a1], false, multi && !viral0);
-			else bad = too_many_mismatches(p, f, an, a2, f.sq(a1), f.seq_len[a1], f.fwd(a2) != f.fwd(a1), multi && !viral0);
+			if (n == 2) bad = too_many_mismatches_group(g, p, f, an, a1, in.cig1, in.seq1, f.seq_len[a1], false, multi && !viral0);
+			else bad = too_many_mismatches_group(g, p, f, an, a2, in.cig2, in.seq1, f.seq_len[a1], f.fwd(a2) != f.fwd(a1), multi && !viral0);
 		}
 		if (bad) label = F_mismatches;
 	}
 	if (p.enabled(F_low_entropy)) {
 		const bool examine = label == F_none || (label != F_duplicates && is_itd_shaped(f, i, p.max_itd_length));
-		if (examine && low_entropy(f, i, p.max_kmer_content, scratch, stride)) label = F_low_entropy;
+		if (examine) {
+			bool low = low_entropy_mate_group(g, entropy_scopes_of(f, i, MATE1, in.cig0, in.cig2, p.max_kmer_content), in.seq0, counters, dense);
+			if (!low) low = low_entropy_mate_group(g, entropy_scopes_of(f, i, MATE2, in.cig1, in.cig2, p.max_kmer_content), in.seq1, counters, dense);
+			if (low) label = F_low_entropy;
+		}
 	}
 	return label;
+}
+
+// one thread per fragment (host build, and the reference point of the tests)
+ARB_HD u8 classify_sequences(const read_filter_params& p, const frag_view& f, const annot_view& an, u32 i, u32* scratch, u32 stride) {
+	(void) stride; // scratch: 64 counters + dense codes, contiguous (the one-lane group has no bank conflicts to avoid)
+	lane_group g; g.lane = 0; g.lanes = 1; g.mask = 0;
+#ifdef __CUDA_ARCH__
+	g.mask = 1u << (threadIdx.x & 31u);
+#endif
+	return classify_sequences_group(g, p, f, an, i, fragment_inputs_of(f, i), scratch, scratch + 64);
 }
 
 } // namespace arb
