@@ -7,6 +7,22 @@ using namespace arb;
 struct arb_ctx { engine e; };
 static std::string g_create_error;
 
+// ---- page-locked host memory for the caller's columns -----------------------------------------------------------------------------------------------
+// The host side builds its large columns in recycled blocks (host/ingest.h, host_block_get); in the CUDA library fresh blocks are page-locked, so that
+// arb_push_chunk_begin/end copy them asynchronously at full PCIe speed. ARB_PINNED_HOST=0 keeps them pageable.
+namespace arb { namespace host { void set_host_block_backend(void* (*alloc)(size_t), void (*release)(void*)); } }
+static int g_host_memory_device = -1;
+#ifdef ARB_DEVICE_BUILD
+static void* pinned_alloc(size_t bytes) {
+	if (g_host_memory_device >= 0) { int cur = -1; if (cudaGetDevice(&cur) != cudaSuccess || cur != g_host_memory_device) { if (cudaSetDevice(g_host_memory_device) != cudaSuccess) { cudaGetLastError(); return NULL; } } }
+	void* p = NULL;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return NULL; }
+	return p;
+}
+static void pinned_free(void* p) { cudaFreeHost(p); }
+namespace { struct install_pinned_backend { install_pinned_backend() { const char* s = getenv("ARB_PINNED_HOST"); if (!s || atoi(s) != 0) arb::host::set_host_block_backend(pinned_alloc, pinned_free); } } g_install_pinned_backend; }
+#endif
+
 #ifdef ARB_DEVICE_BUILD
 #define ARB_BIND_DEVICE(ctx) ARB_CUDA_CHECK(cudaSetDevice((ctx)->e.device));
 #else
@@ -61,13 +77,17 @@ void arb_ctx_destroy(arb_ctx* ctx) {
 	delete ctx; // device blocks go back to the pool, not to the driver: the next context on this device reuses them
 }
 void arb_release_device_memory(void) { pool_trim(); }
+void arb_set_host_memory_device(int device) { g_host_memory_device = device; }
 const char* arb_last_error(arb_ctx* ctx) { return ctx ? ctx->e.last_error.c_str() : g_create_error.c_str(); }
 
 void arb_default_params(arb_params* p) { if (p) default_params(*p); }
 int arb_set_params(arb_ctx* ctx, const arb_params* p) { ARB_API_BEGIN(ctx) ctx->e.set_params(*p); ARB_API_END(ctx) }
 int arb_set_contigs(arb_ctx* ctx, const arb_contigs* c) { ARB_API_BEGIN(ctx) ctx->e.set_contigs(*c); ARB_API_END(ctx) }
 int arb_set_annotation(arb_ctx* ctx, const arb_annotation* a) { ARB_API_BEGIN(ctx) ctx->e.set_annotation(*a); ARB_API_END(ctx) }
+int arb_set_contig_flags(arb_ctx* ctx, const uint8_t* flags, uint32_t n) { ARB_API_BEGIN(ctx) ctx->e.set_contig_flags(flags, n); ARB_API_END(ctx) }
 int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk(*c); ARB_API_END(ctx) }
+int arb_push_chunk_begin(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk_begin(*c); ARB_API_END(ctx) }
+int arb_push_chunk_end(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk_end(*c); ARB_API_END(ctx) }
 int arb_run_read_filters(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.run_read_filters(); ARB_API_END(ctx) }
 int arb_get_fragment_filters(arb_ctx* ctx, uint8_t* f, uint8_t* early) { ARB_API_BEGIN(ctx) ctx->e.get_fragment_filters(f, early); ARB_API_END(ctx) }
 int arb_set_fragment_filters(arb_ctx* ctx, const uint8_t* f) { ARB_API_BEGIN(ctx) ctx->e.set_fragment_filters(f); ARB_API_END(ctx) }

@@ -18,6 +18,7 @@ engine::engine(): cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), 
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
+	mismap_group_pass = true; if (const char* s = getenv("ARB_MISMAP_GROUP")) mismap_group_pass = atoi(s) != 0;
 	mismap_budget = 4096; mismap_lanes = 1024; mismap_spawn_budget = 0; mismap_task_lanes = 32;
 	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
 	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));
@@ -29,11 +30,14 @@ engine::engine(): cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), 
 	ex.scratch = &scratch;
 #ifdef ARB_DEVICE_BUILD
 	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&ex.stream, cudaStreamNonBlocking));
+	ARB_CUDA_CHECK(cudaStreamCreateWithFlags(&copy_ex.stream, cudaStreamNonBlocking));
 #endif
+	copy_ex.scratch = &scratch; push_open = false;
 }
 
 engine::~engine() { // arb_ctx_destroy has made the context's device current; buffers go back to that device's pool after the stream has drained
 #ifdef ARB_DEVICE_BUILD
+	if (copy_ex.stream) { cudaStreamSynchronize(copy_ex.stream); cudaStreamDestroy(copy_ex.stream); copy_ex.stream = 0; }
 	if (ex.stream) { cudaStreamSynchronize(ex.stream); cudaStreamDestroy(ex.stream); ex.stream = 0; }
 #endif
 }
@@ -94,6 +98,16 @@ void engine::set_contigs(const arb_contigs& c) {
 	table_n = 0; // mismatch table depends on the genome size
 }
 
+void engine::set_contig_flags(const u8* flags, u32 n) { // per-sample flags (interesting / viral patterns, verdicts of the viral heuristics) without re-sending the genome
+	if (!has_contigs || n != annot.n_contigs) throw arb_error("arb_set_contig_flags: contig table not set or of a different size");
+	bool interesting_changed = false;
+	for (u32 k = 0; k < n; ++k) if ((flags[k] ^ annot.h_contig_flags[k]) & CF_INTERESTING) interesting_changed = true;
+	annot.h_contig_flags.assign(flags, flags + n);
+	annot.contig_flags.upload(ex, annot.h_contig_flags.data(), n);
+	ex.sync();
+	if (interesting_changed) table_n = 0; // the mismatch table depends on the genome size (filter_mismatches.cpp:105-108)
+}
+
 void engine::set_annotation(const arb_annotation& a) {
 	if (has_contigs && a.n_contigs != annot.n_contigs) throw arb_error("annotation and contig table disagree on the number of contigs");
 	annot.n_genes = a.n_genes; annot.n_exons = a.n_exons; annot.n_contigs = a.n_contigs;
@@ -114,17 +128,22 @@ void engine::set_annotation(const arb_annotation& a) {
 	has_annotation = true;
 }
 
-void engine::push_chunk(const arb_soa_chunk& c) {
+// The fragment table goes to the device in two parts. Everything ingest produces is final when ingest ends and is copied first, asynchronously on the
+// copy stream (the caller's columns are page-locked when they were built in blocks of the host pool, arb_host_alloc) -- the caller annotates meanwhile;
+// the annotation columns (alignment flags with the exonic / strand bits, gene sets) follow, and push_chunk_end returns when the table is resident.
+void engine::push_chunk_begin(const arb_soa_chunk& c) {
 	const u32 n = c.n_fragments;
+	ex.sync(); // kernels of the previous sample may still read the buffers that are about to be overwritten
 	frags.n = n;
-	stage_timer t_h2d(ex);
-	frags.n_aln.upload(ex, c.n_aln, n); frags.fflags.upload(ex, c.fflags, n); frags.filter.upload(ex, c.filter, n);
-	frags.early.ensure(n); frags.swapped.ensure(n); frags.swapped.zero(ex, n);
-	frags.contig.upload(ex, c.contig, 3 * (size_t) n); frags.start.upload(ex, c.start, 3 * (size_t) n); frags.end.upload(ex, c.end, 3 * (size_t) n);
-	frags.aflags.upload(ex, c.aflags, 3 * (size_t) n); frags.cigar_off.upload(ex, c.cigar_off, 3 * (size_t) n); frags.cigar_cnt.upload(ex, c.cigar_cnt, 3 * (size_t) n);
-	frags.seq_off.upload(ex, c.seq_off, 2 * (size_t) n); frags.seq_len.upload(ex, c.seq_len, 2 * (size_t) n);
-	frags.genes_off.upload(ex, c.genes_off, 3 * (size_t) n); frags.genes_cnt.upload(ex, c.genes_cnt, 3 * (size_t) n);
-	frags.cigar.upload(ex, c.cigar, c.n_cigar); frags.seq.upload(ex, c.seq, c.n_seq_bytes); frags.genes.upload(ex, c.genes, c.n_genes);
+	const exec_ctx& cx = copy_ex;
+	stage_timer t_h2d(cx);
+	frags.n_aln.upload(cx, c.n_aln, n); frags.fflags.upload(cx, c.fflags, n); frags.filter.upload(cx, c.filter, n);
+	frags.early.ensure(n); frags.swapped.ensure(n); frags.swapped.zero(cx, n);
+	frags.contig.upload(cx, c.contig, 3 * (size_t) n); frags.start.upload(cx, c.start, 3 * (size_t) n); frags.end.upload(cx, c.end, 3 * (size_t) n);
+	frags.cigar_off.upload(cx, c.cigar_off, 3 * (size_t) n); frags.cigar_cnt.upload(cx, c.cigar_cnt, 3 * (size_t) n);
+	frags.seq_off.upload(cx, c.seq_off, 2 * (size_t) n); frags.seq_len.upload(cx, c.seq_len, 2 * (size_t) n);
+	frags.cigar.upload(cx, c.cigar, c.n_cigar); frags.seq.upload(cx, c.seq, c.n_seq_bytes);
+	// host-side statistics of the chunk while the copies run
 	u32 max_len = 0;
 	for (size_t k = 0; k < 2 * (size_t) n; ++k) if (c.seq_len[k] > max_len) max_len = c.seq_len[k];
 	frags.max_seq_len = max_len;
@@ -137,19 +156,34 @@ void engine::push_chunk(const arb_soa_chunk& c) {
 			for (u32 s = 0; s < 2; ++s) { const size_t a = s * (size_t) n + i; if (c.seq_off[a] != at) { canonical = false; break; } at += ((c.seq_len[a] + 1) / 2 + 15) / 16; }
 		frags.canonical_seq_layout = canonical && at * 16 <= c.n_seq_bytes;
 	}
-	timings.h2d_ms = t_h2d.stop();
-	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 1 + 4 + 2 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes + c.n_genes * 4;
-	// Column budget of SURVEY.md section 8(d): every column read once at its compact width -- 11 B per alignment {contig u16, start, end, flags u8}, CIGAR ops and
-	// gene ids with a 4-byte offset per alignment, 6 B per fragment {rank, flags, label}; sequences at 3 bit/base, gathered reference bases at 2 bit/base.
 	u64 n_alignments = 0, bases = 0;
 	for (size_t k = 0; k < n; ++k) n_alignments += c.n_aln[k];
 	for (size_t k = 0; k < 2 * (size_t) n; ++k) bases += c.seq_len[k];
+	push_alignments = n_alignments; push_bases = bases;
+	timings.h2d_ms = t_h2d.stop(); // waits for part one: the caller's annotation takes far longer than the copy, and the timing stays a pure copy time
+	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes;
+	push_open = true;
+	filters_done = false;
+	cands.n = 0;
+}
+
+void engine::push_chunk_end(const arb_soa_chunk& c) {
+	if (!push_open || c.n_fragments != frags.n) throw arb_error("arb_push_chunk_end without a matching arb_push_chunk_begin");
+	const u32 n = c.n_fragments;
+	const exec_ctx& cx = copy_ex;
+	stage_timer t_h2d(cx);
+	frags.aflags.upload(cx, c.aflags, 3 * (size_t) n);
+	frags.genes_off.upload(cx, c.genes_off, 3 * (size_t) n); frags.genes_cnt.upload(cx, c.genes_cnt, 3 * (size_t) n); frags.genes.upload(cx, c.genes, c.n_genes);
+	timings.h2d_ms += t_h2d.stop();
+	timings.h2d_bytes += (u64) n * 3 * (1 + 4 + 2) + c.n_genes * 4;
+	// Column budget of SURVEY.md section 8(d): every column read once at its compact width -- 11 B per alignment {contig u16, start, end, flags u8}, CIGAR ops and
+	// gene ids with a 4-byte offset per alignment, 6 B per fragment {rank, flags, label}; sequences at 3 bit/base, gathered reference bases at 2 bit/base.
+	const u64 n_alignments = push_alignments, bases = push_bases;
 	head_bytes = n_alignments * 11 + ((u64) c.n_cigar + n_alignments) * 4 + ((u64) c.n_genes + n_alignments) * 4 + (u64) n * 6;
 	sequence_bytes = bases * 3 / 8 + bases * 2 / 8 + ((u64) c.n_cigar + n_alignments) * 4 + n_alignments * 11 + (u64) n * 2;
 	timings.classify_algorithmic_bytes = head_bytes + sequence_bytes;
-	ex.sync();
-	filters_done = false;
-	cands.n = 0;
+	cx.sync();
+	push_open = false;
 }
 
 unsigned long engine::genome_size() const { // filter_mismatches.cpp:105-108
@@ -216,15 +250,15 @@ struct cascade_sequences_fn { // one thread per fragment: host build only (the d
 };
 
 #ifdef ARB_DEVICE_BUILD
-// The sequence rules (mismatches, low entropy) for a tile of fragments per block iteration: CASCADE_LANES lanes per fragment.
-//  * the tile's read sequences are one contiguous stretch of the sequence pool (fragments lie in name order, slots 0 and 1 back to back): ONE bulk copy
-//    (cp.async.bulk, completion on an mbarrier) brings it to shared memory while the threads fetch the tile's columns; a chunk whose pool is laid out
-//    differently (arb_push_chunk accepts any offsets) is read in place;
+// The sequence rules (mismatches, low entropy): CASCADE_LANES lanes per fragment, a warp takes four consecutive fragments at a time.
+//  * the read sequences of a warp's fragments are one contiguous stretch of the sequence pool (fragments lie in name order, slots 0 and 1 back to back): ONE bulk
+//    copy (cp.async.bulk, completion on the warp's mbarrier) brings it to shared memory while the lanes fetch the fragments' columns; a chunk whose pool is
+//    laid out differently (arb_push_chunk accepts any offsets) is read in place;
 //  * the lanes of a group take the 8-base words of a read in turn: reference words are read 32 bytes per group and load, 3-mers are counted with
 //    shared-memory atomics into the group's 64 counters (read_filters.h, classify_sequences_group).
-// Persistent grid: blocks stride over the tiles.
-static const u32 CASCADE_LANES = 8, CASCADE_THREADS = 256, CASCADE_GROUPS = CASCADE_THREADS / CASCADE_LANES;
-struct cascade_tile_params { u32 group_words /* 64 counters + dense codes, per group */; u32 seq_capacity_units /* 16-byte units of staging room, 0 = read in place */; u32 n_seq_units /* size of the sequence pool */; };
+// Persistent grid: the warps stride over the tiles.
+static const u32 CASCADE_LANES = 8, CASCADE_THREADS = 256, CASCADE_GROUPS = CASCADE_THREADS / CASCADE_LANES, CASCADE_GROUPS_PER_WARP = 32 / CASCADE_LANES;
+struct cascade_tile_params { u32 group_words /* 64 counters + dense codes + predecessor masks, per group */; u32 seq_capacity_units /* 16-byte units of staging room per warp, 0 = read in place */; u32 n_seq_units /* size of the sequence pool */; };
 
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64* bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
@@ -237,41 +271,44 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 }
 
 __global__ void __launch_bounds__(CASCADE_THREADS) k_cascade_sequences(read_filter_params p, frag_view f, annot_view an, const u8* __restrict__ needs_sequences, cascade_tile_params tp) {
+	// Every WARP works on its own: a tile is the CASCADE_GROUPS_PER_WARP consecutive fragments of one warp, staged by the warp's own bulk copy on the warp's own
+	// mbarrier -- no block-wide barrier, so a fragment that takes long (many alignment blocks, a long read) holds up three neighbours, not a block.
 	extern __shared__ __align__(128) u8 smem[];
-	u8* const staged = smem;                                                        // sequences of the tile
-	u32* const group_scratch = (u32*) (smem + (size_t) tp.seq_capacity_units * 16); // counters + dense codes per group
-	__shared__ __align__(8) u64 bar;
-	__shared__ u32 s_lo, s_units;
-	const u32 group = threadIdx.x / CASCADE_LANES;
-	lane_group g; g.lane = threadIdx.x % CASCADE_LANES; g.lanes = CASCADE_LANES; g.mask = ((1u << CASCADE_LANES) - 1u) << ((threadIdx.x & 31u) / CASCADE_LANES * CASCADE_LANES);
-	u32* const counters = group_scratch + (size_t) group * tp.group_words;
-	if (threadIdx.x == 0) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-	__syncthreads();
+	const u32 warp = threadIdx.x / 32, lane32 = threadIdx.x & 31u, group_in_warp = lane32 / CASCADE_LANES;
+	const u32 warp_seq_bytes = tp.seq_capacity_units * 16; // staging room of one warp
+	u8* const staged = smem + (size_t) warp * warp_seq_bytes;
+	u32* const counters = (u32*) (smem + (size_t) (CASCADE_THREADS / 32) * warp_seq_bytes) + (size_t) (threadIdx.x / CASCADE_LANES) * tp.group_words;
+	__shared__ __align__(8) u64 bars[CASCADE_THREADS / 32];
+	u64* const bar = &bars[warp];
+	lane_group g; g.lane = threadIdx.x % CASCADE_LANES; g.lanes = CASCADE_LANES; g.mask = ((1u << CASCADE_LANES) - 1u) << (group_in_warp * CASCADE_LANES);
+	if (lane32 == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	__syncwarp();
 	u32 parity = 0;
-	const u32 n_tiles = (f.n + CASCADE_GROUPS - 1) / CASCADE_GROUPS;
-	for (u32 tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-		const u32 first = tile * CASCADE_GROUPS, end = hd_min(first + CASCADE_GROUPS, f.n);
-		if (threadIdx.x == 0) {
-			u32 units = 0, lo = 0;
-			if (tp.seq_capacity_units) { // canonical pool: the tile's sequences end where the next fragment's begin
+	const u32 n_tiles = (f.n + CASCADE_GROUPS_PER_WARP - 1) / CASCADE_GROUPS_PER_WARP;
+	const u32 n_warps = gridDim.x * (CASCADE_THREADS / 32);
+	for (u32 tile = blockIdx.x * (CASCADE_THREADS / 32) + warp; tile < n_tiles; tile += n_warps) {
+		const u32 first = tile * CASCADE_GROUPS_PER_WARP, end = hd_min(first + CASCADE_GROUPS_PER_WARP, f.n);
+		const u32 i = first + group_in_warp;
+		const bool mine = i < end && needs_sequences[i];
+		if (!__any_sync(0xFFFFFFFFu, mine)) continue;
+		u32 lo = 0, units = 0;
+		if (tp.seq_capacity_units) { // canonical pool: the tile's sequences end where the next fragment's begin
+			if (lane32 == 0) {
 				lo = f.seq_off[first];
 				const u32 hi = end < f.n ? f.seq_off[end] : tp.n_seq_units;
-				if (hi > lo && hi - lo <= tp.seq_capacity_units) { units = hi - lo; mbar_expect_tx(&bar, units * 16); bulk_g2s(staged, f.seq + (size_t) lo * 16, units * 16, &bar); }
+				if (hi > lo && hi - lo <= tp.seq_capacity_units) { units = hi - lo; mbar_expect_tx(bar, units * 16); bulk_g2s(staged, f.seq + (size_t) lo * 16, units * 16, bar); }
 			}
-			s_lo = lo; s_units = units;
+			lo = __shfl_sync(0xFFFFFFFFu, lo, 0); units = __shfl_sync(0xFFFFFFFFu, units, 0);
 		}
-		__syncthreads();
-		const u32 lo = s_lo, units = s_units;
-		const u32 i = first + group;
-		const bool mine = i < end && needs_sequences[i];
-		if (units) { mbar_wait(&bar, parity); parity ^= 1; }
+		fragment_inputs in;
+		if (mine) in = fragment_inputs_of(f, i); // the columns of the fragment travel while the bulk copy is in flight
+		if (units) { mbar_wait(bar, parity); parity ^= 1; }
 		if (mine) {
-			fragment_inputs in = fragment_inputs_of(f, i);
 			if (units) { in.seq0 = staged + (size_t) (f.seq_off[f.idx(i, 0)] - lo) * 16; in.seq1 = staged + (size_t) (f.seq_off[f.idx(i, 1)] - lo) * 16; }
 			const u8 label = classify_sequences_group(g, p, f, an, i, in, counters, counters + 64);
 			if (g.lane == 0) f.filter[i] = label;
 		}
-		__syncthreads(); // the staging buffer is free again
+		__syncwarp(); // the warp's staging buffer is free again
 	}
 }
 #endif
@@ -341,13 +378,13 @@ void engine::run_read_filters() {
 		if (n) {
 			// shared memory per block: staging room for the tile's sequences + per group 64 counters and one word of dense codes per 8 bases (reads beyond 500 bases
 			// are counted exactly by one lane and need no dense codes)
-			const u32 len_cap = std::min<u32>(frags.max_seq_len, 500);
+			const u32 len_cap = std::min<u32>(frags.max_seq_len, 1000);
 			cascade_tile_params tp;
-			tp.group_words = (64 + (len_cap + 7) / 8 + 2) | 1; // odd: the groups' counters start in different banks
+			tp.group_words = (64 + 2 * ((len_cap + 7) / 8) + 4) | 1; // odd: the groups' counters start in different banks
 			const u32 units_per_read = ((frags.max_seq_len + 1) / 2 + 15) / 16;
-			tp.seq_capacity_units = frags.canonical_seq_layout && (size_t) units_per_read * 2 * CASCADE_GROUPS * 16 <= 96 * 1024 ? units_per_read * 2 * CASCADE_GROUPS : 0;
+			tp.seq_capacity_units = frags.canonical_seq_layout && (size_t) units_per_read * 2 * CASCADE_GROUPS * 16 <= 96 * 1024 ? units_per_read * 2 * CASCADE_GROUPS_PER_WARP : 0;
 			tp.n_seq_units = (u32) (frags.n_seq_bytes / 16);
-			const size_t shared_bytes = (size_t) tp.seq_capacity_units * 16 + (size_t) tp.group_words * 4 * CASCADE_GROUPS;
+			const size_t shared_bytes = (size_t) tp.seq_capacity_units * 16 * (CASCADE_THREADS / 32) + (size_t) tp.group_words * 4 * CASCADE_GROUPS;
 			if (shared_bytes != cascade_smem_bytes) { // function attributes and occupancy are per device: cached in the context
 				ARB_CUDA_CHECK(cudaFuncSetAttribute(k_cascade_sequences, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) std::max<size_t>(shared_bytes, 48 * 1024)));
 				int per_sm = 0, n_sm = 0;
@@ -355,7 +392,7 @@ void engine::run_read_filters() {
 				ARB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
 				cascade_resident_blocks = (u32) std::max(1, per_sm) * (u32) n_sm; cascade_smem_bytes = shared_bytes;
 			}
-			const u32 n_tiles = (n + CASCADE_GROUPS - 1) / CASCADE_GROUPS;
+			const u32 n_tiles = (n + CASCADE_GROUPS - 1) / CASCADE_GROUPS; // block-sized chunks of the warps' tiles
 			const u32 grid = std::min<u32>(n_tiles, cascade_resident_blocks); // persistent: SM count x resident blocks per SM
 			k_cascade_sequences<<<grid, CASCADE_THREADS, shared_bytes, ex.stream>>>(p, f, annot.view(), needs.ptr(), tp);
 			ARB_CUDA_CHECK(cudaGetLastError());
@@ -363,7 +400,7 @@ void engine::run_read_filters() {
 		}
 #else
 		cascade_sequences_fn sf = {p, f, annot.view(), needs.ptr()};
-		for_each_scratch<256>(ex, n, sf); // 64 counters + dense codes of reads up to 500 bases
+		for_each_scratch<384>(ex, n, sf); // 64 counters + dense codes + predecessor masks of reads up to 1,000 bases
 #endif
 		timings.cascade_sequences_ms = t_seq.stop();
 		timings.classify_ms = t_cls.stop();

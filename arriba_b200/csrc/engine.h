@@ -96,8 +96,12 @@ public:
 	~engine();
 	void set_contigs(const arb_contigs& c);
 	void set_annotation(const arb_annotation& a);
+	void set_contig_flags(const u8* flags, u32 n);
 	void set_params(const arb_params& p) { params = p; }
-	void push_chunk(const arb_soa_chunk& c);
+	void push_chunk(const arb_soa_chunk& c) { push_chunk_begin(c); push_chunk_end(c); }
+	void push_chunk_begin(const arb_soa_chunk& c); // everything but the annotation columns (aflags, gene sets), asynchronously on the copy stream
+	void push_chunk_end(const arb_soa_chunk& c);   // the annotation columns; returns when the whole table is resident
+	exec_ctx copy_ex; bool push_open; // copy stream: H2D of a chunk overlaps with host work (annotation) and with kernels on `ex`
 	void run_read_filters();
 	void get_fragment_filters(u8* filter_out, u8* early_out);
 	void set_fragment_filters(const u8* filter);
@@ -115,10 +119,10 @@ public:
 	dbuf<u32> merge_log; u32 merge_log_n;
 	// k-mer index / re-alignment
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
-	u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
+	u64 push_alignments, push_bases; u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
 	size_t cascade_smem_bytes; u32 cascade_resident_blocks; // launch shape of the sequence kernel on this context's device
 	int device;
-	int mismap_budget, mismap_spawn_budget, mismap_min_blocks; u32 mismap_lanes, mismap_task_lanes, mismap_table_slots, homolog_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
+	bool mismap_group_pass; int mismap_budget, mismap_spawn_budget, mismap_min_blocks; u32 mismap_lanes, mismap_task_lanes, mismap_table_slots, homolog_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
 	void set_splice_sites(const u32* off, const i32* sites);
 	u64 build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs);

@@ -24,6 +24,7 @@ typedef uint8_t u8;
 typedef uint16_t u16;
 typedef uint32_t u32;
 typedef uint64_t u64;
+typedef int16_t i16;
 typedef int32_t i32;
 typedef int64_t i64;
 

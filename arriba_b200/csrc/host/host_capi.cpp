@@ -47,6 +47,7 @@ int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
 	*out = NULL;
 	try {
 		if (!o->bam_file || !o->gtf_file || !o->assembly_file) throw std::runtime_error("bam_file, gtf_file and assembly_file are mandatory");
+		arb_set_host_memory_device(o->device); // the device whose context page-locks the recycled host blocks
 		arb_pipeline* x = new arb_pipeline();
 		run_options& r = x->p.opt;
 		r.bam_file = o->bam_file; r.gtf_file = o->gtf_file; r.assembly_file = o->assembly_file;
@@ -82,6 +83,7 @@ int arb_pipeline_step(arb_pipeline* x, int step) {
 	PIPE_END(x)
 }
 
+int arb_pipeline_plan_shard(arb_pipeline* x, int world) { PIPE_BEGIN(x) x->p.shard_planned = world > 1; PIPE_END(x) }
 int arb_pipeline_set_shard(arb_pipeline* x, int rank, int world) { PIPE_BEGIN(x) x->p.set_shard(rank, world); PIPE_END(x) }
 int arb_pipeline_shard_members(arb_pipeline* x, int rank, const uint32_t** members, uint64_t* n) {
 	PIPE_BEGIN(x)

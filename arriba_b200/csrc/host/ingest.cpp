@@ -2,6 +2,7 @@
 // (every alignment of a read name is handled by the same worker, so mate collation and "first insertion wins" stay local),
 // and the fragments are finally ordered by name, which is the order every later stage relies on.
 #include "ingest.h"
+#include <set>
 #include "../annot_hd.h"
 #include <zlib.h>
 #include <fcntl.h>
@@ -25,8 +26,10 @@ namespace arb { namespace host {
 namespace {
 struct host_block_pool {
 	std::mutex lock; std::vector<std::pair<size_t, void*> > free_blocks; size_t held;
+	std::set<void*> from_backend; // blocks obtained from the backend (page-locked memory in the CUDA library): they go back through it
 	host_block_pool(): held(0) {}
 };
+void* (*g_backend_alloc)(size_t) = NULL; void (*g_backend_free)(void*) = NULL;
 host_block_pool& block_pool() { static host_block_pool* p = new host_block_pool(); return *p; } // never destroyed: blocks may be returned during static destruction
 }
 void* host_block_get(size_t bytes, size_t& granted) {
@@ -38,22 +41,29 @@ void* host_block_get(size_t bytes, size_t& granted) {
 			void* p = pool.free_blocks[k].second; pool.free_blocks[k] = pool.free_blocks.back(); pool.free_blocks.pop_back(); pool.held -= bytes; return p;
 		}
 	}
+	if (g_backend_alloc) { // page-locked: the columns built in such blocks are copied to the device asynchronously at full PCIe speed, and the blocks are recycled
+		void* p = g_backend_alloc(bytes);
+		if (p) { std::lock_guard<std::mutex> g(pool.lock); pool.from_backend.insert(p); return p; }
+	}
 	return malloc(bytes);
+}
+static void release_block(host_block_pool& pool, void* p) { // pool.lock held
+	std::set<void*>::iterator it = pool.from_backend.find(p);
+	if (it != pool.from_backend.end()) { pool.from_backend.erase(it); g_backend_free(p); } else free(p);
 }
 void host_block_put(void* p, size_t granted) {
 	host_block_pool& pool = block_pool();
-	{
-		std::lock_guard<std::mutex> g(pool.lock);
-		if (pool.held + granted <= ((size_t) 64 << 30)) { pool.free_blocks.push_back(std::make_pair(granted, p)); pool.held += granted; return; }
-	}
-	free(p);
+	std::lock_guard<std::mutex> g(pool.lock);
+	if (pool.held + granted <= ((size_t) 64 << 30)) { pool.free_blocks.push_back(std::make_pair(granted, p)); pool.held += granted; return; }
+	release_block(pool, p);
 }
 void host_block_trim() {
 	host_block_pool& pool = block_pool();
 	std::lock_guard<std::mutex> g(pool.lock);
-	for (size_t k = 0; k < pool.free_blocks.size(); ++k) free(pool.free_blocks[k].second);
+	for (size_t k = 0; k < pool.free_blocks.size(); ++k) release_block(pool, pool.free_blocks[k].second);
 	pool.free_blocks.clear(); pool.held = 0;
 }
+void set_host_block_backend(void* (*alloc)(size_t), void (*release)(void*)) { g_backend_alloc = alloc; g_backend_free = release; }
 
 static void fail(const std::string& m) { throw std::runtime_error(m); }
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -29,6 +29,8 @@ struct coverage_windows { // 20 bp windows (read_stats.hpp:14)
 void* host_block_get(size_t bytes, size_t& granted);
 void host_block_put(void* p, size_t granted);
 void host_block_trim();
+// where fresh blocks come from (default: malloc). The CUDA library installs cudaHostAlloc / cudaFreeHost (capi.cu); a NULL result falls back to malloc.
+void set_host_block_backend(void* (*alloc)(size_t), void (*release)(void*));
 
 // vector whose resize() leaves new elements uninitialised: the large columns are first touched (and zeroed where needed) by the threads that fill them
 template <class T> struct default_init_allocator {

@@ -46,6 +46,7 @@ void pipeline::ingest() {
 	read_chimeric_alignments(opt.bam_file, ref, io, frags, coverage, istats);
 	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")";
 	say(s.str());
+	if (!shard_planned && (getenv("ARB_EARLY_UPLOAD") == NULL || atoi(getenv("ARB_EARLY_UPLOAD")) != 0)) begin_upload();
 	t_ingest = now_s() - t0;
 }
 
@@ -74,17 +75,44 @@ void pipeline::annotate() {
 	t_annotate = now_s() - t0;
 }
 
-void pipeline::upload() {
-	const double t0 = now_s();
+void pipeline::upload_reference() {
 	if (!ctx) { if (arb_ctx_create(&ctx, opt.device) != 0) throw std::runtime_error(arb_last_error(NULL)); }
 	check(ctx, arb_set_params(ctx, &opt.params), "arb_set_params");
-	if (!reference_on_device) {
+	if (reference_on_device) return;
 	const u32 nc = (u32) ref.contig_ids.size();
 	std::vector<const char*> seqs(nc, (const char*) NULL);
 	for (u32 c = 0; c < nc; ++c) if (ref.has_sequence(c)) seqs[c] = ref.sequence(c);
 	arb_contigs contigs = {nc, ref.contig_flags.data(), ref.seq_len.data(), seqs.data()};
 	check(ctx, arb_set_contigs(ctx, &contigs), "arb_set_contigs");
+	reference_on_device = true;
+}
+
+arb_soa_chunk pipeline::chunk_of(fragment_table& frags) {
+	arb_soa_chunk c;
+	c.n_fragments = frags.n; c.n_aln = frags.n_aln.data(); c.fflags = frags.fflags.data(); c.filter = frags.filter.data();
+	c.contig = frags.contig.data(); c.start = frags.start.data(); c.end = frags.end.data(); c.aflags = frags.aflags.data();
+	c.cigar_off = frags.cigar_off.data(); c.cigar_cnt = frags.cigar_cnt.data(); c.seq_off = frags.seq_off.data(); c.seq_len = frags.seq_len.data();
+	c.genes_off = frags.genes_off.data(); c.genes_cnt = frags.genes_cnt.data();
+	c.cigar = frags.cigar.data(); c.n_cigar = frags.cigar.size(); c.seq = frags.seq.data(); c.n_seq_bytes = frags.seq.size(); c.genes = frags.genes.data(); c.n_genes = frags.genes.size();
+	return c;
+}
+
+// end of ingest: the genome and every column ingest produced start their way to the device while the host annotates (the gene sets follow in upload())
+void pipeline::begin_upload() {
+	ref.set_contig_flags(opt.interesting_contigs, opt.viral_contigs); // the contig table is complete once the BAM header has been read
+	ref.flatten();
+	upload_reference();
+	arb_soa_chunk c = chunk_of(frags);
+	check(ctx, arb_push_chunk_begin(ctx, &c), "arb_push_chunk_begin");
+	upload_begun = true;
+}
+
+void pipeline::upload() {
+	const double t0 = now_s();
+	upload_reference();
+	{ // annotation: after the dummy genes were added, and the contig flags with the per-sample verdicts on viral contigs
 	arb_annotation a;
+	const u32 nc = (u32) ref.contig_ids.size();
 	a.n_genes = (u32) ref.genes.size(); a.gene_contig = ref.f_gene_contig.data(); a.gene_start = ref.f_gene_start.data(); a.gene_end = ref.f_gene_end.data();
 	a.gene_strand = ref.f_gene_strand.data(); a.gene_exonic_length = ref.f_gene_exonic_length.data(); a.gene_flags = ref.f_gene_flags.data();
 	a.n_exons = (u32) ref.exons.size(); a.exon_gene = ref.f_exon_gene.data(); a.exon_start = ref.f_exon_start.data(); a.exon_end = ref.f_exon_end.data();
@@ -93,16 +121,13 @@ void pipeline::upload() {
 	a.exon_region_begin = ref.exon_index.begin.data(); a.exon_region_end = ref.exon_index.end.data(); a.exon_region_off = ref.exon_index.off.data(); a.exon_region_items = ref.exon_index.items.data();
 	a.gene_region_begin = ref.gene_index.begin.data(); a.gene_region_end = ref.gene_index.end.data(); a.gene_region_off = ref.gene_index.off.data(); a.gene_region_items = ref.gene_index.items.data();
 	check(ctx, arb_set_annotation(ctx, &a), "arb_set_annotation");
-	reference_on_device = true;
+	check(ctx, arb_set_contig_flags(ctx, ref.contig_flags.data(), nc), "arb_set_contig_flags");
 	}
 	fragment_table& frags = shard_world > 1 ? local : this->frags; // a sharded run uploads its own part only
-	arb_soa_chunk c;
-	c.n_fragments = frags.n; c.n_aln = frags.n_aln.data(); c.fflags = frags.fflags.data(); c.filter = frags.filter.data();
-	c.contig = frags.contig.data(); c.start = frags.start.data(); c.end = frags.end.data(); c.aflags = frags.aflags.data();
-	c.cigar_off = frags.cigar_off.data(); c.cigar_cnt = frags.cigar_cnt.data(); c.seq_off = frags.seq_off.data(); c.seq_len = frags.seq_len.data();
-	c.genes_off = frags.genes_off.data(); c.genes_cnt = frags.genes_cnt.data();
-	c.cigar = frags.cigar.data(); c.n_cigar = frags.cigar.size(); c.seq = frags.seq.data(); c.n_seq_bytes = frags.seq.size(); c.genes = frags.genes.data(); c.n_genes = frags.genes.size();
-	check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+	arb_soa_chunk c = chunk_of(frags);
+	if (upload_begun && shard_world == 1) check(ctx, arb_push_chunk_end(ctx, &c), "arb_push_chunk_end");
+	else check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+	upload_begun = false;
 	frags_on_device = true;
 	t_upload = now_s() - t0;
 }

@@ -6,6 +6,27 @@
 
 namespace arb {
 
+#ifdef ARB_DEVICE_BUILD
+// pass 1 of the re-alignment: MISMAP_LANES lanes per (candidate, read) item, worklist of continuations in shared memory (mismap_hd.h, evaluate_group)
+static const u32 MISMAP_LANES = 8, MISMAP_THREADS = 256, MISMAP_GROUPS = MISMAP_THREADS / MISMAP_LANES, MISMAP_WORKLIST = 64;
+__global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
+	__shared__ realign_work tasks[MISMAP_GROUPS][MISMAP_WORKLIST];
+	__shared__ u32 tops[MISMAP_GROUPS];
+	const u32 group = threadIdx.x / MISMAP_LANES;
+	lane_group g; g.lane = threadIdx.x % MISMAP_LANES; g.lanes = MISMAP_LANES; g.mask = ((1u << MISMAP_LANES) - 1u) << ((threadIdx.x & 31u) / MISMAP_LANES * MISMAP_LANES);
+	const u32 j = blockIdx.x * MISMAP_GROUPS + group;
+	if (j >= n_items || it.skip(j)) return;
+	const u32 i = it.item_frag[j];
+	if (((const volatile u8*) it.mismapper)[i]) return; // another candidate's evaluation of this fragment already decided (the label is an OR)
+	realign_worklist wl = {tasks[group], &tops[group], MISMAP_WORKLIST};
+	const u32 verdict = evaluate_group(g, it, j, wl, budget);
+	if (g.lane == 0) {
+		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
+		else if (verdict == REALIGN_EXHAUSTED) heavy[atomicAdd(n_heavy, 1u)] = j;
+	}
+}
+#endif
+
 void engine::set_splice_sites(const u32* off, const i32* sites) {
 	splice_off.upload(ex, off, (size_t) annot.n_genes + 1);
 	splice_sites.upload(ex, sites, off[annot.n_genes]);
@@ -107,10 +128,19 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	// pass 1: a thread per item, bounded; pass 2: the few items stuck in repeats, `lanes` threads each (mismap_hd.h, realign_ctl)
 	dbuf<u32> heavy(I), n_heavy(1);
 	n_heavy.zero(ex, 1);
-	mismap_item_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
 	stage_timer t1(ex);
 	auto launch = [&](u32 n, const auto& fn) { if (mismap_min_blocks >= 4) for_each_occ<4>(ex, n, fn); else if (mismap_min_blocks == 3) for_each_occ<3>(ex, n, fn); else for_each(ex, n, fn); };
-	launch(I, mi);
+	if (mismap_group_pass) {
+#ifdef ARB_DEVICE_BUILD
+		if (I) { k_mismap_items<<<(I + MISMAP_GROUPS - 1) / MISMAP_GROUPS, MISMAP_THREADS, 0, ex.stream>>>(items, I, mismap_budget, heavy.ptr(), n_heavy.ptr()); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+#else
+		mismap_item_group_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
+		for_each(ex, I, mi);
+#endif
+	} else { // ARB_MISMAP_GROUP=0: the one-thread-per-item pass with device recursion (kept for comparison)
+		mismap_item_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
+		launch(I, mi);
+	}
 	timings.mismappers_pass1_ms = t1.stop();
 	u32 H = 0; n_heavy.download(ex, &H, 1);
 	stage_timer t2(ex);

@@ -8,6 +8,7 @@
 #include "model.h"
 #include "annot_hd.h"
 #include "prims.h"
+#include "read_filters.h"
 #include <math.h>
 
 #ifdef ARB_COST_PROBE
@@ -345,6 +346,160 @@ struct mismap_items {
 	}
 };
 
+// ---- pass 1 by a GROUP of lanes per item, without recursion -------------------------------------------------------------------------------------------
+// The search is an OR over (read position, k-mer hit) pairs and over the continuations they start (a continuation = the same search from a later read
+// position with a lower bound on the hits). Read positions are independent of each other -- score and skipped bases at position p follow from p alone -- so
+// the lanes of a group take the positions of a search in turn, and a continuation is not called but pushed on the group's small worklist (shared memory)
+// and searched by the whole group later. No device recursion, no per-thread memo in local memory; the order of evaluation differs from the reference's,
+// the result (an OR) does not. An item that overflows the worklist or the step budget goes to the cooperative pass 2 like before.
+struct realign_work { i32 gene_pos; i16 score; u16 read_pos; u16 gene_k; u8 segment, rc_deletions /* bit 7 strand, bits 0..6 deletions left */; };
+struct realign_worklist { realign_work* tasks; u32* top; u32 capacity; };
+ARB_HD u32 worklist_fetch_add(u32* p, u32 v) {
+#ifdef __CUDA_ARCH__
+	return atomicAdd(p, v);
+#else
+	const u32 old = *p; *p = old + v; return old;
+#endif
+}
+ARB_HD bool realign_can_start(int score, int read_pos, int len, int min_score) { return read_pos + 8 < len && read_pos + min_score <= len + score + 16; } // filter_mismappers.cpp:90-94
+ARB_HD void worklist_push(const realign_worklist& wl, const realign_work& current, int score, int read_pos, int gene_pos, int max_deletions, int len, int min_score) {
+	if (!realign_can_start(score, read_pos, len, min_score)) return; // the continuation would return at once
+	const u32 slot = worklist_fetch_add(wl.top, 1);
+	if (slot >= wl.capacity) return; // noticed by the group when it reads `top` next: the item goes to pass 2
+	realign_work t = current; t.score = (i16) score; t.read_pos = (u16) read_pos; t.gene_pos = gene_pos; t.rc_deletions = (u8) ((current.rc_deletions & 0x80u) | (u32) max_deletions);
+	wl.tasks[slot] = t;
+}
+// 8-mer (2 bits per base) of the read slice at position r, on the strand of the search
+ARB_HD u32 env_kmer(const realign_env& env, u32 r) {
+	if (!env.rc) return nt16_dense2(nt16_window(env.seq, 0x7fffffffu, (i32) (env.off + r)));
+	// reverse strand: bases r..r+7 are the complements of the stored bases off+len-1-r .. off+len-8-r: bit reversal of the word reverses the order of the nibbles
+	// and complements A/C/G/T/N; every other code keeps more than one bit and maps to 3 like the character it stands for
+	return nt16_dense2(brev32(nt16_window(env.seq, 0x7fffffffu, (i32) (env.off + env.len - 8 - r))));
+}
+// one search (top level or continuation) by the lanes of a group; returns whether THIS lane found a placement
+ARB_HD bool realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, u32& steps) {
+	const u8* const seq = env.seq; const u32 off = env.off; const bool rc = env.rc; const int len = (int) env.len;
+	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
+	const i32 wstart = env.wstart, wend = env.wend; const int min_score = env.min_score;
+	const u32* const g4 = env.g4; const char* const ref = env.ref;
+	const int read_pos0 = task.read_pos, score0 = task.score, gene_pos = task.gene_pos, max_deletions = task.rc_deletions & 0x7f;
+	const bool leading = read_pos0 == 0; // every base before the seed was skipped: no penalty for them (local alignment start)
+	for (int read_pos = read_pos0 + (int) g.lane; ; read_pos += (int) g.lanes) {
+		const int skipped = read_pos - read_pos0, score = score0 - skipped;
+		if (!realign_can_start(score, read_pos, len, min_score)) return false; // the valid positions are a prefix
+		const u32 km = env_kmer(env, (u32) read_pos);
+		const u32 lo = bucket[km], hi = bucket[km + 1];
+		if (lo == hi) continue;
+		for (u32 h = lower_bound_i32(pos, lo, hi, gene_pos); h < hi; ++h) {
+			const int hit = pos[h];
+			if (hit >= wend) break;
+			++steps;
+			int ext = score + 8;
+			if (leading) ext += skipped;
+			if (ext >= min_score) return true;
+			{ // extend to the left over the skipped bases, one mismatch allowed
+				int r = read_pos - 1, gp = hit - 1; u32 mm = 0;
+				while (r >= read_pos - skipped && gp >= wstart) {
+					if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
+					else if (++mm > 1) break;
+					--r; --gp;
+				}
+			}
+			{ // extend to the right; a spliced continuation at splice sites and one deletion at the first mismatch go to the worklist
+				int r = read_pos + 8, gp = hit + 8; u32 mm = 0, consecutive = 0;
+				u32 ss = lower_bound_i32(env.splice, 0, env.n_splice, gp - 1);
+				i32 next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff;
+				while (r < len && gp <= wend) {
+					++steps;
+					if (gp - 1 >= next_site) {
+						if (gp - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
+						if (gp - 1 == next_site) worklist_push(wl, task, ext, r, gp, max_deletions, len, min_score);
+					}
+					if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
+					else {
+						if (++mm == 1 && max_deletions > 0 && len >= 30) worklist_push(wl, task, ext, r, gp, max_deletions - 1, len, min_score);
+						--ext;
+						if (++consecutive >= 4) break;
+					}
+					++r; ++gp;
+				}
+			}
+		}
+	}
+}
+
+// filter_mismappers.cpp:247-270 by a group: the lanes share the clipped bases
+ARB_HD bool extends_linearly_group(const lane_group& g, const frag_view& f, const annot_view& an, u32 a /* SPLIT_READ */) {
+	const u8* seq = f.sq(a); const u32 len = f.seq_len[a];
+	const char* ref = an.assembly + an.contig_seq_off[f.contig[a]]; const i32 clen = (i32) an.contig_len[f.contig[a]];
+	int n; u32 matches = 0;
+	if (f.fwd(a)) {
+		const u32 pre = f.preclip(a);
+		n = hd_min((int) pre, f.start[a]);
+		for (int i = (int) g.lane; i < n; i += (int) g.lanes) if (nt16_char(nt16_at(seq, pre - n + i)) == ref[f.start[a] - n + i]) ++matches;
+	} else {
+		const u32 post = f.postclip(a);
+		n = hd_min((int) post, clen - f.end[a] - 2);
+		if (n < 0) n = (int) post; // clipped segment runs over the contig end: the reference compares the whole clipped segment (std::string::substr with a huge count)
+		for (int i = (int) g.lane; i < n; i += (int) g.lanes) { const i32 gp = f.end[a] + 1 + i; if (gp < clen && nt16_char(nt16_at(seq, len - post + i)) == ref[gp]) ++matches; }
+	}
+	matches = g.sum(matches);
+#ifdef __CUDA_ARCH__
+	return (double) matches >= floor((double) __fmul_rn((float) (u32) n, 0.7f));
+#else
+	volatile float prod = (float) (u32) n * 0.7f;
+	return (double) matches >= floor((double) prod);
+#endif
+}
+
+enum { REALIGN_UNDECIDED_NO = 0, REALIGN_FOUND = 1, REALIGN_EXHAUSTED = 2 };
+// one item by a group: 0 = not mis-mapped, 1 = mis-mapped, 2 = gave up (worklist or budget), re-aligned cooperatively in pass 2
+ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, int budget) {
+	if (g.lane == 0) *wl.top = 0;
+	g.sync();
+	if (it.item_kind[j] == 0 && extends_linearly_group(g, it.f, it.an, it.f.idx(it.item_frag[j], SPLIT_READ))) return REALIGN_FOUND;
+	// top-level searches: both sequences of the item against every gene of the other breakpoint, both strands (filter_mismappers.cpp:189-230, :296-333)
+	u32 n = 0; bool too_many = false;
+	for (u32 x = 0; x < 2 && !too_many; ++x) {
+		const realign_segment s = it.segment(j, x);
+		if (s.read.len >= 300) continue;
+		for (u32 k = 0; k < s.n_genes; ++k) {
+			realign_env env;
+			if (!segment_env(s, k, it.p.max_mate_gap, it.an, it.ix, it.sp, env)) continue;
+			if (!realign_can_start(0, 0, (int) env.len, env.min_score)) continue;
+			if (n + 2 > wl.capacity || k >= 0xFFFFu) { too_many = true; break; }
+			if (g.lane == 0) {
+				realign_work t; t.gene_pos = env.wstart; t.score = 0; t.read_pos = 0; t.gene_k = (u16) k; t.segment = (u8) x; t.rc_deletions = 1;
+				wl.tasks[n] = t; t.rc_deletions = 0x81; wl.tasks[n + 1] = t;
+			}
+			n += 2;
+		}
+	}
+	if (too_many) return REALIGN_EXHAUSTED;
+	if (g.lane == 0) *wl.top = n;
+	g.sync();
+	u32 total_steps = 0;
+	for (;;) {
+		const u32 top = *(volatile u32*) wl.top;
+		if (top == 0) return REALIGN_UNDECIDED_NO;
+		if (top > wl.capacity) return REALIGN_EXHAUSTED; // a continuation did not fit
+		const realign_work task = wl.tasks[top - 1];
+		g.sync();
+		if (g.lane == 0) *wl.top = top - 1;
+		g.sync();
+		const realign_segment s = it.segment(j, task.segment);
+		realign_env env;
+		segment_env(s, task.gene_k, it.p.max_mate_gap, it.an, it.ix, it.sp, env); // it was usable when the task was made
+		if (task.rc_deletions & 0x80u) env.rc = !s.read.rc;
+		u32 steps = 0;
+		const bool found = realign_group(g, env, task, wl, steps);
+		if (g.any(found)) return REALIGN_FOUND;
+		total_steps += g.sum(steps);
+		if (budget > 0 && total_steps > (u32) budget) return REALIGN_EXHAUSTED;
+		g.sync();
+	}
+}
+
 // pass 1: one thread per item with a step budget; items that run out of budget undecided are queued for pass 2
 struct mismap_item_fn {
 	mismap_items it; int budget; u32* heavy; u32* n_heavy;
@@ -359,6 +514,21 @@ struct mismap_item_fn {
 #ifdef ARB_COST_PROBE
 		fprintf(stderr, "COST %u %u %u %llu %d\n", j, it.item_cand[j], (unsigned) it.item_kind[j], arb_cost_probe, (int) bad); arb_cost_probe = 0;
 #endif
+	}
+};
+// pass 1, one lane per item (host build; the device runs k_mismap_items with groups of lanes)
+struct mismap_item_group_fn {
+	mismap_items it; int budget; u32* heavy; u32* n_heavy;
+	ARB_HD void operator()(u32 j) const {
+		if (it.skip(j)) return;
+		const u32 i = it.item_frag[j];
+		if (((const volatile u8*) it.mismapper)[i]) return;
+		realign_work tasks[64]; u32 top = 0;
+		realign_worklist wl = {tasks, &top, 64};
+		lane_group g; g.lane = 0; g.lanes = 1; g.mask = 1;
+		const u32 verdict = evaluate_group(g, it, j, wl, budget);
+		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
+		else if (verdict == REALIGN_EXHAUSTED) heavy[atomic_add_u32(n_heavy, 1)] = j;
 	}
 };
 // pass 2: `lanes` threads per queued item share the top-level k-mer hits; continuations go to the item's registry

@@ -453,49 +453,74 @@ ARB_HD bool low_entropy_mate_exact(const entropy_scopes& sc, const u8* seq, u32*
 	return false;
 }
 
-// Group version. Pass 1 counts EVERY occurrence (overlapping ones too) with the lanes in parallel: an upper bound of the reference's counts, so a mate whose
-// bound stays below all three thresholds is not of low entropy. The few mates that reach a threshold are counted exactly by one lane.
-// `counters`: 64 words of the group, `dense`: one word per 8 bases of the longest read (+1).
+// Group version, exact. Whether the k-mer at position p is counted depends only on the two positions before it:
+//   counted[p] = !((km[p] == km[p-1] && counted[p-1]) || (km[p] == km[p-2] && counted[p-2]))
+// and km[p] == km[p-1] needs four equal bases in a row, km[p] == km[p-2] a period-2 stretch of five: in ordinary reads 30 of 32 positions are counted
+// unconditionally. The lanes take the 8-position words of the read in turn. Pass A stores per word which positions equal a predecessor; in pass B a lane
+// walks back to the nearest word without such positions (after it everything is counted), replays the few words in between to learn the state at its own
+// word, and adds its counted k-mers to the group's 64 counters with shared-memory atomics. Counters start at 512 - threshold per scope (three 10-bit fields),
+// so "some scope reached its threshold" is one OR over the counters at the end -- counts only grow, the reference's early exit sees the same.
+// `counters`: 64 words of the group, `dense`: two words per 8 bases of the longest read (+2): 2-bit codes, then the predecessor masks.
+ARB_HD void entropy_replay_word(u32 m, u32& c1, u32& c2, u32& counted) { // m: bit 14-2j = equals predecessor at distance 1, bit 30-2j = at distance 2 (position j of the word)
+	counted = 0;
+	#pragma unroll
+	for (u32 j = 0; j < 8; ++j) {
+		const u32 e1 = m >> (14 - 2 * j) & 1u, e2 = m >> (30 - 2 * j) & 1u;
+		const u32 c = ((e1 & c1) | (e2 & c2)) ^ 1u;
+		counted |= c << j; c2 = c1; c1 = c;
+	}
+}
 ARB_HD bool low_entropy_mate_group(const lane_group& g, const entropy_scopes& sc, const u8* seq, u32* counters, u32* dense) {
 	const u32 len = sc.len;
-	if (len < 3) return false;
-	bool suspicious = len > 500; // every occurrence is counted here: a 10-bit field (512 - threshold + count) must not wrap. Longer reads: exact count only
-	if (!suspicious) {
-		const u32 start_value = (512 - sc.max_all) | (512 - sc.max_1) << 10 | (512 - sc.max_2) << 20, reached = 1u << 9 | 1u << 19 | 1u << 29;
-		const u32 n_words = ((len + 31) / 32) * 4, used_words = (len + 7) / 8;
-		for (u32 k = g.lane; k < 64; k += g.lanes) counters[k] = start_value;
-		for (u32 w = g.lane; w <= used_words; w += g.lanes) dense[w] = nt16_dense2(nt16_word(seq, w, n_words));
-		g.sync();
-		// positions of window x: a_x <= pos < b_x (pos + 1 >= s && pos < e)
-		const i32 a1 = (i32) hd_max(sc.s1, 1u) - 1, b1 = sc.e1 + 1 > sc.s1 ? (i32) sc.e1 : 0, a2 = (i32) hd_max(sc.s2, 1u) - 1, b2 = sc.e2 + 1 > sc.s2 ? (i32) sc.e2 : 0;
-		const i32 last = (i32) len - 3; // positions 0 .. last-1 are examined (the last k-mer never is, filter_low_entropy.cpp:77)
-		for (u32 w = g.lane; (i32) (8 * w) < last; w += g.lanes) {
-			const i32 p0 = (i32) (8 * w);
-			const u32 d = dense[w] << 16 | dense[w + 1]; // bases p0 .. p0+15, two bits each, first base on top
-			const u32 v = (u32) hd_min(8, last - p0);   // examined positions of this word
-			#define ARB_RANGE_MASK(a_, b_) ((((1u << (u32) hd_min(hd_max((b_) - p0, 0), 8)) - 1u) & ~((1u << (u32) hd_min(hd_max((a_) - p0, 0), 8)) - 1u)))
-			const u32 m = ARB_RANGE_MASK(a1, b1) | ARB_RANGE_MASK(a2, b2) << 10; // bit j: position p0+j in window 1, bit 10+j: in window 2
-			#undef ARB_RANGE_MASK
-			#pragma unroll
-			for (u32 j = 0; j < 8; ++j) {
-				if (j < v) {
-					const u32 km = d >> (26 - 2 * j) & 63u;
-					group_add(&counters[km], 1u + ((m >> j & 0x401u) << 10));
-				}
-			}
-		}
-		g.sync();
-		u32 acc = 0;
-		for (u32 k = g.lane; k < 64; k += g.lanes) acc |= counters[k];
-		suspicious = g.any((acc & reached) != 0);
-		g.sync();
+	if (len < 4) return false; // no position is examined (pos + 3 < len)
+	if (len > 1000) { // a 10-bit field (512 - threshold + count) could wrap: the plain sequential count
+		bool hit = false;
+		if (g.lane == 0) hit = low_entropy_mate_exact(sc, seq, counters, 1);
+		hit = g.any(hit); g.sync();
+		return hit;
 	}
-	if (!suspicious) return false;
-	bool hit = false;
-	if (g.lane == 0) hit = low_entropy_mate_exact(sc, seq, counters, 1);
-	hit = g.any(hit);
+	const u32 start_value = (512 - sc.max_all) | (512 - sc.max_1) << 10 | (512 - sc.max_2) << 20, reached = 1u << 9 | 1u << 19 | 1u << 29;
+	const u32 n_words = ((len + 31) / 32) * 4, used_words = (len + 7) / 8;
+	const i32 last = (i32) len - 3; // positions 0 .. last-1 are examined (the last k-mer never is, filter_low_entropy.cpp:77)
+	const u32 W = ((u32) last + 7) / 8;
+	u32* const masks = dense + used_words + 2;
+	for (u32 k = g.lane; k < 64; k += g.lanes) counters[k] = start_value;
+	for (u32 w = g.lane; w <= used_words; w += g.lanes) dense[w] = nt16_dense2(nt16_word(seq, w, n_words));
 	g.sync();
-	return hit;
+	for (u32 w = g.lane; w < W; w += g.lanes) { // pass A: which positions repeat the k-mer one or two positions before
+		const u64 d = (u64) (w ? dense[w - 1] : 0u) << 32 | (u64) dense[w] << 16 | dense[w + 1]; // bases 8w-8 .. 8w+15, base t of the window in bits 47-2t, 46-2t
+		const u64 x1 = d ^ d >> 2, x2 = d ^ d >> 4;                                                // field t: base t against base t-1 / t-2
+		const u64 z1 = ~(x1 | x1 >> 1) & 0x555555555555ull, z2 = ~(x2 | x2 >> 1) & 0x555555555555ull; // bit 46-2t: equal
+		u32 e1 = (u32) ((z1 & z1 << 2 & z1 << 4) >> 16) & 0x5555u, e2 = (u32) ((z2 & z2 << 2 & z2 << 4) >> 16) & 0x5555u; // position j of the word (t = 8+j) at bit 14-2j
+		if (w == 0) { e1 &= 0x1555u; e2 &= 0x0555u; } // positions 0 (and 1) have no predecessor at that distance
+		masks[w] = e1 | e2 << 16;
+	}
+	g.sync();
+	// positions of window x: a_x <= pos < b_x (pos + 1 >= s && pos < e)
+	const i32 a1 = (i32) hd_max(sc.s1, 1u) - 1, b1 = sc.e1 + 1 > sc.s1 ? (i32) sc.e1 : 0, a2 = (i32) hd_max(sc.s2, 1u) - 1, b2 = sc.e2 + 1 > sc.s2 ? (i32) sc.e2 : 0;
+	for (u32 w = g.lane; w < W; w += g.lanes) { // pass B
+		u32 ws = w;
+		while (ws > 0 && masks[ws - 1] != 0) --ws;
+		u32 c1 = ws ? 1u : 0u, c2 = c1, counted;
+		for (u32 u = ws; u < w; ++u) entropy_replay_word(masks[u], c1, c2, counted);
+		const u32 m = masks[w];
+		if (m) entropy_replay_word(m, c1, c2, counted); else counted = 0xffu;
+		const i32 p0 = (i32) (8 * w);
+		const u32 d = dense[w] << 16 | dense[w + 1]; // bases p0 .. p0+15
+		counted &= (1u << (u32) hd_min(8, last - p0)) - 1u; // examined positions of this word
+		#define ARB_RANGE_MASK(a_, b_) ((((1u << (u32) hd_min(hd_max((b_) - p0, 0), 8)) - 1u) & ~((1u << (u32) hd_min(hd_max((a_) - p0, 0), 8)) - 1u)))
+		const u32 in = ARB_RANGE_MASK(a1, b1) | ARB_RANGE_MASK(a2, b2) << 10; // bit j: position p0+j in window 1, bit 10+j: in window 2
+		#undef ARB_RANGE_MASK
+		#pragma unroll
+		for (u32 j = 0; j < 8; ++j)
+			if (counted >> j & 1u) group_add(&counters[d >> (26 - 2 * j) & 63u], 1u + ((in >> j & 0x401u) << 10));
+	}
+	g.sync();
+	u32 acc = 0;
+	for (u32 k = g.lane; k < 64; k += g.lanes) acc |= counters[k];
+	const bool low = g.any((acc & reached) != 0);
+	g.sync();
+	return low;
 }
 
 // pointers of the fragment's data as the kernel staged them (shared memory) or where they lie (global memory)

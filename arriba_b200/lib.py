@@ -297,6 +297,7 @@ def _load_pipeline_api(lib):
     lib.arb_pipeline_write_output.argtypes = [C.c_void_p]
     lib.arb_pipeline_candidates.argtypes = [C.c_void_p, _p(Candidates), _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8))]
     lib.arb_pipeline_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.arb_pipeline_plan_shard.argtypes = [C.c_void_p, C.c_int]
     lib.arb_pipeline_shard_members.argtypes = [C.c_void_p, C.c_int, _p(_p(C.c_uint32)), _p(C.c_uint64)]
     lib.arb_pipeline_export_shard.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64)]
     lib.arb_pipeline_import_shards.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64), C.c_uint32]
@@ -353,6 +354,9 @@ class Pipeline:
             self.step(s)
 
     # ---- one sample on several GPUs (include/arriba_b200.h, "One sample on several GPUs"); the transport is the caller's, see sharded.py
+    def plan_shard(self, world):
+        self._check(self.lib.arb_pipeline_plan_shard(self.h, world))
+
     def set_shard(self, rank, world):
         self._check(self.lib.arb_pipeline_set_shard(self.h, rank, world))
 

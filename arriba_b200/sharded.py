@@ -28,6 +28,7 @@ def all_gather_bytes(blob):
 
 def run_sharded(pipeline, rank, world, last_event=None, write_output=True, gather=all_gather_bytes, reference_loaded=False):
     """Runs `pipeline` (an arriba_b200.lib.Pipeline) as rank `rank` of `world`; every rank ends with the complete result, rank 0 writes the files."""
+    pipeline.plan_shard(world)
     for s in (L.STEP_LOAD_REFERENCE, L.STEP_INGEST, L.STEP_ANNOTATE):
         if s == L.STEP_LOAD_REFERENCE and reference_loaded:
             continue

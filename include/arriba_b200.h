@@ -40,6 +40,9 @@ typedef struct arb_contigs {
 	const char* const* sequence;   /* upper-case bases per contig, NULL if not loaded */
 } arb_contigs;
 int arb_set_contigs(arb_ctx* ctx, const arb_contigs* contigs);
+/* per-sample contig flags without re-sending the sequences: bit0 interesting, bit1 viral, bit2 / bit3 = verdicts of filter_top_expressed_viral_contigs /
+   filter_low_coverage_viral_contigs on a viral contig (computed by the caller per contig; the per-fragment rules run in arb_run_read_filters) */
+int arb_set_contig_flags(arb_ctx* ctx, const uint8_t* flags, uint32_t n_contigs);
 
 typedef struct arb_annotation {
 	uint32_t n_genes;              /* gene id == index; ids ascend in creation order (GTF order, then dummy genes) */
@@ -99,6 +102,13 @@ typedef struct arb_soa_chunk {
 	const uint32_t* genes; uint64_t n_genes;     /* gene ids, each set ascending */
 } arb_soa_chunk;
 int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* chunk); /* H2D copy; replaces the resident fragment table */
+/* The same in two parts, so that the copy overlaps the caller's annotation pass: _begin copies everything read_chimeric_alignments produced (all columns but
+ * aflags and the gene sets) asynchronously on the context's copy stream; _end copies aflags / genes_off / genes_cnt / genes and returns when the table is
+ * resident. The columns must stay valid and unchanged (apart from the annotation columns) between the two calls. Copies are asynchronous when the columns
+ * are page-locked; the whole-run driver builds them in page-locked blocks (cudaHostAlloc, recycled across samples). */
+int arb_push_chunk_begin(arb_ctx* ctx, const arb_soa_chunk* chunk);
+int arb_push_chunk_end(arb_ctx* ctx, const arb_soa_chunk* chunk);
+void arb_set_host_memory_device(int device); /* device whose context page-locks the host blocks (one process per GPU: the process's device) */
 
 /* ---- read-level filter cascade ---------------------------------------------------------------------------
  * Replaces filter_duplicates, filter_uninteresting_contigs, filter_viral_contigs, filter_proximal_read_through,
@@ -256,6 +266,7 @@ int arb_pipeline_step(arb_pipeline* p, int step);  /* steps must be run in order
  *   after ARB_STEP_FIND_FUSIONS:  export ARB_EXCHANGE_CANDIDATES, all-gather, import (merges the tables; the rank then holds the complete state)
  * After the second import every rank continues exactly like a single-GPU run; outputs are byte-identical for any world size. */
 enum { ARB_EXCHANGE_LABELS = 0, ARB_EXCHANGE_CANDIDATES = 1 };
+int arb_pipeline_plan_shard(arb_pipeline* p, int world); /* before ARB_STEP_INGEST: the run will be sharded (no early copy of the whole table) */
 int arb_pipeline_set_shard(arb_pipeline* p, int rank, int world);
 int arb_pipeline_shard_members(arb_pipeline* p, int rank, const uint32_t** fragments, uint64_t* n); /* name ranks assigned to `rank`, ascending (any rank may ask) */
 int arb_pipeline_export_shard(arb_pipeline* p, int what, const void** blob, uint64_t* bytes); /* blob stays valid until the next export */
