@@ -6,6 +6,108 @@ namespace arb {
 
 static u32 bits_for(u32 n) { u32 b = 1; while (b < 32 && ((u64) 1 << b) < n) ++b; return b; }
 
+#ifdef ARB_DEVICE_BUILD
+// Pass B on the device: one WARP per unfiltered candidate that has a bucket. The bucket's discordant mates lie in name order in bucket-ordered columns
+// (breakpoints, fragment, label), so a warp reads them coalesced, 32 at a time; the two geometric tests (fusions.cpp:383-398) are independent per mate and
+// are taken with a ballot. The order-dependent part -- the subsampling counters `listed` / `counted` (fusions.cpp:400-406) -- only matters once a counter
+// can reach the threshold inside the chunk: until then every mate that passes is listed (rank = prefix popcount of the ballot); chunks where the threshold
+// is in reach are replayed serially from the ballot (same statements as walk_b_fn, which stays the host-build path and the statement of the rule).
+struct bucket_columns { const i32* bp1; const i32* bp2; const u32* frag; const u8* label; };
+struct gather_bucket_fn { record_view r; const u32* drec; const u32* bperm; i32* bp1; i32* bp2; u32* frag; u8* label;
+	ARB_HD void operator()(u32 p) const { const u32 k = drec[bperm[p]]; bp1[p] = r.bp1[k]; bp2[p] = r.bp2[k]; frag[p] = r.frag[k]; label[p] = (u8) (r.meta[k] >> 8); } };
+struct probe_bucket_fn { // bucket of every candidate pass B looks at (0xFFFFFFFF: none), and the flag of the compaction
+	record_view r; cand_out c; hash_index_view bucket_table; const u32* drec; const u32* bucket_head_scan; u32* bucket; u32* active;
+	ARB_HD void operator()(u32 cand) const {
+		u32 b = 0xFFFFFFFFu;
+		if (c.filter[cand] == F_none) {
+			const u32 d1 = c.dir1[cand], d2 = c.dir2[cand];
+			bucket_probe probe = {r, drec, c.gene1[cand], c.gene2[cand], (d1 ? 1u : 0u) | (d2 ? 2u : 0u)};
+			const u32 slot = bucket_table.find(probe);
+			if (slot != hash_index_view::EMPTY) b = bucket_head_scan[bucket_table.mn[slot]];
+		}
+		bucket[cand] = b; active[cand] = b != 0xFFFFFFFFu; c.n_listd[cand] = 0;
+	}
+};
+static const u32 WALK_B_THREADS = 256;
+__global__ void __launch_bounds__(WALK_B_THREADS) k_walk_b(const u32* active_cands, u32 n_active, const u32* bucket_of_cand, bucket_columns bc, const u32* bseg_off,
+                                                            frag_view f, annot_view an, cand_out c, const u32* listd_off, u32* listd, u32* need_swap, i32 max_mate_gap, u32 threshold, u32 fill) {
+	const u32 warp = (blockIdx.x * WALK_B_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+	if (warp >= n_active) return;
+	const u32 FULL = 0xFFFFFFFFu;
+	const u32 cand = active_cands[warp], b = bucket_of_cand[cand];
+	const u32 g1 = c.gene1[cand], g2 = c.gene2[cand], d1 = c.dir1[cand], d2 = c.dir2[cand];
+	const i32 bp1 = c.bp1[cand], bp2 = c.bp2[cand];
+	const i32 overlap = (c.n_list1[cand] + c.n_list2[cand] > 0) ? 2 : max_mate_gap;
+	const i32 lim1 = d1 == DOWNSTREAM ? bp1 + overlap : bp1 - overlap, lim2 = d2 == DOWNSTREAM ? bp2 + overlap : bp2 - overlap;
+	const i32 g1s = an.gene_start[g1], g1e = an.gene_end[g1], g2s = an.gene_start[g2], g2e = an.gene_end[g2];
+	const bool intragenic = g1 == g2 || (bp1 >= g2s - 10000 && bp1 <= g2e + 10000 && bp2 >= g1s - 10000 && bp2 <= g1e + 10000);
+	u32 listed = 0, counted = 0;
+	i32 an1 = c.anchor1[cand], an2 = c.anchor2[cand];
+	u32 w = fill ? listd_off[cand] : 0;
+	const u32 seg_end = bseg_off[b + 1];
+	bool done = false;
+	for (u32 base = bseg_off[b]; base < seg_end && !done; base += 32) {
+		const u32 p = base + lane;
+		bool pass = false; u32 frag = 0; u8 fl = 0;
+		if (p < seg_end) {
+			const i32 m1 = bc.bp1[p], m2 = bc.bp2[p];
+			pass = ((d1 == DOWNSTREAM && m1 <= lim1) || (d1 == UPSTREAM && m1 >= lim1)) && ((d2 == DOWNSTREAM && m2 <= lim2) || (d2 == UPSTREAM && m2 >= lim2)) &&
+			       ((!intragenic && !(m1 >= g2s && m1 <= g2e) && !(m2 >= g1s && m2 <= g1e)) || (hd_abs(bp1 - m1) <= max_mate_gap && hd_abs(bp2 - m2) <= max_mate_gap));
+			if (pass) { frag = bc.frag[p]; fl = bc.label[p]; }
+		}
+		u32 mask = __ballot_sync(FULL, pass);
+		if (mask == 0) continue;
+		const u32 none_mask = __ballot_sync(FULL, pass && fl == F_none);
+		if (listed >= threshold) { // labelled mates are no longer listed (fusions.cpp:400): only the unlabelled ones count from here on
+			mask = none_mask; pass = pass && fl == F_none;
+			if (mask == 0) continue;
+		}
+		// the values the anchors and the canonical mate order need, per listed mate
+		i32 v1 = 0, v2 = 0; bool out_of_order = false;
+		if (pass) {
+			u32 x = f.idx(frag, MATE1), y = f.idx(frag, MATE2);
+			const i32 xs = f.start[x], xe = f.end[x], ys = f.start[y], ye = f.end[y];
+			const u16 xc = f.contig[x], yc = f.contig[y];
+			const i32 xb = f.fwd(x) ? xe : xs, yb = f.fwd(y) ? ye : ys;
+			out_of_order = xc > yc || (xc == yc && xb > yb);
+			const i32 s1 = out_of_order ? ys : xs, e1 = out_of_order ? ye : xe, s2 = out_of_order ? xs : ys, e2 = out_of_order ? xe : ye;
+			v1 = d1 == DOWNSTREAM ? s1 : e1; v2 = d2 == DOWNSTREAM ? s2 : e2;
+		}
+		const u32 n_pass = __popc(mask), n_none = __popc(mask & none_mask);
+		const bool zero_value = __any_sync(FULL, pass && (v1 <= 0 || v2 <= 0)); // 0 means "unset" to expand_anchor: such a chunk is replayed statement by statement
+		const bool in_reach = listed >= threshold ? counted + n_none > threshold : listed + n_pass > threshold;
+		if (!in_reach && !zero_value) {
+			if (fill && pass) { listd[w + __popc(mask & ((1u << lane) - 1u))] = frag; if (out_of_order) need_swap[frag] = 1; }
+			w += n_pass; listed += n_pass; counted += n_none;
+			// anchors: minimum (downstream) / maximum (upstream) of the listed mates' values and the anchor so far
+			i32 r1 = pass ? v1 : (d1 == DOWNSTREAM ? 0x7FFFFFFF : (i32) 0x80000000), r2 = pass ? v2 : (d2 == DOWNSTREAM ? 0x7FFFFFFF : (i32) 0x80000000);
+			for (int o = 16; o > 0; o >>= 1) {
+				const i32 t1 = __shfl_xor_sync(FULL, r1, o), t2 = __shfl_xor_sync(FULL, r2, o);
+				r1 = d1 == DOWNSTREAM ? (t1 < r1 ? t1 : r1) : (t1 > r1 ? t1 : r1); r2 = d2 == DOWNSTREAM ? (t2 < r2 ? t2 : r2) : (t2 > r2 ? t2 : r2);
+			}
+			expand_anchor(an1, d1, r1, r1); expand_anchor(an2, d2, r2, r2);
+		} else {
+			for (u32 m = mask; m; m &= m - 1) {
+				const int src = __ffs((int) m) - 1;
+				const u32 fl_s = __shfl_sync(FULL, (u32) fl, src), frag_s = __shfl_sync(FULL, frag, src);
+				const i32 v1_s = __shfl_sync(FULL, v1, src), v2_s = __shfl_sync(FULL, v2, src);
+				const bool ooo_s = __shfl_sync(FULL, (u32) out_of_order, src) != 0;
+				if (fl_s != F_none && listed >= threshold) continue;
+				if (counted >= threshold) { done = true; break; }
+				++listed; if (fl_s == F_none) ++counted;
+				expand_anchor(an1, d1, v1_s, v1_s); expand_anchor(an2, d2, v2_s, v2_s);
+				if (fill && lane == 0) { listd[w] = frag_s; if (ooo_s) need_swap[frag_s] = 1; }
+				++w;
+			}
+		}
+	}
+	if (lane == 0) {
+		if (!fill) c.n_listd[cand] = listed;
+		else { c.discordant_mates[cand] = counted; c.anchor1[cand] = an1; c.anchor2[cand] = an2; }
+	}
+}
+#endif
+
 struct fill_u32_fn { u32* p; u32 v; ARB_HD void operator()(u32 i) const { p[i] = v; } };
 
 void engine::find_fusions(i32 max_mate_gap) {
@@ -102,6 +204,27 @@ void engine::find_fusions(i32 max_mate_gap) {
 	// 6. pass B (count, scan, fill) + canonical mate order
 	cand_out cob = co; cob.n_list1 = n_list1.ptr(); cob.n_list2 = n_list2.ptr(); cob.n_listd = n_listd.ptr();
 	dbuf<u32> need_swap(n); need_swap.zero(ex, n);
+#ifdef ARB_DEVICE_BUILD
+	{
+		dbuf<i32> o_bp1(D), o_bp2(D); dbuf<u32> o_frag(D); dbuf<u8> o_label(D);
+		gather_bucket_fn gb = {r, drec.ptr(), bperm.ptr(), o_bp1.ptr(), o_bp2.ptr(), o_frag.ptr(), o_label.ptr()};
+		for_each(ex, D, gb);
+		dbuf<u32> bucket_of_cand(C), act((size_t) C + 1), active_cands(C);
+		probe_bucket_fn pb = {r, cob, bucket_table.view(), drec.ptr(), bhead.ptr(), bucket_of_cand.ptr(), act.ptr()};
+		for_each(ex, C, pb);
+		exclusive_scan_u32(ex, act.ptr(), act.ptr(), C);
+		u32 A = 0; act.download(ex, &A, 1, C);
+		compact_fn ca = {act.ptr(), NULL, active_cands.ptr(), C};
+		for_each(ex, C, ca);
+		bucket_columns bcols = {o_bp1.ptr(), o_bp2.ptr(), o_frag.ptr(), o_label.ptr()};
+		const u32 blocks = (u32) (((u64) A * 32 + WALK_B_THREADS - 1) / WALK_B_THREADS);
+		if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, NULL, NULL, need_swap.ptr(), max_mate_gap, T, 0); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+		exclusive_scan_u32(ex, n_listd.ptr(), cands.listd_off.ptr(), C);
+		u32 LD = 0; cands.listd_off.download(ex, &LD, 1, C);
+		cands.n_listd = LD; cands.listd.ensure(LD);
+		if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, cands.listd_off.ptr(), cands.listd.ptr(), need_swap.ptr(), max_mate_gap, T, 1); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+	}
+#else
 	walk_b_fn wb = {r, f, an, cob, bucket_table.view(), drec.ptr(), bhead.ptr(), bperm.ptr(), bseg_off.ptr(), NULL, NULL, need_swap.ptr(), max_mate_gap, T, 0};
 	for_each(ex, C, wb);
 	exclusive_scan_u32(ex, n_listd.ptr(), cands.listd_off.ptr(), C);
@@ -109,6 +232,7 @@ void engine::find_fusions(i32 max_mate_gap) {
 	cands.n_listd = LD; cands.listd.ensure(LD);
 	wb.listd_off = cands.listd_off.ptr(); wb.listd = cands.listd.ptr(); wb.fill = 1;
 	for_each(ex, C, wb);
+#endif
 	swap_mates_fn sm = {f, need_swap.ptr(), frags.swapped.ptr()};
 	for_each(ex, n, sm);
 
