@@ -88,6 +88,10 @@ int arb_set_contig_flags(arb_ctx* ctx, const uint8_t* flags, uint32_t n) { ARB_A
 int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk(*c); ARB_API_END(ctx) }
 int arb_push_chunk_begin(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk_begin(*c); ARB_API_END(ctx) }
 int arb_push_chunk_end(arb_ctx* ctx, const arb_soa_chunk* c) { ARB_API_BEGIN(ctx) ctx->e.push_chunk_end(*c); ARB_API_END(ctx) }
+int arb_annotate_pass1(arb_ctx* ctx, const uint8_t* aflags, int32_t strandedness, uint32_t* n_dummy) { ARB_API_BEGIN(ctx) const uint32_t k = ctx->e.annotate_pass1(aflags, strandedness); if (n_dummy) *n_dummy = k; ARB_API_END(ctx) }
+int arb_get_dummy_genes(arb_ctx* ctx, uint16_t* contig, int32_t* start, int32_t* end) { ARB_API_BEGIN(ctx) ctx->e.get_dummy_genes(contig, start, end); ARB_API_END(ctx) }
+int arb_annotate_pass2(arb_ctx* ctx, uint64_t* n_gene_ids) { ARB_API_BEGIN(ctx) const uint64_t k = ctx->e.annotate_pass2(); if (n_gene_ids) *n_gene_ids = k; ARB_API_END(ctx) }
+int arb_get_annotation_columns(arb_ctx* ctx, uint8_t* aflags, uint32_t* genes_off, uint16_t* genes_cnt, uint32_t* genes) { ARB_API_BEGIN(ctx) ctx->e.get_annotation_columns(aflags, genes_off, genes_cnt, genes); ARB_API_END(ctx) }
 int arb_run_read_filters(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.run_read_filters(); ARB_API_END(ctx) }
 int arb_get_fragment_filters(arb_ctx* ctx, uint8_t* f, uint8_t* early) { ARB_API_BEGIN(ctx) ctx->e.get_fragment_filters(f, early); ARB_API_END(ctx) }
 int arb_set_fragment_filters(arb_ctx* ctx, const uint8_t* f) { ARB_API_BEGIN(ctx) ctx->e.set_fragment_filters(f); ARB_API_END(ctx) }

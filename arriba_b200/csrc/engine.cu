@@ -14,7 +14,7 @@ void default_params(arb_params& p) { // options.cpp:71-107
 	p.max_mismapper_fraction = 0.8f; p.max_homolog_identity = 0.3f;
 }
 
-engine::engine(): cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
+engine::engine(): annot_pool_cap(0), n_dummy(0), n_gene_entries(0), push_cigar_ops(0), cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
@@ -159,7 +159,7 @@ void engine::push_chunk_begin(const arb_soa_chunk& c) {
 	u64 n_alignments = 0, bases = 0;
 	for (size_t k = 0; k < n; ++k) n_alignments += c.n_aln[k];
 	for (size_t k = 0; k < 2 * (size_t) n; ++k) bases += c.seq_len[k];
-	push_alignments = n_alignments; push_bases = bases;
+	push_alignments = n_alignments; push_bases = bases; push_cigar_ops = c.n_cigar;
 	timings.h2d_ms = t_h2d.stop(); // waits for part one: the caller's annotation takes far longer than the copy, and the timing stays a pure copy time
 	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes;
 	push_open = true;
@@ -176,13 +176,19 @@ void engine::push_chunk_end(const arb_soa_chunk& c) {
 	frags.genes_off.upload(cx, c.genes_off, 3 * (size_t) n); frags.genes_cnt.upload(cx, c.genes_cnt, 3 * (size_t) n); frags.genes.upload(cx, c.genes, c.n_genes);
 	timings.h2d_ms += t_h2d.stop();
 	timings.h2d_bytes += (u64) n * 3 * (1 + 4 + 2) + c.n_genes * 4;
+	cx.sync();
+	finish_push(c.n_genes);
+}
+
+// the resident table is complete: column budget of the cascade launches for it
+void engine::finish_push(u64 n_gene_ids) {
+	const u32 n = frags.n;
 	// Column budget of SURVEY.md section 8(d): every column read once at its compact width -- 11 B per alignment {contig u16, start, end, flags u8}, CIGAR ops and
 	// gene ids with a 4-byte offset per alignment, 6 B per fragment {rank, flags, label}; sequences at 3 bit/base, gathered reference bases at 2 bit/base.
 	const u64 n_alignments = push_alignments, bases = push_bases;
-	head_bytes = n_alignments * 11 + ((u64) c.n_cigar + n_alignments) * 4 + ((u64) c.n_genes + n_alignments) * 4 + (u64) n * 6;
-	sequence_bytes = bases * 3 / 8 + bases * 2 / 8 + ((u64) c.n_cigar + n_alignments) * 4 + n_alignments * 11 + (u64) n * 2;
+	head_bytes = n_alignments * 11 + (push_cigar_ops + n_alignments) * 4 + (n_gene_ids + n_alignments) * 4 + (u64) n * 6;
+	sequence_bytes = bases * 3 / 8 + bases * 2 / 8 + (push_cigar_ops + n_alignments) * 4 + n_alignments * 11 + (u64) n * 2;
 	timings.classify_algorithmic_bytes = head_bytes + sequence_bytes;
-	cx.sync();
 	push_open = false;
 }
 

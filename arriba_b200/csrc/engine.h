@@ -101,6 +101,11 @@ public:
 	void push_chunk(const arb_soa_chunk& c) { push_chunk_begin(c); push_chunk_end(c); }
 	void push_chunk_begin(const arb_soa_chunk& c); // everything but the annotation columns (aflags, gene sets), asynchronously on the copy stream
 	void push_chunk_end(const arb_soa_chunk& c);   // the annotation columns; returns when the whole table is resident
+	// device-side annotation of the resident chunk (annotate.cu): between the two passes the gene sets live in fixed rows + a pool
+	u32 annotate_pass1(const u8* aflags, int strandedness); void get_dummy_genes(u16* contig, i32* start, i32* end); u64 annotate_pass2();
+	void get_annotation_columns(u8* aflags, u32* genes_off, u16* genes_cnt, u32* genes);
+	dbuf<u32> annot_rows, annot_pool, annot_ctl; dbuf<u16> annot_cnt; u32 annot_pool_cap, n_dummy; u64 n_gene_entries; dbuf<u16> dummy_contig; dbuf<i32> dummy_start, dummy_end;
+	void finish_push(u64 n_gene_ids); u64 push_cigar_ops;
 	exec_ctx copy_ex; bool push_open; // copy stream: H2D of a chunk overlaps with host work (annotation) and with kernels on `ex`
 	void run_read_filters();
 	void get_fragment_filters(u8* filter_out, u8* early_out);

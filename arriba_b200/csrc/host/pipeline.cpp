@@ -69,8 +69,9 @@ void pipeline::annotate() {
 		strandedness = detect_strandedness(*this);
 		say(std::string("Detecting strandedness (") + (strandedness == 1 ? "yes" : strandedness == 2 ? "reverse" : "no") + ")");
 	}
-	if (strandedness != 0) assign_strands(*this, strandedness);
+	if (!upload_begun) begin_upload(); // the passes run on the device over the resident columns (a sharded run annotates the whole table, then re-packs its part)
 	annotate_fragments(*this);
+	whole_table_resident = true;
 	viral_contig_decisions(*this); // per-contig verdicts of the two viral heuristics; no-op without viral contigs
 	t_annotate = now_s() - t0;
 }
@@ -107,10 +108,8 @@ void pipeline::begin_upload() {
 	upload_begun = true;
 }
 
-void pipeline::upload() {
-	const double t0 = now_s();
-	upload_reference();
-	{ // annotation: after the dummy genes were added, and the contig flags with the per-sample verdicts on viral contigs
+// gene / exon tables and their region indices (after annotate(): with the dummy genes)
+void pipeline::send_annotation() {
 	arb_annotation a;
 	const u32 nc = (u32) ref.contig_ids.size();
 	a.n_genes = (u32) ref.genes.size(); a.gene_contig = ref.f_gene_contig.data(); a.gene_start = ref.f_gene_start.data(); a.gene_end = ref.f_gene_end.data();
@@ -121,18 +120,26 @@ void pipeline::upload() {
 	a.exon_region_begin = ref.exon_index.begin.data(); a.exon_region_end = ref.exon_index.end.data(); a.exon_region_off = ref.exon_index.off.data(); a.exon_region_items = ref.exon_index.items.data();
 	a.gene_region_begin = ref.gene_index.begin.data(); a.gene_region_end = ref.gene_index.end.data(); a.gene_region_off = ref.gene_index.off.data(); a.gene_region_items = ref.gene_index.items.data();
 	check(ctx, arb_set_annotation(ctx, &a), "arb_set_annotation");
-	check(ctx, arb_set_contig_flags(ctx, ref.contig_flags.data(), nc), "arb_set_contig_flags");
+}
+
+void pipeline::upload() {
+	const double t0 = now_s();
+	upload_reference();
+	// the contig flags with the per-sample verdicts on viral contigs (the annotation went to the device with annotate())
+	check(ctx, arb_set_contig_flags(ctx, ref.contig_flags.data(), (u32) ref.contig_ids.size()), "arb_set_contig_flags");
+	if (shard_world > 1) { // a sharded run keeps its own part only
+		arb_soa_chunk c = chunk_of(local);
+		check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+		whole_table_resident = false;
+	} else if (!whole_table_resident) { // the complete, annotated table again (end of a sharded run's candidate exchange)
+		arb_soa_chunk c = chunk_of(frags);
+		check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
+		whole_table_resident = true;
 	}
-	fragment_table& frags = shard_world > 1 ? local : this->frags; // a sharded run uploads its own part only
-	arb_soa_chunk c = chunk_of(frags);
-	if (upload_begun && shard_world == 1) check(ctx, arb_push_chunk_end(ctx, &c), "arb_push_chunk_end");
-	else check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
 	upload_begun = false;
 	frags_on_device = true;
 	t_upload = now_s() - t0;
 }
-
-
 
 void pipeline::read_filters() {
 	const double t0 = now_s();

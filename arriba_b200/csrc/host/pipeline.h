@@ -53,13 +53,13 @@ struct pipeline {
 	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
 	pipeline(): ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false), splice_sites_ready(false), events_done(-1),
-	            upload_begun(false), shard_planned(false), shard_rank(0), shard_world(1), frags_on_device(false), reference_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
+	            upload_begun(false), shard_planned(false), whole_table_resident(false), shard_rank(0), shard_world(1), frags_on_device(false), reference_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
 	void annotate();
 	void upload();
-	void upload_reference(); void begin_upload(); arb_soa_chunk chunk_of(fragment_table& t); bool upload_begun, shard_planned; // ingest ends by starting the copy of its columns; annotation overlaps it
+	void upload_reference(); void send_annotation(); void begin_upload(); arb_soa_chunk chunk_of(fragment_table& t); bool upload_begun, shard_planned, whole_table_resident; // ingest ends by starting the copy of its columns; annotation overlaps it
 	void read_filters();
 	void fragment_length();
 	void find_fusions();
@@ -92,7 +92,6 @@ enum { EV_FETCH = 0, EV_MERGE_ADJACENT, EV_MULTIMAPPERS, EV_EVALUE, EV_NON_CODIN
 
 extern const char* const FILTER_NAMES[38];
 int detect_strandedness(pipeline& p);
-void assign_strands(pipeline& p, int strandedness);
 void annotate_fragments(pipeline& p);
 void viral_contig_decisions(pipeline& p); // viral.cpp
 bool estimate_fragment_length(pipeline& p, const u8* early, float& gap_mean, float& gap_stddev, float& read_length_mean);

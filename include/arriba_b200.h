@@ -108,6 +108,19 @@ int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* chunk); /* H2D copy; repla
  * are page-locked; the whole-run driver builds them in page-locked blocks (cudaHostAlloc, recycled across samples). */
 int arb_push_chunk_begin(arb_ctx* ctx, const arb_soa_chunk* chunk);
 int arb_push_chunk_end(arb_ctx* ctx, const arb_soa_chunk* chunk);
+/* ---- annotation of the resident fragments -------------------------------------------------------------------
+ * Replaces the annotation passes of main (source/arriba.cpp:165-325: annotate_alignments per fragment, source/annotation.cpp:431-555; dummy genes for
+ * intergenic breakpoints, arriba.cpp:207-260; second pass :262-319) and assign_strands_from_strandedness (source/read_chimeric_alignments.cpp:775-790).
+ * Call sequence: arb_set_annotation (genes of the GTF) and arb_push_chunk_begin, then
+ *   arb_annotate_pass1  : `aflags` = the alignment flags as ingest left them (3*n); strandedness 0 no, 1 yes, 2 reverse. Returns the number of dummy genes,
+ *   arb_get_dummy_genes : their (contig, start, end) in creation order; the caller appends them to its gene table, rebuilds its gene index and
+ *   arb_set_annotation  : sends the grown table, then
+ *   arb_annotate_pass2  : finishes the gene sets; the resident table is complete (no arb_push_chunk_end). n_gene_ids = size of the gene-id pool,
+ *   arb_get_annotation_columns : the annotation columns for host-side consumers (caller-allocated: 3*n, 3*n, 3*n, n_gene_ids). */
+int arb_annotate_pass1(arb_ctx* ctx, const uint8_t* aflags, int32_t strandedness, uint32_t* n_dummy_genes);
+int arb_get_dummy_genes(arb_ctx* ctx, uint16_t* contig, int32_t* start, int32_t* end);
+int arb_annotate_pass2(arb_ctx* ctx, uint64_t* n_gene_ids);
+int arb_get_annotation_columns(arb_ctx* ctx, uint8_t* aflags, uint32_t* genes_off, uint16_t* genes_cnt, uint32_t* genes);
 void arb_set_host_memory_device(int device); /* device whose context page-locks the host blocks (one process per GPU: the process's device) */
 
 /* ---- read-level filter cascade ---------------------------------------------------------------------------
@@ -200,6 +213,7 @@ typedef struct arb_timings {
 	float cascade_head_ms, cascade_sequences_ms; /* the two launches of the read-level cascade (classify_ms spans both) */
 	uint64_t cascade_queued;    /* fragments the sequence rules (mismatches, low entropy) looked at */
 	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */
+	float annotate_ms;          /* arb_annotate_pass1 + arb_annotate_pass2 (kernels, sorts and scans on the context's stream) */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 /* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver
