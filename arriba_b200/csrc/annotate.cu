@@ -11,7 +11,7 @@
 
 namespace arb {
 
-enum { ANNOT_CAP_PASS1 = 32, ANNOT_CAP_PASS2 = 128 }; // genes under one alignment the passes can hold (loud error beyond)
+enum { ANNOT_CAP_PASS1 = 32, ANNOT_CAP_PASS2 = 65535 }; // genes under one alignment pass 1 can hold / the 16-bit gene count column can express (loud error beyond)
 
 static gene_sets_view sets_view(engine& e) {
 	gene_sets_view v = {e.annot_rows.ptr(), e.annot_cnt.ptr(), e.annot_pool.ptr(), e.annot_ctl.ptr(), e.annot_pool_cap, e.annot_ctl.ptr() + 1};
@@ -79,7 +79,7 @@ u64 engine::annotate_pass2() {
 	const u32 n = frags.n; const size_t A = 3 * (size_t) n;
 	if (A > 0xFFFFFFF0ull) throw arb_error("chunk too large");
 	stage_timer t_all(ex);
-	annotate_pass2_fn<ANNOT_CAP_PASS2> p2 = {annot.view(), frags.view(), sets_view(*this)};
+	annotate_pass2_fn p2 = {annot.view(), frags.view(), sets_view(*this)};
 	for_each(ex, n, p2);
 	check_annotation_errors(*this, "pass 2", ANNOT_CAP_PASS2);
 	dbuf<u32> off(A + 1);

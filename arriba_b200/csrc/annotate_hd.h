@@ -215,25 +215,37 @@ struct dummy_emit_fn {
 	}
 };
 
-// pass 2 of one fragment (arriba.cpp:262-319); `an` now holds the dummy genes
-template <int CAP> struct annotate_pass2_fn {
+// pass 2 of one fragment (arriba.cpp:262-319); `an` now holds the dummy genes. Gene sets are handled as views (pointer, size): a set of pass 1, the item
+// list of the region a breakpoint lies in (the result of a point query, annotation.t.hpp:55-68), or a single picked gene -- nothing is materialised, so a
+// breakpoint covered by hundreds of stacked dummy genes (many reads clipped exactly at the end of a gene region, each the start of a cluster of its own,
+// arriba.cpp:236-256) costs no memory.
+struct gene_list { const u32* v; u32 n; };
+ARB_HD gene_list genes_at(const annot_view& an, u32 contig, i32 pos) {
+	gene_list g = {0, 0};
+	if (contig >= an.n_contigs) return g;
+	const u32 lo = an.gene_region_begin[contig], hi = an.gene_region_begin[contig + 1];
+	const u32 r = region_lower_bound(an.gene_region_end, lo, hi, pos);
+	if (r < hi) { g.v = an.gene_region_items + an.gene_region_off[r]; g.n = an.gene_region_off[r + 1] - an.gene_region_off[r]; }
+	return g;
+}
+struct annotate_pass2_fn {
 	annot_view an; frag_view f; gene_sets_view sets;
 	ARB_HD void operator()(u32 i) const {
 		const u32 na = f.n_aln[i];
 		const u32 a[3] = {f.idx(i, 0), f.idx(i, 1), f.idx(i, 2)};
 		bool changed[3] = {false, false, false};
-		idset<CAP> g[3];
-		for (u32 s = 0; s < na; ++s) sets.load(a[s], g[s]);
+		gene_list g[3] = {{0, 0}, {0, 0}, {0, 0}};
+		u32 single[3]; // a set collapsed to one gene
+		for (u32 s = 0; s < na; ++s) { g[s].v = sets.get(a[s]); g[s].n = sets.cnt[a[s]]; }
 		if (na == 3) {
 			if (g[0].n == 0 || g[1].n == 0) {
 				const i32 bp = f.fwd(a[1]) ? f.start[a[1]] : f.end[a[1]];
-				genes_by_position(an, f.contig[a[1]], bp, bp, g[1]);
-				g[0].n = g[1].n; g[0].overflow = g[1].overflow; for (u32 k = 0; k < g[1].n; ++k) g[0].v[k] = g[1].v[k];
+				g[1] = genes_at(an, f.contig[a[1]], bp); g[0] = g[1];
 				changed[0] = changed[1] = true;
 			}
-			if (g[2].n == 0) { const i32 bp = f.fwd(a[2]) ? f.end[a[2]] : f.start[a[2]]; genes_by_position(an, f.contig[a[2]], bp, bp, g[2]); changed[2] = true; }
+			if (g[2].n == 0) { const i32 bp = f.fwd(a[2]) ? f.end[a[2]] : f.start[a[2]]; g[2] = genes_at(an, f.contig[a[2]], bp); changed[2] = true; }
 		} else {
-			for (u32 s = 0; s < 2; ++s) if (g[s].n == 0) { const i32 bp = f.fwd(a[s]) ? f.end[a[s]] : f.start[a[s]]; genes_by_position(an, f.contig[a[s]], bp, bp, g[s]); changed[s] = true; }
+			for (u32 s = 0; s < 2; ++s) if (g[s].n == 0) { const i32 bp = f.fwd(a[s]) ? f.end[a[s]] : f.start[a[s]]; g[s] = genes_at(an, f.contig[a[s]], bp); changed[s] = true; }
 		}
 		// several dummy genes on one alignment: keep the one that contains the breakpoint (default: MATE1's first gene)
 		const u32 mate1_first = g[0].n ? g[0].v[0] : 0;
@@ -242,7 +254,7 @@ template <int CAP> struct annotate_pass2_fn {
 				const i32 bp = f.fwd(a[s]) ? f.start[a[s]] : f.end[a[s]];
 				u32 pick = s == 0 ? g[0].v[0] : (g[0].n ? g[0].v[0] : mate1_first);
 				for (u32 k = 0; k < g[s].n; ++k) if (an.gene_start[g[s].v[k]] <= bp && an.gene_end[g[s].v[k]] >= bp) pick = g[s].v[k];
-				g[s].clear(); g[s].insert(pick); changed[s] = true;
+				single[s] = pick; g[s].v = &single[s]; g[s].n = 1; changed[s] = true;
 			}
 		}
 		if (na == 3 && g[0].n && g[1].n && g[0].v[0] != g[1].v[0] && (an.gene_flags[g[0].v[0]] & GF_DUMMY) && (an.gene_flags[g[1].v[0]] & GF_DUMMY)) {
@@ -250,11 +262,12 @@ template <int CAP> struct annotate_pass2_fn {
 			u32 pick = g[0].v[0];
 			for (u32 k = 0; k < g[0].n; ++k) if (an.gene_start[g[0].v[k]] <= bp && an.gene_end[g[0].v[k]] >= bp) pick = g[0].v[k];
 			for (u32 k = 0; k < g[1].n; ++k) if (an.gene_start[g[1].v[k]] <= bp && an.gene_end[g[1].v[k]] >= bp) pick = g[1].v[k];
-			g[0].clear(); g[0].insert(pick); g[1].clear(); g[1].insert(pick); changed[0] = changed[1] = true;
+			single[0] = pick; single[1] = pick; g[0].v = &single[0]; g[0].n = 1; g[1].v = &single[1]; g[1].n = 1; changed[0] = changed[1] = true;
 		}
-		bool overflow = false;
-		for (u32 s = 0; s < na; ++s) { overflow = overflow || g[s].overflow; if (changed[s]) sets.set(a[s], g[s].v, g[s].n); }
-		if (overflow) atomic_or_u32(sets.error, 1u);
+		for (u32 s = 0; s < na; ++s) if (changed[s]) {
+			if (g[s].n > 0xFFFFu) { atomic_or_u32(sets.error, 1u); continue; } // the gene count of an alignment is a 16-bit column
+			sets.set(a[s], g[s].v, g[s].n);
+		}
 	}
 };
 

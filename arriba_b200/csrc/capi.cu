@@ -115,6 +115,21 @@ int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* st
 int arb_kmer_index_digest(arb_ctx* ctx, uint64_t* kmers, uint64_t* positions, uint64_t* checksum, uint32_t nc) { ARB_API_BEGIN(ctx) ctx->e.kmer_index_digest(kmers, positions, checksum, nc); ARB_API_END(ctx) }
 int arb_homolog_pairs(arb_ctx* ctx, const uint32_t* ga, const uint32_t* gb, uint32_t n, uint8_t* out) { ARB_API_BEGIN(ctx) ctx->e.homolog_pairs(ga, gb, n, out); ARB_API_END(ctx) }
 int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.filter_mismappers(max_mate_gap); if (n) *n = k; ARB_API_END(ctx) }
+int arb_exchange_header(arb_ctx* ctx, int group, uint64_t* header, uint32_t* n_words) {
+	ARB_API_BEGIN(ctx) std::vector<u64> h; ctx->e.exchange_header(group, h); if (h.size() > 16) throw arb_error("exchange header too long"); for (size_t k = 0; k < h.size(); ++k) header[k] = h[k]; *n_words = (uint32_t) h.size(); ARB_API_END(ctx)
+}
+int arb_exchange_prepare(arb_ctx* ctx, int group, const uint64_t* header, uint32_t n_words) { ARB_API_BEGIN(ctx) ctx->e.exchange_prepare(group, header, n_words); ARB_API_END(ctx) }
+int arb_exchange_buffers(arb_ctx* ctx, int group, void** ptrs, uint64_t* bytes, uint32_t* n) {
+	ARB_API_BEGIN(ctx) std::vector<exchange_buffer> b; ctx->e.exchange_buffers(group, b); if (b.size() > *n) throw arb_error("arb_exchange_buffers: capacity too small"); for (size_t k = 0; k < b.size(); ++k) { ptrs[k] = b[k].p; bytes[k] = b[k].bytes; } *n = (uint32_t) b.size(); ARB_API_END(ctx)
+}
+int arb_exchange_commit(arb_ctx* ctx, int group) { ARB_API_BEGIN(ctx) ctx->e.exchange_commit(group); ARB_API_END(ctx) }
+int arb_set_work_partition(arb_ctx* ctx, const uint32_t* keys, const uint8_t* owner, uint32_t n_keys, int part, int parts) { ARB_API_BEGIN(ctx) ctx->e.set_work_partition(keys, owner, n_keys, part, parts); ARB_API_END(ctx) }
+int arb_candidates_export(arb_ctx* ctx, void** blob, uint64_t* bytes, uint64_t sizes[4]) { ARB_API_BEGIN(ctx) u64 s[4]; u64 b = 0; ctx->e.candidates_export(blob, &b, s); *bytes = b; for (int k = 0; k < 4; ++k) sizes[k] = s[k]; ARB_API_END(ctx) }
+int arb_candidates_import(arb_ctx* ctx, const void* all_blobs, uint64_t stride, const uint64_t* sizes, uint32_t n_parts) { ARB_API_BEGIN(ctx) std::vector<u64> s(sizes, sizes + 4 * (size_t) n_parts); ctx->e.candidates_import(all_blobs, stride, s.data(), n_parts); ARB_API_END(ctx) }
+int arb_swaps_buffer(arb_ctx* ctx, void** p, uint64_t* bytes) { ARB_API_BEGIN(ctx) u64 b = 0; ctx->e.swaps_buffer(p, &b); *bytes = b; ARB_API_END(ctx) }
+int arb_swaps_apply(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.swaps_apply(); ARB_API_END(ctx) }
+int arb_filter_mismappers_part(arb_ctx* ctx, int32_t max_mate_gap, int part, int parts, void** verdicts, uint64_t* bytes) { ARB_API_BEGIN(ctx) u64 b = 0; ctx->e.filter_mismappers_part(max_mate_gap, part, parts, verdicts, &b); *bytes = b; ARB_API_END(ctx) }
+int arb_filter_mismappers_finish(arb_ctx* ctx, uint64_t* n) { ARB_API_BEGIN(ctx) const uint64_t k = ctx->e.filter_mismappers_finish(); if (n) *n = k; ARB_API_END(ctx) }
 int arb_get_timings(arb_ctx* ctx, arb_timings* out) { ARB_API_BEGIN(ctx) *out = ctx->e.timings; ARB_API_END(ctx) }
 int arb_selftest_mismatch_counts(arb_ctx* ctx, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.probe_mismatch_counts(out); ARB_API_END(ctx) } // tests only, not declared in the public header
 int arb_set_candidates(arb_ctx* ctx, const arb_candidates* c) { ARB_API_BEGIN(ctx) if (!c) throw arb_error("null table"); ctx->e.set_candidates(*c); ARB_API_END(ctx) }

@@ -14,7 +14,7 @@ void default_params(arb_params& p) { // options.cpp:71-107
 	p.max_mismapper_fraction = 0.8f; p.max_homolog_identity = 0.3f;
 }
 
-engine::engine(): annot_pool_cap(0), n_dummy(0), n_gene_entries(0), push_cigar_ops(0), cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
+engine::engine(): work_part(0), work_parts(1), mismap_items_total(0), mismap_ms_part(0), n_splice_sites(0), annot_pool_cap(0), n_dummy(0), n_gene_entries(0), push_cigar_ops(0), cascade_smem_bytes(0), cascade_resident_blocks(0), device(0), table_n(0), table_k(0), has_contigs(false), has_annotation(false), filters_done(false), merge_log_n(0), kmer_index_contigs(0), kmer_indexed(0), has_splice_sites(false) {
 	default_params(params);
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
@@ -68,7 +68,7 @@ void engine::set_contigs(const arb_contigs& c) {
 		if (!loaded) annot.h_contig_len[k] = 0;
 		if (loaded) total += ((u64) c.length[k] + 63) & ~(u64) 63;
 	}
-	annot.assembly.ensure(total + 64);
+	annot.assembly.ensure(total + 64); annot.assembly_bytes = total;
 	for (u32 k = 0; k < c.n_contigs; ++k) {
 		if (off[k] == ~(u64) 0) continue;
 #ifdef ARB_DEVICE_BUILD
@@ -83,7 +83,7 @@ void engine::set_contigs(const arb_contigs& c) {
 	annot.contig_seq_off.upload(ex, off.data(), c.n_contigs);
 	{
 		const u64 n_words = total / 8 + 9; // windows read one word past the last base
-		annot.assembly4.ensure(n_words); annot.assembly4.zero(ex, n_words);
+		annot.assembly4.ensure(n_words); annot.assembly4.zero(ex, n_words); annot.assembly4_words = n_words;
 		dbuf<u32> exotic(1); exotic.zero(ex, 1);
 		for (u32 k = 0; k < c.n_contigs; ++k) {
 			if (annot.h_contig_len[k] == 0) continue;
@@ -117,6 +117,7 @@ void engine::set_annotation(const arb_annotation& a) {
 	annot.exon_cds_start.upload(ex, a.exon_cds_start, a.n_exons); annot.exon_cds_end.upload(ex, a.exon_cds_end, a.n_exons);
 	annot.exon_next_start.upload(ex, a.exon_next_start, a.n_exons); annot.exon_flags.upload(ex, a.exon_flags, a.n_exons);
 	const u32 ner = a.exon_region_begin[a.n_contigs], ngr = a.gene_region_begin[a.n_contigs];
+	annot.n_exon_regions = ner; annot.n_gene_regions = ngr; annot.n_exon_items = a.exon_region_off[ner]; annot.n_gene_items = a.gene_region_off[ngr];
 	annot.exon_region_begin.upload(ex, a.exon_region_begin, a.n_contigs + 1); annot.exon_region_end.upload(ex, a.exon_region_end, ner);
 	annot.exon_region_off.upload(ex, a.exon_region_off, ner + 1); annot.exon_region_items.upload(ex, a.exon_region_items, a.exon_region_off[ner]);
 	annot.gene_region_begin.upload(ex, a.gene_region_begin, a.n_contigs + 1); annot.gene_region_end.upload(ex, a.gene_region_end, ngr);

@@ -53,7 +53,8 @@ struct annot_store {
 	std::vector<u8> h_contig_flags; std::vector<u32> h_contig_len;
 	// host mirrors needed by host-side steps
 	std::vector<u16> h_gene_contig; std::vector<i32> h_gene_start, h_gene_end; std::vector<u8> h_gene_strand, h_gene_flags;
-	annot_store(): n_genes(0), n_exons(0), n_contigs(0), assembly4_ok(false) {}
+	u64 assembly_bytes, assembly4_words; u32 n_exon_regions, n_exon_items, n_gene_regions, n_gene_items; // exact sizes of the buffers above (exchange.cu)
+	annot_store(): n_genes(0), n_exons(0), n_contigs(0), assembly4_ok(false), assembly_bytes(0), assembly4_words(0), n_exon_regions(0), n_exon_items(0), n_gene_regions(0), n_gene_items(0) {}
 	annot_view view() const {
 		annot_view v;
 		v.n_genes = n_genes; v.gene_contig = gene_contig.ptr(); v.gene_start = gene_start.ptr(); v.gene_end = gene_end.ptr();
@@ -76,6 +77,8 @@ struct cand_store {
 	dbuf<u32> first_frag; // fragment whose record created the candidate (merge key of the sharded run)
 	cand_store(): n(0), n_list1(0), n_list2(0), n_listd(0) {}
 };
+
+struct exchange_buffer { void* p; u64 bytes; };
 
 class engine {
 public:
@@ -106,6 +109,14 @@ public:
 	void get_annotation_columns(u8* aflags, u32* genes_off, u16* genes_cnt, u32* genes);
 	dbuf<u32> annot_rows, annot_pool, annot_ctl; dbuf<u16> annot_cnt; u32 annot_pool_cap, n_dummy; u64 n_gene_entries; dbuf<u16> dummy_contig; dbuf<i32> dummy_start, dummy_end;
 	void finish_push(u64 n_gene_ids); u64 push_cigar_ops;
+	// one sample on several GPUs (exchange.cu): replicated state travels as groups of device buffers, the work of find_fusions / filter_mismappers is divided
+	void exchange_header(int group, std::vector<u64>& header); void exchange_prepare(int group, const u64* header, u32 n_words);
+	void exchange_buffers(int group, std::vector<exchange_buffer>& out); void exchange_commit(int group);
+	void set_work_partition(const u32* keys, const u8* owner, u32 n_keys, int part, int parts); int work_part, work_parts; dbuf<u8> work_owned;
+	void candidates_export(void** blob, u64* bytes, u64 sizes[4]); void candidates_import(const void* all_blobs, u64 stride, const u64* sizes, u32 n_parts); dbuf<char> cand_blob;
+	void swaps_buffer(void** p, u64* bytes); void swaps_apply(); dbuf<u8> swap_union;
+	void filter_mismappers_part(i32 max_mate_gap, int part, int parts, void** verdicts, u64* bytes); u64 filter_mismappers_finish(); dbuf<u8> mismap_verdicts; u64 mismap_items_total; float mismap_ms_part;
+	u64 n_splice_sites;
 	exec_ctx copy_ex; bool push_open; // copy stream: H2D of a chunk overlaps with host work (annotation) and with kernels on `ex`
 	void run_read_filters();
 	void get_fragment_filters(u8* filter_out, u8* early_out);

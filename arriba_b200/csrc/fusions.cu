@@ -120,7 +120,7 @@ void engine::find_fusions(i32 max_mate_gap) {
 
 	// 1. records
 	dbuf<u32> rec_off((size_t) n + 1);
-	emit_count_fn ec = {f, rec_off.ptr()};
+	emit_count_fn ec = {f, rec_off.ptr(), work_parts > 1 ? work_owned.ptr() : NULL};
 	for_each(ex, n, ec);
 	exclusive_scan_u32(ex, rec_off.ptr(), rec_off.ptr(), n);
 	u32 R = 0; rec_off.download(ex, &R, 1, n);

@@ -56,8 +56,9 @@ ARB_HD frag_ends fragment_ends(const frag_view& f, u32 i) {
 }
 
 struct emit_count_fn {
-	frag_view f; u32* cnt;
+	frag_view f; u32* cnt; const u8* owned; // owned: NULL, or 1 for the fragments whose breakpoint records this part of a multi-GPU run emits (exchange.cu)
 	ARB_HD void operator()(u32 i) const {
+		if (owned && !owned[i]) { cnt[i] = 0; return; }
 		const bool split = f.n_aln[i] == 3;
 		const u32 x = f.idx(i, split ? SPLIT_READ : MATE1), y = f.idx(i, split ? SUPPLEMENTARY : MATE2);
 		cnt[i] = (u32) f.genes_cnt[x] * (u32) f.genes_cnt[y];
@@ -67,6 +68,7 @@ struct emit_count_fn {
 struct emit_fill_fn {
 	frag_view f; const u32* off; record_view r;
 	ARB_HD void operator()(u32 i) const {
+		if (off[i + 1] == off[i]) return; // no records (or not this part's fragment)
 		const frag_ends e = fragment_ends(f, i);
 		const u32 n1 = f.genes_cnt[e.a1], n2 = f.genes_cnt[e.a2];
 		const u32* g1 = f.genes + f.genes_off[e.a1]; const u32* g2 = f.genes + f.genes_off[e.a2];

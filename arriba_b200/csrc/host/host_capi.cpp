@@ -83,18 +83,12 @@ int arb_pipeline_step(arb_pipeline* x, int step) {
 	PIPE_END(x)
 }
 
-int arb_pipeline_plan_shard(arb_pipeline* x, int world) { PIPE_BEGIN(x) x->p.shard_planned = world > 1; PIPE_END(x) }
-int arb_pipeline_set_shard(arb_pipeline* x, int rank, int world) { PIPE_BEGIN(x) x->p.set_shard(rank, world); PIPE_END(x) }
-int arb_pipeline_shard_members(arb_pipeline* x, int rank, const uint32_t** members, uint64_t* n) {
-	PIPE_BEGIN(x)
-	if (rank < 0 || rank >= (int) x->p.shard_members.size()) throw std::runtime_error("no such rank");
-	*members = x->p.shard_members[rank].data(); *n = x->p.shard_members[rank].size();
-	PIPE_END(x)
+int arb_pipeline_attach_device(arb_pipeline* x) { PIPE_BEGIN(x) x->p.attach_device(); PIPE_END(x) }
+int arb_pipeline_work_partition(arb_pipeline* x, int parts, const uint32_t** keys, const uint8_t** owner, uint32_t* n_keys) {
+	PIPE_BEGIN(x) x->p.work_partition(parts); *keys = x->p.partition_keys.data(); *owner = x->p.partition_owner.data(); *n_keys = (uint32_t) x->p.partition_keys.size(); PIPE_END(x)
 }
-int arb_pipeline_export_shard(arb_pipeline* x, int what, const void** blob, uint64_t* bytes) { PIPE_BEGIN(x) arb::u64 b = 0; x->p.export_shard(what, blob, &b); *bytes = b; PIPE_END(x) }
-int arb_pipeline_import_shards(arb_pipeline* x, int what, const void* const* blobs, const uint64_t* bytes, uint32_t n) {
-	PIPE_BEGIN(x) std::vector<arb::u64> b(bytes, bytes + n); x->p.import_shards(what, blobs, b.data(), n); PIPE_END(x)
-}
+int arb_pipeline_mismappers_begin(arb_pipeline* x, int* active) { PIPE_BEGIN(x) const bool a = x->p.mismappers_begin(); if (active) *active = a ? 1 : 0; PIPE_END(x) }
+int arb_pipeline_mismappers_end(arb_pipeline* x) { PIPE_BEGIN(x) x->p.mismappers_end(); PIPE_END(x) }
 int arb_pipeline_run(arb_pipeline* x) { PIPE_BEGIN(x) x->p.run_all(); PIPE_END(x) }
 arb_ctx* arb_pipeline_ctx(arb_pipeline* x) { return x ? x->p.ctx : NULL; }
 

@@ -46,7 +46,7 @@ void pipeline::ingest() {
 	read_chimeric_alignments(opt.bam_file, ref, io, frags, coverage, istats);
 	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")";
 	say(s.str());
-	if (!shard_planned && (getenv("ARB_EARLY_UPLOAD") == NULL || atoi(getenv("ARB_EARLY_UPLOAD")) != 0)) begin_upload();
+	if (getenv("ARB_EARLY_UPLOAD") == NULL || atoi(getenv("ARB_EARLY_UPLOAD")) != 0) begin_upload();
 	t_ingest = now_s() - t0;
 }
 
@@ -69,16 +69,19 @@ void pipeline::annotate() {
 		strandedness = detect_strandedness(*this);
 		say(std::string("Detecting strandedness (") + (strandedness == 1 ? "yes" : strandedness == 2 ? "reverse" : "no") + ")");
 	}
-	if (!upload_begun) begin_upload(); // the passes run on the device over the resident columns (a sharded run annotates the whole table, then re-packs its part)
+	if (!upload_begun) begin_upload(); // the passes run on the device over the resident columns
 	annotate_fragments(*this);
-	whole_table_resident = true;
 	viral_contig_decisions(*this); // per-contig verdicts of the two viral heuristics; no-op without viral contigs
 	t_annotate = now_s() - t0;
 }
 
-void pipeline::upload_reference() {
+void pipeline::attach_device() {
 	if (!ctx) { if (arb_ctx_create(&ctx, opt.device) != 0) throw std::runtime_error(arb_last_error(NULL)); }
 	check(ctx, arb_set_params(ctx, &opt.params), "arb_set_params");
+}
+
+void pipeline::upload_reference() {
+	attach_device();
 	if (reference_on_device) return;
 	const u32 nc = (u32) ref.contig_ids.size();
 	std::vector<const char*> seqs(nc, (const char*) NULL);
@@ -127,15 +130,6 @@ void pipeline::upload() {
 	upload_reference();
 	// the contig flags with the per-sample verdicts on viral contigs (the annotation went to the device with annotate())
 	check(ctx, arb_set_contig_flags(ctx, ref.contig_flags.data(), (u32) ref.contig_ids.size()), "arb_set_contig_flags");
-	if (shard_world > 1) { // a sharded run keeps its own part only
-		arb_soa_chunk c = chunk_of(local);
-		check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
-		whole_table_resident = false;
-	} else if (!whole_table_resident) { // the complete, annotated table again (end of a sharded run's candidate exchange)
-		arb_soa_chunk c = chunk_of(frags);
-		check(ctx, arb_push_chunk(ctx, &c), "arb_push_chunk");
-		whole_table_resident = true;
-	}
 	upload_begun = false;
 	frags_on_device = true;
 	t_upload = now_s() - t0;
@@ -144,14 +138,9 @@ void pipeline::upload() {
 void pipeline::read_filters() {
 	const double t0 = now_s();
 	check(ctx, arb_run_read_filters(ctx), "arb_run_read_filters");
-	if (shard_world > 1) { // labels of the shard only; the global picture arrives with the label exchange (shard.cpp)
-		local_labels.resize(local.n); local_early.resize(local.n);
-		check(ctx, arb_get_fragment_filters(ctx, local_labels.data(), local_early.data()), "arb_get_fragment_filters");
-	} else {
-		labels.resize(frags.n); early.resize(frags.n);
-		check(ctx, arb_get_fragment_filters(ctx, labels.data(), early.data()), "arb_get_fragment_filters");
-		say_read_filter_counts();
-	}
+	labels.resize(frags.n); early.resize(frags.n);
+	check(ctx, arb_get_fragment_filters(ctx, labels.data(), early.data()), "arb_get_fragment_filters");
+	say_read_filter_counts();
 	t_read_filters = now_s() - t0;
 }
 

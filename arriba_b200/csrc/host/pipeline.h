@@ -53,13 +53,13 @@ struct pipeline {
 	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
 	pipeline(): ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false), splice_sites_ready(false), events_done(-1),
-	            upload_begun(false), shard_planned(false), whole_table_resident(false), shard_rank(0), shard_world(1), frags_on_device(false), reference_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
+	            upload_begun(false), t_mismappers_begin(0), frags_on_device(false), reference_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
 	void annotate();
 	void upload();
-	void upload_reference(); void send_annotation(); void begin_upload(); arb_soa_chunk chunk_of(fragment_table& t); bool upload_begun, shard_planned, whole_table_resident; // ingest ends by starting the copy of its columns; annotation overlaps it
+	void upload_reference(); void send_annotation(); void begin_upload(); arb_soa_chunk chunk_of(fragment_table& t); bool upload_begun; // ingest ends by starting the copy of its columns; annotation overlaps it
 	void read_filters();
 	void fragment_length();
 	void find_fusions();
@@ -77,12 +77,11 @@ struct pipeline {
 	void events_until(int last_stage); // runs the event-level chain up to and including `last_stage` (EV_* below)
 	int events_done;
 	void run_all();
-	// one sample on several GPUs (shard.cpp): fragments partitioned by contig pair, two exchanges (labels, candidates) carried by the caller
-	int shard_rank, shard_world; std::vector<std::vector<u32> > shard_members; fragment_table local; std::vector<u8> local_labels, local_early, export_blob;
+	// one sample on several GPUs (shard.cpp; device side csrc/exchange.cu): contig pairs assigned to the parts, the re-alignment stage in two halves
+	std::vector<u32> partition_keys; std::vector<u8> partition_owner; void work_partition(int parts);
+	bool mismappers_begin(); void mismappers_end(); double t_mismappers_begin;
+	void attach_device(); // a part that only works on replicated device state: a context with the run's parameters
 	bool frags_on_device, reference_on_device;
-	void set_shard(int rank, int world);
-	void export_shard(int what, const void** blob, u64* bytes);
-	void import_shards(int what, const void* const* blobs, const u64* bytes, u32 n_blobs);
 	void say_read_filter_counts();
 };
 

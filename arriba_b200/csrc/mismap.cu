@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it
 
 void engine::set_splice_sites(const u32* off, const i32* sites) {
 	splice_off.upload(ex, off, (size_t) annot.n_genes + 1);
-	splice_sites.upload(ex, sites, off[annot.n_genes]);
+	splice_sites.upload(ex, sites, off[annot.n_genes]); n_splice_sites = off[annot.n_genes];
 	ex.sync();
 	has_splice_sites = true;
 }
@@ -107,20 +107,48 @@ void engine::homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out) {
 	o.download(ex, out, n);
 }
 
+// work items j = part, part + parts, ... of the item list (items of one candidate are consecutive: a stride spreads the expensive candidates over the parts)
+struct item_stride_fn {
+	const u32* cand; const u32* frag; const u8* kind; u32 part, parts; u32* o_cand; u32* o_frag; u8* o_kind;
+	ARB_HD void operator()(u32 k) const { const u32 j = k * parts + part; o_cand[k] = cand[j]; o_frag[k] = frag[j]; o_kind[k] = kind[j]; }
+};
+struct verdict_or_fn { const u8* v; u8* mism; ARB_HD void operator()(u32 i) const { if (v[i]) mism[i] = 1; } };
+
 u64 engine::filter_mismappers(i32 max_mate_gap) {
+	void* v; u64 b;
+	filter_mismappers_part(max_mate_gap, 0, 1, &v, &b);
+	return filter_mismappers_finish();
+}
+
+// re-aligns this part's share of the work items; the verdicts (one byte per fragment, 1 = some evaluation says mis-mapped) stay on the device for the caller to
+// combine across parts (MAX) before filter_mismappers_finish
+void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void** verdicts, u64* bytes) {
 	if (!has_splice_sites) throw arb_error("arb_filter_mismappers: arb_set_splice_sites must be called first");
+	if (parts < 1 || part < 0 || part >= parts) throw arb_error("arb_filter_mismappers_part: invalid part");
 	const u32 C = cands.n, N = frags.n;
-	if (C == 0) return 0;
+	mismap_verdicts.ensure(N); mismap_verdicts.zero(ex, N);
+	*verdicts = mismap_verdicts.ptr(); *bytes = N;
+	mismap_items_total = 0; mismap_ms_part = 0;
+	if (C == 0) { ex.sync(); return; }
 	stage_timer t_all(ex);
 	dbuf<u32> item_off((size_t) C + 1);
 	item_count_fn ic = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list2_off.ptr(), cands.listd_off.ptr(), item_off.ptr()};
 	for_each(ex, C, ic);
 	exclusive_scan_u32(ex, item_off.ptr(), item_off.ptr(), C);
 	u32 I = 0; item_off.download(ex, &I, 1, C);
-	dbuf<u32> item_cand(I), item_frag(I); dbuf<u8> item_kind(I), mism(N);
-	mism.zero(ex, N);
+	mismap_items_total = I;
+	dbuf<u32> item_cand(I), item_frag(I); dbuf<u8> item_kind(I); dbuf<u8>& mism = mismap_verdicts;
 	item_fill_fn ifn = {cands.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(), item_off.ptr(), item_cand.ptr(), item_frag.ptr(), item_kind.ptr()};
 	for_each(ex, C, ifn);
+	if (parts > 1) { // this part's share
+		const u32 mine = I > (u32) part ? (I - (u32) part + (u32) parts - 1) / (u32) parts : 0;
+		dbuf<u32> c2(mine), f2(mine); dbuf<u8> k2(mine);
+		item_stride_fn st = {item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), (u32) part, (u32) parts, c2.ptr(), f2.ptr(), k2.ptr()};
+		for_each(ex, mine, st);
+		ex.sync();
+		item_cand.swap(c2); item_frag.swap(f2); item_kind.swap(k2);
+		I = mine;
+	}
 	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
 	gene_splice_view sp = {splice_off.ptr(), splice_sites.ptr()};
 	mismap_params mp = {max_mate_gap, params.max_mismapper_fraction};
@@ -177,14 +205,24 @@ u64 engine::filter_mismappers(i32 max_mate_gap) {
 	{ u32 o = 0; overflow.download(ex, &o, 1); timings.mismapper_overflow = o; timings.mismapper_table_slots = K; }
 	timings.mismappers_pass2_ms = t2.stop();
 	timings.mismapper_heavy_items = H;
+	mismap_ms_part = t_all.stop();
+	ex.sync();
+}
+
+// labels the mis-mapped fragments and discards the candidates most of whose reads are (filter_mismappers.cpp:232-244, :336-356)
+u64 engine::filter_mismappers_finish() {
+	const u32 C = cands.n, N = frags.n;
+	if (C == 0) return 0;
+	stage_timer t_all(ex);
+	dbuf<u8>& mism = mismap_verdicts;
 	mismap_apply_fn ma = {mism.ptr(), frags.filter.ptr()};
 	for_each(ex, N, ma);
 	mismap_count_fn mc = {frags.filter.ptr(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(),
 	                      cands.split_reads1.ptr(), cands.split_reads2.ptr(), cands.discordant_mates.ptr(), cands.filter.ptr(), params.max_mismapper_fraction};
 	for_each(ex, C, mc);
-	timings.mismappers_ms = t_all.stop(); timings.mismapper_items = I;
+	timings.mismappers_ms = mismap_ms_part + t_all.stop(); timings.mismapper_items = mismap_items_total;
 	ex.sync();
-	return I;
+	return mismap_items_total;
 }
 
 } // namespace arb

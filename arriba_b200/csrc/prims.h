@@ -118,6 +118,7 @@ public:
 #endif
 	}
 	void ensure(size_t n) { if (n > n_) alloc(n + n / 4); }
+	void swap(dbuf& o) { std::swap(p_, o.p_); std::swap(n_, o.n_); std::swap(granted_, o.granted_); }
 	T* ptr() const { return p_; }
 	size_t size() const { return n_; }
 	void zero(const exec_ctx& ex, size_t n) { fill_bytes(ex, 0, n); }

@@ -119,7 +119,13 @@ def load(path=None):
                        ("arb_get_fragment_filters", [_p(C.c_uint8), _p(C.c_uint8)]), ("arb_set_fragment_filters", [_p(C.c_uint8)]),
                        ("arb_get_filter_counts", [_p(C.c_uint32)]), ("arb_find_fusions", [C.c_int32]),
                        ("arb_candidates_size", [_p(C.c_uint32), _p(C.c_uint64), _p(C.c_uint64), _p(C.c_uint64)]),
-                       ("arb_get_candidates", [_p(Candidates)]), ("arb_get_slot_swaps", [_p(C.c_uint8)]), ("arb_get_timings", [_p(Timings)])]:
+                       ("arb_get_candidates", [_p(Candidates)]), ("arb_get_slot_swaps", [_p(C.c_uint8)]), ("arb_get_timings", [_p(Timings)]),
+                       ("arb_exchange_header", [C.c_int, _p(C.c_uint64), _p(C.c_uint32)]), ("arb_exchange_prepare", [C.c_int, _p(C.c_uint64), C.c_uint32]),
+                       ("arb_exchange_buffers", [C.c_int, _p(C.c_void_p), _p(C.c_uint64), _p(C.c_uint32)]), ("arb_exchange_commit", [C.c_int]),
+                       ("arb_set_work_partition", [_p(C.c_uint32), _p(C.c_uint8), C.c_uint32, C.c_int, C.c_int]),
+                       ("arb_candidates_export", [_p(C.c_void_p), _p(C.c_uint64), _p(C.c_uint64)]), ("arb_candidates_import", [C.c_void_p, C.c_uint64, _p(C.c_uint64), C.c_uint32]),
+                       ("arb_swaps_buffer", [_p(C.c_void_p), _p(C.c_uint64)]), ("arb_swaps_apply", []),
+                       ("arb_filter_mismappers_part", [C.c_int32, C.c_int, C.c_int, _p(C.c_void_p), _p(C.c_uint64)]), ("arb_filter_mismappers_finish", [_p(C.c_uint64)])]:
         fn = getattr(lib, name)
         fn.argtypes = [C.c_void_p] + args
         fn.restype = C.c_int
@@ -247,6 +253,55 @@ class Context:
         self._check(self.lib.arb_get_timings(self.h, C.byref(t)))
         return t
 
+    # ---- one sample on several GPUs: device buffers for the launcher's transport (include/arriba_b200.h; arriba_b200/sharded.py drives these)
+    def exchange_header(self, group):
+        h = (C.c_uint64 * 16)(); n = C.c_uint32()
+        self._check(self.lib.arb_exchange_header(self.h, group, h, C.byref(n)))
+        return [int(h[k]) for k in range(n.value)]
+
+    def exchange_prepare(self, group, header):
+        h = (C.c_uint64 * len(header))(*header)
+        self._check(self.lib.arb_exchange_prepare(self.h, group, h, len(header)))
+
+    def exchange_buffers(self, group):
+        ptrs = (C.c_void_p * 32)(); sizes = (C.c_uint64 * 32)(); n = C.c_uint32(32)
+        self._check(self.lib.arb_exchange_buffers(self.h, group, ptrs, sizes, C.byref(n)))
+        return [(int(ptrs[k] or 0), int(sizes[k])) for k in range(n.value)]
+
+    def exchange_commit(self, group):
+        self._check(self.lib.arb_exchange_commit(self.h, group))
+
+    def set_work_partition(self, keys, owner, part, parts):
+        keys = np.ascontiguousarray(keys, np.uint32); owner = np.ascontiguousarray(owner, np.uint8)
+        self._check(self.lib.arb_set_work_partition(self.h, ptr(keys), ptr(owner), keys.size, part, parts))
+
+    def candidates_export(self):
+        blob = C.c_void_p(); n = C.c_uint64(); sizes = (C.c_uint64 * 4)()
+        self._check(self.lib.arb_candidates_export(self.h, C.byref(blob), C.byref(n), sizes))
+        return int(blob.value or 0), int(n.value), [int(x) for x in sizes]
+
+    def candidates_import(self, all_blobs_ptr, stride, sizes, n_parts):
+        s = (C.c_uint64 * (4 * n_parts))(*sizes)
+        self._check(self.lib.arb_candidates_import(self.h, C.c_void_p(all_blobs_ptr), stride, s, n_parts))
+
+    def swaps_buffer(self):
+        p = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.arb_swaps_buffer(self.h, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def swaps_apply(self):
+        self._check(self.lib.arb_swaps_apply(self.h))
+
+    def filter_mismappers_part(self, max_mate_gap, part, parts):
+        p = C.c_void_p(); n = C.c_uint64()
+        self._check(self.lib.arb_filter_mismappers_part(self.h, int(max_mate_gap), part, parts, C.byref(p), C.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def filter_mismappers_finish(self):
+        n = C.c_uint64()
+        self._check(self.lib.arb_filter_mismappers_finish(self.h, C.byref(n)))
+        return int(n.value)
+
     def slot_swaps(self):
         s = np.zeros(self.n_fragments, np.uint8)
         self._check(self.lib.arb_get_slot_swaps(self.h, ptr(s)))
@@ -296,11 +351,10 @@ def _load_pipeline_api(lib):
     lib.arb_pipeline_events.argtypes = [C.c_void_p, C.c_int]
     lib.arb_pipeline_write_output.argtypes = [C.c_void_p]
     lib.arb_pipeline_candidates.argtypes = [C.c_void_p, _p(Candidates), _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(_p(C.c_uint8))]
-    lib.arb_pipeline_set_shard.argtypes = [C.c_void_p, C.c_int, C.c_int]
-    lib.arb_pipeline_plan_shard.argtypes = [C.c_void_p, C.c_int]
-    lib.arb_pipeline_shard_members.argtypes = [C.c_void_p, C.c_int, _p(_p(C.c_uint32)), _p(C.c_uint64)]
-    lib.arb_pipeline_export_shard.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64)]
-    lib.arb_pipeline_import_shards.argtypes = [C.c_void_p, C.c_int, _p(C.c_void_p), _p(C.c_uint64), C.c_uint32]
+    lib.arb_pipeline_attach_device.argtypes = [C.c_void_p]
+    lib.arb_pipeline_work_partition.argtypes = [C.c_void_p, C.c_int, _p(_p(C.c_uint32)), _p(_p(C.c_uint8)), _p(C.c_uint32)]
+    lib.arb_pipeline_mismappers_begin.argtypes = [C.c_void_p, _p(C.c_int)]
+    lib.arb_pipeline_mismappers_end.argtypes = [C.c_void_p]
     lib._pipeline_ready = True
 
 
@@ -353,28 +407,22 @@ class Pipeline:
         for s in range(upto + 1):
             self.step(s)
 
-    # ---- one sample on several GPUs (include/arriba_b200.h, "One sample on several GPUs"); the transport is the caller's, see sharded.py
-    def plan_shard(self, world):
-        self._check(self.lib.arb_pipeline_plan_shard(self.h, world))
+    # ---- one sample on several GPUs (include/arriba_b200.h); the transport is the launcher's, see sharded.py
+    def attach_device(self):
+        self._check(self.lib.arb_pipeline_attach_device(self.h))
 
-    def set_shard(self, rank, world):
-        self._check(self.lib.arb_pipeline_set_shard(self.h, rank, world))
+    def work_partition(self, parts):
+        k = _p(C.c_uint32)(); o = _p(C.c_uint8)(); n = C.c_uint32()
+        self._check(self.lib.arb_pipeline_work_partition(self.h, parts, C.byref(k), C.byref(o), C.byref(n)))
+        return _np_from(k, int(n.value), np.uint32), _np_from(o, int(n.value), np.uint8)
 
-    def shard_members(self, rank):
-        m = _p(C.c_uint32)(); n = C.c_uint64()
-        self._check(self.lib.arb_pipeline_shard_members(self.h, rank, C.byref(m), C.byref(n)))
-        return _np_from(m, int(n.value), np.uint32)
+    def mismappers_begin(self):
+        a = C.c_int()
+        self._check(self.lib.arb_pipeline_mismappers_begin(self.h, C.byref(a)))
+        return bool(a.value)
 
-    def export_shard(self, what):
-        blob = C.c_void_p(); n = C.c_uint64()
-        self._check(self.lib.arb_pipeline_export_shard(self.h, what, C.byref(blob), C.byref(n)))
-        return np.ctypeslib.as_array(C.cast(blob, _p(C.c_uint8)), shape=(int(n.value),)).copy()
-
-    def import_shards(self, what, blobs):
-        blobs = [np.ascontiguousarray(b, np.uint8) for b in blobs]
-        ptrs = (C.c_void_p * len(blobs))(*[b.ctypes.data for b in blobs])
-        sizes = (C.c_uint64 * len(blobs))(*[b.size for b in blobs])
-        self._check(self.lib.arb_pipeline_import_shards(self.h, what, ptrs, sizes, len(blobs)))
+    def mismappers_end(self):
+        self._check(self.lib.arb_pipeline_mismappers_end(self.h))
 
     def stats(self):
         s = RunStats()

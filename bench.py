@@ -174,14 +174,15 @@ def main():
             usable = min(cores, max(1.0, float(quota) / float(period)))
     except Exception:
         pass
-    threads = args.threads or max(2, min(64, int(round(2 * usable / max(1, world)))))   # 2 threads per usable CPU measured best (profiles/r01i)
+    threads_all = args.threads or max(2, min(64, int(round(2 * usable))))                 # 2 threads per usable CPU measured best (profiles/r01i)
+    threads = args.threads or max(2, min(64, int(round(2 * usable / max(1, world)))))   # one sample per rank: the ranks share the host
     wl = WORKLOADS[args.workload]
     sample_bp = args.sample_breakpoints or max(50, int(wl["breakpoints"] * 400000 / wl["fragments"]))  # ~400 k fragments: 10-30 s of reference CPU time
     metric = "chimeric reads/sec end-to-end (ingest→fusions.tsv)"   # BASELINE.json; a "read" is one chimeric fragment (read pair + supplementary), the unit the reference counts
     config = {"workload": "synthetic %s: %d fragments 2x%d bp, %d breakpoints, genome %.0f%% of hg38 size (synthetic), %d genes" %
               (args.workload, wl["fragments"], wl["read_length"], wl["breakpoints"], wl["scale"] * 100, wl["genes"]),
               "scope": SCOPE, "value_is": "end to end: BAM on disk -> both TSV files on disk through the public Pipeline API, host<->device copies inside the timed region",
-              "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_cpus_usable": usable}
+              "l2": "inputs (>2 GB of SoA columns per step) exceed the 126 MB L2", "host_threads_per_rank": threads, "host_threads_rank0_sharded": threads_all, "host_cpus_usable": usable}
 
     if args.impl == "reference":
         if rank != 0:
@@ -224,8 +225,10 @@ def main():
 
     def one_step(sharded):
         """ingest .. fusions.tsv through the public Pipeline API; returns a dict of what the step measured"""
-        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=threads, device=local_rank, output=out_tsv, discarded=out_disc)
-        p.step(L.STEP_LOAD_REFERENCE)          # genome + annotation: loaded once per run in a real deployment, outside the timed region
+        # one sample divided over the ranks: rank 0 does the host work with all host threads, the others only hold a device context
+        p = L.Pipeline(prefix + ".bam", prefix + ".gtf", prefix + ".fa", threads=(threads_all if rank == 0 else 2) if sharded else threads, device=local_rank, output=out_tsv, discarded=out_disc)
+        if not sharded or rank == 0:
+            p.step(L.STEP_LOAD_REFERENCE)      # genome + annotation: loaded once per run in a real deployment, outside the timed region
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
@@ -240,7 +243,7 @@ def main():
             p.write_output()
         e2e_s = time.perf_counter() - t0
         ctx = p.context()
-        st = p.stats(); tm = ctx.timings()
+        st = p.stats(); tm = ctx.timings() if ctx.h else L.Timings()
         n_cand = int(st.n_candidates)
         d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
         dev_ms = tm.read_filters_ms + tm.find_fusions_ms + tm.merge_adjacent_ms + tm.evalue_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms
@@ -271,15 +274,21 @@ def main():
         return results, e2e_s, dev_ms, wall
 
     sharded = args.mode == "sharded" and world > 1
-    config["sharding"] = ("ONE sample divided over the ranks (strong scaling): see DESIGN.md section 7" if sharded else
+    config["sharding"] = ("ONE sample over the ranks (strong scaling): rank 0 ingests and broadcasts its resident table over NVLink; find_fusions divided by contig pair, one NCCL all-gather of the candidate tables, filter_mismappers divided by work item (DESIGN.md section 7)" if sharded else
                           "one independent BAM per rank (weak scaling, no collective on the data path)" if world > 1 else "single GPU")
     sampler = ClockSampler(local_rank); sampler.start()
     launches1 = None
     lib = L.load()
-    for _ in range(args.warmup):
-        one_step(sharded)
-    launches1 = lib.arb_kernel_launches()
-    results, e2e_s, dev_ms, wall = timed(sharded, 0, args.steps)
+    try:
+        for _ in range(args.warmup):
+            one_step(sharded)
+        launches1 = lib.arb_kernel_launches()
+        results, e2e_s, dev_ms, wall = timed(sharded, 0, args.steps)
+    except BaseException:
+        import traceback
+        quiet.say("bench.py (rank %d): a step failed\n%s" % (rank, traceback.format_exc()))   # on the real stderr, not in the library's log
+        quiet.__exit__()
+        raise
     launches = lib.arb_kernel_launches() - launches1
     sampler.stop_flag = True; sampler.join(timeout=2)
 

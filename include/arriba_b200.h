@@ -195,6 +195,35 @@ int arb_kmer_index_digest(arb_ctx* ctx, uint64_t* kmers, uint64_t* positions, ui
 int arb_homolog_pairs(arb_ctx* ctx, const uint32_t* gene_a, const uint32_t* gene_b, uint32_t n, uint8_t* is_homolog_out);
 int arb_filter_mismappers(arb_ctx* ctx, int32_t max_mate_gap, uint64_t* n_realigned);
 
+/* ---- one sample on several GPUs (arriba_b200/csrc/exchange.cu) --------------------------------------------
+ * The library never communicates itself: it exposes DEVICE buffers, the caller moves them with its transport (NCCL through torch.distributed in
+ * arriba_b200/sharded.py). The fragment table is replicated from the rank that ingested the BAM (broadcast over NVLink/NVSwitch), the work is divided:
+ * arb_find_fusions only emits the breakpoints of the contig pairs the part owns, arb_filter_mismappers_part re-aligns every parts-th work item.
+ *   exchange groups (broadcast): ARB_XG_CONTIGS genome + contig table, ARB_XG_ANNOTATION gene / exon tables with their indices, ARB_XG_TABLE the resident
+ *   fragment table, ARB_XG_MISMAP_STATE what arb_filter_mismappers reads besides (candidate state and lists, fragment labels, k-mer index, splice sites).
+ *   Sender: arb_exchange_header -> header words. Receiver: arb_exchange_prepare(header) sizes its buffers. Both: arb_exchange_buffers lists the same
+ *   device buffers in the same order (the caller broadcasts each). Receiver: arb_exchange_commit. */
+enum { ARB_XG_CONTIGS = 0, ARB_XG_ANNOTATION = 1, ARB_XG_TABLE = 2, ARB_XG_MISMAP_STATE = 3 };
+int arb_exchange_header(arb_ctx* ctx, int group, uint64_t* header /* capacity 16 */, uint32_t* n_words);
+int arb_exchange_prepare(arb_ctx* ctx, int group, const uint64_t* header, uint32_t n_words);
+int arb_exchange_buffers(arb_ctx* ctx, int group, void** device_ptrs, uint64_t* bytes, uint32_t* n /* in: capacity (32 suffice), out: buffers */);
+int arb_exchange_commit(arb_ctx* ctx, int group);
+/* contig pairs (keys = lower contig << 16 | higher contig, ascending) and the part that owns each; fragments of other pairs emit no breakpoints in
+ * arb_find_fusions. parts == 1 lifts the restriction. (arb_pipeline_work_partition computes a balanced assignment.) */
+int arb_set_work_partition(arb_ctx* ctx, const uint32_t* keys, const uint8_t* owner, uint32_t n_keys, int part, int parts);
+/* the part's candidate table packed into ONE device buffer (sizes = {candidates, list1, list2, listd entries}); after an all-gather of the buffers (padded
+ * to `stride`) every part merges them into the table a single GPU would have built: candidates in first-insertion order (fusions.cpp:253-300) */
+int arb_candidates_export(arb_ctx* ctx, void** device_blob, uint64_t* bytes, uint64_t sizes[4]);
+int arb_candidates_import(arb_ctx* ctx, const void* all_blobs /* device */, uint64_t stride, const uint64_t* sizes /* 4 per part */, uint32_t n_parts);
+/* canonical mate order (fusions.cpp:414-421) of the fragments other parts listed: arb_swaps_buffer = one byte per fragment on the device (1 = this part
+ * exchanged MATE1/MATE2), combined by the caller with a MAX all-reduce in place; arb_swaps_apply performs the exchanges this part has not done */
+int arb_swaps_buffer(arb_ctx* ctx, void** device_ptr, uint64_t* bytes);
+int arb_swaps_apply(arb_ctx* ctx);
+/* arb_filter_mismappers in two steps: _part re-aligns work items part, part + parts, ... and leaves one verdict byte per fragment on the device (combined by
+ * the caller with a MAX all-reduce in place: filter_mismappers.cpp:232-244 only counts verdicts); _finish labels fragments and candidates */
+int arb_filter_mismappers_part(arb_ctx* ctx, int32_t max_mate_gap, int part, int parts, void** device_verdicts, uint64_t* bytes);
+int arb_filter_mismappers_finish(arb_ctx* ctx, uint64_t* n_realigned);
+
 /* ---- device timing (CUDA events recorded on the context's stream around each stage) ---------------------------------- */
 typedef struct arb_timings {
 	float duplicates_ms;        /* duplicate marking (key build + hash group-by + mark) */
@@ -274,17 +303,17 @@ int arb_pipeline_create(arb_pipeline** out, const arb_run_options* options);
 void arb_pipeline_destroy(arb_pipeline* p);
 const char* arb_pipeline_error(arb_pipeline* p);   /* p may be NULL: error of arb_pipeline_create */
 int arb_pipeline_step(arb_pipeline* p, int step);  /* steps must be run in order */
-/* One sample on several GPUs (arriba_b200/csrc/host/shard.cpp). Every rank ingests the BAM, then keeps the fragments of the contig
- * pairs assigned to it (arb_pipeline_set_shard, before ARB_STEP_UPLOAD). Two exchanges follow, carried by the caller (e.g. NCCL all-gather of byte buffers):
- *   after ARB_STEP_READ_FILTERS:  export ARB_EXCHANGE_LABELS, all-gather, import    (fragment-length estimation needs all labels in name order)
- *   after ARB_STEP_FIND_FUSIONS:  export ARB_EXCHANGE_CANDIDATES, all-gather, import (merges the tables; the rank then holds the complete state)
- * After the second import every rank continues exactly like a single-GPU run; outputs are byte-identical for any world size. */
-enum { ARB_EXCHANGE_LABELS = 0, ARB_EXCHANGE_CANDIDATES = 1 };
-int arb_pipeline_plan_shard(arb_pipeline* p, int world); /* before ARB_STEP_INGEST: the run will be sharded (no early copy of the whole table) */
-int arb_pipeline_set_shard(arb_pipeline* p, int rank, int world);
-int arb_pipeline_shard_members(arb_pipeline* p, int rank, const uint32_t** fragments, uint64_t* n); /* name ranks assigned to `rank`, ascending (any rank may ask) */
-int arb_pipeline_export_shard(arb_pipeline* p, int what, const void** blob, uint64_t* bytes); /* blob stays valid until the next export */
-int arb_pipeline_import_shards(arb_pipeline* p, int what, const void* const* blobs, const uint64_t* bytes, uint32_t n_blobs /* = world, rank order */);
+/* One sample on several GPUs (the device side: "one sample on several GPUs" above; arriba_b200/sharded.py is the launcher-side driver). The part that
+ * ingests the BAM runs the pipeline as usual; it replicates its resident state to the other parts (arb_exchange_*), which only hold a context
+ * (arb_pipeline_attach_device: the run's parameters, no host data). arb_pipeline_work_partition (after ARB_STEP_ANNOTATE) assigns the contig pairs to the
+ * parts: keys ascending, owner[k] = part of keys[k]; pairs linked by duplicates stay together; heaviest first to the lightest part.
+ * arb_pipeline_mismappers_begin runs the event chain up to, not including, filter_mismappers and sends the stage's inputs to the device (active = 0: the
+ * stage is switched off); the launcher then calls arb_filter_mismappers_part / _finish on the contexts; arb_pipeline_mismappers_end takes the results back
+ * and the chain resumes with arb_pipeline_events. */
+int arb_pipeline_attach_device(arb_pipeline* p);
+int arb_pipeline_work_partition(arb_pipeline* p, int parts, const uint32_t** keys, const uint8_t** owner, uint32_t* n_keys);
+int arb_pipeline_mismappers_begin(arb_pipeline* p, int* active);
+int arb_pipeline_mismappers_end(arb_pipeline* p);
 int arb_pipeline_run(arb_pipeline* p);             /* all steps */
 arb_ctx* arb_pipeline_ctx(arb_pipeline* p);        /* device context (valid after ARB_STEP_UPLOAD) */
 int arb_pipeline_stats(arb_pipeline* p, arb_run_stats* out);

@@ -1,0 +1,14 @@
+#!/bin/bash
+# r02f: device annotation at full size (stacked dummy genes as list views), two-ranks-on-one-GPU protocol test
+set -u
+D=gpurun_out/r02f; mkdir -p $D
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $D/pytest_gpu.txt
+echo "== bench cfg2"; ARB_TRACE=1 timeout 900 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > $D/bench_cfg2.json 2> $D/bench_cfg2.err; echo "rc=$?"; tail -5 $D/bench_cfg2.err
+python - <<'P'
+import json
+l=json.loads(open('gpurun_out/r02f/bench_cfg2.json').read().strip().splitlines()[-1])
+print('e2e', l['e2e']['seconds_per_step'], 'parity', l['parity_md5_ok'], 'host', l['e2e']['host_seconds'])
+print(l['roofline']['device_ms'])
+P
+grep "^\[laps\]\|^\[ingest\]" /tmp/arb_bench/cfg2_10M_2x101_50k/out_rank0/library_stderr.log | tail -75 > $D/host_stage_laps_cfg2.txt
+grep annotate $D/host_stage_laps_cfg2.txt | tail -6
