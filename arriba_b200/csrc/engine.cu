@@ -19,6 +19,7 @@ engine::engine(): work_part(0), work_parts(1), mismap_items_total(0), mismap_ms_
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
 	mismap_group_pass = true; if (const char* s = getenv("ARB_MISMAP_GROUP")) mismap_group_pass = atoi(s) != 0;
+	mismap_group_lanes = 16; if (const char* s = getenv("ARB_MISMAP_GROUP_LANES")) mismap_group_lanes = (u32) atoi(s);
 	mismap_budget = 4096; mismap_lanes = 1024; mismap_spawn_budget = 0; mismap_task_lanes = 32;
 	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
 	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));

@@ -138,7 +138,7 @@ public:
 	u64 push_alignments, push_bases; u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
 	size_t cascade_smem_bytes; u32 cascade_resident_blocks; // launch shape of the sequence kernel on this context's device
 	int device;
-	bool mismap_group_pass; int mismap_budget, mismap_spawn_budget, mismap_min_blocks; u32 mismap_lanes, mismap_task_lanes, mismap_table_slots, homolog_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
+	bool mismap_group_pass; u32 mismap_group_lanes; int mismap_budget, mismap_spawn_budget, mismap_min_blocks; u32 mismap_lanes, mismap_task_lanes, mismap_table_slots, homolog_lanes; // work control of the re-alignment passes (mismap_hd.h, realign_ctl)
 	dbuf<u32> splice_off; dbuf<i32> splice_sites; bool has_splice_sites;
 	void set_splice_sites(const u32* off, const i32* sites);
 	u64 build_kmer_index(const u32* contig, const i32* start, const i32* end, u32 n, u32 n_index_contigs);

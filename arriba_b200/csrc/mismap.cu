@@ -8,22 +8,30 @@ namespace arb {
 
 #ifdef ARB_DEVICE_BUILD
 // pass 1 of the re-alignment: MISMAP_LANES lanes per (candidate, read) item, worklist of continuations in shared memory (mismap_hd.h, evaluate_group)
-static const u32 MISMAP_LANES = 8, MISMAP_THREADS = 256, MISMAP_GROUPS = MISMAP_THREADS / MISMAP_LANES, MISMAP_WORKLIST = 64;
-__global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
-	__shared__ realign_work tasks[MISMAP_GROUPS][MISMAP_WORKLIST];
-	__shared__ u32 tops[MISMAP_GROUPS];
-	const u32 group = threadIdx.x / MISMAP_LANES;
-	lane_group g; g.lane = threadIdx.x % MISMAP_LANES; g.lanes = MISMAP_LANES; g.mask = ((1u << MISMAP_LANES) - 1u) << ((threadIdx.x & 31u) / MISMAP_LANES * MISMAP_LANES);
-	const u32 j = blockIdx.x * MISMAP_GROUPS + group;
+static const u32 MISMAP_THREADS = 256, MISMAP_WORKLIST = 64;
+template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
+	const u32 GROUPS = MISMAP_THREADS / LANES, QUEUE = 4 * LANES;
+	__shared__ realign_work tasks[GROUPS][MISMAP_WORKLIST];
+	__shared__ realign_hit hits[GROUPS][QUEUE];
+	__shared__ u32 tops[GROUPS];
+	const u32 group = threadIdx.x / LANES;
+	lane_group g; g.lane = threadIdx.x % LANES; g.lanes = LANES; g.mask = (LANES >= 32 ? 0xFFFFFFFFu : ((1u << (LANES & 31u)) - 1u)) << ((threadIdx.x & 31u) / LANES * LANES);
+	const u32 j = blockIdx.x * GROUPS + group;
 	if (j >= n_items || it.skip(j)) return;
 	const u32 i = it.item_frag[j];
 	if (((const volatile u8*) it.mismapper)[i]) return; // another candidate's evaluation of this fragment already decided (the label is an OR)
 	realign_worklist wl = {tasks[group], &tops[group], MISMAP_WORKLIST};
-	const u32 verdict = evaluate_group(g, it, j, wl, budget);
+	realign_hit_queue hq = {hits[group], QUEUE};
+	const u32 verdict = evaluate_group(g, it, j, wl, hq, budget);
 	if (g.lane == 0) {
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomicAdd(n_heavy, 1u)] = j;
 	}
+}
+template <u32 LANES> static void launch_mismap_items(const exec_ctx& ex, const mismap_items& items, u32 I, int budget, u32* heavy, u32* n_heavy) {
+	const u32 GROUPS = MISMAP_THREADS / LANES;
+	k_mismap_items<LANES><<<(I + GROUPS - 1) / GROUPS, MISMAP_THREADS, 0, ex.stream>>>(items, I, budget, heavy, n_heavy);
+	ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels;
 }
 #endif
 
@@ -160,7 +168,11 @@ void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void*
 	auto launch = [&](u32 n, const auto& fn) { if (mismap_min_blocks >= 4) for_each_occ<4>(ex, n, fn); else if (mismap_min_blocks == 3) for_each_occ<3>(ex, n, fn); else for_each(ex, n, fn); };
 	if (mismap_group_pass) {
 #ifdef ARB_DEVICE_BUILD
-		if (I) { k_mismap_items<<<(I + MISMAP_GROUPS - 1) / MISMAP_GROUPS, MISMAP_THREADS, 0, ex.stream>>>(items, I, mismap_budget, heavy.ptr(), n_heavy.ptr()); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+		if (I) { // lanes per work item (ARB_MISMAP_GROUP_LANES): 16 measured best on the default workload (profiles/r02h)
+			if (mismap_group_lanes >= 32) launch_mismap_items<32>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());
+			else if (mismap_group_lanes >= 16) launch_mismap_items<16>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());
+			else launch_mismap_items<8>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());
+		}
 #else
 		mismap_item_group_fn mi = {items, mismap_budget, heavy.ptr(), n_heavy.ptr()};
 		for_each(ex, I, mi);

@@ -376,56 +376,95 @@ ARB_HD u32 env_kmer(const realign_env& env, u32 r) {
 	// and complements A/C/G/T/N; every other code keeps more than one bit and maps to 3 like the character it stands for
 	return nt16_dense2(brev32(nt16_window(env.seq, 0x7fffffffu, (i32) (env.off + env.len - 8 - r))));
 }
-// one search (top level or continuation) by the lanes of a group; returns whether THIS lane found a placement
-ARB_HD bool realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, u32& steps) {
+// One search (top level or continuation) by the lanes of a group, in two alternating phases:
+//   A  every lane takes one read position: 8-mer, bucket, the range of hits inside [lower bound, window end) -- regular work, all lanes busy, the loads of
+//      a whole group in flight together;
+//   B  the hits found (few per position, hundreds in a repeat) are written to the group's queue in shared memory and dealt to the lanes one by one, so a
+//      lane never idles because ITS position happened to have no hit: each lane extends one (position, hit) pair to the left and to the right.
+// Returns REALIGN_FOUND as soon as any lane reaches min_score, REALIGN_EXHAUSTED when the group has spent `budget` steps (the item then goes to pass 2).
+struct realign_hit { i32 hit; u32 read_pos; };
+struct realign_hit_queue { realign_hit* e; u32 capacity; };
+enum { REALIGN_UNDECIDED_NO = 0, REALIGN_FOUND = 1, REALIGN_EXHAUSTED = 2 };
+ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, const realign_worklist& wl, int read_pos, int hit, u32& steps) {
 	const u8* const seq = env.seq; const u32 off = env.off; const bool rc = env.rc; const int len = (int) env.len;
-	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
 	const i32 wstart = env.wstart, wend = env.wend; const int min_score = env.min_score;
 	const u32* const g4 = env.g4; const char* const ref = env.ref;
-	const int read_pos0 = task.read_pos, score0 = task.score, gene_pos = task.gene_pos, max_deletions = task.rc_deletions & 0x7f;
+	const int read_pos0 = task.read_pos, max_deletions = task.rc_deletions & 0x7f;
 	const bool leading = read_pos0 == 0; // every base before the seed was skipped: no penalty for them (local alignment start)
-	for (int read_pos = read_pos0 + (int) g.lane; ; read_pos += (int) g.lanes) {
-		const int skipped = read_pos - read_pos0, score = score0 - skipped;
-		if (!realign_can_start(score, read_pos, len, min_score)) return false; // the valid positions are a prefix
-		const u32 km = env_kmer(env, (u32) read_pos);
-		const u32 lo = bucket[km], hi = bucket[km + 1];
-		if (lo == hi) continue;
-		for (u32 h = lower_bound_i32(pos, lo, hi, gene_pos); h < hi; ++h) {
-			const int hit = pos[h];
-			if (hit >= wend) break;
-			++steps;
-			int ext = score + 8;
-			if (leading) ext += skipped;
-			if (ext >= min_score) return true;
-			{ // extend to the left over the skipped bases, one mismatch allowed
-				int r = read_pos - 1, gp = hit - 1; u32 mm = 0;
-				while (r >= read_pos - skipped && gp >= wstart) {
-					if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
-					else if (++mm > 1) break;
-					--r; --gp;
-				}
-			}
-			{ // extend to the right; a spliced continuation at splice sites and one deletion at the first mismatch go to the worklist
-				int r = read_pos + 8, gp = hit + 8; u32 mm = 0, consecutive = 0;
-				u32 ss = lower_bound_i32(env.splice, 0, env.n_splice, gp - 1);
-				i32 next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff;
-				while (r < len && gp <= wend) {
-					++steps;
-					if (gp - 1 >= next_site) {
-						if (gp - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
-						if (gp - 1 == next_site) worklist_push(wl, task, ext, r, gp, max_deletions, len, min_score);
-					}
-					if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
-					else {
-						if (++mm == 1 && max_deletions > 0 && len >= 30) worklist_push(wl, task, ext, r, gp, max_deletions - 1, len, min_score);
-						--ext;
-						if (++consecutive >= 4) break;
-					}
-					++r; ++gp;
-				}
-			}
+	const int skipped = read_pos - read_pos0, score = (int) task.score - skipped;
+	++steps;
+	int ext = score + 8;
+	if (leading) ext += skipped;
+	if (ext >= min_score) return true;
+	{ // extend to the left over the skipped bases, one mismatch allowed
+		int r = read_pos - 1, gp = hit - 1; u32 mm = 0;
+		while (r >= read_pos - skipped && gp >= wstart) {
+			if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
+			else if (++mm > 1) break;
+			--r; --gp;
 		}
 	}
+	{ // extend to the right; a spliced continuation at splice sites and one deletion at the first mismatch go to the worklist
+		int r = read_pos + 8, gp = hit + 8; u32 mm = 0, consecutive = 0;
+		u32 ss = lower_bound_i32(env.splice, 0, env.n_splice, gp - 1);
+		i32 next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff;
+		while (r < len && gp <= wend) {
+			++steps;
+			if (gp - 1 >= next_site) {
+				if (gp - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
+				if (gp - 1 == next_site) worklist_push(wl, task, ext, r, gp, max_deletions, len, min_score);
+			}
+			if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
+			else {
+				if (++mm == 1 && max_deletions > 0 && len >= 30) worklist_push(wl, task, ext, r, gp, max_deletions - 1, len, min_score);
+				--ext;
+				if (++consecutive >= 4) break;
+			}
+			++r; ++gp;
+		}
+	}
+	return false;
+}
+ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, const realign_hit_queue& hq, u32& steps, u32 step_limit) {
+	const int len = (int) env.len;
+	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
+	const i32 wend = env.wend; const int min_score = env.min_score;
+	const int read_pos0 = task.read_pos, score0 = task.score, gene_pos = task.gene_pos;
+	u32 fill = 0; // entries in the queue (the same value on every lane)
+	bool positions_left = true;
+	for (int base = read_pos0; positions_left || fill; base += (int) g.lanes) {
+		// ---- phase A: one read position per lane
+		u32 h0 = 0, remaining = 0; int read_pos = base + (int) g.lane;
+		if (positions_left) {
+			const bool valid = realign_can_start(score0 - (read_pos - read_pos0), read_pos, len, min_score); // the valid positions are a prefix
+			if (valid) {
+				const u32 km = env_kmer(env, (u32) read_pos);
+				const u32 lo = bucket[km], hi = bucket[km + 1];
+				if (lo != hi) { h0 = lower_bound_i32(pos, lo, hi, gene_pos); remaining = lower_bound_i32(pos, h0, hi, wend) - h0; }
+			}
+			positions_left = g.any(valid) && realign_can_start(score0 - (base + (int) g.lanes - read_pos0), base + (int) g.lanes, len, min_score);
+		}
+		// ---- phase B: queue the hits, drain the queue when it is full enough (or nothing is left to add)
+		for (;;) {
+			const u32 before = g.exclusive_sum(remaining), total = g.sum(remaining);
+			const u32 space = hq.capacity - fill;
+			const u32 take = before >= space ? 0u : hd_min(remaining, space - before);
+			for (u32 k = 0; k < take; ++k) { realign_hit e = {pos[h0 + k], (u32) read_pos}; hq.e[fill + before + k] = e; }
+			h0 += take; remaining -= take;
+			fill += hd_min(total, space);
+			const bool more_here = total > space;
+			if (!more_here && positions_left && fill + g.lanes <= hq.capacity / 2) break; // room for another round of positions
+			g.sync();
+			bool found = false;
+			for (u32 q = g.lane; q < fill && !found; q += g.lanes) found = realign_extend(env, task, wl, (int) hq.e[q].read_pos, hq.e[q].hit, steps);
+			if (g.any(found)) return REALIGN_FOUND;
+			if (step_limit && g.sum(steps) > step_limit) return REALIGN_EXHAUSTED;
+			g.sync();
+			fill = 0;
+			if (!more_here) break;
+		}
+	}
+	return REALIGN_UNDECIDED_NO;
 }
 
 // filter_mismappers.cpp:247-270 by a group: the lanes share the clipped bases
@@ -452,9 +491,8 @@ ARB_HD bool extends_linearly_group(const lane_group& g, const frag_view& f, cons
 #endif
 }
 
-enum { REALIGN_UNDECIDED_NO = 0, REALIGN_FOUND = 1, REALIGN_EXHAUSTED = 2 };
 // one item by a group: 0 = not mis-mapped, 1 = mis-mapped, 2 = gave up (worklist or budget), re-aligned cooperatively in pass 2
-ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, int budget) {
+ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, const realign_hit_queue& hq, int budget) {
 	if (g.lane == 0) *wl.top = 0;
 	g.sync();
 	if (it.item_kind[j] == 0 && extends_linearly_group(g, it.f, it.an, it.f.idx(it.item_frag[j], SPLIT_READ))) return REALIGN_FOUND;
@@ -492,8 +530,8 @@ ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, co
 		segment_env(s, task.gene_k, it.p.max_mate_gap, it.an, it.ix, it.sp, env); // it was usable when the task was made
 		if (task.rc_deletions & 0x80u) env.rc = !s.read.rc;
 		u32 steps = 0;
-		const bool found = realign_group(g, env, task, wl, steps);
-		if (g.any(found)) return REALIGN_FOUND;
+		const u32 verdict = realign_group(g, env, task, wl, hq, steps, budget > 0 && (u32) budget > total_steps ? (u32) budget - total_steps : (budget > 0 ? 1u : 0u));
+		if (verdict != REALIGN_UNDECIDED_NO) return verdict;
 		total_steps += g.sum(steps);
 		if (budget > 0 && total_steps > (u32) budget) return REALIGN_EXHAUSTED;
 		g.sync();
@@ -525,8 +563,9 @@ struct mismap_item_group_fn {
 		if (((const volatile u8*) it.mismapper)[i]) return;
 		realign_work tasks[64]; u32 top = 0;
 		realign_worklist wl = {tasks, &top, 64};
+		realign_hit hits[32]; realign_hit_queue hq = {hits, 32};
 		lane_group g; g.lane = 0; g.lanes = 1; g.mask = 1;
-		const u32 verdict = evaluate_group(g, it, j, wl, budget);
+		const u32 verdict = evaluate_group(g, it, j, wl, hq, budget);
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomic_add_u32(n_heavy, 1)] = j;
 	}

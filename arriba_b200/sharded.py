@@ -44,6 +44,12 @@ class Transport:
         self.direct = dist.get_backend() == "nccl" or not lib_is_cuda   # collectives run on the buffers themselves
         self.dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
+    def fence(self):
+        """The collectives run on the transport's own CUDA stream, the library's kernels on the context's: the host waits for the device before the library
+        touches a buffer a collective wrote (and before a buffer a collective still reads can be recycled)."""
+        if self.cuda:
+            self.torch.cuda.synchronize()
+
     def _bcast(self, v):
         if self.direct:
             self.dist.broadcast(v, 0)
@@ -77,6 +83,7 @@ class Transport:
         for p, b in ctx.exchange_buffers(group):
             if b:
                 self._bcast(view(p, b, self.cuda))
+        self.fence()
         if self.rank != 0:
             ctx.exchange_commit(group)
 
@@ -88,6 +95,7 @@ class Transport:
                 self.dist.all_reduce(v, op=self.dist.ReduceOp.MAX)
             else:
                 h = v.cpu(); self.dist.all_reduce(h, op=self.dist.ReduceOp.MAX); v.copy_(h)
+            self.fence()
 
     def gather_candidates(self, ctx):
         """the single all-gather of the candidate tables, then the merge on every rank"""
@@ -104,9 +112,9 @@ class Transport:
         dist.all_gather_into_tensor(recv, send)
         if self.cuda and not self.direct:
             recv = recv.cuda()
-        if self.cuda:
-            torch.cuda.synchronize()
+        self.fence()
         ctx.candidates_import(recv.data_ptr(), stride, [everyone[5 * r + k] for r in range(self.world) for k in range(4)], self.world)
+        self.fence()   # `recv` is released when this returns
 
 
 def run_sharded(pipeline, rank, world, last_event=None, write_output=True, reference_loaded=False):
