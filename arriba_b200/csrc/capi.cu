@@ -104,12 +104,18 @@ int arb_candidates_size(arb_ctx* ctx, uint32_t* n, uint64_t* n1, uint64_t* n2, u
 }
 int arb_get_candidates(arb_ctx* ctx, arb_candidates* out) { ARB_API_BEGIN(ctx) ctx->e.get_candidates(*out); ARB_API_END(ctx) }
 int arb_set_candidate_state(arb_ctx* ctx, const uint8_t* f, const uint32_t* s1, const uint32_t* s2, const uint32_t* dm, const float* ev) { ARB_API_BEGIN(ctx) ctx->e.set_candidate_state(f, s1, s2, dm, ev); ARB_API_END(ctx) }
+int arb_get_candidate_filters(arb_ctx* ctx, uint8_t* f) { ARB_API_BEGIN(ctx) ctx->e.cands.filter.download(ctx->e.ex, f, ctx->e.cands.n); ARB_API_END(ctx) }
 int arb_get_candidate_state(arb_ctx* ctx, uint8_t* f, uint32_t* s1, uint32_t* s2, uint32_t* dm, float* ev) { ARB_API_BEGIN(ctx) ctx->e.get_candidate_state(f, s1, s2, dm, ev); ARB_API_END(ctx) }
 int arb_set_candidate_lists(arb_ctx* ctx, const uint32_t* l1o, const uint32_t* l1, const uint32_t* l2o, const uint32_t* l2) { ARB_API_BEGIN(ctx) ctx->e.set_candidate_lists(l1o, l1, l2o, l2); ARB_API_END(ctx) }
 int arb_merge_adjacent(arb_ctx* ctx, int32_t max_distance, uint32_t* n) { ARB_API_BEGIN(ctx) uint32_t k = ctx->e.merge_adjacent(max_distance); if (n) *n = k; ARB_API_END(ctx) }
 int arb_get_merge_log(arb_ctx* ctx, uint32_t* triples, uint32_t n) { ARB_API_BEGIN(ctx) ctx->e.get_merge_log(triples, n); ARB_API_END(ctx) }
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in) { ARB_API_BEGIN(ctx) ctx->e.estimate_evalues(*in); ARB_API_END(ctx) }
 int arb_filter_relative_support(arb_ctx* ctx, float cutoff) { ARB_API_BEGIN(ctx) ctx->e.filter_relative_support(cutoff); ARB_API_END(ctx) }
+int arb_set_coverage(arb_ctx* ctx, const uint16_t* const* cov, const uint64_t* n_windows, uint32_t n_contigs) { ARB_API_BEGIN(ctx) std::vector<u64> w(n_windows, n_windows + n_contigs); ctx->e.set_coverage(cov, w.data(), n_contigs); ARB_API_END(ctx) }
+int arb_reads_by_gene(arb_ctx* ctx, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.reads_by_gene(out); ARB_API_END(ctx) }
+int arb_filter_in_vitro(arb_ctx* ctx, const uint32_t* reads, uint32_t n_genes, uint32_t threshold, const uint64_t* pairs, uint64_t n_pairs) { ARB_API_BEGIN(ctx) ctx->e.filter_in_vitro(reads, n_genes, threshold, (const u64*) pairs, n_pairs); ARB_API_END(ctx) }
+int arb_spliced_support(arb_ctx* ctx, const uint32_t* reads, uint32_t n_genes, uint32_t threshold, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.spliced_support(reads, n_genes, threshold, out); ARB_API_END(ctx) }
+int arb_filter_multimappers(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.filter_multimappers(); ARB_API_END(ctx) }
 int arb_set_splice_sites(arb_ctx* ctx, const uint32_t* off, const int32_t* sites) { ARB_API_BEGIN(ctx) ctx->e.set_splice_sites(off, sites); ARB_API_END(ctx) }
 int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* start, const int32_t* end, uint32_t n, uint32_t nc, uint64_t* n_indexed) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.build_kmer_index(contig, start, end, n, nc); if (n_indexed) *n_indexed = k; ARB_API_END(ctx) }
 int arb_kmer_index_digest(arb_ctx* ctx, uint64_t* kmers, uint64_t* positions, uint64_t* checksum, uint32_t nc) { ARB_API_BEGIN(ctx) ctx->e.kmer_index_digest(kmers, positions, checksum, nc); ARB_API_END(ctx) }

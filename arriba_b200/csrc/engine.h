@@ -131,10 +131,15 @@ public:
 	u32 merge_adjacent(i32 max_distance);
 	void get_merge_log(u32* triples, u32 n);
 	void estimate_evalues(const arb_evalue_inputs& in);
-	void filter_relative_support(float cutoff);
+	void filter_relative_support(float cutoff); void filter_multimappers();
 	dbuf<u32> merge_log; u32 merge_log_n;
+	// filter_in_vitro on the device (events.cu): coverage windows of the sample, expression per gene
+	void set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs); void reads_by_gene(u32* out);
+	void filter_in_vitro(const u32* reads, u32 n_genes, u32 threshold, const u64* pairs, u64 n_pairs); void spliced_support(const u32* reads, u32 n_genes, u32 threshold, u32* support_out);
+	dbuf<u16> coverage_windows; dbuf<u64> coverage_off; dbuf<u32> coverage_n; u32 coverage_contigs;
 	// k-mer index / re-alignment
 	dbuf<i32> kmer_pos; dbuf<u32> kmer_bucket_off; u32 kmer_index_contigs; u64 kmer_indexed;
+	dbuf<u32> kmer_block_first, kmer_block_base; u32 kmer_block_shift, kmer_blocks; struct kmer_index_view index_view(); // block table of the index (mismap_hd.h)
 	u64 push_alignments, push_bases; u64 head_bytes, sequence_bytes; // column budgets of the two cascade launches for the resident chunk
 	size_t cascade_smem_bytes; u32 cascade_resident_blocks; // launch shape of the sequence kernel on this context's device
 	int device;

@@ -111,4 +111,75 @@ void engine::filter_relative_support(float cutoff) {
 	ex.sync();
 }
 
+// ------------------------------------------------------------------------------------------- filter_in_vitro and its inputs
+void engine::set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs) {
+	std::vector<u64> off(n_contigs, 0); std::vector<u32> wins(n_contigs, 0);
+	u64 total = 0;
+	for (u32 c = 0; c < n_contigs; ++c) { off[c] = total; if (n_windows[c] > 0xFFFFFFFFull) throw arb_error("arb_set_coverage: contig too long"); wins[c] = (u32) n_windows[c]; total += n_windows[c]; }
+	coverage_windows.ensure(total + 1);
+	for (u32 c = 0; c < n_contigs; ++c) if (n_windows[c]) {
+#ifdef ARB_DEVICE_BUILD
+		ARB_CUDA_CHECK(cudaMemcpyAsync(coverage_windows.ptr() + off[c], per_contig[c], n_windows[c] * 2, cudaMemcpyHostToDevice, ex.stream));
+#else
+		memcpy(coverage_windows.ptr() + off[c], per_contig[c], n_windows[c] * 2);
+#endif
+	}
+	coverage_off.upload(ex, off.data(), n_contigs); coverage_n.upload(ex, wins.data(), n_contigs);
+	coverage_contigs = n_contigs;
+	ex.sync();
+}
+
+void engine::reads_by_gene(u32* out) {
+	dbuf<u32> reads(annot.n_genes); reads.zero(ex, annot.n_genes);
+	reads_by_gene_fn fn = {frags.view(), reads.ptr()};
+	for_each(ex, frags.n, fn);
+	reads.download(ex, out, annot.n_genes);
+}
+
+void engine::filter_in_vitro(const u32* reads, u32 n_genes, u32 threshold, const u64* pairs, u64 n_pairs) {
+	if (n_genes != annot.n_genes) throw arb_error("arb_filter_in_vitro: reads_by_gene must have one entry per gene");
+	if (coverage_contigs == 0) throw arb_error("arb_filter_in_vitro: arb_set_coverage must be called first");
+	const u32 C = cands.n;
+	if (C == 0) return;
+	dbuf<u32> d_reads; dbuf<u64> d_pairs;
+	d_reads.upload(ex, reads, n_genes); d_pairs.upload(ex, pairs, n_pairs);
+	stage_timer t_all(ex);
+	coverage_view cov = {coverage_windows.ptr(), coverage_off.ptr(), coverage_n.ptr(), coverage_contigs};
+	in_vitro_inputs in = {d_reads.ptr(), threshold, d_pairs.ptr(), n_pairs};
+	in_vitro_fn fn = {make_state(cands, NULL, NULL), frags.view(), annot.view(), cov, in, cands.listd_off.ptr(), cands.listd.ptr()};
+	for_each(ex, C, fn);
+	timings.in_vitro_ms = t_all.stop();
+	ex.sync();
+}
+
+void engine::spliced_support(const u32* reads, u32 n_genes, u32 threshold, u32* support_out) {
+	if (n_genes != annot.n_genes) throw arb_error("arb_spliced_support: reads_by_gene must have one entry per gene");
+	if (coverage_contigs == 0) throw arb_error("arb_spliced_support: arb_set_coverage must be called first");
+	const u32 C = cands.n;
+	if (C == 0) return;
+	dbuf<u32> d_reads, d_support(C);
+	d_reads.upload(ex, reads, n_genes);
+	coverage_view cov = {coverage_windows.ptr(), coverage_off.ptr(), coverage_n.ptr(), coverage_contigs};
+	spliced_support_fn fn = {make_state(cands, NULL, NULL), frags.view(), annot.view(), cov, d_reads.ptr(), threshold,
+	                         cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(), d_support.ptr()};
+	for_each(ex, C, fn);
+	d_support.download(ex, support_out, C);
+}
+
+void engine::filter_multimappers() {
+	const u32 C = cands.n, N = frags.n;
+	if (C == 0 || N == 0) return;
+	stage_timer t_all(ex);
+	dbuf<u32> best(N); best.fill_bytes(ex, 0xFF, N);
+	cand_state s = make_state(cands, NULL, NULL);
+	multimapper_best_fn bf = {s, annot.view(), frags.view(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr(), best.ptr()};
+	for_each(ex, C, bf);
+	multimapper_cluster_fn cf = {s, annot.view(), frags.view(), best.ptr()};
+	for_each(ex, N, cf);
+	multimapper_recount_fn rf = {s, frags.view(), cands.list1_off.ptr(), cands.list1.ptr(), cands.list2_off.ptr(), cands.list2.ptr(), cands.listd_off.ptr(), cands.listd.ptr()};
+	for_each(ex, C, rf);
+	timings.multimappers_ms = t_all.stop();
+	ex.sync();
+}
+
 } // namespace arb

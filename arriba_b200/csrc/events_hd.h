@@ -186,4 +186,245 @@ struct relative_support_fn { // filter_relative_support.cpp:209-223
 	}
 };
 
+// ---- expression per gene (filter_in_vitro.cpp:48-83): supporting fragments per gene of MATE1 and of the last alignment
+struct reads_by_gene_fn {
+	frag_view f; u32* reads;
+	ARB_HD void operator()(u32 i) const {
+		const u32 a = f.idx(i, 0), b = f.idx(i, f.n_aln[i] == 2 ? 1 : 2);
+		for (u32 g = 0; g < f.genes_cnt[a]; ++g) atomic_add_u32(&reads[f.genes[f.genes_off[a] + g]], 1);
+		for (u32 g = 0; g < f.genes_cnt[b]; ++g) atomic_add_u32(&reads[f.genes[f.genes_off[b] + g]], 1);
+	}
+};
+
+// coverage windows on the device (read_stats.cpp:268-306): 20 bp windows per contig, one flat array
+struct coverage_view {
+	const u16* windows; const u64* contig_off; const u32* contig_windows; u32 n_contigs;
+	ARB_HD int get(u32 contig, i32 position, u32 direction) const {
+		if (contig >= n_contigs || contig_windows[contig] == 0) return -1;
+		const u16* c = windows + contig_off[contig];
+		if (direction == UPSTREAM) return position < 20 ? 0 : (int) c[position / 20 - 1];
+		return (int) c[position / 20 + 1];
+	}
+};
+
+// ---- filter_in_vitro (filter_in_vitro.cpp:85-228), one thread per candidate: the verdict of a candidate does not depend on the other verdicts
+struct in_vitro_inputs { const u32* reads_by_gene; u32 threshold; const u64* exonic_pairs; u64 n_pairs; };
+struct in_vitro_fn {
+	cand_state c; frag_view f; annot_view an; coverage_view cov; in_vitro_inputs in;
+	const u32* listd_off; const u32* listd;
+	ARB_HD u32 higher_expressed(u16 contig, i32 bp, u32 gene) const { // the most expressed gene at the breakpoint, the candidate's own gene unless another one has more reads
+		u32 highest = in.reads_by_gene[gene];
+		if (contig >= an.n_contigs) return gene;
+		const u32 lo = an.gene_region_begin[contig], hi = an.gene_region_begin[contig + 1];
+		const u32 r = region_lower_bound(an.gene_region_end, lo, hi, bp);
+		if (r < hi) for (u32 x = an.gene_region_off[r]; x < an.gene_region_off[r + 1]; ++x) { const u32 g = an.gene_region_items[x]; if (in.reads_by_gene[g] > highest) { highest = in.reads_by_gene[g]; gene = g; } }
+		return gene;
+	}
+	ARB_HD u32 pair_count(u32 a, u32 b) const { // width of the equal range of (a, b) in the sorted pair list
+		const u64 key = (u64) a << 32 | b;
+		u64 lo = 0, hi = in.n_pairs;
+		while (lo < hi) { const u64 mid = lo + ((hi - lo) >> 1); if (in.exonic_pairs[mid] < key) lo = mid + 1; else hi = mid; }
+		u64 lo2 = lo, hi2 = in.n_pairs;
+		while (lo2 < hi2) { const u64 mid = lo2 + ((hi2 - lo2) >> 1); if (in.exonic_pairs[mid] <= key) lo2 = mid + 1; else hi2 = mid; }
+		return (u32) (lo2 - lo);
+	}
+	ARB_HD void operator()(u32 k) const {
+		const u8 fl = c.filter[k]; const u8 bits = c.bits[k];
+		const bool spliced1 = bits & CB_SPLICED1, spliced2 = bits & CB_SPLICED2, exonic1 = bits & CB_EXONIC1, exonic2 = bits & CB_EXONIC2;
+		if (fl != F_none && !((spliced1 || spliced2) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) return;
+		float rt = 0;
+		if (!exonic1) rt += 0.5f; else if (!spliced1) rt += 1;
+		if (!exonic2) rt += 0.5f; else if (!spliced2) rt += 1;
+		const u32 own_split = c.split_reads1[k] + c.split_reads2[k], dm = c.discordant_mates[k];
+		if (own_split > 2 && own_split * 2 > dm) return; // total_split >= own_split: "total_split * 2 <= discordant_mates || total_split <= 2" cannot hold
+		const u16 contig1 = c.contig1[k], contig2 = c.contig2[k]; const i32 bp1 = c.bp1[k], bp2 = c.bp2[k];
+		const u32 g1 = higher_expressed(contig1, bp1, c.gene1[k]), g2 = higher_expressed(contig2, bp2, c.gene2[k]);
+		const u32 x1 = in.reads_by_gene[g1], x2 = in.reads_by_gene[g2];
+		if (!(x1 + x2 > in.threshold)) return; // only breakpoints in highly expressed genes are suspected
+		u32 clipped1 = 0, clipped2 = 0;
+		for (u32 p = listd_off[k]; p < listd_off[k + 1]; ++p) {
+			const u32 i = listd[p];
+			if (f.filter[i] != F_none) continue;
+			for (u32 s = 0; s < f.n_aln[i]; ++s) {
+				const u32 a = f.idx(i, s);
+				if (f.fwd(a) && f.postclip(a) >= 3) { if (f.contig[a] == contig1 && f.end[a] == bp1) ++clipped1; else if (f.contig[a] == contig2 && f.end[a] == bp2) ++clipped2; }
+				else if (!f.fwd(a) && f.preclip(a) >= 3) { if (f.contig[a] == contig1 && f.start[a] == bp1) ++clipped1; else if (f.contig[a] == contig2 && f.start[a] == bp2) ++clipped2; }
+			}
+		}
+		const u32 total_split = hd_min(clipped1, clipped2) + own_split;
+		if (!(total_split * 2 <= dm || total_split <= 2)) return;
+		if (!((double) total_split <= 2 + 0.0001 * (double) (x1 + x2))) return;
+		const u32 sup = own_split + dm;
+		if (sup >= 10 && (spliced1 || spliced2) && ((spliced1 || !exonic1) && (spliced2 || !exonic2))) {
+			const int cov1 = cov.get(contig1, bp1, c.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM), cov2 = cov.get(contig2, bp2, c.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+			if (((int) sup * 4) >= hd_max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup) return; // well covered on both sides: kept
+		}
+		const u32 threshold = in.threshold;
+		if (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || sup <= 1 ||
+		    hd_max(pair_count(g1, g2), pair_count(c.gene1[k], c.gene2[k])) > 8)
+			c.filter[k] = F_in_vitro;
+	}
+};
+
+// ---- recover_both_spliced: spliced support of a candidate (recover_both_spliced.cpp:15-62), a pure function of the candidate
+struct spliced_support_fn {
+	cand_state c; frag_view f; annot_view an; coverage_view cov; const u32* reads_by_gene; u32 threshold;
+	const u32* l1o; const u32* l1; const u32* l2o; const u32* l2; const u32* ldo; const u32* ld; u32* support; // 0xFFFFFFFF: not eligible
+	ARB_HD bool both_spliced(u32 k) const { // common.hpp:280-284
+		const u8 bits = c.bits[k];
+		const bool f1 = an.gene_strand[c.gene1[k]], f2 = an.gene_strand[c.gene2[k]];
+		return (bits & CB_SPLICED1) && (bits & CB_SPLICED2) && ((f1 == f2 && c.dir1[k] != c.dir2[k]) || (f1 != f2 && c.dir1[k] == c.dir2[k]));
+	}
+	ARB_HD bool long_exon_at(u16 contig, i32 bp) const { // any exon over the breakpoint longer than 1000 bases (a point query returns the region's items)
+		if (contig >= an.n_contigs) return false;
+		const u32 lo = an.exon_region_begin[contig], hi = an.exon_region_begin[contig + 1];
+		const u32 r = region_lower_bound(an.exon_region_end, lo, hi, bp);
+		if (r < hi) for (u32 x = an.exon_region_off[r]; x < an.exon_region_off[r + 1]; ++x) { const u32 e = an.exon_region_items[x]; if (an.exon_end[e] + 1 - an.exon_start[e] > 1000) return true; }
+		return false;
+	}
+	ARB_HD void scan(const u32* off, const u32* list, u32 k, u32& multi, u32& unique) const {
+		for (u32 p = off[k]; p < off[k + 1]; ++p) { const u32 i = list[p]; if (f.fflags[i] & FF_MULTIMAPPER) ++multi; else if (f.filter[i] == F_none) ++unique; }
+	}
+	ARB_HD u32 spliced_support(u32 k) const {
+		const u32 max_coverage = 1000; // arriba.cpp:492
+		const bool bs = both_spliced(k);
+		if (reads_by_gene[c.gene1[k]] > threshold || reads_by_gene[c.gene2[k]] > threshold) return (bs && c.discordant_mates[k] <= c.split_reads1[k] + c.split_reads2[k]) ? 1u : 0u;
+		if (!bs) {
+			const u32 cov1 = (u32) cov.get(c.contig1[k], c.bp1[k], c.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM), cov2 = (u32) cov.get(c.contig2[k], c.bp2[k], c.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
+			if (cov1 + cov2 > cand_support(c, k) * max_coverage) return 0;
+			if (long_exon_at(c.contig1[k], c.bp1[k]) || long_exon_at(c.contig2[k], c.bp2[k])) return 0;
+		}
+		u32 multi = 0, unique = 0;
+		scan(l1o, l1, k, multi, unique); scan(l2o, l2, k, multi, unique); scan(ldo, ld, k, multi, unique);
+		const u32 listed = (l1o[k + 1] - l1o[k]) + (l2o[k + 1] - l2o[k]) + (ldo[k + 1] - ldo[k]);
+		if ((double) multi >= 0.5 * (double) listed) return 0;
+		return unique == 0 ? 1u : unique;
+	}
+	ARB_HD void operator()(u32 k) const {
+		support[k] = 0xFFFFFFFFu;
+		const u8 fl = c.filter[k];
+		if (fl == F_merge_adjacent) return;
+		if (fl == F_none || fl == F_in_vitro || fl == F_intronic || fl == F_relative_support || fl == F_min_support || (fl == F_inconsistently_clipped && both_spliced(k))) {
+			const u32 s = spliced_support(k);
+			if (s > 0) support[k] = s;
+		}
+	}
+};
+
+// ---- filter_multimappers (filter_multimappers.cpp:14-168)
+// alignment score of a fragment (:14-77): matches +1, insertions / deletions / introns off splice sites -1
+ARB_HD bool any_gene_spliced(const frag_view& f, const annot_view& an, u32 a, i32 pos, u32 direction) {
+	for (u32 k = 0; k < f.genes_cnt[a]; ++k) if (is_breakpoint_spliced(an, f.genes[f.genes_off[a] + k], direction, pos)) return true;
+	return false;
+}
+ARB_HD int segment_score(const frag_view& f, const annot_view& an, u32 a, const u8* seq, u32 seq_len, bool revcomp) {
+	const u32 contig = f.contig[a];
+	if (an.contig_len[contig] == 0) return 0;
+	int score = 0; i32 ref = f.start[a]; u32 rp = 0;
+	const u32* c = f.cig(a);
+	const u64 base = an.contig_seq_off[contig];
+	for (u32 k = 0; k < f.cigar_cnt[a]; ++k) {
+		const u32 op = cig_op(c[k]), len = cig_len(c[k]);
+		switch (op) {
+			case C_S: case C_H: rp += len; break;
+			case C_D: --score; ref += (i32) len; break;
+			case C_N: if (!any_gene_spliced(f, an, a, ref, DOWNSTREAM) || !any_gene_spliced(f, an, a, ref + (i32) len, UPSTREAM)) --score; ref += (i32) len; break;
+			case C_I: --score; rp += len; break;
+			case C_EQ: score += (int) len; ref += (i32) len; rp += len; break;
+			case C_X: ref += (i32) len; rp += len; break;
+			case C_M:
+				for (u32 j = 0; j < len; ++j, ++ref, ++rp) {
+					if (rp >= seq_len) continue;
+					const u32 code = revcomp ? nt16_complement(nt16_at(seq, seq_len - 1 - rp)) : nt16_at(seq, rp);
+					if ((u32) ref < an.contig_len[contig] && nt16_char(code) == an.assembly[base + (u32) ref]) ++score;
+				}
+				break;
+			default: break;
+		}
+	}
+	return score;
+}
+ARB_HD int alignment_score(const frag_view& f, const annot_view& an, u32 i) {
+	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
+	int score = segment_score(f, an, a0, f.sq(a0), f.seq_len[a0], false) + segment_score(f, an, a1, f.sq(a1), f.seq_len[a1], false);
+	if (f.n_aln[i] == 3) {
+		score += segment_score(f, an, a2, f.sq(a1), f.seq_len[a1], f.fwd(a2) != f.fwd(a1));
+		if (!any_gene_spliced(f, an, a2, f.fwd(a2) ? f.end[a2] : f.start[a2], f.fwd(a2) ? DOWNSTREAM : UPSTREAM) || !any_gene_spliced(f, an, a1, f.fwd(a1) ? f.start[a1] : f.end[a1], f.fwd(a1) ? UPSTREAM : DOWNSTREAM)) --score;
+	}
+	return score;
+}
+// total order "has more support" (filter_multimappers.cpp:79-113): is candidate x better than y?
+ARB_HD bool cand_better(const cand_state& c, const annot_view& an, u32 x, u32 y) {
+	const u32 sx = cand_support(c, x), sy = cand_support(c, y);
+	if (sy != sx) return sy < sx;
+	const bool c1x = an.gene_flags[c.gene1[x]] & GF_CODING, c1y = an.gene_flags[c.gene1[y]] & GF_CODING;
+	if (c1x != c1y) return c1x;
+	const bool c2x = an.gene_flags[c.gene2[x]] & GF_CODING, c2y = an.gene_flags[c.gene2[y]] & GF_CODING;
+	if (c2x != c2y) return c2x;
+	if (c.contig1[x] != c.contig1[y]) return c.contig1[x] < c.contig1[y];
+	if (c.contig2[x] != c.contig2[y]) return c.contig2[x] < c.contig2[y];
+	if (c.bp1[x] != c.bp1[y]) return c.bp1[x] < c.bp1[y];
+	if (c.bp2[x] != c.bp2[y]) return c.bp2[x] < c.bp2[y];
+	if (c.dir1[x] != c.dir1[y]) return c.dir1[x] < c.dir1[y];
+	if (c.dir2[x] != c.dir2[y]) return c.dir2[x] < c.dir2[y];
+	if (c.gene1[x] != c.gene1[y]) return c.gene1[x] < c.gene1[y];
+	return c.gene2[x] < c.gene2[y];
+}
+// most supported candidate per multi-mapping fragment: the order is total, so the result does not depend on who comes first (compare-and-swap per fragment)
+struct multimapper_best_fn {
+	cand_state c; annot_view an; frag_view f; const u32* l1o; const u32* l1; const u32* l2o; const u32* l2; const u32* ldo; const u32* ld; u32* best;
+	ARB_HD void consider(u32 cand, u32 frag) const {
+		if (!(f.fflags[frag] & FF_MULTIMAPPER)) return;
+		u32 seen = *(volatile u32*) &best[frag];
+		for (;;) {
+			if (!(seen == 0xFFFFFFFFu || cand_better(c, an, cand, seen))) return;
+			const u32 was = atomic_cas_u32(&best[frag], seen, cand);
+			if (was == seen) return;
+			seen = was;
+		}
+	}
+	ARB_HD void operator()(u32 k) const {
+		for (u32 p = l1o[k]; p < l1o[k + 1]; ++p) consider(k, l1[p]);
+		for (u32 p = l2o[k]; p < l2o[k + 1]; ++p) consider(k, l2[p]);
+		for (u32 p = ldo[k]; p < ldo[k + 1]; ++p) consider(k, ld[p]);
+	}
+};
+// clusters = maximal runs of fragments that share the read name (FF_SAME_NAME_AS_PREVIOUS marks the members after the first); one thread per cluster:
+// the member with the best alignment score survives, ties go to the one whose best candidate has more support (:128-151)
+struct multimapper_cluster_fn {
+	cand_state c; annot_view an; frag_view f; const u32* best;
+	ARB_HD bool more_support(u32 fa, u32 fb) const {
+		const u32 x = best[fa], y = best[fb];
+		if (x == 0xFFFFFFFFu) return false;
+		if (y == 0xFFFFFFFFu) return true;
+		return cand_better(c, an, x, y);
+	}
+	ARB_HD void operator()(u32 i) const {
+		const u8 fl = f.fflags[i];
+		if (!(fl & FF_MULTIMAPPER) || (fl & FF_SAME_NAME_AS_PREVIOUS)) return;
+		u32 j = i + 1;
+		while (j < f.n && (f.fflags[j] & FF_SAME_NAME_AS_PREVIOUS)) ++j;
+		if (j - i <= 1) return;
+		u32 best_frag = 0xFFFFFFFFu; int best_score = (int) 0x80000000;
+		for (u32 x = i; x < j; ++x) {
+			const int s = alignment_score(f, an, x);
+			if (best_score < s) { best_frag = x; best_score = s; }
+			else if (best_score == s && more_support(x, best_frag)) best_frag = x;
+		}
+		for (u32 x = i; x < j; ++x) if (x != best_frag && f.filter[x] == F_none) f.filter[x] = F_multimappers;
+	}
+};
+struct multimapper_recount_fn { // :153-166
+	cand_state c; frag_view f; const u32* l1o; const u32* l1; const u32* l2o; const u32* l2; const u32* ldo; const u32* ld;
+	ARB_HD void operator()(u32 k) const {
+		if (c.filter[k] != F_none || cand_support(c, k) == 0) return;
+		u32 s1 = c.split_reads1[k], s2 = c.split_reads2[k], dm = c.discordant_mates[k];
+		for (u32 p = l1o[k]; p < l1o[k + 1]; ++p) if (f.filter[l1[p]] == F_multimappers && s1 > 0) --s1;
+		for (u32 p = l2o[k]; p < l2o[k + 1]; ++p) if (f.filter[l2[p]] == F_multimappers && s2 > 0) --s2;
+		for (u32 p = ldo[k]; p < ldo[k + 1]; ++p) if (f.filter[ld[p]] == F_multimappers && dm > 0) --dm;
+		c.split_reads1[k] = s1; c.split_reads2[k] = s2; c.discordant_mates[k] = dm;
+		if (s1 + s2 + dm == 0) c.filter[k] = F_multimappers;
+	}
+};
+
 } // namespace arb

@@ -39,7 +39,7 @@ void engine::exchange_header(int group, std::vector<u64>& h) {
 			break;
 		case XG_MISMAP_STATE:
 			h.push_back(cands.n); h.push_back(cands.n_list1); h.push_back(cands.n_list2); h.push_back(frags.n); h.push_back(kmer_indexed); h.push_back(kmer_index_contigs);
-			h.push_back(annot.n_genes); h.push_back(n_splice_sites); h.push_back(has_splice_sites ? 1 : 0);
+			h.push_back(annot.n_genes); h.push_back(n_splice_sites); h.push_back(has_splice_sites ? 1 : 0); h.push_back(kmer_block_shift); h.push_back(kmer_blocks);
 			break;
 		default: throw arb_error("exchange: unknown group");
 	}
@@ -81,7 +81,7 @@ void engine::exchange_prepare(int group, const u64* h, u32 n_words) {
 			break;
 		}
 		case XG_MISMAP_STATE: {
-			need(10);
+			need(12);
 			if ((u32) h[1] != cands.n || (u32) h[4] != frags.n) throw arb_error("exchange: re-alignment state of another candidate table / fragment table");
 			cands.n_list1 = h[2]; cands.n_list2 = h[3];
 			cands.list1.ensure(cands.n_list1); cands.list2.ensure(cands.n_list2);
@@ -91,6 +91,8 @@ void engine::exchange_prepare(int group, const u64* h, u32 n_words) {
 			n_splice_sites = h[8];
 			splice_off.ensure((size_t) annot.n_genes + 1); splice_sites.ensure(n_splice_sites);
 			has_splice_sites = h[9] != 0;
+			kmer_block_shift = (u32) h[10]; kmer_blocks = (u32) h[11];
+			kmer_block_base.ensure((size_t) kmer_index_contigs + 1); kmer_block_first.ensure((u64) kmer_blocks << 16);
 			break;
 		}
 		default: throw arb_error("exchange: unknown group");
@@ -129,6 +131,7 @@ void engine::exchange_buffers(int group, std::vector<exchange_buffer>& out) {
 			add_buf(out, frags.filter, frags.n);
 			add_buf(out, kmer_pos, kmer_indexed); add_buf(out, kmer_bucket_off, (u64) kmer_index_contigs * 65536 + 2);
 			add_buf(out, splice_off, (u64) annot.n_genes + 1); add_buf(out, splice_sites, n_splice_sites);
+			add_buf(out, kmer_block_base, (u64) kmer_index_contigs + 1); add_buf(out, kmer_block_first, kmer_block_shift ? (u64) kmer_blocks << 16 : 0);
 			break;
 		}
 		default: throw arb_error("exchange: unknown group");

@@ -249,128 +249,13 @@ void pipeline::merge_adjacent() {
 	log_remaining("Merging adjacent fusion breakpoints");
 }
 
-// ------------------------------------------------------------------------------------------- multimappers (filter_multimappers.cpp)
-static int segment_score(const frag_view& f, const annot_view& an, u32 a, const u8* seq, u32 seq_len, bool revcomp) {
-	const u32 contig = f.contig[a];
-	if (an.contig_len[contig] == 0) return 0;
-	int score = 0; i32 ref = f.start[a]; u32 rp = 0;
-	const u32* c = f.cig(a);
-	const u64 base = an.contig_seq_off[contig];
-	auto gap_at_splice_site = [&](i32 pos, u32 direction) { for (u32 k = 0; k < f.genes_cnt[a]; ++k) if (is_breakpoint_spliced(an, f.genes[f.genes_off[a] + k], direction, pos)) return true; return false; };
-	for (u32 k = 0; k < f.cigar_cnt[a]; ++k) {
-		const u32 op = cig_op(c[k]), len = cig_len(c[k]);
-		switch (op) {
-			case C_S: case C_H: rp += len; break;
-			case C_D: --score; ref += (i32) len; break;
-			case C_N: if (!gap_at_splice_site(ref, DOWNSTREAM) || !gap_at_splice_site(ref + (i32) len, UPSTREAM)) --score; ref += (i32) len; break;
-			case C_I: --score; rp += len; break;
-			case C_EQ: score += (int) len; ref += (i32) len; rp += len; break;
-			case C_X: ref += (i32) len; rp += len; break;
-			case C_M:
-				for (u32 j = 0; j < len; ++j, ++ref, ++rp) {
-					if (rp >= seq_len) continue;
-					const u32 code = revcomp ? nt16_complement(nt16_at(seq, seq_len - 1 - rp)) : nt16_at(seq, rp);
-					if ((u32) ref < an.contig_len[contig] && nt16_char(code) == an.assembly[base + (u32) ref]) ++score;
-				}
-				break;
-			default: break;
-		}
-	}
-	return score;
-}
-static int alignment_score(const frag_view& f, const annot_view& an, u32 i) {
-	const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1), a2 = f.idx(i, 2);
-	int score = segment_score(f, an, a0, f.sq(a0), f.seq_len[a0], false) + segment_score(f, an, a1, f.sq(a1), f.seq_len[a1], false);
-	if (f.n_aln[i] == 3) {
-		score += segment_score(f, an, a2, f.sq(a1), f.seq_len[a1], f.fwd(a2) != f.fwd(a1));
-		auto any_spliced = [&](u32 a, i32 pos, u32 direction) { for (u32 k = 0; k < f.genes_cnt[a]; ++k) if (is_breakpoint_spliced(an, f.genes[f.genes_off[a] + k], direction, pos)) return true; return false; };
-		if (!any_spliced(a2, f.fwd(a2) ? f.end[a2] : f.start[a2], f.fwd(a2) ? DOWNSTREAM : UPSTREAM) || !any_spliced(a1, f.fwd(a1) ? f.start[a1] : f.end[a1], f.fwd(a1) ? UPSTREAM : DOWNSTREAM)) --score;
-	}
-	return score;
-}
-
-void pipeline::filter_multimappers() {
-	event_table& e = ev;
-	const frag_view f = frags.view(); const annot_view an = ref.host_view();
-	const u32 N = frags.n;
-	// total order "has more support" (filter_multimappers.cpp:79-113); smaller rank = better
-	auto better = [&](u32 x, u32 y) { // is candidate x better than y?
-		if (e.supporting_reads(y) != e.supporting_reads(x)) return e.supporting_reads(y) < e.supporting_reads(x);
-		const bool c1x = ref.genes[e.gene1[x]].is_protein_coding, c1y = ref.genes[e.gene1[y]].is_protein_coding;
-		if (c1x != c1y) return c1x;
-		const bool c2x = ref.genes[e.gene2[x]].is_protein_coding, c2y = ref.genes[e.gene2[y]].is_protein_coding;
-		if (c2x != c2y) return c2x;
-		if (e.contig1[x] != e.contig1[y]) return e.contig1[x] < e.contig1[y];
-		if (e.contig2[x] != e.contig2[y]) return e.contig2[x] < e.contig2[y];
-		if (e.bp1[x] != e.bp1[y]) return e.bp1[x] < e.bp1[y];
-		if (e.bp2[x] != e.bp2[y]) return e.bp2[x] < e.bp2[y];
-		if (e.dir1[x] != e.dir1[y]) return e.dir1[x] < e.dir1[y];
-		if (e.dir2[x] != e.dir2[y]) return e.dir2[x] < e.dir2[y];
-		if (e.gene1[x] != e.gene1[y]) return e.gene1[x] < e.gene1[y];
-		return e.gene2[x] < e.gene2[y];
-	};
-	stage_laps laps("multimappers");
-	const u32 NONE = 0xFFFFFFFFu;
-	std::vector<u32> best(N, NONE); // most supported candidate per multimapping fragment
-	// `better` is a total order, so the best candidate of a fragment does not depend on the visiting order: candidates in parallel, compare-and-swap per fragment
-	auto consider = [&](u32 cand, u32 frag) {
-		if (!(frags.fflags[frag] & FF_MULTIMAPPER)) return;
-		u32 seen = __atomic_load_n(&best[frag], __ATOMIC_RELAXED);
-		while ((seen == NONE || better(cand, seen)) && !__atomic_compare_exchange_n(&best[frag], &seen, cand, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
-	};
-	parallel_rows(threads, e.n, [&](u32 k) {
-		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) consider(k, e.list1[p]);
-		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) consider(k, e.list2[p]);
-		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) consider(k, e.listd[p]);
-	});
-	laps.lap("best candidate per fragment");
-	auto more_support = [&](u32 fa, u32 fb) { // fusion_has_more_support(most_supported[fa], most_supported[fb]) with NULL handling
-		const u32 x = best[fa], y = best[fb];
-		if (x == NONE) return false;
-		if (y == NONE) return true;
-		return better(x, y);
-	};
-	// clusters = maximal runs of fragments sharing the name up to the last comma
-	auto stem = [&](u32 i, u64& len) { const char* s = frags.names.data() + frags.name_off[i]; u64 l = frags.name_off[i + 1] - frags.name_off[i]; u64 k = l; while (k > 0 && s[k - 1] != ',') --k; len = k > 0 ? k - 1 : l; return s; };
-	// clusters are independent: a thread takes the clusters that START in its slice of the name order (a cluster may run on into the next slice)
-	{
-		const int T = std::max(1, std::min(threads, (int) (N / 4096 + 1)));
-		std::vector<std::thread> pool; std::vector<std::string> errors(T);
-		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
-			try {
-				u32 i = (u32) ((u64) N * t / T); const u32 stop = (u32) ((u64) N * (t + 1) / T);
-				// skip the tail of a cluster that started in the previous slice
-				if (i > 0 && i < N && (frags.fflags[i] & FF_MULTIMAPPER)) { u64 lp; const char* sp = stem(i - 1, lp); for (; i < N; ++i) { u64 li; const char* si = stem(i, li); if (li != lp || memcmp(sp, si, lp) != 0) break; } }
-				while (i < stop) {
-					if (!(frags.fflags[i] & FF_MULTIMAPPER)) { ++i; continue; } // the flag marks exactly the fragments that share their stem with a neighbour (ingest)
-					u64 li; const char* si = stem(i, li);
-					u32 j = i + 1;
-					for (; j < N; ++j) { u64 lj; const char* sj = stem(j, lj); if (lj != li || memcmp(si, sj, li) != 0) break; }
-					if (j - i > 1) {
-						u32 best_frag = NONE; int best_score = INT_MIN;
-						for (u32 x = i; x < j; ++x) {
-							const int s = alignment_score(f, an, x);
-							if (best_score < s) { best_frag = x; best_score = s; }
-							else if (best_score == s && more_support(x, best_frag)) best_frag = x;
-						}
-						for (u32 x = i; x < j; ++x) if (x != best_frag && labels[x] == F_none) labels[x] = F_multimappers;
-					}
-					i = j;
-				}
-			} catch (const std::exception& x) { errors[t] = x.what(); }
-		});
-		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-		for (int t = 0; t < T; ++t) if (!errors[t].empty()) throw std::runtime_error(errors[t]);
-	}
-	laps.lap("clusters");
-	parallel_rows(threads, e.n, [&](u32 k) {
-		if (e.filter[k] != F_none || e.supporting_reads(k) == 0) return;
-		for (u32 p = e.list1_off[k]; p < e.list1_off[k + 1]; ++p) if (labels[e.list1[p]] == F_multimappers && e.split_reads1[k] > 0) --e.split_reads1[k];
-		for (u32 p = e.list2_off[k]; p < e.list2_off[k + 1]; ++p) if (labels[e.list2[p]] == F_multimappers && e.split_reads2[k] > 0) --e.split_reads2[k];
-		for (u32 p = e.listd_off[k]; p < e.listd_off[k + 1]; ++p) if (labels[e.listd[p]] == F_multimappers && e.discordant_mates[k] > 0) --e.discordant_mates[k];
-		if (e.supporting_reads(k) == 0) e.filter[k] = F_multimappers;
-	});
-	laps.lap("read counts");
+// ------------------------------------------------------------------------------------------- multimappers (filter_multimappers.cpp), on the device
+void pipeline::filter_multimappers() { // csrc/events_hd.h: multimapper_best_fn, multimapper_cluster_fn, multimapper_recount_fn
+	check(ctx, arb_set_fragment_filters(ctx, labels.data()), "arb_set_fragment_filters");
+	push_candidate_state();
+	check(ctx, arb_filter_multimappers(ctx), "arb_filter_multimappers");
+	pull_candidate_state();
+	check(ctx, arb_get_fragment_filters(ctx, labels.data(), NULL), "arb_get_fragment_filters");
 	log_remaining("Filtering multi-mapping fusions by alignment score and read support");
 }
 
@@ -562,22 +447,8 @@ void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::ve
 	const u32 N = frags.n;
 	const size_t G = ref.genes.size();
 	reads_by_gene.assign(G, 0); present.assign(G, 0);
-	{ // per-thread histograms over the fragments' gene sets, then summed
-		const int T = std::max(1, std::min(threads, (int) (N / 8192 + 1)));
-		std::vector<std::vector<u32> > part(T, std::vector<u32>(G, 0));
-		std::vector<std::thread> pool;
-		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
-			std::vector<u32>& h = part[t];
-			for (size_t i = (size_t) N * t / T; i < (size_t) N * (t + 1) / T; ++i) {
-				const size_t a = i, b = (size_t) (frags.n_aln[i] == 2 ? 1 : 2) * N + i;
-				for (u32 g = 0; g < frags.genes_cnt[a]; ++g) ++h[frags.genes[frags.genes_off[a] + g]];
-				for (u32 g = 0; g < frags.genes_cnt[b]; ++g) ++h[frags.genes[frags.genes_off[b] + g]];
-			}
-		});
-		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-		for (int t = 0; t < T; ++t) for (size_t g = 0; g < G; ++g) reads_by_gene[g] += part[t][g];
-		for (size_t g = 0; g < G; ++g) present[g] = reads_by_gene[g] > 0;
-	}
+	check(ctx, arb_reads_by_gene(ctx, reads_by_gene.data()), "arb_reads_by_gene"); // counted on the device over the resident gene sets (csrc/events_hd.h, reads_by_gene_fn)
+	for (size_t g = 0; g < G; ++g) present[g] = reads_by_gene[g] > 0;
 	std::vector<u32> genes;
 	for (u32 g = 0; g < present.size(); ++g) if (present[g]) genes.push_back(g);
 	threshold = 0;
@@ -590,9 +461,6 @@ void pipeline::find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::ve
 }
 
 void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
-	const annot_view an = ref.host_view();
-	const u32 N = frags.n;
-	const frag_view f = frags.view();
 	stage_laps laps("in_vitro");
 	std::vector<u64> exonic_breakpoints; // one (gene, partner) key per exonic, unspliced breakpoint pair, sorted: a count is the width of an equal range
 	for (u32 k = 0; k < ev.n; ++k)
@@ -604,75 +472,23 @@ void pipeline::filter_in_vitro() { // filter_in_vitro.cpp:85-228
 	std::vector<u32> reads_by_gene; std::vector<u8> present; unsigned int threshold;
 	find_top_expressed_genes(reads_by_gene, present, threshold, opt.high_expression_quantile); // -Q
 	laps.lap("top expressed genes");
-	auto higher_expressed = [&](u16 contig, i32 bp, u32 gene) {
-		unsigned int highest = reads_by_gene[gene];
-		index_query<1024>(gene_index(an), contig, bp, bp, [&](const u32* genes, u32 n) { for (u32 x = 0; x < n; ++x) if (reads_by_gene[genes[x]] > highest) { highest = reads_by_gene[genes[x]]; gene = genes[x]; } },
-		                  "too many overlapping annotation records at one locus");
-		return gene;
-	};
-	auto pair_count = [&](u32 a, u32 b) { const u64 key = (u64) a << 32 | b; const std::pair<std::vector<u64>::const_iterator, std::vector<u64>::const_iterator> r = std::equal_range(exonic_breakpoints.begin(), exonic_breakpoints.end(), key); return (unsigned int) (r.second - r.first); };
-	parallel_rows(threads, ev.n, [&](u32 k) {
-		const u8 fl = ev.filter[k];
-		if (fl != F_none && !((ev.spliced1(k) || ev.spliced2(k)) && (fl == F_relative_support || fl == F_min_support || fl == F_homopolymer))) return;
-		float rt = 0;
-		if (!ev.exonic1(k)) rt += 0.5; else if (!ev.spliced1(k)) rt += 1;
-		if (!ev.exonic2(k)) rt += 0.5; else if (!ev.spliced2(k)) rt += 1;
-		// The verdict is one boolean expression (filter_in_vitro.cpp:196-222); its terms are evaluated cheapest first and the expensive ones (supporting
-		// mates that are clipped at the breakpoints, the most expressed gene at either breakpoint, exonic breakpoint pairs) only while they can still matter.
-		const unsigned int own_split = ev.split_reads1[k] + ev.split_reads2[k];
-		if (own_split > 2 && own_split * 2 > ev.discordant_mates[k]) return; // total_split >= own_split: "total_split * 2 <= discordant_mates || total_split <= 2" cannot hold
-		const u32 g1 = higher_expressed(ev.contig1[k], ev.bp1[k], ev.gene1[k]), g2 = higher_expressed(ev.contig2[k], ev.bp2[k], ev.gene2[k]);
-		const unsigned int x1 = reads_by_gene[g1], x2 = reads_by_gene[g2];
-		if (!(x1 + x2 > threshold)) return; // only breakpoints in highly expressed genes are suspected: most candidates leave here
-		unsigned int clipped1 = 0, clipped2 = 0;
-		for (u32 p = ev.listd_off[k]; p < ev.listd_off[k + 1]; ++p) {
-			const u32 i = ev.listd[p];
-			if (labels[i] != F_none) continue;
-			for (u32 s = 0; s < frags.n_aln[i]; ++s) {
-				const u32 a = (u32) ((size_t) s * N + i);
-				if (f.fwd(a) && f.postclip(a) >= 3) { if (f.contig[a] == ev.contig1[k] && f.end[a] == ev.bp1[k]) ++clipped1; else if (f.contig[a] == ev.contig2[k] && f.end[a] == ev.bp2[k]) ++clipped2; }
-				else if (!f.fwd(a) && f.preclip(a) >= 3) { if (f.contig[a] == ev.contig1[k] && f.start[a] == ev.bp1[k]) ++clipped1; else if (f.contig[a] == ev.contig2[k] && f.start[a] == ev.bp2[k]) ++clipped2; }
-			}
-		}
-		const unsigned int total_split = std::min(clipped1, clipped2) + own_split;
-		if (!(total_split * 2 <= ev.discordant_mates[k] || total_split <= 2)) return;
-		if (!(total_split <= 2 + 0.0001 * (x1 + x2))) return;
-		const unsigned int sup = ev.supporting_reads(k);
-		if (sup >= 10 && (ev.spliced1(k) || ev.spliced2(k)) && ((ev.spliced1(k) || !ev.exonic1(k)) && (ev.spliced2(k) || !ev.exonic2(k)))) {
-			const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
-			const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
-			if (((int) sup * 4) >= std::max(cov1, cov2) && cov1 > (int) sup && cov2 > (int) sup) return; // well covered on both sides: kept
-		}
-		if (rt > 1 || (rt > 0 && (x1 > threshold || x2 > threshold)) || x1 > 2 * threshold || x2 > 2 * threshold || (x1 > threshold && x2 > threshold) || sup <= 1 ||
-		    std::max(pair_count(g1, g2), pair_count(ev.gene1[k], ev.gene2[k])) > 8)
-			ev.filter[k] = F_in_vitro;
-	});
+	// the verdicts: one thread per candidate on the device (csrc/events_hd.h, in_vitro_fn) -- every candidate walks its discordant mates, which lie all over
+	// the fragment table
+	ensure_coverage_on_device();
+	check(ctx, arb_set_fragment_filters(ctx, labels.data()), "arb_set_fragment_filters");
+	push_candidate_state();
+	check(ctx, arb_filter_in_vitro(ctx, reads_by_gene.data(), (uint32_t) reads_by_gene.size(), threshold, (const uint64_t*) exonic_breakpoints.data(), exonic_breakpoints.size()), "arb_filter_in_vitro");
+	check(ctx, arb_get_candidate_filters(ctx, ev.filter.data()), "arb_get_candidate_filters");
 	laps.lap("candidates");
 	log_remaining("Filtering in vitro-generated fusions");
 }
 
-// recover_both_spliced.cpp:15-62
-unsigned int pipeline::spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold) {
-	const annot_view an = ref.host_view();
-	const int max_exon_size = 1000; const unsigned int max_coverage = 1000; // arriba.cpp:492
-	if (reads_by_gene[ev.gene1[k]] > threshold || reads_by_gene[ev.gene2[k]] > threshold)
-		return (both_spliced(ev, ref, k) && ev.discordant_mates[k] <= ev.split_reads1[k] + ev.split_reads2[k]) ? 1 : 0;
-	if (!both_spliced(ev, ref, k)) {
-		const unsigned int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
-		const unsigned int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
-		if (cov1 + cov2 > ev.supporting_reads(k) * max_coverage) return 0;
-		idset<4096> exons;
-		query_index(exon_index(an), ev.contig1[k], ev.bp1[k], ev.bp1[k], exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
-		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
-		query_index(exon_index(an), ev.contig2[k], ev.bp2[k], ev.bp2[k], exons); if (exons.overflow) throw std::runtime_error("too many overlapping annotation records at one locus");
-		for (u32 x = 0; x < exons.n; ++x) if (ref.exons[exons.v[x]].end + 1 - ref.exons[exons.v[x]].start > max_exon_size) return 0;
-	}
-	unsigned int multi = 0, unique = 0;
-	auto scan = [&](const column<u32>& list, u32 lo, u32 hi) { for (u32 p = lo; p < hi; ++p) { if (frags.fflags[list[p]] & FF_MULTIMAPPER) ++multi; else if (labels[list[p]] == F_none) ++unique; } };
-	scan(ev.list1, ev.list1_off[k], ev.list1_off[k + 1]); scan(ev.list2, ev.list2_off[k], ev.list2_off[k + 1]); scan(ev.listd, ev.listd_off[k], ev.listd_off[k + 1]);
-	if (multi >= 0.5 * (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) return 0;
-	if (unique == 0) return 1;
-	return unique;
+void pipeline::ensure_coverage_on_device() {
+	if (coverage_on_device) return;
+	std::vector<const u16*> cov(coverage.coverage.size(), (const u16*) NULL); std::vector<uint64_t> windows(coverage.coverage.size(), 0);
+	for (size_t c = 0; c < coverage.coverage.size(); ++c) { cov[c] = coverage.coverage[c].data(); windows[c] = coverage.coverage[c].size(); }
+	check(ctx, arb_set_coverage(ctx, cov.data(), windows.data(), (uint32_t) cov.size()), "arb_set_coverage");
+	coverage_on_device = true;
 }
 
 void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
@@ -683,14 +499,10 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	// spliced support of every candidate that may back another one up (recover_both_spliced.cpp:104-118); a pure function of the candidate: host threads
 	const u32 NOT_ELIGIBLE = 0xFFFFFFFFu;
 	std::vector<u32> support(ev.n, NOT_ELIGIBLE);
-	parallel_rows(threads, ev.n, [&](u32 k) {
-		const u8 fl = ev.filter[k];
-		if (fl == F_merge_adjacent) return;
-		if (fl == F_none || fl == F_in_vitro || fl == F_intronic || fl == F_relative_support || fl == F_min_support || (fl == F_inconsistently_clipped && both_spliced(ev, ref, k))) {
-			const unsigned int s = spliced_support(k, reads_by_gene, threshold);
-			if (s > 0) support[k] = s;
-		}
-	});
+	ensure_coverage_on_device();
+	check(ctx, arb_set_fragment_filters(ctx, labels.data()), "arb_set_fragment_filters");
+	push_candidate_state();
+	check(ctx, arb_spliced_support(ctx, reads_by_gene.data(), (uint32_t) reads_by_gene.size(), threshold, support.data()), "arb_spliced_support"); // csrc/events_hd.h, spliced_support_fn
 	// group them by (gene1, gene2, direction1, direction2): sorted keys instead of the reference's map of vectors (only sums over a group are taken)
 	auto key_of = [&](u32 k, bool flip) { return (u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) ((ev.dir1[k] != 0) != flip) << 1 | (u64) ((ev.dir2[k] != 0) != flip); };
 	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");

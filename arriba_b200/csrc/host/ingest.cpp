@@ -1087,7 +1087,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		parallel_for(T, n > 0 ? (size_t) n - 1 : 0, [&](int, size_t lo, size_t hi) {
 			for (size_t i = lo; i < hi; ++i) { const u64 la = stem_len((u32) i), lb = stem_len((u32) i + 1); same[i] = la == lb && memcmp(out.names.data() + out.name_off[i], out.names.data() + out.name_off[i + 1], la) == 0; }
 		});
-		parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) if (same[i] || (i > 0 && same[i - 1])) out.fflags[i] |= FF_MULTIMAPPER; });
+		parallel_for(T, (size_t) n, [&](int, size_t lo, size_t hi) { for (size_t i = lo; i < hi; ++i) { if (same[i] || (i > 0 && same[i - 1])) out.fflags[i] |= FF_MULTIMAPPER; if (i > 0 && same[i - 1]) out.fflags[i] |= FF_SAME_NAME_AS_PREVIOUS; } });
 	}
 	stats.t_finalize = now_s() - tf;
 	lap("multimapper flags");

@@ -53,7 +53,7 @@ struct pipeline {
 	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
 	pipeline(): ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false), splice_sites_ready(false), events_done(-1),
-	            upload_begun(false), t_mismappers_begin(0), frags_on_device(false), reference_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
+	            upload_begun(false), t_mismappers_begin(0), frags_on_device(false), reference_on_device(false), coverage_on_device(false) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -72,7 +72,6 @@ struct pipeline {
 	void write_output();
 	void make_kmer_index(); void filter_homologs(); void filter_mismappers(); bool splice_sites_ready;
 	void find_top_expressed_genes(std::vector<u32>& reads_by_gene, std::vector<u8>& present, unsigned int& threshold, float quantile);
-	unsigned int spliced_support(u32 k, const std::vector<u32>& reads_by_gene, unsigned int threshold);
 	float intronic_fraction(u32 gene);
 	void events_until(int last_stage); // runs the event-level chain up to and including `last_stage` (EV_* below)
 	int events_done;
@@ -80,8 +79,8 @@ struct pipeline {
 	// one sample on several GPUs (shard.cpp; device side csrc/exchange.cu): contig pairs assigned to the parts, the re-alignment stage in two halves
 	std::vector<u32> partition_keys; std::vector<u8> partition_owner; void work_partition(int parts);
 	bool mismappers_begin(); void mismappers_end(); double t_mismappers_begin;
-	void attach_device(); // a part that only works on replicated device state: a context with the run's parameters
-	bool frags_on_device, reference_on_device;
+	void ensure_coverage_on_device(); void attach_device(); // a part that only works on replicated device state: a context with the run's parameters
+	bool frags_on_device, reference_on_device, coverage_on_device;
 	void say_read_filter_counts();
 };
 

@@ -10,9 +10,8 @@ namespace arb {
 // pass 1 of the re-alignment: MISMAP_LANES lanes per (candidate, read) item, worklist of continuations in shared memory (mismap_hd.h, evaluate_group)
 static const u32 MISMAP_THREADS = 256, MISMAP_WORKLIST = 64;
 template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
-	const u32 GROUPS = MISMAP_THREADS / LANES, QUEUE = 4 * LANES;
+	const u32 GROUPS = MISMAP_THREADS / LANES;
 	__shared__ realign_work tasks[GROUPS][MISMAP_WORKLIST];
-	__shared__ realign_hit hits[GROUPS][QUEUE];
 	__shared__ u32 tops[GROUPS];
 	const u32 group = threadIdx.x / LANES;
 	lane_group g; g.lane = threadIdx.x % LANES; g.lanes = LANES; g.mask = (LANES >= 32 ? 0xFFFFFFFFu : ((1u << (LANES & 31u)) - 1u)) << ((threadIdx.x & 31u) / LANES * LANES);
@@ -21,8 +20,7 @@ template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_
 	const u32 i = it.item_frag[j];
 	if (((const volatile u8*) it.mismapper)[i]) return; // another candidate's evaluation of this fragment already decided (the label is an OR)
 	realign_worklist wl = {tasks[group], &tops[group], MISMAP_WORKLIST};
-	realign_hit_queue hq = {hits[group], QUEUE};
-	const u32 verdict = evaluate_group(g, it, j, wl, hq, budget);
+	const u32 verdict = evaluate_group(g, it, j, wl, budget);
 	if (g.lane == 0) {
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomicAdd(n_heavy, 1u)] = j;
@@ -76,9 +74,36 @@ u64 engine::build_kmer_index(const u32* contig, const i32* start, const i32* end
 #else
 	memcpy(kmer_pos.ptr(), pos.ptr(), (size_t) K * 4);
 #endif
+	{ // block table (mismap_hd.h, kmer_index_view): blocks of 128 kb, larger where the table would exceed 2 GiB (ARB_KMER_BLOCKS=0 switches it off)
+		kmer_block_shift = 0; kmer_blocks = 0;
+		const char* sw = getenv("ARB_KMER_BLOCKS");
+		if (!sw || atoi(sw) != 0) {
+			u32 shift = 17;
+			std::vector<u32> base(n_index_contigs + 1, 0);
+			for (;; ++shift) {
+				u64 total = 0;
+				for (u32 c = 0; c < n_index_contigs; ++c) { base[c] = (u32) total; total += ((u64) (c < annot.h_contig_len.size() ? annot.h_contig_len[c] : 0) >> shift) + 1; }
+				base[n_index_contigs] = (u32) total;
+				if (total * 65536 * 4 <= ((u64) 2 << 30) || shift >= 24) break;
+			}
+			kmer_block_shift = shift; kmer_blocks = base[n_index_contigs];
+			kmer_block_base.upload(ex, base.data(), (size_t) n_index_contigs + 1);
+			const u64 cells = (u64) kmer_blocks << 16;
+			kmer_block_first.ensure(cells); kmer_block_first.fill_bytes(ex, 0xFF, cells);
+			block_first_min_fn mn = {key.ptr(), kmer_pos.ptr(), kmer_block_base.ptr(), kmer_block_shift, kmer_block_first.ptr()};
+			for_each(ex, K, mn);
+			block_first_sweep_fn sf = {kmer_bucket_off.ptr(), kmer_block_base.ptr(), kmer_block_first.ptr()};
+			for_each(ex, n_index_contigs << 16, sf);
+		}
+	}
 	timings.kmer_index_ms = t_all.stop(); timings.kmer_positions = K;
 	ex.sync();
 	return K;
+}
+
+kmer_index_view engine::index_view() {
+	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs, kmer_block_shift ? kmer_block_first.ptr() : NULL, kmer_block_base.ptr(), kmer_block_shift};
+	return ix;
 }
 
 void engine::kmer_index_digest(u64* kmers, u64* positions, u64* checksum, u32 n_contigs) {
@@ -99,7 +124,7 @@ void engine::homolog_pairs(const u32* ga, const u32* gb, u32 n, u8* out) {
 	if (n == 0) return;
 	dbuf<u32> a, b; dbuf<u8> o(n);
 	a.upload(ex, ga, n); b.upload(ex, gb, n);
-	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
+	kmer_index_view ix = index_view();
 	stage_timer t_all(ex);
 	if (homolog_lanes > 1 && (u64) n * homolog_lanes < 0x80000000ull) { // a few pairs of long, similar genes dominate: lanes per pair (mismap_hd.h, homolog_count_fn)
 		dbuf<u32> count(n); count.zero(ex, n);
@@ -157,7 +182,7 @@ void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void*
 		item_cand.swap(c2); item_frag.swap(f2); item_kind.swap(k2);
 		I = mine;
 	}
-	kmer_index_view ix = {kmer_pos.ptr(), kmer_bucket_off.ptr(), kmer_index_contigs};
+	kmer_index_view ix = index_view();
 	gene_splice_view sp = {splice_off.ptr(), splice_sites.ptr()};
 	mismap_params mp = {max_mate_gap, params.max_mismapper_fraction};
 	mismap_items items = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr()};
@@ -168,7 +193,7 @@ void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void*
 	auto launch = [&](u32 n, const auto& fn) { if (mismap_min_blocks >= 4) for_each_occ<4>(ex, n, fn); else if (mismap_min_blocks == 3) for_each_occ<3>(ex, n, fn); else for_each(ex, n, fn); };
 	if (mismap_group_pass) {
 #ifdef ARB_DEVICE_BUILD
-		if (I) { // lanes per work item (ARB_MISMAP_GROUP_LANES): 16 measured best on the default workload (profiles/r02h)
+		if (I) { // lanes per work item (ARB_MISMAP_GROUP_LANES)
 			if (mismap_group_lanes >= 32) launch_mismap_items<32>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());
 			else if (mismap_group_lanes >= 16) launch_mismap_items<16>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());
 			else launch_mismap_items<8>(ex, items, I, mismap_budget, heavy.ptr(), n_heavy.ptr());

@@ -24,11 +24,37 @@ namespace arb {
 ARB_HD u32 base2(char c) { return c == 'T' ? 0u : c == 'G' ? 1u : c == 'C' ? 2u : 3u; } // every other character (A, N, IUPAC) is 3
 ARB_HD char complement_char(char c) { switch (c) { case 'A': return 'T'; case 'T': return 'A'; case 'C': return 'G'; case 'G': return 'C'; default: return c; } }
 
+// A bucket holds the positions of one 8-mer on a whole contig (hundreds of entries once half of a chromosome is indexed), while a search only wants the
+// hits at or after a lower bound inside one gene window. block_first answers that without a binary search over the bucket: the contig is cut into blocks
+// of 2^block_shift bases, and block_first[(first block of the contig + b) << 16 | 8-mer] is the index of the bucket's first position >= b << block_shift
+// (the bucket's end if there is none): one load, then a step or two forward.
 struct kmer_index_view {
 	const i32* pos;          // positions sorted by (contig, 8-mer, position)
 	const u32* bucket_off;   // n_index_contigs * 65536 + 1
 	u32 n_index_contigs;     // contigs >= this have no index (kmer_indices.size() in the reference)
+	const u32* block_first; const u32* contig_block_base; u32 block_shift; // 0 when the table was not built
 	ARB_HD void bucket(u32 contig, u32 kmer, u32& lo, u32& hi) const { const u64 b = (u64) contig * 65536 + kmer; lo = bucket_off[b]; hi = bucket_off[b + 1]; }
+	// first entry of the bucket [lo, hi) of (contig, kmer) whose position is >= from
+	ARB_HD u32 first_at_or_after(u32 contig, u32 kmer, u32 lo, u32 hi, i32 from) const {
+		if (from <= 0) return lo;
+		if (!block_first) { u32 a = lo, b = hi; while (a < b) { const u32 mid = a + ((b - a) >> 1); if (pos[mid] < from) a = mid + 1; else b = mid; } return a; }
+		u32 h = block_first[((u64) contig_block_base[contig] + ((u32) from >> block_shift)) << 16 | kmer];
+		while (h < hi && pos[h] < from) ++h;
+		return h;
+	}
+};
+// index construction: the block table
+struct block_first_min_fn { // entry idx of the sorted index: the smallest index per (block, 8-mer)
+	const u32* key /* contig << 16 | 8-mer */; const i32* pos; const u32* contig_block_base; u32 block_shift; u32* block_first;
+	ARB_HD void operator()(u32 idx) const { const u32 contig = key[idx] >> 16, km = key[idx] & 0xffffu; atomic_min_u32(&block_first[((u64) contig_block_base[contig] + ((u32) pos[idx] >> block_shift)) << 16 | km], idx); }
+};
+struct block_first_sweep_fn { // thread per (contig, 8-mer): blocks without an entry point at the next later entry of the bucket
+	const u32* bucket_off; const u32* contig_block_base; u32* block_first;
+	ARB_HD void operator()(u32 t) const {
+		const u32 contig = t >> 16, km = t & 0xffffu;
+		u32 next = bucket_off[(u64) contig * 65536 + km + 1];
+		for (u32 b = contig_block_base[contig + 1]; b-- > contig_block_base[contig]; ) { u32& v = block_first[(u64) b << 16 | km]; if (v == 0xFFFFFFFFu) v = next; else next = v; }
+	}
 };
 
 // ---- index construction
@@ -68,11 +94,20 @@ ARB_HD u32 nt16_base2(u32 code) { return 0xFFFCFDEFu >> (2 * code) & 3u; }
 struct realign_env {
 	const u8* seq; u32 off, len; bool rc;        // the read slice
 	const i32* pos; const u32* bucket;           // k-mer hits and the 65,536 bucket offsets of the window's contig
+	const u32* block_first; u32 block_shift;     // the contig's part of the block table (kmer_index_view), 0 if there is none
 	const i32* splice; u32 n_splice;             // downstream splice sites of the gene
 	i32 wstart, wend;                            // gene +- padding
 	int min_score;
 	const u32* g4; const char* ref;              // reference of the contig: packed nt16 codes, or characters when g4 == 0
 };
+// first hit of the bucket [lo, hi) of `km` at or after gene_pos
+ARB_HD u32 env_first_hit(const realign_env& env, u32 km, u32 lo, u32 hi, i32 gene_pos) {
+	if (gene_pos <= 0) return lo;
+	if (!env.block_first) { while (lo < hi) { const u32 mid = lo + ((hi - lo) >> 1); if (env.pos[mid] < gene_pos) lo = mid + 1; else hi = mid; } return lo; }
+	u32 h = env.block_first[(u64) ((u32) gene_pos >> env.block_shift) << 16 | km];
+	while (h < hi && env.pos[h] < gene_pos) ++h;
+	return h;
+}
 ARB_HD u32 env_code(const u8* seq, u32 off, u32 len, bool rc, u32 r) { // nt16 code of base r of the (possibly reverse-complemented) slice
 	const u32 code = nt16_at(seq, rc ? off + len - 1 - r : off + r);
 	return rc ? nt16_comp(code) : code;
@@ -176,7 +211,7 @@ ARB_HD_RECURSIVE bool realign(int score, int read_pos, int gene_pos, int max_del
 	for (;;) {
 		const u32 lo = bucket[km], hi = bucket[km + 1];
 		if (lo != hi) {
-			u32 h = lower_bound_i32(pos, lo, hi, gene_pos), step = 1;
+			u32 h = env_first_hit(env, km, lo, hi, gene_pos), step = 1;
 			if (top && ctl.lanes > 1) { // deal this position's hits to the lanes, continuing the round-robin of the previous positions
 				if (ctl.stop && *ctl.stop) REALIGN_RETURN(false);
 				const u32 n_hits = lower_bound_i32(pos, h, hi, wend) - h;
@@ -256,6 +291,7 @@ ARB_HD bool segment_env(const realign_segment& s, u32 k, int max_mate_gap, const
 	if (contig >= ix.n_index_contigs) return false;
 	env.seq = s.read.nt16; env.off = s.read.off; env.len = s.read.len; env.rc = s.read.rc;
 	env.pos = ix.pos; env.bucket = ix.bucket_off + (u64) contig * 65536;
+	env.block_first = ix.block_first ? ix.block_first + ((u64) ix.contig_block_base[contig] << 16) : 0; env.block_shift = ix.block_shift;
 	env.splice = sp.sites + sp.off[g]; env.n_splice = sp.off[g + 1] - sp.off[g];
 	env.min_score = s.min_score();
 	env.g4 = an.assembly4 ? an.assembly4 + an.contig_seq_off[contig] / 8 : 0; env.ref = an.assembly + an.contig_seq_off[contig];
@@ -376,14 +412,9 @@ ARB_HD u32 env_kmer(const realign_env& env, u32 r) {
 	// and complements A/C/G/T/N; every other code keeps more than one bit and maps to 3 like the character it stands for
 	return nt16_dense2(brev32(nt16_window(env.seq, 0x7fffffffu, (i32) (env.off + env.len - 8 - r))));
 }
-// One search (top level or continuation) by the lanes of a group, in two alternating phases:
-//   A  every lane takes one read position: 8-mer, bucket, the range of hits inside [lower bound, window end) -- regular work, all lanes busy, the loads of
-//      a whole group in flight together;
-//   B  the hits found (few per position, hundreds in a repeat) are written to the group's queue in shared memory and dealt to the lanes one by one, so a
-//      lane never idles because ITS position happened to have no hit: each lane extends one (position, hit) pair to the left and to the right.
-// Returns REALIGN_FOUND as soon as any lane reaches min_score, REALIGN_EXHAUSTED when the group has spent `budget` steps (the item then goes to pass 2).
-struct realign_hit { i32 hit; u32 read_pos; };
-struct realign_hit_queue { realign_hit* e; u32 capacity; };
+// One search (top level or continuation) by the lanes of a group: the lanes take the read positions in turn (score and skipped bases at a position follow
+// from the position alone); a lane looks up its position's 8-mer, finds the first hit at or after the lower bound through the block table and extends
+// every hit inside the window. Returns REALIGN_FOUND on the lane that reached min_score (the caller combines the lanes).
 enum { REALIGN_UNDECIDED_NO = 0, REALIGN_FOUND = 1, REALIGN_EXHAUSTED = 2 };
 ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, const realign_worklist& wl, int read_pos, int hit, u32& steps) {
 	const u8* const seq = env.seq; const u32 off = env.off; const bool rc = env.rc; const int len = (int) env.len;
@@ -425,46 +456,22 @@ ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, con
 	}
 	return false;
 }
-ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, const realign_hit_queue& hq, u32& steps, u32 step_limit) {
+ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, u32& steps) {
 	const int len = (int) env.len;
 	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
 	const i32 wend = env.wend; const int min_score = env.min_score;
 	const int read_pos0 = task.read_pos, score0 = task.score, gene_pos = task.gene_pos;
-	u32 fill = 0; // entries in the queue (the same value on every lane)
-	bool positions_left = true;
-	for (int base = read_pos0; positions_left || fill; base += (int) g.lanes) {
-		// ---- phase A: one read position per lane
-		u32 h0 = 0, remaining = 0; int read_pos = base + (int) g.lane;
-		if (positions_left) {
-			const bool valid = realign_can_start(score0 - (read_pos - read_pos0), read_pos, len, min_score); // the valid positions are a prefix
-			if (valid) {
-				const u32 km = env_kmer(env, (u32) read_pos);
-				const u32 lo = bucket[km], hi = bucket[km + 1];
-				if (lo != hi) { h0 = lower_bound_i32(pos, lo, hi, gene_pos); remaining = lower_bound_i32(pos, h0, hi, wend) - h0; }
-			}
-			positions_left = g.any(valid) && realign_can_start(score0 - (base + (int) g.lanes - read_pos0), base + (int) g.lanes, len, min_score);
-		}
-		// ---- phase B: queue the hits, drain the queue when it is full enough (or nothing is left to add)
-		for (;;) {
-			const u32 before = g.exclusive_sum(remaining), total = g.sum(remaining);
-			const u32 space = hq.capacity - fill;
-			const u32 take = before >= space ? 0u : hd_min(remaining, space - before);
-			for (u32 k = 0; k < take; ++k) { realign_hit e = {pos[h0 + k], (u32) read_pos}; hq.e[fill + before + k] = e; }
-			h0 += take; remaining -= take;
-			fill += hd_min(total, space);
-			const bool more_here = total > space;
-			if (!more_here && positions_left && fill + g.lanes <= hq.capacity / 2) break; // room for another round of positions
-			g.sync();
-			bool found = false;
-			for (u32 q = g.lane; q < fill && !found; q += g.lanes) found = realign_extend(env, task, wl, (int) hq.e[q].read_pos, hq.e[q].hit, steps);
-			if (g.any(found)) return REALIGN_FOUND;
-			if (step_limit && g.sum(steps) > step_limit) return REALIGN_EXHAUSTED;
-			g.sync();
-			fill = 0;
-			if (!more_here) break;
+	for (int read_pos = read_pos0 + (int) g.lane; ; read_pos += (int) g.lanes) {
+		if (!realign_can_start(score0 - (read_pos - read_pos0), read_pos, len, min_score)) return REALIGN_UNDECIDED_NO; // the valid positions are a prefix
+		const u32 km = env_kmer(env, (u32) read_pos);
+		const u32 lo = bucket[km], hi = bucket[km + 1];
+		if (lo == hi) continue;
+		for (u32 h = env_first_hit(env, km, lo, hi, gene_pos); h < hi; ++h) {
+			const int hit = pos[h];
+			if (hit >= wend) break;
+			if (realign_extend(env, task, wl, read_pos, hit, steps)) return REALIGN_FOUND;
 		}
 	}
-	return REALIGN_UNDECIDED_NO;
 }
 
 // filter_mismappers.cpp:247-270 by a group: the lanes share the clipped bases
@@ -492,7 +499,7 @@ ARB_HD bool extends_linearly_group(const lane_group& g, const frag_view& f, cons
 }
 
 // one item by a group: 0 = not mis-mapped, 1 = mis-mapped, 2 = gave up (worklist or budget), re-aligned cooperatively in pass 2
-ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, const realign_hit_queue& hq, int budget) {
+ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, int budget) {
 	if (g.lane == 0) *wl.top = 0;
 	g.sync();
 	if (it.item_kind[j] == 0 && extends_linearly_group(g, it.f, it.an, it.f.idx(it.item_frag[j], SPLIT_READ))) return REALIGN_FOUND;
@@ -530,8 +537,8 @@ ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, co
 		segment_env(s, task.gene_k, it.p.max_mate_gap, it.an, it.ix, it.sp, env); // it was usable when the task was made
 		if (task.rc_deletions & 0x80u) env.rc = !s.read.rc;
 		u32 steps = 0;
-		const u32 verdict = realign_group(g, env, task, wl, hq, steps, budget > 0 && (u32) budget > total_steps ? (u32) budget - total_steps : (budget > 0 ? 1u : 0u));
-		if (verdict != REALIGN_UNDECIDED_NO) return verdict;
+		const u32 verdict = realign_group(g, env, task, wl, steps);
+		if (g.any(verdict == REALIGN_FOUND)) return REALIGN_FOUND;
 		total_steps += g.sum(steps);
 		if (budget > 0 && total_steps > (u32) budget) return REALIGN_EXHAUSTED;
 		g.sync();
@@ -563,9 +570,8 @@ struct mismap_item_group_fn {
 		if (((const volatile u8*) it.mismapper)[i]) return;
 		realign_work tasks[64]; u32 top = 0;
 		realign_worklist wl = {tasks, &top, 64};
-		realign_hit hits[32]; realign_hit_queue hq = {hits, 32};
 		lane_group g; g.lane = 0; g.lanes = 1; g.mask = 1;
-		const u32 verdict = evaluate_group(g, it, j, wl, hq, budget);
+		const u32 verdict = evaluate_group(g, it, j, wl, budget);
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomic_add_u32(n_heavy, 1)] = j;
 	}
@@ -690,7 +696,7 @@ ARB_HD bool homolog_position_matches(const homolog_pair& p, const kmer_index_vie
 	u32 k = 0;
 	for (u32 b = 0; b < 8; ++b) k = k << 2 | base2(p.small_at(pos + b));
 	u32 lo, hi; ix.bucket(p.bc, k, lo, hi);
-	for (u32 h = lower_bound_i32(ix.pos, lo, hi, p.bs); h < hi && ix.pos[h] <= p.be; ++h) {
+	for (u32 h = ix.first_at_or_after(p.bc, k, lo, hi, p.bs); h < hi && ix.pos[h] <= p.be; ++h) {
 		const i32 hit = ix.pos[h];
 		if (!(p.sc != p.bc || hit < p.ss || hit > p.se)) continue;
 		bool same = true;

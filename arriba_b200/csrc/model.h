@@ -12,7 +12,7 @@ namespace arb {
 // per-alignment flag bits (aflags)
 enum { AF_SUPPLEMENTARY = 1, AF_FIRST_IN_PAIR = 2, AF_EXONIC = 4, AF_FORWARD = 8, AF_PRED_FORWARD = 16, AF_PRED_AMBIGUOUS = 32 };
 // per-fragment flag bits (fflags)
-enum { FF_SINGLE_END = 1, FF_MULTIMAPPER = 2, FF_DUPLICATE = 4 };
+enum { FF_SINGLE_END = 1, FF_MULTIMAPPER = 2, FF_DUPLICATE = 4, FF_SAME_NAME_AS_PREVIOUS = 8 /* same read name (up to the last comma) as the fragment before it */ };
 // slot meaning after ingest normalisation (common.hpp:208-211)
 enum { MATE1 = 0, MATE2 = 1, SPLIT_READ = 1, SUPPLEMENTARY = 2 };
 

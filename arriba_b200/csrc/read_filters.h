@@ -304,15 +304,6 @@ struct lane_group {
 #endif
 		return v;
 	}
-	ARB_HD u32 exclusive_sum(u32 v) const { // sum of v over the lanes of the group before this one
-#ifdef __CUDA_ARCH__
-		u32 incl = v;
-		for (u32 d = 1; d < lanes; d <<= 1) { const u32 t = __shfl_up_sync(mask, incl, d, (int) lanes); if (lane >= d) incl += t; }
-		return incl - v;
-#else
-		(void) v; return 0;
-#endif
-	}
 	ARB_HD bool any(bool p) const {
 #ifdef __CUDA_ARCH__
 		return (__ballot_sync(mask, p) & mask) != 0;

@@ -89,7 +89,7 @@ int arb_set_params(arb_ctx* ctx, const arb_params* p);
 typedef struct arb_soa_chunk {
 	uint32_t n_fragments;
 	const uint8_t* n_aln;          /* 2 or 3 */
-	const uint8_t* fflags;         /* bit0 single_end, bit1 multimapper, bit2 duplicate (BAM 0x400) */
+	const uint8_t* fflags;         /* bit0 single_end, bit1 multimapper, bit2 duplicate (BAM 0x400), bit3 same read name (up to the last comma) as the fragment before */
 	const uint8_t* filter;         /* initial labels (normally all 0) */
 	const uint16_t* contig; const int32_t* start; const int32_t* end;
 	const uint8_t* aflags;         /* bit0 supplementary, 1 first_in_pair, 2 exonic, 3 forward strand, 4 predicted strand forward, 5 predicted strand ambiguous */
@@ -163,6 +163,7 @@ int arb_get_slot_swaps(arb_ctx* ctx, uint8_t* swapped_out /* n fragments: 1 if M
  * The mutable candidate columns (filter, read counts, e-value) travel between the host-side event logic and the device
  * with arb_set/get_candidate_state; candidates are addressed by their id (first-insertion order). */
 int arb_set_candidate_state(arb_ctx* ctx, const uint8_t* filter, const uint32_t* split_reads1, const uint32_t* split_reads2, const uint32_t* discordant_mates, const float* evalue);
+int arb_get_candidate_filters(arb_ctx* ctx, uint8_t* filter /* n candidates */); /* the label column alone */
 int arb_get_candidate_state(arb_ctx* ctx, uint8_t* filter, uint32_t* split_reads1, uint32_t* split_reads2, uint32_t* discordant_mates, float* evalue);
 int arb_set_candidate_lists(arb_ctx* ctx, const uint32_t* list1_off, const uint32_t* list1, const uint32_t* list2_off, const uint32_t* list2);
 /* Replaces merge_adjacent_fusions (source/merge_adjacent_fusions.cpp:19). n_itd_merges: internal tandem duplications whose read
@@ -182,6 +183,22 @@ typedef struct arb_evalue_inputs {
 } arb_evalue_inputs;
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
+
+/* Replaces filter_multimappers (source/filter_multimappers.cpp:115): of the fragments that share a read name (fflags bit1 / bit3) only the one with the best
+ * alignment score keeps its label, ties go to the fragment whose best candidate has more support; read counts of the candidates follow. Works on the
+ * resident candidate state and fragment labels; results through arb_get_candidate_state / arb_get_fragment_filters. */
+int arb_filter_multimappers(arb_ctx* ctx);
+/* Replaces find_top_expressed_genes' counting (source/filter_in_vitro.cpp:48-83) and the per-candidate verdicts of filter_in_vitro_generated_fusions
+ * (:85-228). arb_set_coverage: the sample's coverage windows (source/read_stats.cpp:268-306: 20 bp windows per contig, n_windows[c] = 0 for contigs
+ * without one). arb_reads_by_gene: supporting fragments per gene (the caller derives the expression quantile, -Q). arb_filter_in_vitro works on the
+ * resident candidate state (arb_set_candidate_state) and fragment labels (arb_set_fragment_filters) and marks candidates F_in_vitro; exonic_pairs: sorted
+ * (gene << 32 | partner) keys, one per exonic, unspliced breakpoint pair and direction (:93-104). */
+int arb_set_coverage(arb_ctx* ctx, const uint16_t* const* coverage_per_contig, const uint64_t* n_windows, uint32_t n_contigs);
+int arb_reads_by_gene(arb_ctx* ctx, uint32_t* reads_out /* n_genes */);
+int arb_filter_in_vitro(arb_ctx* ctx, const uint32_t* reads_by_gene, uint32_t n_genes, uint32_t threshold, const uint64_t* exonic_pairs, uint64_t n_pairs);
+/* spliced support of every candidate that may back another one up (source/recover_both_spliced.cpp:15-62, :104-118): support_out[k] = the support,
+ * 0xFFFFFFFF where the candidate is not eligible or has none; works on the resident candidate state and fragment labels like arb_filter_in_vitro */
+int arb_spliced_support(arb_ctx* ctx, const uint32_t* reads_by_gene, uint32_t n_genes, uint32_t threshold, uint32_t* support_out /* n candidates */);
 
 /* ---- k-mer index of the fused genes, gene homology, re-alignment of supporting reads -----------------------------------
  * arb_build_kmer_index replaces make_kmer_index (source/filter_mismappers.cpp:47): `intervals` are the disjoint, sorted unions of the
@@ -243,6 +260,8 @@ typedef struct arb_timings {
 	uint64_t cascade_queued;    /* fragments the sequence rules (mismatches, low entropy) looked at */
 	uint64_t cascade_algorithmic_bytes[2]; /* SURVEY.md section 8(d) column budget of the two launches */
 	float annotate_ms;          /* arb_annotate_pass1 + arb_annotate_pass2 (kernels, sorts and scans on the context's stream) */
+	float in_vitro_ms;          /* arb_filter_in_vitro */
+	float multimappers_ms;      /* arb_filter_multimappers */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 /* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver

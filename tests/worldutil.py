@@ -115,6 +115,11 @@ def chunk_from_dump(d):
     dst = slot_of * n + frag_of
     ch = {"n_fragments": n, "n_aln": d["n_aln"].copy(), "filter": np.zeros(n, np.uint8),
           "fflags": (d["single_end"] | d["multimapper"] << 1 | d["duplicate"] << 2).astype(np.uint8)}
+    if "names" in d and "name_off" in d:   # bit 3: same read name (up to the last comma) as the fragment before it
+        blob = bytes(d["names"]); off = d["name_off"].astype(np.int64)
+        stems = [blob[off[i]:off[i + 1]].rpartition(b",")[0] or blob[off[i]:off[i + 1]] for i in range(n)]
+        same = np.array([i > 0 and stems[i] == stems[i - 1] for i in range(n)], bool)
+        ch["fflags"] |= (same.astype(np.uint8) << 3)
     def slot_array(src, dtype):
         out = np.zeros(3 * n, dtype); out[dst] = src; return out
     ch["contig"] = slot_array(d["contig"], np.uint16); ch["start"] = slot_array(d["start"], np.int32); ch["end"] = slot_array(d["end"], np.int32)
