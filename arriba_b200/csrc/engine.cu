@@ -19,7 +19,7 @@ engine::engine(): kmer_block_shift(0), kmer_blocks(0), coverage_contigs(0), work
 	memset(&timings, 0, sizeof(timings));
 	// tuning hooks of the re-alignment passes (mismap_hd.h): ARB_MISMAP_BUDGET (0 = thread-per-item only), ARB_MISMAP_LANES, ARB_MISMAP_SPAWN (0 = no task rounds), ARB_MISMAP_TASK_LANES
 	mismap_group_pass = true; if (const char* s = getenv("ARB_MISMAP_GROUP")) mismap_group_pass = atoi(s) != 0;
-	mismap_group_lanes = 8; if (const char* s = getenv("ARB_MISMAP_GROUP_LANES")) mismap_group_lanes = (u32) atoi(s);
+	mismap_group_lanes = 16; if (const char* s = getenv("ARB_MISMAP_GROUP_LANES")) mismap_group_lanes = (u32) atoi(s);
 	mismap_budget = 4096; mismap_lanes = 1024; mismap_spawn_budget = 0; mismap_task_lanes = 32;
 	if (const char* s = getenv("ARB_MISMAP_BUDGET")) mismap_budget = atoi(s);
 	if (const char* s = getenv("ARB_MISMAP_LANES")) mismap_lanes = (u32) std::max(1, atoi(s));
@@ -133,6 +133,43 @@ void engine::set_annotation(const arb_annotation& a) {
 // The fragment table goes to the device in two parts. Everything ingest produces is final when ingest ends and is copied first, asynchronously on the
 // copy stream (the caller's columns are page-locked when they were built in blocks of the host pool, arb_host_alloc) -- the caller annotates meanwhile;
 // the annotation columns (alignment flags with the exonic / strand bits, gene sets) follow, and push_chunk_end returns when the table is resident.
+struct chunk_stats_fn { // out: [0] longest sequence, [1] bases, [2] alignments, [3] breaks of the canonical pool layout
+	frag_view f; unsigned long long* out;
+	ARB_HD static void add(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+		atomicAdd(p, v);
+#else
+		*p += v;
+#endif
+	}
+	ARB_HD static void take_max(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+		atomicMax(p, v);
+#else
+		if (v > *p) *p = v;
+#endif
+	}
+	ARB_HD void operator()(u32 i) const {
+		const u32 a0 = f.idx(i, 0), a1 = f.idx(i, 1);
+		const u32 l0 = f.seq_len[a0], l1 = f.seq_len[a1];
+		const u32 u0 = ((l0 + 1) / 2 + 15) / 16, u1 = ((l1 + 1) / 2 + 15) / 16;
+		u32 breaks = 0;
+		if (f.seq_off[a1] != f.seq_off[a0] + u0) ++breaks;
+		if (i + 1 < f.n) { if (f.seq_off[f.idx(i + 1, 0)] != f.seq_off[a1] + u1) ++breaks; }
+#ifdef __CUDA_ARCH__
+		// one atomic per warp and statistic
+		const unsigned active = __activemask();
+		u32 mx = l0 > l1 ? l0 : l1, bases = l0 + l1, alns = f.n_aln[i];
+		for (int d = 16; d; d >>= 1) { const u32 m2 = __shfl_xor_sync(active, mx, d), b2 = __shfl_xor_sync(active, bases, d), a2 = __shfl_xor_sync(active, alns, d), k2 = __shfl_xor_sync(active, breaks, d); mx = m2 > mx ? m2 : mx; bases += b2; alns += a2; breaks += k2; }
+		if (active == 0xFFFFFFFFu) { if ((threadIdx.x & 31u) == 0) { take_max(out, mx); add(out + 1, bases); add(out + 2, alns); if (breaks) add(out + 3, breaks); } return; }
+		mx = l0 > l1 ? l0 : l1; bases = l0 + l1; alns = f.n_aln[i]; breaks = (f.seq_off[a1] != f.seq_off[a0] + u0) + ((i + 1 < f.n) && f.seq_off[f.idx(i + 1, 0)] != f.seq_off[a1] + u1);
+#else
+		const u32 mx = l0 > l1 ? l0 : l1, bases = l0 + l1, alns = f.n_aln[i];
+#endif
+		take_max(out, mx); add(out + 1, bases); add(out + 2, alns); if (breaks) add(out + 3, breaks);
+	}
+};
+
 void engine::push_chunk_begin(const arb_soa_chunk& c) {
 	const u32 n = c.n_fragments;
 	ex.sync(); // kernels of the previous sample may still read the buffers that are about to be overwritten
@@ -145,23 +182,18 @@ void engine::push_chunk_begin(const arb_soa_chunk& c) {
 	frags.cigar_off.upload(cx, c.cigar_off, 3 * (size_t) n); frags.cigar_cnt.upload(cx, c.cigar_cnt, 3 * (size_t) n);
 	frags.seq_off.upload(cx, c.seq_off, 2 * (size_t) n); frags.seq_len.upload(cx, c.seq_len, 2 * (size_t) n);
 	frags.cigar.upload(cx, c.cigar, c.n_cigar); frags.seq.upload(cx, c.seq, c.n_seq_bytes);
-	// host-side statistics of the chunk while the copies run
-	u32 max_len = 0;
-	for (size_t k = 0; k < 2 * (size_t) n; ++k) if (c.seq_len[k] > max_len) max_len = c.seq_len[k];
-	frags.max_seq_len = max_len;
-	// canonical pool layout (what ingest writes): sequences in fragment order, slot 0 then slot 1, back to back in 16-byte units; the sequence kernel then
-	// stages a tile of fragments with one bulk copy (k_cascade_sequences). Any other layout is read in place.
+	// statistics of the chunk, taken on the device behind the copies (a pass over four columns: serial on the host it cost a tenth of a second per 10 M
+	// fragments): longest sequence, bases, alignments, and whether the sequence pool has the canonical layout (what ingest writes: sequences in fragment
+	// order, slot 0 then slot 1, back to back in 16-byte units -- the sequence kernel then stages a tile of fragments with one bulk copy)
+	chunk_stats.ensure(8); chunk_stats.zero(cx, 8);
+	chunk_stats_fn cs = {frags.view(), (unsigned long long*) chunk_stats.ptr()};
+	for_each(cx, n, cs);
+	u64 st[4] = {0, 0, 0, 0};
+	chunk_stats.download(cx, st, 4);
+	frags.max_seq_len = (u32) st[0];
 	frags.n_seq_bytes = c.n_seq_bytes;
-	{
-		bool canonical = n > 0 && c.n_seq_bytes % 16 == 0; u64 at = n ? c.seq_off[0] : 0;
-		for (size_t i = 0; i < n && canonical; ++i)
-			for (u32 s = 0; s < 2; ++s) { const size_t a = s * (size_t) n + i; if (c.seq_off[a] != at) { canonical = false; break; } at += ((c.seq_len[a] + 1) / 2 + 15) / 16; }
-		frags.canonical_seq_layout = canonical && at * 16 <= c.n_seq_bytes;
-	}
-	u64 n_alignments = 0, bases = 0;
-	for (size_t k = 0; k < n; ++k) n_alignments += c.n_aln[k];
-	for (size_t k = 0; k < 2 * (size_t) n; ++k) bases += c.seq_len[k];
-	push_alignments = n_alignments; push_bases = bases; push_cigar_ops = c.n_cigar;
+	frags.canonical_seq_layout = n > 0 && c.n_seq_bytes % 16 == 0 && st[3] == 0;
+	push_alignments = st[2]; push_bases = st[1]; push_cigar_ops = c.n_cigar;
 	timings.h2d_ms = t_h2d.stop(); // waits for part one: the caller's annotation takes far longer than the copy, and the timing stays a pure copy time
 	timings.h2d_bytes = (u64) n * 3 + (u64) n * 3 * (2 + 4 + 4 + 4 + 2) + (u64) n * 2 * (4 + 2) + c.n_cigar * 4 + c.n_seq_bytes;
 	push_open = true;

@@ -108,7 +108,7 @@ public:
 	u32 annotate_pass1(const u8* aflags, int strandedness); void get_dummy_genes(u16* contig, i32* start, i32* end); u64 annotate_pass2();
 	void get_annotation_columns(u8* aflags, u32* genes_off, u16* genes_cnt, u32* genes);
 	dbuf<u32> annot_rows, annot_pool, annot_ctl; dbuf<u16> annot_cnt; u32 annot_pool_cap, n_dummy; u64 n_gene_entries; dbuf<u16> dummy_contig; dbuf<i32> dummy_start, dummy_end;
-	void finish_push(u64 n_gene_ids); u64 push_cigar_ops;
+	void finish_push(u64 n_gene_ids); u64 push_cigar_ops; dbuf<u64> chunk_stats;
 	// one sample on several GPUs (exchange.cu): replicated state travels as groups of device buffers, the work of find_fusions / filter_mismappers is divided
 	void exchange_header(int group, std::vector<u64>& header); void exchange_prepare(int group, const u64* header, u32 n_words);
 	void exchange_buffers(int group, std::vector<exchange_buffer>& out); void exchange_commit(int group);

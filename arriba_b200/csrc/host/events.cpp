@@ -138,8 +138,8 @@ void event_table::replay_iteration_order(int hash_threads) {
 			bucket[b] = BEFORE_BEGIN;
 		}
 	}
-	order.clear(); order.reserve(n);
-	for (u32 p = next[BEFORE_BEGIN]; p != NONE; p = next[p]) order.push_back(p);
+	order.clear(); order.reserve(n); rank_of.assign(n, 0);
+	for (u32 p = next[BEFORE_BEGIN]; p != NONE; p = next[p]) { rank_of[p] = (u32) order.size(); order.push_back(p); }
 	if (order.size() != n) throw std::runtime_error("candidate keys are not unique");
 }
 
@@ -272,27 +272,22 @@ void pipeline::estimate_evalues() {
 	{
 		struct occurrence { u32 gene; i32 bp1, bp2; u32 rank; u32 partner; };
 		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
-		const size_t n_order = e.order.size();
 		std::vector<occurrence, default_init_allocator<occurrence> > all;
-		{ // collected by slices of the iteration order, concatenated in slice order
-			const int T = std::max(1, std::min(threads, (int) (n_order / 4096 + 1)));
+		{ // few candidates are still unfiltered here: the table is read front to back (the rank of a candidate in the iteration order is looked up, not followed)
+			const int T = std::max(1, std::min(threads, (int) (e.n / 65536 + 1)));
 			std::vector<std::vector<occurrence> > part(T);
 			std::vector<std::thread> pool;
 			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
 				std::vector<occurrence>& v = part[t];
-				for (size_t q = n_order * t / T; q < n_order * (t + 1) / T; ++q) {
-					const u32 k = e.order[q];
+				for (u32 k = (u32) ((u64) e.n * t / T); k < (u32) ((u64) e.n * (t + 1) / T); ++k) {
 					if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
-					const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], (u32) q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], (u32) q, e.gene2[k]};
+					const u32 q = e.rank_of[k];
+					const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], q, e.gene2[k]};
 					v.push_back(a); v.push_back(b);
 				}
 			});
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-			std::vector<size_t> at(T + 1, 0); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + part[t].size();
-			all.resize(at[T]);
-			pool.clear();
-			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { std::copy(part[t].begin(), part[t].end(), all.begin() + at[t]); });
-			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+			for (int t = 0; t < T; ++t) all.insert(all.end(), part[t].begin(), part[t].end());
 		}
 		parallel_sort(all, before, threads);
 		for (size_t x = 0; x < all.size(); ++x)
@@ -556,10 +551,9 @@ void pipeline::select_best() { // select_best.cpp
 	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
 	struct entry { u64 key; u32 rank, cand; };
 	std::vector<entry> entries;
-	for (size_t q = 0; q < ev.order.size(); ++q) {
-		const u32 k = ev.order[q];
+	for (u32 k = 0; k < ev.n; ++k) { // the table front to back: the rank in the iteration order is a column (rank_of), the sort below restores the order
 		if (ev.filter[k] != F_none) continue;
-		const entry x = {(u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) (ev.dir1[k] != 0) << 1 | (u64) (ev.dir2[k] != 0), (u32) q, k};
+		const entry x = {(u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) (ev.dir1[k] != 0) << 1 | (u64) (ev.dir2[k] != 0), ev.rank_of[k], k};
 		entries.push_back(x);
 	}
 	parallel_sort(entries, [](const entry& a, const entry& b) { return a.key != b.key ? a.key < b.key : a.rank < b.rank; }, threads);
@@ -699,9 +693,12 @@ void pipeline::filter_no_coverage() { // filter_no_coverage.cpp
 void pipeline::recover_isoforms() { // recover_isoforms.cpp
 	typedef std::tuple<u32, u32, bool, bool> pair_key;
 	std::map<pair_key, u32> fused; // last unfiltered candidate in iteration order wins
-	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; if (ev.filter[k] == F_none) fused[pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k])] = k; }
-	for (size_t q = 0; q < ev.order.size(); ++q) {
-		const u32 k = ev.order[q]; const u8 fl = ev.filter[k];
+	for (u32 k = 0; k < ev.n; ++k) if (ev.filter[k] == F_none) { // the one with the highest rank in the iteration order
+		const std::pair<std::map<pair_key, u32>::iterator, bool> ins = fused.insert(std::make_pair(pair_key(ev.gene1[k], ev.gene2[k], (bool) ev.dir1[k], (bool) ev.dir2[k]), k));
+		if (!ins.second && ev.rank_of[k] > ev.rank_of[ins.first->second]) ins.first->second = k;
+	}
+	for (u32 k = 0; k < ev.n; ++k) { // a verdict per candidate, independent of the others (`fused` and the breakpoints it points at do not change)
+		const u8 fl = ev.filter[k];
 		if (fl == F_none) continue;
 		if (fl == F_merge_adjacent || fl == F_blacklist || fl == F_end_to_end || fl == F_duplicates || ev.gene1[k] == ev.gene2[k]) continue;
 		if (!(ev.spliced1(k) && ev.spliced2(k))) continue;
@@ -825,8 +822,13 @@ void pipeline::filter_mismappers() { // filter_mismappers.cpp:272-359, on the de
 }
 
 void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no structural-variant input: closest_genomic_breakpoint = -1)
-	std::vector<std::vector<u32> > by_gene(ref.genes.size());
-	for (size_t q = 0; q < ev.order.size(); ++q) { const u32 k = ev.order[q]; by_gene[ev.gene1[k]].push_back(k); by_gene[ev.gene2[k]].push_back(k); }
+	// the candidates of every gene (only counted below, so their order does not matter): one CSR table instead of a vector per gene
+	struct gene_list { const u32* p; size_t n; size_t size() const { return n; } u32 operator[](size_t x) const { return p[x]; } };
+	std::vector<u32> by_gene_off(ref.genes.size() + 1, 0), by_gene_items(2 * (size_t) ev.n);
+	for (u32 k = 0; k < ev.n; ++k) { ++by_gene_off[ev.gene1[k] + 1]; ++by_gene_off[ev.gene2[k] + 1]; }
+	for (size_t g = 0; g < ref.genes.size(); ++g) by_gene_off[g + 1] += by_gene_off[g];
+	{ std::vector<u32> at(by_gene_off.begin(), by_gene_off.end() - 1); for (u32 k = 0; k < ev.n; ++k) { by_gene_items[at[ev.gene1[k]]++] = k; by_gene_items[at[ev.gene2[k]]++] = k; } }
+	auto by_gene = [&](u32 g) { gene_list l = {by_gene_items.data() + by_gene_off[g], by_gene_off[g + 1] - by_gene_off[g]}; return l; };
 	enum { LOW = 0, MEDIUM = 1, HIGH = 2 };
 	parallel_rows(threads, ev.n, [&](u32 k) {
 		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
@@ -842,7 +844,7 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 			else {
 				unsigned int deletions = 0;
 				for (int side = 0; side < 2; ++side) {
-					const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[k] : ev.gene2[k]];
+					const gene_list v = by_gene(side == 0 ? ev.gene1[k] : ev.gene2[k]);
 					for (size_t x = 0; x < v.size(); ++x) {
 						const u32 o = v[x];
 						if (ev.filter[o] == F_none && ev.split_reads1[o] + ev.split_reads2[o] > 0 && ev.dir1[o] == DOWNSTREAM && ev.dir2[o] == UPSTREAM &&
@@ -864,7 +866,7 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 		if (conf < HIGH && ev.spliced1(k) && ev.spliced2(k) && !ev.is_read_through(k) && ev.gene1[k] != ev.gene2[k]) {
 			unsigned int n_spliced = 0;
 			for (int side = 0; side < 2; ++side) {
-				const std::vector<u32>& v = by_gene[side == 0 ? ev.gene1[k] : ev.gene2[k]];
+				const gene_list v = by_gene(side == 0 ? ev.gene1[k] : ev.gene2[k]);
 				for (size_t x = 0; x < v.size(); ++x) { const u32 o = v[x]; if (ev.gene1[o] == ev.gene1[k] && ev.gene2[o] == ev.gene2[k] && ev.spliced1(o) && ev.spliced2(o) && (std::abs(ev.bp1[o] - ev.bp1[k]) > 2 || std::abs(ev.bp2[o] - ev.bp2[k]) > 2)) ++n_spliced; }
 			}
 			if (n_spliced > 0) ++conf;

@@ -24,6 +24,7 @@ struct event_table {
 	column<float> evalue;
 	column<u32> list1_off, list2_off, listd_off, list1, list2, listd; // CSR, fragment indices in name order
 	std::vector<u32> order; // order[k] = candidate visited k-th by the reference's loops
+	std::vector<u32> rank_of; // inverse of `order`
 	event_table(): n(0) {}
 
 	bool exonic1(u32 k) const { return bits[k] & CB_EXONIC1; }

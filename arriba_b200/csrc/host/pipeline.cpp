@@ -36,6 +36,11 @@ void pipeline::load_reference() {
 	ref.build_gene_index();
 	ref.compute_exonic_lengths();
 	ref.flatten();
+	// the genome goes to the device with the reference (once per process in a deployment that runs sample after sample); a BAM header that names contigs the
+	// assembly does not have makes begin_upload() send the grown contig table again
+	ref.set_contig_flags(opt.interesting_contigs, opt.viral_contigs);
+	ref.flatten();
+	if (getenv("ARB_EARLY_REFERENCE") == NULL || atoi(getenv("ARB_EARLY_REFERENCE")) != 0) upload_reference();
 	t_reference = now_s() - t0;
 }
 
@@ -82,13 +87,13 @@ void pipeline::attach_device() {
 
 void pipeline::upload_reference() {
 	attach_device();
-	if (reference_on_device) return;
 	const u32 nc = (u32) ref.contig_ids.size();
+	if (reference_on_device && contigs_on_device == nc) return;
 	std::vector<const char*> seqs(nc, (const char*) NULL);
 	for (u32 c = 0; c < nc; ++c) if (ref.has_sequence(c)) seqs[c] = ref.sequence(c);
 	arb_contigs contigs = {nc, ref.contig_flags.data(), ref.seq_len.data(), seqs.data()};
 	check(ctx, arb_set_contigs(ctx, &contigs), "arb_set_contigs");
-	reference_on_device = true;
+	reference_on_device = true; contigs_on_device = nc;
 }
 
 arb_soa_chunk pipeline::chunk_of(fragment_table& frags) {

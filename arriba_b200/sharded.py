@@ -127,6 +127,12 @@ def run_sharded(pipeline, rank, world, last_event=None, write_output=True, refer
             pipeline.write_output()
         return
     tr = Transport(rank, world, pipeline.lib.arb_backend().decode().startswith("cuda"))
+    import os, sys, time
+    trace = os.environ.get("ARB_TRACE") and rank == 0
+    t_last = [time.perf_counter()]
+    def lap(what):
+        if trace:
+            tr.fence(); t = time.perf_counter(); sys.stderr.write("[laps] sharded                %-34s %8.1f ms\n" % (what, (t - t_last[0]) * 1e3)); t_last[0] = t
     last_event = len(L.EV_NAMES) - 1 if last_event is None else last_event
     if rank == 0:
         for s in (L.STEP_LOAD_REFERENCE, L.STEP_INGEST, L.STEP_ANNOTATE, L.STEP_UPLOAD):
@@ -136,37 +142,48 @@ def run_sharded(pipeline, rank, world, last_event=None, write_output=True, refer
     else:
         pipeline.attach_device()
     ctx = pipeline.context()
+    lap("ingest + annotate (rank 0)")
     for g in (XG_CONTIGS, XG_ANNOTATION, XG_TABLE):
         tr.bcast_group(ctx, g)
+    lap("genome, annotation, table -> all ranks")
     keys, owner = pipeline.work_partition(world) if rank == 0 else (np.zeros(0, np.uint32), np.zeros(0, np.uint8))
     keys = tr.bcast_array(keys, np.uint32); owner = tr.bcast_array(owner, np.uint8)
     ctx.set_work_partition(keys, owner, rank, world)
+    lap("work partition")
     if rank == 0:
         pipeline.step(L.STEP_READ_FILTERS); pipeline.step(L.STEP_FRAGMENT_LENGTH)
         gap = int(pipeline.stats().max_mate_gap)
     else:
         ctx.run_read_filters(); gap = 0
     gap = tr.bcast_ints([gap], 1)[0]
+    lap("read filters + fragment length")
     if rank == 0:
         pipeline.step(L.STEP_FIND_FUSIONS)
     else:
         ctx.find_fusions(gap)
+    lap("find_fusions (own contig pairs)")
     tr.gather_candidates(ctx)
     p, n = ctx.swaps_buffer(); tr.max_bytes(p, n); ctx.swaps_apply()
+    lap("candidate all-gather + merge + mate swaps")
     if last_event < L.EV_NAMES.index("mismappers"):
         if rank == 0:
             pipeline.events(last_event)
         return
     active = pipeline.mismappers_begin() if rank == 0 else False
     active = bool(tr.bcast_ints([int(active)], 1)[0])
+    lap("event chain up to the re-alignment (rank 0)")
     if active:
         tr.bcast_group(ctx, XG_MISMAP_STATE)
+        lap("re-alignment inputs -> all ranks")
         p, n = ctx.filter_mismappers_part(gap, rank, world)
         tr.max_bytes(p, n)
         if rank == 0:
             ctx.filter_mismappers_finish()
+        lap("re-alignment (own items) + verdict all-reduce")
     if rank == 0:
         pipeline.mismappers_end()
         pipeline.events(last_event)
+        lap("rest of the event chain (rank 0)")
         if write_output:
             pipeline.write_output()
+        lap("output (rank 0)")
