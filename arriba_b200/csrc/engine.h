@@ -132,6 +132,7 @@ public:
 	void get_merge_log(u32* triples, u32 n);
 	void estimate_evalues(const arb_evalue_inputs& in);
 	void filter_relative_support(float cutoff); void filter_multimappers();
+	void replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out);
 	dbuf<u32> merge_log; u32 merge_log_n;
 	// filter_in_vitro on the device (events.cu): coverage windows of the sample, expression per gene
 	void set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs); void reads_by_gene(u32* out);

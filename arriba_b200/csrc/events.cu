@@ -182,4 +182,35 @@ void engine::filter_multimappers() {
 	ex.sync();
 }
 
+// phases: candidates [phase_start[j], phase_start[j + 1]) are inserted while the map has phase_buckets[j] buckets (phase_start[n_phases] = n candidates)
+void engine::replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out) {
+	const u32 C = cands.n;
+	if (C == 0) return;
+	if (n_phases == 0 || phase_start[0] != 0 || phase_start[n_phases] != C) throw arb_error("arb_replay_insertion_order: the phases must cover all candidates");
+	stage_timer t_all(ex);
+	dbuf<u64> code(C);
+	order_code_fn cf = {make_state(cands, NULL, NULL), code.ptr()};
+	for_each(ex, C, cf);
+	dbuf<u32> seq(C), bucket(C), key(C), val(C), tk(C), tv(C), first;
+	for (u32 j = 0; j < n_phases; ++j) {
+		const u32 from = phase_start[j], m = phase_start[j + 1]; const u64 B = phase_buckets[j];
+		if (m < from || B == 0 || B > 0xFFFFFFF0ull) throw arb_error("arb_replay_insertion_order: malformed phase");
+		if (m == from) continue;
+		order_append_fn ap = {seq.ptr(), from}; for_each(ex, m - from, ap); // the list so far is seq[0, from)
+		first.ensure(B); first.fill_bytes(ex, 0xFF, B);
+		order_bucket_fn bf = {seq.ptr(), code.ptr(), B, bucket.ptr(), first.ptr()};
+		for_each(ex, m, bf);
+		order_key_fn kf = {seq.ptr(), bucket.ptr(), first.ptr(), m, key.ptr(), val.ptr()};
+		for_each(ex, m, kf);
+		u32 bits = 1; while (bits < 32 && ((u64) 1 << bits) < m) ++bits;
+		radix_sort_pairs_u32(ex, key.ptr(), val.ptr(), tk.ptr(), tv.ptr(), m, bits);
+		seq.swap(val);
+	}
+	dbuf<u32> rank(C);
+	order_rank_fn rf = {seq.ptr(), rank.ptr()};
+	for_each(ex, C, rf);
+	timings.order_ms = t_all.stop();
+	seq.download(ex, order_out, C); rank.download(ex, rank_out, C);
+}
+
 } // namespace arb

@@ -427,4 +427,29 @@ struct multimapper_recount_fn { // :153-166
 	}
 };
 
+// ---- iteration order of the reference's candidate map (fusions_t = std::unordered_map, common.hpp:286-314), which several event stages and the discarded
+// file depend on. libstdc++ keeps all nodes in one list; a new node goes to the FRONT of its bucket's run, or -- first node of its bucket -- to the front
+// of the whole list; growing re-inserts the nodes, in list order, into the new bucket array by the same rule (bits/hashtable.h: _M_insert_bucket_begin,
+// _M_rehash_aux). So for an insertion sequence S into an empty table of B buckets the list reads: buckets by DESCENDING time of their first node, inside a
+// bucket nodes by DESCENDING time -- a sort, not a simulation. The whole history is a chain of such sorts: at every growth the current list, followed by the
+// candidates inserted until the next growth, is the sequence of the next sort. The caller supplies the growth schedule (the library's own policy object).
+struct order_code_fn { // value-identical to the reference's recursive tuple hash: h(e0) ^ (H(rest) << 4), H() = 0; std::hash of an integer is the integer
+	cand_state c; u64* code;
+	ARB_HD void operator()(u32 k) const {
+		u64 h = 0;
+		h = (u64) (c.dir2[k] != 0) ^ (h << 4); h = (u64) (c.dir1[k] != 0) ^ (h << 4);
+		h = (u64) (i64) c.bp2[k] ^ (h << 4); h = (u64) (i64) c.bp1[k] ^ (h << 4);
+		h = (u64) c.contig2[k] ^ (h << 4); h = (u64) c.contig1[k] ^ (h << 4);
+		h = (u64) c.gene2[k] ^ (h << 4); h = (u64) c.gene1[k] ^ (h << 4);
+		code[k] = h;
+	}
+};
+struct order_bucket_fn { const u32* seq; const u64* code; u64 n_buckets; u32* bucket; u32* first; ARB_HD void operator()(u32 i) const { const u32 b = (u32) (code[seq[i]] % n_buckets); bucket[i] = b; atomic_min_u32(&first[b], i); } };
+struct order_key_fn { // position i' of the reversed sequence: key ascending = first node of the bucket descending
+	const u32* seq; const u32* bucket; const u32* first; u32 m; u32* key; u32* val;
+	ARB_HD void operator()(u32 r) const { const u32 i = m - 1 - r; key[r] = m - 1 - first[bucket[i]]; val[r] = seq[i]; }
+};
+struct order_append_fn { u32* seq; u32 from; ARB_HD void operator()(u32 k) const { seq[from + k] = from + k; } };
+struct order_rank_fn { const u32* order; u32* rank; ARB_HD void operator()(u32 q) const { rank[order[q]] = q; } };
+
 } // namespace arb

@@ -81,66 +81,29 @@ template <class V, class Less> static void parallel_sort(V& v, Less less, int th
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 
 // ------------------------------------------------------------------------------------------- iteration order
-namespace {
-typedef std::tuple<unsigned int, unsigned int, unsigned short, unsigned short, int, int, bool, bool> cand_key;
-struct cand_key_hash { // value-identical to the reference's recursive tuple hash: h(e0) ^ (H(rest) << 4), H() = 0   (common.hpp:295-314)
-	size_t operator()(const cand_key& k) const {
-		size_t h = 0;
-		h = std::hash<bool>()(std::get<7>(k)) ^ (h << 4);
-		h = std::hash<bool>()(std::get<6>(k)) ^ (h << 4);
-		h = std::hash<int>()(std::get<5>(k)) ^ (h << 4);
-		h = std::hash<int>()(std::get<4>(k)) ^ (h << 4);
-		h = std::hash<unsigned short>()(std::get<3>(k)) ^ (h << 4);
-		h = std::hash<unsigned short>()(std::get<2>(k)) ^ (h << 4);
-		h = std::hash<unsigned int>()(std::get<1>(k)) ^ (h << 4);
-		h = std::hash<unsigned int>()(std::get<0>(k)) ^ (h << 4);
-		return h;
-	}
-};
-}
-
-// The reference inserts the candidates, in the order the device numbers them, into a std::unordered_map and later ITERATES it. libstdc++ keeps all nodes in
-// one singly linked list; a bucket stores the node BEFORE its first node; a new node goes to the front of its bucket, or to the front of the whole list if
-// the bucket was empty; growing re-threads the list in its current order (bits/hashtable.h: _M_insert_bucket_begin, _M_rehash_aux). Replaying that with
-// index arrays instead of a real map gives the same order without one heap node per candidate; bucket counts come from the library's own policy object.
-void event_table::replay_iteration_order(int hash_threads) {
-	const u32 NONE = 0xFFFFFFFFu, BEFORE_BEGIN = n; // list positions: 0..n-1 candidates, n = the list head sentinel
-	std::vector<size_t> code(n);
-	parallel_rows(hash_threads, n, [&](u32 k) { code[k] = cand_key_hash()(cand_key(gene1[k], gene2[k], contig1[k], contig2[k], bp1[k], bp2[k], (bool) dir1[k], (bool) dir2[k])); });
-	std::vector<u32> next((size_t) n + 1, NONE);
-	std::vector<u32> bucket(1, NONE); // node before the first node of the bucket
+// The reference inserts the candidates, in the order the device numbers them, into a std::unordered_map and later ITERATES it. The order is computed on the
+// device from the resident candidate keys (csrc/events_hd.h, "iteration order"); the host contributes what only its C++ library knows: when the table grows and
+// to how many buckets (the library's own policy object, asked exactly like unordered_map::insert asks it).
+void pipeline::replay_iteration_order() {
+	const u32 n = ev.n;
+	ev.order.assign(n, 0); ev.rank_of.assign(n, 0);
+	if (n == 0) return;
+	std::vector<u32> phase_start; std::vector<uint64_t> phase_buckets;
 	std::__detail::_Prime_rehash_policy policy;
 	size_t n_buckets = 1;
-	for (u32 k = 0; k < n; ++k) {
+	phase_start.push_back(0); phase_buckets.push_back(1);
+	for (size_t k = 0; k < n; ) {
 		const std::pair<bool, size_t> grow = policy._M_need_rehash(n_buckets, k, 1);
 		if (grow.first) {
-			std::vector<u32> fresh(grow.second, NONE);
-			u32 p = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = NONE;
-			size_t first_bucket = 0;
-			while (p != NONE) {
-				const u32 following = next[p];
-				const size_t b = code[p] % grow.second;
-				if (fresh[b] == NONE) {
-					next[p] = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = p; fresh[b] = BEFORE_BEGIN;
-					if (next[p] != NONE) fresh[first_bucket] = p;
-					first_bucket = b;
-				} else { next[p] = next[fresh[b]]; next[fresh[b]] = p; }
-				p = following;
-			}
-			bucket.swap(fresh); n_buckets = grow.second;
+			n_buckets = grow.second;
+			if (phase_start.back() == k) phase_buckets.back() = n_buckets; else { phase_start.push_back((u32) k); phase_buckets.push_back(n_buckets); }
 		}
-		if (k + 16 < n) __builtin_prefetch(&bucket[code[k + 16] % n_buckets]);
-		const size_t b = code[k] % n_buckets;
-		if (bucket[b] != NONE) { next[k] = next[bucket[b]]; next[bucket[b]] = k; }
-		else {
-			next[k] = next[BEFORE_BEGIN]; next[BEFORE_BEGIN] = k;
-			if (next[k] != NONE) bucket[code[next[k]] % n_buckets] = k;
-			bucket[b] = BEFORE_BEGIN;
-		}
+		// the policy answers "no" without changing its state until the element count passes its next threshold
+		const size_t next = policy._M_next_resize;
+		k = std::max(k + 1, std::min<size_t>(next, n));
 	}
-	order.clear(); order.reserve(n); rank_of.assign(n, 0);
-	for (u32 p = next[BEFORE_BEGIN]; p != NONE; p = next[p]) { rank_of[p] = (u32) order.size(); order.push_back(p); }
-	if (order.size() != n) throw std::runtime_error("candidate keys are not unique");
+	phase_start.push_back(n);
+	check(ctx, arb_replay_insertion_order(ctx, phase_start.data(), phase_buckets.data(), (uint32_t) phase_buckets.size(), ev.order.data(), ev.rank_of.data()), "arb_replay_insertion_order");
 }
 
 // ------------------------------------------------------------------------------------------- helpers on (table, reference)
@@ -182,12 +145,8 @@ void pipeline::fetch_candidates() {
 	check(ctx, arb_get_candidates(ctx, &c), "arb_get_candidates");
 	laps.lap("device -> host");
 	e.list1.resize(n1); e.list2.resize(n2); e.listd.resize(nd);
-	// the order needs the candidate keys only, which no later stage changes: it is replayed (one thread, after the hashes) beside the stages up to the e-value
-	if (order_thread.joinable()) order_thread.join();
-	order_error.clear();
-	e.order.clear();
-	order_thread = std::thread([this]() { try { ev.replay_iteration_order(threads); } catch (const std::exception& x) { order_error = x.what(); if (order_error.empty()) order_error = "iteration order"; } });
-	laps.lap("iteration order started");
+	replay_iteration_order(); // needs the candidate keys only, which no later stage changes
+	laps.lap("iteration order (device)");
 	// mirror the canonical mate order the device established for listed discordant mates (fusions.cpp:414-421)
 	std::vector<u8> swapped(frags.n);
 	check(ctx, arb_get_slot_swaps(ctx, swapped.data()), "arb_get_slot_swaps");
@@ -204,10 +163,7 @@ void pipeline::fetch_candidates() {
 	std::ostringstream s; s << "Finding fusions and counting supporting reads (total=" << count_unfiltered(e) << ")"; say(s.str());
 }
 
-void pipeline::order_ready() {
-	if (order_thread.joinable()) order_thread.join();
-	if (!order_error.empty()) { const std::string what = order_error; order_error.clear(); throw std::runtime_error(what); }
-}
+void pipeline::order_ready() {} // the order is complete when fetch_candidates returns
 
 void pipeline::push_candidate_state() {
 	check(ctx, arb_set_candidate_state(ctx, ev.filter.data(), ev.split_reads1.data(), ev.split_reads2.data(), ev.discordant_mates.data(), ev.evalue.data()), "arb_set_candidate_state");

@@ -36,7 +36,6 @@ struct event_table {
 	u32 n_list2(u32 k) const { return list2_off[k + 1] - list2_off[k]; }
 	u32 n_listd(u32 k) const { return listd_off[k + 1] - listd_off[k]; }
 	bool is_read_through(u32 k) const { return contig1[k] == contig2[k] && bp2[k] - bp1[k] < 400000 && dir1[k] == DOWNSTREAM && dir2[k] == UPSTREAM; } // common.hpp:265-269
-	void replay_iteration_order(int hash_threads = 1);
 };
 
 }} // namespace

@@ -21,7 +21,7 @@ void pipeline::say(const std::string& line) {
 	if (opt.echo_progress) { time_t now = time(0); char buf[64]; strftime(buf, sizeof(buf), "[%Y-%m-%dT%X]", localtime(&now)); std::cout << buf << " " << line << std::endl; }
 }
 
-pipeline::~pipeline() { if (order_thread.joinable()) order_thread.join(); if (ctx) arb_ctx_destroy(ctx); }
+pipeline::~pipeline() { if (ctx) arb_ctx_destroy(ctx); }
 
 static void check(arb_ctx* ctx, int rc, const char* what) { if (rc != 0) throw std::runtime_error(std::string(what) + ": " + arb_last_error(ctx)); }
 

@@ -44,10 +44,8 @@ struct pipeline {
 	int strandedness; i32 max_mate_gap; float read_length_mean, mate_gap_mean, mate_gap_stddev; bool fragment_length_ok;
 	std::vector<u8> labels, early;
 	event_table ev;
-	// ev.order (the reference's iteration order of its candidate map) is replayed by a helper thread while the first event stages, which do not need it, run;
-	// order_ready() is called by everything that reads ev.order
-	std::thread order_thread; std::string order_error;
-	void order_ready();
+	// ev.order (the reference's iteration order of its candidate map) is computed by fetch_candidates on the device
+	void order_ready(); void replay_iteration_order();
 	void say(const std::string& line); // appends to `log`, echoes with a time stamp when opt.echo_progress
 	std::string log; // the reference's progress lines (arriba.cpp:61-66 style, without time stamps)
 	double t_events[32], t_output;

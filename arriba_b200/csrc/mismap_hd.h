@@ -416,6 +416,28 @@ ARB_HD u32 env_kmer(const realign_env& env, u32 r) {
 // from the position alone); a lane looks up its position's 8-mer, finds the first hit at or after the lower bound through the block table and extends
 // every hit inside the window. Returns REALIGN_FOUND on the lane that reached min_score (the caller combines the lanes).
 enum { REALIGN_UNDECIDED_NO = 0, REALIGN_FOUND = 1, REALIGN_EXHAUSTED = 2 };
+// Eight bases of the read slice (on the strand of the search, from base r0) against eight reference bases from g0, in one XOR of packed words:
+// bit 28 - 4j of `differs` is set where base r0 + j differs from reference base g0 + j. false = this stretch has to be compared base by base (no packed
+// reference, or -- reverse strand -- an ambiguity code among the `cnt` bases in question: the reference complements A/C/G/T only, assembly.hpp:9-22, while
+// the bit reversal that complements a whole word would turn R into Y).
+ARB_HD bool env_differs8(const realign_env& env, int r0, int g0, int first, int cnt, u32& differs) { // bases first .. first + cnt - 1 of the window matter
+	if (!env.g4 || g0 < 0) return false;
+	u32 rw;
+	if (!env.rc) rw = nt16_window(env.seq, 0x7fffffffu, (i32) env.off + r0);
+	else {
+		const u32 w0 = nt16_window(env.seq, 0x7fffffffu, (i32) (env.off + env.len) - 8 - r0); // stored bases, in stored order: window base j is nibble 7 - j of w0
+		const u32 s2 = (w0 & 0x55555555u) + (w0 >> 1 & 0x55555555u), c4 = (s2 & 0x33333333u) + (s2 >> 2 & 0x33333333u); // bits set per nibble: 1 (A/C/G/T) or 4 (N) are fine
+		const u32 odd = (c4 ^ (c4 >> 2)) & 0x11111111u;   // nibble count 1 -> 1, 4 -> 1, 0 / 2 -> 0, 3 -> 1 ...
+		const u32 three = c4 & (c4 >> 1) & 0x11111111u;    // ... except 3
+		const u32 simple = odd & ~three;                   // bit 4k: nibble k holds A, C, G, T or N
+		const u32 wanted = (cnt >= 8 ? 0x11111111u : ((0x11111111u >> (32 - 4 * cnt)))) << (4 * first); // window bases first .. first+cnt-1 = nibbles first .. of w0 (reversed order)
+		if ((simple & wanted) != wanted) return false;
+		rw = brev32(w0);
+	}
+	const u32 x = rw ^ packed_window(env.g4, (u64) (u32) g0);
+	differs = (x | x >> 1 | x >> 2 | x >> 3) & 0x11111111u;
+	return true;
+}
 ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, const realign_worklist& wl, int read_pos, int hit, u32& steps) {
 	const u8* const seq = env.seq; const u32 off = env.off; const bool rc = env.rc; const int len = (int) env.len;
 	const i32 wstart = env.wstart, wend = env.wend; const int min_score = env.min_score;
@@ -427,12 +449,24 @@ ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, con
 	int ext = score + 8;
 	if (leading) ext += skipped;
 	if (ext >= min_score) return true;
-	{ // extend to the left over the skipped bases, one mismatch allowed
+	{ // extend to the left over the skipped bases, one mismatch allowed; eight bases per packed comparison where that is possible
 		int r = read_pos - 1, gp = hit - 1; u32 mm = 0;
-		while (r >= read_pos - skipped && gp >= wstart) {
-			if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
-			else if (++mm > 1) break;
-			--r; --gp;
+		const int r_stop = read_pos - skipped;
+		bool open = true;
+		while (open && r >= r_stop && gp >= wstart) {
+			const int cnt = hd_min(8, hd_min(r - r_stop + 1, gp - wstart + 1)); // bases r, r-1, ... r-cnt+1 = window bases 7 .. 8-cnt of the window that starts at r - 7
+			u32 differs;
+			if (env_differs8(env, r - 7, gp - 7, 8 - cnt, cnt, differs)) {
+				for (int j = 7; j > 7 - cnt; --j) {
+					if (!(differs >> (28 - 4 * j) & 1u)) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
+					else if (++mm > 1) { open = false; break; }
+				}
+				r -= cnt; gp -= cnt;
+			} else {
+				if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ext += leading ? 1 : 2; if (ext >= min_score) return true; }
+				else if (++mm > 1) break;
+				--r; --gp;
+			}
 		}
 	}
 	{ // extend to the right; a spliced continuation at splice sites and one deletion at the first mismatch go to the worklist
@@ -440,18 +474,22 @@ ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, con
 		u32 ss = lower_bound_i32(env.splice, 0, env.n_splice, gp - 1);
 		i32 next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff;
 		while (r < len && gp <= wend) {
-			++steps;
-			if (gp - 1 >= next_site) {
-				if (gp - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
-				if (gp - 1 == next_site) worklist_push(wl, task, ext, r, gp, max_deletions, len, min_score);
+			int cnt = hd_min(8, hd_min(len - r, wend - gp + 1));
+			u32 differs;
+			if (!env_differs8(env, r, gp, 0, cnt, differs)) { cnt = 1; differs = env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r)) ? 0u : 0x10000000u; }
+			for (int j = 0; j < cnt; ++j, ++r, ++gp) {
+				++steps;
+				if (gp - 1 >= next_site) {
+					if (gp - 1 > next_site) { ++ss; next_site = ss < env.n_splice ? env.splice[ss] : 0x7fffffff; }
+					if (gp - 1 == next_site) worklist_push(wl, task, ext, r, gp, max_deletions, len, min_score);
+				}
+				if (!(differs >> (28 - 4 * j) & 1u)) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
+				else {
+					if (++mm == 1 && max_deletions > 0 && len >= 30) worklist_push(wl, task, ext, r, gp, max_deletions - 1, len, min_score);
+					--ext;
+					if (++consecutive >= 4) return false;
+				}
 			}
-			if (env_ref_equals(g4, ref, gp, env_code(seq, off, (u32) len, rc, (u32) r))) { ++ext; if (ext >= min_score) return true; consecutive = 0; }
-			else {
-				if (++mm == 1 && max_deletions > 0 && len >= 30) worklist_push(wl, task, ext, r, gp, max_deletions - 1, len, min_score);
-				--ext;
-				if (++consecutive >= 4) break;
-			}
-			++r; ++gp;
 		}
 	}
 	return false;

@@ -184,6 +184,13 @@ typedef struct arb_evalue_inputs {
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
 
+/* The order in which the reference's loops visit the candidates = the iteration order of fusions_t, a std::unordered_map (source/common.hpp:286-314) the
+ * candidates were inserted into in id order; estimate_expected_fusions, select_best, recover_isoforms, filter_homologs and the discarded file depend on it.
+ * libstdc++ puts a new node at the front of its bucket's run of the node list (a new bucket's run at the front of the list) and re-inserts the list, in
+ * order, when the table grows: the order follows from a chain of sorts, one per growth, done on the device over the resident candidate keys. The growth
+ * schedule is the caller's (its C++ library's std::__detail::_Prime_rehash_policy): candidates [phase_start[j], phase_start[j+1]) are inserted while the
+ * table has phase_buckets[j] buckets; phase_start has n_phases + 1 entries. order_out[q] = id of the candidate visited q-th, rank_out = its inverse. */
+int arb_replay_insertion_order(arb_ctx* ctx, const uint32_t* phase_start, const uint64_t* phase_buckets, uint32_t n_phases, uint32_t* order_out, uint32_t* rank_out);
 /* Replaces filter_multimappers (source/filter_multimappers.cpp:115): of the fragments that share a read name (fflags bit1 / bit3) only the one with the best
  * alignment score keeps its label, ties go to the fragment whose best candidate has more support; read counts of the candidates follow. Works on the
  * resident candidate state and fragment labels; results through arb_get_candidate_state / arb_get_fragment_filters. */
@@ -262,6 +269,7 @@ typedef struct arb_timings {
 	float annotate_ms;          /* arb_annotate_pass1 + arb_annotate_pass2 (kernels, sorts and scans on the context's stream) */
 	float in_vitro_ms;          /* arb_filter_in_vitro */
 	float multimappers_ms;      /* arb_filter_multimappers */
+	float order_ms;             /* arb_replay_insertion_order */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 /* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver
