@@ -116,6 +116,10 @@ int arb_reads_by_gene(arb_ctx* ctx, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.r
 int arb_filter_in_vitro(arb_ctx* ctx, const uint32_t* reads, uint32_t n_genes, uint32_t threshold, const uint64_t* pairs, uint64_t n_pairs) { ARB_API_BEGIN(ctx) ctx->e.filter_in_vitro(reads, n_genes, threshold, (const u64*) pairs, n_pairs); ARB_API_END(ctx) }
 int arb_spliced_support(arb_ctx* ctx, const uint32_t* reads, uint32_t n_genes, uint32_t threshold, uint32_t* out) { ARB_API_BEGIN(ctx) ctx->e.spliced_support(reads, n_genes, threshold, out); ARB_API_END(ctx) }
 int arb_replay_insertion_order(arb_ctx* ctx, const uint32_t* phase_start, const uint64_t* phase_buckets, uint32_t n_phases, uint32_t* order_out, uint32_t* rank_out) { ARB_API_BEGIN(ctx) ctx->e.replay_insertion_order(phase_start, (const u64*) phase_buckets, n_phases, order_out, rank_out); ARB_API_END(ctx) }
+int arb_partner_counts(arb_ctx* ctx, int32_t* out) { ARB_API_BEGIN(ctx) ctx->e.partner_counts(out); ARB_API_END(ctx) }
+int arb_set_row_texts(arb_ctx* ctx, const arb_row_texts* t) { ARB_API_BEGIN(ctx) if (!t) throw arb_error("null tables"); ctx->e.set_row_texts(*t); ARB_API_END(ctx) }
+int arb_format_discarded_rows(arb_ctx* ctx, const uint8_t* confidence, uint64_t* n_rows, uint64_t* n_bytes) { ARB_API_BEGIN(ctx) u64 r = 0, b = 0; ctx->e.format_discarded_rows(confidence, &r, &b); *n_rows = r; *n_bytes = b; ARB_API_END(ctx) }
+int arb_get_row_text(arb_ctx* ctx, char* out) { ARB_API_BEGIN(ctx) ctx->e.get_row_text(out); ARB_API_END(ctx) }
 int arb_filter_multimappers(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.filter_multimappers(); ARB_API_END(ctx) }
 int arb_set_splice_sites(arb_ctx* ctx, const uint32_t* off, const int32_t* sites) { ARB_API_BEGIN(ctx) ctx->e.set_splice_sites(off, sites); ARB_API_END(ctx) }
 int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* start, const int32_t* end, uint32_t n, uint32_t nc, uint64_t* n_indexed) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.build_kmer_index(contig, start, end, n, nc); if (n_indexed) *n_indexed = k; ARB_API_END(ctx) }

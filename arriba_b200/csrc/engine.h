@@ -132,7 +132,12 @@ public:
 	void get_merge_log(u32* triples, u32 n);
 	void estimate_evalues(const arb_evalue_inputs& in);
 	void filter_relative_support(float cutoff); void filter_multimappers();
-	void replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out);
+	void replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out); dbuf<u32> order_rank;
+	void partner_counts(i32* count_out); dbuf<u32> order_seq;
+	// rows of the discarded-fusions file (rows.cu)
+	void set_row_texts(const arb_row_texts& t); void format_discarded_rows(const u8* confidence, u64* n_rows, u64* n_bytes); void get_row_text(char* out);
+	dbuf<char> row_gene_name, row_gene_id, row_contig_name, row_filter_name, row_text; dbuf<u32> row_gene_name_off, row_gene_id_off, row_contig_name_off, row_filter_name_off; dbuf<i32> row_exon_prev, row_exon_next;
+	u8 row_filters_by_name[ARB_N_FILTERS]; u32 row_max_itd_length; bool has_row_texts; u64 row_text_bytes; struct cand_state make_state_for_rows();
 	dbuf<u32> merge_log; u32 merge_log_n;
 	// filter_in_vitro on the device (events.cu): coverage windows of the sample, expression per gene
 	void set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs); void reads_by_gene(u32* out);

@@ -13,6 +13,8 @@ static cand_state make_state(cand_store& c, u32* n1, u32* n2) {
 	return s;
 }
 
+cand_state engine::make_state_for_rows() { return make_state(cands, NULL, NULL); }
+
 void engine::set_candidate_state(const u8* f, const u32* s1, const u32* s2, const u32* dm, const float* ev) {
 	const u32 C = cands.n;
 	cands.filter.upload(ex, f, C); cands.split_reads1.upload(ex, s1, C); cands.split_reads2.upload(ex, s2, C); cands.discordant_mates.upload(ex, dm, C); cands.evalue.upload(ex, ev, C);
@@ -206,11 +208,59 @@ void engine::replay_insertion_order(const u32* phase_start, const u64* phase_buc
 		radix_sort_pairs_u32(ex, key.ptr(), val.ptr(), tk.ptr(), tv.ptr(), m, bits);
 		seq.swap(val);
 	}
-	dbuf<u32> rank(C);
-	order_rank_fn rf = {seq.ptr(), rank.ptr()};
+	order_rank.ensure(C);
+	order_rank_fn rf = {seq.ptr(), order_rank.ptr()};
 	for_each(ex, C, rf);
 	timings.order_ms = t_all.stop();
-	seq.download(ex, order_out, C); rank.download(ex, rank_out, C);
+	seq.download(ex, order_out, C); order_rank.download(ex, rank_out, C);
+	order_seq.swap(seq); // kept for the stages that visit candidates in this order on the device
+}
+
+// a gene's count = its distinct partners that have no more partners than the gene itself (filter_relative_support.cpp:19-60)
+void engine::partner_counts(i32* count_out) {
+	const u32 C = cands.n, G = annot.n_genes;
+	for (u32 g = 0; g < G; ++g) count_out[g] = 0;
+	if (C == 0) return;
+	if (order_rank.size() < C) throw arb_error("arb_partner_counts: arb_replay_insertion_order must be called first");
+	stage_timer t_all(ex);
+	cand_state s = make_state(cands, NULL, NULL);
+	dbuf<u32> flag((size_t) C + 1);
+	partner_eligible_fn el = {s, flag.ptr()};
+	for_each(ex, C, el);
+	exclusive_scan_u32(ex, flag.ptr(), flag.ptr(), C);
+	u32 E = 0; flag.download(ex, &E, 1, C);
+	if (E == 0) return;
+	if (E > 0x7FFFFFF0u) throw arb_error("too many candidates");
+	const u32 M = 2 * E;
+	dbuf<u32> occ(M), key(M), tk(M), tv(M);
+	partner_emit_fn em = {s, flag.ptr(), occ.ptr()};
+	for_each(ex, C, em);
+	u32 cbits = 1; while (cbits < 32 && ((u64) 1 << cbits) < C) ++cbits;
+	u32 gbits = 1; while (gbits < 32 && ((u64) 1 << gbits) < G) ++gbits;
+	const u32 bits[4] = {cbits, 32, 32, gbits};
+	for (int which = 0; which < 4; ++which) { // LSD over (gene, breakpoint1, breakpoint2, rank): every pass sorts the current order of the occurrences (stable)
+		partner_key_fn kf = {s, order_rank.ptr(), occ.ptr(), key.ptr(), which};
+		for_each(ex, M, kf);
+		radix_sort_pairs_u32(ex, key.ptr(), occ.ptr(), tk.ptr(), tv.ptr(), M, bits[which]);
+	}
+	dbuf<u32> head((size_t) M + 1);
+	partner_head_fn hf = {s, occ.ptr(), head.ptr()};
+	for_each(ex, M, hf);
+	exclusive_scan_u32(ex, head.ptr(), head.ptr(), M);
+	u32 P = 0; head.download(ex, &P, 1, M);
+	dbuf<u32> pg(P), pp(P), uflag(P), n_partners(G), count(G);
+	partner_pair_fn pf = {s, occ.ptr(), head.ptr(), pg.ptr(), pp.ptr()};
+	for_each(ex, M, pf);
+	// pairs by (gene, partner): stable sort by partner, then by gene (the group heads are in gene order already, the partners inside a gene are not)
+	radix_sort_pairs_u32(ex, pp.ptr(), pg.ptr(), tk.ptr(), tv.ptr(), P, gbits);
+	radix_sort_pairs_u32(ex, pg.ptr(), pp.ptr(), tk.ptr(), tv.ptr(), P, gbits);
+	n_partners.zero(ex, G); count.zero(ex, G);
+	partner_unique_fn uf = {pg.ptr(), pp.ptr(), uflag.ptr(), n_partners.ptr()};
+	for_each(ex, P, uf);
+	partner_count_fn cf = {pg.ptr(), pp.ptr(), uflag.ptr(), n_partners.ptr(), count.ptr()};
+	for_each(ex, P, cf);
+	timings.partners_ms = t_all.stop();
+	count.download(ex, (u32*) count_out, G);
 }
 
 } // namespace arb

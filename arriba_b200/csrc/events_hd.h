@@ -452,4 +452,30 @@ struct order_key_fn { // position i' of the reversed sequence: key ascending = f
 struct order_append_fn { u32* seq; u32 from; ARB_HD void operator()(u32 k) const { seq[from + k] = from + k; } };
 struct order_rank_fn { const u32* order; u32* rank; ARB_HD void operator()(u32 q) const { rank[order[q]] = q; } };
 
+// ---- fusion partners per gene for the e-value model (filter_relative_support.cpp:19-60). Of the candidates that share (gene, breakpoint1, breakpoint2) --
+// the same breakpoints annotated with overlapping partner genes -- only the one the reference visits FIRST contributes its partner (`overlap_duplicates`):
+// first = smallest rank in the iteration order. Sort the (gene, breakpoints, rank) occurrences, keep group heads, make the (gene, partner) pairs unique.
+struct partner_eligible_fn { cand_state c; u32* flag; ARB_HD void operator()(u32 k) const { flag[k] = (c.filter[k] == F_none && c.gene1[k] != c.gene2[k]) ? 1u : 0u; } };
+struct partner_emit_fn { // occurrence 2e: (gene2 sees partner gene1), 2e + 1: (gene1 sees partner gene2)
+	cand_state c; const u32* flag_scan; u32* occ_cand;
+	ARB_HD void operator()(u32 k) const { if (flag_scan[k + 1] != flag_scan[k]) { const u32 e = flag_scan[k]; occ_cand[2 * e] = k << 1; occ_cand[2 * e + 1] = k << 1 | 1u; } }
+};
+ARB_HD u32 occ_gene(const cand_state& c, u32 o) { return (o & 1u) ? c.gene1[o >> 1] : c.gene2[o >> 1]; }
+ARB_HD u32 occ_partner(const cand_state& c, u32 o) { return (o & 1u) ? c.gene2[o >> 1] : c.gene1[o >> 1]; }
+struct partner_key_fn { // which: 0 rank, 1 breakpoint2, 2 breakpoint1, 3 gene (least significant first)
+	cand_state c; const u32* rank; const u32* occ; u32* key; int which;
+	ARB_HD void operator()(u32 i) const { const u32 o = occ[i], k = o >> 1; key[i] = which == 0 ? rank[k] : which == 1 ? (u32) c.bp2[k] : which == 2 ? (u32) c.bp1[k] : occ_gene(c, o); }
+};
+struct partner_head_fn { // first occurrence of its (gene, breakpoint1, breakpoint2) group
+	cand_state c; const u32* occ; u32* head;
+	ARB_HD void operator()(u32 i) const {
+		if (i == 0) { head[i] = 1; return; }
+		const u32 a = occ[i - 1], b = occ[i];
+		head[i] = (occ_gene(c, a) != occ_gene(c, b) || c.bp1[a >> 1] != c.bp1[b >> 1] || c.bp2[a >> 1] != c.bp2[b >> 1]) ? 1u : 0u;
+	}
+};
+struct partner_pair_fn { cand_state c; const u32* occ; const u32* head_scan; u32* gene; u32* partner; ARB_HD void operator()(u32 i) const { if (head_scan[i + 1] != head_scan[i]) { gene[head_scan[i]] = occ_gene(c, occ[i]); partner[head_scan[i]] = occ_partner(c, occ[i]); } } };
+struct partner_unique_fn { const u32* gene; const u32* partner; u32* flag; u32* n_partners; ARB_HD void operator()(u32 i) const { const u32 u = (i == 0 || gene[i] != gene[i - 1] || partner[i] != partner[i - 1]) ? 1u : 0u; flag[i] = u; if (u) atomic_add_u32(&n_partners[gene[i]], 1); } };
+struct partner_count_fn { const u32* gene; const u32* partner; const u32* flag; const u32* n_partners; u32* count; ARB_HD void operator()(u32 i) const { if (flag[i] && n_partners[gene[i]] >= n_partners[partner[i]]) atomic_add_u32(&count[gene[i]], 1); } };
+
 } // namespace arb

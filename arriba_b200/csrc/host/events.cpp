@@ -186,19 +186,40 @@ void pipeline::merge_adjacent() {
 		for (u32 k = 0; k < n_log; ++k) { es[k].winner = triples[3 * k]; es[k].loser = triples[3 * k + 1]; es[k].pos = triples[3 * k + 2]; es[k].seq = k; }
 		// a winner's entries were logged by one thread in order; winners are replayed by sorted position
 		std::stable_sort(es.begin(), es.end(), [](const entry& a, const entry& b) { return a.pos != b.pos ? a.pos < b.pos : a.seq < b.seq; });
-		std::vector<std::vector<u32> > l1(ev.n), l2(ev.n); std::vector<u8> touched(ev.n, 0);
-		auto materialise = [&](u32 k) { if (!touched[k]) { touched[k] = 1; l1[k].assign(ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); l2[k].assign(ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]); } };
+		// only the handful of candidates that take part get a list of their own; the table is then rewritten in long runs of untouched candidates
+		std::map<u32, std::pair<std::vector<u32>, std::vector<u32> > > own;
+		auto materialise = [&](u32 k) -> std::pair<std::vector<u32>, std::vector<u32> >& {
+			std::map<u32, std::pair<std::vector<u32>, std::vector<u32> > >::iterator it = own.find(k);
+			if (it != own.end()) return it->second;
+			std::pair<std::vector<u32>, std::vector<u32> >& l = own[k];
+			l.first.assign(ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); l.second.assign(ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]);
+			return l;
+		};
 		for (size_t k = 0; k < es.size(); ++k) {
-			materialise(es[k].winner); materialise(es[k].loser);
-			l1[es[k].winner].insert(l1[es[k].winner].end(), l1[es[k].loser].begin(), l1[es[k].loser].end());
-			l2[es[k].winner].insert(l2[es[k].winner].end(), l2[es[k].loser].begin(), l2[es[k].loser].end());
+			std::pair<std::vector<u32>, std::vector<u32> >& w = materialise(es[k].winner); const std::pair<std::vector<u32>, std::vector<u32> > l = materialise(es[k].loser); // a copy: winner and loser are different candidates, but the map may re-balance
+			w.first.insert(w.first.end(), l.first.begin(), l.first.end());
+			w.second.insert(w.second.end(), l.second.begin(), l.second.end());
 		}
-		column<u32> o1((size_t) ev.n + 1, 0), o2((size_t) ev.n + 1, 0), n1, n2;
-		for (u32 k = 0; k < ev.n; ++k) {
-			if (touched[k]) { n1.insert(n1.end(), l1[k].begin(), l1[k].end()); n2.insert(n2.end(), l2[k].begin(), l2[k].end()); }
-			else { n1.insert(n1.end(), ev.list1.begin() + ev.list1_off[k], ev.list1.begin() + ev.list1_off[k + 1]); n2.insert(n2.end(), ev.list2.begin() + ev.list2_off[k], ev.list2.begin() + ev.list2_off[k + 1]); }
+		size_t grow1 = 0, grow2 = 0;
+		for (std::map<u32, std::pair<std::vector<u32>, std::vector<u32> > >::iterator it = own.begin(); it != own.end(); ++it) { grow1 += it->second.first.size(); grow2 += it->second.second.size(); }
+		column<u32> o1((size_t) ev.n + 1), o2((size_t) ev.n + 1), n1, n2;
+		n1.reserve(ev.list1.size() + grow1); n2.reserve(ev.list2.size() + grow2);
+		o1[0] = o2[0] = 0;
+		u32 from = 0;
+		auto copy_run = [&](u32 to) { // candidates [from, to) keep their lists
+			if (to <= from) return;
+			const u32 d1 = (u32) n1.size() - ev.list1_off[from], d2 = (u32) n2.size() - ev.list2_off[from];
+			n1.insert(n1.end(), ev.list1.begin() + ev.list1_off[from], ev.list1.begin() + ev.list1_off[to]); n2.insert(n2.end(), ev.list2.begin() + ev.list2_off[from], ev.list2.begin() + ev.list2_off[to]);
+			for (u32 k = from; k < to; ++k) { o1[k + 1] = ev.list1_off[k + 1] + d1; o2[k + 1] = ev.list2_off[k + 1] + d2; }
+		};
+		for (std::map<u32, std::pair<std::vector<u32>, std::vector<u32> > >::iterator it = own.begin(); it != own.end(); ++it) {
+			const u32 k = it->first;
+			copy_run(k);
+			n1.insert(n1.end(), it->second.first.begin(), it->second.first.end()); n2.insert(n2.end(), it->second.second.begin(), it->second.second.end());
 			o1[k + 1] = (u32) n1.size(); o2[k + 1] = (u32) n2.size();
+			from = k + 1;
 		}
+		copy_run(ev.n);
 		ev.list1.swap(n1); ev.list2.swap(n2); ev.list1_off.swap(o1); ev.list2_off.swap(o2);
 		check(ctx, arb_set_candidate_lists(ctx, ev.list1_off.data(), ev.list1.data(), ev.list2_off.data(), ev.list2.data()), "arb_set_candidate_lists");
 	}
@@ -221,41 +242,12 @@ void pipeline::estimate_evalues() {
 	stage_laps laps("evalue");
 	order_ready(); // first stage that visits candidates in the reference's order
 	laps.lap("iteration order joined");
-	// global statistics (filter_relative_support.cpp:19-127). Fusion partners of every gene: of the candidates that share (gene, breakpoint1, breakpoint2)
-	// -- the same breakpoints annotated with overlapping partner genes -- only the one the reference visits FIRST contributes its partner
-	// (`overlap_duplicates`, :22-30). First = smallest rank in the replayed iteration order; found by sorting instead of a hash map per candidate.
-	std::vector<u64> pairs;
-	{
-		struct occurrence { u32 gene; i32 bp1, bp2; u32 rank; u32 partner; };
-		auto before = [](const occurrence& x, const occurrence& y) { return x.gene != y.gene ? x.gene < y.gene : x.bp1 != y.bp1 ? x.bp1 < y.bp1 : x.bp2 != y.bp2 ? x.bp2 < y.bp2 : x.rank < y.rank; };
-		std::vector<occurrence, default_init_allocator<occurrence> > all;
-		{ // few candidates are still unfiltered here: the table is read front to back (the rank of a candidate in the iteration order is looked up, not followed)
-			const int T = std::max(1, std::min(threads, (int) (e.n / 65536 + 1)));
-			std::vector<std::vector<occurrence> > part(T);
-			std::vector<std::thread> pool;
-			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
-				std::vector<occurrence>& v = part[t];
-				for (u32 k = (u32) ((u64) e.n * t / T); k < (u32) ((u64) e.n * (t + 1) / T); ++k) {
-					if (e.filter[k] != F_none || e.gene1[k] == e.gene2[k]) continue;
-					const u32 q = e.rank_of[k];
-					const occurrence a = {e.gene2[k], e.bp1[k], e.bp2[k], q, e.gene1[k]}, b = {e.gene1[k], e.bp1[k], e.bp2[k], q, e.gene2[k]};
-					v.push_back(a); v.push_back(b);
-				}
-			});
-			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-			for (int t = 0; t < T; ++t) all.insert(all.end(), part[t].begin(), part[t].end());
-		}
-		parallel_sort(all, before, threads);
-		for (size_t x = 0; x < all.size(); ++x)
-			if (x == 0 || all[x].gene != all[x - 1].gene || all[x].bp1 != all[x - 1].bp1 || all[x].bp2 != all[x - 1].bp2) pairs.push_back((u64) all[x].gene << 32 | all[x].partner);
-		parallel_sort(pairs, [](u64 a, u64 b) { return a < b; }, threads); pairs.erase(std::unique(pairs.begin(), pairs.end()), pairs.end());
-	}
-	laps.lap("partner pairs");
-	std::vector<u32> n_partners(ref.genes.size(), 0);
-	for (size_t x = 0; x < pairs.size(); ++x) ++n_partners[pairs[x] >> 32];
-	// a gene's count = its partners that have no more partners than the gene itself
+	// global statistics (filter_relative_support.cpp:19-127). Fusion partners of every gene (:19-60): counted on the device over the resident candidate
+	// state and the iteration order it already holds (csrc/events_hd.h, "fusion partners per gene")
+	push_candidate_state();
 	std::vector<i32> partner_count(ref.genes.size(), 0);
-	for (size_t x = 0; x < pairs.size(); ++x) { const u32 g = (u32) (pairs[x] >> 32), partner = (u32) pairs[x]; if (n_partners[g] >= n_partners[partner]) ++partner_count[g]; }
+	check(ctx, arb_partner_counts(ctx, partner_count.data()), "arb_partner_counts");
+	laps.lap("partner counts (device)");
 	arb_evalue_inputs in; memset(&in, 0, sizeof(in));
 	u32 spliced = 0, exonic = 0, intronic = 0, mixed = 0, dups = 0, invs = 0, same = 0, diff = 0;
 	std::vector<u8> with_fusion(ref.genes.size(), 0), with_read_through(ref.genes.size(), 0);
@@ -566,15 +558,28 @@ void pipeline::filter_marginal_read_through() { // filter_marginal_read_through.
 void pipeline::recover_many_spliced() { // recover_many_spliced.cpp
 	const unsigned int min_spliced_events = opt.min_spliced_events; // -M
 	auto eligible_filter = [](u8 f) { return f == F_inconsistently_clipped || f == F_relative_support || f == F_min_support || f == F_select_best; };
-	std::map<std::pair<u32, u32>, std::set<std::pair<i32, i32> > > spliced;
+	// distinct (breakpoint1 / 10, breakpoint2 / 10) pairs per gene pair: sorted tuples instead of the reference's map of sets (only the set sizes are used)
+	struct event { u32 gene1, gene2; i32 b1, b2; };
+	std::vector<event> events;
 	for (u32 k = 0; k < ev.n; ++k)
-		if (!ev.is_read_through(k) && (ev.spliced1(k) || ev.spliced2(k)) && ev.gene1[k] != ev.gene2[k] && !overlaps_both(ev, ref, k) && (ev.filter[k] == F_none || eligible_filter(ev.filter[k])))
-			spliced[std::make_pair(ev.gene1[k], ev.gene2[k])].insert(std::make_pair(ev.bp1[k] / 10, ev.bp2[k] / 10));
-	for (u32 k = 0; k < ev.n; ++k) {
-		if (ev.filter[k] == F_none) continue;
-		if (ev.is_read_through(k) || ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) continue;
-		if (eligible_filter(ev.filter[k]) && (ev.spliced1(k) || ev.spliced2(k)) && spliced[std::make_pair(ev.gene1[k], ev.gene2[k])].size() >= min_spliced_events) ev.filter[k] = F_none;
+		if ((ev.spliced1(k) || ev.spliced2(k)) && ev.gene1[k] != ev.gene2[k] && (ev.filter[k] == F_none || eligible_filter(ev.filter[k])) && !ev.is_read_through(k) && !overlaps_both(ev, ref, k)) {
+			const event x = {ev.gene1[k], ev.gene2[k], ev.bp1[k] / 10, ev.bp2[k] / 10}; events.push_back(x);
+		}
+	auto before = [](const event& a, const event& b) { return a.gene1 != b.gene1 ? a.gene1 < b.gene1 : a.gene2 != b.gene2 ? a.gene2 < b.gene2 : a.b1 != b.b1 ? a.b1 < b.b1 : a.b2 < b.b2; };
+	parallel_sort(events, before, threads);
+	std::vector<std::pair<u64, u32> > pair_events; // (gene1 << 32 | gene2, distinct events), ascending
+	for (size_t x = 0; x < events.size(); ++x) {
+		if (x > 0 && !before(events[x - 1], events[x])) continue; // the same event again
+		const u64 key = (u64) events[x].gene1 << 32 | events[x].gene2;
+		if (pair_events.empty() || pair_events.back().first != key) pair_events.push_back(std::make_pair(key, 0u));
+		++pair_events.back().second;
 	}
+	auto events_of = [&](u32 g1, u32 g2) { const u64 key = (u64) g1 << 32 | g2; std::vector<std::pair<u64, u32> >::const_iterator it = std::lower_bound(pair_events.begin(), pair_events.end(), std::make_pair(key, 0u)); return it != pair_events.end() && it->first == key ? it->second : 0u; };
+	parallel_rows(threads, ev.n, [&](u32 k) {
+		if (ev.filter[k] == F_none || !eligible_filter(ev.filter[k]) || !(ev.spliced1(k) || ev.spliced2(k))) return;
+		if (ev.is_read_through(k) || ev.gene1[k] == ev.gene2[k] || overlaps_both(ev, ref, k)) return;
+		if (events_of(ev.gene1[k], ev.gene2[k]) >= min_spliced_events) ev.filter[k] = F_none;
+	});
 	log_remaining("Searching for fusions with >=4 spliced events");
 }
 
@@ -708,15 +713,18 @@ void pipeline::make_kmer_index() { // windows of make_kmer_index (filter_mismapp
 }
 
 void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() itself is evaluated on the device in two batches
+	stage_laps laps("homologs");
 	// remaining candidates in the reference's list order: push_front over the iteration order = reverse iteration order
 	std::vector<u32> rem;
-	for (size_t q = ev.order.size(); q-- > 0;) if (ev.filter[ev.order[q]] == F_none) rem.push_back(ev.order[q]);
+	for (u32 k = 0; k < ev.n; ++k) if (ev.filter[k] == F_none) rem.push_back(k);
+	std::sort(rem.begin(), rem.end(), [&](u32 a, u32 b) { return ev.rank_of[a] > ev.rank_of[b]; });
 	// batch 1: the two genes of every remaining candidate
 	std::vector<u32> ga, gb; std::vector<u8> res;
 	for (size_t x = 0; x < rem.size(); ++x) { ga.push_back(ev.gene1[rem[x]]); gb.push_back(ev.gene2[rem[x]]); }
 	res.resize(ga.size() + 1);
 	if (!ga.empty()) check(ctx, arb_homolog_pairs(ctx, ga.data(), gb.data(), (uint32_t) ga.size(), res.data()), "arb_homolog_pairs");
 	std::vector<u8> self_homolog(res.begin(), res.begin() + ga.size());
+	laps.lap("own gene pairs (device)");
 	// batch 2: partner genes of candidates that share a gene (a superset of what the sequential pass will ask for)
 	auto partner_genes = [&](u32 f, u32 o, u32& h1, u32& h2) { // which genes would be compared for the pair (f, o)?  (filter_homologs.cpp:97-113)
 		if (ev.gene1[f] == ev.gene1[o] && ev.bp2[f] != ev.bp2[o]) { h1 = ev.gene2[f]; h2 = ev.gene2[o]; return true; }
@@ -727,7 +735,8 @@ void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() i
 	};
 	std::vector<std::vector<u32> > by_gene(ref.genes.size()); // positions in rem, ascending
 	for (size_t x = 0; x < rem.size(); ++x) { by_gene[ev.gene1[rem[x]]].push_back((u32) x); if (ev.gene2[rem[x]] != ev.gene1[rem[x]]) by_gene[ev.gene2[rem[x]]].push_back((u32) x); }
-	std::map<std::pair<u32, u32>, u32> pair_index; ga.clear(); gb.clear();
+	// the distinct gene pairs: collected as 64-bit keys, sorted, made unique (a tree map took most of this stage's time)
+	std::vector<u64> pair_keys; ga.clear(); gb.clear();
 	for (size_t x = 0; x < rem.size(); ++x) {
 		if (self_homolog[x]) continue;
 		const u32 f = rem[x];
@@ -737,13 +746,19 @@ void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() i
 				if (v[y] <= x) continue;
 				u32 h1, h2;
 				if (!partner_genes(f, rem[v[y]], h1, h2)) continue;
-				if (pair_index.insert(std::make_pair(std::make_pair(h1, h2), (u32) ga.size())).second) { ga.push_back(h1); gb.push_back(h2); }
+				pair_keys.push_back((u64) h1 << 32 | h2);
 			}
 			if (ev.gene1[f] == ev.gene2[f]) break;
 		}
 	}
+	parallel_sort(pair_keys, [](u64 a, u64 b) { return a < b; }, threads);
+	pair_keys.erase(std::unique(pair_keys.begin(), pair_keys.end()), pair_keys.end());
+	for (size_t k = 0; k < pair_keys.size(); ++k) { ga.push_back((u32) (pair_keys[k] >> 32)); gb.push_back((u32) pair_keys[k]); }
+	auto pair_index_of = [&](u32 h1, u32 h2) { return (size_t) (std::lower_bound(pair_keys.begin(), pair_keys.end(), (u64) h1 << 32 | h2) - pair_keys.begin()); };
+	laps.lap("gene pairs of candidates that share a gene");
 	res.assign(ga.size() + 1, 0);
 	if (!ga.empty()) check(ctx, arb_homolog_pairs(ctx, ga.data(), gb.data(), (uint32_t) ga.size(), res.data()), "arb_homolog_pairs");
+	laps.lap("identity of the pairs (device)");
 	// sequential resolution, exactly in list order
 	for (size_t x = 0; x < rem.size(); ++x) {
 		const u32 f = rem[x];
@@ -759,7 +774,7 @@ void pipeline::filter_homologs() { // filter_homologs.cpp:65-141; is_homolog() i
 			u32 h1, h2;
 			if (!partner_genes(f, o, h1, h2)) continue;
 			const unsigned int a1 = (ev.split_reads1[f] > 0) + (ev.split_reads2[f] > 0) + (ev.discordant_mates[f] > 0), a2 = (ev.split_reads1[o] > 0) + (ev.split_reads2[o] > 0) + (ev.discordant_mates[o] > 0);
-			if (!res[pair_index.at(std::make_pair(h1, h2))]) continue;
+			if (!res[pair_index_of(h1, h2)]) continue;
 			if (a1 > a2 || (a1 == a2 && ev.supporting_reads(f) > ev.supporting_reads(o)) || (a1 == a2 && ev.supporting_reads(f) == ev.supporting_reads(o) && ev.evalue[f] <= ev.evalue[o])) ev.filter[o] = F_homologs;
 			else { ev.filter[f] = F_homologs; break; }
 		}

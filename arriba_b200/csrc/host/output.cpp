@@ -741,8 +741,44 @@ struct writer {
 	}
 
 	// A file is produced in two steps, so that the (lock-bound) copy of one file into the page cache can run beside the (CPU-bound) formatting of the other
-	struct formatted { std::string header; std::vector<std::string> slices, warnings; };
+	struct formatted { std::string header; std::vector<std::string> slices, warnings; column<char> blob; /* rows formatted on the device: one block instead of slices */ };
+	static std::string header_line() { return "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n"; }
+	// the discarded file without -X: every column follows from resident device state; the rows are formatted there (csrc/rows_hd.h) and come back as one block
+	void format_discarded_rows_on_device(formatted& out) const {
+		output_laps laps;
+		sort_filters_by_name();
+		pipeline& pl = p;
+		if (!pl.row_texts_on_device) {
+			std::vector<char> gn, gi, cn, fn; std::vector<u32> gno(1, 0), gio(1, 0), cno(1, 0), fno(1, 0);
+			for (size_t g = 0; g < ref.genes.size(); ++g) { gn.insert(gn.end(), ref.genes[g].name.begin(), ref.genes[g].name.end()); gno.push_back((u32) gn.size()); gi.insert(gi.end(), ref.genes[g].gene_id.begin(), ref.genes[g].gene_id.end()); gio.push_back((u32) gi.size()); }
+			for (size_t c = 0; c < ref.contig_ids.size(); ++c) { const std::string& nm = ref.original_names[c]; cn.insert(cn.end(), nm.begin(), nm.end()); cno.push_back((u32) cn.size()); }
+			for (int f = 0; f < 38; ++f) { fn.insert(fn.end(), FILTER_NAMES[f], FILTER_NAMES[f] + strlen(FILTER_NAMES[f])); fno.push_back((u32) fn.size()); }
+			std::vector<i32> prev(ref.exons.size()), next(ref.exons.size());
+			for (size_t x = 0; x < ref.exons.size(); ++x) { prev[x] = ref.exons[x].prev >= 0 ? ref.exons[x].prev : -1; next[x] = ref.exons[x].next >= 0 ? ref.exons[x].next : -1; }
+			gn.push_back(0); gi.push_back(0); cn.push_back(0); fn.push_back(0);
+			arb_row_texts t; memset(&t, 0, sizeof(t));
+			t.n_genes = (u32) ref.genes.size(); t.n_exons = (u32) ref.exons.size(); t.n_contigs = (u32) ref.contig_ids.size();
+			t.gene_name = gn.data(); t.gene_name_off = gno.data(); t.gene_id = gi.data(); t.gene_id_off = gio.data(); t.contig_name = cn.data(); t.contig_name_off = cno.data(); t.filter_name = fn.data(); t.filter_name_off = fno.data();
+			t.exon_prev = prev.data(); t.exon_next = next.data();
+			for (int x = 0; x < 38; ++x) t.filters_by_name[x] = (u8) filters_by_name[x];
+			t.max_itd_length = p.opt.params.max_itd_length;
+			if (arb_set_row_texts(pl.ctx, &t) != 0) throw std::runtime_error(std::string("arb_set_row_texts: ") + arb_last_error(pl.ctx));
+			pl.row_texts_on_device = true;
+		}
+		pl.ensure_coverage_on_device();
+		if (arb_set_fragment_filters(pl.ctx, pl.labels.data()) != 0) throw std::runtime_error(std::string("arb_set_fragment_filters: ") + arb_last_error(pl.ctx));
+		pl.push_candidate_state();
+		uint64_t n_rows = 0, n_bytes = 0;
+		if (arb_format_discarded_rows(pl.ctx, e.confidence.data(), &n_rows, &n_bytes) != 0) throw std::runtime_error(std::string("arb_format_discarded_rows: ") + arb_last_error(pl.ctx));
+		out.blob.resize(n_bytes ? n_bytes : 1);
+		if (n_bytes && arb_get_row_text(pl.ctx, out.blob.data()) != 0) throw std::runtime_error(std::string("arb_get_row_text: ") + arb_last_error(pl.ctx));
+		out.blob.resize(n_bytes);
+		out.header = header_line();
+		out.slices.clear(); out.warnings.clear();
+		laps.lap("discarded", "rows formatted (device)");
+	}
 	void format_rows(bool discarded, bool extra_info, formatted& out) const {
+		if (discarded && !extra_info && (getenv("ARB_DEVICE_ROWS") == NULL || atoi(getenv("ARB_DEVICE_ROWS")) != 0)) { format_discarded_rows_on_device(out); return; }
 		sort_filters_by_name();
 		output_laps laps; const char* const which = discarded ? "discarded" : "fusions";
 		std::vector<u32> rows;
@@ -758,7 +794,7 @@ struct writer {
 				return bx != by ? by_support(bx, by) : by_support(x, y);
 			});
 		}
-		const std::string header = "#gene1\tgene2\tstrand1(gene/fusion)\tstrand2(gene/fusion)\tbreakpoint1\tbreakpoint2\tsite1\tsite2\ttype\tsplit_reads1\tsplit_reads2\tdiscordant_mates\tcoverage1\tcoverage2\tconfidence\treading_frame\ttags\tretained_protein_domains\tclosest_genomic_breakpoint1\tclosest_genomic_breakpoint2\tgene_id1\tgene_id2\ttranscript_id1\ttranscript_id2\tdirection1\tdirection2\tfilters\tfusion_transcript\tpeptide_sequence\tread_identifiers\n";
+		const std::string header = header_line();
 		// Rows are independent and cost very different amounts (the best-supported fusions come first and carry hundreds of reads each): threads draw small
 		// chunks of rows from a shared counter; every chunk is formatted into its own string and later copied to its offset of the file (flush_rows).
 		const size_t CHUNK = 32;
@@ -805,7 +841,8 @@ struct writer {
 		const int T = std::max(1, std::min(p.threads, (int) (n_chunks ? n_chunks : 1)));
 		std::vector<u64> at(n_chunks + 1); at[0] = header.size(); for (size_t c = 0; c < n_chunks; ++c) at[c + 1] = at[c] + slices[c].size();
 		bool ok = true;
-		const u64 total = at[n_chunks];
+		const u64 blob_bytes = text.blob.size(); const char* const blob = text.blob.data(); // rows formatted on the device (then there are no slices)
+		const u64 total = at[n_chunks] + blob_bytes;
 		// a regular file is sized once and filled through a shared mapping by all threads (buffered write() calls to ONE file serialise on its inode lock);
 		// anything else (a pipe, /dev/stdout) gets one sequential writer
 		void* map = MAP_FAILED;
@@ -815,13 +852,16 @@ struct writer {
 			char* const out = (char*) map;
 			memcpy(out, header.data(), header.size());
 			std::vector<std::thread> pool;
+			const int TB = std::max(1, p.threads);
 			for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (size_t c = n_chunks * t / T; c < n_chunks * (t + 1) / T; ++c) memcpy(out + at[c], slices[c].data(), slices[c].size()); });
+			if (blob_bytes) for (int t = 0; t < TB; ++t) pool.emplace_back([&, t]() { const u64 lo = blob_bytes * t / TB, hi = blob_bytes * (t + 1) / TB; memcpy(out + at[n_chunks] + lo, blob + lo, hi - lo); });
 			for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
 			ok = ::munmap(map, total) == 0;
 		} else {
 			auto write_all = [&](const char* data, size_t n) { while (n > 0) { const ssize_t w = ::write(fd, data, n); if (w <= 0) return false; data += w; n -= (size_t) w; } return true; };
 			ok = write_all(header.data(), header.size());
 			for (size_t c = 0; c < n_chunks && ok; ++c) ok = write_all(slices[c].data(), slices[c].size());
+			if (ok && blob_bytes) ok = write_all(blob, blob_bytes);
 		}
 		ok = ::close(fd) == 0 && ok;
 		laps.lap(which, "file written");

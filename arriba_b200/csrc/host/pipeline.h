@@ -51,7 +51,7 @@ struct pipeline {
 	double t_events[32], t_output;
 	double t_reference, t_ingest, t_annotate, t_upload, t_read_filters, t_fragment_length, t_find_fusions;
 	pipeline(): ctx(NULL), strandedness(0), max_mate_gap(0), read_length_mean(0), mate_gap_mean(0), mate_gap_stddev(0), fragment_length_ok(false), splice_sites_ready(false), events_done(-1),
-	            upload_begun(false), t_mismappers_begin(0), frags_on_device(false), reference_on_device(false), coverage_on_device(false), contigs_on_device(0) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
+	            upload_begun(false), t_mismappers_begin(0), frags_on_device(false), reference_on_device(false), coverage_on_device(false), row_texts_on_device(false), contigs_on_device(0) { for (int q = 0; q < 32; ++q) t_events[q] = 0; t_output = 0; t_reference = t_ingest = t_annotate = t_upload = t_read_filters = t_fragment_length = t_find_fusions = 0; }
 	~pipeline();
 	void load_reference();
 	void ingest();
@@ -78,7 +78,7 @@ struct pipeline {
 	std::vector<u32> partition_keys; std::vector<u8> partition_owner; void work_partition(int parts);
 	bool mismappers_begin(); void mismappers_end(); double t_mismappers_begin;
 	void ensure_coverage_on_device(); void attach_device(); // a part that only works on replicated device state: a context with the run's parameters
-	bool frags_on_device, reference_on_device, coverage_on_device; u32 contigs_on_device;
+	bool frags_on_device, reference_on_device, coverage_on_device, row_texts_on_device; u32 contigs_on_device;
 	void say_read_filter_counts();
 };
 

@@ -20,7 +20,12 @@ template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_
 	const u32 i = it.item_frag[j];
 	if (((const volatile u8*) it.mismapper)[i]) return; // another candidate's evaluation of this fragment already decided (the label is an OR)
 	realign_worklist wl = {tasks[group], &tops[group], MISMAP_WORKLIST};
-	const u32 verdict = evaluate_group(g, it, j, wl, budget);
+	realign_tally tally = {0, 0, 0};
+	const u32 verdict = evaluate_group(g, it, j, wl, budget, tally);
+	if (it.tallies) { // sequences and bases are the same on every lane, the hits are per lane
+		const u32 hits = g.sum(tally.hits);
+		if (g.lane == 0) { unsigned long long* t = it.tallies + 3 * (j % mismap_items::TALLY_SLOTS); atomicAdd(t, (unsigned long long) tally.sequences); atomicAdd(t + 1, (unsigned long long) tally.bases); atomicAdd(t + 2, (unsigned long long) hits); }
+	}
 	if (g.lane == 0) {
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomicAdd(n_heavy, 1u)] = j;
@@ -185,7 +190,8 @@ void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void*
 	kmer_index_view ix = index_view();
 	gene_splice_view sp = {splice_off.ptr(), splice_sites.ptr()};
 	mismap_params mp = {max_mate_gap, params.max_mismapper_fraction};
-	mismap_items items = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr()};
+	dbuf<unsigned long long> tallies(3 * (size_t) mismap_items::TALLY_SLOTS); tallies.zero(ex, 3 * (size_t) mismap_items::TALLY_SLOTS);
+	mismap_items items = {frags.view(), annot.view(), ix, sp, mp, item_cand.ptr(), item_frag.ptr(), item_kind.ptr(), cands.contig1.ptr(), cands.contig2.ptr(), cands.filter.ptr(), mism.ptr(), tallies.ptr()};
 	// pass 1: a thread per item, bounded; pass 2: the few items stuck in repeats, `lanes` threads each (mismap_hd.h, realign_ctl)
 	dbuf<u32> heavy(I), n_heavy(1);
 	n_heavy.zero(ex, 1);
@@ -207,6 +213,15 @@ void engine::filter_mismappers_part(i32 max_mate_gap, int part, int parts, void*
 		launch(I, mi);
 	}
 	timings.mismappers_pass1_ms = t1.stop();
+	{ // per re-aligned sequence of length l: 3l/8 (read) + 8(l - 8) (bucket offsets) + 4 * hits + l/2 (extension windows)
+		std::vector<unsigned long long> t(3 * (size_t) mismap_items::TALLY_SLOTS);
+		tallies.download(ex, t.data(), t.size());
+		u64 sequences = 0, bases = 0, hits = 0;
+		for (size_t k = 0; k < t.size(); k += 3) { sequences += t[k]; bases += t[k + 1]; hits += t[k + 2]; }
+		timings.mismapper_sequences = sequences; timings.mismapper_hits = hits;
+		timings.mismapper_algorithmic_bytes = bases * 3 / 8 + 8 * (bases - 8 * sequences) + 4 * hits + bases / 2;
+		items.tallies = NULL; // the cooperative passes are not part of the budget
+	}
 	u32 H = 0; n_heavy.download(ex, &H, 1);
 	stage_timer t2(ex);
 	// pass 2 and the task rounds: continuations are registered per item (mismap_hd.h, realign_ctl::table) and run as tasks, one per distinct continuation

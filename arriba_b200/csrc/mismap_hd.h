@@ -340,10 +340,14 @@ ARB_HD bool extends_linearly(const frag_view& f, const annot_view& an, u32 a /* 
 struct mismap_params { i32 max_mate_gap; float max_mismapper_fraction; };
 
 // one work item = one (candidate, listed fragment) pair
+// what pass 1 looked at, for the SURVEY.md section 8(d) byte budget of the re-alignment: sequences searched (segment x gene x strand), their bases, k-mer hits visited
+struct realign_tally { u32 sequences, bases, hits; };
 struct mismap_items {
 	frag_view f; annot_view an; kmer_index_view ix; gene_splice_view sp; mismap_params p;
 	const u32* item_cand; const u32* item_frag; const u8* item_kind /* 0 split read, 1 discordant */; const u16* cand_contig1; const u16* cand_contig2; const u8* cand_filter;
 	u8* mismapper; // per fragment, set to 1 when any evaluation says "mis-mapped"
+	unsigned long long* tallies; // 0, or 3 * TALLY_SLOTS counters (sequences, bases, hits), spread over slots to keep the atomics apart
+	enum { TALLY_SLOTS = 1024 };
 	ARB_HD bool skip(u32 j) const { return cand_filter[item_cand[j]] != F_none || f.filter[item_frag[j]] != F_none; }
 	// segment 0 / 1 of item j: split read -> clipped part vs. the genes of the split read's anchor side, then mate1 (+ aligned part) vs. the genes of the
 	// supplementary; discordant mates -> each mate vs. the genes of the other (filter_mismappers.cpp:296-333)
@@ -494,7 +498,7 @@ ARB_HD bool realign_extend(const realign_env& env, const realign_work& task, con
 	}
 	return false;
 }
-ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, u32& steps) {
+ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const realign_work& task, const realign_worklist& wl, u32& steps, u32& hits) {
 	const int len = (int) env.len;
 	const i32* const pos = env.pos; const u32* const bucket = env.bucket;
 	const i32 wend = env.wend; const int min_score = env.min_score;
@@ -507,6 +511,7 @@ ARB_HD u32 realign_group(const lane_group& g, const realign_env& env, const real
 		for (u32 h = env_first_hit(env, km, lo, hi, gene_pos); h < hi; ++h) {
 			const int hit = pos[h];
 			if (hit >= wend) break;
+			++hits;
 			if (realign_extend(env, task, wl, read_pos, hit, steps)) return REALIGN_FOUND;
 		}
 	}
@@ -537,7 +542,7 @@ ARB_HD bool extends_linearly_group(const lane_group& g, const frag_view& f, cons
 }
 
 // one item by a group: 0 = not mis-mapped, 1 = mis-mapped, 2 = gave up (worklist or budget), re-aligned cooperatively in pass 2
-ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, int budget) {
+ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, const realign_worklist& wl, int budget, realign_tally& tally) {
 	if (g.lane == 0) *wl.top = 0;
 	g.sync();
 	if (it.item_kind[j] == 0 && extends_linearly_group(g, it.f, it.an, it.f.idx(it.item_frag[j], SPLIT_READ))) return REALIGN_FOUND;
@@ -551,6 +556,7 @@ ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, co
 			if (!segment_env(s, k, it.p.max_mate_gap, it.an, it.ix, it.sp, env)) continue;
 			if (!realign_can_start(0, 0, (int) env.len, env.min_score)) continue;
 			if (n + 2 > wl.capacity || k >= 0xFFFFu) { too_many = true; break; }
+			tally.sequences += 2; tally.bases += 2 * env.len;
 			if (g.lane == 0) {
 				realign_work t; t.gene_pos = env.wstart; t.score = 0; t.read_pos = 0; t.gene_k = (u16) k; t.segment = (u8) x; t.rc_deletions = 1;
 				wl.tasks[n] = t; t.rc_deletions = 0x81; wl.tasks[n + 1] = t;
@@ -575,7 +581,7 @@ ARB_HD u32 evaluate_group(const lane_group& g, const mismap_items& it, u32 j, co
 		segment_env(s, task.gene_k, it.p.max_mate_gap, it.an, it.ix, it.sp, env); // it was usable when the task was made
 		if (task.rc_deletions & 0x80u) env.rc = !s.read.rc;
 		u32 steps = 0;
-		const u32 verdict = realign_group(g, env, task, wl, steps);
+		const u32 verdict = realign_group(g, env, task, wl, steps, tally.hits);
 		if (g.any(verdict == REALIGN_FOUND)) return REALIGN_FOUND;
 		total_steps += g.sum(steps);
 		if (budget > 0 && total_steps > (u32) budget) return REALIGN_EXHAUSTED;
@@ -609,7 +615,9 @@ struct mismap_item_group_fn {
 		realign_work tasks[64]; u32 top = 0;
 		realign_worklist wl = {tasks, &top, 64};
 		lane_group g; g.lane = 0; g.lanes = 1; g.mask = 1;
-		const u32 verdict = evaluate_group(g, it, j, wl, budget);
+		realign_tally tally = {0, 0, 0};
+		const u32 verdict = evaluate_group(g, it, j, wl, budget, tally);
+		if (it.tallies) { unsigned long long* t = it.tallies + 3 * (j % mismap_items::TALLY_SLOTS); t[0] += tally.sequences; t[1] += tally.bases; t[2] += tally.hits; }
 		if (verdict == REALIGN_FOUND) it.mismapper[i] = 1;
 		else if (verdict == REALIGN_EXHAUSTED) heavy[atomic_add_u32(n_heavy, 1)] = j;
 	}

@@ -191,6 +191,10 @@ int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/fi
  * schedule is the caller's (its C++ library's std::__detail::_Prime_rehash_policy): candidates [phase_start[j], phase_start[j+1]) are inserted while the
  * table has phase_buckets[j] buckets; phase_start has n_phases + 1 entries. order_out[q] = id of the candidate visited q-th, rank_out = its inverse. */
 int arb_replay_insertion_order(arb_ctx* ctx, const uint32_t* phase_start, const uint64_t* phase_buckets, uint32_t n_phases, uint32_t* order_out, uint32_t* rank_out);
+/* Replaces the fusion-partner tally of estimate_expected_fusions (source/filter_relative_support.cpp:19-60) on the resident candidate state: of the
+ * candidates that share (gene, breakpoint1, breakpoint2) only the first in the iteration order (arb_replay_insertion_order) contributes its partner;
+ * partner_count_out[g] = distinct partners of g that have no more partners than g -- the `partner_count` input of arb_estimate_evalues. */
+int arb_partner_counts(arb_ctx* ctx, int32_t* partner_count_out /* n_genes */);
 /* Replaces filter_multimappers (source/filter_multimappers.cpp:115): of the fragments that share a read name (fflags bit1 / bit3) only the one with the best
  * alignment score keeps its label, ties go to the fragment whose best candidate has more support; read counts of the candidates follow. Works on the
  * resident candidate state and fragment labels; results through arb_get_candidate_state / arb_get_fragment_filters. */
@@ -206,6 +210,25 @@ int arb_filter_in_vitro(arb_ctx* ctx, const uint32_t* reads_by_gene, uint32_t n_
 /* spliced support of every candidate that may back another one up (source/recover_both_spliced.cpp:15-62, :104-118): support_out[k] = the support,
  * 0xFFFFFFFF where the candidate is not eligible or has none; works on the resident candidate state and fragment labels like arb_filter_in_vitro */
 int arb_spliced_support(arb_ctx* ctx, const uint32_t* reads_by_gene, uint32_t n_genes, uint32_t threshold, uint32_t* support_out /* n candidates */);
+
+/* ---- rows of the discarded-fusions file -------------------------------------------------------------------------------------
+ * Replaces write_fusions_to_file (source/output_fusions.cpp:1043-1261) for the file of discarded fusions (-O) without -X: one row per candidate whose
+ * filter is set, in the iteration order of the candidate map (arb_replay_insertion_order), formatted on the device from the resident candidate state,
+ * fragment labels (filters column), annotation and coverage. The caller supplies what the device does not hold: names, the exons' neighbours in their
+ * transcripts, the alphabetical order of the filter names, the confidence column. The header line stays with the caller. */
+typedef struct arb_row_texts {
+	uint32_t n_genes, n_exons, n_contigs;
+	const char* gene_name; const uint32_t* gene_name_off;       /* string k = chars[off[k], off[k+1]) */
+	const char* gene_id; const uint32_t* gene_id_off;
+	const char* contig_name; const uint32_t* contig_name_off;   /* as named in the input files ("chr1") */
+	const char* filter_name; const uint32_t* filter_name_off;   /* ARB_N_FILTERS names */
+	const int32_t* exon_prev; const int32_t* exon_next;         /* exon ids, -1 = none */
+	uint8_t filters_by_name[ARB_N_FILTERS];                     /* filter ids in alphabetical order of their names */
+	uint32_t max_itd_length;
+} arb_row_texts;
+int arb_set_row_texts(arb_ctx* ctx, const arb_row_texts* texts);
+int arb_format_discarded_rows(arb_ctx* ctx, const uint8_t* confidence /* per candidate: 0 low, 1 medium, 2 high */, uint64_t* n_rows, uint64_t* n_bytes);
+int arb_get_row_text(arb_ctx* ctx, char* out /* n_bytes */);
 
 /* ---- k-mer index of the fused genes, gene homology, re-alignment of supporting reads -----------------------------------
  * arb_build_kmer_index replaces make_kmer_index (source/filter_mismappers.cpp:47): `intervals` are the disjoint, sorted unions of the
@@ -270,6 +293,10 @@ typedef struct arb_timings {
 	float in_vitro_ms;          /* arb_filter_in_vitro */
 	float multimappers_ms;      /* arb_filter_multimappers */
 	float order_ms;             /* arb_replay_insertion_order */
+	float partners_ms;          /* arb_partner_counts */
+	float rows_ms;              /* arb_format_discarded_rows */
+	uint64_t mismapper_algorithmic_bytes; /* SURVEY.md section 8(d) budget of pass 1 of the re-alignment: per searched sequence of length l, 3l/8 + 8(l-8) + 4*hits + l/2 */
+	uint64_t mismapper_sequences, mismapper_hits; /* sequences searched by pass 1 (segment x gene x strand) and k-mer hits they visited */
 } arb_timings;
 int arb_get_timings(arb_ctx* ctx, arb_timings* out);
 /* Device scratch memory is pooled per device and survives arb_ctx_destroy so that the next sample reuses it; this returns it to the driver
