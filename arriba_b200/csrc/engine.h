@@ -134,6 +134,8 @@ public:
 	void filter_relative_support(float cutoff); void filter_multimappers();
 	void replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out); dbuf<u32> order_rank;
 	void partner_counts(i32* count_out); dbuf<u32> order_seq;
+	// BAM record boundaries and per-worker record lists of an inflated chunk (bamscan.cu)
+	void bam_scan(const u8* chunk, u64 bytes, u64 first, i32 n_ref, u32 n_shards, u64* consumed, u32* n_records, u32* shard_begin, u32* record_offsets, u32* malformed); dbuf<u8> bam_buf;
 	// rows of the discarded-fusions file (rows.cu)
 	void set_row_texts(const arb_row_texts& t); void format_discarded_rows(const u8* confidence, u64* n_rows, u64* n_bytes); void get_row_text(char* out);
 	dbuf<char> row_gene_name, row_gene_id, row_contig_name, row_filter_name, row_text; dbuf<u32> row_gene_name_off, row_gene_id_off, row_contig_name_off, row_filter_name_off; dbuf<i32> row_exon_prev, row_exon_next;

@@ -2,6 +2,7 @@
 // (every alignment of a read name is handled by the same worker, so mate collation and "first insertion wins" stay local),
 // and the fragments are finally ordered by name, which is the order every later stage relies on.
 #include "ingest.h"
+#include "../../../include/arriba_b200.h"
 #include <set>
 #include "../annot_hd.h"
 #include <zlib.h>
@@ -726,7 +727,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	bool header_done = false;
 	u64 total_records = 0;
 	// A chunk is inflated, cut into records and sharded ("prepare") while the workers still parse the previous one ("process").
-	struct chunk_t { std::vector<u8> buf; std::vector<u64> rec_off; std::vector<u8> rec_shard; std::vector<u32> shard_items, shard_begin; size_t consumed; bool last; chunk_t(): consumed(0), last(false) {} };
+	struct chunk_t { column<u8> buf /* page-locked: copied to the device for the record scan */; column<u32> shard_rec_off /* record offsets, worker by worker, file order inside a worker's list */; std::vector<u32> shard_begin; size_t n_records, consumed; bool last; chunk_t(): n_records(0), consumed(0), last(false) {} };
 	chunk_t chunks[2];
 	size_t b0 = 0;
 	double t_inflate = 0, t_scan = 0; // written by the preparing thread only
@@ -735,7 +736,8 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		size_t b1 = b0; u64 bytes = 0;
 		while (b1 < bam.blocks.size() && (bytes == 0 || bytes + bam.blocks[b1].out_len <= chunk_target)) bytes += bam.blocks[b1++].out_len;
 		if (b1 == b0 && carry > 0) fail("failed to load alignments"); // truncated file
-		std::vector<u8>& buf = c.buf;
+		column<u8>& buf = c.buf;
+		if (buf.capacity() < carry + bytes) buf.reserve(carry + bytes + (16u << 20)); // one page-locked block per buffer for the whole file (chunks differ a little in size)
 		buf.resize(carry + bytes);
 		if (carry) memcpy(buf.data(), prev->buf.data() + prev->consumed, carry);
 		double ti = now_s();
@@ -780,91 +782,19 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			}
 			header_done = true;
 		}
-		// record boundaries: a sequential hop over the block_size fields; the shard of every record (hash of the read name) is then computed by all threads
+		// record boundaries, read-name hashes and the per-worker record lists: on the device (csrc/bamscan.cu)
 		double tp = now_s();
-		std::vector<u64>& rec_off = c.rec_off; std::vector<u8>& rec_shard = c.rec_shard;
-		rec_off.clear();
 		{
-			// A record can only be found from the one before it. To walk the chain on all threads, every piece of the buffer guesses its first record
-			// (first offset from which a few consecutive records look sane) and hops from there; the guesses are then VERIFIED: the chain of piece s must
-			// arrive exactly at the guess of piece s+1. Where it does not, the walk simply continues serially through the next piece.
-			const u8* const B = buf.data(); const size_t end = buf.size();
-			const i32 n_ref = (i32) tid_to_contig.size();
-			auto plausible = [&](size_t q) { // a BAM record could start at q (SAMv1 4.2); a necessary condition only
-				if (q + 36 > end) return false;
-				const u32 bs = rd32(B + q);
-				if (bs < 33 || bs > (1u << 26) || q + 4 + bs > end) return false;
-				const i32 tid = (i32) rd32(B + q + 4), pos = (i32) rd32(B + q + 8), mtid = (i32) rd32(B + q + 24), mpos = (i32) rd32(B + q + 28);
-				const u32 lq = B[q + 12], nc = rd16(B + q + 16); const i32 ls = (i32) rd32(B + q + 20);
-				if (tid < -1 || tid >= n_ref || mtid < -1 || mtid >= n_ref || pos < -1 || mpos < -1 || lq == 0 || ls < 0) return false;
-				if (32ull + lq + 4ull * nc + ((u64) ls + 1) / 2 + (u64) ls > bs) return false;
-				return B[q + 36 + lq - 1] == 0;
-			};
-			const size_t span = end > p ? end - p : 0;
-			const size_t min_span = getenv("ARB_SCAN_MIN_BYTES") ? (size_t) atol(getenv("ARB_SCAN_MIN_BYTES")) : (size_t) 16 << 20; // test hook
-			const int pieces = span > min_span ? T : 1;
-			std::vector<size_t> guess(pieces + 1, end), stop_at(pieces, 0);
-			std::vector<std::vector<u64> > found(pieces);
-			guess[0] = p;
-			auto hop = [&](size_t q, size_t limit, std::vector<u64>& out) { // records starting before `limit`; returns where the chain stands afterwards
-				while (q < limit && q + 4 <= end) {
-					const u32 bs = rd32(B + q);
-					if (q + 4 + bs > end) break;
-					if (bs < 33) fail("failed to load alignments");
-					out.push_back(q);
-					q += 4 + bs;
-				}
-				return q;
-			};
-			if (pieces > 1) {
-				parallel_for(T, (size_t) pieces, [&](int, size_t lo, size_t hi) {
-					for (size_t s = lo; s < hi; ++s) {
-						if (s > 0) { // guess: first offset of the piece from which three records in a row look sane
-							size_t q = p + span * s / pieces; const size_t give_up = std::min(end, q + (4u << 20));
-							for (; q < give_up; ++q) {
-								if (!plausible(q)) continue;
-								const size_t q2 = q + 4 + rd32(B + q); if (q2 < end && !plausible(q2)) continue;
-								const size_t q3 = q2 < end ? q2 + 4 + rd32(B + q2) : end; if (q3 < end && q3 + 36 <= end && !plausible(q3)) continue;
-								break;
-							}
-							guess[s] = q < give_up ? q : end;
-						}
-					}
-				});
-				parallel_for(T, (size_t) pieces, [&](int, size_t lo, size_t hi) { for (size_t s = lo; s < hi; ++s) if (guess[s] < end) stop_at[s] = hop(guess[s], guess[s + 1], found[s]); else stop_at[s] = end; });
-			}
-			// stitch: follow the true chain; a piece whose guess the chain hits exactly contributes its whole list
-			size_t q = p;
-			for (int s = 0; s < pieces; ++s) {
-				if (pieces > 1 && q == guess[s] && guess[s] < end) { rec_off.insert(rec_off.end(), found[s].begin(), found[s].end()); q = stop_at[s]; }
-				else q = hop(q, pieces > 1 ? guess[s + 1] : end, rec_off); // wrong or missing guess: walk this stretch
-			}
-			q = hop(q, end, rec_off); // whatever lies beyond the last verified piece
-			p = q;
+			if (buf.size() >= 0xFFFFFFF0ull) fail("failed to load alignments (chunk too large)");
+			c.shard_begin.assign((size_t) T + 1, 0);
+			c.shard_rec_off.resize(buf.size() / 36 + 2);
+			uint64_t consumed = 0; uint32_t n_records = 0, malformed = 0;
+			if (arb_bam_scan(opt.scan_ctx, buf.data(), buf.size(), p, (int32_t) tid_to_contig.size(), (uint32_t) T, &consumed, &n_records, c.shard_begin.data(), c.shard_rec_off.data(), &malformed) != 0)
+				fail(std::string("arb_bam_scan: ") + arb_last_error(opt.scan_ctx));
+			if (malformed) fail("failed to load alignments");
+			c.n_records = n_records; p = consumed;
 		}
 		c.consumed = p;
-		rec_shard.resize(rec_off.size());
-		parallel_for(T, rec_off.size(), [&](int, size_t lo, size_t hi) {
-			for (size_t k = lo; k < hi; ++k) {
-				const u8* rec = buf.data() + rec_off[k] + 4;
-				const u8* q = rec + 32; const u32 lq = rec[8];
-				u64 h = 1469598103934665603ULL;
-				for (u32 x = 0; x + 1 < lq && q[x]; ++x) { h ^= q[x]; h *= 1099511628211ULL; }
-				rec_shard[k] = (u8) ((h >> 20) % (u64) T);
-			}
-		});
-		{ // the records of every shard, in file order (a stable counting sort by shard over slices of the record list): a worker then walks its own list only
-			const size_t n_rec = rec_off.size();
-			if (n_rec > 0xFFFFFFFFull) fail("failed to load alignments");
-			std::vector<u32> counts((size_t) T * T, 0); // [slice][shard]
-			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t sl = lo; sl < hi; ++sl) { u32* cnt = &counts[sl * T]; for (size_t k = n_rec * sl / T; k < n_rec * (sl + 1) / T; ++k) ++cnt[rec_shard[k]]; } });
-			c.shard_begin.assign(T + 1, 0);
-			u32 at = 0;
-			for (int sh = 0; sh < T; ++sh) { c.shard_begin[sh] = at; for (int sl = 0; sl < T; ++sl) { const u32 n = counts[(size_t) sl * T + sh]; counts[(size_t) sl * T + sh] = at; at += n; } }
-			c.shard_begin[T] = at;
-			c.shard_items.resize(n_rec);
-			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t sl = lo; sl < hi; ++sl) { u32* pos = &counts[sl * T]; for (size_t k = n_rec * sl / T; k < n_rec * (sl + 1) / T; ++k) c.shard_items[pos[rec_shard[k]]++] = (u32) k; } });
-		}
 		t_scan += now_s() - tp;
 		if (c.last && c.consumed != buf.size()) fail("failed to load alignments");
 	};
@@ -878,15 +808,15 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 		const double tp = now_s();
 		std::string process_error;
 		try {
-			total_records += c.rec_off.size();
+			total_records += c.n_records;
 			parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) {
 				for (size_t t = lo; t < hi; ++t) {
 					worker& w = workers[t];
 					const u8* base = c.buf.data();
-					const u32* const mine = c.shard_items.data(); const u32 stop = c.shard_begin[t + 1];
+					const u32* const mine = c.shard_rec_off.data(); const u32 stop = c.shard_begin[t + 1];
 					for (u32 x = c.shard_begin[t]; x < stop; ++x) {
-						if (x + 3 < stop) { const u8* ahead = base + c.rec_off[mine[x + 3]]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); } // fixed fields + name, and where the tags of a 2x101 / 2x151 record start
-						const u64 off = c.rec_off[mine[x]];
+						if (x + 3 < stop) { const u8* ahead = base + mine[x + 3]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); } // fixed fields + name, and where the tags of a 2x101 / 2x151 record start
+						const u64 off = mine[x];
 						w.process(base + off + 4, rd32(base + off));
 					}
 					w.park_waiting();

@@ -11,6 +11,7 @@
 #include <utility>
 #include <new>
 #include "refdata.h"
+struct arb_ctx;
 
 namespace arb { namespace host {
 
@@ -73,7 +74,7 @@ struct ingest_stats {
 	double t_inflate, t_parse, t_finalize;
 };
 
-struct ingest_options { bool external_duplicate_marking; u32 max_itd_length; std::string interesting_contigs, viral_contigs; int threads; };
+struct ingest_options { bool external_duplicate_marking; u32 max_itd_length; std::string interesting_contigs, viral_contigs; int threads; struct ::arb_ctx* scan_ctx /* device context that finds the records of every chunk (arb_bam_scan) */; };
 
 // reads the BAM, fills `out` (name order, slots normalised, multimappers marked); throws std::runtime_error on fatal input errors
 void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const ingest_options& opt, fragment_table& out, coverage_windows& coverage, ingest_stats& stats);

@@ -48,6 +48,7 @@ void pipeline::ingest() {
 	const double t0 = now_s();
 	ingest_options io; io.external_duplicate_marking = opt.params.external_duplicate_marking; io.max_itd_length = opt.params.max_itd_length;
 	io.interesting_contigs = opt.interesting_contigs; io.viral_contigs = opt.viral_contigs; io.threads = threads;
+	attach_device(); io.scan_ctx = ctx;
 	read_chimeric_alignments(opt.bam_file, ref, io, frags, coverage, istats);
 	std::ostringstream s; s << "Reading chimeric alignments from '" << opt.bam_file << "' (total=" << frags.n << ")";
 	say(s.str());

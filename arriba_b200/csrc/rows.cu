@@ -1,4 +1,5 @@
 // rows.cu -- driver of the device-side formatting of the discarded-fusions file (see rows_hd.h).
+#include <cstdlib>
 #include "engine.h"
 #include "rows_hd.h"
 
@@ -50,23 +51,25 @@ void engine::format_discarded_rows(const u8* confidence, u64* n_rows, u64* n_byt
 	fm.t.max_itd_length = row_max_itd_length;
 	fm.l1o = cands.list1_off.ptr(); fm.l1 = cands.list1.ptr(); fm.l2o = cands.list2_off.ptr(); fm.l2 = cands.list2.ptr(); fm.ldo = cands.listd_off.ptr(); fm.ld = cands.listd.ptr();
 	// pass 1: row lengths, block by block (32-bit offsets inside a block of rows)
-	const u32 BLOCK = 1u << 21; // 2 M rows: even kilobyte rows stay below 2^32 bytes
+	u32 BLOCK = 1u << 21; // 2 M rows: even kilobyte rows stay below 2^32 bytes
+	if (const char* e = getenv("ARB_ROW_BLOCK")) BLOCK = (u32) std::max(4L, atol(e)) / 4 * 4; // test hook: many blocks
 	const u32 n_blocks = (R + BLOCK - 1) / BLOCK;
-	dbuf<u32> length((size_t) R + n_blocks + 1);
+	const size_t STRIDE = (size_t) BLOCK + 4; // a block's lengths + its total, every block's array 16-byte aligned (the scan reads vectors)
+	dbuf<u32> length(STRIDE * n_blocks + 4);
 	std::vector<u64> base(n_blocks + 1, 0);
 	for (u32 b = 0; b < n_blocks; ++b) {
 		const u32 lo = b * BLOCK, n = std::min(BLOCK, R - lo);
-		u32* len = length.ptr() + lo + b; // n + 1 entries per block
+		u32* len = length.ptr() + STRIDE * b; // n + 1 entries
 		row_length_fn lf = {fm, rows.ptr() + lo, len};
 		for_each(ex, n, lf);
 		exclusive_scan_u32(ex, len, len, n);
-		u32 total = 0; length.download(ex, &total, 1, (size_t) lo + b + n);
+		u32 total = 0; length.download(ex, &total, 1, STRIDE * b + n);
 		base[b + 1] = base[b] + total;
 	}
 	row_text.ensure(base[n_blocks] + 1);
 	for (u32 b = 0; b < n_blocks; ++b) {
 		const u32 lo = b * BLOCK, n = std::min(BLOCK, R - lo);
-		row_write_fn wf = {fm, rows.ptr() + lo, length.ptr() + lo + b, row_text.ptr() + base[b]};
+		row_write_fn wf = {fm, rows.ptr() + lo, length.ptr() + STRIDE * b, row_text.ptr() + base[b]};
 		for_each(ex, n, wf);
 	}
 	row_text_bytes = base[n_blocks];

@@ -108,6 +108,14 @@ int arb_push_chunk(arb_ctx* ctx, const arb_soa_chunk* chunk); /* H2D copy; repla
  * are page-locked; the whole-run driver builds them in page-locked blocks (cudaHostAlloc, recycled across samples). */
 int arb_push_chunk_begin(arb_ctx* ctx, const arb_soa_chunk* chunk);
 int arb_push_chunk_end(arb_ctx* ctx, const arb_soa_chunk* chunk);
+/* ---- BAM records of an inflated chunk -------------------------------------------------------------------------
+ * The bookkeeping the reference's record loop (source/read_chimeric_alignments.cpp:611, sam_read1) does implicitly: where the records of a chunk of inflated
+ * BGZF payload start (SAMv1 4.2: every record begins with its block_size) and which worker parses which record -- lists by read-name hash (FNV-1a), so that
+ * the records of a fragment meet in one list; file order is kept inside a list. chunk: page-locked host memory makes the copy asynchronous; first = offset of
+ * the first record; n_ref = reference sequences of the BAM header (sanity of guessed record starts); consumed = offset behind the last complete record;
+ * record_offsets: capacity bytes / 36 + 1; malformed != 0: a block_size < 33 was met where a one-thread walk would have met it. */
+int arb_bam_scan(arb_ctx* ctx, const uint8_t* chunk, uint64_t bytes, uint64_t first, int32_t n_ref, uint32_t n_lists, uint64_t* consumed, uint32_t* n_records,
+                 uint32_t* list_begin /* n_lists + 1 */, uint32_t* record_offsets, uint32_t* malformed);
 /* ---- annotation of the resident fragments -------------------------------------------------------------------
  * Replaces the annotation passes of main (source/arriba.cpp:165-325: annotate_alignments per fragment, source/annotation.cpp:431-555; dummy genes for
  * intergenic breakpoints, arriba.cpp:207-260; second pass :262-319) and assign_strands_from_strandedness (source/read_chimeric_alignments.cpp:775-790).
@@ -295,6 +303,7 @@ typedef struct arb_timings {
 	float order_ms;             /* arb_replay_insertion_order */
 	float partners_ms;          /* arb_partner_counts */
 	float rows_ms;              /* arb_format_discarded_rows */
+	float bam_scan_ms;          /* arb_bam_scan, summed over the chunks of the last sample (copy + kernels + lists back) */
 	uint64_t mismapper_algorithmic_bytes; /* SURVEY.md section 8(d) budget of pass 1 of the re-alignment: per searched sequence of length l, 3l/8 + 8(l-8) + 4*hits + l/2 */
 	uint64_t mismapper_sequences, mismapper_hits; /* sequences searched by pass 1 (segment x gene x strand) and k-mer hits they visited */
 } arb_timings;

@@ -26,6 +26,18 @@ def test_e2e_hostsim(worlds, hostsim_lib, tmp_path):
     check_e2e(worlds.get("small"), hostsim_lib, tmp_path)
 
 
+def test_e2e_hostsim_row_blocks(worlds, hostsim_lib, tmp_path, monkeypatch):
+    """the discarded rows are formatted on the device in blocks of rows (32-bit offsets inside a block): many small blocks"""
+    monkeypatch.setenv("ARB_ROW_BLOCK", "1000")
+    check_e2e(worlds.get("small"), hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_row_blocks(worlds, cuda_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("ARB_ROW_BLOCK", "1000")
+    check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
+
+
 def test_e2e_hostsim_l151(worlds, hostsim_lib, tmp_path):
     check_e2e(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, tmp_path)
 

@@ -117,8 +117,9 @@ def test_front_end_cuda(worlds, cuda_lib):
 
 @pytest.mark.parametrize("threads,min_bytes", [(7, "20000"), (16, "1000"), (3, "300")])
 def test_front_end_hostsim_parallel_record_scan(worlds, hostsim_lib, monkeypatch, threads, min_bytes):
-    """Record boundaries found by several threads from guessed starts (verified against the true chain), down to pieces smaller than a record."""
+    """Record boundaries found piecewise from guessed starts (verified against the true chain; csrc/bamscan.cu), down to pieces smaller than a record."""
     monkeypatch.setenv("ARB_SCAN_MIN_BYTES", min_bytes)
+    monkeypatch.setenv("ARB_BAM_SCAN_PIECE", str(max(50, int(min_bytes) // 4)))
     check_front_end(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, threads=threads)
 
 
