@@ -123,6 +123,10 @@ int arb_partner_counts(arb_ctx* ctx, int32_t* out) { ARB_API_BEGIN(ctx) ctx->e.p
 int arb_set_row_texts(arb_ctx* ctx, const arb_row_texts* t) { ARB_API_BEGIN(ctx) if (!t) throw arb_error("null tables"); ctx->e.set_row_texts(*t); ARB_API_END(ctx) }
 int arb_format_discarded_rows(arb_ctx* ctx, const uint8_t* confidence, uint64_t* n_rows, uint64_t* n_bytes) { ARB_API_BEGIN(ctx) u64 r = 0, b = 0; ctx->e.format_discarded_rows(confidence, &r, &b); *n_rows = r; *n_bytes = b; ARB_API_END(ctx) }
 int arb_get_row_text(arb_ctx* ctx, char* out) { ARB_API_BEGIN(ctx) ctx->e.get_row_text(out); ARB_API_END(ctx) }
+int arb_build_consensus(arb_ctx* ctx, const uint32_t* candidates, uint32_t n_rows, arb_consensus_info* info) { ARB_API_BEGIN(ctx) ctx->e.build_consensus(candidates, n_rows, *info); ARB_API_END(ctx) }
+int arb_get_consensus(arb_ctx* ctx, uint32_t* seq_off, uint32_t* pos_off, uint32_t* clip_off, uint8_t* verdict, uint32_t* non_template, char* seq, int32_t* pos, char* clip) {
+	ARB_API_BEGIN(ctx) ctx->e.get_consensus(seq_off, pos_off, clip_off, verdict, non_template, seq, pos, clip); ARB_API_END(ctx)
+}
 int arb_filter_multimappers(arb_ctx* ctx) { ARB_API_BEGIN(ctx) ctx->e.filter_multimappers(); ARB_API_END(ctx) }
 int arb_set_splice_sites(arb_ctx* ctx, const uint32_t* off, const int32_t* sites) { ARB_API_BEGIN(ctx) ctx->e.set_splice_sites(off, sites); ARB_API_END(ctx) }
 int arb_build_kmer_index(arb_ctx* ctx, const uint32_t* contig, const int32_t* start, const int32_t* end, uint32_t n, uint32_t nc, uint64_t* n_indexed) { ARB_API_BEGIN(ctx) uint64_t k = ctx->e.build_kmer_index(contig, start, end, n, nc); if (n_indexed) *n_indexed = k; ARB_API_END(ctx) }

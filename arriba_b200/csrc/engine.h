@@ -140,6 +140,9 @@ public:
 	void set_row_texts(const arb_row_texts& t); void format_discarded_rows(const u8* confidence, u64* n_rows, u64* n_bytes); void get_row_text(char* out);
 	dbuf<char> row_gene_name, row_gene_id, row_contig_name, row_filter_name, row_text; dbuf<u32> row_gene_name_off, row_gene_id_off, row_contig_name_off, row_filter_name_off; dbuf<i32> row_exon_prev, row_exon_next;
 	u8 row_filters_by_name[ARB_N_FILTERS]; u32 row_max_itd_length; bool has_row_texts; u64 row_text_bytes; struct cand_state make_state_for_rows();
+	// pileups and consensus sequences of the rows of fusions.tsv (consensus.cu)
+	void build_consensus(const u32* rows, u32 n_rows, arb_consensus_info& info); void get_consensus(u32* seq_off, u32* pos_off, u32* clip_off, u8* verdict, u32* non_template, char* seq, i32* pos, char* clip);
+	dbuf<u32> cons_seq_off, cons_pos_off, cons_clip_off, cons_non_template; dbuf<u8> cons_verdict; dbuf<char> cons_seq, cons_clip; dbuf<i32> cons_pos; u32 cons_rows; u64 cons_seq_bytes, cons_pos_count, cons_clip_bytes;
 	dbuf<u32> merge_log; u32 merge_log_n;
 	// filter_in_vitro on the device (events.cu): coverage windows of the sample, expression per gene
 	void set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs); void reads_by_gene(u32* out);

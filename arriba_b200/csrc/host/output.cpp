@@ -288,9 +288,16 @@ struct writer {
 	static bool lower_acgt(char c) { return c == 'a' || c == 't' || c == 'c' || c == 'g'; }
 
 	// ---- fusion transcript (output_fusions.cpp:242-466)
-	void transcript_sequence(u32 k, std::string& sequence, std::vector<i32>& positions) const {
-		const bool strands_ambiguous = e.bits[k] & CB_PSTRANDS_AMBIGUOUS, tstart_ambiguous = e.bits2[k] & 1;
-		if (strands_ambiguous || tstart_ambiguous) { sequence = "."; positions.push_back(-1); return; }
+	// the two consensus sequences of a candidate with the positions of their characters, the bases beyond the breakpoints, and the non-template count:
+	// from the device (csrc/consensus_hd.h) or, for the rows it left over, from the pileups below
+	struct side_strings { std::string s1, s2, c1, c2; std::vector<i32> p1, p2; unsigned int non_template; };
+	bool transcript_unknown(u32 k) const { return (e.bits[k] & CB_PSTRANDS_AMBIGUOUS) || (e.bits2[k] & 1); }
+	void transcript_sequence(u32 k, std::string& sequence, std::vector<i32>& positions, const side_strings* from_device = NULL) const {
+		if (transcript_unknown(k)) { sequence = "."; positions.push_back(-1); return; }
+		if (from_device) { side_strings copy = *from_device; finish_transcript(k, copy, sequence, positions); return; }
+		side_strings sides; host_sides(k, sides); finish_transcript(k, sides, sequence, positions);
+	}
+	void host_sides(u32 k, side_strings& out) const {
 		const u32 d1 = e.dir1[k], d2 = e.dir2[k]; const i32 bp1 = e.bp1[k], bp2 = e.bp2[k];
 		static thread_local pile_builder build1, build2;
 		pile_builder& pile1 = build1; pile_builder& pile2 = build2;
@@ -316,10 +323,15 @@ struct writer {
 				if (cs + cu >= f.seq_len[s]) { const unsigned int unmapped = cs + cu - f.seq_len[s]; if (++count[unmapped] > count[non_template]) non_template = unmapped; }
 			}
 		}
-		std::string s1, s2, c1, c2; std::vector<i32> p1, p2;
 		pileup_t columns;
-		pile1.flatten(columns); consensus(columns, bp1, d1, e.gene1[k], s1, p1, c1);
-		pile2.flatten(columns); consensus(columns, bp2, d2, e.gene2[k], s2, p2, c2);
+		pile1.flatten(columns); consensus(columns, bp1, d1, e.gene1[k], out.s1, out.p1, out.c1);
+		pile2.flatten(columns); consensus(columns, bp2, d2, e.gene2[k], out.s2, out.p2, out.c2);
+		out.non_template = non_template;
+	}
+	void finish_transcript(u32 k, side_strings& sides, std::string& sequence, std::vector<i32>& positions) const {
+		const u32 d1 = e.dir1[k], d2 = e.dir2[k];
+		std::string& s1 = sides.s1; std::string& s2 = sides.s2; std::string& c1 = sides.c1; std::string& c2 = sides.c2; std::vector<i32>& p1 = sides.p1; std::vector<i32>& p2 = sides.p2;
+		const unsigned int non_template = sides.non_template;
 		if (e.n_list1(k) + e.n_list2(k) == 0) { // breakpoints are not known exactly
 			if (d1 == DOWNSTREAM) { s1 += "..."; p1.resize(p1.size() + 3, -1); } else { s1 = "..." + s1; p1.insert(p1.begin(), 3, -1); }
 			if (d2 == DOWNSTREAM) { s2 += "..."; p2.resize(p2.size() + 3, -1); } else { s2 = "..." + s2; p2.insert(p2.begin(), 3, -1); }
@@ -672,7 +684,7 @@ struct writer {
 		for (u32 r = e.listd_off[k]; r < e.listd_off[k + 1] && r < e.listd_off[k] + 8; ++r) __builtin_prefetch(&p.labels[e.listd[r]]);
 	}
 
-	void format_row(row_buffer& out, u32 k, bool extra_info) const {
+	void format_row(row_buffer& out, u32 k, bool extra_info, const side_strings* from_device = NULL) const {
 			static const char* CONF[] = {"low", "medium", "high", "high"};
 			std::string site5 = site(e.gene1[k], e.spliced1(k), e.exonic1(k), e.contig1[k], e.bp1[k]), site3 = site(e.gene2[k], e.spliced2(k), e.exonic2(k), e.contig2[k], e.bp2[k]);
 			u32 g5 = e.gene1[k], g3 = e.gene2[k], c5 = e.contig1[k], c3 = e.contig2[k], d5 = e.dir1[k], d3 = e.dir2[k], s5 = e.split_reads1[k], s3 = e.split_reads2[k];
@@ -683,7 +695,7 @@ struct writer {
 			std::string tseq = ".", pep = ".", frame = "."; i32 tr5 = -1, tr3 = -1;
 			if (extra_info) {
 				std::vector<i32> positions;
-				transcript_sequence(k, tseq, positions);
+				transcript_sequence(k, tseq, positions, from_device);
 				std::vector<i32> t5, t3;
 				matching_transcripts(tseq, positions, g5, st5, ambiguous, 5, t5);
 				matching_transcripts(tseq, positions, g3, st3, ambiguous, 3, t3);
@@ -777,6 +789,44 @@ struct writer {
 		out.slices.clear(); out.warnings.clear();
 		laps.lap("discarded", "rows formatted (device)");
 	}
+	// pileups and consensus sequences of the rows of fusions.tsv on the device, in batches of rows; what the device leaves over (verdict != 0) is done by host_sides
+	struct device_consensus {
+		enum { BATCH = 32768 };
+		struct batch { std::vector<u32> seq_off, pos_off, clip_off, non_template; std::vector<u8> verdict; std::vector<char> seq, clip; std::vector<i32> pos; };
+		std::vector<batch> batches; std::vector<u32> slot_of_row; // row x -> index among the rows handed to the device, or ~0
+		bool get(size_t x, side_strings& out) const {
+			if (x >= slot_of_row.size() || slot_of_row[x] == ~0u) return false;
+			const batch& b = batches[slot_of_row[x] / BATCH]; const u32 r = slot_of_row[x] % BATCH, j = 2 * r;
+			if (b.verdict[j] != 0 || b.verdict[j + 1] != 0 || b.non_template[r] == 0xFFFFFFFFu) return false;
+			out.s1.assign(b.seq.data() + b.seq_off[j], b.seq_off[j + 1] - b.seq_off[j]); out.s2.assign(b.seq.data() + b.seq_off[j + 1], b.seq_off[j + 2] - b.seq_off[j + 1]);
+			out.c1.assign(b.clip.data() + b.clip_off[j], b.clip_off[j + 1] - b.clip_off[j]); out.c2.assign(b.clip.data() + b.clip_off[j + 1], b.clip_off[j + 2] - b.clip_off[j + 1]);
+			out.p1.assign(b.pos.data() + b.pos_off[j], b.pos.data() + b.pos_off[j + 1]); out.p2.assign(b.pos.data() + b.pos_off[j + 1], b.pos.data() + b.pos_off[j + 2]);
+			out.non_template = b.non_template[r];
+			return true;
+		}
+	};
+	void consensus_on_device(const std::vector<u32>& rows, device_consensus& out) const {
+		pipeline& pl = p;
+		std::vector<u32> cands; out.slot_of_row.assign(rows.size(), ~0u);
+		for (size_t x = 0; x < rows.size(); ++x) if (!transcript_unknown(rows[x])) { out.slot_of_row[x] = (u32) cands.size(); cands.push_back(rows[x]); }
+		if (cands.empty()) return;
+		if (arb_set_fragment_filters(pl.ctx, pl.labels.data()) != 0) throw std::runtime_error(std::string("arb_set_fragment_filters: ") + arb_last_error(pl.ctx));
+		pl.push_candidate_state();
+		u64 left_to_host = 0, retried = 0, reasons[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		for (size_t lo = 0; lo < cands.size(); lo += device_consensus::BATCH) {
+			const u32 n = (u32) std::min<size_t>(device_consensus::BATCH, cands.size() - lo);
+			arb_consensus_info info;
+			if (arb_build_consensus(pl.ctx, cands.data() + lo, n, &info) != 0) throw std::runtime_error(std::string("arb_build_consensus: ") + arb_last_error(pl.ctx));
+			out.batches.emplace_back(); device_consensus::batch& b = out.batches.back();
+			b.seq_off.resize(2 * (size_t) n + 1); b.pos_off.resize(2 * (size_t) n + 1); b.clip_off.resize(2 * (size_t) n + 1); b.verdict.resize(2 * (size_t) n); b.non_template.resize(n);
+			b.seq.resize(info.seq_bytes + 1); b.pos.resize(info.pos_count + 1); b.clip.resize(info.clip_bytes + 1);
+			if (arb_get_consensus(pl.ctx, b.seq_off.data(), b.pos_off.data(), b.clip_off.data(), b.verdict.data(), b.non_template.data(), b.seq.data(), b.pos.data(), b.clip.data()) != 0) throw std::runtime_error(std::string("arb_get_consensus: ") + arb_last_error(pl.ctx));
+			for (size_t j = 0; j < b.verdict.size(); ++j) if (b.verdict[j]) { ++left_to_host; for (int q = 0; q < 8; ++q) if (b.verdict[j] >> q & 1) ++reasons[q]; }
+			retried += info.retried_jobs;
+		}
+		if (getenv("ARB_TRACE")) fprintf(stderr, "[laps] output fusions    consensus jobs %zu, second launch %llu, left to the host %llu (tiles %llu, side list %llu, introns %llu, empty key %llu, counters %llu, output %llu, odd column %llu)\n", cands.size() * 2, (unsigned long long) retried, (unsigned long long) left_to_host,
+			(unsigned long long) reasons[0], (unsigned long long) reasons[2], (unsigned long long) reasons[3], (unsigned long long) reasons[4], (unsigned long long) reasons[5], (unsigned long long) reasons[6], (unsigned long long) reasons[7]);
+	}
 	void format_rows(bool discarded, bool extra_info, formatted& out) const {
 		if (discarded && !extra_info && (getenv("ARB_DEVICE_ROWS") == NULL || atoi(getenv("ARB_DEVICE_ROWS")) != 0)) { format_discarded_rows_on_device(out); return; }
 		sort_filters_by_name();
@@ -795,6 +845,8 @@ struct writer {
 			});
 		}
 		const std::string header = header_line();
+		device_consensus from_device;
+		if (extra_info && !discarded && (getenv("ARB_DEVICE_CONSENSUS") == NULL || atoi(getenv("ARB_DEVICE_CONSENSUS")) != 0)) { consensus_on_device(rows, from_device); laps.lap(which, "pileups + consensus (device)"); }
 		// Rows are independent and cost very different amounts (the best-supported fusions come first and carry hundreds of reads each): threads draw small
 		// chunks of rows from a shared counter; every chunk is formatted into its own string and later copied to its offset of the file (flush_rows).
 		const size_t CHUNK = 32;
@@ -817,7 +869,8 @@ struct writer {
 							if (x + 6 < rows.size()) prefetch_candidate(rows[x + 6]);
 							if (x + 4 < rows.size()) prefetch_lists(rows[x + 4]);
 							if (x + 2 < rows.size()) prefetch_labels(rows[x + 2]);
-							format_row(text, rows[x], extra_info);
+							side_strings sides;
+							format_row(text, rows[x], extra_info, from_device.get(x, sides) ? &sides : NULL);
 						}
 						slices[c].swap(text.s);
 					}

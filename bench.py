@@ -246,7 +246,7 @@ def main():
         st = p.stats(); tm = ctx.timings() if ctx.h else L.Timings()
         n_cand = int(st.n_candidates)
         d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
-        dev_ms = tm.annotate_ms + tm.read_filters_ms + tm.find_fusions_ms + tm.order_ms + tm.merge_adjacent_ms + tm.multimappers_ms + tm.evalue_ms + tm.in_vitro_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms
+        dev_ms = tm.annotate_ms + tm.read_filters_ms + tm.find_fusions_ms + tm.order_ms + tm.merge_adjacent_ms + tm.multimappers_ms + tm.evalue_ms + tm.in_vitro_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms + tm.partners_ms + tm.rows_ms + tm.consensus_ms + tm.bam_scan_ms
         ev = {n: round(st.event_seconds[i], 2) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.2}
         say("[bench] step: e2e %.2f s, device %.1f ms, ingest %.2f, annotate %.2f, upload %.2f, output %.2f, events >= 0.2 s: %s" %
             (e2e_s, dev_ms, st.seconds[L.STEP_INGEST], st.seconds[L.STEP_ANNOTATE], st.seconds[L.STEP_UPLOAD], st.output_seconds, ev))
@@ -345,7 +345,8 @@ def main():
     dominant = max(kernels, key=lambda k: k["kernel_ms"])
     device_ms = {"annotate": tm.annotate_ms, "order": tm.order_ms, "multimappers": tm.multimappers_ms, "in_vitro": tm.in_vitro_ms, "duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
                  "merge_adjacent": tm.merge_adjacent_ms, "evalue": tm.evalue_ms, "kmer_index": tm.kmer_index_ms, "homologs": tm.homologs_ms, "mismappers": tm.mismappers_ms,
-                 "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms}
+                 "mismappers_pass1": tm.mismappers_pass1_ms, "mismappers_pass2": tm.mismappers_pass2_ms,
+                 "partners": tm.partners_ms, "discarded_rows": tm.rows_ms, "consensus": tm.consensus_ms, "bam_scan": tm.bam_scan_ms}
     roofline = dict(dominant)
     roofline.update({"kernels": kernels, "device_ms": device_ms,
                      "mismapper_sequences": int(tm.mismapper_sequences), "mismapper_hits": int(tm.mismapper_hits),

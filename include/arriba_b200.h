@@ -237,6 +237,16 @@ typedef struct arb_row_texts {
 int arb_set_row_texts(arb_ctx* ctx, const arb_row_texts* texts);
 int arb_format_discarded_rows(arb_ctx* ctx, const uint8_t* confidence /* per candidate: 0 low, 1 medium, 2 high */, uint64_t* n_rows, uint64_t* n_bytes);
 int arb_get_row_text(arb_ctx* ctx, char* out /* n_bytes */);
+/* ---- read pileups and consensus sequences of the rows of fusions.tsv ---------------------------------------------------------
+ * arb_build_consensus replaces pileup_chimeric_alignments (source/output_fusions.cpp:25) and get_sequence_from_pileup (:109) as called by
+ * get_fusion_transcript_sequence (:242-318) for a batch of candidates: per candidate two pileups (one per breakpoint) over ten views of its supporting reads,
+ * each reduced to the consensus string, the genomic position of every character (-1 = none) and the bases beyond the breakpoint; and the number of
+ * non-template bases between the fused segments (:300-318). Job 2 r + s is side s (0: breakpoint 1) of candidates[r]. arb_get_consensus copies the packed
+ * results: *_off hold 2 n_rows + 1 offsets, verdict[j] != 0 marks a job the device left to the caller (tables full, 16-bit counters, empty insertion key),
+ * non_template[r] == 0xFFFFFFFF a row whose non-template count the caller computes. Fragment labels and candidate state must be current on the device. */
+typedef struct arb_consensus_info { uint32_t n_rows, retried_jobs; uint64_t seq_bytes, pos_count, clip_bytes; } arb_consensus_info;
+int arb_build_consensus(arb_ctx* ctx, const uint32_t* candidates, uint32_t n_rows, arb_consensus_info* info);
+int arb_get_consensus(arb_ctx* ctx, uint32_t* seq_off, uint32_t* pos_off, uint32_t* clip_off, uint8_t* verdict, uint32_t* non_template, char* seq, int32_t* pos, char* clip);
 
 /* ---- k-mer index of the fused genes, gene homology, re-alignment of supporting reads -----------------------------------
  * arb_build_kmer_index replaces make_kmer_index (source/filter_mismappers.cpp:47): `intervals` are the disjoint, sorted unions of the
@@ -304,6 +314,8 @@ typedef struct arb_timings {
 	float partners_ms;          /* arb_partner_counts */
 	float rows_ms;              /* arb_format_discarded_rows */
 	float bam_scan_ms;          /* arb_bam_scan, summed over the chunks of the last sample (copy + kernels + lists back) */
+	float consensus_ms;         /* arb_build_consensus, summed over the batches of the last sample */
+	float reserved_ms;
 	uint64_t mismapper_algorithmic_bytes; /* SURVEY.md section 8(d) budget of pass 1 of the re-alignment: per searched sequence of length l, 3l/8 + 8(l-8) + 4*hits + l/2 */
 	uint64_t mismapper_sequences, mismapper_hits; /* sequences searched by pass 1 (segment x gene x strand) and k-mer hits they visited */
 } arb_timings;

@@ -38,6 +38,29 @@ def test_e2e_cuda_row_blocks(worlds, cuda_lib, tmp_path, monkeypatch):
     check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
 
 
+def test_e2e_hostsim_consensus_overflow(worlds, hostsim_lib, tmp_path, monkeypatch):
+    """pileups and consensus of the fusions rows (csrc/consensus_hd.h) with tiny tables: most jobs go through the second launch, some are left to the host code"""
+    monkeypatch.setenv("ARB_CONSENSUS_TILES", "4")
+    check_e2e(worlds.get("small"), hostsim_lib, tmp_path)
+
+
+def test_e2e_hostsim_consensus_on_host(worlds, hostsim_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("ARB_DEVICE_CONSENSUS", "0")
+    check_e2e(worlds.get("small"), hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_consensus_overflow(worlds, cuda_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("ARB_CONSENSUS_TILES", "4")
+    check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_consensus_on_host(worlds, cuda_lib, tmp_path, monkeypatch):
+    monkeypatch.setenv("ARB_DEVICE_CONSENSUS", "0")
+    check_e2e(worlds.get("small"), cuda_lib, tmp_path, threads=8)
+
+
 def test_e2e_hostsim_l151(worlds, hostsim_lib, tmp_path):
     check_e2e(worlds.get("l151", read_length=151, seed=7, extra=("--shuffle", "--varnames")), hostsim_lib, tmp_path)
 
