@@ -791,8 +791,8 @@ struct writer {
 	}
 	// pileups and consensus sequences of the rows of fusions.tsv on the device, in batches of rows; what the device leaves over (verdict != 0) is done by host_sides
 	struct device_consensus {
-		enum { BATCH = 32768 };
-		struct batch { std::vector<u32> seq_off, pos_off, clip_off, non_template; std::vector<u8> verdict; std::vector<char> seq, clip; std::vector<i32> pos; };
+		enum { BATCH = 65536 };
+		struct batch { column<u32> seq_off, pos_off, clip_off, non_template; column<u8> verdict; column<char> seq, clip; column<i32> pos; }; // page-locked blocks, not zeroed
 		std::vector<batch> batches; std::vector<u32> slot_of_row; // row x -> index among the rows handed to the device, or ~0
 		bool get(size_t x, side_strings& out) const {
 			if (x >= slot_of_row.size() || slot_of_row[x] == ~0u) return false;
@@ -810,17 +810,21 @@ struct writer {
 		std::vector<u32> cands; out.slot_of_row.assign(rows.size(), ~0u);
 		for (size_t x = 0; x < rows.size(); ++x) if (!transcript_unknown(rows[x])) { out.slot_of_row[x] = (u32) cands.size(); cands.push_back(rows[x]); }
 		if (cands.empty()) return;
+		output_laps laps;
 		if (arb_set_fragment_filters(pl.ctx, pl.labels.data()) != 0) throw std::runtime_error(std::string("arb_set_fragment_filters: ") + arb_last_error(pl.ctx));
 		pl.push_candidate_state();
+		laps.lap("fusions", "consensus: labels + state -> device");
 		u64 left_to_host = 0, retried = 0, reasons[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		for (size_t lo = 0; lo < cands.size(); lo += device_consensus::BATCH) {
 			const u32 n = (u32) std::min<size_t>(device_consensus::BATCH, cands.size() - lo);
 			arb_consensus_info info;
 			if (arb_build_consensus(pl.ctx, cands.data() + lo, n, &info) != 0) throw std::runtime_error(std::string("arb_build_consensus: ") + arb_last_error(pl.ctx));
+			laps.lap("fusions", "consensus: kernels");
 			out.batches.emplace_back(); device_consensus::batch& b = out.batches.back();
 			b.seq_off.resize(2 * (size_t) n + 1); b.pos_off.resize(2 * (size_t) n + 1); b.clip_off.resize(2 * (size_t) n + 1); b.verdict.resize(2 * (size_t) n); b.non_template.resize(n);
 			b.seq.resize(info.seq_bytes + 1); b.pos.resize(info.pos_count + 1); b.clip.resize(info.clip_bytes + 1);
 			if (arb_get_consensus(pl.ctx, b.seq_off.data(), b.pos_off.data(), b.clip_off.data(), b.verdict.data(), b.non_template.data(), b.seq.data(), b.pos.data(), b.clip.data()) != 0) throw std::runtime_error(std::string("arb_get_consensus: ") + arb_last_error(pl.ctx));
+			laps.lap("fusions", "consensus: strings -> host");
 			for (size_t j = 0; j < b.verdict.size(); ++j) if (b.verdict[j]) { ++left_to_host; for (int q = 0; q < 8; ++q) if (b.verdict[j] >> q & 1) ++reasons[q]; }
 			retried += info.retried_jobs;
 		}
