@@ -113,6 +113,15 @@ void engine::filter_relative_support(float cutoff) {
 	ex.sync();
 }
 
+u32 engine::filter_simple(int stage, float exonic_fraction, int min_support) {
+	if (stage < SIMPLE_NON_CODING_NEIGHBORS || stage > SIMPLE_MIN_SUPPORT) throw arb_error("arb_filter_simple: unknown stage");
+	dbuf<u32> remaining(1); remaining.zero(ex, 1);
+	simple_filter_fn fn = {make_state(cands, NULL, NULL), annot.view(), stage, exonic_fraction, min_support, remaining.ptr()};
+	for_each(ex, cands.n, fn);
+	u32 r = 0; remaining.download(ex, &r, 1);
+	return r;
+}
+
 // ------------------------------------------------------------------------------------------- filter_in_vitro and its inputs
 void engine::set_coverage(const u16* const* per_contig, const u64* n_windows, u32 n_contigs) {
 	std::vector<u64> off(n_contigs, 0); std::vector<u32> wins(n_contigs, 0);

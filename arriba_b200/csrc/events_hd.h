@@ -186,6 +186,37 @@ struct relative_support_fn { // filter_relative_support.cpp:209-223
 	}
 };
 
+// ---- per-candidate predicates of the event chain that only look at the candidate itself: filter_non_coding_neighbors.cpp, filter_intragenic_both_exonic.cpp,
+// filter_min_support.cpp; `remaining` counts the candidates that are still unfiltered afterwards (the stage's "(remaining=N)" line)
+enum { SIMPLE_NON_CODING_NEIGHBORS = 0, SIMPLE_INTRAGENIC_EXONIC = 1, SIMPLE_MIN_SUPPORT = 2 };
+struct simple_filter_fn {
+	cand_state c; annot_view an; int stage; float exonic_fraction; int min_support; u32* remaining;
+	ARB_HD bool read_through(u32 k) const { return c.contig1[k] == c.contig2[k] && c.bp2[k] - c.bp1[k] < 400000 && c.dir1[k] == DOWNSTREAM && c.dir2[k] == UPSTREAM; } // common.hpp:265-269
+	ARB_HD bool overlaps_both(u32 k) const { // common.hpp:260-264
+		const u32 g1 = c.gene1[k], g2 = c.gene2[k];
+		return (c.bp1[k] >= an.gene_start[g2] && c.bp1[k] <= an.gene_end[g2]) || (c.bp2[k] >= an.gene_start[g1] && c.bp2[k] <= an.gene_end[g1]);
+	}
+	ARB_HD void operator()(u32 k) const {
+		if (c.filter[k] != F_none) return;
+		const u32 g1 = c.gene1[k], g2 = c.gene2[k];
+		u8 verdict = F_none;
+		if (stage == SIMPLE_NON_CODING_NEIGHBORS) {
+			if (!(an.gene_flags[g1] & GF_CODING) && !(an.gene_flags[g2] & GF_CODING) && read_through(k)) verdict = F_non_coding_neighbors;
+		} else if (stage == SIMPLE_INTRAGENIC_EXONIC) {
+			const u8 b = c.bits[k];
+			if ((overlaps_both(k) || g1 == g2) && (b & CB_EXONIC1) && (b & CB_EXONIC2) && !((b & CB_SPLICED1) && (b & CB_SPLICED2))) {
+				const int sd = spliced_distance(an, c.contig1[k], c.bp1[k], c.bp2[k], g1);
+				const int distance = c.bp2[k] - c.bp1[k];
+				if (sd == distance || 1.0 * sd / distance < exonic_fraction) verdict = F_intragenic_exonic;
+			}
+		} else {
+			const int split = (int) (c.split_reads1[k] + c.split_reads2[k]);
+			if (split + (int) c.discordant_mates[k] < min_support || (overlaps_both(k) && split < min_support)) verdict = F_min_support;
+		}
+		if (verdict != F_none) c.filter[k] = verdict; else atomic_add_u32(remaining, 1);
+	}
+};
+
 // ---- expression per gene (filter_in_vitro.cpp:48-83): supporting fragments per gene of MATE1 and of the last alignment
 struct reads_by_gene_fn {
 	frag_view f; u32* reads;

@@ -307,33 +307,17 @@ void pipeline::filter_relative_support() {
 }
 
 // ------------------------------------------------------------------------------------------- cheap predicates
-void pipeline::filter_non_coding_neighbors() { // filter_non_coding_neighbors.cpp
-	for (u32 k = 0; k < ev.n; ++k) if (ev.filter[k] == F_none && !ref.genes[ev.gene1[k]].is_protein_coding && !ref.genes[ev.gene2[k]].is_protein_coding && ev.is_read_through(k)) ev.filter[k] = F_non_coding_neighbors;
-	log_remaining("Filtering fusions with both breakpoints in adjacent non-coding/intergenic regions");
+// the three predicates between the e-value and its cutoff look at one candidate each: on the device (csrc/events_hd.h, simple_filter_fn); only the filter column travels
+static void simple_stage(pipeline& p, int stage, const char* what) {
+	p.push_candidate_state();
+	uint32_t remaining = 0;
+	check(p.ctx, arb_filter_simple(p.ctx, stage, p.opt.exonic_fraction, p.opt.min_support, &remaining), "arb_filter_simple");
+	check(p.ctx, arb_get_candidate_filters(p.ctx, p.ev.filter.data()), "arb_get_candidate_filters");
+	std::ostringstream s; s << what << " (remaining=" << remaining << ")"; p.say(s.str());
 }
-
-void pipeline::filter_intragenic_both_exonic() { // filter_intragenic_both_exonic.cpp
-	const annot_view an = ref.host_view();
-	const float exonic_fraction = opt.exonic_fraction; // -e
-	parallel_rows(threads, ev.n, [&](u32 k) {
-		if (ev.filter[k] != F_none) return;
-		if ((overlaps_both(ev, ref, k) || ev.gene1[k] == ev.gene2[k]) && ev.exonic1(k) && ev.exonic2(k) && !(ev.spliced1(k) && ev.spliced2(k))) {
-			const int sd = spliced_distance(an, ev.contig1[k], ev.bp1[k], ev.bp2[k], ev.gene1[k]);
-			const int distance = ev.bp2[k] - ev.bp1[k];
-			if (sd == distance || 1.0 * sd / distance < exonic_fraction) ev.filter[k] = F_intragenic_exonic;
-		}
-	});
-	log_remaining("Filtering intragenic fusions with both breakpoints in exonic regions");
-}
-
-void pipeline::filter_min_support() { // filter_min_support.cpp
-	const int min_support = opt.min_support; // -S
-	for (u32 k = 0; k < ev.n; ++k) {
-		if (ev.filter[k] != F_none) continue;
-		if ((int) ev.supporting_reads(k) < min_support || (overlaps_both(ev, ref, k) && (int) (ev.split_reads1[k] + ev.split_reads2[k]) < min_support)) ev.filter[k] = F_min_support;
-	}
-	log_remaining("Filtering fusions with <2 supporting reads");
-}
+void pipeline::filter_non_coding_neighbors() { simple_stage(*this, 0, "Filtering fusions with both breakpoints in adjacent non-coding/intergenic regions"); } // filter_non_coding_neighbors.cpp
+void pipeline::filter_intragenic_both_exonic() { simple_stage(*this, 1, "Filtering intragenic fusions with both breakpoints in exonic regions"); } // filter_intragenic_both_exonic.cpp
+void pipeline::filter_min_support() { simple_stage(*this, 2, "Filtering fusions with <2 supporting reads"); } // filter_min_support.cpp
 
 void pipeline::recover_internal_tandem_duplication() { // recover_internal_tandem_duplication.cpp
 	const annot_view an = ref.host_view();
@@ -802,10 +786,10 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 	auto by_gene = [&](u32 g) { gene_list l = {by_gene_items.data() + by_gene_off[g], by_gene_off[g + 1] - by_gene_off[g]}; return l; };
 	enum { LOW = 0, MEDIUM = 1, HIGH = 2 };
 	parallel_rows(threads, ev.n, [&](u32 k) {
+		if (ev.filter[k] != F_none) { ev.confidence[k] = LOW; return; } // before the coverage is looked up: nearly all candidates are filtered by now
 		const int cov1 = coverage.get_coverage(ev.contig1[k], ev.bp1[k], ev.dir1[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		const int cov2 = coverage.get_coverage(ev.contig2[k], ev.bp2[k], ev.dir2[k] == UPSTREAM ? DOWNSTREAM : UPSTREAM);
 		const float coverage_fraction = ((float) (ev.n_list1(k) + ev.n_list2(k) + ev.n_listd(k))) / std::max(1, std::max(cov1, cov2));
-		if (ev.filter[k] != F_none) { ev.confidence[k] = LOW; return; }
 		int conf = HIGH;
 		const u32 s1 = ev.split_reads1[k], s2 = ev.split_reads2[k], d = ev.discordant_mates[k], sup = s1 + s2 + d;
 		if (ev.evalue[k] > 0.3 || sup < 2) conf = LOW;

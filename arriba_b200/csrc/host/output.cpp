@@ -11,6 +11,7 @@
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/uio.h>
 #include <unistd.h>
 #include <chrono>
 #include <cmath>
@@ -921,12 +922,17 @@ struct writer {
 		} else {
 			auto write_all = [&](const char* data, size_t n) { while (n > 0) { const ssize_t w = ::write(fd, data, std::min<size_t>(n, (size_t) 8 << 20)); if (w <= 0) return false; data += w; n -= (size_t) w; } return true; };
 			ok = write_all(header.data(), header.size());
-			std::string piece; // the slices of 32 rows are gathered into pieces of a few megabytes: fewer system calls
-			for (size_t c = 0; c < n_chunks && ok; ++c) {
-				if (piece.size() + slices[c].size() > ((size_t) 4 << 20) && !piece.empty()) { ok = write_all(piece.data(), piece.size()); piece.clear(); }
-				if (slices[c].size() >= ((size_t) 4 << 20)) ok = ok && write_all(slices[c].data(), slices[c].size()); else piece += slices[c];
+			for (size_t c = 0; c < n_chunks && ok; ) { // the slices of 32 rows go out a thousand at a time (writev): no copy, few system calls
+				struct iovec v[512]; int nv = 0; size_t bytes = 0;
+				for (; c < n_chunks && nv < 512; ++c) if (!slices[c].empty()) { v[nv].iov_base = (void*) slices[c].data(); v[nv].iov_len = slices[c].size(); bytes += slices[c].size(); ++nv; }
+				for (int first = 0; bytes > 0 && ok; ) {
+					const ssize_t w = ::writev(fd, v + first, nv - first);
+					if (w <= 0) { ok = false; break; }
+					bytes -= (size_t) w;
+					size_t done = (size_t) w; while (first < nv && done >= v[first].iov_len) { done -= v[first].iov_len; ++first; }
+					if (first < nv) { v[first].iov_base = (char*) v[first].iov_base + done; v[first].iov_len -= done; }
+				}
 			}
-			if (ok && !piece.empty()) ok = write_all(piece.data(), piece.size());
 			if (ok && blob_bytes) ok = write_all(blob, blob_bytes);
 		}
 		ok = ::close(fd) == 0 && ok;

@@ -191,6 +191,10 @@ typedef struct arb_evalue_inputs {
 } arb_evalue_inputs;
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
+/* the per-candidate predicates between the e-value and its cutoff, on the resident candidate state: stage 0 = filter_non_coding_neighbors
+ * (source/filter_non_coding_neighbors.cpp), 1 = filter_intragenic_both_exonic (source/filter_intragenic_both_exonic.cpp, -e exonic_fraction),
+ * 2 = filter_min_support (source/filter_min_support.cpp, -S min_support); *remaining = candidates still unfiltered, the function's return value in the reference */
+int arb_filter_simple(arb_ctx* ctx, int32_t stage, float exonic_fraction, int32_t min_support, uint32_t* remaining);
 
 /* The order in which the reference's loops visit the candidates = the iteration order of fusions_t, a std::unordered_map (source/common.hpp:286-314) the
  * candidates were inserted into in id order; estimate_expected_fusions, select_best, recover_isoforms, filter_homologs and the discarded file depend on it.

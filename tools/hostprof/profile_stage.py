@@ -44,7 +44,7 @@ def main():
     sampled("annotate", lambda: p.step(lib.STEP_ANNOTATE))
     for s in range(lib.STEP_ANNOTATE + 1, lib.STEP_COUNT):
         p.step(s)
-    p.events(len(lib.EV_NAMES) - 1)
+    sampled("events", lambda: p.events(len(lib.EV_NAMES) - 1))
     sampled("output", p.write_output)
     p.close()
 
