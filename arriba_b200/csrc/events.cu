@@ -113,6 +113,17 @@ void engine::filter_relative_support(float cutoff) {
 	ex.sync();
 }
 
+void engine::evalue_tallies(u32* out) {
+	dbuf<u32> tally(ET_COUNT); tally.zero(ex, ET_COUNT);
+	dbuf<u8> with_fusion((size_t) annot.n_genes + 1), with_read_through((size_t) annot.n_genes + 1);
+	with_fusion.zero(ex, annot.n_genes); with_read_through.zero(ex, annot.n_genes);
+	evalue_tally_fn fn = {make_state(cands, NULL, NULL), annot.view(), tally.ptr(), with_fusion.ptr(), with_read_through.ptr()};
+	for_each(ex, cands.n, fn);
+	evalue_gene_tally_fn gf = {with_fusion.ptr(), with_read_through.ptr(), tally.ptr()};
+	for_each(ex, annot.n_genes, gf);
+	tally.download(ex, out, ET_COUNT);
+}
+
 u32 engine::filter_simple(int stage, float exonic_fraction, int min_support) {
 	if (stage < SIMPLE_NON_CODING_NEIGHBORS || stage > SIMPLE_MIN_SUPPORT) throw arb_error("arb_filter_simple: unknown stage");
 	dbuf<u32> remaining(1); remaining.zero(ex, 1);

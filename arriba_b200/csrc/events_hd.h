@@ -186,6 +186,34 @@ struct relative_support_fn { // filter_relative_support.cpp:209-223
 	}
 };
 
+// ---- global tallies of the e-value model (filter_relative_support.cpp:62-127): breakpoint locations, intragenic duplications / inversions, spliced pairs, genes
+// with fusions / with read-through fusions, and the largest number of supporting reads (size of the pow tables the caller builds)
+enum { ET_SPLICED = 0, ET_EXONIC, ET_INTRONIC, ET_MIXED, ET_DUPLICATIONS, ET_INVERSIONS, ET_SPLICED_SAME, ET_SPLICED_DIFFERENT, ET_GENES_WITH_FUSIONS, ET_GENES_WITH_READ_THROUGH, ET_MAX_READS, ET_COUNT };
+struct evalue_tally_fn {
+	cand_state c; annot_view an; u32* tally; u8* with_fusion; u8* with_read_through;
+	ARB_HD void operator()(u32 k) const {
+		const u32 g1 = c.gene1[k], g2 = c.gene2[k];
+		const bool dummy = (an.gene_flags[g1] & GF_DUMMY) || (an.gene_flags[g2] & GF_DUMMY);
+		const u32 split = c.split_reads1[k] + c.split_reads2[k], support = split + c.discordant_mates[k];
+		const u8 b = c.bits[k]; const bool unfiltered = c.filter[k] == F_none;
+		if (unfiltered && (c.contig1[k] != c.contig2[k] || c.bp2[k] - c.bp1[k] > 500000) && support >= 2 && split > 0 && !dummy)
+			atomic_add_u32(&tally[(b & (CB_SPLICED1 | CB_SPLICED2)) ? ET_SPLICED : ((b & CB_EXONIC1) && (b & CB_EXONIC2)) ? ET_EXONIC : (!(b & CB_EXONIC1) && !(b & CB_EXONIC2)) ? ET_INTRONIC : ET_MIXED], 1);
+		if (unfiltered && g1 == g2 && split >= 2) { if (c.dir1[k] == UPSTREAM && c.dir2[k] == DOWNSTREAM) atomic_add_u32(&tally[ET_DUPLICATIONS], 1); else if (c.dir1[k] == c.dir2[k]) atomic_add_u32(&tally[ET_INVERSIONS], 1); }
+		if ((b & CB_SPLICED1) && (b & CB_SPLICED2)) atomic_add_u32(&tally[g1 == g2 ? ET_SPLICED_SAME : ET_SPLICED_DIFFERENT], 1);
+		if (!dummy && split > 0) {
+			with_fusion[g1] = 1; with_fusion[g2] = 1;
+			if (c.contig1[k] == c.contig2[k] && c.bp2[k] - c.bp1[k] < 400000 && c.dir1[k] == DOWNSTREAM && c.dir2[k] == UPSTREAM) { with_read_through[g1] = 1; with_read_through[g2] = 1; }
+		}
+#ifdef __CUDA_ARCH__
+		if (support > tally[ET_MAX_READS]) atomicMax(&tally[ET_MAX_READS], support);
+#else
+		if (support > tally[ET_MAX_READS]) tally[ET_MAX_READS] = support;
+#endif
+	}
+};
+struct evalue_gene_tally_fn { const u8* with_fusion; const u8* with_read_through; u32* tally;
+	ARB_HD void operator()(u32 g) const { if (with_fusion[g]) atomic_add_u32(&tally[ET_GENES_WITH_FUSIONS], 1); if (with_read_through[g]) atomic_add_u32(&tally[ET_GENES_WITH_READ_THROUGH], 1); } };
+
 // ---- per-candidate predicates of the event chain that only look at the candidate itself: filter_non_coding_neighbors.cpp, filter_intragenic_both_exonic.cpp,
 // filter_min_support.cpp; `remaining` counts the candidates that are still unfiltered afterwards (the stage's "(remaining=N)" line)
 enum { SIMPLE_NON_CODING_NEIGHBORS = 0, SIMPLE_INTRAGENIC_EXONIC = 1, SIMPLE_MIN_SUPPORT = 2 };

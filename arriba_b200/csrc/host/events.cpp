@@ -249,29 +249,16 @@ void pipeline::estimate_evalues() {
 	check(ctx, arb_partner_counts(ctx, partner_count.data()), "arb_partner_counts");
 	laps.lap("partner counts (device)");
 	arb_evalue_inputs in; memset(&in, 0, sizeof(in));
-	u32 spliced = 0, exonic = 0, intronic = 0, mixed = 0, dups = 0, invs = 0, same = 0, diff = 0;
-	std::vector<u8> with_fusion(ref.genes.size(), 0), with_read_through(ref.genes.size(), 0);
-	for (u32 k = 0; k < e.n; ++k) {
-		const bool dummy = ref.genes[e.gene1[k]].is_dummy || ref.genes[e.gene2[k]].is_dummy;
-		const u32 split = e.split_reads1[k] + e.split_reads2[k];
-		if (e.filter[k] == F_none && (e.contig1[k] != e.contig2[k] || e.bp2[k] - e.bp1[k] > 500000) && e.supporting_reads(k) >= 2 && split > 0 && !dummy) {
-			if (e.spliced1(k) || e.spliced2(k)) ++spliced; else if (e.exonic1(k) && e.exonic2(k)) ++exonic; else if (!e.exonic1(k) && !e.exonic2(k)) ++intronic; else ++mixed;
-		}
-		if (e.filter[k] == F_none && e.gene1[k] == e.gene2[k] && split >= 2) { if (e.dir1[k] == UPSTREAM && e.dir2[k] == DOWNSTREAM) ++dups; else if (e.dir1[k] == e.dir2[k]) ++invs; }
-		if (e.spliced1(k) && e.spliced2(k)) { if (e.gene1[k] == e.gene2[k]) ++same; else ++diff; }
-		if (!dummy && split > 0) {
-			with_fusion[e.gene1[k]] = with_fusion[e.gene2[k]] = 1;
-			if (e.is_read_through(k)) with_read_through[e.gene1[k]] = with_read_through[e.gene2[k]] = 1;
-		}
-	}
+	uint32_t tally[11]; // breakpoint locations, intragenic duplications / inversions, spliced pairs, genes with (read-through) fusions, most supporting reads: csrc/events_hd.h, evalue_tally_fn
+	check(ctx, arb_evalue_tallies(ctx, tally), "arb_evalue_tallies");
+	u32 spliced = tally[0], exonic = tally[1], intronic = tally[2], mixed = tally[3], dups = tally[4], invs = tally[5], same = tally[6], diff = tally[7];
 	if (spliced + exonic + intronic + mixed < 100 || spliced == 0 || exonic == 0 || intronic == 0 || mixed == 0) { spliced = 10; exonic = 65; intronic = 10; mixed = 15; }
 	if (invs + dups < 100) { invs = 1; dups = 1; }
 	if (same + diff < 100) { same = 0; diff = 100; }
-	size_t genes_with_fusions = 0, genes_with_read_through = 0;
-	for (size_t g = 0; g < with_fusion.size(); ++g) { genes_with_fusions += with_fusion[g]; genes_with_read_through += with_read_through[g]; }
+	const size_t genes_with_fusions = tally[8], genes_with_read_through = tally[9];
 	const float rt_fraction = genes_with_fusions == 0 ? 0 : 1.0 * genes_with_read_through / genes_with_fusions;
 	// pow() tables over the integer domains of the reference's expressions (filter_relative_support.cpp:143-205), same libm
-	u32 max_reads = 0; for (u32 k = 0; k < e.n; ++k) max_reads = std::max(max_reads, e.supporting_reads(k));
+	const u32 max_reads = tally[10];
 	std::vector<double> t_reads(max_reads + 2), t_intra(max_reads + 2), t_inter(max_reads + 2), t_s1000(1000), t_s400(400);
 	// the two distance tables (400,000 entries each) do not depend on the sample: filled once per process, on all threads
 	static std::vector<double> t_rt, t_prox; static std::once_flag distance_tables;

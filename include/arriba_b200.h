@@ -191,6 +191,10 @@ typedef struct arb_evalue_inputs {
 } arb_evalue_inputs;
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
+/* global tallies of the e-value model over the resident candidate state (source/filter_relative_support.cpp:62-127), in this order: breakpoints of distant
+ * fusions that are spliced / both exonic / both intronic / mixed, intragenic duplications, intragenic inversions, both-spliced candidates within one gene / between
+ * two genes, genes with fusions, genes with read-through fusions, largest number of supporting reads of a candidate */
+int arb_evalue_tallies(arb_ctx* ctx, uint32_t out[11]);
 /* the per-candidate predicates between the e-value and its cutoff, on the resident candidate state: stage 0 = filter_non_coding_neighbors
  * (source/filter_non_coding_neighbors.cpp), 1 = filter_intragenic_both_exonic (source/filter_intragenic_both_exonic.cpp, -e exonic_fraction),
  * 2 = filter_min_support (source/filter_min_support.cpp, -S min_support); *remaining = candidates still unfiltered, the function's return value in the reference */
