@@ -9,7 +9,7 @@ namespace arb {
 #ifdef ARB_DEVICE_BUILD
 // pass 1 of the re-alignment: MISMAP_LANES lanes per (candidate, read) item, worklist of continuations in shared memory (mismap_hd.h, evaluate_group)
 static const u32 MISMAP_THREADS = 256, MISMAP_WORKLIST = 64;
-template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
+template <u32 LANES> __global__ void __launch_bounds__(MISMAP_THREADS, 3) k_mismap_items(mismap_items it, u32 n_items, int budget, u32* heavy, u32* n_heavy) {
 	const u32 GROUPS = MISMAP_THREADS / LANES;
 	__shared__ realign_work tasks[GROUPS][MISMAP_WORKLIST];
 	__shared__ u32 tops[GROUPS];
