@@ -113,6 +113,7 @@ int arb_set_candidate_lists(arb_ctx* ctx, const uint32_t* l1o, const uint32_t* l
 int arb_merge_adjacent(arb_ctx* ctx, int32_t max_distance, uint32_t* n) { ARB_API_BEGIN(ctx) uint32_t k = ctx->e.merge_adjacent(max_distance); if (n) *n = k; ARB_API_END(ctx) }
 int arb_get_merge_log(arb_ctx* ctx, uint32_t* triples, uint32_t n) { ARB_API_BEGIN(ctx) ctx->e.get_merge_log(triples, n); ARB_API_END(ctx) }
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in) { ARB_API_BEGIN(ctx) ctx->e.estimate_evalues(*in); ARB_API_END(ctx) }
+int arb_select_best(arb_ctx* ctx, uint32_t* remaining) { ARB_API_BEGIN(ctx) const uint32_t r = ctx->e.select_best(); if (remaining) *remaining = r; ARB_API_END(ctx) }
 int arb_evalue_tallies(arb_ctx* ctx, uint32_t out[11]) { ARB_API_BEGIN(ctx) ctx->e.evalue_tallies(out); ARB_API_END(ctx) }
 int arb_filter_simple(arb_ctx* ctx, int32_t stage, float exonic_fraction, int32_t min_support, uint32_t* remaining) { ARB_API_BEGIN(ctx) const uint32_t r = ctx->e.filter_simple(stage, exonic_fraction, min_support); if (remaining) *remaining = r; ARB_API_END(ctx) }
 int arb_filter_relative_support(arb_ctx* ctx, float cutoff) { ARB_API_BEGIN(ctx) ctx->e.filter_relative_support(cutoff); ARB_API_END(ctx) }

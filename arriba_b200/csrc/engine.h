@@ -131,7 +131,7 @@ public:
 	u32 merge_adjacent(i32 max_distance);
 	void get_merge_log(u32* triples, u32 n);
 	void estimate_evalues(const arb_evalue_inputs& in);
-	void filter_relative_support(float cutoff); void filter_multimappers(); u32 filter_simple(int stage, float exonic_fraction, int min_support); void evalue_tallies(u32* out);
+	void filter_relative_support(float cutoff); void filter_multimappers(); u32 filter_simple(int stage, float exonic_fraction, int min_support); void evalue_tallies(u32* out); u32 select_best();
 	void replay_insertion_order(const u32* phase_start, const u64* phase_buckets, u32 n_phases, u32* order_out, u32* rank_out); dbuf<u32> order_rank;
 	void partner_counts(i32* count_out); dbuf<u32> order_seq;
 	// BAM record boundaries and per-worker record lists of an inflated chunk (bamscan.cu)

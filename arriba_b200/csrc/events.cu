@@ -113,6 +113,42 @@ void engine::filter_relative_support(float cutoff) {
 	ex.sync();
 }
 
+u32 engine::select_best() {
+	const u32 C = cands.n;
+	if (C == 0) return 0;
+	if (order_rank.size() < C) throw arb_error("arb_select_best: arb_replay_insertion_order must be called first");
+	if (annot.n_genes >= (1u << 30)) throw arb_error("arb_select_best: too many genes");
+	cand_state s = make_state(cands, NULL, NULL);
+	dbuf<u32> flag((size_t) C + 1);
+	select_eligible_fn el = {s, flag.ptr()};
+	for_each(ex, C, el);
+	exclusive_scan_u32(ex, flag.ptr(), flag.ptr(), C);
+	u32 M = 0; flag.download(ex, &M, 1, C);
+	if (M == 0) return 0;
+	dbuf<u32> ids(M), key(M), tk(M), tv(M);
+	merge_gather_fn mg = {flag.ptr(), ids.ptr()};
+	for_each(ex, C, mg);
+	u32 rank_bits = 1; while (rank_bits < 32 && ((u64) 1 << rank_bits) < C) ++rank_bits;
+	u32 gene_bits = 1; while (gene_bits < 32 && ((u64) 1 << gene_bits) < annot.n_genes) ++gene_bits;
+	for (int which = 0; which < 3; ++which) { // LSD: iteration rank, then the two words of the key
+		select_key_fn kf = {s, order_rank.ptr(), ids.ptr(), key.ptr(), which};
+		for_each(ex, M, kf);
+		radix_sort_pairs_u32(ex, key.ptr(), ids.ptr(), tk.ptr(), tv.ptr(), M, which == 0 ? rank_bits : which == 1 ? gene_bits + 2 : gene_bits);
+	}
+	dbuf<u32> head((size_t) M + 1);
+	select_head_fn hf = {s, ids.ptr(), head.ptr()};
+	for_each(ex, M, hf);
+	exclusive_scan_u32(ex, head.ptr(), head.ptr(), M);
+	u32 G = 0; head.download(ex, &G, 1, M);
+	dbuf<u32> group_start((size_t) G + 1);
+	merge_cluster_start_fn cs = {head.ptr(), group_start.ptr(), M, G};
+	for_each(ex, M, cs);
+	select_group_fn gf = {s, ids.ptr(), group_start.ptr()};
+	for_each(ex, G, gf);
+	ex.sync();
+	return G; // one candidate per group is left
+}
+
 void engine::evalue_tallies(u32* out) {
 	dbuf<u32> tally(ET_COUNT); tally.zero(ex, ET_COUNT);
 	dbuf<u8> with_fusion((size_t) annot.n_genes + 1), with_read_through((size_t) annot.n_genes + 1);

@@ -214,6 +214,47 @@ struct evalue_tally_fn {
 struct evalue_gene_tally_fn { const u8* with_fusion; const u8* with_read_through; u32* tally;
 	ARB_HD void operator()(u32 g) const { if (with_fusion[g]) atomic_add_u32(&tally[ET_GENES_WITH_FUSIONS], 1); if (with_read_through[g]) atomic_add_u32(&tally[ET_GENES_WITH_READ_THROUGH], 1); } };
 
+// ---- select_best (select_best.cpp): the candidates of one (gene1, gene2, direction1, direction2) compete in the order the reference visits them -- the comparison is
+// not a total order, so the order matters: stable sorts by (key, iteration rank), then every group is one sequential scan
+struct select_eligible_fn { cand_state c; u32* flag; ARB_HD void operator()(u32 k) const { flag[k] = c.filter[k] == F_none ? 1u : 0u; } };
+struct select_key_fn { // which: 0 = iteration rank, 1 = low word of the key (gene2 << 4 | directions), 2 = high word (gene1)
+	cand_state c; const u32* rank; const u32* ids; u32* key; int which;
+	ARB_HD void operator()(u32 j) const {
+		const u32 k = ids[j];
+		key[j] = which == 0 ? rank[k] : which == 1 ? (c.gene2[k] << 2 | (c.dir1[k] != 0 ? 2u : 0u) | (c.dir2[k] != 0 ? 1u : 0u)) : c.gene1[k];
+	}
+};
+struct select_head_fn { cand_state c; const u32* ids; u32* head;
+	ARB_HD void operator()(u32 j) const {
+		if (j == 0) { head[j] = 1; return; }
+		const u32 a = ids[j - 1], b = ids[j];
+		head[j] = (c.gene1[a] != c.gene1[b] || c.gene2[a] != c.gene2[b] || (c.dir1[a] != 0) != (c.dir1[b] != 0) || (c.dir2[a] != 0) != (c.dir2[b] != 0)) ? 1u : 0u;
+	}
+};
+struct select_group_fn {
+	cand_state c; const u32* ids; const u32* group_start;
+	ARB_HD u32 rank(u32 k) const { const bool s1 = c.split_reads1[k] != 0, s2 = c.split_reads2[k] != 0, d = c.discordant_mates[k] != 0; return (s1 && s2) ? 3u : ((s1 || s2) && d) ? 2u : (s1 || s2) ? 1u : 0u; }
+	ARB_HD bool challenger_wins(u32 k, u32 b) const { // select_best.cpp:22-60
+		if (rank(k) > rank(b)) return true;
+		if (rank(k) != rank(b)) return false;
+		if (cand_support(c, k) > cand_support(c, b)) return true;
+		if (cand_support(c, k) != cand_support(c, b)) return false;
+		const bool k1 = c.bits[k] & CB_EXONIC1, k2 = c.bits[k] & CB_EXONIC2, b1 = c.bits[b] & CB_EXONIC1, b2 = c.bits[b] & CB_EXONIC2;
+		if ((k1 && !b1) || (k2 && !b2)) return true;
+		if ((!b1 || k1 == b1) && (!b2 || k2 == b2)) {
+			if ((c.dir1[k] == DOWNSTREAM && c.bp1[k] > c.bp1[b]) || (c.dir1[k] == UPSTREAM && c.bp1[k] < c.bp1[b])) return true;
+			if (c.bp1[k] == c.bp1[b]) return (c.dir2[k] == DOWNSTREAM && c.bp2[k] > c.bp2[b]) || (c.dir2[k] == UPSTREAM && c.bp2[k] < c.bp2[b]);
+		}
+		return false;
+	}
+	ARB_HD void operator()(u32 g) const {
+		const u32 lo = group_start[g], hi = group_start[g + 1];
+		u32 best = ids[lo];
+		for (u32 x = lo + 1; x < hi; ++x) if (challenger_wins(ids[x], best)) best = ids[x];
+		for (u32 x = lo; x < hi; ++x) if (ids[x] != best) c.filter[ids[x]] = F_select_best;
+	}
+};
+
 // ---- per-candidate predicates of the event chain that only look at the candidate itself: filter_non_coding_neighbors.cpp, filter_intragenic_both_exonic.cpp,
 // filter_min_support.cpp; `remaining` counts the candidates that are still unfiltered afterwards (the stage's "(remaining=N)" line)
 enum { SIMPLE_NON_CODING_NEIGHBORS = 0, SIMPLE_INTRAGENIC_EXONIC = 1, SIMPLE_MIN_SUPPORT = 2 };

@@ -463,49 +463,12 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	log_remaining("Searching for fusions with spliced split reads");
 }
 
-void pipeline::select_best() { // select_best.cpp
-	auto rank = [&](u32 k) { const bool s1 = ev.split_reads1[k] != 0, s2 = ev.split_reads2[k] != 0, d = ev.discordant_mates[k] != 0; return (s1 && s2) ? 3u : ((s1 || s2) && d) ? 2u : (s1 || s2) ? 1u : 0u; };
-	// candidates of one (gene1, gene2, direction1, direction2) compete in the order the reference visits them (the comparison is not a total order, so the
-	// order matters): sort by (key, iteration rank) instead of the reference's map, then every group is an independent sequential scan
-	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
-	struct entry { u64 key; u32 rank, cand; };
-	std::vector<entry> entries;
-	for (u32 k = 0; k < ev.n; ++k) { // the table front to back: the rank in the iteration order is a column (rank_of), the sort below restores the order
-		if (ev.filter[k] != F_none) continue;
-		const entry x = {(u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) (ev.dir1[k] != 0) << 1 | (u64) (ev.dir2[k] != 0), ev.rank_of[k], k};
-		entries.push_back(x);
-	}
-	parallel_sort(entries, [](const entry& a, const entry& b) { return a.key != b.key ? a.key < b.key : a.rank < b.rank; }, threads);
-	auto challenger_wins = [&](u32 k, u32 b) { // select_best.cpp:22-60
-		if (rank(k) > rank(b)) return true;
-		if (rank(k) != rank(b)) return false;
-		if (ev.supporting_reads(k) > ev.supporting_reads(b)) return true;
-		if (ev.supporting_reads(k) != ev.supporting_reads(b)) return false;
-		if ((ev.exonic1(k) && !ev.exonic1(b)) || (ev.exonic2(k) && !ev.exonic2(b))) return true;
-		if ((!ev.exonic1(b) || ev.exonic1(k) == ev.exonic1(b)) && (!ev.exonic2(b) || ev.exonic2(k) == ev.exonic2(b))) {
-			if ((ev.dir1[k] == DOWNSTREAM && ev.bp1[k] > ev.bp1[b]) || (ev.dir1[k] == UPSTREAM && ev.bp1[k] < ev.bp1[b])) return true;
-			if (ev.bp1[k] == ev.bp1[b]) return (ev.dir2[k] == DOWNSTREAM && ev.bp2[k] > ev.bp2[b]) || (ev.dir2[k] == UPSTREAM && ev.bp2[k] < ev.bp2[b]);
-		}
-		return false;
-	};
-	// a thread takes the groups that START in its slice
-	{
-		const size_t n_entries = entries.size();
-		const int T = std::max(1, std::min(threads, (int) (n_entries / 4096 + 1)));
-		std::vector<std::thread> pool;
-		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() {
-			size_t x = n_entries * t / T; const size_t stop = n_entries * (t + 1) / T;
-			while (x < stop && x > 0 && entries[x].key == entries[x - 1].key) ++x; // the group belongs to the previous slice
-			while (x < stop) {
-				size_t y = x + 1; u32 best = entries[x].cand;
-				for (; y < n_entries && entries[y].key == entries[x].key; ++y) if (challenger_wins(entries[y].cand, best)) best = entries[y].cand;
-				for (size_t z = x; z < y; ++z) if (entries[z].cand != best) ev.filter[entries[z].cand] = F_select_best;
-				x = y;
-			}
-		});
-		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
-	}
-	log_remaining("Selecting best breakpoints from genes with multiple breakpoints");
+void pipeline::select_best() { // select_best.cpp, on the device (csrc/events_hd.h, select_group_fn): stable sorts by (gene pair + directions, iteration rank), one sequential scan per group
+	push_candidate_state();
+	uint32_t remaining = 0;
+	check(ctx, arb_select_best(ctx, &remaining), "arb_select_best");
+	check(ctx, arb_get_candidate_filters(ctx, ev.filter.data()), "arb_get_candidate_filters");
+	std::ostringstream s; s << "Selecting best breakpoints from genes with multiple breakpoints (remaining=" << remaining << ")"; say(s.str());
 }
 
 void pipeline::filter_marginal_read_through() { // filter_marginal_read_through.cpp

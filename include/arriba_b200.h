@@ -191,6 +191,9 @@ typedef struct arb_evalue_inputs {
 } arb_evalue_inputs;
 int arb_estimate_evalues(arb_ctx* ctx, const arb_evalue_inputs* in);
 int arb_filter_relative_support(arb_ctx* ctx, float evalue_cutoff); /* source/filter_relative_support.cpp:209 */
+/* Replaces select_best (source/select_best.cpp): among the unfiltered candidates of one (gene1, gene2, direction1, direction2) the best one stays, visited in the
+ * reference's iteration order (arb_replay_insertion_order must have run); *remaining = candidates still unfiltered */
+int arb_select_best(arb_ctx* ctx, uint32_t* remaining);
 /* global tallies of the e-value model over the resident candidate state (source/filter_relative_support.cpp:62-127), in this order: breakpoints of distant
  * fusions that are spliced / both exonic / both intronic / mixed, intragenic duplications, intragenic inversions, both-spliced candidates within one gene / between
  * two genes, genes with fusions, genes with read-through fusions, largest number of supporting reads of a candidate */
