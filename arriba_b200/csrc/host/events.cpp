@@ -412,7 +412,7 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	stage_laps laps("spliced");
 	// spliced support of every candidate that may back another one up (recover_both_spliced.cpp:104-118); a pure function of the candidate: host threads
 	const u32 NOT_ELIGIBLE = 0xFFFFFFFFu;
-	std::vector<u32> support(ev.n, NOT_ELIGIBLE);
+	column<u32> support(ev.n); // page-locked, written in full by the device
 	ensure_coverage_on_device();
 	check(ctx, arb_set_fragment_filters(ctx, labels.data()), "arb_set_fragment_filters");
 	push_candidate_state();
@@ -421,7 +421,16 @@ void pipeline::recover_both_spliced() { // recover_both_spliced.cpp:64-182
 	auto key_of = [&](u32 k, bool flip) { return (u64) ev.gene1[k] << 34 | (u64) ev.gene2[k] << 4 | (u64) ((ev.dir1[k] != 0) != flip) << 1 | (u64) ((ev.dir2[k] != 0) != flip); };
 	if (ref.genes.size() >= (1u << 30)) throw std::runtime_error("too many genes");
 	std::vector<std::pair<u64, u32> > grouped;
-	for (u32 k = 0; k < ev.n; ++k) if (support[k] != NOT_ELIGIBLE) grouped.push_back(std::make_pair(key_of(k, false), k));
+	{ // the eligible candidates, collected by all threads (the sort below orders them by (key, candidate) whatever the order here)
+		const int T = std::max(1, std::min(threads, (int) (ev.n / 65536 + 1)));
+		std::vector<std::vector<std::pair<u64, u32> > > part(T);
+		std::vector<std::thread> pool;
+		for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { for (u32 k = (u32) ((u64) ev.n * t / T); k < (u32) ((u64) ev.n * (t + 1) / T); ++k) if (support[k] != NOT_ELIGIBLE) part[t].push_back(std::make_pair(key_of(k, false), k)); });
+		for (size_t t = 0; t < pool.size(); ++t) pool[t].join();
+		size_t total = 0; for (int t = 0; t < T; ++t) total += part[t].size();
+		grouped.reserve(total);
+		for (int t = 0; t < T; ++t) grouped.insert(grouped.end(), part[t].begin(), part[t].end());
+	}
 	laps.lap("support of eligible candidates");
 	parallel_sort(grouped, [](const std::pair<u64, u32>& a, const std::pair<u64, u32>& b) { return a < b; }, threads);
 	laps.lap("grouped by gene pair");
@@ -730,9 +739,17 @@ void pipeline::assign_confidence() { // filter_genomic_support.cpp:222-402 (no s
 	// the candidates of every gene (only counted below, so their order does not matter): one CSR table instead of a vector per gene
 	struct gene_list { const u32* p; size_t n; size_t size() const { return n; } u32 operator[](size_t x) const { return p[x]; } };
 	std::vector<u32> by_gene_off(ref.genes.size() + 1, 0), by_gene_items(2 * (size_t) ev.n);
-	for (u32 k = 0; k < ev.n; ++k) { ++by_gene_off[ev.gene1[k] + 1]; ++by_gene_off[ev.gene2[k] + 1]; }
-	for (size_t g = 0; g < ref.genes.size(); ++g) by_gene_off[g + 1] += by_gene_off[g];
-	{ std::vector<u32> at(by_gene_off.begin(), by_gene_off.end() - 1); for (u32 k = 0; k < ev.n; ++k) { by_gene_items[at[ev.gene1[k]]++] = k; by_gene_items[at[ev.gene2[k]]++] = k; } }
+	{ // counting sort by gene on all threads: a histogram per slice of the table, offsets by (gene, slice), every slice fills its own places
+		const size_t G = ref.genes.size();
+		const int T = std::max(1, std::min(std::min(threads, 16), (int) (ev.n / 65536 + 1))); // a histogram of G counters per slice
+		std::vector<std::vector<u32> > count(T, std::vector<u32>(G, 0));
+		auto slice = [&](int t, u32& lo, u32& hi) { lo = (u32) ((u64) ev.n * t / T); hi = (u32) ((u64) ev.n * (t + 1) / T); };
+		{ std::vector<std::thread> pool; for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { u32 lo, hi; slice(t, lo, hi); std::vector<u32>& c = count[t]; for (u32 k = lo; k < hi; ++k) { ++c[ev.gene1[k]]; ++c[ev.gene2[k]]; } }); for (size_t t = 0; t < pool.size(); ++t) pool[t].join(); }
+		u32 at = 0;
+		for (size_t g = 0; g < G; ++g) { by_gene_off[g] = at; for (int t = 0; t < T; ++t) { const u32 c = count[t][g]; count[t][g] = at; at += c; } }
+		by_gene_off[G] = at;
+		{ std::vector<std::thread> pool; for (int t = 0; t < T; ++t) pool.emplace_back([&, t]() { u32 lo, hi; slice(t, lo, hi); std::vector<u32>& c = count[t]; for (u32 k = lo; k < hi; ++k) { by_gene_items[c[ev.gene1[k]]++] = k; by_gene_items[c[ev.gene2[k]]++] = k; } }); for (size_t t = 0; t < pool.size(); ++t) pool[t].join(); }
+	}
 	auto by_gene = [&](u32 g) { gene_list l = {by_gene_items.data() + by_gene_off[g], by_gene_off[g + 1] - by_gene_off[g]}; return l; };
 	enum { LOW = 0, MEDIUM = 1, HIGH = 2 };
 	parallel_rows(threads, ev.n, [&](u32 k) {
