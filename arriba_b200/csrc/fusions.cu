@@ -30,15 +30,19 @@ struct probe_bucket_fn { // bucket of every candidate pass B looks at (0xFFFFFFF
 	}
 };
 // lists of the one-pass variant: from the candidates' stretches of the scratch buffer to their places in the CSR list, one warp per candidate
-__global__ void __launch_bounds__(256) k_walk_b_pack(const u32* active_cands, u32 n_active, const u32* scratch, u32 stretch, const u32* listd_off, u32* listd) {
+__global__ void __launch_bounds__(256) k_walk_b_pack(const u32* active_cands, u32 n_active, const u32* scratch, const u32* stretch_off, const u32* listd_off, u32* listd) {
 	const u32 warp = (blockIdx.x * 256u + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
 	if (warp >= n_active) return;
 	const u32 cand = active_cands[warp], lo = listd_off[cand], n = listd_off[cand + 1] - lo;
-	for (u32 x = lane; x < n; x += 32) listd[lo + x] = scratch[(size_t) warp * stretch + x];
+	for (u32 x = lane; x < n; x += 32) listd[lo + x] = scratch[stretch_off[warp] + x];
 }
+struct stretch_size_fn { const u32* active_cands; const u32* bucket_of_cand; const u32* bseg_off; u64 cap; u32* size;
+	ARB_HD void operator()(u32 w) const { const u32 b = bucket_of_cand[active_cands[w]]; const u64 n = bseg_off[b + 1] - bseg_off[b]; size[w] = (u32) (n < cap ? n : cap); } };
+static bool sf_fits(u32 n_active, const dbuf<u32>&, u32 threshold) { return (u64) n_active * 2 * (u64) threshold < (1ull << 32); } // the scan adds in 32 bits: only when even the largest possible total fits
 static const u32 WALK_B_THREADS = 256;
 __global__ void __launch_bounds__(WALK_B_THREADS) k_walk_b(const u32* active_cands, u32 n_active, const u32* bucket_of_cand, bucket_columns bc, const u32* bseg_off,
                                                             frag_view f, annot_view an, cand_out c, const u32* listd_off, u32* listd, u32* need_swap, i32 max_mate_gap, u32 threshold, u32 fill) {
+	// fill: 0 = count, 1 = fill the CSR list (listd_off per candidate), 2 = count and fill in ONE walk: listd_off then holds the start of each WARP's stretch of a scratch buffer
 	const u32 warp = (blockIdx.x * WALK_B_THREADS + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
 	if (warp >= n_active) return;
 	const u32 FULL = 0xFFFFFFFFu;
@@ -51,7 +55,7 @@ __global__ void __launch_bounds__(WALK_B_THREADS) k_walk_b(const u32* active_can
 	const bool intragenic = g1 == g2 || (bp1 >= g2s - 10000 && bp1 <= g2e + 10000 && bp2 >= g1s - 10000 && bp2 <= g1e + 10000);
 	u32 listed = 0, counted = 0;
 	i32 an1 = c.anchor1[cand], an2 = c.anchor2[cand];
-	u32 w = fill == 2 ? warp * (2 * threshold) : fill ? listd_off[cand] : 0; // fill == 2: one pass, the list goes to the candidate's own stretch of a scratch buffer (a list never exceeds 2 x threshold)
+	u32 w = fill == 2 ? listd_off[warp] : fill ? listd_off[cand] : 0;
 	const u32 seg_end = bseg_off[b + 1];
 	bool done = false;
 	for (u32 base = bseg_off[b]; base < seg_end && !done; base += 32) {
@@ -227,14 +231,17 @@ void engine::find_fusions(i32 max_mate_gap) {
 		bucket_columns bcols = {o_bp1.ptr(), o_bp2.ptr(), o_frag.ptr(), o_label.ptr()};
 		const u32 blocks = (u32) (((u64) A * 32 + WALK_B_THREADS - 1) / WALK_B_THREADS);
 		// A list holds at most 2 x threshold mates (fusions.cpp:400-406: labelled mates are listed while fewer than `threshold` are, unlabelled ones until `threshold`
-		// of them are): with a stretch of that size per candidate ONE walk writes the lists, a copy packs them. Huge thresholds (-U) keep the count / fill walks.
-		const bool one_pass = A != 0 && (u64) A * 2 * T <= ((u64) 1 << 28) && getenv("ARB_WALK_B_TWO_PASS") == NULL;
-		dbuf<u32> stretches; if (one_pass) stretches.alloc((size_t) A * 2 * T);
-		if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, NULL, one_pass ? stretches.ptr() : NULL, need_swap.ptr(), max_mate_gap, T, one_pass ? 2 : 0); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+		// of them are) and never more than its bucket has: with a stretch of that size per candidate ONE walk writes the lists, a copy packs them. When the stretches
+		// would not fit (huge -U, or millions of candidates on big buckets) the count / fill walks remain.
+		dbuf<u32> stretch_off((size_t) A + 1), stretches; u32 S = 0;
+		if (A) { stretch_size_fn sf = {active_cands.ptr(), bucket_of_cand.ptr(), bseg_off.ptr(), 2 * (u64) T, stretch_off.ptr()}; for_each(ex, A, sf); exclusive_scan_u32(ex, stretch_off.ptr(), stretch_off.ptr(), A); stretch_off.download(ex, &S, 1, A); }
+		const bool one_pass = A != 0 && S < (1u << 28) && sf_fits(A, bseg_off, T) && getenv("ARB_WALK_B_TWO_PASS") == NULL;
+		if (one_pass) stretches.alloc((size_t) S + 1);
+		if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, one_pass ? stretch_off.ptr() : NULL, one_pass ? stretches.ptr() : NULL, need_swap.ptr(), max_mate_gap, T, one_pass ? 2 : 0); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
 		exclusive_scan_u32(ex, n_listd.ptr(), cands.listd_off.ptr(), C);
 		u32 LD = 0; cands.listd_off.download(ex, &LD, 1, C);
 		cands.n_listd = LD; cands.listd.ensure(LD);
-		if (one_pass) { k_walk_b_pack<<<blocks, 256, 0, ex.stream>>>(active_cands.ptr(), A, stretches.ptr(), 2 * T, cands.listd_off.ptr(), cands.listd.ptr()); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
+		if (one_pass) { k_walk_b_pack<<<blocks, 256, 0, ex.stream>>>(active_cands.ptr(), A, stretches.ptr(), stretch_off.ptr(), cands.listd_off.ptr(), cands.listd.ptr()); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
 		else if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, cands.listd_off.ptr(), cands.listd.ptr(), need_swap.ptr(), max_mate_gap, T, 1); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
 	}
 #else
