@@ -182,19 +182,57 @@ struct worker {
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
 	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size; u32 last_fragment;
 	void park_waiting() { if (waiting_ptr) { pending.emplace(waiting_key, std::vector<u8>(waiting_ptr, waiting_ptr + waiting_size)); waiting_ptr = NULL; } } // before the chunk buffer is recycled
-	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), last_fragment(0xFFFFFFFFu), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true) {}
+	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), last_fragment(0xFFFFFFFFu), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true), key_hash_hint(0) {}
 
-	u32 fragment(const std::string& name, bool* created = NULL) {
+	u32 fragment(const std::string& name, bool* created = NULL, u64 hashed = 0) {
 		// the records of one fragment follow each other in a collated BAM: remember the last answer before walking the table
 		if (last_fragment != 0xFFFFFFFFu) { const frag_build& f = frags[last_fragment]; if (f.name_len == name.size() && memcmp(names.data() + f.name_off, name.data(), name.size()) == 0) { if (created) *created = false; return last_fragment; } }
-		const u32 id = fragment_lookup(name, created);
+		const u32 id = fragment_lookup(name, created, hashed);
 		last_fragment = id;
 		return id;
 	}
-	u32 fragment_lookup(const std::string& name, bool* created) {
+	// Look-ahead of the record loop (read_chimeric_alignments below): the table walk of a record's fragment -- name slot, fragment, its name and last alignment --
+	// is a chain of cache misses in tables of gigabytes. The loop computes the key hash of the record five steps ahead and requests the links of the chain one
+	// step apart, so that process() finds them in the cache. Requests only: nothing here changes what process() does.
+	u64 key_hash_hint; // hash of the key of the record process() is about to see (0: none)
+	static u64 key_hash(const char* name, size_t n_name, i64 hit_index) { // FNV-1a over "<qname>,<HI>", folded like fragment_lookup does
+		u64 h = 1469598103934665603ULL;
+		for (size_t i = 0; i < n_name; ++i) { h ^= (u8) name[i]; h *= 1099511628211ULL; }
+		h ^= (u8) ','; h *= 1099511628211ULL;
+		char digits[24]; int n = 0; u64 v = hit_index < 0 ? 0 - (u64) hit_index : (u64) hit_index; do { digits[n++] = (char) ('0' + v % 10); v /= 10; } while (v);
+		if (hit_index < 0) { h ^= (u8) '-'; h *= 1099511628211ULL; }
+		while (n > 0) { h ^= (u8) digits[--n]; h *= 1099511628211ULL; }
+		h ^= h >> 29;
+		return h; // 0 (one key in 2^64) reads as "no hint": fragment_lookup then hashes the key itself
+	}
+	u64 ahead_hash(const u8* p, u32 size) { // the key hash of a record that has not been processed yet; also asks for its coverage windows
+		rec_t r;
+		if (!parse_record(p, size, r)) return 0;
+		if ((r.flag & BF_UNMAP) || ((r.flag & BF_PAIRED) && (r.flag & BF_MUNMAP))) return 0;
+		i64 hit_index = 1;
+		const u8* hi = find_aux(r, 'H', 'I');
+		if (hi) hit_index = aux_int(hi); else if (r.flag & BF_SECONDARY) return 0;
+		if (r.tid >= 0 && (size_t) r.tid < tid_to_contig->size() && !(r.flag & BF_SUPPLEMENTARY)) {
+			const u32 contig = (*tid_to_contig)[r.tid];
+			if (contig < cov->coverage.size() && !cov->coverage[contig].empty()) { const size_t w = (size_t) (r.pos < 0 ? 0 : r.pos) / 20; if (w < cov->coverage[contig].size()) { __builtin_prefetch(&cov->coverage[contig][w], 1); __builtin_prefetch(&cov->coverage[contig][std::min(w + 5, cov->coverage[contig].size() - 1)], 1); } }
+		}
+		const u64 h = key_hash(r.qname, strnlen(r.qname, r.l_qname), hit_index);
+		if (!name_slots.empty()) __builtin_prefetch(&name_slots[(size_t) h & (name_slots.size() - 1)]);
+		return h;
+	}
+	void ahead_fragment(u64 h) const { if (h && !name_slots.empty()) { const u32 id = name_slots[(size_t) h & (name_slots.size() - 1)]; if (id && id <= frags.size()) __builtin_prefetch(&frags[id - 1]); } }
+	void ahead_tail(u64 h) const {
+		if (!h || name_slots.empty()) return;
+		const u32 id = name_slots[(size_t) h & (name_slots.size() - 1)];
+		if (!id || id > frags.size()) return;
+		const frag_build& f = frags[id - 1];
+		if (f.name_off < names.size()) __builtin_prefetch(names.data() + f.name_off);
+		if (f.tail >= 0 && (size_t) f.tail < alns.size()) __builtin_prefetch(&alns[f.tail], 1);
+	}
+	u32 fragment_lookup(const std::string& name, bool* created, u64 hashed = 0) {
 		if (name_slots.empty()) name_slots.assign(1u << 12, 0);
-		u64 h = 1469598103934665603ULL; for (size_t i = 0; i < name.size(); ++i) { h ^= (u8) name[i]; h *= 1099511628211ULL; }
-		h ^= h >> 29; // the low bits of the same hash chose the worker
+		u64 h = hashed;
+		if (!h) { h = 1469598103934665603ULL; for (size_t i = 0; i < name.size(); ++i) { h ^= (u8) name[i]; h *= 1099511628211ULL; } h ^= h >> 29; } // the low bits of the same hash chose the worker
 		size_t mask = name_slots.size() - 1, at = (size_t) h & mask;
 		for (; name_slots[at] != 0; at = (at + 1) & mask) {
 			const frag_build& f = frags[name_slots[at] - 1];
@@ -477,13 +515,13 @@ struct worker {
 		r.tid = (*tid_to_contig)[r.tid];
 
 		if (r.flag & BF_SUPPLEMENTARY) {
-			if (clipped_at_correct_end(r)) add_alignment(fragment(key), r, true); else ++malformed;
+			if (clipped_at_correct_end(r)) add_alignment(fragment(key, NULL, key_hash_hint), r, true); else ++malformed;
 			no_chimeric = false;
 			return;
 		}
 		if ((*interesting_contig)[r.tid]) ++mapped_reads;
 		if ((r.flag & BF_PAIRED) && !(r.flag & BF_PROPER)) { // discordant mate
-			add_alignment(fragment(key), r, false);
+			add_alignment(fragment(key, NULL, key_hash_hint), r, false);
 			no_chimeric = false;
 			if (!opt->external_duplicate_marking || !(r.flag & BF_DUP)) add_coverage(r, NULL, true, true); // all flag bits cleared (`flag &= !BAM_FPAIRED`)
 			return;
@@ -524,7 +562,7 @@ struct worker {
 		}
 		bool is_read_through = false;
 		if ((find_aux(r, 'S', 'A') && clipped_at_correct_end(r)) || (m && find_aux(*m, 'S', 'A') && clipped_at_correct_end(*m))) {
-			const u32 f = fragment(key);
+			const u32 f = fragment(key, NULL, key_hash_hint);
 			add_alignment(f, r, false);
 			if (m) add_alignment(f, *m, false);
 			no_chimeric = false;
@@ -801,6 +839,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	if (bam.blocks.empty()) fail("failed to read SAM header");
 	prepare(chunks[0], NULL);
 	bool reserved_ahead = false;
+	const bool look_ahead = getenv("ARB_INGEST_LOOKAHEAD") == NULL || atoi(getenv("ARB_INGEST_LOOKAHEAD")) != 0;
 	for (int cur = 0;; cur ^= 1) {
 		chunk_t& c = chunks[cur];
 		std::string prepare_error; std::thread next;
@@ -814,11 +853,21 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 					worker& w = workers[t];
 					const u8* base = c.buf.data();
 					const u32* const mine = c.shard_rec_off.data(); const u32 stop = c.shard_begin[t + 1];
-					for (u32 x = c.shard_begin[t]; x < stop; ++x) {
-						if (x + 3 < stop) { const u8* ahead = base + mine[x + 3]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); } // fixed fields + name, and where the tags of a 2x101 / 2x151 record start
+					u64 ring[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // key hashes of the records ahead (worker::ahead_hash)
+					const u32 first = c.shard_begin[t];
+					for (u32 x = first; x < stop; ++x) {
+						if (look_ahead) {
+							if (x + 9 < stop) { const u8* ahead = base + mine[x + 9]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); } // fixed fields + name, and where the tags of a 2x101 / 2x151 record start
+							if (x == first) for (u32 y = x; y < x + 5 && y < stop; ++y) ring[y & 7] = w.ahead_hash(base + mine[y] + 4, rd32(base + mine[y]));
+							if (x + 5 < stop) ring[(x + 5) & 7] = w.ahead_hash(base + mine[x + 5] + 4, rd32(base + mine[x + 5]));
+							if (x + 3 < stop) w.ahead_fragment(ring[(x + 3) & 7]);
+							if (x + 1 < stop) w.ahead_tail(ring[(x + 1) & 7]);
+							w.key_hash_hint = ring[x & 7];
+						} else if (x + 3 < stop) { const u8* ahead = base + mine[x + 3]; __builtin_prefetch(ahead); __builtin_prefetch(ahead + 64); __builtin_prefetch(ahead + 192); __builtin_prefetch(ahead + 256); }
 						const u64 off = mine[x];
 						w.process(base + off + 4, rd32(base + off));
 					}
+					w.key_hash_hint = 0;
 					w.park_waiting();
 				}
 			});

@@ -328,16 +328,25 @@ def main():
     peak, peak_src = measured_peak()
     jobs = 1 if (sharded or world == 1) else world
 
-    def kernel_entry(name, ms, alg_bytes, unit_note, traffic_key):
-        traffic = None
+    def kernel_entry(name, ms, alg_bytes, unit_note, traffic_key, l2_key=None):
+        traffic = None; t = {}
         try:
             t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             traffic = t.get(args.workload, {}).get(traffic_key)
         except Exception:
             pass
         ach = alg_bytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
-        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": ms, "algorithmic_bytes_are": unit_note}
+        entry = {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                 "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": ms, "algorithmic_bytes_are": unit_note}
+        if l2_key:   # explanation for a gather-bound kernel: bytes its loads request from L1/L2 per launch (32-byte sectors, from the same ncu capture) over the live kernel time
+            try:
+                l2 = t.get(args.workload, {}).get(l2_key)
+                if l2 and ms > 0:
+                    entry["l1_l2_request_gbs"] = l2 / (ms * 1e-3) / 1e9
+                    entry["bound_note"] = "gather bound: dependent 4-byte lookups, each a 32-byte sector; DRAM traffic ~ algorithmic bytes, the limiter is the sector rate through L1/L2"
+            except Exception:
+                pass
+        return entry
 
     mean = lambda f: sum(f(r["tm"]) for r in results) / len(results)
     kernels = [
@@ -346,7 +355,7 @@ def main():
         kernel_entry("cascade_sequences (mismatches + low entropy, one launch)", mean(lambda t: t.cascade_sequences_ms), int(tm.cascade_algorithmic_bytes[1]),
                      "SURVEY 8(d): sequences 3 bit/base + gathered reference 2 bit/base + CIGARs + 11 B/alignment of the queued fragments", "cascade_sequences_dram_bytes"),
         kernel_entry("mismappers pass 1 (re-alignment, one launch)", mean(lambda t: t.mismappers_pass1_ms), int(getattr(tm, "mismapper_algorithmic_bytes", 0)),
-                     "SURVEY 8(d): per re-aligned sequence 3l/8 + 8(l-8) + 4*hits + l/2", "mismappers_pass1_dram_bytes"),
+                     "SURVEY 8(d): per re-aligned sequence 3l/8 + 8(l-8) + 4*hits + l/2", "mismappers_pass1_dram_bytes", "mismappers_pass1_l2_bytes"),
     ]
     dominant = max(kernels, key=lambda k: k["kernel_ms"])
     device_ms = {"annotate": tm.annotate_ms, "order": tm.order_ms, "multimappers": tm.multimappers_ms, "in_vitro": tm.in_vitro_ms, "duplicates": tm.duplicates_ms, "classify": tm.classify_ms, "read_filters_total": tm.read_filters_ms, "find_fusions_total": tm.find_fusions_ms, "h2d": tm.h2d_ms,
