@@ -235,7 +235,7 @@ void engine::find_fusions(i32 max_mate_gap) {
 		// would not fit (huge -U, or millions of candidates on big buckets) the count / fill walks remain.
 		dbuf<u32> stretch_off((size_t) A + 1), stretches; u32 S = 0;
 		if (A) { stretch_size_fn sf = {active_cands.ptr(), bucket_of_cand.ptr(), bseg_off.ptr(), 2 * (u64) T, stretch_off.ptr()}; for_each(ex, A, sf); exclusive_scan_u32(ex, stretch_off.ptr(), stretch_off.ptr(), A); stretch_off.download(ex, &S, 1, A); }
-		const bool one_pass = A != 0 && S < (1u << 28) && sf_fits(A, bseg_off, T) && getenv("ARB_WALK_B_TWO_PASS") == NULL;
+		const bool one_pass = A != 0 && S < (1u << 31) && sf_fits(A, bseg_off, T) && getenv("ARB_WALK_B_TWO_PASS") == NULL;
 		if (one_pass) stretches.alloc((size_t) S + 1);
 		if (A) { k_walk_b<<<blocks, WALK_B_THREADS, 0, ex.stream>>>(active_cands.ptr(), A, bucket_of_cand.ptr(), bcols, bseg_off.ptr(), f, an, cob, one_pass ? stretch_off.ptr() : NULL, one_pass ? stretches.ptr() : NULL, need_swap.ptr(), max_mate_gap, T, one_pass ? 2 : 0); ARB_CUDA_CHECK(cudaGetLastError()); ++stats().kernels; }
 		exclusive_scan_u32(ex, n_listd.ptr(), cands.listd_off.ptr(), C);

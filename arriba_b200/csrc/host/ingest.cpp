@@ -67,6 +67,19 @@ void host_block_trim() {
 void set_host_block_backend(void* (*alloc)(size_t), void (*release)(void*)) { g_backend_alloc = alloc; g_backend_free = release; }
 
 static void fail(const std::string& m) { throw std::runtime_error(m); }
+// Tables of hundreds of megabytes that are visited all over (name slots, fragments, alignments, coverage windows): on 4 KiB pages nearly every visit also misses
+// the TLB. Where the kernel offers transparent huge pages on request (THP "madvise"), ask for them; elsewhere the call does nothing.
+static void advise_huge(const void* p, size_t bytes) {
+#ifdef MADV_HUGEPAGE
+	const size_t huge = (size_t) 2 << 20;
+	static const bool enabled = getenv("ARB_HUGE_PAGES") == NULL || atoi(getenv("ARB_HUGE_PAGES")) != 0;
+	if (!enabled || p == NULL || bytes < 4 * huge) return;
+	const uintptr_t lo = ((uintptr_t) p + huge - 1) & ~(uintptr_t) (huge - 1), hi = ((uintptr_t) p + bytes) & ~(uintptr_t) (huge - 1);
+	if (hi > lo) madvise((void*) lo, hi - lo, MADV_HUGEPAGE);
+#else
+	(void) p; (void) bytes;
+#endif
+}
 static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 enum { BF_PAIRED = 1, BF_PROPER = 2, BF_UNMAP = 4, BF_MUNMAP = 8, BF_REVERSE = 16, BF_READ1 = 64, BF_SECONDARY = 256, BF_DUP = 1024, BF_SUPPLEMENTARY = 2048 };
@@ -80,7 +93,7 @@ void coverage_windows::resize(const refdata& ref) {
 	coverage.resize(nc); starts.resize(nc); ends.resize(nc);
 	for (size_t c = 0; c < nc; ++c) if (ref.has_sequence((u32) c)) {
 		const size_t w = ref.seq_len[c] / 20 + 2;
-		if (coverage[c].size() < w) { coverage[c].resize(w, 0); starts[c].resize(w, 0); ends[c].resize(w, 0); }
+		if (coverage[c].size() < w) { coverage[c].reserve(w); advise_huge(coverage[c].data(), w * sizeof(coverage[c][0])); coverage[c].resize(w, 0); starts[c].resize(w, 0); ends[c].resize(w, 0); }
 	}
 }
 bool coverage_windows::fragment_starts_here(u32 contig, i32 start, i32 end) const {
@@ -247,7 +260,7 @@ struct worker {
 		return id;
 	}
 	void resize_name_slots(size_t slots) { // a power of two
-		std::vector<u32> bigger(slots, 0); const size_t mask = bigger.size() - 1;
+		std::vector<u32> bigger; bigger.reserve(slots); advise_huge(bigger.data(), slots * sizeof(u32)); bigger.assign(slots, 0); const size_t mask = bigger.size() - 1;
 		for (size_t k = 0; k < frags.size(); ++k) {
 			const frag_build& g = frags[k];
 			u64 hh = 1469598103934665603ULL; for (u32 i = 0; i < g.name_len; ++i) { hh ^= (u8) names[g.name_off + i]; hh *= 1099511628211ULL; }
@@ -264,7 +277,7 @@ struct worker {
 		auto grow = [&](auto& v) {
 			typedef typename std::remove_reference<decltype(v)>::type::value_type value_type;
 			const size_t want = std::min((size_t) ((double) v.size() * factor) + 1024, std::max(v.size(), cap_bytes / sizeof(value_type)));
-			if (want > v.capacity()) { try { v.reserve(want); } catch (const std::bad_alloc&) {} } // a hint: no address space, no reservation
+			if (want > v.capacity()) { try { v.reserve(want); advise_huge(v.data(), v.capacity() * sizeof(value_type)); } catch (const std::bad_alloc&) {} } // a hint: no address space, no reservation
 		};
 		grow(names); grow(cigars); grow(seqs); grow(alns); grow(frags);
 		const size_t expected = std::min((size_t) ((double) frags.size() * factor), std::max(frags.size(), cap_bytes / sizeof(frag_build)));
@@ -911,7 +924,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 			std::vector<norm_aln> m;
 			const size_t n_frags = w.frags.size(); // fixed: only alignments and CIGARs are appended below
 			keep[t].reserve(n_frags);
-			w.norm_alns.reserve(w.alns.size()); w.norm_cigars.reserve(w.cigars.size()); // normalisation drops alignments, it never adds one: no regrowth, and the parsed pools are not copied
+			w.norm_alns.reserve(w.alns.size()); w.norm_cigars.reserve(w.cigars.size()); advise_huge(w.norm_alns.data(), w.norm_alns.capacity() * sizeof(aln_build)); advise_huge(w.norm_cigars.data(), w.norm_cigars.capacity() * sizeof(u32)); // normalisation drops alignments, it never adds one: no regrowth, and the parsed pools are not copied
 			for (size_t f = 0; f < n_frags; ++f) {
 				// a fragment's alignments were stored as its records arrived, far apart: the chain of the fragments a few steps ahead is requested early
 				if (f + 12 < n_frags && w.frags[f + 12].head >= 0) { __builtin_prefetch(&w.alns[w.frags[f + 12].head]); __builtin_prefetch(w.names.data() + w.frags[f + 12].name_off); }
