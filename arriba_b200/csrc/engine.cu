@@ -225,6 +225,13 @@ void engine::finish_push(u64 n_gene_ids) {
 	sequence_bytes = bases * 3 / 8 + bases * 2 / 8 + (push_cigar_ops + n_alignments) * 4 + n_alignments * 11 + (u64) n * 2;
 	timings.classify_algorithmic_bytes = head_bytes + sequence_bytes;
 	push_open = false;
+#ifdef ARB_DEVICE_BUILD
+	{ // realign() (mismap_hd.h) recurses once per continuation, each at least 8 read bases further on, reads of 300 bases and more are not re-aligned: frames of < 512 B
+		const size_t levels = std::min<size_t>(frags.max_seq_len, 300) / 8 + 4, wanted = 1024 + 512 * levels;
+		size_t have = 0;
+		if (cudaDeviceGetLimit(&have, cudaLimitStackSize) == cudaSuccess && have < wanted) ARB_CUDA_CHECK(cudaDeviceSetLimit(cudaLimitStackSize, wanted));
+	}
+#endif
 }
 
 unsigned long engine::genome_size() const { // filter_mismatches.cpp:105-108

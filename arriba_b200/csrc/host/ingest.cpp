@@ -156,6 +156,7 @@ static const u8* find_aux(const rec_t& r, char a, char b) { // returns pointer t
 			}
 			default: return NULL;
 		}
+		if (next > r.aux_end) return NULL; // truncated field: its payload lies past the record (htslib reports corrupted aux data and returns no tag)
 		if (hit) return v;
 		s = next;
 	}
