@@ -308,8 +308,8 @@ def main():
         if golden:
             got = {"fusions.tsv": md5_of(out_tsv), "fusions.discarded.tsv": md5_of(out_disc)}
             parity = {"checked": True, "ok": got == {k: golden[k] for k in got}, "md5": got, "reference_md5": {k: golden[k] for k in got}, "source": golden.get("source")}
-        else:
-            parity = {"checked": False, "reason": "no committed reference md5 for this workload"}
+        else:   # the sums of what the steps wrote are recorded all the same: the reference's run of a large workload takes hours on one core and may be compared afterwards
+            parity = {"checked": False, "reason": "no committed reference md5 for this workload", "md5": {"fusions.tsv": md5_of(out_tsv), "fusions.discarded.tsv": md5_of(out_disc)}}
 
     secondary = None
     if dist and not args.no_secondary and e2e_s < 40.0:   # the other multi-GPU mode, a few steps
