@@ -39,7 +39,7 @@ static void tune_allocator() {
 	mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20);
 }
 
-void arb_release_host_memory(void) { arb::host::host_block_trim(); }
+void arb_release_host_memory(void) { arb::host::host_block_trim(); arb::host::release_worker_cache(); }
 
 int arb_pipeline_create(arb_pipeline** out, const arb_run_options* o) {
 	tune_allocator();

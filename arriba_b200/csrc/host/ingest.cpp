@@ -182,6 +182,7 @@ static bool clipped_at_correct_end(const rec_t& r) {
 struct aln_build { u8 supplementary, first_in_pair, forward; u16 contig; i32 start, end; u32 cigar_off, cigar_cnt; u64 seq_off; u32 seq_len; i32 next; };
 struct frag_build { u64 name_off; u32 name_len; i32 head, tail; u32 count; u8 single_end, duplicate; };
 
+struct final_frag { u32 worker; u32 frag; u64 prefix0, prefix1; };
 struct name_ref { const char* p; u32 len; };
 struct name_hash { size_t operator()(const std::string& s) const { u64 h = 1469598103934665603ULL; for (size_t i = 0; i < s.size(); ++i) { h ^= (u8) s[i]; h *= 1099511628211ULL; } return (size_t) h; } };
 
@@ -196,7 +197,17 @@ struct worker {
 	u64 mapped_reads, malformed, missing_hi, records; std::vector<u64> viral_reads; bool no_chimeric;
 	std::string key, clip_chars, waiting_key; const u8* waiting_ptr; u32 waiting_size; u32 last_fragment;
 	void park_waiting() { if (waiting_ptr) { pending.emplace(waiting_key, std::vector<u8>(waiting_ptr, waiting_ptr + waiting_size)); waiting_ptr = NULL; } } // before the chunk buffer is recycled
+	std::vector<final_frag> keep; // the fragments that survive slot normalisation, with their name prefixes
 	worker(): cov(NULL), waiting_ptr(NULL), waiting_size(0), last_fragment(0xFFFFFFFFu), mapped_reads(0), malformed(0), missing_hi(0), records(0), no_chimeric(true), key_hash_hint(0) {}
+	// A worker's pools are gigabytes that a sample touches for the first time page by page (a tenth of the ingest's CPU time went into those faults, tools/hostprof
+	// on the GPU box): the workers of a finished sample are kept for the next one -- contents dropped, memory kept (arb_release_host_memory gives it back).
+	void recycle() {
+		names.clear(); cigars.clear(); seqs.clear(); alns.clear(); frags.clear(); norm_alns.clear(); norm_cigars.clear(); keep.clear(); pending.clear(); viral_reads.clear();
+		std::fill(name_slots.begin(), name_slots.end(), 0u);
+		ref = NULL; opt = NULL; tid_to_contig = NULL; interesting_contig = NULL; viral_contig = NULL; cov = NULL;
+		mapped_reads = malformed = missing_hi = records = 0; no_chimeric = true; waiting_ptr = NULL; waiting_size = 0; last_fragment = 0xFFFFFFFFu; key_hash_hint = 0;
+		key.clear(); clip_chars.clear(); waiting_key.clear();
+	}
 
 	u32 fragment(const std::string& name, bool* created = NULL, u64 hashed = 0) {
 		// the records of one fragment follow each other in a collated BAM: remember the last answer before walking the table
@@ -592,6 +603,24 @@ struct worker {
 };
 
 
+// workers of finished samples, kept for the next one (one set; a set is only reused by a run with the same number of workers)
+static std::mutex g_worker_cache_lock; static std::vector<worker>* g_worker_cache = NULL;
+static std::vector<worker>* take_workers(int T) {
+	std::vector<worker>* set = NULL;
+	{ std::lock_guard<std::mutex> g(g_worker_cache_lock); set = g_worker_cache; g_worker_cache = NULL; }
+	if (set && (int) set->size() != T) { std::thread([set]() { delete set; }).detach(); set = NULL; } // unmapping gigabytes takes most of a second: not on this thread
+	return set ? set : new std::vector<worker>(T);
+}
+static void put_workers(std::vector<worker>* set) { // recycled by a helper thread: clearing the name slots touches every page of them once
+	std::thread([set]() {
+		for (size_t t = 0; t < set->size(); ++t) (*set)[t].recycle();
+		std::vector<worker>* old = NULL;
+		{ std::lock_guard<std::mutex> g(g_worker_cache_lock); old = g_worker_cache; g_worker_cache = set; }
+		delete old;
+	}).detach();
+}
+void release_worker_cache() { std::vector<worker>* old = NULL; { std::lock_guard<std::mutex> g(g_worker_cache_lock); old = g_worker_cache; g_worker_cache = NULL; } delete old; }
+
 // ------------------------------------------------------------------------------------------- BGZF container
 struct bgzf_file {
 	const u8* data; size_t size; int fd;
@@ -759,7 +788,6 @@ frag_view fragment_table::view() {
 	return v;
 }
 
-struct final_frag { u32 worker; u32 frag; u64 prefix0, prefix1; };
 
 void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const ingest_options& opt, fragment_table& out, coverage_windows& coverage, ingest_stats& stats) {
 	const int T = std::min(255, std::max(1, opt.threads)); // shard ids are bytes
@@ -774,7 +802,8 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	// chunks of ~128 MiB of decompressed data, each a whole number of BGZF blocks; a record that straddles a chunk
 	// boundary is carried over to the front of the next buffer
 	const u64 chunk_target = getenv("ARB_CHUNK_BYTES") ? (u64) atoll(getenv("ARB_CHUNK_BYTES")) : 128ull << 20; // env: test hook (many small chunks)
-	std::vector<worker> workers(T);
+	struct worker_set { std::vector<worker>* set; explicit worker_set(int n): set(take_workers(n)) {} ~worker_set() { if (set) put_workers(set); } } held(T); // back to the cache on every way out
+	std::vector<worker>& workers = *held.set;
 	std::vector<u16> tid_to_contig; std::vector<u8> interesting_contig, viral_contig;
 	bool header_done = false;
 	u64 total_records = 0;
@@ -917,14 +946,13 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	if (stats.mapped_reads == 0) fail("no normal reads found");
 
 	// ---- slot normalisation, rejection of malformed fragments ----
-	std::vector<std::vector<final_frag> > keep(T);
 	std::vector<u64> malformed_by_worker(T, 0);
 	parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) {
 		for (size_t t = lo; t < hi; ++t) {
 			worker& w = workers[t];
 			std::vector<norm_aln> m;
 			const size_t n_frags = w.frags.size(); // fixed: only alignments and CIGARs are appended below
-			keep[t].reserve(n_frags);
+			w.keep.reserve(n_frags);
 			w.norm_alns.reserve(w.alns.size()); w.norm_cigars.reserve(w.cigars.size()); advise_huge(w.norm_alns.data(), w.norm_alns.capacity() * sizeof(aln_build)); advise_huge(w.norm_cigars.data(), w.norm_cigars.capacity() * sizeof(u32)); // normalisation drops alignments, it never adds one: no regrowth, and the parsed pools are not copied
 			for (size_t f = 0; f < n_frags; ++f) {
 				// a fragment's alignments were stored as its records arrived, far apart: the chain of the fragments a few steps ahead is requested early
@@ -949,7 +977,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 				final_frag ff; ff.worker = (u32) t; ff.frag = (u32) f; ff.prefix0 = ff.prefix1 = 0;
 				const char* nm = w.names.data() + fb.name_off;
 				for (u32 k = 0; k < 16 && k < fb.name_len; ++k) { u64& dst = k < 8 ? ff.prefix0 : ff.prefix1; dst |= (u64) (u8) nm[k] << (56 - 8 * (k & 7)); }
-				keep[t].push_back(ff);
+				w.keep.push_back(ff);
 			}
 		}
 	});
@@ -962,9 +990,9 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	// ---- name order: std::string::compare semantics == unsigned byte-wise comparison, shorter string first on a common prefix ----
 	std::vector<final_frag, default_init_allocator<final_frag> > order;
 	{ // every worker's list goes to its own stretch of the table, copied (and first touched) by its own thread
-		std::vector<size_t> at(T + 1, 0); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + keep[t].size();
+		std::vector<size_t> at(T + 1, 0); for (int t = 0; t < T; ++t) at[t + 1] = at[t] + workers[t].keep.size();
 		order.resize(at[T]);
-		parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) { std::copy(keep[t].begin(), keep[t].end(), order.begin() + at[t]); std::vector<final_frag>().swap(keep[t]); } });
+		parallel_for(T, (size_t) T, [&](int, size_t lo, size_t hi) { for (size_t t = lo; t < hi; ++t) { std::copy(workers[t].keep.begin(), workers[t].keep.end(), order.begin() + at[t]); workers[t].keep.clear(); } });
 	}
 	auto name_less = [&](const final_frag& a, const final_frag& b) {
 		if (a.prefix0 != b.prefix0) return a.prefix0 < b.prefix0;
@@ -1084,12 +1112,7 @@ void read_chimeric_alignments(const std::string& bam_path, refdata& ref, const i
 	}
 	stats.t_finalize = now_s() - tf;
 	lap("multimapper flags");
-	// the per-worker pools (gigabytes) are handed to a helper thread: unmapping them costs most of a second and nothing below needs to wait for it
-	{
-		std::vector<worker>* doomed = new std::vector<worker>();
-		doomed->swap(workers);
-		std::thread([doomed]() { delete doomed; }).detach();
-	}
+	// the workers go back to the cache when `held` leaves scope (their contents are dropped by a helper thread)
 	lap("free worker state");
 }
 

@@ -28,6 +28,7 @@ struct coverage_windows { // 20 bp windows (read_stats.hpp:14)
 // them), and a process that runs sample after sample would pay it for gigabytes of columns every time. Blocks of 1 MiB and more go back to a free list per
 // size class (steps of 25 %) instead of the C library; host_block_trim() (arb_release_host_memory) hands them to the system.
 void* host_block_get(size_t bytes, size_t& granted);
+void release_worker_cache(); // the ingest keeps the workers' pools of a finished sample for the next one (ingest.cpp)
 void host_block_put(void* p, size_t granted);
 void host_block_trim();
 // where fresh blocks come from (default: malloc). The CUDA library installs cudaHostAlloc / cudaFreeHost (capi.cu); a NULL result falls back to malloc.

@@ -9,7 +9,7 @@ def main():
     for l in open(path):
         m, off, _ = l.rstrip("\n").split("\t")
         mods[m.split("/")[-1]] += 1
-        if m == lib:
+        if m == lib or m.split("/")[-1] == lib.split("/")[-1]:
             offs[off] += 1
     total = sum(mods.values())
     print("samples", total, dict(mods.most_common(6)))
