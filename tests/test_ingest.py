@@ -159,3 +159,30 @@ def test_front_end_hostsim_many_chunks(worlds, hostsim_lib, monkeypatch, threads
     name = "chunks_" + "_".join(x.strip("-") for x in extra) if extra else "small"
     kw = dict(seed=5, extra=extra) if extra else {}
     check_front_end(worlds.get(name, **kw), hostsim_lib, threads=threads)
+
+
+def test_pools_are_kept_between_samples_and_can_be_released(worlds, hostsim_lib, tmp_path):
+    """the ingest keeps the workers' pools of a finished sample (csrc/host/ingest.cpp, take_workers / put_workers): a second sample in the same process, a third
+    after arb_release_host_memory, and one with another number of workers must all read the same table"""
+    import numpy as np
+    from arriba_b200 import lib as L
+    world = worlds.get("small")
+    def table(threads):
+        p = L.Pipeline(world.prefix + ".bam", world.prefix + ".gtf", world.prefix + ".fa", threads=threads, lib_path=hostsim_lib,
+                       output=str(tmp_path / "f.tsv"), discarded=str(tmp_path / "d.tsv"))
+        p.step(L.STEP_LOAD_REFERENCE); p.step(L.STEP_INGEST)
+        f = p.fragments()
+        mine = ("n_aln", "fflags", "contig", "start", "end", "cigar_off", "cigar_cnt", "seq_off", "seq_len", "cigar", "seq", "name_off")   # what the ingest itself fills (the gene columns belong to the annotation)
+        out = {k: np.array(f[k], copy=True) for k in mine}
+        out["names"] = np.frombuffer(f["names_blob"], dtype=np.uint8).copy()
+        p.close()
+        return out
+    first = table(4)
+    again = table(4)
+    L.load(hostsim_lib).arb_release_host_memory()
+    after_release = table(4)
+    other_width = table(3)
+    for other in (again, after_release, other_width):
+        assert sorted(other) == sorted(first)
+        for k in first:
+            assert np.array_equal(first[k], other[k]), k
