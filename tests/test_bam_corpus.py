@@ -1,0 +1,76 @@
+"""BAM files from a second, independent writer (tests/bamtools.py: plain-Python reading of SAMv1 4.1 / 4.2) through the oracle and through the product's
+ingest. The file means the same to the reference as the synth-written one it was made from (same core fields, CIGARs, sequences, HI and SA), so
+ (1) the oracle must write the same two output files for both -- a check of the oracle's htslib shim against a writer that shares no code with it --
+ (2) the product's front end must reproduce the oracle's fragment table, coverage and labels field by field from the transcoded file, and
+ (3) both output files must come out byte-identical,
+while every auxiliary type, tag order and integer width, missing qualities, and BGZF members of 1 byte .. 64 KiB (stored / deflated, empty ones in the
+middle, records and their length words split over members, no EOF marker) pass through the readers."""
+import os, shutil
+import pytest
+import bamtools, worldutil
+from test_ingest import check_front_end
+from test_e2e import check_e2e
+
+
+def transcoded_world(worlds, tmp_root, seed, eof=True, **kw):
+    base = worlds.get(**kw) if kw else worlds.get("small")
+    d = os.path.join(str(tmp_root), "transcoded_%d_%d" % (seed, eof)); os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, "w")
+    for ext in (".fa", ".gtf"):
+        if not os.path.exists(prefix + ext):
+            os.symlink(base.prefix + ext, prefix + ext)
+    if not os.path.exists(prefix + ".bam"):
+        n = bamtools.transcode(base.prefix + ".bam", prefix + ".bam", seed, eof)
+        assert n > 1000
+        worldutil.run_oracle(prefix, os.path.join(d, "oracle"))
+    return base, worldutil.World(prefix, os.path.join(d, "oracle"))
+
+
+@pytest.fixture(scope="module")
+def corpus(worlds, tmp_path_factory):
+    root = tmp_path_factory.mktemp("bam_corpus")
+    return {(seed, eof): transcoded_world(worlds, root, seed, eof) for seed, eof in ((1, True), (2, False))}
+
+
+def test_python_reader_round_trip(worlds, tmp_path):
+    """the reader/writer pair itself: records survive split -> join unchanged, and a re-framed file reads back the same"""
+    base = worlds.get("small")
+    text, refs, bodies = bamtools.read_bam(base.prefix + ".bam")
+    assert all(bamtools.join_record(bamtools.split_record(b)) == b for b in bodies[:5000])
+    import random
+    out = os.path.join(str(tmp_path), "again.bam")
+    bamtools.write_bam(out, text, refs, bodies[:20000], random.Random(5))
+    assert bamtools.read_bam(out) == (text, refs, bodies[:20000])
+
+
+@pytest.mark.parametrize("which", [(1, True), (2, False)])
+def test_oracle_reads_the_transcoded_file_the_same(corpus, which):
+    base, tr = corpus[which]
+    for name in ("fusions.tsv", "fusions.discarded.tsv"):
+        assert open(os.path.join(tr.outdir, name), "rb").read() == open(os.path.join(base.outdir, name), "rb").read(), name
+    assert len(open(os.path.join(tr.outdir, "fusions.tsv")).read().split("\n")) > 5
+
+
+@pytest.mark.parametrize("which,threads", [((1, True), 3), ((2, False), 1)])
+def test_front_end_hostsim_transcoded(corpus, hostsim_lib, which, threads):
+    check_front_end(corpus[which][1], hostsim_lib, threads=threads)
+
+
+def test_front_end_hostsim_transcoded_small_chunks(corpus, hostsim_lib, monkeypatch):
+    """with the file read in chunks of a few members and the record boundaries found piecewise"""
+    monkeypatch.setenv("ARB_CHUNK_BYTES", "50000"); monkeypatch.setenv("ARB_SCAN_MIN_BYTES", "700")
+    check_front_end(corpus[(1, True)][1], hostsim_lib, threads=6)
+
+
+def test_e2e_hostsim_transcoded(corpus, hostsim_lib, tmp_path):
+    check_e2e(corpus[(2, False)][1], hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_front_end_cuda_transcoded(corpus, cuda_lib):
+    check_front_end(corpus[(1, True)][1], cuda_lib, threads=8)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_transcoded(corpus, cuda_lib, tmp_path):
+    check_e2e(corpus[(2, False)][1], cuda_lib, tmp_path, threads=8)
