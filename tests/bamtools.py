@@ -185,3 +185,102 @@ def transcode(src, dst, seed, eof=True):
     text = text + b"@CO\ttranscoded by tests/bamtools.py\n@CO\t" + b"HI:i:1 SA:Z:x " * rng.randint(0, 50) + b"\n"
     write_bam(dst, text, refs, [transcode_record(b, rng) for b in bodies], rng, eof)
     return len(bodies)
+
+
+# ---- record-level mutations: files the aligner would not write, which the reference nevertheless has defined behaviour for (flag tests, the malformed-
+# fragment rules of read_chimeric_alignments.cpp:451-495, supplementary clips at the wrong end, missing HI, orphans). The oracle says what comes out.
+C_M, C_S, C_H, C_EQ, C_X = 0, 4, 5, 7, 8
+
+
+def _cigar_ops(r):
+    return list(struct.unpack("<%dI" % (len(r["cigar"]) // 4), r["cigar"]))
+
+
+def _set_cigar(r, ops):
+    r["cigar"] = struct.pack("<%dI" % len(ops), *ops)
+
+
+def _replace_op(r, which, src, dst):
+    """turns the first / last CIGAR operation from `src` into `dst` (same length); False if it is not a `src`"""
+    ops = _cigar_ops(r)
+    if not ops or (ops[which] & 15) != src:
+        return False
+    ops[which] = (ops[which] >> 4) << 4 | dst
+    _set_cigar(r, ops)
+    return True
+
+
+MUTATIONS = ("unmapped", "mate_unmapped", "clear_proper", "set_proper", "drop_record", "double_supplementary", "clip_to_other_end", "hard_clip_supplementary",
+             "hard_clip_primary", "single_end", "secondary_without_hi", "other_hi", "match_ops", "supplementary_elsewhere", "flip_strand", "swap_mate_flags", "third_primary",
+             "drop_sa", "negative_hi")
+
+
+def mutate_fragment(recs, kind, rng, n_ref):
+    """recs: list of split records of one read name (modified in place); returns the new list"""
+    pick = rng.randrange(len(recs)); r = recs[pick]
+    supp = [x for x in recs if x["flag"] & 0x800]; prim = [x for x in recs if not x["flag"] & 0x800]
+    if kind == "unmapped":
+        r["flag"] |= 0x4
+    elif kind == "mate_unmapped":
+        r["flag"] |= 0x8
+    elif kind == "clear_proper":
+        for x in recs: x["flag"] &= ~0x2
+    elif kind == "set_proper":
+        for x in recs: x["flag"] |= 0x2
+    elif kind == "drop_record":
+        del recs[pick]
+    elif kind == "double_supplementary" and supp:
+        recs.append(dict(supp[0]))
+    elif kind == "clip_to_other_end" and supp:
+        ops = _cigar_ops(supp[0]); ops.reverse(); _set_cigar(supp[0], ops)
+    elif kind == "hard_clip_supplementary" and supp:
+        _replace_op(supp[0], 0, C_S, C_H); _replace_op(supp[0], -1, C_S, C_H)   # legal (STAR's HardClip); the sequence is kept, which the reference never looks at
+    elif kind == "hard_clip_primary" and prim:
+        x = rng.choice(prim)
+        if not _replace_op(x, 0, C_S, C_H): _replace_op(x, -1, C_S, C_H)
+    elif kind == "single_end":
+        for x in recs: x["flag"] &= ~(0x1 | 0x2 | 0x8 | 0x20 | 0x40 | 0x80)
+    elif kind == "secondary_without_hi":
+        r["flag"] |= 0x100; r["aux"] = [a for a in r["aux"] if a[0] != b"HI"]
+    elif kind == "other_hi":
+        r["aux"] = [a for a in r["aux"] if a[0] != b"HI"] + [(b"HI", b"C", bytes([rng.randint(2, 9)]))]
+    elif kind == "negative_hi":
+        for x in recs: x["aux"] = [a for a in x["aux"] if a[0] != b"HI"] + [(b"HI", b"i", struct.pack("<i", -3))]
+    elif kind == "match_ops":
+        ops = _cigar_ops(r); _set_cigar(r, [(o >> 4) << 4 | rng.choice([C_EQ, C_X]) if (o & 15) == C_M else o for o in ops])
+    elif kind == "supplementary_elsewhere" and supp:
+        supp[0]["tid"] = rng.randrange(n_ref); supp[0]["pos"] = rng.randint(1000, 50000)
+    elif kind == "flip_strand":
+        r["flag"] ^= 0x10
+    elif kind == "swap_mate_flags":
+        for x in recs:
+            if x["flag"] & 0xC0 in (0x40, 0x80): x["flag"] ^= 0xC0
+    elif kind == "third_primary" and prim:
+        recs.append(dict(rng.choice(prim)))
+    elif kind == "drop_sa":
+        for x in recs: x["aux"] = [a for a in x["aux"] if a[0] != b"SA"]
+    return recs
+
+
+def mutate(src, dst, seed, rate=0.15, kinds=MUTATIONS):
+    """rewrites `src` with one mutation applied to a fraction `rate` of its read names; returns {kind: how many}"""
+    rng = random.Random(seed)
+    text, refs, bodies = read_bam(src)
+    recs = [split_record(b) for b in bodies]
+    by_name = {}
+    for i, r in enumerate(recs):
+        by_name.setdefault(r["qname"], []).append(i)
+    replaced = {}; tally = {}
+    for name, idx in by_name.items():
+        if rng.random() >= rate:
+            continue
+        kind = rng.choice(kinds)
+        replaced[idx[0]] = mutate_fragment([recs[i] for i in idx], kind, rng, len(refs))
+        for i in idx[1:]:
+            replaced[i] = []
+        tally[kind] = tally.get(kind, 0) + 1
+    out = []
+    for i, r in enumerate(recs):
+        out += [join_record(x) for x in replaced[i]] if i in replaced else [bodies[i]]
+    write_bam(dst, text, refs, out, rng)
+    return tally

@@ -74,3 +74,42 @@ def test_front_end_cuda_transcoded(corpus, cuda_lib):
 @pytest.mark.gpu
 def test_e2e_cuda_transcoded(corpus, cuda_lib, tmp_path):
     check_e2e(corpus[(2, False)][1], cuda_lib, tmp_path, threads=8)
+
+
+# ---- files an aligner would not write: flag combinations, malformed fragments, orphans, wrong-end clips, missing / odd HI (bamtools.MUTATIONS) ----
+def mutated_world(worlds, root, mutation_seed, rate, **kw):
+    base = worlds.get(**kw) if kw else worlds.get("small")
+    d = os.path.join(str(root), "mutated_%d" % mutation_seed); os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, "w")
+    for ext in (".fa", ".gtf"):
+        os.symlink(base.prefix + ext, prefix + ext)
+    tally = bamtools.mutate(base.prefix + ".bam", prefix + ".bam", mutation_seed, rate)
+    assert set(tally) == set(bamtools.MUTATIONS) and min(tally.values()) > 50, tally
+    worldutil.run_oracle(prefix, os.path.join(d, "oracle"))
+    w = worldutil.World(prefix, os.path.join(d, "oracle"))
+    assert "SAM records were malformed" in open(os.path.join(w.outdir, "stderr.txt")).read()   # the repair / rejection rules did fire in the reference
+    return w
+
+
+@pytest.fixture(scope="module")
+def mutated(worlds, tmp_path_factory):
+    root = tmp_path_factory.mktemp("bam_mutated")
+    return {"collated": mutated_world(worlds, root, 21, 0.3),
+            "shuffled": mutated_world(worlds, root, 22, 0.3, name="l151", read_length=151, seed=7, extra=("--shuffle", "--varnames"))}
+
+
+@pytest.mark.parametrize("which,threads", [("collated", 1), ("collated", 5), ("shuffled", 4)])
+def test_front_end_hostsim_mutated_records(mutated, hostsim_lib, which, threads):
+    """a third of the read names carry one of 19 kinds of damage; the fragment table, the malformed count's consequences, coverage and labels equal the reference's"""
+    check_front_end(mutated[which], hostsim_lib, threads=threads)
+
+
+@pytest.mark.parametrize("which", ["collated", "shuffled"])
+def test_e2e_hostsim_mutated_records(mutated, hostsim_lib, tmp_path, which):
+    check_e2e(mutated[which], hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_e2e_cuda_mutated_records(mutated, cuda_lib, tmp_path):
+    check_front_end(mutated["collated"], cuda_lib, threads=8)
+    check_e2e(mutated["shuffled"], cuda_lib, tmp_path, threads=8)
