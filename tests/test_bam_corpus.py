@@ -113,3 +113,35 @@ def test_e2e_hostsim_mutated_records(mutated, hostsim_lib, tmp_path, which):
 def test_e2e_cuda_mutated_records(mutated, cuda_lib, tmp_path):
     check_front_end(mutated["collated"], cuda_lib, threads=8)
     check_e2e(mutated["shuffled"], cuda_lib, tmp_path, threads=8)
+
+
+if __name__ == "__main__":   # python tests/test_bam_corpus.py SEED N : N random worlds (test_random_worlds.py), damaged and re-framed, through oracle and product
+    import sys, random, tempfile
+    from arriba_b200 import _build
+    from test_random_worlds import random_world_arguments
+    rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
+    with tempfile.TemporaryDirectory() as d:
+        cache = worldutil.WorldCache(d); bad = 0
+        for k in range(int(sys.argv[2]) if len(sys.argv) > 2 else 10):
+            kw = random_world_arguments(rng)
+            base = cache.get("w%d" % k, **kw)
+            wd = os.path.join(d, "damaged%d" % k); os.makedirs(wd)
+            prefix = os.path.join(wd, "w")
+            for ext in (".fa", ".gtf"):
+                os.symlink(base.prefix + ext, prefix + ext)
+            rate = rng.choice([0.02, 0.2, 0.6])
+            bamtools.mutate(base.prefix + ".bam", prefix + ".tmp.bam", rng.randint(1, 10 ** 6), rate)
+            bamtools.transcode(prefix + ".tmp.bam", prefix + ".bam", rng.randint(1, 10 ** 6)); os.remove(prefix + ".tmp.bam")
+            try:
+                worldutil.run_oracle(prefix, os.path.join(wd, "oracle"), dump=False)
+            except RuntimeError as e:   # e.g. every chimeric fragment damaged: the reference stops with an error; the product must stop with the same one
+                print(k, "reference stops:", str(e).strip().splitlines()[-1][:200], flush=True)
+                continue
+            w = worldutil.World(prefix, os.path.join(wd, "oracle"))
+            try:
+                check_e2e(w, _build.build_hostsim(), wd, threads=rng.choice([1, 3, 6])); ok = True
+            except AssertionError as e:
+                ok = False; print(str(e)[:1000])
+            print(k, "identical" if ok else "DIFFERENT", rate, kw, flush=True); bad += not ok
+            shutil.rmtree(wd)
+        sys.exit(1 if bad else 0)
