@@ -215,7 +215,7 @@ MUTATIONS = ("unmapped", "mate_unmapped", "clear_proper", "set_proper", "drop_re
              "drop_sa", "negative_hi")
 
 
-def mutate_fragment(recs, kind, rng, n_ref):
+def mutate_fragment(recs, kind, rng, refs):
     """recs: list of split records of one read name (modified in place); returns the new list"""
     pick = rng.randrange(len(recs)); r = recs[pick]
     supp = [x for x in recs if x["flag"] & 0x800]; prim = [x for x in recs if not x["flag"] & 0x800]
@@ -249,7 +249,7 @@ def mutate_fragment(recs, kind, rng, n_ref):
     elif kind == "match_ops":
         ops = _cigar_ops(r); _set_cigar(r, [(o >> 4) << 4 | rng.choice([C_EQ, C_X]) if (o & 15) == C_M else o for o in ops])
     elif kind == "supplementary_elsewhere" and supp:
-        supp[0]["tid"] = rng.randrange(n_ref); supp[0]["pos"] = rng.randint(1000, 50000)
+        supp[0]["tid"] = rng.randrange(len(refs)); supp[0]["pos"] = rng.randint(1000, max(1000, refs[supp[0]["tid"]][1] - 2000))   # inside the contig: past its end the reference reads beyond its coverage vector (undefined)
     elif kind == "flip_strand":
         r["flag"] ^= 0x10
     elif kind == "swap_mate_flags":
@@ -275,7 +275,7 @@ def mutate(src, dst, seed, rate=0.15, kinds=MUTATIONS):
         if rng.random() >= rate:
             continue
         kind = rng.choice(kinds)
-        replaced[idx[0]] = mutate_fragment([recs[i] for i in idx], kind, rng, len(refs))
+        replaced[idx[0]] = mutate_fragment([recs[i] for i in idx], kind, rng, refs)
         for i in idx[1:]:
             replaced[i] = []
         tally[kind] = tally.get(kind, 0) + 1
