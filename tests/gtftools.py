@@ -68,3 +68,23 @@ def damage_gtf(src, dst, seed, rate, contig_lengths, kinds=KINDS):
         rng.shuffle(body); out = head + body
     open(dst, "w").write("\n".join(out))
     return tally
+
+
+def rewrite_fasta(names, seqs, dst, seed):
+    """The assembly as another tool might have written it (assembly.cpp:29-60 reads the name up to the first blank, upper-cases, skips empty lines): descriptions
+    after the names, ragged line lengths, empty lines, lower / mixed case, IUPAC codes, unplaced contigs before and after, no newline at the end."""
+    rng = random.Random(seed)
+    with open(dst, "wb") as f:
+        f.write(b">GL000220.1 unplaced scaffold\n" + b"ACGT" * 500 + b"\n")
+        for name, s in zip(names, seqs):
+            b = bytearray(s)
+            for _ in range(len(b) // 3000):
+                b[rng.randrange(len(b))] = rng.choice(b"RYSWKMBDHV")
+            lo = rng.randrange(len(b)); b[lo: lo + len(b) // 3] = bytes(b[lo: lo + len(b) // 3]).lower()
+            f.write(b">" + name.encode() + rng.choice([b"", b" dna:chromosome REF", b"\tAC:CM000663.2  gi:568336023"]) + b"\n")
+            at = 0
+            while at < len(b):
+                n = rng.randint(1, 200); f.write(bytes(b[at: at + n]) + b"\n"); at += n
+                if rng.random() < 0.02:
+                    f.write(b"\n")
+        f.write(b">KI270728.1\n" + b"TTTTGGGG" * 300 + b"\n>chrUn_x\n\n>last\nACGTNNNN")

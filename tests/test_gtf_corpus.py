@@ -1,5 +1,6 @@
 """Damaged annotation files (tests/gtftools.py: 18 kinds the reference's GTF reader has defined behaviour for, annotation.cpp:113-377) through the oracle and
-through the product: gene and exon tables, annotated fragment table, labels and both output files must be the reference's."""
+through the product (one of the two worlds also with a re-written assembly file: descriptions, ragged and empty lines, mixed case, IUPAC codes,
+unplaced contigs): gene and exon tables, annotated fragment table, labels and both output files must be the reference's."""
 import os
 import pytest
 import gtftools, worldutil
@@ -15,8 +16,11 @@ def damaged(worlds, tmp_path_factory):
         lengths = {n: len(s) for n, s in zip(names, seqs)}
         d = os.path.join(str(tmp_path_factory.mktemp("gtf_corpus")), "w%d" % seed); os.makedirs(d)
         prefix = os.path.join(d, "w")
-        for ext in (".fa", ".bam"):
-            os.symlink(base.prefix + ext, prefix + ext)
+        os.symlink(base.prefix + ".bam", prefix + ".bam")
+        if seed == 31:   # and the assembly as another tool might have written it
+            gtftools.rewrite_fasta(names, seqs, prefix + ".fa", seed)
+        else:
+            os.symlink(base.prefix + ".fa", prefix + ".fa")
         tally = gtftools.damage_gtf(base.prefix + ".gtf", prefix + ".gtf", seed, rate, lengths)
         assert set(tally) == set(gtftools.KINDS), tally
         worldutil.run_oracle(prefix, os.path.join(d, "oracle"))
