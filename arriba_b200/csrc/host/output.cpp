@@ -47,7 +47,8 @@ struct pile_column {
 	enum { N_SYMBOLS = 20 };
 	unsigned int single[N_SYMBOLS]; std::map<std::string, unsigned int> other;
 	pile_column() { for (int k = 0; k < N_SYMBOLS; ++k) single[k] = 0; }
-	static int index_of(char c) { static signed char table[256]; static bool ready = false; if (!ready) { for (int k = 0; k < 256; ++k) table[k] = -1; for (int k = 0; k < N_SYMBOLS; ++k) table[(unsigned char) symbols()[k]] = (signed char) k; ready = true; } return table[(unsigned char) c]; }
+	struct symbol_table { signed char at[256]; symbol_table() { for (int k = 0; k < 256; ++k) at[k] = -1; for (int k = 0; k < N_SYMBOLS; ++k) at[(unsigned char) symbols()[k]] = (signed char) k; } };
+	static int index_of(char c) { static const symbol_table table; return table.at[(unsigned char) c]; } // a local static: initialised once, also when several threads arrive together
 	void add(char c, unsigned int n = 1) { const int x = index_of(c); if (x >= 0) single[x] += n; else other[std::string(1, c)] += n; }
 	void add(const std::string& s, unsigned int n = 1) { if (s.size() == 1) add(s[0], n); else other[s] += n; }
 	unsigned int total() const { unsigned int t = 0; for (int k = 0; k < N_SYMBOLS; ++k) t += single[k]; for (std::map<std::string, unsigned int>::const_iterator it = other.begin(); it != other.end(); ++it) t += it->second; return t; }
@@ -457,14 +458,10 @@ struct writer {
 	// ---- peptide (annotate_protein_domains.cpp:164-400)
 	static char translate(const std::string& triplet) {
 		// all three letters plain bases: table built once from the general rule below
-		static char table[64]; static bool ready = false;
+		struct codon_table { char aa[64]; codon_table() { static const char L[] = "ACGT"; for (int x = 0; x < 64; ++x) { std::string t3; t3 += L[x >> 4]; t3 += L[x >> 2 & 3]; t3 += L[x & 3]; aa[x] = translate_general(t3); } } };
+		static const codon_table table; // initialised once, by whichever row-formatting thread comes first (the language guards the initialisation of a local static)
 		auto code = [](char c) { switch (c) { case 'A': case 'a': return 0; case 'C': case 'c': return 1; case 'G': case 'g': return 2; case 'T': case 't': return 3; default: return -1; } };
-		if (!ready) { // benign race: every thread writes the same values
-			static const char L[] = "ACGT";
-			for (int x = 0; x < 64; ++x) { std::string t3; t3 += L[x >> 4]; t3 += L[x >> 2 & 3]; t3 += L[x & 3]; table[x] = translate_general(t3); }
-			ready = true;
-		}
-		if (triplet.size() == 3) { const int a = code(triplet[0]), b = code(triplet[1]), c = code(triplet[2]); if (a >= 0 && b >= 0 && c >= 0) return table[a << 4 | b << 2 | c]; }
+		if (triplet.size() == 3) { const int a = code(triplet[0]), b = code(triplet[1]), c = code(triplet[2]); if (a >= 0 && b >= 0 && c >= 0) return table.aa[a << 4 | b << 2 | c]; }
 		return translate_general(triplet);
 	}
 	static char translate_general(const std::string& triplet) {
