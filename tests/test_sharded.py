@@ -71,7 +71,7 @@ def test_partition_is_closed_and_balanced(worlds, hostsim_lib):
     assert sizes.min() > 0.5 * n / parts, sizes
 
 
-@pytest.mark.parametrize("n_ranks", [2, 3])
+@pytest.mark.parametrize("n_ranks", [2, 3, 8])   # 8 = the largest world the scaling run uses
 def test_sharded_equals_single_hostsim(worlds, hostsim_lib, tmp_path, n_ranks):
     w = worlds.get("cfg5", **dict(scale=0.002, genes=800, breakpoints=400, fragments=40000, extra=("--mismapper-frac", "0.3", "--paralog-frac", "0.15")))
     want = single(w, hostsim_lib, tmp_path)
