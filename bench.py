@@ -260,13 +260,24 @@ def main():
         ctx = p.context()
         st = p.stats(); tm = ctx.timings() if ctx.h else L.Timings()
         n_cand = int(st.n_candidates)
-        d2h = n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * int(st.n_fragments)  # candidate columns + list offsets + labels (lists add ~4 B per supporting read)
+        # bytes that cross PCIe in a step, from the sizes of what is copied: up = the inflated BAM chunks (the device finds the record boundaries and deals the records to the
+        # parsing threads) + the fragment table; down = the record lists, the annotation columns, candidate columns + list offsets + labels, and the text of the
+        # discarded-fusions file, which the device formats (the strings of the fusions rows add a few MB)
+        nf = int(st.n_fragments)
+        try:
+            bam_bytes = os.path.getsize(prefix + ".bam"); disc_bytes = os.path.getsize(out_disc) if (rank == 0 or not sharded) else 0
+        except OSError:
+            bam_bytes = disc_bytes = 0
+        d2h_parts = {"record_lists": 4 * int(st.n_records), "annotation_columns": (3 + 12 + 6 + 4 * 4) * nf,   # flags, offsets, counts, ~4 gene ids per fragment
+                     "candidates_lists_labels": n_cand * 46 + 3 * 4 * (n_cand + 1) + 2 * nf, "discarded_rows_text": disc_bytes}
+        h2d_parts = {"bam_chunks": bam_bytes, "fragment_table": int(tm.h2d_bytes)}
+        d2h = sum(d2h_parts.values())
         dev_ms = tm.annotate_ms + tm.read_filters_ms + tm.find_fusions_ms + tm.order_ms + tm.merge_adjacent_ms + tm.multimappers_ms + tm.evalue_ms + tm.in_vitro_ms + tm.kmer_index_ms + tm.homologs_ms + tm.mismappers_ms + tm.partners_ms + tm.rows_ms + tm.consensus_ms + tm.bam_scan_ms
         ev = {n: round(st.event_seconds[i], 2) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.2}
         say("[bench] step: e2e %.2f s, device %.1f ms, ingest %.2f, annotate %.2f, upload %.2f, output %.2f, events >= 0.2 s: %s" %
             (e2e_s, dev_ms, st.seconds[L.STEP_INGEST], st.seconds[L.STEP_ANNOTATE], st.seconds[L.STEP_UPLOAD], st.output_seconds, ev))
         p.close()
-        return {"n": int(st.n_fragments), "e2e_s": e2e_s, "dev_ms": dev_ms, "st": st, "tm": tm, "d2h": d2h, "n_cand": n_cand}
+        return {"n": int(st.n_fragments), "e2e_s": e2e_s, "dev_ms": dev_ms, "st": st, "tm": tm, "d2h": d2h, "n_cand": n_cand, "d2h_parts": d2h_parts, "h2d_parts": h2d_parts}
 
     def timed(sharded, warmup, steps):
         for _ in range(warmup):
@@ -379,7 +390,8 @@ def main():
     line = {"metric": metric, "value": n_frag * jobs / e2e_s, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": e2e_s * 1e3, "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
             "clocks": sampler.summary(),
-            "e2e": {"value": n_frag * jobs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(tm.h2d_bytes), "d2h_bytes_per_step": int(results[-1]["d2h"]),
+            "e2e": {"value": n_frag * jobs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(sum(results[-1]["h2d_parts"].values())), "d2h_bytes_per_step": int(results[-1]["d2h"]),
+                    "h2d_bytes_are": results[-1]["h2d_parts"], "d2h_bytes_are": results[-1]["d2h_parts"],
                     "seconds_per_step": e2e_s, "host_seconds": {n: round(st.seconds[i], 3) for i, n in enumerate(L.STEP_NAMES) if i > 0},
                     "event_seconds": {n: round(st.event_seconds[i], 3) for i, n in enumerate(L.EV_NAMES) if st.event_seconds[i] >= 0.001}, "output_seconds": round(st.output_seconds, 3),
                     "ingest_split": {"inflate": round(st.t_inflate, 3), "parse": round(st.t_parse, 3), "finalize": round(st.t_finalize, 3)}},
