@@ -4,7 +4,7 @@
 // Written from the SAM/BAM specification (SAMv1 section 4.2: BAM record layout; section 4.1:
 // BGZF = concatenated gzip members) -- no htslib source was available or consulted.
 // parity unpinned at the htslib boundary: the reference ships no test vectors for BAM decoding;
-// tests/test_ingest.py and tests/test_bam_corpus.py pin this reader against BAMs from two independent spec-level writers (tools/synth.cpp, tests/bamtools.py).
+// tests/test_ingest.py and tests/test_z_bam_corpus.py pin this reader against BAMs from two independent spec-level writers (tools/synth.cpp, tests/bamtools.py).
 #include <zlib.h>
 #include <stdio.h>
 #include <stdlib.h>

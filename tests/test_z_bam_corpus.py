@@ -1,4 +1,5 @@
-"""BAM files from a second, independent writer (tests/bamtools.py: plain-Python reading of SAMv1 4.1 / 4.2) through the oracle and through the product's
+"""(File names with z: the input corpora run after the established tests.)
+BAM files from a second, independent writer (tests/bamtools.py: plain-Python reading of SAMv1 4.1 / 4.2) through the oracle and through the product's
 ingest. The file means the same to the reference as the synth-written one it was made from (same core fields, CIGARs, sequences, HI and SA), so
  (1) the oracle must write the same two output files for both -- a check of the oracle's htslib shim against a writer that shares no code with it --
  (2) the product's front end must reproduce the oracle's fragment table, coverage and labels field by field from the transcoded file, and
@@ -115,7 +116,7 @@ def test_e2e_cuda_mutated_records(mutated, cuda_lib, tmp_path):
     check_e2e(mutated["shuffled"], cuda_lib, tmp_path, threads=8)
 
 
-if __name__ == "__main__":   # python tests/test_bam_corpus.py SEED N : N random worlds (test_random_worlds.py), damaged and re-framed, through oracle and product
+if __name__ == "__main__":   # python tests/test_z_bam_corpus.py SEED N : N random worlds (test_random_worlds.py), damaged and re-framed, through oracle and product
     import sys, random, tempfile
     from arriba_b200 import _build
     from test_random_worlds import random_world_arguments
