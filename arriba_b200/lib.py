@@ -188,7 +188,7 @@ class Context:
             if name in ("n_genes", "n_exons", "n_contigs"):
                 setattr(s, name, int(a[name]))
             else:
-                arr = np.ascontiguousarray(a[name]); keep.append(arr)
+                arr = np.require(a[name], requirements=["C", "A"]); keep.append(arr)   # contiguous and naturally aligned, as the C ABI expects
                 setattr(s, name, ptr(arr))
         self._check(self.lib.arb_set_annotation(self.h, C.byref(s)))
 
@@ -200,7 +200,7 @@ class Context:
         for name, ctype in SoaChunk._fields_:
             if name in ("n_fragments", "n_cigar", "n_seq_bytes", "n_genes"):
                 continue
-            arr = np.ascontiguousarray(ch[name]); keep.append(arr)
+            arr = np.require(ch[name], requirements=["C", "A"]); keep.append(arr)
             setattr(s, name, ptr(arr))
         s.n_cigar = len(ch["cigar"]); s.n_seq_bytes = len(ch["seq"]); s.n_genes = len(ch["genes"])
         self.n_fragments = s.n_fragments

@@ -15,7 +15,7 @@ def read_dump(path):
         name = buf[p:p + nl].decode(); p += nl
         dt = _DT[buf[p:p + 2]]; p += 2
         cnt = int(np.frombuffer(buf, np.uint64, 1, p)[0]); p += 8
-        out[name] = np.frombuffer(buf, dt, cnt, p); p += cnt * np.dtype(dt).itemsize
+        out[name] = np.frombuffer(buf, dt, cnt, p).copy(); p += cnt * np.dtype(dt).itemsize   # a copy: views into the file sit at odd offsets, the C ABI expects naturally aligned arrays
     return out
 
 def read_dir(d):
