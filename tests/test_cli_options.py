@@ -52,11 +52,22 @@ def test_cli_error_parity(worlds, cli, tmp_path):
     open(d + "/empty.gtf", "w").write("")
     open(d + "/no_exons.gtf", "w").write("\n".join(l for l in gtf if "\texon\t" not in l))
     open(d + "/two_contigs.fa", "w").write(">" + ">".join(fa[1:3]))
-    cases = [(d + "/truncated.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/empty.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/garbage.bam", w.prefix + ".gtf", w.prefix + ".fa"),
+    # files that hold no chimeric fragment, no normal read, or no record at all (tests/bamtools.py re-writes the world's BAM)
+    import bamtools, random
+    text, refs, bodies = bamtools.read_bam(w.prefix + ".bam")
+    recs = [(b, bamtools.split_record(b)) for b in bodies[:30000]]
+    normal = [b for b, r in recs if (r["flag"] & 0x3) == 0x3 and not (r["flag"] & 0x900) and not any(t == b"SA" for t, _, _ in r["aux"])]
+    chimeric = [b for b, r in recs if (r["flag"] & 0x1) and not (r["flag"] & 0x2)]
+    assert len(normal) > 10 and len(chimeric) > 10
+    bamtools.write_bam(d + "/only_normal.bam", text, refs, normal, random.Random(1)); bamtools.write_bam(d + "/only_chimeric.bam", text, refs, chimeric, random.Random(2))
+    bamtools.write_bam(d + "/header_only.bam", text, refs, [], random.Random(3))
+    cases = [(d + "/only_normal.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/only_chimeric.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/header_only.bam", w.prefix + ".gtf", w.prefix + ".fa"),
+             (d + "/truncated.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/empty.bam", w.prefix + ".gtf", w.prefix + ".fa"), (d + "/garbage.bam", w.prefix + ".gtf", w.prefix + ".fa"),
              (w.prefix + ".bam", d + "/empty.gtf", w.prefix + ".fa"), (w.prefix + ".bam", d + "/no_exons.gtf", w.prefix + ".fa"), (w.prefix + ".bam", w.prefix + ".gtf", d + "/two_contigs.fa")]
     for b, g, a in cases:
         seen = []
         for exe in (oracle, cli):
             r = subprocess.run([exe, "-x", b, "-g", g, "-a", a, "-o", d + "/o.tsv", "-O", d + "/d.tsv", "-f", "blacklist"] + (["-@", "2"] if exe == cli else []), capture_output=True, text=True, timeout=300)
             seen.append((r.returncode, [l for l in r.stderr.split("\n") if l.startswith("ERROR")]))
-        assert seen[0][0] == 1 and seen[0] == seen[1], (b, g, a, seen)
+        assert seen[0] == seen[1], (b, g, a, seen)
+        assert seen[0][0] == 1 or b.endswith("only_chimeric.bam"), (b, g, a, seen)   # chimeric mates count as mapped reads: the reference runs through (and so must the product)
