@@ -538,6 +538,11 @@ struct worker {
 		key += ','; key += std::to_string(hit_index);
 		if (r.tid < 0 || (size_t) r.tid >= tid_to_contig->size()) fail("failed to load alignments");
 		r.tid = (*tid_to_contig)[r.tid];
+		// An alignment that starts before or runs past the end of its contig is not a valid record (SAMv1 1.4), and what the reference does with one is undefined:
+		// it indexes its coverage vectors and the contig's sequence beyond their ends (on such a file it aborts in free() or writes garbage columns). Here the same
+		// indices would leave the coverage windows on the host and the genome on the device: the run stops with an error instead.
+		if (ref->has_sequence((u32) r.tid) && (r.pos < 0 || (i64) r.endpos() > (i64) ref->seq_len[r.tid]))
+			fail("alignment of read '" + std::string(r.qname, strnlen(r.qname, r.l_qname)) + "' extends beyond the end of contig '" + ref->original_names[r.tid] + "' (was the file aligned to another assembly?)");
 
 		if (r.flag & BF_SUPPLEMENTARY) {
 			if (clipped_at_correct_end(r)) add_alignment(fragment(key, NULL, key_hash_hint), r, true); else ++malformed;
