@@ -541,7 +541,13 @@ struct worker {
 		// An alignment that starts before or runs past the end of its contig is not a valid record (SAMv1 1.4), and what the reference does with one is undefined:
 		// it indexes its coverage vectors and the contig's sequence beyond their ends (on such a file it aborts in free() or writes garbage columns). Here the same
 		// indices would leave the coverage windows on the host and the genome on the device: the run stops with an error instead.
-		if (ref->has_sequence((u32) r.tid) && (r.pos < 0 || (i64) r.endpos() > (i64) ref->seq_len[r.tid]))
+		// Likewise a mapped record without CIGAR operations, or whose CIGAR consumes more bases than the record holds (a sequence of '*' included): the reference
+		// dies on those (segmentation fault, or std::out_of_range from substr); everything downstream indexes the sequence by the CIGAR.
+		i64 ref_span = 0, query_span = 0;
+		for (u32 k = 0; k < r.n_cigar; ++k) { const u32 c = r.cig(k), o = c & 15; if (o == C_M || o == C_EQ || o == C_X) { ref_span += c >> 4; query_span += c >> 4; } else if (o == C_D || o == C_N) ref_span += c >> 4; else if (o == C_I || o == C_S) query_span += c >> 4; }
+		if (r.n_cigar == 0 || query_span > (i64) r.l_seq)
+			fail("CIGAR string of read '" + std::string(r.qname, strnlen(r.qname, r.l_qname)) + "' does not fit its sequence (" + std::to_string(query_span) + " bases in " + std::to_string(r.n_cigar) + " operations, sequence of " + std::to_string(r.l_seq) + ")");
+		if (ref->has_sequence((u32) r.tid) && (r.pos < 0 || (i64) r.pos + (ref_span ? ref_span : 1) > (i64) ref->seq_len[r.tid]))
 			fail("alignment of read '" + std::string(r.qname, strnlen(r.qname, r.l_qname)) + "' extends beyond the end of contig '" + ref->original_names[r.tid] + "' (was the file aligned to another assembly?)");
 
 		if (r.flag & BF_SUPPLEMENTARY) {

@@ -118,24 +118,33 @@ def test_e2e_cuda_mutated_records(mutated, cuda_lib, tmp_path):
 
 
 def test_alignment_beyond_the_contig_end_stops_the_run(worlds, hostsim_lib, tmp_path):
-    """Not a valid record, and undefined in the reference (it indexes its coverage vectors and the contig string past their ends; on such files it aborts in free()
+    """Alignments off the ends of their contig; mapped records without CIGAR, or whose CIGAR consumes more bases than the record holds (the reference dies on those:
+    segmentation fault or std::out_of_range). Not valid records, and undefined in the reference (it indexes its coverage vectors and the contig string past their ends; on such files it aborts in free()
     or prints garbage): the product stops with an error instead of touching memory past the coverage windows (host) or the genome (device)."""
     import random, subprocess
     from arriba_b200 import _build
     base = worlds.get("small")
     text, refs, bodies = bamtools.read_bam(base.prefix + ".bam")
-    for case, shift in (("past", 5000), ("straddling", -30)):
+    def past(r): r["pos"] = refs[r["tid"]][1] + 5000
+    def straddling(r): r["pos"] = refs[r["tid"]][1] - 30
+    def before(r): r["pos"] = -5
+    def cigar_longer(r): bamtools._set_cigar(r, [((o >> 4) + 50) << 4 | (o & 15) if (o & 15) == 0 else o for o in bamtools._cigar_ops(r)])
+    def no_cigar(r): bamtools._set_cigar(r, [])
+    def no_sequence(r): r["l_seq"] = 0; r["seq"] = b""; r["qual"] = b""
+    for damage, message in ((past, "extends beyond the end of contig"), (straddling, "extends beyond the end of contig"), (before, "extends beyond the end of contig"),
+                            (cigar_longer, "does not fit its sequence"), (no_cigar, "does not fit its sequence"), (no_sequence, "does not fit its sequence")):
+        case = damage.__name__
         out = []; done = False
         for b in bodies:
             r = bamtools.split_record(b)
             if not done and r["tid"] >= 0 and not r["flag"] & 0x904 and (r["flag"] & 0x3) == 0x3:
-                r["pos"] = refs[r["tid"]][1] + shift; b = bamtools.join_record(r); done = True
+                damage(r); b = bamtools.join_record(r); done = True
             out.append(b)
         prefix = os.path.join(str(tmp_path), case)
         bamtools.write_bam(prefix + ".bam", text, refs, out, random.Random(1))
         r = subprocess.run([_build.build_cli_hostsim(), "-x", prefix + ".bam", "-g", base.prefix + ".gtf", "-a", base.prefix + ".fa", "-o", prefix + ".tsv", "-O", prefix + ".d.tsv", "-f", "blacklist", "-@", "3"], capture_output=True, text=True, timeout=300)
         errors = [l for l in r.stderr.splitlines() if l.startswith("ERROR")]
-        assert r.returncode == 1 and len(errors) == 1 and "extends beyond the end of contig" in errors[0], (case, r.returncode, errors)
+        assert r.returncode == 1 and len(errors) == 1 and message in errors[0], (case, r.returncode, errors)
 
 
 if __name__ == "__main__":   # python tests/test_z_bam_corpus.py SEED N : N random worlds (test_random_worlds.py), damaged and re-framed, through oracle and product
