@@ -2,6 +2,8 @@
 the reference run with the same arguments (options.cpp:270-485; defaults options.cpp:71-107)."""
 import os
 import subprocess
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pytest
 import worldutil
 from arriba_b200 import _build
@@ -71,3 +73,57 @@ def test_cli_error_parity(worlds, cli, tmp_path):
             seen.append((r.returncode, [l for l in r.stderr.split("\n") if l.startswith("ERROR")]))
         assert seen[0] == seen[1], (b, g, a, seen)
         assert seen[0][0] == 1 or b.endswith("only_chimeric.bam"), (b, g, a, seen)   # chimeric mates count as mapped reads: the reference runs through (and so must the product)
+
+
+# ---- random option combinations on random worlds (python tests/test_cli_options.py SEED N runs N more) ----
+FILTERS="duplicates inconsistently_clipped homopolymer read_through same_gene small_insert_size long_gap hairpin multimappers mismatches mismappers relative_support intronic non_coding_neighbors intragenic_exonic internal_tandem_duplication min_support known_fusions spliced end_to_end in_vitro merge_adjacent select_best marginal_read_through short_anchor no_coverage many_spliced no_genomic_support uninteresting_contigs viral_contigs top_expressed_viral_contigs low_coverage_viral_contigs genomic_support isoforms low_entropy homologs".split()
+
+
+def random_options(rng):
+    pool=[("-E",lambda: "%g"%rng.choice([0.001,0.05,0.3,1,10,1000])),("-S",lambda:str(rng.choice([0,1,2,3,5,20]))),("-m",lambda:"%g"%rng.choice([0,0.2,0.8,1])),("-L",lambda:"%g"%rng.choice([0,0.1,0.3,0.9,1])),
+          ("-H",lambda:str(rng.choice([2,3,6,10,40]))),("-R",lambda:str(rng.choice([0,100,10000,1000000]))),("-A",lambda:str(rng.choice([0,10,23,40,90]))),("-M",lambda:str(rng.choice([0,1,4,10]))),
+          ("-K",lambda:"%g"%rng.choice([0,0.3,0.6,1])),("-V",lambda:"%g"%rng.choice([0,0.001,0.01,0.5,1])),("-F",lambda:str(rng.choice([1,100,200,1000]))),("-U",lambda:str(rng.choice([1,2,10,300,32767]))),
+          ("-Q",lambda:"%g"%rng.choice([0,0.5,0.998,1])),("-e",lambda:"%g"%rng.choice([0,0.33,1])),("-l",lambda:str(rng.choice([1,50,100,5000]))),("-z",lambda:"%g"%rng.choice([0,0.07,0.5,1])),("-Z",lambda:str(rng.choice([1,10,100]))),
+          ("-s",lambda:rng.choice(["auto","yes","no","reverse"])),("-u",None),("-X",None),("-i",lambda:rng.choice(["1,2,3,4,5,X","1 2 3 4 5 6 7 8 9 10 11 12","*"])),("-v",lambda:rng.choice(["21,22","Y","AC_* NC_*"])),
+          ("-T",lambda:str(rng.choice([1,2,5]))),("-C",lambda:"%g"%rng.choice([0,0.05,0.5,1]))]
+    rng.shuffle(pool); out=[]
+    for name,val in pool[:rng.randint(1,6)]:
+        out.append(name)
+        if val: out.append(val())
+    fl=["blacklist"]+rng.sample(FILTERS, rng.choice([0,0,1,3,8]))
+    return out+["-f",",".join(fl)]
+
+def run_random_combination(rng, cli, d, k):
+    """one random world, one random option set, reference and product side by side; True when both stop with the same error or both write the same two files"""
+    from test_random_worlds import random_world_arguments
+    oracle = _build.build_oracle()
+    kw = random_world_arguments(rng); pre = os.path.join(d, "w%d" % k)
+    worldutil.run_synth(pre, **{kk: v for kk, v in kw.items() if kk != "extra"}, extra=kw["extra"])
+    opts = random_options(rng); res = []
+    for exe, tag in ((oracle, "r"), (cli, "p")):
+        r = subprocess.run([exe, "-x", pre + ".bam", "-g", pre + ".gtf", "-a", pre + ".fa", "-o", pre + "." + tag + ".tsv", "-O", pre + "." + tag + ".d.tsv"] + opts + (["-@", str(rng.choice([1, 3, 6]))] if exe == cli else []),
+                           capture_output=True, text=True, env=dict(os.environ, ARB_DET_ALLOC="1"), timeout=900)
+        res.append((r.returncode, [l for l in r.stderr.splitlines() if l.startswith("ERROR")]))
+    if res[0][0] != 0 or res[1][0] != 0:
+        return res[0] == res[1], opts, kw
+    same = all(open(pre + ".r" + e, "rb").read() == open(pre + ".p" + e, "rb").read() for e in (".tsv", ".d.tsv"))
+    return same, opts, kw
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cli_random_option_combination(cli, tmp_path, seed):
+    import random
+    ok, opts, kw = run_random_combination(random.Random(seed), cli, str(tmp_path), seed)
+    assert ok, (opts, kw)
+
+
+if __name__ == "__main__":
+    import random, sys, tempfile
+    rng = random.Random(int(sys.argv[1]) if len(sys.argv) > 1 else 1); bad = 0
+    with tempfile.TemporaryDirectory() as d:
+        for k in range(int(sys.argv[2]) if len(sys.argv) > 2 else 10):
+            ok, opts, kw = run_random_combination(rng, _build.build_cli_hostsim(), d, k)
+            print(k, "identical" if ok else "DIFFERENT", opts, "" if ok else kw, flush=True); bad += not ok
+            for f in os.listdir(d):
+                os.remove(os.path.join(d, f))
+    sys.exit(1 if bad else 0)
