@@ -32,11 +32,9 @@ void arb_default_run_options(arb_run_options* o) {
 
 // Dozens of host threads allocate and free at the same time (record parsing, annotation, row formatting). glibc gives every thread its own arena, but arenas
 // hand memory back to the kernel and map new chunks all the time, and those calls serialise on the process's address-space lock: keep what was obtained.
-static void tune_allocator() {
-	static bool done = false;
-	if (done) return;
-	done = true;
-	mallopt(M_TRIM_THRESHOLD, 1 << 30); mallopt(M_TOP_PAD, 64 << 20); mallopt(M_MMAP_THRESHOLD, 32 << 20);
+static void tune_allocator() { // once per process, also when two threads create their first pipelines at the same moment (a local static's initialiser runs once)
+	static const int done = (mallopt(M_TRIM_THRESHOLD, 1 << 30), mallopt(M_TOP_PAD, 64 << 20), mallopt(M_MMAP_THRESHOLD, 32 << 20), 1);
+	(void) done;
 }
 
 void arb_release_host_memory(void) { arb::host::host_block_trim(); arb::host::release_worker_cache(); }
