@@ -115,6 +115,10 @@ public:
 #else
 		p_ = (T*) malloc(bytes);
 		if (!p_) throw arb_error("out of memory");
+		// the device pool hands out recycled blocks with whatever the last user left in them, malloc hands out fresh (zero) pages for anything large: with
+		// ARB_HOSTSIM_POISON set the stand-in fills new buffers with a pattern, so that a functor that counts on zeroed scratch shows in the CPU tests
+		static const bool poison = getenv("ARB_HOSTSIM_POISON") != NULL;
+		if (poison) memset((void*) p_, 0xA5, bytes);
 #endif
 	}
 	void ensure(size_t n) { if (n > n_) alloc(n + n / 4); }
