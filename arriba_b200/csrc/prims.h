@@ -197,9 +197,22 @@ template <u32 WORDS, class F> void for_each_scratch(const exec_ctx& ex, u32 n, c
 	++stats().kernels;
 }
 #else
-template <class F> void for_each(const exec_ctx&, u32 n, const F& f) { for (u32 i = 0; i < n; ++i) f(i); ++stats().kernels; }
+// The stand-in visits the items of a launch one after the other. A GPU visits them in no particular order, so a functor must not depend on it: with
+// ARB_HOSTSIM_ORDER=1 the stand-in walks backwards, with 2 in a scattered order (a stride coprime to n), and the CPU tests must give the same results.
+inline int hostsim_order() { static const int mode = getenv("ARB_HOSTSIM_ORDER") ? atoi(getenv("ARB_HOSTSIM_ORDER")) : 0; return mode; }
+template <class G> inline void hostsim_visit(u32 n, const G& g) {
+	const int mode = hostsim_order();
+	if (mode == 0 || n < 2) { for (u32 i = 0; i < n; ++i) g(i); return; }
+	if (mode == 1) { for (u32 i = n; i-- > 0;) g(i); return; }
+	u64 stride = (u64) n * 5 / 13 + 1; // some stride near 0.38 n, made coprime to n
+	auto gcd = [](u64 a, u64 b) { while (b) { const u64 t = a % b; a = b; b = t; } return a; };
+	while (gcd(stride, n) != 1) ++stride;
+	u64 at = n / 3;
+	for (u32 k = 0; k < n; ++k) { g((u32) at); at = (at + stride) % n; }
+}
+template <class F> void for_each(const exec_ctx&, u32 n, const F& f) { hostsim_visit(n, [&](u32 i) { f(i); }); ++stats().kernels; }
 template <int MIN_BLOCKS, class F> void for_each_occ(const exec_ctx& ex, u32 n, const F& f) { for_each(ex, n, f); }
-template <u32 WORDS, class F> void for_each_scratch(const exec_ctx&, u32 n, const F& f) { u32 scratch[WORDS]; for (u32 i = 0; i < n; ++i) f(i, scratch, 1); ++stats().kernels; }
+template <u32 WORDS, class F> void for_each_scratch(const exec_ctx&, u32 n, const F& f) { u32 scratch[WORDS]; hostsim_visit(n, [&](u32 i) { f(i, scratch, 1); }); ++stats().kernels; }
 #endif
 
 // ------------------------------------------------------------------------------------------- atomics usable from HD functors
