@@ -136,7 +136,9 @@ def reference_run(prefix, threads):
 
 # full-size run of the unmodified reference on the default workload, measured once on the development container (profiles/cfg2_full_size_parity.txt):
 # the sample above flatters the reference (its std::map / unordered_map walks get slower per fragment as the containers grow)
-REFERENCE_FULL_SIZE = {"cfg2_10M_2x101_50k": {"fragments": 11810114, "seconds": 1535.0, "value": 11810114 / 1535.0, "cores": 1, "where": "development container, profiles/cfg2_full_size_parity.txt (25 min 35 s)"}}
+REFERENCE_FULL_SIZE = {"cfg2_10M_2x101_50k": {"fragments": 11810114, "seconds": 1535.0, "value": 11810114 / 1535.0, "cores": 1, "where": "development container, profiles/cfg2_full_size_parity.txt (25 min 35 s)"},
+                       "cfg5_10M_mismapper": {"fragments": 11732540, "seconds": 968.0, "value": 11732540 / 968.0, "cores": 1, "where": "development container, tests/golden/full_size_md5.json (16 min 8 s)"},
+                       "cfg3_15M_2x151_75k": {"fragments": 17587876, "seconds": None, "value": None, "cores": 1, "where": "development container: stopped after 3 h 1 min of CPU time inside filter_mismappers, not finished (profiles/r02z/full_size_host_parity.txt)"}}
 
 
 class QuietStderr:
